@@ -1,0 +1,164 @@
+/*
+ * dpf.h — C ABI of libdpf_b200: the B200-native (sm_100a) replacement for the data-parallel hot path of
+ * Dynamic Partition Forest (reference: MacLLL/SimilaritySearchByRDF; all file:line below are relative to
+ * the reference tree).
+ *
+ * The reference has no FFI of its own: its plug points are Scala/Java types.  Each entry
+ * point below names the reference interface it replaces; INTEGRATION.md shows the JNI/Scala stub that binds it.
+ *
+ * Conventions
+ *   - every function returns an int status (DPF_OK == 0); nothing aborts the process, no C++ exception
+ *     crosses the boundary; dpf_last_error(h) gives the message of the last failure on that handle;
+ *   - the caller owns every buffer it passes; the library owns all device memory behind a handle;
+ *   - plain functions take HOST pointers (pinned memory is faster but not required) and include the
+ *     host<->device copies; *_dev functions take DEVICE pointers on the handle's GPU and are asynchronous on
+ *     the handle's stream until dpf_sync;
+ *   - a handle is thread-compatible (calls are serialised internally); separate handles are independent;
+ *   - there is no CPU fallback: with no usable CUDA device dpf_create fails with DPF_ERR_CUDA.
+ *   - arrays are C-order, native endianness; ids are int32 running counters assigned in fit order
+ *     (DensevectorRDFInit.scala:174-184: the id in the input file is ignored).
+ */
+#ifndef DPF_H
+#define DPF_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPF_ABI_VERSION 1
+
+typedef struct dpf_index* dpf_handle;
+
+enum {
+    DPF_OK = 0,
+    DPF_ERR_INVALID = 1,   /* bad argument / configuration                                   */
+    DPF_ERR_STATE = 2,     /* call order (family not set, not fitted, dense/sparse mixed)     */
+    DPF_ERR_CUDA = 3,      /* CUDA runtime failure or no device                               */
+    DPF_ERR_NOMEM = 4,     /* device or host allocation failed                                */
+    DPF_ERR_CAPACITY = 5   /* caller's output buffer too small (needed size is reported)      */
+};
+
+enum { DPF_FAMILY_ANGLE = 0, DPF_FAMILY_PSTABLE = 1 };                 /* mclab.lsh.name (LSH.scala:29-53) */
+enum { DPF_KEY_ORIGINAL = 0, DPF_KEY_SAMPLING = 1, DPF_KEY_CONTINUE_BITS = 2, DPF_KEY_ANGLE_NEW = 3 };
+                                                                       /* mclab.lsh.typeOfIndex (LSH.scala:152-161) */
+enum { DPF_METRIC_DOT = 0, DPF_METRIC_ANGULAR = 1, DPF_METRIC_L2 = 2 };
+enum { DPF_PROBE_NONE = 0, DPF_PROBE_DENSE = 1 };
+    /* DPF_PROBE_DENSE: getSimilarWithStepWiseFaster(key, DenseVector, steps) multi-probe (RandomDrawTreeMap.java:742-797)
+       DPF_PROBE_NONE : sparse overload / id-based getSimilarWithStepWise (RandomDrawTreeMap.java:686-732, 630-675) */
+
+typedef struct {
+    int32_t abi_version;      /* DPF_ABI_VERSION                                                              */
+    int32_t device;           /* CUDA device ordinal                                                           */
+    int32_t d;                /* mclab.lsh.vectorDim (dense) or feature-space size D (sparse)                  */
+    int32_t L;                /* tableNum * permutationNum (DensevectorRDFInit.scala:107)                      */
+    int32_t k;                /* mclab.lshTable.chainLength (1..32)                                            */
+    int32_t pb;               /* mclab.lsh.partitionBits (0..8): 2^pb sub-indexes per table                    */
+    int32_t bucket_bits;      /* mclab.lshTable.bucketBits   (RandomDrawTreeMap.java:435-438)                   */
+    int32_t dir_node_size;    /* mclab.lshTable.dirNodeSize  (RandomDrawTreeMap.java:446-465), power of two     */
+    int32_t bucket_overflow;  /* mclab.lshTable.bufferOverflow = BUCKET_OVERFLOW (RandomDrawTreeMap.java:1719) */
+    int32_t family_kind;      /* DPF_FAMILY_*                                                                  */
+    int32_t key_transform;    /* DPF_KEY_*                                                                     */
+    int32_t self_exclude_small_ids; /* reproduce `ln.key != key` on boxed Integers (RandomDrawTreeMap.java:982) */
+    int32_t rank;             /* content-based partition scheme on G GPUs: this handle owns the sub-indexes    */
+    int32_t world;            /*   { p : p % world == rank } of every table (Partitioner.scala:27-64); 0,1 = all */
+} dpf_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* replaces DensevectorRDFInit.initializeRDFHashMap (DensevectorRDFInit.scala:50-118): table construction */
+int dpf_create(const dpf_config* cfg, dpf_handle* out);
+int dpf_destroy(dpf_handle h);                       /* clearAndClose (DensevectorRDFInit.scala:453-458) */
+const char* dpf_last_error(dpf_handle h);
+const char* dpf_strerror(int code);
+int dpf_sync(dpf_handle h);
+
+/* ---- hash functions: inputs, generated/loaded on the host side (AngleHashFamily.scala:121-177) ---------- */
+/* A: P x d row-major distinct functions; chain_idx: L x k -> row of A (tableIndexGenerators, LSH.scala:27);
+ * b[P], w[P]: pStable offsets/widths (PStableHashFamily.scala:185-191), NULL for the angle family. */
+int dpf_set_family(dpf_handle h, const double* A, int32_t P, const int32_t* chain_idx, const double* b,
+                   const int32_t* w);
+/* Ap: L x pb x 32 — each table's private LocalitySensitivePartitioner functions (DensevectorRDFInit.scala:63-77) */
+int dpf_set_partitioners(dpf_handle h, const double* Ap);
+
+/* ---- LSH.calculateIndex + LocalitySensitivePartitioner.getPartition, batched (parity hook) --------------
+ * replaces LSH.calculateIndex (LSH.scala:93-166) / LocalitySensitiveHasher.hash (Hasher.scala:44-54) /
+ * getPartition (Partitioner.scala:40-64).  keys_out, pids_out: L x n int32, table-major; pids_out may be NULL. */
+int dpf_hash_dense(dpf_handle h, const double* X, int64_t n, int32_t* keys_out, int32_t* pids_out);
+int dpf_hash_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values, int64_t n,
+                 int32_t* keys_out, int32_t* pids_out);
+
+/* ---- fit: DensevectorRDFInit.newMultiThreadFit / newFastFit (DensevectorRDFInit.scala:127-206) and the
+ * sparse twin (SparsevectorRDFInit.scala:124-203), after the text has been parsed.  Appends n vectors with ids
+ * size()..size()+n-1 and (re)builds the forest so that it equals sequential ascending-id RandomDrawTreeMap.put
+ * (RandomDrawTreeMap.java:1558-1584, 1662-1790). */
+int dpf_fit_dense(dpf_handle h, const double* X, int64_t n);
+int dpf_fit_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values, int64_t n);
+/* X_dev stays owned by the caller and must outlive the handle (no copy is made: 100M x 96 FP64 is 76.8 GB) */
+int dpf_fit_dense_dev(dpf_handle h, const double* X_dev, int64_t n);
+int64_t dpf_size(dpf_handle h);
+
+/* ---- query: candidate sets = DensevectorRDFInit.NewMultiThreadQueryBatch (DensevectorRDFInit.scala:335-360),
+ * SparsevectorRDFInit.NewMultiThreadQueryBatch (SparsevectorRDFInit.scala:324-348) --------------------------
+ * qids may be NULL (no self-exclusion).  Output is CSR: offsets_out[nq+1], ids_out sorted unique per query.
+ * If total > cap the call returns DPF_ERR_CAPACITY with *total_out set; offsets_out is still valid. */
+int dpf_query_candidates_dense(dpf_handle h, const double* Q, int64_t nq, const int32_t* qids, int32_t steps,
+                               int32_t probe_mode, int64_t* offsets_out, int32_t* ids_out, int64_t cap,
+                               int64_t* total_out);
+int dpf_query_candidates_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values,
+                             int64_t nq, const int32_t* qids, int32_t steps, int64_t* offsets_out,
+                             int32_t* ids_out, int64_t cap, int64_t* total_out);
+int dpf_query_candidates_by_id(dpf_handle h, const int32_t* qids, int64_t nq, int32_t steps,
+                               int64_t* offsets_out, int32_t* ids_out, int64_t cap, int64_t* total_out);
+
+/* ---- query + re-rank + top-k = DensevectorRDFInit.topKAndPrecisionScore's gather/dgemv/argsort
+ * (DensevectorRDFInit.scala:472-507).  metric DOT is the reference's (descending dot product); ANGULAR
+ * (descending cosine) and L2 (ascending squared distance) are the north-star additions.  Ties: ascending id.
+ * ids_out: nq x topk (-1 padded), score_out: nq x topk (NaN padded). */
+int dpf_query_topk_dense(dpf_handle h, const double* Q, int64_t nq, const int32_t* qids, int32_t steps,
+                         int32_t probe_mode, int32_t topk, int32_t metric, int32_t* ids_out, double* score_out);
+int dpf_query_topk_dense_dev(dpf_handle h, const double* Q_dev, int64_t nq, const int32_t* qids_dev,
+                             int32_t steps, int32_t probe_mode, int32_t topk, int32_t metric,
+                             int32_t* ids_out_dev, double* score_out_dev);
+/* re-rank caller-supplied candidate sets (parity hook: "ids exact given the same candidate set") */
+int dpf_rerank_dense(dpf_handle h, const double* Q, int64_t nq, const int64_t* offsets, const int32_t* cand,
+                     int32_t topk, int32_t metric, int32_t* ids_out, double* score_out);
+
+/* ---- multi-GPU: merge per-GPU top-k lists after the NCCL all-gather -----------------------
+ * gathered_*_dev: G x nq x topk as produced by all-gathering dpf_query_topk_dense_dev outputs; duplicates of
+ * one id (same vector reached through tables owned by different GPUs) are collapsed. */
+int dpf_merge_topk_dev(dpf_handle h, const int32_t* gathered_ids_dev, const double* gathered_scores_dev,
+                       int32_t G, int64_t nq, int32_t topk, int32_t metric, int32_t* ids_out_dev,
+                       double* score_out_dev);
+
+/* ---- introspection --------------------------------------------------------------------------------------- */
+/* canonical dump of one table's forest (parity hook for bucket membership): leaf buckets in (root, path) order,
+ * ids ascending inside a bucket.  desc: nbuckets x 3 = (root = pid*SEG+seg, level, path of slots MAXL..level).
+ * Pass NULLs to get counts. */
+int dpf_dump_buckets(dpf_handle h, int32_t table, int64_t* nbuckets_out, int64_t* nids_out, int32_t* desc_out,
+                     int64_t* off_out, int32_t* ids_out);
+
+enum {
+    DPF_STAT_SIZE = 0,             /* vectors indexed                                                        */
+    DPF_STAT_NEAR_ZERO_FIXUPS = 1, /* projections within the DMMA error bound of 0, recomputed in reference
+                                      order (cumulative over hash calls)                                    */
+    DPF_STAT_SINGLETON_SPLITS = 2, /* quirk Q1 events (RandomDrawTreeMap.java:1733-1734), last build          */
+    DPF_STAT_SPLITS = 3,           /* directory nodes created by bucket overflow, last build                 */
+    DPF_STAT_DIR_NODES = 4,        /* all directory nodes incl. roots                                        */
+    DPF_STAT_NLZ_GT28 = 5,         /* (query,table) pairs with nlz(h) > 28 (quirk Q4), last query            */
+    DPF_STAT_LAST_CANDIDATES = 6,  /* unique candidates of the last query batch                              */
+    DPF_STAT_LAST_CAND_WITH_DUPS = 7, /* bucket entries visited by the last query batch                      */
+    DPF_STAT_COUNT = 16
+};
+int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occupancy_out /* 2^pb or NULL */);
+
+/* per-stage device times of the last fit / query call, measured with CUDA events on the handle's stream */
+enum {
+    DPF_T_HASH = 0, DPF_T_FIXUP = 1, DPF_T_PACK = 2, DPF_T_SORT = 3, DPF_T_SPLIT = 4,
+    DPF_T_PROBE_COUNT = 5, DPF_T_EXPAND = 6, DPF_T_RERANK = 7, DPF_T_CAND_SORT = 8, DPF_T_COUNT = 16
+};
+int dpf_set_profiling(dpf_handle h, int32_t enable);
+int dpf_stage_times_ms(dpf_handle h, float* ms_out /* DPF_T_COUNT */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

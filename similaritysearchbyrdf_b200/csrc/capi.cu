@@ -1,0 +1,578 @@
+// capi.cu — the extern "C" boundary declared in include/dpf.h.  Every entry point takes the handle's lock,
+// selects the handle's device, runs the device pipeline on the handle's stream and converts failures into
+// DPF_ERR_* codes (no exception leaves the library, nothing aborts the process).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace dpf;
+
+namespace {
+
+int ilog2_exact(int v) {
+    int r = 0;
+    while ((1 << r) < v) r++;
+    return ((1 << r) == v) ? r : -1;
+}
+
+template <class F>
+int guarded(dpf_handle h, F&& f) {
+    if (!h) return DPF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    try {
+        DPF_CUDA(cudaSetDevice(h->cfg.device));
+        f();
+        return DPF_OK;
+    } catch (const Error& e) {
+        h->last_error = e.msg;
+        cudaGetLastError();   // clear a sticky-less error state
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        h->last_error = "host allocation failed";
+        return DPF_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        h->last_error = e.what();
+        return DPF_ERR_INVALID;
+    }
+}
+
+void begin_profile(dpf_index* h) {
+    if (!h->profiling) return;
+    for (int i = 0; i < DPF_T_COUNT; ++i) { h->ev_used[i] = false; h->stage_ms[i] = 0.f; }
+}
+void end_profile(dpf_index* h) {
+    if (!h->profiling) return;
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < DPF_T_COUNT; ++i)
+        if (h->ev_used[i]) cudaEventElapsedTime(&h->stage_ms[i], h->ev[2 * i], h->ev[2 * i + 1]);
+}
+
+template <class T>
+void h2d(dpf_index* h, T* dst, const T* src, size_t n) {
+    if (n) DPF_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+}
+template <class T>
+void d2h(dpf_index* h, T* dst, const T* src, size_t n) {
+    if (n) DPF_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+}
+
+void require_ready(dpf_index* h, bool need_fit) {
+    DPF_REQUIRE(h->family_set, DPF_ERR_STATE, "dpf_set_family has not been called");
+    DPF_REQUIRE(h->part_set || h->cfg.pb == 0, DPF_ERR_STATE, "dpf_set_partitioners has not been called");
+    if (need_fit) DPF_REQUIRE(h->fitted && h->n > 0, DPF_ERR_STATE, "need to fit the data first");
+}
+
+// make room for n more keys (table-major, leading dimension key_ld), preserving what is there
+void grow_keys(dpf_index* h, int64_t add) {
+    const int L = h->cfg.L;
+    const int64_t need = h->n + add;
+    if (need <= h->key_ld) return;
+    const int64_t nld = std::max<int64_t>(need, h->key_ld + h->key_ld / 2);
+    DevBuf<int32_t> nk;
+    DevBuf<uint8_t> np;
+    nk.reserve((size_t)L * nld);
+    np.reserve((size_t)L * nld);
+    if (h->n > 0) {
+        DPF_CUDA(cudaMemcpy2DAsync(nk.p, nld * sizeof(int32_t), h->keys.p, h->key_ld * sizeof(int32_t),
+                                   h->n * sizeof(int32_t), L, cudaMemcpyDeviceToDevice, h->stream));
+        DPF_CUDA(cudaMemcpy2DAsync(np.p, nld, h->pids.p, h->key_ld, h->n, L, cudaMemcpyDeviceToDevice, h->stream));
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    std::swap(h->keys.p, nk.p); std::swap(h->keys.cap, nk.cap);
+    std::swap(h->pids.p, np.p); std::swap(h->pids.cap, np.cap);
+    h->key_ld = nld;
+}
+
+bool use_exact_hash() {
+    const char* e = getenv("DPF_HASH_EXACT");
+    return e && e[0] == '1';
+}
+
+void hash_dense_any(dpf_index* h, const double* Xd, int64_t n, int32_t* keys, uint8_t* pids, int64_t ld) {
+    if (use_exact_hash() && h->cfg.family_kind == DPF_FAMILY_ANGLE) hash_dense_device_exact(h, Xd, n, keys, pids, ld);
+    else hash_dense_device(h, Xd, n, keys, pids, ld);
+}
+
+// widen uint8 pids to the ABI's int32 on the host
+void pids_to_host(dpf_index* h, const uint8_t* dev, int64_t count, int32_t* out) {
+    std::vector<uint8_t> tmp((size_t)count);
+    d2h(h, tmp.data(), dev, (size_t)count);
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < count; ++i) out[i] = tmp[(size_t)i];
+}
+
+// shared tail of the candidate queries: CSR out to the host
+void emit_candidates(dpf_index* h, int64_t nq, int64_t* offsets_out, int32_t* ids_out, int64_t cap, int64_t* total_out) {
+    DevBuf<int64_t> off;
+    off.reserve(nq + 1);
+    const int64_t total = finalize_candidates_sorted(h, nq, off.p);
+    d2h(h, offsets_out, off.p, (size_t)nq + 1);
+    if (total_out) *total_out = total;
+    if (total <= cap && ids_out) d2h(h, ids_out, h->cand.p, (size_t)total);
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
+    DPF_REQUIRE(total <= cap, DPF_ERR_CAPACITY, "candidate buffer too small");
+}
+
+void upload_queries_dense(dpf_index* h, const double* Q, int64_t nq, const int32_t* qids) {
+    const int d = h->cfg.d, L = h->cfg.L;
+    h->qbuf.reserve((size_t)nq * d);
+    h2d(h, h->qbuf.p, Q, (size_t)nq * d);
+    h->qidbuf.reserve(nq + 1);
+    if (qids) h2d(h, h->qidbuf.p, qids, (size_t)nq);
+    h->qkeys.reserve((size_t)L * nq);
+    h->qpids.reserve((size_t)L * nq);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dpf_strerror(int code) {
+    switch (code) {
+        case DPF_OK: return "ok";
+        case DPF_ERR_INVALID: return "invalid argument";
+        case DPF_ERR_STATE: return "invalid state / call order";
+        case DPF_ERR_CUDA: return "CUDA failure";
+        case DPF_ERR_NOMEM: return "out of memory";
+        case DPF_ERR_CAPACITY: return "output buffer too small";
+        default: return "unknown";
+    }
+}
+
+int dpf_create(const dpf_config* cfg, dpf_handle* out) {
+    if (!cfg || !out) return DPF_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->abi_version != DPF_ABI_VERSION) return DPF_ERR_INVALID;
+    if (cfg->d <= 0 || cfg->L <= 0 || cfg->L > kMaxTables || cfg->k <= 0 || cfg->k > kMaxChain || cfg->pb < 0 ||
+        cfg->pb > kMaxPb || cfg->bucket_bits < 1 || cfg->bucket_bits > 32 || cfg->bucket_overflow < 1)
+        return DPF_ERR_INVALID;
+    const int nb = ilog2_exact(cfg->dir_node_size);
+    if (nb < 1 || nb > 8) return DPF_ERR_INVALID;
+    const int seg_bits = 32 - cfg->bucket_bits;
+    const int maxl = (cfg->k - seg_bits) / nb - 1;            // RandomDrawTreeMap.java:456
+    if (maxl < 0 || seg_bits > 12) return DPF_ERR_INVALID;
+    if (cfg->world > 1 && (cfg->rank < 0 || cfg->rank >= cfg->world)) return DPF_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return DPF_ERR_CUDA;   // no CPU fallback
+    }
+    dpf_index* h = nullptr;
+    try {
+        h = new dpf_index();
+        h->cfg = *cfg;
+        h->tp = TreeParams{1 << seg_bits, seg_bits, nb, 1 << nb, maxl, cfg->bucket_bits, cfg->pb,
+                           (1 << cfg->pb) * (1 << seg_bits), cfg->bucket_overflow};
+        DPF_CUDA(cudaSetDevice(cfg->device));
+        DPF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        DPF_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+        for (int i = 0; i < 2 * DPF_T_COUNT; ++i) DPF_CUDA(cudaEventCreate(&h->ev[i]));
+        h->counters.reserve(64);
+        h->occupancy.assign(1 << cfg->pb, 0.0);
+    } catch (const Error& e) {
+        delete h;
+        return e.code;
+    } catch (...) {
+        delete h;
+        return DPF_ERR_NOMEM;
+    }
+    *out = h;
+    return DPF_OK;
+}
+
+int dpf_destroy(dpf_handle h) {
+    if (!h) return DPF_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 2 * DPF_T_COUNT; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return DPF_OK;
+}
+
+const char* dpf_last_error(dpf_handle h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int dpf_sync(dpf_handle h) {
+    return guarded(h, [&] { DPF_CUDA(cudaStreamSynchronize(h->stream)); });
+}
+
+int dpf_set_family(dpf_handle h, const double* A, int32_t P, const int32_t* chain_idx, const double* b, const int32_t* w) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(A && chain_idx && P > 0, DPF_ERR_INVALID, "null family");
+        DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "hash functions cannot change once vectors are indexed");
+        const int d = h->cfg.d, L = h->cfg.L, k = h->cfg.k;
+        for (int64_t i = 0; i < (int64_t)L * k; ++i)
+            DPF_REQUIRE(chain_idx[i] >= 0 && chain_idx[i] < P, DPF_ERR_INVALID, "chain_idx out of range");
+        if (h->cfg.family_kind == DPF_FAMILY_PSTABLE) {
+            DPF_REQUIRE(b && w, DPF_ERR_INVALID, "pStable family needs b and w");
+            for (int p = 0; p < P; ++p) DPF_REQUIRE(w[p] != 0, DPF_ERR_INVALID, "pStable w must be non-zero");
+        }
+        h->P = P;
+        h->PW = (P + 31) / 32;
+        h->hA.assign(A, A + (size_t)P * d);
+        h->A.reserve((size_t)P * d);
+        h2d(h, h->A.p, A, (size_t)P * d);
+        h->chain.reserve((size_t)L * k);
+        h2d(h, h->chain.p, chain_idx, (size_t)L * k);
+        if (h->cfg.family_kind == DPF_FAMILY_PSTABLE) {
+            h->fb.reserve(P);
+            h->fw.reserve(P);
+            h2d(h, h->fb.p, b, (size_t)P);
+            h2d(h, h->fw.p, w, (size_t)P);
+        }
+        h->At.release();
+        if (h->cfg.pb == 0) {
+            h->Ap.reserve(1);
+            h->part_set = true;
+        }
+        prepare_family(h);
+        h->family_set = true;
+    });
+}
+
+int dpf_set_partitioners(dpf_handle h, const double* Ap) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "partitioners cannot change once vectors are indexed");
+        const size_t cnt = (size_t)h->cfg.L * h->cfg.pb * 32;
+        DPF_REQUIRE(Ap || cnt == 0, DPF_ERR_INVALID, "null partitioner functions");
+        h->Ap.reserve(std::max<size_t>(cnt, 1));
+        h2d(h, h->Ap.p, Ap, cnt);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        h->part_set = true;
+    });
+}
+
+int dpf_hash_dense(dpf_handle h, const double* X, int64_t n, int32_t* keys_out, int32_t* pids_out) {
+    return guarded(h, [&] {
+        require_ready(h, false);
+        DPF_REQUIRE(n >= 0 && (n == 0 || (X && keys_out)), DPF_ERR_INVALID, "null buffer");
+        if (n == 0) return;
+        begin_profile(h);
+        const int d = h->cfg.d, L = h->cfg.L;
+        DevBuf<double> Xd;
+        DevBuf<int32_t> kd;
+        DevBuf<uint8_t> pd;
+        Xd.reserve((size_t)n * d);
+        kd.reserve((size_t)L * n);
+        pd.reserve((size_t)L * n);
+        h2d(h, Xd.p, X, (size_t)n * d);
+        hash_dense_any(h, Xd.p, n, kd.p, pd.p, n);
+        d2h(h, keys_out, kd.p, (size_t)L * n);
+        if (pids_out) pids_to_host(h, pd.p, (int64_t)L * n, pids_out);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        end_profile(h);
+    });
+}
+
+int dpf_hash_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values, int64_t n,
+                 int32_t* keys_out, int32_t* pids_out) {
+    return guarded(h, [&] {
+        require_ready(h, false);
+        DPF_REQUIRE(n >= 0 && (n == 0 || (indptr && keys_out)), DPF_ERR_INVALID, "null buffer");
+        if (n == 0) return;
+        begin_profile(h);
+        const int L = h->cfg.L;
+        const int64_t nnz = indptr[n] - indptr[0];
+        DPF_REQUIRE(indptr[0] == 0, DPF_ERR_INVALID, "indptr must start at 0");
+        for (int64_t i = 0; i < nnz; ++i)
+            DPF_REQUIRE(indices[i] >= 0 && indices[i] < h->cfg.d, DPF_ERR_INVALID, "CSR index out of range");
+        DevBuf<int64_t> pd_;
+        DevBuf<int32_t> id_, kd;
+        DevBuf<double> vd;
+        DevBuf<uint8_t> pd;
+        pd_.reserve(n + 1); id_.reserve(std::max<int64_t>(nnz, 1)); vd.reserve(std::max<int64_t>(nnz, 1));
+        kd.reserve((size_t)L * n); pd.reserve((size_t)L * n);
+        h2d(h, pd_.p, indptr, (size_t)n + 1);
+        h2d(h, id_.p, indices, (size_t)nnz);
+        h2d(h, vd.p, values, (size_t)nnz);
+        hash_csr_device(h, pd_.p, id_.p, vd.p, n, kd.p, pd.p, n);
+        d2h(h, keys_out, kd.p, (size_t)L * n);
+        if (pids_out) pids_to_host(h, pd.p, (int64_t)L * n, pids_out);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        end_profile(h);
+    });
+}
+
+static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_device) {
+    require_ready(h, false);
+    DPF_REQUIRE(n > 0 && X, DPF_ERR_INVALID, "empty fit");
+    DPF_REQUIRE(h->n == 0 || h->dense, DPF_ERR_STATE, "index holds sparse vectors");
+    DPF_REQUIRE(h->n + n < (1LL << 31), DPF_ERR_INVALID, "ids are int32");
+    begin_profile(h);
+    const int d = h->cfg.d;
+    h->dense = true;
+    const double* Xnew;
+    if (on_device) {
+        DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "dpf_fit_dense_dev borrows the buffer and cannot append");
+        h->Xdev = X;
+        h->X_borrowed = true;
+        Xnew = X;
+    } else {
+        DPF_REQUIRE(!h->X_borrowed, DPF_ERR_STATE, "cannot append to a borrowed device buffer");
+        h->X.grow_keep((size_t)(h->n + n) * d, (size_t)h->n * d, h->stream);
+        h2d(h, h->X.p + (size_t)h->n * d, X, (size_t)n * d);
+        h->Xdev = h->X.p;
+        Xnew = h->X.p + (size_t)h->n * d;
+    }
+    grow_keys(h, n);
+    hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
+    h->n += n;
+    build_forest(h);
+    h->stats[DPF_STAT_SIZE] = h->n;
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
+    end_profile(h);
+}
+
+int dpf_fit_dense(dpf_handle h, const double* X, int64_t n) {
+    return guarded(h, [&] { fit_dense_common(h, X, n, false); });
+}
+int dpf_fit_dense_dev(dpf_handle h, const double* X_dev, int64_t n) {
+    return guarded(h, [&] { fit_dense_common(h, X_dev, n, true); });
+}
+
+int dpf_fit_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values, int64_t n) {
+    return guarded(h, [&] {
+        require_ready(h, false);
+        DPF_REQUIRE(n > 0 && indptr && indices && values, DPF_ERR_INVALID, "empty fit");
+        DPF_REQUIRE(h->n == 0 || !h->dense, DPF_ERR_STATE, "index holds dense vectors");
+        DPF_REQUIRE(indptr[0] == 0, DPF_ERR_INVALID, "indptr must start at 0");
+        DPF_REQUIRE(h->n + n < (1LL << 31), DPF_ERR_INVALID, "ids are int32");
+        begin_profile(h);
+        h->dense = false;
+        const int64_t nnz = indptr[n];
+        for (int64_t i = 0; i < nnz; ++i)
+            DPF_REQUIRE(indices[i] >= 0 && indices[i] < h->cfg.d, DPF_ERR_INVALID, "CSR index out of range");
+        // append to the CSR store (row pointers rebased)
+        h->sp_ptr.grow_keep((size_t)(h->n + n + 1), (size_t)(h->n ? h->n + 1 : 0), h->stream);
+        h->sp_idx.grow_keep((size_t)(h->sp_nnz + nnz) + 1, (size_t)h->sp_nnz, h->stream);
+        h->sp_val.grow_keep((size_t)(h->sp_nnz + nnz) + 1, (size_t)h->sp_nnz, h->stream);
+        std::vector<int64_t> rebased((size_t)n + 1);
+        for (int64_t i = 0; i <= n; ++i) rebased[(size_t)i] = indptr[i] + h->sp_nnz;
+        h2d(h, h->sp_ptr.p + h->n, rebased.data(), (size_t)n + 1);
+        h2d(h, h->sp_idx.p + h->sp_nnz, indices, (size_t)nnz);
+        h2d(h, h->sp_val.p + h->sp_nnz, values, (size_t)nnz);
+        grow_keys(h, n);
+        hash_csr_device(h, h->sp_ptr.p + h->n, h->sp_idx.p, h->sp_val.p, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));   // `rebased` must outlive the copy
+        h->sp_nnz += nnz;
+        h->n += n;
+        build_forest(h);
+        h->stats[DPF_STAT_SIZE] = h->n;
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        end_profile(h);
+    });
+}
+
+int64_t dpf_size(dpf_handle h) { return h ? h->n : -1; }
+
+int dpf_query_candidates_dense(dpf_handle h, const double* Q, int64_t nq, const int32_t* qids, int32_t steps,
+                               int32_t probe_mode, int64_t* offsets_out, int32_t* ids_out, int64_t cap,
+                               int64_t* total_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && Q && offsets_out, DPF_ERR_INVALID, "null buffer");
+        DPF_REQUIRE(steps >= 0 && (probe_mode == DPF_PROBE_NONE || probe_mode == DPF_PROBE_DENSE), DPF_ERR_INVALID, "bad steps/probe_mode");
+        begin_profile(h);
+        upload_queries_dense(h, Q, nq, qids);
+        hash_dense_any(h, h->qbuf.p, nq, h->qkeys.p, h->qpids.p, nq);
+        collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids ? h->qidbuf.p : nullptr}, steps, probe_mode);
+        emit_candidates(h, nq, offsets_out, ids_out, cap, total_out);
+        end_profile(h);
+    });
+}
+
+int dpf_query_candidates_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values,
+                             int64_t nq, const int32_t* qids, int32_t steps, int64_t* offsets_out, int32_t* ids_out,
+                             int64_t cap, int64_t* total_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && indptr && offsets_out, DPF_ERR_INVALID, "null buffer");
+        DPF_REQUIRE(indptr[0] == 0 && steps >= 0, DPF_ERR_INVALID, "indptr must start at 0");
+        begin_profile(h);
+        const int L = h->cfg.L;
+        const int64_t nnz = indptr[nq];
+        for (int64_t i = 0; i < nnz; ++i)
+            DPF_REQUIRE(indices[i] >= 0 && indices[i] < h->cfg.d, DPF_ERR_INVALID, "CSR index out of range");
+        DevBuf<int64_t> pd_;
+        DevBuf<int32_t> id_;
+        DevBuf<double> vd;
+        pd_.reserve(nq + 1); id_.reserve(std::max<int64_t>(nnz, 1)); vd.reserve(std::max<int64_t>(nnz, 1));
+        h2d(h, pd_.p, indptr, (size_t)nq + 1);
+        h2d(h, id_.p, indices, (size_t)nnz);
+        h2d(h, vd.p, values, (size_t)nnz);
+        h->qidbuf.reserve(nq + 1);
+        if (qids) h2d(h, h->qidbuf.p, qids, (size_t)nq);
+        h->qkeys.reserve((size_t)L * nq);
+        h->qpids.reserve((size_t)L * nq);
+        hash_csr_device(h, pd_.p, id_.p, vd.p, nq, h->qkeys.p, h->qpids.p, nq);
+        // the sparse overload has steps but no probes (RandomDrawTreeMap.java:686-732, quirk Q5)
+        collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids ? h->qidbuf.p : nullptr}, steps, DPF_PROBE_NONE);
+        emit_candidates(h, nq, offsets_out, ids_out, cap, total_out);
+        end_profile(h);
+    });
+}
+
+int dpf_query_candidates_by_id(dpf_handle h, const int32_t* qids, int64_t nq, int32_t steps, int64_t* offsets_out,
+                               int32_t* ids_out, int64_t cap, int64_t* total_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && qids && offsets_out && steps >= 0, DPF_ERR_INVALID, "null buffer");
+        begin_profile(h);
+        const int L = h->cfg.L;
+        h->qidbuf.reserve(nq + 1);
+        h2d(h, h->qidbuf.p, qids, (size_t)nq);
+        h->qkeys.reserve((size_t)L * nq);
+        h->qpids.reserve((size_t)L * nq);
+        gather_query_keys(h, h->qidbuf.p, nq);
+        collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, h->qidbuf.p}, steps, DPF_PROBE_NONE);
+        emit_candidates(h, nq, offsets_out, ids_out, cap, total_out);
+        end_profile(h);
+    });
+}
+
+static void topk_device(dpf_index* h, const double* Qd, int64_t nq, const int32_t* qids_dev, int steps, int probe_mode,
+                        int topk, int metric, int32_t* ids_out_dev, double* score_out_dev) {
+    const int L = h->cfg.L;
+    h->qkeys.reserve((size_t)L * nq);
+    h->qpids.reserve((size_t)L * nq);
+    hash_dense_any(h, Qd, nq, h->qkeys.p, h->qpids.p, nq);
+    collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids_dev}, steps, probe_mode);
+    rerank_topk(h, Qd, nq, h->q_off.p, h->q_cnt.p, h->cand.p, topk, metric, ids_out_dev, score_out_dev);
+}
+
+int dpf_query_topk_dense(dpf_handle h, const double* Q, int64_t nq, const int32_t* qids, int32_t steps,
+                         int32_t probe_mode, int32_t topk, int32_t metric, int32_t* ids_out, double* score_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && Q && ids_out && score_out, DPF_ERR_INVALID, "null buffer");
+        DPF_REQUIRE(steps >= 0 && metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad steps/metric");
+        begin_profile(h);
+        upload_queries_dense(h, Q, nq, qids);
+        h->out_ids.reserve((size_t)nq * topk);
+        h->out_scores.reserve((size_t)nq * topk);
+        topk_device(h, h->qbuf.p, nq, qids ? h->qidbuf.p : nullptr, steps, probe_mode, topk, metric, h->out_ids.p,
+                    h->out_scores.p);
+        d2h(h, ids_out, h->out_ids.p, (size_t)nq * topk);
+        d2h(h, score_out, h->out_scores.p, (size_t)nq * topk);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        end_profile(h);
+    });
+}
+
+int dpf_query_topk_dense_dev(dpf_handle h, const double* Q_dev, int64_t nq, const int32_t* qids_dev, int32_t steps,
+                             int32_t probe_mode, int32_t topk, int32_t metric, int32_t* ids_out_dev,
+                             double* score_out_dev) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && Q_dev && ids_out_dev && score_out_dev, DPF_ERR_INVALID, "null buffer");
+        DPF_REQUIRE(steps >= 0 && metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad steps/metric");
+        begin_profile(h);
+        topk_device(h, Q_dev, nq, qids_dev, steps, probe_mode, topk, metric, ids_out_dev, score_out_dev);
+        end_profile(h);
+    });
+}
+
+int dpf_rerank_dense(dpf_handle h, const double* Q, int64_t nq, const int64_t* offsets, const int32_t* cand,
+                     int32_t topk, int32_t metric, int32_t* ids_out, double* score_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && Q && offsets && ids_out && score_out, DPF_ERR_INVALID, "null buffer");
+        DPF_REQUIRE(metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad metric");
+        const int64_t total = offsets[nq];
+        for (int64_t i = 0; i < total; ++i)
+            DPF_REQUIRE(cand[i] >= 0 && cand[i] < h->n, DPF_ERR_INVALID, "candidate id out of range");
+        begin_profile(h);
+        const int d = h->cfg.d;
+        h->qbuf.reserve((size_t)nq * d);
+        h2d(h, h->qbuf.p, Q, (size_t)nq * d);
+        DevBuf<int64_t> off;
+        DevBuf<int32_t> cnt, cd;
+        off.reserve(nq + 1); cnt.reserve(nq); cd.reserve(std::max<int64_t>(total, 1));
+        h2d(h, off.p, offsets, (size_t)nq + 1);
+        h2d(h, cd.p, cand, (size_t)total);
+        counts_from_offsets(h, off.p, nq, cnt.p);
+        h->out_ids.reserve((size_t)nq * topk);
+        h->out_scores.reserve((size_t)nq * topk);
+        rerank_topk(h, h->qbuf.p, nq, off.p, cnt.p, cd.p, topk, metric, h->out_ids.p, h->out_scores.p);
+        d2h(h, ids_out, h->out_ids.p, (size_t)nq * topk);
+        d2h(h, score_out, h->out_scores.p, (size_t)nq * topk);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        end_profile(h);
+    });
+}
+
+int dpf_merge_topk_dev(dpf_handle h, const int32_t* gathered_ids_dev, const double* gathered_scores_dev, int32_t G,
+                       int64_t nq, int32_t topk, int32_t metric, int32_t* ids_out_dev, double* score_out_dev) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(gathered_ids_dev && gathered_scores_dev && ids_out_dev && score_out_dev, DPF_ERR_INVALID, "null buffer");
+        merge_topk(h, gathered_ids_dev, gathered_scores_dev, G, nq, topk, metric, ids_out_dev, score_out_dev);
+    });
+}
+
+int dpf_dump_buckets(dpf_handle h, int32_t table, int64_t* nbuckets_out, int64_t* nids_out, int32_t* desc_out,
+                     int64_t* off_out, int32_t* ids_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(table >= 0 && table < h->cfg.L, DPF_ERR_INVALID, "table out of range");
+        const TreeParams& tp = h->tp;
+        const int64_t slots = (int64_t)h->num_nodes * tp.W;
+        std::vector<int32_t> cp((size_t)slots), cc((size_t)slots);
+        d2h(h, cp.data(), h->child_ptr.p, (size_t)slots);
+        d2h(h, cc.data(), h->child_cnt.p, (size_t)slots);
+        const int64_t tb = h->h_table_base[table], tn = h->h_table_base[table + 1] - tb;
+        std::vector<int32_t> ids((size_t)tn);
+        d2h(h, ids.data(), h->ids_sorted.p + tb, (size_t)tn);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        int64_t nbk = 0, nid = 0;
+        struct Frame { int32_t node; int level; int64_t path; int next; };
+        for (int r = 0; r < tp.R; ++r) {
+            std::vector<Frame> st;
+            st.push_back(Frame{table * tp.R + r, tp.MAXL, 0, 0});
+            while (!st.empty()) {
+                Frame& f = st.back();
+                if (f.next >= tp.W) { st.pop_back(); continue; }
+                const int slot = f.next++;
+                const int64_t idx = (int64_t)f.node * tp.W + slot;
+                const int32_t c = cc[(size_t)idx], p = cp[(size_t)idx];
+                if (c == 0) continue;
+                const int64_t path = (f.path << tp.nb) | slot;
+                if (c < 0) { const Frame nf{p, f.level - 1, path, 0}; st.push_back(nf); continue; }
+                if (desc_out) { desc_out[nbk * 3] = r; desc_out[nbk * 3 + 1] = f.level; desc_out[nbk * 3 + 2] = (int32_t)path; }
+                if (off_out) off_out[nbk] = nid;
+                if (ids_out) std::memcpy(ids_out + nid, ids.data() + p, (size_t)c * sizeof(int32_t));
+                nid += c;
+                nbk++;
+            }
+        }
+        if (off_out) off_out[nbk] = nid;
+        if (nbuckets_out) *nbuckets_out = nbk;
+        if (nids_out) *nids_out = nid;
+    });
+}
+
+int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(stats_out, DPF_ERR_INVALID, "null buffer");
+        h->stats[DPF_STAT_SIZE] = h->n;
+        for (int i = 0; i < DPF_STAT_COUNT; ++i) stats_out[i] = h->stats[i];
+        if (occupancy_out)
+            for (size_t i = 0; i < h->occupancy.size(); ++i) occupancy_out[i] = h->occupancy[i];
+    });
+}
+
+int dpf_set_profiling(dpf_handle h, int32_t enable) {
+    return guarded(h, [&] { h->profiling = enable != 0; });
+}
+
+int dpf_stage_times_ms(dpf_handle h, float* ms_out) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(ms_out, DPF_ERR_INVALID, "null buffer");
+        if (h->profiling) end_profile(h);
+        for (int i = 0; i < DPF_T_COUNT; ++i) ms_out[i] = h->stage_ms[i];
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// common.cuh — internal declarations shared by the translation units of libdpf_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dpf.h"
+
+namespace dpf {
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing: device-side failures become DPF_ERR_* codes, never exceptions across the ABI
+// ---------------------------------------------------------------------------------------------------------
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define DPF_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            throw ::dpf::Error{e__ == cudaErrorMemoryAllocation ? DPF_ERR_NOMEM : DPF_ERR_CUDA,          \
+                               std::string(#expr) + ": " + cudaGetErrorString(e__)};                     \
+    } while (0)
+
+#define DPF_REQUIRE(cond, code, text)                        \
+    do {                                                     \
+        if (!(cond)) throw ::dpf::Error{(code), (text)};     \
+    } while (0)
+
+// owning device buffer (grow-only); all allocations of a handle go through these
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // ensure capacity >= n elements; contents are NOT preserved
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        release();
+        DPF_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+        cap = n;
+    }
+    // ensure capacity >= n elements, keeping the first `keep` elements
+    void grow_keep(size_t n, size_t keep, cudaStream_t st) {
+        if (n <= cap) return;
+        size_t ncap = n + n / 4;
+        T* q = nullptr;
+        DPF_CUDA(cudaMalloc((void**)&q, ncap * sizeof(T)));
+        if (keep && p) DPF_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        DPF_CUDA(cudaStreamSynchronize(st));
+        if (p) cudaFree(p);
+        p = q;
+        cap = ncap;
+    }
+};
+
+// tree geometry (RandomDrawTreeMap.java:435-465)
+struct TreeParams {
+    int SEG;          // 2^(32-bucket_bits)
+    int seg_bits;     // 32-bucket_bits
+    int nb;           // log2(dirNodeSize)
+    int W;            // dirNodeSize = 2^nb
+    int MAXL;         // (chainLength - seg_bits)/nb - 1
+    int bucket_bits;
+    int pb;           // partition bits
+    int R;            // roots per table = 2^pb * SEG
+    int T;            // BUCKET_OVERFLOW
+};
+
+// flat forest in HBM: node n has W children; child_cnt: 0 empty, >0 leaf bucket of that many ids starting at
+// ids_sorted[table_base[t] + child_ptr], <0 directory whose node index is child_ptr.
+struct ForestView {
+    const int32_t* child_ptr;
+    const int32_t* child_cnt;
+    const int32_t* ids_sorted;
+    const int64_t* table_base;  // L+1
+    int32_t num_nodes;
+};
+
+enum : int { kMaxTables = 256, kMaxChain = 32, kMaxPb = 8 };
+
+}  // namespace dpf
+
+// ---------------------------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------------------------
+struct dpf_index {
+    dpf_config cfg{};
+    dpf::TreeParams tp{};
+    int P = 0;
+    int PW = 0;  // sign words per vector = ceil(P/32)
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string last_error;
+    bool family_set = false, part_set = false, dense = true, fitted = false;
+    int num_sms = 148;
+
+    // hash functions
+    dpf::DevBuf<double> A;        // P x d row-major
+    dpf::DevBuf<double> At;       // d x Ppad feature-major copy for the CSR kernel (built on demand)
+    dpf::DevBuf<double> Anorm;    // P  (||a_p||_2)
+    dpf::DevBuf<int32_t> chain;   // L x k
+    dpf::DevBuf<double> fb;       // P (pStable b)
+    dpf::DevBuf<int32_t> fw;      // P (pStable w)
+    dpf::DevBuf<double> Ap;       // L x pb x 32
+    std::vector<double> hA;       // host copy (for At construction)
+    int At_ld = 0;
+
+    // data store
+    int64_t n = 0;
+    dpf::DevBuf<double> X;        // owned dense store (n x d) unless borrowed
+    const double* Xdev = nullptr; // points at X.p or at the caller's buffer (dpf_fit_dense_dev)
+    bool X_borrowed = false;
+    dpf::DevBuf<int64_t> sp_ptr;  // CSR store
+    dpf::DevBuf<int32_t> sp_idx;
+    dpf::DevBuf<double> sp_val;
+    int64_t sp_nnz = 0;
+
+    // per-vector keys / partition ids, table-major with leading dimension key_ld
+    dpf::DevBuf<int32_t> keys;
+    dpf::DevBuf<uint8_t> pids;
+    int64_t key_ld = 0;
+
+    // forest
+    dpf::DevBuf<int32_t> child_ptr, child_cnt, ids_sorted;
+    dpf::DevBuf<int64_t> table_base;
+    std::vector<int64_t> h_table_base;
+    std::vector<double> occupancy;   // 2^pb: ids per sub-index averaged over tables (last build)
+    int32_t num_nodes = 0, node_cap = 0;
+
+    // scratch
+    dpf::DevBuf<uint32_t> signs;      // n x PW
+    dpf::DevBuf<int32_t> pq;          // n x P quantised pStable values
+    dpf::DevBuf<int2> fix_list;
+    dpf::DevBuf<int32_t> counters;    // small device counters
+    dpf::DevBuf<uint32_t> sk0, sk1, sv0, sv1;  // sort ping-pong
+    dpf::DevBuf<uint32_t> hist;
+    dpf::DevBuf<int32_t> work0, work1;         // split worklists
+    dpf::DevBuf<uint32_t> bitmap;              // candidate de-dup bitmaps
+    dpf::DevBuf<int64_t> q_off;                // nq+1
+    dpf::DevBuf<int32_t> q_cnt;                // nq
+    dpf::DevBuf<int32_t> cand;                 // candidate ids
+    dpf::DevBuf<unsigned long long> sk64a, sk64b;
+    dpf::DevBuf<double> qbuf;                  // device copy of queries
+    dpf::DevBuf<int32_t> qidbuf, qkeys;
+    dpf::DevBuf<uint8_t> qpids;
+    dpf::DevBuf<int32_t> out_ids;
+    dpf::DevBuf<double> out_scores;
+    dpf::DevBuf<char> stage;                   // generic staging
+
+    // stats / profiling
+    int64_t stats[DPF_STAT_COUNT] = {0};
+    bool profiling = false;
+    cudaEvent_t ev[2 * DPF_T_COUNT] = {nullptr};
+    bool ev_used[DPF_T_COUNT] = {false};
+    float stage_ms[DPF_T_COUNT] = {0};
+};
+
+namespace dpf {
+
+// RAII stage timer: records CUDA events on the handle's stream around a stage when profiling is on
+struct StageTimer {
+    dpf_index* h;
+    int id;
+    StageTimer(dpf_index* h_, int id_) : h(h_), id(id_) {
+        if (h->profiling) {
+            cudaEventRecord(h->ev[2 * id], h->stream);
+        }
+    }
+    ~StageTimer() {
+        if (h->profiling) {
+            cudaEventRecord(h->ev[2 * id + 1], h->stream);
+            h->ev_used[id] = true;
+        }
+    }
+};
+
+// ---- hash.cu ------------------------------------------------------------------------------------------------
+// keys/pids for n dense vectors already on the device; keys_out/pids_out table-major with leading dim ld
+void hash_dense_device(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_out, uint8_t* pids_out, int64_t ld);
+void hash_dense_device_exact(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_out, uint8_t* pids_out, int64_t ld);
+void hash_csr_device(dpf_index* h, const int64_t* ptr, const int32_t* idx, const double* val, int64_t n,
+                     int32_t* keys_out, uint8_t* pids_out, int64_t ld);
+void prepare_family(dpf_index* h);
+
+// ---- sort.cu ------------------------------------------------------------------------------------------------
+// stable LSD radix sort of the bit range [lo_bit, hi_bit) — result ends in (*keys_io, *vals_io) which may be
+// swapped with the alternates.
+void radix_sort_pairs_u32(dpf_index* h, uint32_t** keys, uint32_t** keys_alt, uint32_t** vals, uint32_t** vals_alt,
+                          int64_t n, int lo_bit, int hi_bit);
+void radix_sort_keys_u64(dpf_index* h, unsigned long long** keys, unsigned long long** keys_alt, int64_t n, int lo_bit,
+                         int hi_bit);
+void exclusive_scan_i64(dpf_index* h, const int32_t* in, int64_t* out, int64_t n);  // out has n+1 entries
+
+// ---- forest.cu ----------------------------------------------------------------------------------------------
+void build_forest(dpf_index* h);
+ForestView forest_view(const dpf_index* h);
+
+// ---- query.cu -----------------------------------------------------------------------------------------------
+struct QueryKeys {
+    const int32_t* keys;   // L x ld
+    int64_t ld;
+    int64_t nq;
+    const int32_t* qids;   // device, may be null
+};
+// unique (unsorted) candidate lists: fills h->q_off (upper-bound offsets), h->q_cnt (unique counts), h->cand
+void collect_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode);
+// CSR with sorted unique ids on the device: out_off (nq+1), returns total; ids in h->cand compacted+sorted
+int64_t finalize_candidates_sorted(dpf_index* h, int64_t nq, int64_t* off_dev);
+void rerank_topk(dpf_index* h, const double* Qd, int64_t nq, const int64_t* off, const int32_t* cnt, const int32_t* cand,
+                 int topk, int metric, int32_t* ids_out, double* score_out);
+void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);
+void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt);
+void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,
+                int32_t* ids_out, double* score_out);
+
+}  // namespace dpf

@@ -1,0 +1,551 @@
+// query.cu — K4 (tree descent, multi-step sub-index search, multi-probe, candidate de-dup) and K5 (candidate
+// gather + FP64 re-rank + top-k), plus the multi-GPU top-k merge.
+//
+// Replaces, per query batch (reference file:line relative to /root/reference):
+//   RandomDrawTreeMap.getSimilarWithStepWiseFaster / getSimilarWithStepWise   src/main/java/mclab/mapdb/RandomDrawTreeMap.java:630-797
+//   findStepWiseSubIndexIDs :613-621, getInnerWithSimilarity :1106-1121, searchWithSimilarity :940-994
+//   DensevectorRDFInit.QueryTask (union over tables)                           src/main/scala/mclab/deploy/DensevectorRDFInit.scala:414-432
+//   topKAndPrecisionScore's gather + dgemv + argsort                          DensevectorRDFInit.scala:472-507
+//
+// K4: one warp per (query, table); lane i evaluates probe key h ^ (1 << i) (the reference's probe list has at
+// most 28 entries, so a warp covers it exactly); the warp walks the flat W-way nodes, removes duplicate buckets
+// with match.any, then streams each distinct bucket's ids (coalesced) through a per-query bitmap (shared memory
+// when the index fits, else a per-CTA slice in HBM) so that every id is emitted once.
+// K5: one warp per candidate row: 128-bit coalesced loads of the FP64 row, fused dot / cosine / squared-L2
+// against the query held in shared memory, warp-shuffle reduction, per-warp top-k lists merged per query.
+#include "common.cuh"
+
+namespace dpf {
+
+// ---------------------------------------------------------------------------------------------------------
+// descent
+// ---------------------------------------------------------------------------------------------------------
+struct ProbeCtx {
+    ForestView f;
+    TreeParams tp;
+    int L, steps, probe_mode, rank, world, self_exclude;
+};
+
+// bucket lookup for one probe key (RandomDrawTreeMap.java:940-994): empty slot -> nothing; leaf -> (ptr,cnt);
+// directory -> descend; falling off level 0 -> nothing
+__device__ __forceinline__ bool descend(const ForestView& f, const TreeParams& tp, int root_node, uint32_t probe,
+                                        int& ptr, int& cnt) {
+    int node = root_node;
+    for (int level = tp.MAXL; level >= 0; --level) {
+        const int slot = (int)((probe >> (tp.nb * level)) & (uint32_t)(tp.W - 1));
+        const int64_t idx = (int64_t)node * tp.W + slot;
+        const int c = __ldg(f.child_cnt + idx);
+        const int p = __ldg(f.child_ptr + idx);
+        if (c == 0) return false;
+        if (c > 0) { ptr = p; cnt = c; return true; }
+        node = p;
+    }
+    return false;
+}
+
+// Probe list of one (query, table): dense = { h ^ (1<<i) : 0 <= i < 28 - nlz(h) } — h itself is NOT in the list
+// and its length depends on nlz(h) (RandomDrawTreeMap.java:753-756, quirk Q4); none = { h }.
+// Returns the number of probes, or -1 for the reference's NegativeArraySizeException case.
+__device__ __forceinline__ int probe_count(uint32_t h, int probe_mode) {
+    if (probe_mode == DPF_PROBE_NONE) return 1;
+    return 32 - __clz((int)h) - 4;
+}
+
+// For one sub-index: every lane looks up its probe, duplicates are folded; on return `leader` marks the lanes
+// that hold a distinct, non-empty bucket.
+__device__ __forceinline__ void warp_lookup(const ProbeCtx& c, int t, int sub, int seg, uint32_t h, int nprobes,
+                                            int lane, bool& leader, int& ptr, int& cnt) {
+    ptr = 0;
+    cnt = 0;
+    bool ok = false;
+    if (lane < nprobes) {
+        const uint32_t probe = (c.probe_mode == DPF_PROBE_NONE) ? h : (h ^ (1u << lane));
+        ok = descend(c.f, c.tp, t * c.tp.R + sub * c.tp.SEG + seg, probe, ptr, cnt);
+    }
+    const int key = ok ? ptr : (-1 - lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    leader = ok && ((__ffs(peers) - 1) == lane);
+}
+
+// pass A: upper bound of the candidate count per query (sum of distinct bucket sizes over tables)
+__global__ void __launch_bounds__(256)
+k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t nq,
+              int32_t* __restrict__ q_ub, unsigned long long* __restrict__ stat /* [0] nlz>28, [1] with-dups */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= nq * c.L) return;
+    const int64_t q = wid / c.L;
+    const int t = (int)(wid % c.L);
+    const uint32_t h = (uint32_t)qkeys[(int64_t)t * ld + q];
+    const int pid = qpids[(int64_t)t * ld + q];
+    const int seg = c.tp.seg_bits ? (int)(h >> c.tp.bucket_bits) : 0;
+    const int nprobes = probe_count(h, c.probe_mode);
+    if (nprobes < 0) {
+        if (lane == 0) atomicAdd(&stat[0], 1ULL);
+        return;
+    }
+    int total = 0;
+    const int np = 1 << c.tp.pb;
+    for (int sub = 0; sub < np; ++sub) {       // findStepWiseSubIndexIDs (RandomDrawTreeMap.java:613-621)
+        if (__popc(sub ^ pid) > c.steps) continue;
+        if (c.world > 1 && (sub % c.world) != c.rank) continue;   // this GPU's sub-forest only
+        bool leader;
+        int ptr, cnt;
+        warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);
+        total += leader ? cnt : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0 && total > 0) {
+        atomicAdd(&q_ub[q], total);
+        atomicAdd(&stat[1], (unsigned long long)total);
+    }
+}
+
+// pass B: expansion + de-dup.  Persistent CTAs pull queries from a counter; bitmap in shared memory (SMEM_BM)
+// or in this CTA's slice of a global scratch.
+constexpr int EXP_THREADS = 512;
+template <bool SMEM_BM>
+__global__ void __launch_bounds__(EXP_THREADS)
+k_expand(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t nq,
+         const int32_t* __restrict__ qids, const int64_t* __restrict__ q_off, int32_t* __restrict__ q_cnt,
+         int32_t* __restrict__ cand, uint32_t* __restrict__ gbitmap, int64_t bm_words, int* __restrict__ next_query) {
+    extern __shared__ uint32_t sbm[];
+    __shared__ int s_q, s_count;
+    uint32_t* bm = SMEM_BM ? sbm : gbitmap + (int64_t)blockIdx.x * bm_words;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = EXP_THREADS / 32;
+    if (SMEM_BM) {
+        for (int64_t i = tid; i < bm_words; i += EXP_THREADS) bm[i] = 0u;
+    }
+    __syncthreads();
+    const int np = 1 << c.tp.pb;
+    for (;;) {
+        if (tid == 0) { s_q = atomicAdd(next_query, 1); s_count = 0; }
+        __syncthreads();
+        const int64_t q = s_q;
+        if (q >= nq) break;
+        const int64_t off = q_off[q];
+        const int qid = qids ? qids[q] : INT32_MIN;
+        // quirk Q3 (RandomDrawTreeMap.java:982): `ln.key != key` compares boxed Integers by reference, so the
+        // query's own id is dropped only inside the Integer cache
+        const bool excl = c.self_exclude && qids && qid >= -128 && qid <= 127;
+        for (int t = warp; t < c.L; t += nwarps) {
+            const uint32_t h = (uint32_t)qkeys[(int64_t)t * ld + q];
+            const int pid = qpids[(int64_t)t * ld + q];
+            const int seg = c.tp.seg_bits ? (int)(h >> c.tp.bucket_bits) : 0;
+            const int nprobes = probe_count(h, c.probe_mode);
+            if (nprobes < 0) continue;
+            const int64_t tbase = c.f.table_base[t];
+            for (int sub = 0; sub < np; ++sub) {
+                if (__popc(sub ^ pid) > c.steps) continue;
+                if (c.world > 1 && (sub % c.world) != c.rank) continue;
+                bool leader;
+                int ptr, cnt;
+                warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);
+                uint32_t todo = __ballot_sync(0xffffffffu, leader);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int bptr = __shfl_sync(0xffffffffu, ptr, src);
+                    const int bcnt = __shfl_sync(0xffffffffu, cnt, src);
+                    const int32_t* ids = c.f.ids_sorted + tbase + bptr;
+                    for (int j0 = 0; j0 < bcnt; j0 += 32) {
+                        const int j = j0 + lane;
+                        bool fresh = false;
+                        int id = 0;
+                        if (j < bcnt) {
+                            id = __ldg(ids + j);
+                            if (!(excl && id == qid)) {
+                                const uint32_t bit = 1u << (id & 31);
+                                const uint32_t old = atomicOr(&bm[id >> 5], bit);
+                                fresh = !(old & bit);
+                            }
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                        if (m) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (fresh) cand[off + base + __popc(m & ((1u << lane) - 1u))] = id;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int count = s_count;
+        if (tid == 0) q_cnt[q] = count;
+        for (int i = tid; i < count; i += EXP_THREADS) bm[cand[off + i] >> 5] = 0u;   // reset only what was touched
+        __syncthreads();
+    }
+}
+
+__global__ void k_gather_query_keys(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pids, int64_t ld,
+                                    const int32_t* __restrict__ qids, int64_t nq, int L, int64_t n,
+                                    int32_t* __restrict__ qkeys, uint8_t* __restrict__ qpids, int* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * L) return;
+    const int t = (int)(i / nq);
+    const int64_t q = i % nq;
+    const int id = qids[q];
+    if (id < 0 || id >= n) { *bad = 1; qkeys[i] = 0; qpids[i] = 0; return; }
+    qkeys[i] = keys[(int64_t)t * ld + id];
+    qpids[i] = pids[(int64_t)t * ld + id];
+}
+
+void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq) {
+    h->counters.reserve(64);
+    DPF_CUDA(cudaMemsetAsync(h->counters.p + 16, 0, sizeof(int32_t), h->stream));
+    const int64_t tot = nq * h->cfg.L;
+    k_gather_query_keys<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+        h->keys.p, h->pids.p, h->key_ld, qids_dev, nq, h->cfg.L, h->n, h->qkeys.p, h->qpids.p, h->counters.p + 16);
+    DPF_CUDA(cudaGetLastError());
+    int32_t bad = 0;
+    DPF_CUDA(cudaMemcpyAsync(&bad, h->counters.p + 16, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
+    // the reference prints "fetch vector ... but got NULL" and calls System.exit(1) (RandomDrawTreeMap.java:1508-1511)
+    DPF_REQUIRE(!bad, DPF_ERR_INVALID, "query id is not in the index");
+}
+
+void collect_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode) {
+    const int64_t nq = qk.nq;
+    ProbeCtx c;
+    c.f = forest_view(h);
+    c.tp = h->tp;
+    c.L = h->cfg.L;
+    c.steps = steps;
+    c.probe_mode = probe_mode;
+    c.world = h->cfg.world > 1 ? h->cfg.world : 1;
+    c.rank = c.world > 1 ? h->cfg.rank : 0;
+    c.self_exclude = h->cfg.self_exclude_small_ids;
+    cudaStream_t st = h->stream;
+    h->q_cnt.reserve(nq + 1);
+    h->q_off.reserve(nq + 1);
+    h->counters.reserve(64);
+    unsigned long long* stat = reinterpret_cast<unsigned long long*>(h->counters.p + 20);
+    DPF_CUDA(cudaMemsetAsync(h->counters.p + 16, 0, 12 * sizeof(int32_t), st));
+    DPF_CUDA(cudaMemsetAsync(h->q_cnt.p, 0, (nq + 1) * sizeof(int32_t), st));
+    {
+        StageTimer tm(h, DPF_T_PROBE_COUNT);
+        const int64_t warps = nq * c.L;
+        k_probe_count<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, h->q_cnt.p, stat);
+        DPF_CUDA(cudaGetLastError());
+        exclusive_scan_i64(h, h->q_cnt.p, h->q_off.p, nq);
+    }
+    int64_t ub_total = 0;
+    unsigned long long hstat[2];
+    DPF_CUDA(cudaMemcpyAsync(&ub_total, h->q_off.p + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaMemcpyAsync(hstat, stat, sizeof(hstat), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaStreamSynchronize(st));
+    h->stats[DPF_STAT_NLZ_GT28] = (int64_t)hstat[0];
+    h->stats[DPF_STAT_LAST_CAND_WITH_DUPS] = (int64_t)hstat[1];
+    h->cand.reserve((size_t)std::max<int64_t>(ub_total, 1));
+    {
+        StageTimer tm(h, DPF_T_EXPAND);
+        const int64_t bm_words = (h->n + 31) / 32 + 1;
+        const size_t smem_need = (size_t)bm_words * sizeof(uint32_t);
+        int* next_query = h->counters.p + 16;
+        const bool use_smem = smem_need <= 200 * 1024;
+        if (use_smem) {
+            static size_t attr = 0;
+            if (smem_need > attr) {
+                DPF_CUDA(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+                attr = smem_need;
+            }
+            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem_need, 1)));
+            const int grid = (int)std::min<int64_t>(nq, (int64_t)h->num_sms * per_sm);
+            k_expand<true><<<grid, EXP_THREADS, smem_need, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, qk.qids, h->q_off.p,
+                                                                  h->q_cnt.p, h->cand.p, nullptr, bm_words, next_query);
+        } else {
+            const int grid = (int)std::min<int64_t>(nq, (int64_t)h->num_sms * 2);
+            const size_t need = (size_t)grid * bm_words;
+            if (h->bitmap.cap < need) {
+                h->bitmap.reserve(need);
+                DPF_CUDA(cudaMemsetAsync(h->bitmap.p, 0, need * sizeof(uint32_t), st));   // kept all-zero between calls
+            }
+            k_expand<false><<<grid, EXP_THREADS, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, qk.qids, h->q_off.p,
+                                                          h->q_cnt.p, h->cand.p, h->bitmap.p, bm_words, next_query);
+        }
+        DPF_CUDA(cudaGetLastError());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sorted unique CSR output
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_compose_keys(const int64_t* __restrict__ q_off, const int64_t* __restrict__ out_off, const int32_t* __restrict__ q_cnt,
+               const int32_t* __restrict__ cand, unsigned long long* __restrict__ keys) {
+    const int64_t q = blockIdx.x;
+    const int cnt = q_cnt[q];
+    const int64_t src = q_off[q], dst = out_off[q];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+        keys[dst + i] = ((unsigned long long)q << 32) | (uint32_t)cand[src + i];
+}
+__global__ void k_low32(const unsigned long long* __restrict__ keys, int64_t n, int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)(uint32_t)keys[i];
+}
+
+int64_t finalize_candidates_sorted(dpf_index* h, int64_t nq, int64_t* off_dev) {
+    StageTimer tm(h, DPF_T_CAND_SORT);
+    cudaStream_t st = h->stream;
+    exclusive_scan_i64(h, h->q_cnt.p, off_dev, nq);
+    int64_t total = 0;
+    DPF_CUDA(cudaMemcpyAsync(&total, off_dev + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaStreamSynchronize(st));
+    h->stats[DPF_STAT_LAST_CANDIDATES] = total;
+    if (total == 0) return 0;
+    h->sk64a.reserve(total);
+    h->sk64b.reserve(total);
+    k_compose_keys<<<(unsigned)nq, 256, 0, st>>>(h->q_off.p, off_dev, h->q_cnt.p, h->cand.p, h->sk64a.p);
+    DPF_CUDA(cudaGetLastError());
+    int idbits = 1, qbits = 1;
+    while ((1LL << idbits) < h->n) idbits++;
+    while ((1LL << qbits) < nq) qbits++;
+    unsigned long long *a = h->sk64a.p, *b = h->sk64b.p;
+    radix_sort_keys_u64(h, &a, &b, total, 0, idbits);
+    radix_sort_keys_u64(h, &a, &b, total, 32, 32 + qbits);
+    k_low32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total, h->cand.p);   // total <= ub_total: fits
+    DPF_CUDA(cudaGetLastError());
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: gather + re-rank + top-k
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RR_THREADS = 256;
+constexpr int RR_WARPS = RR_THREADS / 32;
+constexpr int RR_MAXK = 256;
+
+// total order of results: larger key first, ties by smaller id (key = score, or -distance for L2)
+__device__ __forceinline__ bool better(double ka, int ia, double kb, int ib) {
+    return ka > kb || (ka == kb && ia < ib);
+}
+
+// warp-cooperative insertion into a descending list of length <= K held in shared memory
+__device__ __forceinline__ void warp_insert(double* keys, int* ids, int& count, int K, double key, int id, int lane) {
+    if (count == K && !better(key, id, keys[K - 1], ids[K - 1])) return;
+    // position = number of entries that are better than the new one
+    int pos = 0;
+    for (int base = 0; base < count; base += 32) {
+        const int i = base + lane;
+        const bool b = i < count && better(keys[i], ids[i], key, id);
+        pos += __popc(__ballot_sync(0xffffffffu, b));
+    }
+    const int newcount = min(count + 1, K);
+    // shift [pos, newcount-1) right by one, from the back, 32 at a time
+    for (int hi = newcount - 1; hi > pos; hi -= 32) {
+        const int i = hi - lane;
+        double kv = 0;
+        int iv = 0;
+        const bool mv = i > pos;
+        if (mv) { kv = keys[i - 1]; iv = ids[i - 1]; }
+        __syncwarp();
+        if (mv) { keys[i] = kv; ids[i] = iv; }
+        __syncwarp();
+    }
+    if (lane == 0) { keys[pos] = key; ids[pos] = id; }
+    __syncwarp();
+    count = newcount;
+}
+
+template <bool VEC2>
+__global__ void __launch_bounds__(RR_THREADS)
+k_rerank_topk(const double* __restrict__ X, int d, const double* __restrict__ Q, int64_t nq,
+              const int64_t* __restrict__ off, const int32_t* __restrict__ cnt, const int32_t* __restrict__ cand, int K,
+              int metric, int32_t* __restrict__ ids_out, double* __restrict__ score_out, int* __restrict__ next_query) {
+    extern __shared__ double rsm[];
+    double* qs = rsm;                                    // d (padded to even)
+    double* lkeys = rsm + ((d + 1) & ~1);                // RR_WARPS x K
+    int* lids = reinterpret_cast<int*>(lkeys + RR_WARPS * K);
+    __shared__ int s_q;
+    __shared__ double s_qn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* mykeys = lkeys + warp * K;
+    int* myids = lids + warp * K;
+    for (;;) {
+        if (tid == 0) s_q = atomicAdd(next_query, 1);
+        __syncthreads();
+        const int64_t q = s_q;
+        if (q >= nq) break;
+        for (int j = tid; j < d; j += RR_THREADS) qs[j] = Q[q * d + j];
+        __syncthreads();
+        if (metric == DPF_METRIC_ANGULAR && warp == 0) {
+            double s = 0;
+            for (int j = lane; j < d; j += 32) s = fma(qs[j], qs[j], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) s_qn = sqrt(s);
+        }
+        __syncthreads();
+        const int n_c = cnt[q];
+        const int32_t* cq = cand + off[q];
+        int count = 0;
+        for (int ci = warp; ci < n_c; ci += RR_WARPS) {
+            const int id = __ldg(cq + ci);
+            const double* row = X + (int64_t)id * d;
+            double s = 0.0, xn = 0.0;
+            if (VEC2) {
+                const double2* r2 = reinterpret_cast<const double2*>(row);
+                const double2* q2 = reinterpret_cast<const double2*>(qs);
+                for (int j = lane; j < (d >> 1); j += 32) {
+                    const double2 x = __ldg(r2 + j);
+                    const double2 qq = q2[j];
+                    if (metric == DPF_METRIC_L2) {
+                        const double a = qq.x - x.x, b = qq.y - x.y;
+                        s = fma(a, a, s);
+                        s = fma(b, b, s);
+                    } else {
+                        s = fma(x.x, qq.x, s);
+                        s = fma(x.y, qq.y, s);
+                        if (metric == DPF_METRIC_ANGULAR) { xn = fma(x.x, x.x, xn); xn = fma(x.y, x.y, xn); }
+                    }
+                }
+            } else {
+                for (int j = lane; j < d; j += 32) {
+                    const double x = __ldg(row + j), qq = qs[j];
+                    if (metric == DPF_METRIC_L2) { const double a = qq - x; s = fma(a, a, s); }
+                    else {
+                        s = fma(x, qq, s);
+                        if (metric == DPF_METRIC_ANGULAR) xn = fma(x, x, xn);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (metric == DPF_METRIC_ANGULAR) xn += __shfl_xor_sync(0xffffffffu, xn, o);
+            }
+            if (metric == DPF_METRIC_ANGULAR) s = s / (s_qn * sqrt(xn));
+            const double key = (metric == DPF_METRIC_L2) ? -s : s;
+            if (key == key) warp_insert(mykeys, myids, count, K, key, id, lane);   // NaN scores are never ranked
+        }
+        // merge the per-warp lists: K rounds of "best head" over RR_WARPS sorted lists, done by warp 0
+        __shared__ int s_counts[RR_WARPS];
+        if (lane == 0) s_counts[warp] = count;
+        __syncthreads();
+        if (warp == 0) {
+            int head = 0;
+            const int mycount = lane < RR_WARPS ? s_counts[lane] : 0;
+            for (int r = 0; r < K; ++r) {
+                double bk = 0;
+                int bi = 0x7fffffff, bl = -1;
+                if (lane < RR_WARPS && head < mycount) { bk = lkeys[lane * K + head]; bi = lids[lane * K + head]; bl = lane; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                    if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+                }
+                if (lane == 0) {
+                    ids_out[q * K + r] = bl >= 0 ? bi : -1;
+                    score_out[q * K + r] = bl >= 0 ? (metric == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
+                }
+                if (lane == bl) head++;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_counts_from_offsets(const int64_t* __restrict__ off, int64_t nq, int32_t* __restrict__ cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) cnt[i] = (int32_t)(off[i + 1] - off[i]);
+}
+
+void rerank_topk(dpf_index* h, const double* Qd, int64_t nq, const int64_t* off, const int32_t* cnt, const int32_t* cand,
+                 int topk, int metric, int32_t* ids_out, double* score_out) {
+    DPF_REQUIRE(topk >= 1 && topk <= RR_MAXK, DPF_ERR_INVALID, "topk must be in 1..256");
+    DPF_REQUIRE(h->dense && h->Xdev, DPF_ERR_STATE, "re-rank needs a dense index");
+    if (nq <= 0) return;
+    StageTimer tm(h, DPF_T_RERANK);
+    const int d = h->cfg.d;
+    cudaStream_t st = h->stream;
+    h->counters.reserve(64);
+    int* next_query = h->counters.p + 17;
+    DPF_CUDA(cudaMemsetAsync(next_query, 0, sizeof(int), st));
+    const size_t smem = (size_t)((d + 1) & ~1) * sizeof(double) + (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
+    const bool vec2 = (d % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0);
+    static size_t attr[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > attr[vec2]) {
+        if (vec2) DPF_CUDA(cudaFuncSetAttribute(k_rerank_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else DPF_CUDA(cudaFuncSetAttribute(k_rerank_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr[vec2] = smem;
+    }
+    const int grid = (int)std::min<int64_t>(nq, (int64_t)h->num_sms * 8);
+    if (vec2)
+        k_rerank_topk<true><<<grid, RR_THREADS, smem, st>>>(h->Xdev, d, Qd, nq, off, cnt, cand, topk, metric, ids_out,
+                                                            score_out, next_query);
+    else
+        k_rerank_topk<false><<<grid, RR_THREADS, smem, st>>>(h->Xdev, d, Qd, nq, off, cnt, cand, topk, metric, ids_out,
+                                                             score_out, next_query);
+    DPF_CUDA(cudaGetLastError());
+}
+
+void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt) {
+    k_counts_from_offsets<<<(unsigned)((nq + 255) / 256), 256, 0, h->stream>>>(off, nq, cnt);
+    DPF_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-GPU: merge G per-GPU top-k lists per query; the same id can arrive from several GPUs (reached through
+// tables whose sub-index lives on different GPUs) with a bit-identical score, and is kept once.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_merge_topk(const int32_t* __restrict__ gids, const double* __restrict__ gsc, int G, int64_t nq, int K, int metric,
+             int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    // lane g < G walks list g (each list is already in result order)
+    int head = 0, last = -1;
+    for (int r = 0; r < K; ++r) {
+        double bk;
+        int bi, bl;
+        for (;;) {
+            bk = 0; bi = 0x7fffffff; bl = -1;
+            for (int g0 = 0; g0 < G; g0 += 32) {       // G <= 32 in practice; loop kept for generality
+                const int g = g0 + lane;
+                if (g < G && head < K) {
+                    const int id = gids[((int64_t)g * nq + q) * K + head];
+                    if (id >= 0) {
+                        const double s = gsc[((int64_t)g * nq + q) * K + head];
+                        bk = (metric == DPF_METRIC_L2) ? -s : s; bi = id; bl = lane;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+            }
+            if (bl < 0) break;
+            if (lane == bl) head++;
+            if (bi != last) break;                     // duplicate of the id just emitted: skip it
+        }
+        if (lane == 0) {
+            ids_out[q * K + r] = bl >= 0 ? bi : -1;
+            score_out[q * K + r] = bl >= 0 ? (metric == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
+        }
+        if (bl < 0) {
+            for (int r2 = r + 1; r2 < K; ++r2)
+                if (lane == 0) { ids_out[q * K + r2] = -1; score_out[q * K + r2] = __longlong_as_double(0x7ff8000000000000LL); }
+            break;
+        }
+        last = bi;
+    }
+}
+
+void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,
+                int32_t* ids_out, double* score_out) {
+    DPF_REQUIRE(G >= 1 && G <= 32, DPF_ERR_INVALID, "merge supports 1..32 lists");
+    if (nq <= 0) return;
+    k_merge_topk<<<(unsigned)((nq + 3) / 4), 128, 0, h->stream>>>(gids, gsc, G, nq, topk, metric, ids_out, score_out);
+    DPF_CUDA(cudaGetLastError());
+}
+
+}  // namespace dpf

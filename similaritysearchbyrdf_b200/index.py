@@ -1,0 +1,198 @@
+"""DPFIndex — thin Python handle over the C ABI (include/dpf.h).  All compute happens in libdpf_b200.so on the GPU;
+nothing here falls back to the CPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as B
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class DPFIndex:
+    """One forest of L tables on one GPU.
+
+    Parameters mirror the reference configuration keys (src/test/scala/mclab/TestSettings.scala:9-45):
+    d=mclab.lsh.vectorDim, L=tableNum*permutationNum, k=lshTable.chainLength, pb=lsh.partitionBits,
+    bucket_bits=lshTable.bucketBits, dir_node_size=lshTable.dirNodeSize, bucket_overflow=lshTable.bufferOverflow.
+    """
+
+    def __init__(self, d, L, k=32, pb=3, bucket_bits=28, dir_node_size=32, bucket_overflow=500,
+                 family_kind=B.FAMILY_ANGLE, key_transform=B.KEY_ORIGINAL, self_exclude_small_ids=1, device=0, rank=0,
+                 world=1):
+        self.lib = B.load()
+        self.cfg = B.Config(B.ABI_VERSION, device, d, L, k, pb, bucket_bits, dir_node_size, bucket_overflow,
+                            family_kind, key_transform, self_exclude_small_ids, rank, world)
+        self.h = C.c_void_p()
+        rc = self.lib.dpf_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != B.OK:
+            raise B.DpfError(rc, self.lib.dpf_strerror(rc).decode())
+        self.d, self.L, self.k, self.pb = d, L, k, pb
+
+    # ---- plumbing -------------------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != B.OK:
+            raise B.DpfError(rc, self.lib.dpf_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.lib.dpf_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.lib.dpf_size(self.h))
+
+    def sync(self):
+        self._ck(self.lib.dpf_sync(self.h))
+
+    # ---- hash functions -------------------------------------------------------------------------------------
+    def set_family(self, A, chain_idx, b=None, w=None):
+        A, chain_idx = _f64(A), _i32(chain_idx)
+        if A.ndim != 2 or A.shape[1] != self.d or chain_idx.shape != (self.L, self.k):
+            raise ValueError("A must be P x d and chain_idx L x k")
+        b = None if b is None else _f64(b)
+        w = None if w is None else _i32(w)
+        self.P = A.shape[0]
+        self._ck(self.lib.dpf_set_family(self.h, _p(A), A.shape[0], _p(chain_idx), _p(b), _p(w)))
+
+    def set_partitioners(self, Ap):
+        Ap = _f64(Ap)
+        if Ap.shape != (self.L, self.pb, 32):
+            raise ValueError("Ap must be L x pb x 32")
+        self._ck(self.lib.dpf_set_partitioners(self.h, _p(Ap)))
+
+    # ---- hashing --------------------------------------------------------------------------------------------
+    def hash_dense(self, X):
+        X = _f64(X)
+        n = X.shape[0]
+        keys = np.empty((self.L, n), np.int32)
+        pids = np.empty((self.L, n), np.int32)
+        self._ck(self.lib.dpf_hash_dense(self.h, _p(X), n, _p(keys), _p(pids)))
+        return keys, pids
+
+    def hash_csr(self, indptr, indices, values):
+        indptr, indices, values = _i64(indptr), _i32(indices), _f64(values)
+        n = len(indptr) - 1
+        keys = np.empty((self.L, n), np.int32)
+        pids = np.empty((self.L, n), np.int32)
+        self._ck(self.lib.dpf_hash_csr(self.h, _p(indptr), _p(indices), _p(values), n, _p(keys), _p(pids)))
+        return keys, pids
+
+    # ---- fit ------------------------------------------------------------------------------------------------
+    def fit_dense(self, X):
+        X = _f64(X)
+        self._ck(self.lib.dpf_fit_dense(self.h, _p(X), X.shape[0]))
+
+    def fit_dense_dev(self, dev_ptr, n):
+        """Borrow an n x d FP64 device buffer (e.g. torch tensor .data_ptr()); it must outlive the index."""
+        self._ck(self.lib.dpf_fit_dense_dev(self.h, C.c_void_p(dev_ptr), n))
+
+    def fit_csr(self, indptr, indices, values):
+        indptr, indices, values = _i64(indptr), _i32(indices), _f64(values)
+        self._ck(self.lib.dpf_fit_csr(self.h, _p(indptr), _p(indices), _p(values), len(indptr) - 1))
+
+    # ---- queries --------------------------------------------------------------------------------------------
+    def _cand_call(self, fn, nq, *args):
+        off = np.empty(nq + 1, np.int64)
+        total = C.c_int64(0)
+        cap = max(1 << 16, 64 * nq)
+        while True:
+            ids = np.empty(cap, np.int32)
+            rc = fn(self.h, *args, _p(off), _p(ids), cap, C.byref(total))
+            if rc == B.ERR_CAPACITY:
+                cap = int(total.value)
+                continue
+            self._ck(rc)
+            return off, ids[:total.value].copy()
+
+    def query_candidates_dense(self, Q, qids=None, steps=0, probe_mode=B.PROBE_DENSE):
+        Q = _f64(Q)
+        qids = None if qids is None else _i32(qids)
+        return self._cand_call(self.lib.dpf_query_candidates_dense, Q.shape[0], _p(Q), Q.shape[0], _p(qids), steps,
+                               probe_mode)
+
+    def query_candidates_csr(self, indptr, indices, values, qids=None, steps=0):
+        indptr, indices, values = _i64(indptr), _i32(indices), _f64(values)
+        qids = None if qids is None else _i32(qids)
+        nq = len(indptr) - 1
+        return self._cand_call(self.lib.dpf_query_candidates_csr, nq, _p(indptr), _p(indices), _p(values), nq,
+                               _p(qids), steps)
+
+    def query_candidates_by_id(self, qids, steps=0):
+        qids = _i32(qids)
+        return self._cand_call(self.lib.dpf_query_candidates_by_id, len(qids), _p(qids), len(qids), steps)
+
+    def query_topk_dense(self, Q, qids=None, steps=0, topk=10, metric=B.METRIC_DOT, probe_mode=B.PROBE_DENSE):
+        Q = _f64(Q)
+        qids = None if qids is None else _i32(qids)
+        nq = Q.shape[0]
+        ids = np.empty((nq, topk), np.int32)
+        sc = np.empty((nq, topk), np.float64)
+        self._ck(self.lib.dpf_query_topk_dense(self.h, _p(Q), nq, _p(qids), steps, probe_mode, topk, metric, _p(ids),
+                                               _p(sc)))
+        return ids, sc
+
+    def query_topk_dense_dev(self, q_ptr, nq, qids_ptr, steps, topk, metric, ids_ptr, score_ptr,
+                             probe_mode=B.PROBE_DENSE):
+        """Device-resident variant: all pointers are device addresses on this index's GPU (asynchronous)."""
+        self._ck(self.lib.dpf_query_topk_dense_dev(self.h, C.c_void_p(q_ptr), nq,
+                                                   C.c_void_p(qids_ptr) if qids_ptr else None, steps, probe_mode,
+                                                   topk, metric, C.c_void_p(ids_ptr), C.c_void_p(score_ptr)))
+
+    def rerank_dense(self, Q, offsets, cand, topk, metric=B.METRIC_DOT):
+        Q, offsets, cand = _f64(Q), _i64(offsets), _i32(cand)
+        nq = Q.shape[0]
+        ids = np.empty((nq, topk), np.int32)
+        sc = np.empty((nq, topk), np.float64)
+        self._ck(self.lib.dpf_rerank_dense(self.h, _p(Q), nq, _p(offsets), _p(cand), topk, metric, _p(ids), _p(sc)))
+        return ids, sc
+
+    def merge_topk_dev(self, gids_ptr, gsc_ptr, G, nq, topk, metric, ids_ptr, score_ptr):
+        self._ck(self.lib.dpf_merge_topk_dev(self.h, C.c_void_p(gids_ptr), C.c_void_p(gsc_ptr), G, nq, topk, metric,
+                                             C.c_void_p(ids_ptr), C.c_void_p(score_ptr)))
+
+    # ---- introspection --------------------------------------------------------------------------------------
+    def dump_buckets(self, table):
+        nb, nid = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.dpf_dump_buckets(self.h, table, C.byref(nb), C.byref(nid), None, None, None))
+        desc = np.empty((max(nb.value, 1), 3), np.int32)
+        off = np.empty(nb.value + 1, np.int64)
+        ids = np.empty(max(nid.value, 1), np.int32)
+        self._ck(self.lib.dpf_dump_buckets(self.h, table, C.byref(nb), C.byref(nid), _p(desc), _p(off), _p(ids)))
+        return desc[:nb.value], off, ids[:nid.value]
+
+    def stats(self):
+        s = np.zeros(B.STAT_COUNT, np.int64)
+        occ = np.zeros(1 << self.pb, np.float64)
+        self._ck(self.lib.dpf_stats(self.h, _p(s), _p(occ)))
+        out = {n: int(s[i]) for i, n in enumerate(B.STAT_NAMES)}
+        out["occupancy"] = occ
+        return out
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.dpf_set_profiling(self.h, 1 if on else 0))
+
+    def stage_times_ms(self):
+        ms = np.zeros(B.T_COUNT, np.float32)
+        self._ck(self.lib.dpf_stage_times_ms(self.h, _p(ms)))
+        return {n: float(ms[i]) for i, n in enumerate(B.STAGE_NAMES)}

@@ -1,0 +1,103 @@
+"""Seeded synthetic inputs of the BASELINE.json configurations and hash-function generation.
+
+Hash functions are *inputs* to the native library (the reference draws them from an unseeded RNG,
+AngleHashFamily.scala:29, so they are not reproducible from config; quirk Q7).  `angle_family` is the host-side
+analogue of AngleHashFamily.initHashFamily + pick (AngleHashFamily.scala:37-64, 121-149): U[0,1) magnitudes with a
+random sign, L2-normalised; chains drawn with replacement from the family; permuted tables are shuffles of the
+base chain.
+"""
+import numpy as np
+
+
+def angle_family(d, family_size, table_num, permutation_num, k, seed, by_pulling=True):
+    """Returns (A[P x d], chain_idx[L x k]) with L = table_num * permutation_num."""
+    rng = np.random.default_rng(seed)
+
+    def unit_vectors(m):
+        v = rng.random((m, d))
+        v[v == 0.0] = 0.5                                   # functions must be fully dense (SimilarityCalculator.scala:43)
+        sign = rng.integers(0, 2, (m, d)) > 0
+        v = np.where(sign, v, -v)
+        return v / np.sqrt((v * v).sum(1, keepdims=True))
+
+    if by_pulling:
+        A = unit_vectors(family_size)
+        base = rng.integers(0, family_size, (table_num, k))
+    else:
+        A = unit_vectors(table_num * k)
+        base = np.arange(table_num * k).reshape(table_num, k)
+    chain = np.empty((table_num * permutation_num, k), np.int32)
+    for t in range(table_num):
+        for p in range(permutation_num):
+            chain[permutation_num * t + p] = rng.permutation(base[t])   # rd.shuffle(hashFunctionChain)
+    # keep only the functions that are used, renumbered densely
+    used, inv = np.unique(chain, return_inverse=True)
+    return np.ascontiguousarray(A[used]), inv.reshape(chain.shape).astype(np.int32)
+
+
+def partitioner_family(L, pb, seed):
+    """L private partitioners of pb 32-d functions each (DensevectorRDFInit.scala:63-77)."""
+    rng = np.random.default_rng(seed)
+    v = rng.random((L, pb, 32))
+    v[v == 0.0] = 0.5
+    v = np.where(rng.integers(0, 2, v.shape) > 0, v, -v)
+    return v / np.sqrt((v * v).sum(-1, keepdims=True))
+
+
+def clustered_dense(n, d, seed, centres, spread=0.35, lo=None, hi=None, integer=False, chunk=1 << 18):
+    """n x d FP64 rows: centre + spread * N(0, I); optionally mapped to [lo, hi] and rounded."""
+    rng = np.random.default_rng(seed)
+    C = rng.standard_normal((centres, d))
+    X = np.empty((n, d), np.float64)
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        X[s:s + m] = C[rng.integers(0, centres, m)] + spread * rng.standard_normal((m, d))
+    if lo is not None:
+        mn, mx = -4.0, 4.0
+        X = np.clip((X - mn) / (mx - mn), 0.0, 1.0) * (hi - lo) + lo
+        if integer:
+            X = np.rint(X)
+    return X
+
+
+def config1(n=20000, d=100):
+    """TestSingleRDFSuite 'simple test' shape: 20k x 100-d, 2 queries ~U[0,1)^100 (README.md:32-42)."""
+    X = clustered_dense(n, d, 1001, 200)
+    Q = np.random.default_rng(1001 + 7).random((2, d))
+    return X, Q
+
+
+def config2(n=1_000_000, nq=10_000, d=128):
+    """SIFT shape: non-negative integer-valued doubles in [0, 218]; queries are held-out draws."""
+    X = clustered_dense(n + nq, d, 1002, 1000, lo=0.0, hi=218.0, integer=True)
+    return X[:n], X[n:]
+
+
+def config3(n=1_000_000, nq=1000, d=960):
+    X = clustered_dense(n + nq, d, 1003, 1000, lo=0.0, hi=1.0)
+    return X[:n], X[n:]
+
+
+def config4_csr(n=2_000_000, D=100_000, mean_nnz=60, seed=1004, chunk=1 << 16):
+    """Sparse rows: nnz ~ Poisson(60) clipped >= 1, Zipf(1.1)-distributed distinct indices sorted ascending,
+    values ~U(0,1] L2-normalised.  Returns (indptr int64, indices int32, values f64)."""
+    rng = np.random.default_rng(seed)
+    nnz = np.maximum(rng.poisson(mean_nnz, n), 1).astype(np.int64)
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(nnz, out=indptr[1:])
+    indices = np.empty(indptr[-1], np.int32)
+    values = np.empty(indptr[-1], np.float64)
+    # Zipf over a fixed random relabelling of the features; duplicates inside a row are re-drawn uniformly
+    perm = rng.permutation(D)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        for i in range(s, e):
+            m = int(nnz[i])
+            idx = np.unique(perm[np.minimum(rng.zipf(1.1, m + 8) - 1, D - 1)])
+            while len(idx) < m:
+                idx = np.unique(np.concatenate([idx, rng.integers(0, D, m - len(idx))]))
+            idx = np.sort(rng.choice(idx, m, replace=False)) if len(idx) > m else idx
+            v = 1.0 - rng.random(m)
+            indices[indptr[i]:indptr[i + 1]] = idx
+            values[indptr[i]:indptr[i + 1]] = v / np.sqrt((v * v).sum())
+    return indptr, indices, values

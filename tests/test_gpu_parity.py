@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+Bit-exact for keys, partition ids, bucket membership and candidate sets; ids exact / scores within 1e-12 relative
+for the re-rank (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from similaritysearchbyrdf_b200 import _lib as B
+from similaritysearchbyrdf_b200 import synth
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    X, Q = synth.config1()
+    A, chain, Ap = U.make_functions(100)
+    return X, Q, A, chain, Ap
+
+
+# ---- K1: keys and partition ids -------------------------------------------------------------------------------
+def test_hash_dense_config1_bit_exact(cfg1):
+    X, Q, A, chain, Ap = cfg1
+    o, ix = U.make_oracle(100, A, chain, Ap), U.make_index(100, A, chain, Ap)
+    ko, po = o.hash_dense(X)
+    kg, pg = ix.hash_dense(X)
+    assert np.array_equal(ko, kg)
+    assert np.array_equal(po, pg)
+    print("near-zero fix-ups:", ix.stats()["near_zero_fixups"])
+
+
+def test_hash_dense_pinned_reference_family(golden_dir):
+    # the reference's own pinned functions: 10 tables x 32 functions, 100-d, 98 distinct ids
+    g = np.load(os.path.join(golden_dir, "angle_family_tablenum10.npz"))
+    ids, rows = g["ids"], g["rows"]
+    uniq, first, inv = np.unique(ids, return_index=True, return_inverse=True)
+    A = rows[first]
+    chain = inv.reshape(10, 32).astype(np.int32)
+    Ap = synth.partitioner_family(10, 3, 5)
+    X, _ = synth.config1(n=5000)
+    o, ix = U.make_oracle(100, A, chain, Ap), U.make_index(100, A, chain, Ap)
+    ko, po = o.hash_dense(X)
+    kg, pg = ix.hash_dense(X)
+    assert np.array_equal(ko, kg) and np.array_equal(po, pg)
+
+
+@pytest.mark.parametrize("d,n", [(1, 7), (3, 65), (33, 130), (96, 1000), (128, 2049), (960, 300)])
+def test_hash_dense_shapes(d, n):
+    A, chain, Ap = U.make_functions(d, family_size=max(40, d), table_num=4, permutation_num=2, seed=d)
+    X = np.random.default_rng(d).standard_normal((n, d))
+    o, ix = U.make_oracle(d, A, chain, Ap), U.make_index(d, A, chain, Ap)
+    ko, po = o.hash_dense(X)
+    kg, pg = ix.hash_dense(X)
+    assert np.array_equal(ko, kg) and np.array_equal(po, pg)
+
+
+def test_hash_dense_near_zero_projections_are_fixed_up():
+    # vectors built to be (numerically) orthogonal to some functions: the DMMA sum and the reference's sequential
+    # unfused sum can land on different sides of zero; the fix-up must make the signs exact
+    d = 64
+    A, chain, Ap = U.make_functions(d, family_size=64, table_num=3, permutation_num=1, seed=3)
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((4000, d))
+    for i in range(0, 4000, 2):
+        a = A[rng.integers(0, A.shape[0])]
+        X[i] -= (X[i] @ a) / (a @ a) * a          # projection ~ 1e-17 .. 1e-16
+    X[1] = 0.0                                      # exact zeros -> bit 0 everywhere
+    o, ix = U.make_oracle(d, A, chain, Ap), U.make_index(d, A, chain, Ap)
+    ko, _ = o.hash_dense(X)
+    kg, _ = ix.hash_dense(X)
+    assert np.array_equal(ko, kg)
+    assert ix.stats()["near_zero_fixups"] > 0
+
+
+@pytest.mark.parametrize("transform", ["sampling", "continueBitsCount", "angleNewMethod"])
+def test_hash_key_transforms(cfg1, transform):
+    X, Q, A, chain, Ap = cfg1
+    kt = O.TRANSFORMS[transform]
+    o = U.make_oracle(100, A, chain, Ap, key_transform=kt)
+    ix = U.make_index(100, A, chain, Ap, key_transform=kt)
+    ko, po = o.hash_dense(X[:3000])
+    kg, pg = ix.hash_dense(X[:3000])
+    assert np.array_equal(ko, kg) and np.array_equal(po, pg)
+
+
+def test_hash_pstable_family():
+    d, L, k = 24, 3, 32
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((L * k, d))
+    chain = np.arange(L * k, dtype=np.int32).reshape(L, k)
+    b = rng.random(L * k) * 4
+    w = np.full(L * k, 4, np.int32)
+    Ap = synth.partitioner_family(L, 3, 2)
+    X = rng.standard_normal((3000, d)) * 3
+    o = U.make_oracle(d, A, chain, Ap, family_kind=1, b=b, w=w)
+    ix = U.make_index(d, A, chain, Ap, family_kind=1, b=b, w=w)
+    ko, po = o.hash_dense(X)
+    kg, pg = ix.hash_dense(X)
+    assert np.array_equal(ko, kg) and np.array_equal(po, pg)
+
+
+def _small_csr(n, D, seed, mean=12):
+    rng = np.random.default_rng(seed)
+    nnz = np.maximum(rng.poisson(mean, n), 1)
+    nnz[0] = 1
+    indptr = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
+    idx = np.concatenate([np.sort(rng.choice(D, m, replace=False)) for m in nnz]).astype(np.int32)
+    val = rng.random(indptr[-1]) + 0.01
+    return indptr, idx, val
+
+
+def test_hash_csr_bit_exact():
+    D = 500
+    A, chain, Ap = U.make_functions(D, family_size=100, table_num=10, permutation_num=3, seed=21)
+    indptr, idx, val = _small_csr(4000, D, 22)
+    o, ix = U.make_oracle(D, A, chain, Ap), U.make_index(D, A, chain, Ap)
+    ko, po = o.hash_csr(indptr, idx, val)
+    kg, pg = ix.hash_csr(indptr, idx, val)
+    assert np.array_equal(ko, kg) and np.array_equal(po, pg)
+
+
+# ---- K3: bucket membership -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("T", [500, 40, 4])
+def test_build_bucket_membership_config1(cfg1, T):
+    X, Q, A, chain, Ap = cfg1
+    o = U.make_oracle(100, A, chain, Ap, bucket_overflow=T)
+    ix = U.make_index(100, A, chain, Ap, bucket_overflow=T)
+    o.fit_dense(X)
+    ix.fit_dense(X)
+    U.assert_buckets_equal(o, ix, chain.shape[0])
+    so, sg = o.stats(), ix.stats()
+    assert so["splits"] == sg["splits"] and so["singleton_splits"] == sg["singleton_splits"]
+    assert np.allclose(so["occupancy"], sg["occupancy"])
+
+
+@pytest.mark.parametrize("dir_node_size,T", [(128, 4), (64, 3), (4, 2), (2, 1)])
+def test_build_skewed_keys_order_dependent_splits(dir_node_size, T):
+    # few distinct directions => heavy key collisions => the c0 bookkeeping of the split rule is exercised
+    d = 8
+    A, chain, Ap = U.make_functions(d, family_size=16, table_num=3, permutation_num=2, seed=5)
+    rng = np.random.default_rng(6)
+    C = rng.standard_normal((12, d))
+    X = C[rng.integers(0, 12, 6000)] + 0.02 * rng.standard_normal((6000, d))
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=T, dir_node_size=dir_node_size)
+    ix = U.make_index(d, A, chain, Ap, bucket_overflow=T, dir_node_size=dir_node_size)
+    o.fit_dense(X)
+    ix.fit_dense(X)
+    U.assert_buckets_equal(o, ix, chain.shape[0])
+    assert o.stats()["splits"] == ix.stats()["splits"] > 0
+    assert o.stats()["singleton_splits"] == ix.stats()["singleton_splits"]
+
+
+def test_build_append_equals_sequential_insertion(cfg1):
+    X, Q, A, chain, Ap = cfg1
+    o = U.make_oracle(100, A, chain, Ap, bucket_overflow=6)
+    ix = U.make_index(100, A, chain, Ap, bucket_overflow=6)
+    o.fit_dense(X[:3000]); o.fit_dense(X[3000:5000])
+    ix.fit_dense(X[:3000]); ix.fit_dense(X[3000:5000])
+    assert len(ix) == 5000
+    U.assert_buckets_equal(o, ix, chain.shape[0])
+
+
+# ---- K4: candidate sets --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("steps", [0, 1, 2, 3])
+def test_candidates_dense_multiprobe(cfg1, steps):
+    X, Q, A, chain, Ap = cfg1
+    o = U.make_oracle(100, A, chain, Ap, bucket_overflow=40)
+    ix = U.make_index(100, A, chain, Ap, bucket_overflow=40)
+    o.fit_dense(X); ix.fit_dense(X)
+    Qs = np.concatenate([Q, X[:200]])
+    qids = np.concatenate([[0, 1], np.arange(200)]).astype(np.int32)     # README: query ids 0,1
+    U.assert_csr_equal(o.query_candidates_dense(Qs, qids, steps), ix.query_candidates_dense(Qs, qids, steps))
+    assert o.stats()["nlz_gt28"] == ix.stats()["nlz_gt28"]
+
+
+def test_candidates_self_exclusion_quirk(cfg1):
+    X, Q, A, chain, Ap = cfg1
+    o = U.make_oracle(100, A, chain, Ap); ix = U.make_index(100, A, chain, Ap)
+    o.fit_dense(X[:5000]); ix.fit_dense(X[:5000])
+    qids = np.array([5, 127, 128, 4000], np.int32)
+    co = o.query_candidates_dense(X[qids], qids, 0)
+    cg = ix.query_candidates_dense(X[qids], qids, 0)
+    U.assert_csr_equal(co, cg)
+    sets = U.csr_sets(*cg)
+    assert 5 not in sets[0] and 127 not in sets[1]          # inside the Integer cache: excluded
+    assert 128 in sets[2] and 4000 in sets[3]               # outside: the query finds itself
+
+
+def test_candidates_by_id_and_no_probe(cfg1):
+    X, Q, A, chain, Ap = cfg1
+    o = U.make_oracle(100, A, chain, Ap, bucket_overflow=40); ix = U.make_index(100, A, chain, Ap, bucket_overflow=40)
+    o.fit_dense(X); ix.fit_dense(X)
+    qids = np.arange(0, 20000, 97, dtype=np.int32)
+    for steps in (0, 2):
+        U.assert_csr_equal(o.query_candidates_by_id(qids, steps), ix.query_candidates_by_id(qids, steps))
+        U.assert_csr_equal(o.query_candidates_dense(X[qids], qids, steps, O.PROBE_NONE),
+                           ix.query_candidates_dense(X[qids], qids, steps, B.PROBE_NONE))
+
+
+def test_candidates_csr_path():
+    D = 500
+    A, chain, Ap = U.make_functions(D, family_size=100, table_num=10, permutation_num=3, seed=21)
+    indptr, idx, val = _small_csr(6000, D, 23)
+    o = U.make_oracle(D, A, chain, Ap, bucket_overflow=20); ix = U.make_index(D, A, chain, Ap, bucket_overflow=20)
+    o.fit_csr(indptr, idx, val); ix.fit_csr(indptr, idx, val)
+    U.assert_buckets_equal(o, ix, chain.shape[0])
+    qp, qi, qv = _small_csr(64, D, 24)
+    for steps in (0, 1):
+        U.assert_csr_equal(o.query_candidates_csr(qp, qi, qv, None, steps), ix.query_candidates_csr(qp, qi, qv, None, steps))
+    qids = np.arange(0, 6000, 61, dtype=np.int32)
+    U.assert_csr_equal(o.query_candidates_by_id(qids, 1), ix.query_candidates_by_id(qids, 1))
+
+
+# ---- K5: re-rank / top-k -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2])
+@pytest.mark.parametrize("topk", [10, 100])
+def test_topk_parity(cfg1, metric, topk):
+    X, Q, A, chain, Ap = cfg1
+    o = U.make_oracle(100, A, chain, Ap); ix = U.make_index(100, A, chain, Ap)
+    o.fit_dense(X); ix.fit_dense(X)
+    Qs = np.concatenate([Q, X[1000:1100] + 0.01])
+    io, so = o.query_topk_dense(Qs, None, 1, topk, metric)
+    ig, sg = ix.query_topk_dense(Qs, None, 1, topk, metric)
+    U.assert_topk_close(io, so, ig, sg)
+
+
+def test_rerank_given_same_candidates_odd_dim():
+    d = 33
+    A, chain, Ap = U.make_functions(d, family_size=40, table_num=4, permutation_num=1, seed=8)
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((3000, d))
+    o = U.make_oracle(d, A, chain, Ap); ix = U.make_index(d, A, chain, Ap)
+    o.fit_dense(X); ix.fit_dense(X)
+    Q = rng.standard_normal((16, d))
+    off = np.arange(0, 17 * 150, 150, dtype=np.int64)
+    cand = np.concatenate([np.sort(rng.choice(3000, 150, replace=False)) for _ in range(16)]).astype(np.int32)
+    off[1] = off[0]                                           # an empty candidate set -> padded row
+    for metric in (0, 1, 2):
+        io, so = o.rerank_dense(Q, off, cand, 10, metric)
+        ig, sg = ix.rerank_dense(Q, off, cand, 10, metric)
+        U.assert_topk_close(io, so, ig, sg)
+        assert (ig[0] == -1).all() and np.isnan(sg[0]).all()
+
+
+# ---- error behaviour -----------------------------------------------------------------------------------------
+def test_error_codes():
+    from similaritysearchbyrdf_b200 import DPFIndex
+    ix = DPFIndex(d=4, L=2, k=32)
+    with pytest.raises(B.DpfError) as e:
+        ix.fit_dense(np.zeros((3, 4)))                        # family not set
+    assert e.value.code == B.ERR_STATE
+    A, chain, Ap = U.make_functions(4, family_size=40, table_num=2, permutation_num=1)
+    ix.set_family(A, chain); ix.set_partitioners(Ap)
+    with pytest.raises(B.DpfError) as e:
+        ix.query_topk_dense(np.zeros((1, 4)))                 # "need to fit the data first"
+    assert e.value.code == B.ERR_STATE
+    ix.fit_dense(np.random.default_rng(0).standard_normal((100, 4)))
+    with pytest.raises(B.DpfError) as e:
+        ix.query_candidates_by_id(np.array([100], np.int32))  # unknown id
+    assert e.value.code == B.ERR_INVALID
