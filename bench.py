@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DPF hot path on B200 (contract: see the task statement / DESIGN.md).
+
+Metric (BASELINE.json): batch kNN queries/s at fixed recall@10 (+ index build vectors/s as extra keys).
+Workload at every N: BASELINE.json configs[1] — 1M x 128-d synthetic dense vectors (SIFT shape), 10k-query
+batch, k=10, steps=0, reference test defaults (L=30 tables, k=32 bits, 8 sub-indexes, T=500).
+A "step" = one pass of the whole query batch through hash -> probe -> de-dup -> gather/re-rank -> top-k
+(for N>1: + NCCL all-gather of the per-GPU top-k and the merge kernel).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC_NAME = "batch kNN queries/sec at fixed recall@10"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--qsteps", type=int, default=0, help="multi-step sub-index search radius (reference `steps`)")
+    ap.add_argument("--metric", default="dot", choices=["dot", "angular", "l2"])
+    ap.add_argument("--cpu-sample", type=int, default=512, help="queries in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from similaritysearchbyrdf_b200 import synth
+    t0 = time.time()
+    X, Q = synth.config2(args.n, args.nq, args.d)
+    A, chain = synth.angle_family(args.d, max(100, args.d), 10, 3, 32, 88387 + 2)
+    Ap = synth.partitioner_family(chain.shape[0], 3, 88387 + 3)
+    return X, Q, A, chain, Ap, time.time() - t0
+
+
+def config_dict(args, n_gpus):
+    return {
+        "workload": "configs[1]: 1M x 128-d synthetic dense (SIFT shape), 10k-query batch, k=10",
+        "n_vectors": args.n, "dim": args.d, "n_queries": args.nq, "topk": args.topk, "steps": args.qsteps,
+        "rerank_metric": args.metric, "tables": 30, "chain_length": 32, "partition_bits": 3, "bucket_overflow": 500,
+        "dir_node_size": 32, "probe": "dense multi-probe",
+        "partitioning": f"sub-indexes p%{n_gpus}==rank per GPU, vectors replicated" if n_gpus > 1 else "single GPU",
+        "cache": "inputs larger than L2 (vector store 1.0 GB vs 126 MB L2); no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_arm(args, X, Q, A, chain, Ap, sample, steps, warmup):
+    """Builds the full index with the CPU oracle, then times `steps` passes over a bounded query sample."""
+    from oracle import oracle_py as O
+    metric = {"dot": 0, "angular": 1, "l2": 2}[args.metric]
+    cores = os.cpu_count() or 1
+    o = O.Oracle(d=args.d, L=chain.shape[0], k=chain.shape[1], P=A.shape[0], pb=Ap.shape[1])
+    o.set_family(A, chain)
+    o.set_partitioners(Ap)
+    t0 = time.time()
+    o.fit_dense(X, nthreads=cores)
+    build_s = time.time() - t0
+    Qs = np.ascontiguousarray(Q[:sample])
+    for _ in range(warmup):
+        o.query_topk_dense(Qs[: max(8, sample // 8)], None, args.qsteps, args.topk, metric, nthreads=cores)
+    t0 = time.time()
+    for _ in range(steps):
+        ids, _ = o.query_topk_dense(Qs, None, args.qsteps, args.topk, metric, nthreads=cores)
+    dt = (time.time() - t0) / steps
+    return {"qps": sample / dt, "ms_per_step": dt * 1e3, "build_vectors_per_s": len(X) / build_s, "cores": cores,
+            "sample": f"{sample} of the {len(Q)} queries per step against the full {len(X)}-vector index "
+                      f"(index built by the same oracle in {build_s:.1f} s)", "ids": ids}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, Q, A, chain, Ap, _ = workload(args)
+    r = cpu_arm(args, X, Q, A, chain, Ap, min(args.cpu_sample, args.nq), args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": r["qps"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, 1),
+        "cpu_baseline": {"value": r["qps"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                         "note": "C++ restatement of the reference algorithm (no JVM in the image); omits the "
+                                 "reference's (de)serialisation/boxing, so it is faster than the JVM path"},
+        "e2e": {"value": r["qps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "build_vectors_per_s": r["build_vectors_per_s"], "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.gpu_id, self.rows, self.proc = gpu_id, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_id), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from similaritysearchbyrdf_b200 import DPFIndex
+    from similaritysearchbyrdf_b200 import _lib as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    metric = {"dot": B.METRIC_DOT, "angular": B.METRIC_ANGULAR, "l2": B.METRIC_L2}[args.metric]
+
+    X, Q, A, chain, Ap, gen_s = workload(args)
+    n, nq, d, K = args.n, args.nq, args.d, args.topk
+    stream = torch.cuda.Stream(device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        Xd = torch.from_numpy(X).to(dev)
+        Qd = torch.from_numpy(Q).to(dev)
+        ix = DPFIndex(d=d, L=chain.shape[0], k=chain.shape[1], pb=Ap.shape[1], device=local, rank=rank, world=world)
+        ix.set_family(A, chain)
+        ix.set_partitioners(Ap)
+        ix.set_stream(stream.cuda_stream)
+        ix.set_profiling(True)
+
+        # ---- index build (inputs resident in HBM), device-timed ------------------------------------------------
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ix.fit_dense_dev(Xd.data_ptr(), n)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        build_ms = e0.elapsed_time(e1)
+        build_stage = ix.stage_times_ms()
+        bstats = ix.stats()
+
+        ids_d = torch.empty((nq, K), dtype=torch.int32, device=dev)
+        sc_d = torch.empty((nq, K), dtype=torch.float64, device=dev)
+        if world > 1:
+            g_ids = torch.empty((world, nq, K), dtype=torch.int32, device=dev)
+            g_sc = torch.empty((world, nq, K), dtype=torch.float64, device=dev)
+            m_ids = torch.empty((nq, K), dtype=torch.int32, device=dev)
+            m_sc = torch.empty((nq, K), dtype=torch.float64, device=dev)
+
+        def step_device():
+            ix.query_topk_dense_dev(Qd.data_ptr(), nq, 0, args.qsteps, K, metric, ids_d.data_ptr(), sc_d.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(g_ids, ids_d)
+                dist.all_gather_into_tensor(g_sc, sc_d)
+                ix.merge_topk_dev(g_ids.data_ptr(), g_sc.data_ptr(), world, nq, K, metric, m_ids.data_ptr(),
+                                  m_sc.data_ptr())
+
+        # ---- value: device-resident steps ---------------------------------------------------------------------
+        for _ in range(args.warmup):
+            step_device()
+        launches0 = ix.stats()["kernel_launches"]
+        uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
+        clocks = ClockSampler(f"GPU-{uuid}" if uuid is not None else local)
+        barrier()
+        clocks.start()
+        rerank_ms, stage_acc = [], {}
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+            st = ix.stage_times_ms()           # events recorded on the launching stream; call syncs the stream
+            rerank_ms.append(st["rerank"])
+            for k_, v in st.items():
+                stage_acc[k_] = stage_acc.get(k_, 0.0) + v / args.steps
+        e1.record(stream)
+        barrier()
+        clk = clocks.stop()
+        dt_ms = e0.elapsed_time(e1)
+        launches = (ix.stats()["kernel_launches"] - launches0) // max(args.steps, 1)
+        t = torch.tensor([dt_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item()) / args.steps
+        qstats = ix.stats()
+        result_ids = (m_ids if world > 1 else ids_d).cpu().numpy()
+
+        # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region ----------
+        Qh = torch.from_numpy(Q).pin_memory()
+        ids_h = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+        sc_h = torch.empty((nq, K), dtype=torch.float64).pin_memory()
+        Qh_np, ids_np, sc_np = Qh.numpy(), ids_h.numpy(), sc_h.numpy()
+
+        def step_e2e():
+            if world == 1:
+                rc = ix.lib.dpf_query_topk_dense(ix.h, Qh_np.ctypes.data, nq, None, args.qsteps, B.PROBE_DENSE, K, metric,
+                                                 ids_np.ctypes.data, sc_np.ctypes.data)
+                ix._ck(rc)
+            else:
+                Qd.copy_(Qh, non_blocking=True)
+                step_device()
+                ids_h.copy_(m_ids, non_blocking=True)
+                sc_h.copy_(m_sc, non_blocking=True)
+                stream.synchronize()
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item()) / args.steps
+
+        # ---- e2e build through the host API (fresh index, host buffer) -----------------------------------------
+        e2e_build_ms = None
+        if world == 1:
+            ix2 = DPFIndex(d=d, L=chain.shape[0], k=chain.shape[1], pb=Ap.shape[1], device=local)
+            ix2.set_family(A, chain)
+            ix2.set_partitioners(Ap)
+            ix2.set_stream(stream.cuda_stream)
+            Xh = torch.from_numpy(X).pin_memory()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ix2.fit_dense(Xh.numpy())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            e2e_build_ms = e0.elapsed_time(e1)
+            ix2.close()
+            del Xh
+
+        # ---- recall@10 against exact FP64 brute force (outside every timed region) -----------------------------
+        recall = None
+        if rank == 0:
+            hits = 0
+            for s in range(0, nq, 500):
+                qb = Qd[s:s + 500]
+                if args.metric == "l2":
+                    sc = -(torch.cdist(qb, Xd) ** 2)
+                else:
+                    sc = qb @ Xd.T
+                    if args.metric == "angular":
+                        sc = sc / (Xd.norm(dim=1)[None, :] * qb.norm(dim=1)[:, None])
+                gt = sc.topk(K, dim=1).indices.cpu().numpy()
+                got = result_ids[s:s + 500]
+                hits += sum(len(set(gt[i]) & set(got[i])) for i in range(len(gt)))
+                del sc
+            recall = hits / (nq * K)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_rerank_topk: candidate gather + FP64 re-rank + top-k) -------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ncand_unique = int(qstats["last_candidates"])     # unique candidates of one batch (device counter)
+    alg_bytes = ncand_unique * (8 * d + 4)
+    rr_ms = float(np.mean(rerank_ms)) if rerank_ms else None
+    achieved = alg_bytes / (rr_ms * 1e-3) / 1e9 if rr_ms else None
+    roofline = {"kernel": "k_rerank_topk", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": rr_ms,
+                "unique_candidates_per_query": ncand_unique / nq,
+                "step_share": rr_ms / ms_per_step if rr_ms else None}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(args, X, Q, A, chain, Ap, min(args.cpu_sample, nq), 1, 1)
+        agree = float(np.mean([len(set(r["ids"][i]) & set(result_ids[i])) / K for i in range(len(r["ids"]))]))
+        cpu = {"value": r["qps"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "build_vectors_per_s": r["build_vectors_per_s"], "topk_overlap_with_gpu": agree}
+
+    line = {
+        "metric": METRIC_NAME, "value": nq / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+        "recall_at_10": recall, "clocks": clk,
+        "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nq * d * 8),
+                "d2h_bytes_per_step": int(nq * K * 12), "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "build": {"vectors_per_s": n / (build_ms * 1e-3), "ms": build_ms, "stage_ms": build_stage,
+                  "e2e_vectors_per_s": n / (e2e_build_ms * 1e-3) if e2e_build_ms else None,
+                  "near_zero_fixups": bstats["near_zero_fixups"], "splits": bstats["splits"],
+                  "singleton_splits": bstats["singleton_splits"], "dir_nodes": bstats["dir_nodes"]},
+        "query_stage_ms": stage_acc, "candidates_with_dups_per_query": qstats["last_cand_with_dups"] / nq,
+        "datagen_s": gen_s,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

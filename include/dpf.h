@@ -70,6 +70,9 @@ int dpf_destroy(dpf_handle h);                       /* clearAndClose (Densevect
 const char* dpf_last_error(dpf_handle h);
 const char* dpf_strerror(int code);
 int dpf_sync(dpf_handle h);
+/* run the handle's work on the caller's CUDA stream (cudaStream_t; e.g. torch.cuda.current_stream().cuda_stream)
+ * so that the caller's CUDA events bracket it; NULL restores the handle's own stream */
+int dpf_set_stream(dpf_handle h, void* cuda_stream);
 
 /* ---- hash functions: inputs, generated/loaded on the host side (AngleHashFamily.scala:121-177) ---------- */
 /* A: P x d row-major distinct functions; chain_idx: L x k -> row of A (tableIndexGenerators, LSH.scala:27);
@@ -146,6 +149,7 @@ enum {
     DPF_STAT_NLZ_GT28 = 5,         /* (query,table) pairs with nlz(h) > 28 (quirk Q4), last query            */
     DPF_STAT_LAST_CANDIDATES = 6,  /* unique candidates of the last query batch                              */
     DPF_STAT_LAST_CAND_WITH_DUPS = 7, /* bucket entries visited by the last query batch                      */
+    DPF_STAT_KERNEL_LAUNCHES = 8,  /* kernels launched by this library in this process (cumulative)          */
     DPF_STAT_COUNT = 16
 };
 int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occupancy_out /* 2^pb or NULL */);

@@ -14,12 +14,12 @@ METRIC_DOT, METRIC_ANGULAR, METRIC_L2 = 0, 1, 2
 PROBE_NONE, PROBE_DENSE = 0, 1
 STAT_COUNT, T_COUNT = 16, 16
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
-              "last_cand_with_dups"]
+              "last_cand_with_dups", "kernel_launches"]
 STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort"]
 
 # every symbol include/dpf.h declares
 EXPORTS = [
-    "dpf_create", "dpf_destroy", "dpf_last_error", "dpf_strerror", "dpf_sync", "dpf_set_family",
+    "dpf_create", "dpf_destroy", "dpf_last_error", "dpf_strerror", "dpf_sync", "dpf_set_stream", "dpf_set_family",
     "dpf_set_partitioners", "dpf_hash_dense", "dpf_hash_csr", "dpf_fit_dense", "dpf_fit_csr", "dpf_fit_dense_dev",
     "dpf_size", "dpf_query_candidates_dense", "dpf_query_candidates_csr", "dpf_query_candidates_by_id",
     "dpf_query_topk_dense", "dpf_query_topk_dense_dev", "dpf_rerank_dense", "dpf_merge_topk_dev", "dpf_dump_buckets",
@@ -60,6 +60,7 @@ def load():
     L.dpf_strerror.restype = C.c_char_p
     L.dpf_strerror.argtypes = [C.c_int]
     L.dpf_sync.argtypes = [vp]
+    L.dpf_set_stream.argtypes = [vp, vp]
     L.dpf_set_family.argtypes = [vp, vp, i32, vp, vp, vp]
     L.dpf_set_partitioners.argtypes = [vp, vp]
     L.dpf_hash_dense.argtypes = [vp, vp, i64, vp, vp]

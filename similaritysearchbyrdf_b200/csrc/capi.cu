@@ -9,6 +9,10 @@
 
 using namespace dpf;
 
+namespace dpf {
+unsigned long long g_launches = 0;
+}
+
 namespace {
 
 int ilog2_exact(int v) {
@@ -40,13 +44,19 @@ int guarded(dpf_handle h, F&& f) {
 
 void begin_profile(dpf_index* h) {
     if (!h->profiling) return;
-    for (int i = 0; i < DPF_T_COUNT; ++i) { h->ev_used[i] = false; h->stage_ms[i] = 0.f; }
+    h->ev_used = 0;
+    for (int i = 0; i < DPF_T_COUNT; ++i) h->stage_ms[i] = 0.f;
 }
 void end_profile(dpf_index* h) {
-    if (!h->profiling) return;
+    if (!h->profiling || h->ev_used == 0) return;
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < DPF_T_COUNT; ++i)
-        if (h->ev_used[i]) cudaEventElapsedTime(&h->stage_ms[i], h->ev[2 * i], h->ev[2 * i + 1]);
+    for (int i = 0; i < DPF_T_COUNT; ++i) h->stage_ms[i] = 0.f;
+    for (size_t s = 0; s < h->ev_used; ++s) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[2 * s], h->ev_pool[2 * s + 1]) == cudaSuccess)
+            h->stage_ms[h->ev_stage[s]] += ms;
+    }
+    h->ev_used = 0;
 }
 
 template <class T>
@@ -103,15 +113,48 @@ void pids_to_host(dpf_index* h, const uint8_t* dev, int64_t count, int32_t* out)
     for (int64_t i = 0; i < count; ++i) out[i] = tmp[(size_t)i];
 }
 
-// shared tail of the candidate queries: CSR out to the host
-void emit_candidates(dpf_index* h, int64_t nq, int64_t* offsets_out, int32_t* ids_out, int64_t cap, int64_t* total_out) {
+constexpr int64_t kCandBudget = 1LL << 29;   // ids of candidate scratch per chunk of queries (2 GiB)
+
+// allocate the candidate scratch once for the largest chunk (a reallocation between chunks would serialise the
+// stream on cudaFree)
+void reserve_candidate_scratch(dpf_index* h, const std::vector<int64_t>& ub) {
+    const int64_t nq = (int64_t)ub.size() - 1;
+    int64_t mx = 1;
+    for (int64_t q0 = 0; q0 < nq;) {
+        const int64_t q1 = next_chunk_end(ub, q0, kCandBudget);
+        mx = std::max(mx, ub[(size_t)q1] - ub[(size_t)q0]);
+        q0 = q1;
+    }
+    h->cand.reserve((size_t)mx);
+}
+
+// shared body of the candidate queries: probe, then per memory-bounded chunk expand -> sort -> copy out (CSR)
+void run_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t* offsets_out, int32_t* ids_out,
+                    int64_t cap, int64_t* total_out) {
+    const int64_t nq = qk.nq;
+    std::vector<int64_t> ub;
+    probe_count_all(h, qk, steps, probe_mode, ub);
+    reserve_candidate_scratch(h, ub);
     DevBuf<int64_t> off;
     off.reserve(nq + 1);
-    const int64_t total = finalize_candidates_sorted(h, nq, off.p);
-    d2h(h, offsets_out, off.p, (size_t)nq + 1);
-    if (total_out) *total_out = total;
-    if (total <= cap && ids_out) d2h(h, ids_out, h->cand.p, (size_t)total);
+    int64_t total = 0;
+    for (int64_t q0 = 0; q0 < nq;) {
+        const int64_t q1 = next_chunk_end(ub, q0, kCandBudget);
+        const int64_t base = ub[(size_t)q0];
+        expand_range(h, qk, steps, probe_mode, q0, q1, base, ub[(size_t)q1] - base);
+        const int64_t tc = finalize_candidates_sorted(h, q0, q1, base, off.p);
+        if (ids_out && total + tc <= cap) d2h(h, ids_out + total, h->cand.p, (size_t)tc);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        total += tc;
+        q0 = q1;
+    }
+    std::vector<int32_t> cnt((size_t)nq);
+    d2h(h, cnt.data(), h->q_cnt.p, (size_t)nq);
     DPF_CUDA(cudaStreamSynchronize(h->stream));
+    offsets_out[0] = 0;
+    for (int64_t i = 0; i < nq; ++i) offsets_out[i + 1] = offsets_out[i] + cnt[(size_t)i];
+    h->stats[DPF_STAT_LAST_CANDIDATES] = total;
+    if (total_out) *total_out = total;
     DPF_REQUIRE(total <= cap, DPF_ERR_CAPACITY, "candidate buffer too small");
 }
 
@@ -168,7 +211,6 @@ int dpf_create(const dpf_config* cfg, dpf_handle* out) {
         DPF_CUDA(cudaSetDevice(cfg->device));
         DPF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         DPF_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-        for (int i = 0; i < 2 * DPF_T_COUNT; ++i) DPF_CUDA(cudaEventCreate(&h->ev[i]));
         h->counters.reserve(64);
         h->occupancy.assign(1 << cfg->pb, 0.0);
     } catch (const Error& e) {
@@ -186,8 +228,8 @@ int dpf_destroy(dpf_handle h) {
     if (!h) return DPF_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 2 * DPF_T_COUNT; ++i)
-        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) { h->stream = h->own_stream; h->own_stream = nullptr; }
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return DPF_OK;
@@ -197,6 +239,19 @@ const char* dpf_last_error(dpf_handle h) { return h ? h->last_error.c_str() : "n
 
 int dpf_sync(dpf_handle h) {
     return guarded(h, [&] { DPF_CUDA(cudaStreamSynchronize(h->stream)); });
+}
+
+int dpf_set_stream(dpf_handle h, void* cuda_stream) {
+    return guarded(h, [&] {
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        if (cuda_stream) {
+            if (!h->own_stream) h->own_stream = h->stream;
+            h->stream = (cudaStream_t)cuda_stream;
+        } else if (h->own_stream) {
+            h->stream = h->own_stream;
+            h->own_stream = nullptr;
+        }
+    });
 }
 
 int dpf_set_family(dpf_handle h, const double* A, int32_t P, const int32_t* chain_idx, const double* b, const int32_t* w) {
@@ -378,8 +433,8 @@ int dpf_query_candidates_dense(dpf_handle h, const double* Q, int64_t nq, const 
         begin_profile(h);
         upload_queries_dense(h, Q, nq, qids);
         hash_dense_any(h, h->qbuf.p, nq, h->qkeys.p, h->qpids.p, nq);
-        collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids ? h->qidbuf.p : nullptr}, steps, probe_mode);
-        emit_candidates(h, nq, offsets_out, ids_out, cap, total_out);
+        run_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids ? h->qidbuf.p : nullptr}, steps, probe_mode, offsets_out,
+                       ids_out, cap, total_out);
         end_profile(h);
     });
 }
@@ -409,8 +464,8 @@ int dpf_query_candidates_csr(dpf_handle h, const int64_t* indptr, const int32_t*
         h->qpids.reserve((size_t)L * nq);
         hash_csr_device(h, pd_.p, id_.p, vd.p, nq, h->qkeys.p, h->qpids.p, nq);
         // the sparse overload has steps but no probes (RandomDrawTreeMap.java:686-732, quirk Q5)
-        collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids ? h->qidbuf.p : nullptr}, steps, DPF_PROBE_NONE);
-        emit_candidates(h, nq, offsets_out, ids_out, cap, total_out);
+        run_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids ? h->qidbuf.p : nullptr}, steps, DPF_PROBE_NONE, offsets_out,
+                       ids_out, cap, total_out);
         end_profile(h);
     });
 }
@@ -427,8 +482,8 @@ int dpf_query_candidates_by_id(dpf_handle h, const int32_t* qids, int64_t nq, in
         h->qkeys.reserve((size_t)L * nq);
         h->qpids.reserve((size_t)L * nq);
         gather_query_keys(h, h->qidbuf.p, nq);
-        collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, h->qidbuf.p}, steps, DPF_PROBE_NONE);
-        emit_candidates(h, nq, offsets_out, ids_out, cap, total_out);
+        run_candidates(h, QueryKeys{h->qkeys.p, nq, nq, h->qidbuf.p}, steps, DPF_PROBE_NONE, offsets_out, ids_out, cap,
+                       total_out);
         end_profile(h);
     });
 }
@@ -439,8 +494,20 @@ static void topk_device(dpf_index* h, const double* Qd, int64_t nq, const int32_
     h->qkeys.reserve((size_t)L * nq);
     h->qpids.reserve((size_t)L * nq);
     hash_dense_any(h, Qd, nq, h->qkeys.p, h->qpids.p, nq);
-    collect_candidates(h, QueryKeys{h->qkeys.p, nq, nq, qids_dev}, steps, probe_mode);
-    rerank_topk(h, Qd, nq, h->q_off.p, h->q_cnt.p, h->cand.p, topk, metric, ids_out_dev, score_out_dev);
+    const QueryKeys qk{h->qkeys.p, nq, nq, qids_dev};
+    std::vector<int64_t> ub;
+    probe_count_all(h, qk, steps, probe_mode, ub);
+    reserve_candidate_scratch(h, ub);
+    for (int64_t q0 = 0; q0 < nq;) {   // memory-bounded chunks of queries: expand -> gather/re-rank/top-k
+        const int64_t q1 = next_chunk_end(ub, q0, kCandBudget);
+        const int64_t base = ub[(size_t)q0];
+        expand_range(h, qk, steps, probe_mode, q0, q1, base, ub[(size_t)q1] - base);
+        int64_t max_cnt = 1;
+        for (int64_t q = q0; q < q1; ++q) max_cnt = std::max(max_cnt, ub[(size_t)q + 1] - ub[(size_t)q]);
+        rerank_topk(h, Qd, q0, q1, base, h->q_off.p, h->q_cnt.p, h->cand.p, max_cnt, ub[(size_t)q1] - base, topk, metric,
+                    ids_out_dev, score_out_dev);
+        q0 = q1;
+    }
 }
 
 int dpf_query_topk_dense(dpf_handle h, const double* Q, int64_t nq, const int32_t* qids, int32_t steps,
@@ -496,7 +563,9 @@ int dpf_rerank_dense(dpf_handle h, const double* Q, int64_t nq, const int64_t* o
         counts_from_offsets(h, off.p, nq, cnt.p);
         h->out_ids.reserve((size_t)nq * topk);
         h->out_scores.reserve((size_t)nq * topk);
-        rerank_topk(h, h->qbuf.p, nq, off.p, cnt.p, cd.p, topk, metric, h->out_ids.p, h->out_scores.p);
+        int64_t max_cnt = 1;
+        for (int64_t q = 0; q < nq; ++q) max_cnt = std::max(max_cnt, offsets[q + 1] - offsets[q]);
+        rerank_topk(h, h->qbuf.p, 0, nq, 0, off.p, cnt.p, cd.p, max_cnt, total, topk, metric, h->out_ids.p, h->out_scores.p);
         d2h(h, ids_out, h->out_ids.p, (size_t)nq * topk);
         d2h(h, score_out, h->out_scores.p, (size_t)nq * topk);
         DPF_CUDA(cudaStreamSynchronize(h->stream));
@@ -557,6 +626,13 @@ int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
     return guarded(h, [&] {
         DPF_REQUIRE(stats_out, DPF_ERR_INVALID, "null buffer");
         h->stats[DPF_STAT_SIZE] = h->n;
+        if (h->fitted && h->counters.cap >= 32) {   // unique candidates of the last batch (device counter)
+            unsigned long long u = 0;
+            DPF_CUDA(cudaMemcpyAsync(&u, h->counters.p + 24, sizeof(u), cudaMemcpyDeviceToHost, h->stream));
+            DPF_CUDA(cudaStreamSynchronize(h->stream));
+            h->stats[DPF_STAT_LAST_CANDIDATES] = (int64_t)u;
+        }
+        h->stats[DPF_STAT_KERNEL_LAUNCHES] = (int64_t)g_launches;
         for (int i = 0; i < DPF_STAT_COUNT; ++i) stats_out[i] = h->stats[i];
         if (occupancy_out)
             for (size_t i = 0; i < h->occupancy.size(); ++i) occupancy_out[i] = h->occupancy[i];
@@ -570,7 +646,7 @@ int dpf_set_profiling(dpf_handle h, int32_t enable) {
 int dpf_stage_times_ms(dpf_handle h, float* ms_out) {
     return guarded(h, [&] {
         DPF_REQUIRE(ms_out, DPF_ERR_INVALID, "null buffer");
-        if (h->profiling) end_profile(h);
+        end_profile(h);
         for (int i = 0; i < DPF_T_COUNT; ++i) ms_out[i] = h->stage_ms[i];
     });
 }

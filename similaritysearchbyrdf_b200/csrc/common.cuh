@@ -92,6 +92,10 @@ struct ForestView {
 
 enum : int { kMaxTables = 256, kMaxChain = 32, kMaxPb = 8 };
 
+// process-wide count of kernel launches issued by this library (reported through dpf_stats)
+extern unsigned long long g_launches;
+#define DPF_LAUNCHED() (++::dpf::g_launches)
+
 }  // namespace dpf
 
 // ---------------------------------------------------------------------------------------------------------
@@ -102,7 +106,8 @@ struct dpf_index {
     dpf::TreeParams tp{};
     int P = 0;
     int PW = 0;  // sign words per vector = ceil(P/32)
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream all work of this handle runs on
+    cudaStream_t own_stream = nullptr;  // the handle's own stream while a caller stream is installed
     std::mutex mu;
     std::string last_error;
     bool family_set = false, part_set = false, dense = true, fitted = false;
@@ -158,33 +163,45 @@ struct dpf_index {
     dpf::DevBuf<int32_t> qidbuf, qkeys;
     dpf::DevBuf<uint8_t> qpids;
     dpf::DevBuf<int32_t> out_ids;
+    dpf::DevBuf<int32_t> ucnt, part_id;        // re-rank work units / partial top-k lists
+    dpf::DevBuf<int64_t> unit_off;
+    dpf::DevBuf<double> part_key;
     dpf::DevBuf<double> out_scores;
     dpf::DevBuf<char> stage;                   // generic staging
 
     // stats / profiling
     int64_t stats[DPF_STAT_COUNT] = {0};
     bool profiling = false;
-    cudaEvent_t ev[2 * DPF_T_COUNT] = {nullptr};
-    bool ev_used[DPF_T_COUNT] = {false};
+    std::vector<cudaEvent_t> ev_pool;          // event pairs; one pair per timed stage instance of the last call
+    std::vector<int> ev_stage;                 // stage id of pair i
+    size_t ev_used = 0;                        // pairs used by the current call
     float stage_ms[DPF_T_COUNT] = {0};
 };
 
 namespace dpf {
 
-// RAII stage timer: records CUDA events on the handle's stream around a stage when profiling is on
+// RAII stage timer: records a CUDA event pair on the handle's stream around a stage when profiling is on; a
+// stage that runs several times in one call (chunks) gets one pair per instance and the times are summed
 struct StageTimer {
     dpf_index* h;
-    int id;
-    StageTimer(dpf_index* h_, int id_) : h(h_), id(id_) {
-        if (h->profiling) {
-            cudaEventRecord(h->ev[2 * id], h->stream);
+    size_t slot = 0;
+    bool on;
+    StageTimer(dpf_index* h_, int id) : h(h_), on(h_->profiling) {
+        if (!on) return;
+        slot = h->ev_used++;
+        if (h->ev_pool.size() < 2 * (slot + 1)) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            h->ev_pool.push_back(a);
+            h->ev_pool.push_back(b);
+            h->ev_stage.push_back(id);
         }
+        h->ev_stage[slot] = id;
+        cudaEventRecord(h->ev_pool[2 * slot], h->stream);
     }
     ~StageTimer() {
-        if (h->profiling) {
-            cudaEventRecord(h->ev[2 * id + 1], h->stream);
-            h->ev_used[id] = true;
-        }
+        if (on) cudaEventRecord(h->ev_pool[2 * slot + 1], h->stream);
     }
 };
 
@@ -216,12 +233,14 @@ struct QueryKeys {
     int64_t nq;
     const int32_t* qids;   // device, may be null
 };
-// unique (unsorted) candidate lists: fills h->q_off (upper-bound offsets), h->q_cnt (unique counts), h->cand
-void collect_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode);
-// CSR with sorted unique ids on the device: out_off (nq+1), returns total; ids in h->cand compacted+sorted
-int64_t finalize_candidates_sorted(dpf_index* h, int64_t nq, int64_t* off_dev);
-void rerank_topk(dpf_index* h, const double* Qd, int64_t nq, const int64_t* off, const int32_t* cnt, const int32_t* cand,
-                 int topk, int metric, int32_t* ids_out, double* score_out);
+void probe_count_all(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, std::vector<int64_t>& off_host);
+int64_t next_chunk_end(const std::vector<int64_t>& off, int64_t q0, int64_t budget);
+void expand_range(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1, int64_t base,
+                  int64_t ub_chunk);
+int64_t finalize_candidates_sorted(dpf_index* h, int64_t q0, int64_t q1, int64_t base, int64_t* off_dev);
+void rerank_topk(dpf_index* h, const double* Qd, int64_t q0, int64_t q1, int64_t base, const int64_t* off,
+                 const int32_t* cnt, const int32_t* cand, int64_t max_cnt, int64_t total_ub, int topk, int metric,
+                 int32_t* ids_out, double* score_out);
 void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);
 void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt);
 void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,

@@ -203,7 +203,7 @@ void build_forest(dpf_index* h) {
         StageTimer tm(h, DPF_T_SORT);
         if (n > 0) {
             const dim3 grid((unsigned)((n + 255) / 256), L);
-            k_count_depth1<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, rank, world, cnt1.p);
+            k_count_depth1<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, rank, world, cnt1.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
         }
         exclusive_scan_i64(h, cnt1.p, start1.p, ncodes);
@@ -252,7 +252,7 @@ void build_forest(dpf_index* h) {
             h->sk0.reserve(items); h->sk1.reserve(items); h->sv0.reserve(items); h->sv1.reserve(items);
             const dim3 grid((unsigned)((n + 255) / 256), gt);
             k_make_sort_keys<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, t0, rank, world, field_bits, h->sk0.p,
-                                                   h->sv0.p);
+                                                   h->sv0.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             uint32_t *k0 = h->sk0.p, *k1 = h->sk1.p, *v0 = h->sv0.p, *v1 = h->sv1.p;
             const int64_t owned = h->h_table_base[t0 + gt] - h->h_table_base[t0];
@@ -286,7 +286,7 @@ void build_forest(dpf_index* h) {
         StageTimer tm(h, DPF_T_SPLIT);
         k_init_depth1<<<(unsigned)((ncodes + 255) / 256), 256, 0, st>>>(cnt1.p, start1.p, h->table_base.p, ncodes, tp,
                                                                          h->child_ptr.p, h->child_cnt.p, h->counters.p,
-                                                                         workA.p, h->node_cap);
+                                                                         workA.p, h->node_cap); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         int32_t hc[4];
         DPF_CUDA(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -299,7 +299,7 @@ void build_forest(dpf_index* h) {
             DPF_CUDA(cudaMemsetAsync(h->counters.p + 2, 0, sizeof(int32_t), st));
             k_split_level<<<nwork, SP_THREADS, 0, st>>>(cur, h->keys.p, ld, tp, level, h->table_base.p, h->ids_sorted.p,
                                                         tmp.p, h->child_ptr.p, h->child_cnt.p, h->counters.p, nxt,
-                                                        h->node_cap, stat_dev);
+                                                        h->node_cap, stat_dev); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             DPF_CUDA(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
             DPF_CUDA(cudaStreamSynchronize(st));

@@ -495,6 +495,7 @@ static void pack_launch(dpf_index* h, int64_t n, int32_t* keys_out, uint8_t* pid
         k_pack_keys<false><<<grid, 256, 0, h->stream>>>(h->signs.p, nullptr, h->chain.p, h->Ap.p, n, h->P, h->PW,
                                                         h->cfg.k, h->cfg.pb, h->cfg.key_transform, keys_out, pids_out,
                                                         ld);
+    DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }
 
@@ -516,7 +517,7 @@ void hash_dense_device(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_
             const int nct = (P + EX_T - 1) / EX_T;
             const unsigned grid = (unsigned)(((m + EX_T - 1) / EX_T) * nct);
             k_project_exact<true><<<grid, 256, 0, h->stream>>>(Xc, h->A.p, m, d, P, PW, nct, h->fb.p, h->fw.p, nullptr,
-                                                               h->pq.p);
+                                                               h->pq.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
         } else {
             for (;;) {
@@ -528,7 +529,7 @@ void hash_dense_device(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_
                     const int smem = (2 * BM + 2 * BN) * LDS_ * (int)sizeof(double);
                     k_project_dmma<<<grid, K1_THREADS, smem, h->stream>>>(Xc, h->A.p, h->Anorm.p, m, d, P, PW, nct, coef,
                                                                           h->signs.p, h->fix_list.p, h->counters.p,
-                                                                          (int)h->fix_list.cap);
+                                                                          (int)h->fix_list.cap); DPF_LAUNCHED();
                     DPF_CUDA(cudaGetLastError());
                 }
                 int32_t cnt = 0;
@@ -542,7 +543,7 @@ void hash_dense_device(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_
                 if (cnt > 0) {
                     StageTimer tm(h, DPF_T_FIXUP);
                     k_fixup_exact<<<std::min(1024, (cnt + 127) / 128), 128, 0, h->stream>>>(
-                        Xc, h->A.p, d, PW, h->fix_list.p, h->counters.p, (int)h->fix_list.cap, h->signs.p);
+                        Xc, h->A.p, d, PW, h->fix_list.p, h->counters.p, (int)h->fix_list.cap, h->signs.p); DPF_LAUNCHED();
                     DPF_CUDA(cudaGetLastError());
                 }
                 break;
@@ -565,7 +566,7 @@ void hash_dense_device_exact(dpf_index* h, const double* Xd, int64_t n, int32_t*
             const int nct = (P + EX_T - 1) / EX_T;
             const unsigned grid = (unsigned)(((m + EX_T - 1) / EX_T) * nct);
             k_project_exact<false><<<grid, 256, 0, h->stream>>>(Xd + r0 * d, h->A.p, m, d, P, PW, nct, nullptr, nullptr,
-                                                                h->signs.p, nullptr);
+                                                                h->signs.p, nullptr); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
         }
         pack_launch(h, m, keys_out + r0, pids_out ? pids_out + r0 : nullptr, ld);
@@ -582,6 +583,7 @@ static void csr_launch(dpf_index* h, const int64_t* ptr, const int32_t* idx, con
     else
         k_project_csr<PPL, false><<<grid, wpb * 32, 0, h->stream>>>(ptr, idx, val, h->At.p, h->At_ld, m, h->P, h->PW,
                                                                      nullptr, nullptr, h->signs.p, nullptr);
+    DPF_LAUNCHED();
 }
 
 void hash_csr_device(dpf_index* h, const int64_t* ptr, const int32_t* idx, const double* val, int64_t n,

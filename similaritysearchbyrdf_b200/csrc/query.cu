@@ -107,9 +107,10 @@ k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
 constexpr int EXP_THREADS = 512;
 template <bool SMEM_BM>
 __global__ void __launch_bounds__(EXP_THREADS)
-k_expand(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t nq,
-         const int32_t* __restrict__ qids, const int64_t* __restrict__ q_off, int32_t* __restrict__ q_cnt,
-         int32_t* __restrict__ cand, uint32_t* __restrict__ gbitmap, int64_t bm_words, int* __restrict__ next_query) {
+k_expand(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t q0,
+         int64_t q1, int64_t base, const int32_t* __restrict__ qids, const int64_t* __restrict__ q_off, int32_t* __restrict__ q_cnt,
+         int32_t* __restrict__ cand, uint32_t* __restrict__ gbitmap, int64_t bm_words, int* __restrict__ next_query,
+         unsigned long long* __restrict__ stat_unique) {
     extern __shared__ uint32_t sbm[];
     __shared__ int s_q, s_count;
     uint32_t* bm = SMEM_BM ? sbm : gbitmap + (int64_t)blockIdx.x * bm_words;
@@ -122,9 +123,9 @@ k_expand(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restric
     for (;;) {
         if (tid == 0) { s_q = atomicAdd(next_query, 1); s_count = 0; }
         __syncthreads();
-        const int64_t q = s_q;
-        if (q >= nq) break;
-        const int64_t off = q_off[q];
+        const int64_t q = q0 + s_q;
+        if (q >= q1) break;
+        const int64_t off = q_off[q] - base;
         const int qid = qids ? qids[q] : INT32_MIN;
         // quirk Q3 (RandomDrawTreeMap.java:982): `ln.key != key` compares boxed Integers by reference, so the
         // query's own id is dropped only inside the Integer cache
@@ -174,7 +175,7 @@ k_expand(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restric
         }
         __syncthreads();
         const int count = s_count;
-        if (tid == 0) q_cnt[q] = count;
+        if (tid == 0) { q_cnt[q] = count; atomicAdd(stat_unique, (unsigned long long)count); }
         for (int i = tid; i < count; i += EXP_THREADS) bm[cand[off + i] >> 5] = 0u;   // reset only what was touched
         __syncthreads();
     }
@@ -198,7 +199,7 @@ void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq) {
     DPF_CUDA(cudaMemsetAsync(h->counters.p + 16, 0, sizeof(int32_t), h->stream));
     const int64_t tot = nq * h->cfg.L;
     k_gather_query_keys<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
-        h->keys.p, h->pids.p, h->key_ld, qids_dev, nq, h->cfg.L, h->n, h->qkeys.p, h->qpids.p, h->counters.p + 16);
+        h->keys.p, h->pids.p, h->key_ld, qids_dev, nq, h->cfg.L, h->n, h->qkeys.p, h->qpids.p, h->counters.p + 16); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
     int32_t bad = 0;
     DPF_CUDA(cudaMemcpyAsync(&bad, h->counters.p + 16, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -207,8 +208,7 @@ void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq) {
     DPF_REQUIRE(!bad, DPF_ERR_INVALID, "query id is not in the index");
 }
 
-void collect_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode) {
-    const int64_t nq = qk.nq;
+static ProbeCtx make_ctx(dpf_index* h, int steps, int probe_mode) {
     ProbeCtx c;
     c.f = forest_view(h);
     c.tp = h->tp;
@@ -218,6 +218,14 @@ void collect_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_
     c.world = h->cfg.world > 1 ? h->cfg.world : 1;
     c.rank = c.world > 1 ? h->cfg.rank : 0;
     c.self_exclude = h->cfg.self_exclude_small_ids;
+    return c;
+}
+
+// pass A over the whole batch: h->q_cnt = per-query upper bound, h->q_off = its exclusive scan (device) and
+// off_host = the same offsets on the host, from which the caller cuts the batch into memory-bounded chunks
+void probe_count_all(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, std::vector<int64_t>& off_host) {
+    const int64_t nq = qk.nq;
+    const ProbeCtx c = make_ctx(h, steps, probe_mode);
     cudaStream_t st = h->stream;
     h->q_cnt.reserve(nq + 1);
     h->q_off.reserve(nq + 1);
@@ -228,57 +236,73 @@ void collect_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_
     {
         StageTimer tm(h, DPF_T_PROBE_COUNT);
         const int64_t warps = nq * c.L;
-        k_probe_count<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, h->q_cnt.p, stat);
+        k_probe_count<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, h->q_cnt.p, stat); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         exclusive_scan_i64(h, h->q_cnt.p, h->q_off.p, nq);
     }
-    int64_t ub_total = 0;
+    off_host.resize((size_t)nq + 1);
     unsigned long long hstat[2];
-    DPF_CUDA(cudaMemcpyAsync(&ub_total, h->q_off.p + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaMemcpyAsync(off_host.data(), h->q_off.p, (nq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaMemcpyAsync(hstat, stat, sizeof(hstat), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaStreamSynchronize(st));
     h->stats[DPF_STAT_NLZ_GT28] = (int64_t)hstat[0];
     h->stats[DPF_STAT_LAST_CAND_WITH_DUPS] = (int64_t)hstat[1];
-    h->cand.reserve((size_t)std::max<int64_t>(ub_total, 1));
-    {
-        StageTimer tm(h, DPF_T_EXPAND);
-        const int64_t bm_words = (h->n + 31) / 32 + 1;
-        const size_t smem_need = (size_t)bm_words * sizeof(uint32_t);
-        int* next_query = h->counters.p + 16;
-        const bool use_smem = smem_need <= 200 * 1024;
-        if (use_smem) {
-            static size_t attr = 0;
-            if (smem_need > attr) {
-                DPF_CUDA(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
-                attr = smem_need;
-            }
-            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem_need, 1)));
-            const int grid = (int)std::min<int64_t>(nq, (int64_t)h->num_sms * per_sm);
-            k_expand<true><<<grid, EXP_THREADS, smem_need, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, qk.qids, h->q_off.p,
-                                                                  h->q_cnt.p, h->cand.p, nullptr, bm_words, next_query);
-        } else {
-            const int grid = (int)std::min<int64_t>(nq, (int64_t)h->num_sms * 2);
-            const size_t need = (size_t)grid * bm_words;
-            if (h->bitmap.cap < need) {
-                h->bitmap.reserve(need);
-                DPF_CUDA(cudaMemsetAsync(h->bitmap.p, 0, need * sizeof(uint32_t), st));   // kept all-zero between calls
-            }
-            k_expand<false><<<grid, EXP_THREADS, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, qk.qids, h->q_off.p,
-                                                          h->q_cnt.p, h->cand.p, h->bitmap.p, bm_words, next_query);
+}
+
+// end of the chunk starting at q0 whose candidate upper bound fits `budget` ids (always at least one query)
+int64_t next_chunk_end(const std::vector<int64_t>& off, int64_t q0, int64_t budget) {
+    const int64_t nq = (int64_t)off.size() - 1;
+    int64_t q1 = q0 + 1;
+    while (q1 < nq && off[(size_t)q1 + 1] - off[(size_t)q0] <= budget) q1++;
+    return q1;
+}
+
+// pass B for queries [q0, q1): unique (unsorted) candidates of query q at h->cand[q_off[q] - base ...], count in q_cnt[q]
+void expand_range(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1, int64_t base,
+                  int64_t ub_chunk) {
+    const ProbeCtx c = make_ctx(h, steps, probe_mode);
+    cudaStream_t st = h->stream;
+    const int64_t nqc = q1 - q0;
+    unsigned long long* stat = reinterpret_cast<unsigned long long*>(h->counters.p + 20);
+    h->cand.reserve((size_t)std::max<int64_t>(ub_chunk, 1));
+    StageTimer tm(h, DPF_T_EXPAND);
+    const int64_t bm_words = (h->n + 31) / 32 + 1;
+    const size_t smem_need = (size_t)bm_words * sizeof(uint32_t);
+    int* next_query = h->counters.p + 16;
+    DPF_CUDA(cudaMemsetAsync(next_query, 0, sizeof(int), st));
+    const bool use_smem = smem_need <= 200 * 1024;
+    if (use_smem) {
+        static size_t attr = 0;
+        if (smem_need > attr) {
+            DPF_CUDA(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+            attr = smem_need;
         }
-        DPF_CUDA(cudaGetLastError());
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem_need, 1)));
+        const int grid = (int)std::min<int64_t>(nqc, (int64_t)h->num_sms * per_sm);
+        k_expand<true><<<grid, EXP_THREADS, smem_need, st>>>(c, qk.keys, h->qpids.p, qk.ld, q0, q1, base, qk.qids, h->q_off.p,
+                                                              h->q_cnt.p, h->cand.p, nullptr, bm_words, next_query, stat + 2); DPF_LAUNCHED();
+    } else {
+        const int grid = (int)std::min<int64_t>(nqc, (int64_t)h->num_sms * 2);
+        const size_t need = (size_t)h->num_sms * 2 * bm_words;
+        if (h->bitmap.cap < need) {
+            h->bitmap.reserve(need);
+            DPF_CUDA(cudaMemsetAsync(h->bitmap.p, 0, need * sizeof(uint32_t), st));   // kept all-zero between calls
+        }
+        k_expand<false><<<grid, EXP_THREADS, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, q0, q1, base, qk.qids, h->q_off.p,
+                                                      h->q_cnt.p, h->cand.p, h->bitmap.p, bm_words, next_query, stat + 2); DPF_LAUNCHED();
     }
+    DPF_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // sorted unique CSR output
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_compose_keys(const int64_t* __restrict__ q_off, const int64_t* __restrict__ out_off, const int32_t* __restrict__ q_cnt,
-               const int32_t* __restrict__ cand, unsigned long long* __restrict__ keys) {
+k_compose_keys(const int64_t* __restrict__ q_off, int64_t base, const int64_t* __restrict__ out_off,
+               const int32_t* __restrict__ q_cnt, const int32_t* __restrict__ cand, unsigned long long* __restrict__ keys) {
     const int64_t q = blockIdx.x;
     const int cnt = q_cnt[q];
-    const int64_t src = q_off[q], dst = out_off[q];
+    const int64_t src = q_off[q] - base, dst = out_off[q];
     for (int i = threadIdx.x; i < cnt; i += blockDim.x)
         keys[dst + i] = ((unsigned long long)q << 32) | (uint32_t)cand[src + i];
 }
@@ -287,26 +311,28 @@ __global__ void k_low32(const unsigned long long* __restrict__ keys, int64_t n, 
     if (i < n) out[i] = (int32_t)(uint32_t)keys[i];
 }
 
-int64_t finalize_candidates_sorted(dpf_index* h, int64_t nq, int64_t* off_dev) {
+// sorted unique ids of queries [q0, q1), concatenated, left at h->cand[0 .. total); off_dev (q1-q0+1 entries) gets
+// the chunk-local CSR offsets
+int64_t finalize_candidates_sorted(dpf_index* h, int64_t q0, int64_t q1, int64_t base, int64_t* off_dev) {
     StageTimer tm(h, DPF_T_CAND_SORT);
     cudaStream_t st = h->stream;
-    exclusive_scan_i64(h, h->q_cnt.p, off_dev, nq);
+    const int64_t nqc = q1 - q0;
+    exclusive_scan_i64(h, h->q_cnt.p + q0, off_dev, nqc);
     int64_t total = 0;
-    DPF_CUDA(cudaMemcpyAsync(&total, off_dev + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaMemcpyAsync(&total, off_dev + nqc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaStreamSynchronize(st));
-    h->stats[DPF_STAT_LAST_CANDIDATES] = total;
     if (total == 0) return 0;
     h->sk64a.reserve(total);
     h->sk64b.reserve(total);
-    k_compose_keys<<<(unsigned)nq, 256, 0, st>>>(h->q_off.p, off_dev, h->q_cnt.p, h->cand.p, h->sk64a.p);
+    k_compose_keys<<<(unsigned)nqc, 256, 0, st>>>(h->q_off.p + q0, base, off_dev, h->q_cnt.p + q0, h->cand.p, h->sk64a.p); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
     int idbits = 1, qbits = 1;
     while ((1LL << idbits) < h->n) idbits++;
-    while ((1LL << qbits) < nq) qbits++;
+    while ((1LL << qbits) < nqc) qbits++;
     unsigned long long *a = h->sk64a.p, *b = h->sk64b.p;
     radix_sort_keys_u64(h, &a, &b, total, 0, idbits);
     radix_sort_keys_u64(h, &a, &b, total, 32, 32 + qbits);
-    k_low32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total, h->cand.p);   // total <= ub_total: fits
+    k_low32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total, h->cand.p); DPF_LAUNCHED();   // total <= upper bound: fits
     DPF_CUDA(cudaGetLastError());
     return total;
 }
@@ -314,9 +340,15 @@ int64_t finalize_candidates_sorted(dpf_index* h, int64_t nq, int64_t* off_dev) {
 // ---------------------------------------------------------------------------------------------------------
 // K5: gather + re-rank + top-k
 // ---------------------------------------------------------------------------------------------------------
+// Work decomposition: a query's candidate list is cut into units of `seg` candidates; persistent CTAs pull units
+// from a counter, so the grid stays full whether the batch is many light queries or a few heavy ones.  Each unit
+// produces a sorted partial top-k; k_topk_select merges a query's partial lists.
 constexpr int RR_THREADS = 256;
 constexpr int RR_WARPS = RR_THREADS / 32;
 constexpr int RR_MAXK = 256;
+constexpr int RR_ROWS = 4;          // candidate rows in flight per warp
+constexpr int RR_MIN_SEG = 2048;    // candidates per unit (lower bound)
+constexpr int RR_MAX_UNITS = 128;   // units per query (upper bound; = threads of k_topk_select)
 
 // total order of results: larger key first, ties by smaller id (key = score, or -distance for L2)
 __device__ __forceinline__ bool better(double ka, int ia, double kb, int ib) {
@@ -326,16 +358,14 @@ __device__ __forceinline__ bool better(double ka, int ia, double kb, int ib) {
 // warp-cooperative insertion into a descending list of length <= K held in shared memory
 __device__ __forceinline__ void warp_insert(double* keys, int* ids, int& count, int K, double key, int id, int lane) {
     if (count == K && !better(key, id, keys[K - 1], ids[K - 1])) return;
-    // position = number of entries that are better than the new one
-    int pos = 0;
+    int pos = 0;   // number of entries that are better than the new one
     for (int base = 0; base < count; base += 32) {
         const int i = base + lane;
         const bool b = i < count && better(keys[i], ids[i], key, id);
         pos += __popc(__ballot_sync(0xffffffffu, b));
     }
     const int newcount = min(count + 1, K);
-    // shift [pos, newcount-1) right by one, from the back, 32 at a time
-    for (int hi = newcount - 1; hi > pos; hi -= 32) {
+    for (int hi = newcount - 1; hi > pos; hi -= 32) {   // shift [pos, newcount-1) right by one, from the back
         const int i = hi - lane;
         double kv = 0;
         int iv = 0;
@@ -350,79 +380,135 @@ __device__ __forceinline__ void warp_insert(double* keys, int* ids, int& count, 
     count = newcount;
 }
 
-template <bool VEC2>
+__global__ void k_unit_counts(const int32_t* __restrict__ cnt, int64_t q0, int64_t nqc, int seg, int32_t* __restrict__ ucnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nqc) ucnt[i] = (cnt[q0 + i] + seg - 1) / seg;
+}
+
+template <bool VEC2, int METRIC>
+__device__ __forceinline__ void score_rows(const double* __restrict__ X, int d, const double* qs, const int (&id)[RR_ROWS],
+                                           int lane, double (&s)[RR_ROWS], double (&xn)[RR_ROWS]) {
+#pragma unroll
+    for (int r = 0; r < RR_ROWS; ++r) { s[r] = 0.0; xn[r] = 0.0; }
+    if (VEC2) {
+        const double2* q2 = reinterpret_cast<const double2*>(qs);
+        for (int j = lane; j < (d >> 1); j += 32) {
+            double2 x[RR_ROWS];
+#pragma unroll
+            for (int r = 0; r < RR_ROWS; ++r)    // all loads of the iteration are issued before any use
+                x[r] = __ldg(reinterpret_cast<const double2*>(X + (int64_t)id[r] * d) + j);
+            const double2 qq = q2[j];
+#pragma unroll
+            for (int r = 0; r < RR_ROWS; ++r) {
+                if (METRIC == DPF_METRIC_L2) {
+                    const double a = qq.x - x[r].x, b = qq.y - x[r].y;
+                    s[r] = fma(a, a, s[r]);
+                    s[r] = fma(b, b, s[r]);
+                } else {
+                    s[r] = fma(x[r].x, qq.x, s[r]);
+                    s[r] = fma(x[r].y, qq.y, s[r]);
+                    if (METRIC == DPF_METRIC_ANGULAR) { xn[r] = fma(x[r].x, x[r].x, xn[r]); xn[r] = fma(x[r].y, x[r].y, xn[r]); }
+                }
+            }
+        }
+    } else {
+        for (int j = lane; j < d; j += 32) {
+            double x[RR_ROWS];
+#pragma unroll
+            for (int r = 0; r < RR_ROWS; ++r) x[r] = __ldg(X + (int64_t)id[r] * d + j);
+            const double qq = qs[j];
+#pragma unroll
+            for (int r = 0; r < RR_ROWS; ++r) {
+                if (METRIC == DPF_METRIC_L2) { const double a = qq - x[r]; s[r] = fma(a, a, s[r]); }
+                else {
+                    s[r] = fma(x[r], qq, s[r]);
+                    if (METRIC == DPF_METRIC_ANGULAR) xn[r] = fma(x[r], x[r], xn[r]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < RR_ROWS; ++r) {
+            s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+            if (METRIC == DPF_METRIC_ANGULAR) xn[r] += __shfl_xor_sync(0xffffffffu, xn[r], o);
+        }
+}
+
+template <bool VEC2, int METRIC>
 __global__ void __launch_bounds__(RR_THREADS)
-k_rerank_topk(const double* __restrict__ X, int d, const double* __restrict__ Q, int64_t nq,
-              const int64_t* __restrict__ off, const int32_t* __restrict__ cnt, const int32_t* __restrict__ cand, int K,
-              int metric, int32_t* __restrict__ ids_out, double* __restrict__ score_out, int* __restrict__ next_query) {
+k_rerank_units(const double* __restrict__ X, int d, const double* __restrict__ Q, int64_t q0, int64_t nqc, int64_t base,
+               const int64_t* __restrict__ off, const int32_t* __restrict__ cnt, const int32_t* __restrict__ cand,
+               const int64_t* __restrict__ unit_off, int seg, int K, double* __restrict__ part_key,
+               int32_t* __restrict__ part_id, int* __restrict__ next_unit) {
     extern __shared__ double rsm[];
     double* qs = rsm;                                    // d (padded to even)
     double* lkeys = rsm + ((d + 1) & ~1);                // RR_WARPS x K
     int* lids = reinterpret_cast<int*>(lkeys + RR_WARPS * K);
-    __shared__ int s_q;
+    __shared__ int s_u;
+    __shared__ int s_counts[RR_WARPS];
     __shared__ double s_qn;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* mykeys = lkeys + warp * K;
     int* myids = lids + warp * K;
+    const int64_t total_units = unit_off[nqc];
+    int64_t cur_q = -1;
     for (;;) {
-        if (tid == 0) s_q = atomicAdd(next_query, 1);
+        if (tid == 0) s_u = atomicAdd(next_unit, 1);
         __syncthreads();
-        const int64_t q = s_q;
-        if (q >= nq) break;
-        for (int j = tid; j < d; j += RR_THREADS) qs[j] = Q[q * d + j];
-        __syncthreads();
-        if (metric == DPF_METRIC_ANGULAR && warp == 0) {
-            double s = 0;
-            for (int j = lane; j < d; j += 32) s = fma(qs[j], qs[j], s);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) s_qn = sqrt(s);
+        const int64_t u = s_u;
+        if (u >= total_units) break;
+        // unit -> (query, segment): last query whose first unit is <= u
+        int64_t lo = 0, hi = nqc - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (unit_off[mid] <= u) lo = mid; else hi = mid - 1;
         }
-        __syncthreads();
+        const int64_t q = q0 + lo;
+        const int sgm = (int)(u - unit_off[lo]);
+        if (q != cur_q) {                                // units of one query are consecutive: q is usually unchanged
+            for (int j = tid; j < d; j += RR_THREADS) qs[j] = Q[q * d + j];
+            cur_q = q;
+            __syncthreads();
+            if (METRIC == DPF_METRIC_ANGULAR) {
+                if (warp == 0) {
+                    double s = 0;
+                    for (int j = lane; j < d; j += 32) s = fma(qs[j], qs[j], s);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) s_qn = sqrt(s);
+                }
+                __syncthreads();
+            }
+        }
         const int n_c = cnt[q];
-        const int32_t* cq = cand + off[q];
+        const int c_begin = sgm * seg, c_end = min(n_c, c_begin + seg);
+        const int32_t* cq = cand + (off[q] - base);
+        const double qn = (METRIC == DPF_METRIC_ANGULAR) ? s_qn : 1.0;
         int count = 0;
-        for (int ci = warp; ci < n_c; ci += RR_WARPS) {
-            const int id = __ldg(cq + ci);
-            const double* row = X + (int64_t)id * d;
-            double s = 0.0, xn = 0.0;
-            if (VEC2) {
-                const double2* r2 = reinterpret_cast<const double2*>(row);
-                const double2* q2 = reinterpret_cast<const double2*>(qs);
-                for (int j = lane; j < (d >> 1); j += 32) {
-                    const double2 x = __ldg(r2 + j);
-                    const double2 qq = q2[j];
-                    if (metric == DPF_METRIC_L2) {
-                        const double a = qq.x - x.x, b = qq.y - x.y;
-                        s = fma(a, a, s);
-                        s = fma(b, b, s);
-                    } else {
-                        s = fma(x.x, qq.x, s);
-                        s = fma(x.y, qq.y, s);
-                        if (metric == DPF_METRIC_ANGULAR) { xn = fma(x.x, x.x, xn); xn = fma(x.y, x.y, xn); }
-                    }
-                }
-            } else {
-                for (int j = lane; j < d; j += 32) {
-                    const double x = __ldg(row + j), qq = qs[j];
-                    if (metric == DPF_METRIC_L2) { const double a = qq - x; s = fma(a, a, s); }
-                    else {
-                        s = fma(x, qq, s);
-                        if (metric == DPF_METRIC_ANGULAR) xn = fma(x, x, xn);
-                    }
-                }
-            }
+        // a warp takes 32 consecutive candidates per round (one coalesced id load), RR_ROWS rows in flight
+        for (int c0 = c_begin + warp * 32; c0 < c_end; c0 += RR_WARPS * 32) {
+            const int nloc = min(32, c_end - c0);
+            const int myid = (lane < nloc) ? __ldg(cq + c0 + lane) : 0;
+            for (int r0 = 0; r0 < nloc; r0 += RR_ROWS) {
+                int id[RR_ROWS];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (metric == DPF_METRIC_ANGULAR) xn += __shfl_xor_sync(0xffffffffu, xn, o);
+                for (int r = 0; r < RR_ROWS; ++r) id[r] = __shfl_sync(0xffffffffu, myid, min(r0 + r, nloc - 1));
+                double s[RR_ROWS], xn[RR_ROWS];
+                score_rows<VEC2, METRIC>(X, d, qs, id, lane, s, xn);
+#pragma unroll
+                for (int r = 0; r < RR_ROWS; ++r) {
+                    if (r0 + r < nloc) {
+                        double v = s[r];
+                        if (METRIC == DPF_METRIC_ANGULAR) v = v / (qn * sqrt(xn[r]));
+                        const double key = (METRIC == DPF_METRIC_L2) ? -v : v;
+                        if (key == key) warp_insert(mykeys, myids, count, K, key, id[r], lane);   // NaN is never ranked
+                    }
+                }
             }
-            if (metric == DPF_METRIC_ANGULAR) s = s / (s_qn * sqrt(xn));
-            const double key = (metric == DPF_METRIC_L2) ? -s : s;
-            if (key == key) warp_insert(mykeys, myids, count, K, key, id, lane);   // NaN scores are never ranked
         }
-        // merge the per-warp lists: K rounds of "best head" over RR_WARPS sorted lists, done by warp 0
-        __shared__ int s_counts[RR_WARPS];
+        // merge the per-warp lists into this unit's sorted partial list (K rounds of "best head", warp 0)
         if (lane == 0) s_counts[warp] = count;
         __syncthreads();
         if (warp == 0) {
@@ -439,13 +525,50 @@ k_rerank_topk(const double* __restrict__ X, int d, const double* __restrict__ Q,
                     const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
                     if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
                 }
-                if (lane == 0) {
-                    ids_out[q * K + r] = bl >= 0 ? bi : -1;
-                    score_out[q * K + r] = bl >= 0 ? (metric == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
-                }
+                if (lane == 0) { part_key[u * K + r] = bk; part_id[u * K + r] = bl >= 0 ? bi : -1; }
                 if (lane == bl) head++;
             }
         }
+        __syncthreads();
+    }
+}
+
+// final selection: thread g walks partial list g of its query (lists are sorted); K rounds of block-wide best head
+__global__ void __launch_bounds__(RR_MAX_UNITS)
+k_topk_select(const int64_t* __restrict__ unit_off, int64_t q0, int K, int metric, const double* __restrict__ part_key,
+              const int32_t* __restrict__ part_id, int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
+    __shared__ double wk[RR_MAX_UNITS / 32];
+    __shared__ int wi[RR_MAX_UNITS / 32], wl[RR_MAX_UNITS / 32];
+    const int64_t ql = blockIdx.x, q = q0 + ql;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t u0 = unit_off[ql];
+    const int G = (int)(unit_off[ql + 1] - u0);
+    int head = 0;
+    for (int r = 0; r < K; ++r) {
+        double bk = 0;
+        int bi = 0x7fffffff, bl = -1;
+        if (tid < G && head < K) {
+            const int id = part_id[(u0 + tid) * K + head];
+            if (id >= 0) { bk = part_key[(u0 + tid) * K + head]; bi = id; bl = tid; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+        }
+        if (lane == 0) { wk[warp] = bk; wi[warp] = bi; wl[warp] = bl; }
+        __syncthreads();
+        bk = wk[0]; bi = wi[0]; bl = wl[0];
+#pragma unroll
+        for (int w = 1; w < RR_MAX_UNITS / 32; ++w)
+            if (wl[w] >= 0 && (bl < 0 || better(wk[w], wi[w], bk, bi))) { bk = wk[w]; bi = wi[w]; bl = wl[w]; }
+        if (tid == 0) {
+            ids_out[q * K + r] = bl >= 0 ? bi : -1;
+            score_out[q * K + r] = bl >= 0 ? (metric == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
+        }
+        if (tid == bl) head++;
         __syncthreads();
     }
 }
@@ -455,37 +578,65 @@ __global__ void k_counts_from_offsets(const int64_t* __restrict__ off, int64_t n
     if (i < nq) cnt[i] = (int32_t)(off[i + 1] - off[i]);
 }
 
-void rerank_topk(dpf_index* h, const double* Qd, int64_t nq, const int64_t* off, const int32_t* cnt, const int32_t* cand,
-                 int topk, int metric, int32_t* ids_out, double* score_out) {
+template <bool VEC2, int METRIC>
+static void launch_rerank_units(dpf_index* h, int grid, size_t smem, const double* Qd, int64_t q0, int64_t nqc, int64_t base,
+                                const int64_t* off, const int32_t* cnt, const int32_t* cand, int seg, int topk,
+                                int* next_unit) {
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        DPF_CUDA(cudaFuncSetAttribute(k_rerank_units<VEC2, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    k_rerank_units<VEC2, METRIC><<<grid, RR_THREADS, smem, h->stream>>>(h->Xdev, h->cfg.d, Qd, q0, nqc, base, off, cnt, cand,
+                                                                        h->unit_off.p, seg, topk, h->part_key.p,
+                                                                        h->part_id.p, next_unit);
+    DPF_LAUNCHED();
+    DPF_CUDA(cudaGetLastError());
+}
+
+// max_cnt: upper bound of the candidate count of any query in [q0, q1) (sizes the units)
+void rerank_topk(dpf_index* h, const double* Qd, int64_t q0, int64_t q1, int64_t base, const int64_t* off,
+                 const int32_t* cnt, const int32_t* cand, int64_t max_cnt, int64_t total_ub, int topk, int metric,
+                 int32_t* ids_out, double* score_out) {
+    const int64_t nqc = q1 - q0;
     DPF_REQUIRE(topk >= 1 && topk <= RR_MAXK, DPF_ERR_INVALID, "topk must be in 1..256");
     DPF_REQUIRE(h->dense && h->Xdev, DPF_ERR_STATE, "re-rank needs a dense index");
-    if (nq <= 0) return;
+    if (nqc <= 0) return;
     StageTimer tm(h, DPF_T_RERANK);
     const int d = h->cfg.d;
     cudaStream_t st = h->stream;
+    const int seg = (int)std::max<int64_t>(RR_MIN_SEG, (max_cnt + RR_MAX_UNITS - 1) / RR_MAX_UNITS);
+    const int64_t units_ub = total_ub / seg + nqc + 1;
+    h->ucnt.reserve(nqc + 1);
+    h->unit_off.reserve(nqc + 1);
+    h->part_key.reserve((size_t)units_ub * topk);
+    h->part_id.reserve((size_t)units_ub * topk);
     h->counters.reserve(64);
-    int* next_query = h->counters.p + 17;
-    DPF_CUDA(cudaMemsetAsync(next_query, 0, sizeof(int), st));
+    int* next_unit = h->counters.p + 17;
+    DPF_CUDA(cudaMemsetAsync(next_unit, 0, sizeof(int), st));
+    k_unit_counts<<<(unsigned)((nqc + 255) / 256), 256, 0, st>>>(cnt, q0, nqc, seg, h->ucnt.p); DPF_LAUNCHED();
+    exclusive_scan_i64(h, h->ucnt.p, h->unit_off.p, nqc);
     const size_t smem = (size_t)((d + 1) & ~1) * sizeof(double) + (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
     const bool vec2 = (d % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0);
-    static size_t attr[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > attr[vec2]) {
-        if (vec2) DPF_CUDA(cudaFuncSetAttribute(k_rerank_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else DPF_CUDA(cudaFuncSetAttribute(k_rerank_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr[vec2] = smem;
+    const int grid = (int)std::min<int64_t>(units_ub, (int64_t)h->num_sms * 6);
+#define DPF_RR(V, M) launch_rerank_units<V, M>(h, grid, smem, Qd, q0, nqc, base, off, cnt, cand, seg, topk, next_unit)
+    if (vec2) {
+        if (metric == DPF_METRIC_DOT) DPF_RR(true, DPF_METRIC_DOT);
+        else if (metric == DPF_METRIC_ANGULAR) DPF_RR(true, DPF_METRIC_ANGULAR);
+        else DPF_RR(true, DPF_METRIC_L2);
+    } else {
+        if (metric == DPF_METRIC_DOT) DPF_RR(false, DPF_METRIC_DOT);
+        else if (metric == DPF_METRIC_ANGULAR) DPF_RR(false, DPF_METRIC_ANGULAR);
+        else DPF_RR(false, DPF_METRIC_L2);
     }
-    const int grid = (int)std::min<int64_t>(nq, (int64_t)h->num_sms * 8);
-    if (vec2)
-        k_rerank_topk<true><<<grid, RR_THREADS, smem, st>>>(h->Xdev, d, Qd, nq, off, cnt, cand, topk, metric, ids_out,
-                                                            score_out, next_query);
-    else
-        k_rerank_topk<false><<<grid, RR_THREADS, smem, st>>>(h->Xdev, d, Qd, nq, off, cnt, cand, topk, metric, ids_out,
-                                                             score_out, next_query);
+#undef DPF_RR
+    k_topk_select<<<(unsigned)nqc, RR_MAX_UNITS, 0, st>>>(h->unit_off.p, q0, topk, metric, h->part_key.p, h->part_id.p,
+                                                           ids_out, score_out); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }
 
 void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt) {
-    k_counts_from_offsets<<<(unsigned)((nq + 255) / 256), 256, 0, h->stream>>>(off, nq, cnt);
+    k_counts_from_offsets<<<(unsigned)((nq + 255) / 256), 256, 0, h->stream>>>(off, nq, cnt); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }
 
@@ -544,7 +695,7 @@ void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int
                 int32_t* ids_out, double* score_out) {
     DPF_REQUIRE(G >= 1 && G <= 32, DPF_ERR_INVALID, "merge supports 1..32 lists");
     if (nq <= 0) return;
-    k_merge_topk<<<(unsigned)((nq + 3) / 4), 128, 0, h->stream>>>(gids, gsc, G, nq, topk, metric, ids_out, score_out);
+    k_merge_topk<<<(unsigned)((nq + 3) / 4), 128, 0, h->stream>>>(gids, gsc, G, nq, topk, metric, ids_out, score_out); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }
 

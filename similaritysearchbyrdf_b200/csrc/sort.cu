@@ -69,12 +69,12 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_add(uint32_t* __restrict__ 
 static void scan_u32_inplace(uint32_t* data, int64_t n, uint32_t* scratch, cudaStream_t st) {
     const int64_t nb = (n + SC_TILE - 1) / SC_TILE;
     if (nb <= 1) {
-        k_scan_tile<<<1, SC_THREADS, 0, st>>>(data, n, nullptr);
+        k_scan_tile<<<1, SC_THREADS, 0, st>>>(data, n, nullptr); DPF_LAUNCHED();
         return;
     }
-    k_scan_tile<<<(unsigned)nb, SC_THREADS, 0, st>>>(data, n, scratch);
+    k_scan_tile<<<(unsigned)nb, SC_THREADS, 0, st>>>(data, n, scratch); DPF_LAUNCHED();
     scan_u32_inplace(scratch, nb, scratch + nb, st);
-    k_scan_add<<<(unsigned)nb, SC_THREADS, 0, st>>>(data, n, scratch);
+    k_scan_add<<<(unsigned)nb, SC_THREADS, 0, st>>>(data, n, scratch); DPF_LAUNCHED();
 }
 
 static size_t scan_scratch_elems(int64_t n) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(1024) k_scan_i32_to_i64(const int32_t* __restr
 }
 
 void exclusive_scan_i64(dpf_index* h, const int32_t* in, int64_t* out, int64_t n) {
-    k_scan_i32_to_i64<<<1, 1024, 0, h->stream>>>(in, out, n);
+    k_scan_i32_to_i64<<<1, 1024, 0, h->stream>>>(in, out, n); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }
 
@@ -221,10 +221,10 @@ static void radix_sort_impl(dpf_index* h, K** keys, K** keys_alt, uint32_t** val
     for (int p = 0; p < passes; ++p) {
         const int bits = (total - (bit - lo_bit) + (passes - p) - 1) / (passes - p);   // balanced digit widths
         const int64_t used = (int64_t)(1 << bits) * ntiles;
-        k_radix_hist<K><<<(unsigned)ntiles, RS_THREADS, 0, h->stream>>>(*keys, n, bit, bits, h->hist.p, ntiles);
+        k_radix_hist<K><<<(unsigned)ntiles, RS_THREADS, 0, h->stream>>>(*keys, n, bit, bits, h->hist.p, ntiles); DPF_LAUNCHED();
         scan_u32_inplace(h->hist.p, used, h->hist.p + hist_elems, h->stream);
         k_radix_scatter<K, HAS_VAL><<<(unsigned)ntiles, RS_THREADS, 0, h->stream>>>(
-            *keys, HAS_VAL ? *vals : nullptr, *keys_alt, HAS_VAL ? *vals_alt : nullptr, n, bit, bits, h->hist.p, ntiles);
+            *keys, HAS_VAL ? *vals : nullptr, *keys_alt, HAS_VAL ? *vals_alt : nullptr, n, bit, bits, h->hist.p, ntiles); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         std::swap(*keys, *keys_alt);
         if (HAS_VAL) std::swap(*vals, *vals_alt);

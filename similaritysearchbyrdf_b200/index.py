@@ -65,6 +65,11 @@ class DPFIndex:
     def sync(self):
         self._ck(self.lib.dpf_sync(self.h))
 
+    def set_stream(self, cuda_stream):
+        """Run this index's work on the caller's CUDA stream (an integer cudaStream_t, e.g.
+        torch.cuda.current_stream().cuda_stream); 0/None restores the index's own stream."""
+        self._ck(self.lib.dpf_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     # ---- hash functions -------------------------------------------------------------------------------------
     def set_family(self, A, chain_idx, b=None, w=None):
         A, chain_idx = _f64(A), _i32(chain_idx)

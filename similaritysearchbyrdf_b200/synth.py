@@ -44,19 +44,26 @@ def partitioner_family(L, pb, seed):
     return v / np.sqrt((v * v).sum(-1, keepdims=True))
 
 
-def clustered_dense(n, d, seed, centres, spread=0.35, lo=None, hi=None, integer=False, chunk=1 << 18):
-    """n x d FP64 rows: centre + spread * N(0, I); optionally mapped to [lo, hi] and rounded."""
+def clustered_dense(n, d, seed, centres, spread=0.35, lo=None, hi=None, integer=False, relu=False, chunk=1 << 18):
+    """n x d FP64 rows: centre + spread * N(0, I).  With lo/hi the values are mapped to [lo, hi] (and rounded when
+    `integer`); with `relu` negative coordinates are clamped to zero first (histogram-like, about half the
+    coordinates of a row are zero) so that unrelated rows are far apart in angle, as in real SIFT/GIST data."""
     rng = np.random.default_rng(seed)
     C = rng.standard_normal((centres, d))
     X = np.empty((n, d), np.float64)
     for s in range(0, n, chunk):
         m = min(chunk, n - s)
         X[s:s + m] = C[rng.integers(0, centres, m)] + spread * rng.standard_normal((m, d))
-    if lo is not None:
+    if relu:
+        np.maximum(X, 0.0, out=X)
+        X *= (hi - lo) / 4.0
+        X += lo
+        np.clip(X, lo, hi, out=X)
+    elif lo is not None:
         mn, mx = -4.0, 4.0
         X = np.clip((X - mn) / (mx - mn), 0.0, 1.0) * (hi - lo) + lo
-        if integer:
-            X = np.rint(X)
+    if integer:
+        np.rint(X, out=X)
     return X
 
 
@@ -68,13 +75,15 @@ def config1(n=20000, d=100):
 
 
 def config2(n=1_000_000, nq=10_000, d=128):
-    """SIFT shape: non-negative integer-valued doubles in [0, 218]; queries are held-out draws."""
-    X = clustered_dense(n + nq, d, 1002, 1000, lo=0.0, hi=218.0, integer=True)
+    """SIFT shape: non-negative integer-valued doubles in [0, 218], about half of them zero, ~1000 rows per
+    cluster; queries are held-out draws from the same mixture."""
+    X = clustered_dense(n + nq, d, 1002, max(1, n // 1000), lo=0.0, hi=218.0, integer=True, relu=True)
     return X[:n], X[n:]
 
 
 def config3(n=1_000_000, nq=1000, d=960):
-    X = clustered_dense(n + nq, d, 1003, 1000, lo=0.0, hi=1.0)
+    """GIST shape: values in [0, 1], ~1000 rows per cluster."""
+    X = clustered_dense(n + nq, d, 1003, max(1, n // 1000), lo=0.0, hi=1.0, relu=True)
     return X[:n], X[n:]
 
 

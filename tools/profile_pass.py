@@ -1,0 +1,36 @@
+"""One build + one query batch of BASELINE configs[1] at reduced query count: the command profiled under ncu
+(launch list / --set full).  Prints stage times so the plain run documents itself."""
+import argparse
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from similaritysearchbyrdf_b200 import DPFIndex, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1_000_000)
+ap.add_argument("--nq", type=int, default=1000)
+ap.add_argument("--d", type=int, default=128)
+ap.add_argument("--topk", type=int, default=10)
+ap.add_argument("--repeat", type=int, default=1)
+a = ap.parse_args()
+X, Q = synth.config2(a.n, a.nq, a.d)
+A, chain = synth.angle_family(a.d, max(100, a.d), 10, 3, 32, 88387 + 2)
+Ap = synth.partitioner_family(30, 3, 88387 + 3)
+ix = DPFIndex(d=a.d, L=30, k=32, pb=3)
+ix.set_family(A, chain)
+ix.set_partitioners(Ap)
+ix.set_profiling(True)
+Xd = torch.from_numpy(X).cuda()
+for _ in range(a.repeat):
+    ix2 = DPFIndex(d=a.d, L=30, k=32, pb=3)
+    ix2.set_family(A, chain); ix2.set_partitioners(Ap); ix2.set_profiling(True)
+    ix2.fit_dense_dev(Xd.data_ptr(), a.n)
+    print("build stage ms:", {k: round(v, 3) for k, v in ix2.stage_times_ms().items() if v}, ix2.stats())
+    ix = ix2
+for _ in range(a.repeat + 1):
+    ids, sc = ix.query_topk_dense(Q, None, 0, a.topk, 0)
+    st = ix.stats()
+    print("query stage ms:", {k: round(v, 3) for k, v in ix.stage_times_ms().items() if v},
+          "cand/q", st["last_candidates"] / a.nq, "dups/q", st["last_cand_with_dups"] / a.nq)
