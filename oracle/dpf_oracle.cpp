@@ -444,6 +444,7 @@ void table_query(dpfo* o, const Table& T, int table, int32_t h, int32_t qid, int
     for (int pi = 0; pi < nprobes; ++pi) {
         for (int s = 0; s < np; ++s) {                       // findStepWiseSubIndexIDs :613-621
             if (java_bitcount(s ^ pid) > steps) continue;
+            if (o->cfg.world > 1 && (s % o->cfg.world) != o->cfg.rank) continue;   // another shard owns it
             const std::vector<int32_t>* b = table_lookup(o, T, s, seg, probes[pi]);
             if (!b) continue;
             for (int32_t y : *b) {
@@ -598,8 +599,10 @@ static int fit_common(dpfo* o, const std::vector<int32_t>& keys, const std::vect
                     Tb.keys[base + i] = keys[(size_t)t * n + i];
                     Tb.pids[base + i] = pids[(size_t)t * n + i];
                 }
-                for (int64_t i = 0; i < n; ++i)
+                for (int64_t i = 0; i < n; ++i) {
+                    if (o->cfg.world > 1 && (pids[(size_t)t * n + i] % o->cfg.world) != o->cfg.rank) continue;
                     table_insert(o, Tb, (int32_t)(base + i), keys[(size_t)t * n + i], pids[(size_t)t * n + i]);
+                }
             }
         });
     }
@@ -728,8 +731,7 @@ int64_t dpfo_dump_buckets(dpfo* o, int table, int32_t* desc_out, int64_t* off_ou
     struct Frame { int32_t dir; int level; int64_t path; };
     for (int r = 0; r < roots; ++r) {
         // DFS in ascending slot order => (root, path) lexicographic order
-        std::vector<Frame> stack;
-        std::vector<std::pair<Frame, int>> st;   // frame + next slot
+            std::vector<std::pair<Frame, int>> st;   // frame + next slot
         st.push_back({{r, tp.MAXL, 0}, 0});
         while (!st.empty()) {
             auto& top = st.back();

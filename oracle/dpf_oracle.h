@@ -35,6 +35,8 @@ typedef struct {
     int32_t family_kind;     /* 0 = angle (AngleHashFamily.scala), 1 = pStable                 */
     int32_t key_transform;   /* 0 original, 1 sampling, 2 continueBitsCount, 3 angleNewMethod  */
     int32_t self_exclude_small_ids; /* quirk Q3: RandomDrawTreeMap.java:982 (ids -128..127)    */
+    int32_t rank, world;     /* emulate one shard of the content-based partition scheme: only the
+                                sub-indexes p with p % world == rank are built and searched (0/1 = all) */
 } dpfo_cfg;
 
 enum { DPFO_METRIC_DOT = 0, DPFO_METRIC_ANGULAR = 1, DPFO_METRIC_L2 = 2 };

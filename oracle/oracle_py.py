@@ -20,7 +20,7 @@ TRANSFORMS = {"original": 0, "sampling": 1, "continueBitsCount": 2, "angleNewMet
 class Cfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "d", "L", "k", "P", "pb", "bucket_bits", "dir_node_size", "bucket_overflow", "family_kind",
-        "key_transform", "self_exclude_small_ids")]
+        "key_transform", "self_exclude_small_ids", "rank", "world")]
 
 
 def build(force=False):
@@ -169,9 +169,9 @@ class Oracle:
     """One forest (L tables) of the CPU oracle; mirrors the C-ABI handle of the product library."""
 
     def __init__(self, d, L, k, P, pb=3, bucket_bits=28, dir_node_size=32, bucket_overflow=500, family_kind=0,
-                 key_transform=0, self_exclude_small_ids=1):
+                 key_transform=0, self_exclude_small_ids=1, rank=0, world=1):
         self.cfg = Cfg(d, L, k, P, pb, bucket_bits, dir_node_size, bucket_overflow, family_kind, key_transform,
-                       self_exclude_small_ids)
+                       self_exclude_small_ids, rank, world)
         self.h = lib().dpfo_create(C.byref(self.cfg))
         if not self.h:
             raise ValueError("dpfo_create rejected the configuration")

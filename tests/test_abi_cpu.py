@@ -41,5 +41,33 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "oracle" not in src.lower().replace("oracle/", "oracle/") or f == "__init__.py" and False, \
-                    f"{f} mentions the oracle"
+                assert not re.search(r"^\s*(from|import)\s+oracle\b|dpf_oracle|oracle_py|dpfo_", src, flags=re.M), \
+                    f"{f} reaches into oracle/"
+
+
+def test_jni_shim_compiles_against_stub_header():
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "jni"), "-s", "check"])
+
+
+def test_deploy_parsers_match_reference_formats():
+    """Vector.scala:162-219 formats (VectorSuite.scala:9-53 resources: sparsevectorfile / densevectorfile)."""
+    from similaritysearchbyrdf_b200 import deploy as D
+    vid, size, idx, val = D.Vectors.fromString("(3,3,[0,1,2],[1.0,2.0,3.0])")
+    assert (vid, size, idx.tolist(), val.tolist()) == (3, 3, [0, 1, 2], [1.0, 2.0, 3.0])
+    assert str(D.SparseVector(vid, size, idx, val)) == "(3,3,[0,1,2],[1.0,2.0,3.0])"
+    vid, size, idx, val = D.Vectors.fromPythonString("[1, 3, [1, 2], [1.0, 2.5]]")
+    assert (vid, size, idx.tolist(), val.tolist()) == (1, 3, [1, 2], [1.0, 2.5])
+    vid, vals = D.Vectors.parseDense("[1,[0.1, 0.2,0.4,0.9]]")
+    assert vid == 1 and vals.tolist() == [0.1, 0.2, 0.4, 0.9]
+    assert D.Vectors.fromStringDense("0.3,0.2,0.9").tolist() == [0.3, 0.2, 0.9]
+    assert D.Vectors.analysisKNN("[1, 30, 19, 230]", 3).tolist() == [1, 30, 19]
+    with pytest.raises(ValueError):
+        D.Vectors.fromString("(3,3,[0,1,2])")
+    conf = D.Config.parseString("mclab.lsh.tableNum = 4").withFallback(D.testBaseConf)
+    assert conf.getInt("mclab.lsh.tableNum") == 4 and conf.getInt("mclab.lsh.permutationNum") == 3
+    lsh = D.LSH(conf)
+    assert len(lsh.tableIndexGenerators) == 12 and lsh.chain.shape == (12, 32)   # LSHSuite.scala:24-59 (count only)

@@ -1,0 +1,152 @@
+"""GPU tests written the way the reference's own suites use its facades (TestSingleRDFSuite.scala, README "simple
+test"), plus the two-shard emulation of the content-based partition scheme on one GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from similaritysearchbyrdf_b200 import _lib as B
+from similaritysearchbyrdf_b200 import synth
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_dense_file(path, X):
+    with open(path, "w") as f:
+        for i, row in enumerate(X):
+            f.write("[%d, [%s]]\n" % (i + 7, ", ".join(repr(float(v)) for v in row)))   # file ids are ignored (Q14)
+
+
+def _write_sparse_file(path, indptr, idx, val, D):
+    with open(path, "w") as f:
+        for i in range(len(indptr) - 1):
+            s, e = indptr[i], indptr[i + 1]
+            f.write("[%d, %d, [%s], [%s]]\n" % (i, D, ", ".join(str(int(v)) for v in idx[s:e]),
+                                                ", ".join(repr(float(v)) for v in val[s:e])))
+
+
+def test_deploy_dense_simple_test(tmp_path):
+    """README.md:32-42 / TestSingleRDFSuite: newMultiThreadFit on a file, NewMultiThreadQueryBatch of 2 queries."""
+    from similaritysearchbyrdf_b200 import deploy as D
+    X, Q = synth.config1(n=3000)
+    path = os.path.join(tmp_path, "dense.txt")
+    _write_dense_file(path, X)
+    conf = D.Config.parseString("mclab.lshTable.bufferOverflow=40").withFallback(D.testBaseConf)
+    D.LSHServer.lshEngine = D.LSH(conf)
+    D.LSHServer.isUseDense = True
+    all_vectors = D.DensevectorRDFInit.newMultiThreadFit(path, conf)
+    assert len(all_vectors) == 3000 and all_vectors[5].vectorId == 5
+    queries = [D.DenseVector(0, Q[0]), D.DenseVector(1, Q[1])]
+    res = D.DensevectorRDFInit.NewMultiThreadQueryBatch([0, 1], queries, 0, 5)
+    assert len(res) == 2 and all(isinstance(r, set) for r in res)
+    # multi-thread query == single-thread query (TestSingleRDFSuite.scala:57-60): thread count is immaterial here
+    ids = list(range(100))
+    vecs = [all_vectors[i] for i in ids]
+    a = D.DensevectorRDFInit.NewMultiThreadQueryBatch(ids, vecs, 0, 5)
+    b = D.DensevectorRDFInit.queryBatch(ids, vecs, 0)
+    assert a == b
+    # same functions through the oracle give the same candidate sets
+    lsh = D.LSHServer.lshEngine
+    o = U.make_oracle(100, lsh.A, lsh.chain, D.DensevectorRDFInit.partitioners, bucket_overflow=40)
+    o.fit_dense(X)
+    off, cand = o.query_candidates_dense(np.stack([v.values for v in vecs]), np.array(ids, np.int32), 0)
+    assert [set(cand[off[i]:off[i + 1]].tolist()) for i in range(100)] == a
+    # the overload that takes only vectors inserts them first (DensevectorRDFInit.scala:372-399)
+    r2 = D.DensevectorRDFInit.NewMultiThreadQueryBatch(queries, 0, 5)
+    assert len(D.DensevectorRDFInit.index) == 3002 and len(r2) == 2
+    assert 3000 in r2[0] and 3001 in r2[1]                   # a query now finds itself (ids outside -128..127)
+    topk, precision = D.DensevectorRDFInit.topKAndPrecisionScore(all_vectors, [set(range(10))] * 3, conf, 1)
+    assert len(topk) == 3 and 0.0 <= precision <= 1.0
+    dt, ht = D.DensevectorRDFInit.getDtAndHtNumDistribution()
+    assert abs(ht.sum() - 3002) < 1e-6
+    D.DensevectorRDFInit.clearAndClose()
+    assert D.DensevectorRDFInit.NewMultiThreadQueryBatch([0], [queries[0]], 0, 5) is None   # "need to fit the data first"
+    D.LSHServer.lshEngine = None
+
+
+def test_deploy_sparse_facade(tmp_path):
+    from similaritysearchbyrdf_b200 import deploy as D
+    Dm = 300
+    rng = np.random.default_rng(3)
+    nnz = np.maximum(rng.poisson(10, 2000), 1)
+    indptr = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
+    idx = np.concatenate([np.sort(rng.choice(Dm, m, replace=False)) for m in nnz]).astype(np.int32)
+    val = rng.random(indptr[-1]) + 0.01
+    path = os.path.join(tmp_path, "sparse.txt")
+    _write_sparse_file(path, indptr, idx, val, Dm)
+    conf = D.Config.parseString(f"mclab.lsh.vectorDim={Dm}\nmclab.lshTable.bufferOverflow=20").withFallback(D.testBaseConf)
+    D.LSHServer.lshEngine = D.LSH(conf)
+    vals = D.SparsevectorRDFInit.newMultiThreadFit(path, conf)
+    assert len(vals) == 2000 and D.LSHServer.isUseDense is False
+    ids = list(range(0, 2000, 40))
+    res = D.SparsevectorRDFInit.NewMultiThreadQueryBatch(ids, 1, 5)
+    lsh = D.LSHServer.lshEngine
+    o = U.make_oracle(Dm, lsh.A, lsh.chain, D.SparsevectorRDFInit.partitioners, bucket_overflow=20)
+    o.fit_csr(indptr, idx, val)
+    off, cand = o.query_candidates_by_id(np.array(ids, np.int32), 1)
+    assert [set(cand[off[i]:off[i + 1]].tolist()) for i in range(len(ids))] == res
+    D.SparsevectorRDFInit.clearAndClose()
+    D.LSHServer.lshEngine = None
+
+
+def test_two_rank_emulation_on_one_gpu():
+    """Two handles (rank 0/1 of world 2) on the same device + dpf_merge_topk_dev == the single-handle result."""
+    import torch
+    X, Q = synth.config1(n=8000)
+    A, chain, Ap = U.make_functions(100)
+    Qs = np.concatenate([Q, X[:100] + 0.01])
+    nq, K = len(Qs), 10
+    full = U.make_index(100, A, chain, Ap, bucket_overflow=40)
+    full.fit_dense(X)
+    for metric in (B.METRIC_DOT, B.METRIC_L2):
+        f_ids, f_sc = full.query_topk_dense(Qs, None, 1, K, metric)
+        shards = [U.make_index(100, A, chain, Ap, bucket_overflow=40, rank=r, world=2) for r in range(2)]
+        per = []
+        for s in shards:
+            s.fit_dense(X)
+            per.append(s.query_topk_dense(Qs, None, 1, K, metric))
+        g_ids = torch.from_numpy(np.stack([p[0] for p in per])).cuda()
+        g_sc = torch.from_numpy(np.stack([p[1] for p in per])).cuda()
+        m_ids = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+        m_sc = torch.empty((nq, K), dtype=torch.float64, device="cuda")
+        shards[0].merge_topk_dev(g_ids.data_ptr(), g_sc.data_ptr(), 2, nq, K, metric, m_ids.data_ptr(), m_sc.data_ptr())
+        shards[0].sync()
+        torch.cuda.synchronize()
+        assert np.array_equal(m_ids.cpu().numpy(), f_ids)
+        assert np.array_equal(m_sc.cpu().numpy(), f_sc, equal_nan=True)
+        # each shard equals the oracle restricted to the same sub-indexes
+        for r, s in enumerate(shards):
+            o = U.make_oracle(100, A, chain, Ap, bucket_overflow=40, rank=r, world=2)
+            o.fit_dense(X)
+            U.assert_buckets_equal(o, s, chain.shape[0])
+            U.assert_csr_equal(o.query_candidates_dense(Qs, None, 1), s.query_candidates_dense(Qs, None, 1))
+
+
+def test_full_size_properties_config2_sample():
+    """Size-independent properties at a BASELINE-sized slice: idempotent hashing, every id in exactly one bucket per
+    table, candidate lists sorted unique, a query that is an indexed vector finds itself."""
+    X, Q = synth.config2(n=200_000, nq=64)
+    A, chain = synth.angle_family(128, 128, 10, 3, 32, 88389)
+    Ap = synth.partitioner_family(30, 3, 88390)
+    ix = U.make_index(128, A, chain, Ap)
+    k1, p1 = ix.hash_dense(X[:5000])
+    k2, p2 = ix.hash_dense(X[:5000])
+    assert np.array_equal(k1, k2) and np.array_equal(p1, p2)
+    ix.fit_dense(X)
+    for t in (0, 17, 29):
+        desc, off, ids = ix.dump_buckets(t)
+        assert len(ids) == 200_000 and np.array_equal(np.sort(ids), np.arange(200_000))
+        assert all(np.all(np.diff(ids[off[i]:off[i + 1]]) > 0) for i in range(0, len(off) - 1, 97))
+        sizes = np.diff(off)
+        assert (sizes[desc[:, 1] >= 1] <= 501).all()         # only level-0 buckets may exceed T+1
+    # probe list {h}: the own bucket is always visited (the dense multi-probe list omits h itself, quirk Q4)
+    off, cand = ix.query_candidates_dense(X[1000:1064], np.arange(1000, 1064, dtype=np.int32), 0, B.PROBE_NONE)
+    for i in range(64):
+        c = cand[off[i]:off[i + 1]]
+        assert np.all(np.diff(c) > 0) and (1000 + i) in c
+    off2, cand2 = ix.query_candidates_dense(X[1000:1064], None, 0)
+    assert all(np.all(np.diff(cand2[off2[i]:off2[i + 1]]) > 0) for i in range(64))
+    ids, sc = ix.query_topk_dense(X[1000:1064], None, 0, 10, B.METRIC_L2, B.PROBE_NONE)
+    assert (ids[:, 0] == np.arange(1000, 1064)).all() and (sc[:, 0] == 0).all()
+    assert np.all(np.diff(sc, axis=1) >= 0)
