@@ -150,6 +150,9 @@ enum {
     DPF_STAT_LAST_CANDIDATES = 6,  /* unique candidates of the last query batch                              */
     DPF_STAT_LAST_CAND_WITH_DUPS = 7, /* bucket entries visited by the last query batch                      */
     DPF_STAT_KERNEL_LAUNCHES = 8,  /* kernels launched by this library in this process (cumulative)          */
+    DPF_STAT_BM_PAIRS = 9,         /* bucket-major re-rank, last batch: (bucket, query) pairs                */
+    DPF_STAT_BM_RUNS = 10,         /*   runs of pairs sharing a bucket inside a CTA group                    */
+    DPF_STAT_BM_ROWS_STAGED = 11,  /*   bucket rows staged in shared memory (each 8d bytes of HBM)           */
     DPF_STAT_COUNT = 16
 };
 int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occupancy_out /* 2^pb or NULL */);
@@ -157,7 +160,7 @@ int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occ
 /* per-stage device times of the last fit / query call, measured with CUDA events on the handle's stream */
 enum {
     DPF_T_HASH = 0, DPF_T_FIXUP = 1, DPF_T_PACK = 2, DPF_T_SORT = 3, DPF_T_SPLIT = 4,
-    DPF_T_PROBE_COUNT = 5, DPF_T_EXPAND = 6, DPF_T_RERANK = 7, DPF_T_CAND_SORT = 8, DPF_T_COUNT = 16
+    DPF_T_PROBE_COUNT = 5, DPF_T_EXPAND = 6, DPF_T_RERANK = 7, DPF_T_CAND_SORT = 8, DPF_T_SELECT = 9, DPF_T_COUNT = 16
 };
 int dpf_set_profiling(dpf_handle h, int32_t enable);
 int dpf_stage_times_ms(dpf_handle h, float* ms_out /* DPF_T_COUNT */);

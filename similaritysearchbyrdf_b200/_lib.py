@@ -14,8 +14,9 @@ METRIC_DOT, METRIC_ANGULAR, METRIC_L2 = 0, 1, 2
 PROBE_NONE, PROBE_DENSE = 0, 1
 STAT_COUNT, T_COUNT = 16, 16
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
-              "last_cand_with_dups", "kernel_launches"]
-STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort"]
+              "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",
+              "bm_rows_staged"]
+STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select"]
 
 # every symbol include/dpf.h declares
 EXPORTS = [

@@ -501,6 +501,12 @@ static void topk_device(dpf_index* h, const double* Qd, int64_t nq, const int32_
     for (int64_t q0 = 0; q0 < nq;) {   // memory-bounded chunks of queries: expand -> gather/re-rank/top-k
         const int64_t q1 = next_chunk_end(ub, q0, kCandBudget);
         const int64_t base = ub[(size_t)q0];
+        if (bucket_major_supported(h, metric, topk) && ub[(size_t)q1] - base < (1LL << 32)) {
+            topk_bucket_major(h, Qd, qk, steps, probe_mode, q0, q1, ub[(size_t)q1] - base, topk, metric, ids_out_dev,
+                              score_out_dev);
+            q0 = q1;
+            continue;
+        }
         expand_range(h, qk, steps, probe_mode, q0, q1, base, ub[(size_t)q1] - base);
         int64_t max_cnt = 1;
         for (int64_t q = q0; q < q1; ++q) max_cnt = std::max(max_cnt, ub[(size_t)q + 1] - ub[(size_t)q]);
@@ -631,6 +637,11 @@ int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
             DPF_CUDA(cudaMemcpyAsync(&u, h->counters.p + 24, sizeof(u), cudaMemcpyDeviceToHost, h->stream));
             DPF_CUDA(cudaStreamSynchronize(h->stream));
             h->stats[DPF_STAT_LAST_CANDIDATES] = (int64_t)u;
+            unsigned long long bm[2] = {0, 0};
+            DPF_CUDA(cudaMemcpyAsync(bm, h->counters.p + 26, sizeof(bm), cudaMemcpyDeviceToHost, h->stream));
+            DPF_CUDA(cudaStreamSynchronize(h->stream));
+            h->stats[DPF_STAT_BM_RUNS] = (int64_t)bm[0];
+            h->stats[DPF_STAT_BM_ROWS_STAGED] = (int64_t)bm[1];
         }
         h->stats[DPF_STAT_KERNEL_LAUNCHES] = (int64_t)g_launches;
         for (int i = 0; i < DPF_STAT_COUNT; ++i) stats_out[i] = h->stats[i];

@@ -164,6 +164,12 @@ struct dpf_index {
     dpf::DevBuf<uint8_t> qpids;
     dpf::DevBuf<int32_t> out_ids;
     dpf::DevBuf<int32_t> ucnt, part_id;        // re-rank work units / partial top-k lists
+    dpf::DevBuf<uint32_t> scan_scratch, pair_cnt, pair_base, pair_seg, pair_len;   // bucket-major re-rank
+    dpf::DevBuf<int32_t> pair_q;
+    dpf::DevBuf<unsigned long long> pair_key, pair_key_alt;
+    dpf::DevBuf<double> scores;
+    unsigned long long* bm_sorted = nullptr;   // pair keys sorted by bucket (points into pair_key_alt / sk64a)
+    int64_t bm_npairs = 0;
     dpf::DevBuf<int64_t> unit_off;
     dpf::DevBuf<double> part_key;
     dpf::DevBuf<double> out_scores;
@@ -221,6 +227,7 @@ void radix_sort_pairs_u32(dpf_index* h, uint32_t** keys, uint32_t** keys_alt, ui
 void radix_sort_keys_u64(dpf_index* h, unsigned long long** keys, unsigned long long** keys_alt, int64_t n, int lo_bit,
                          int hi_bit);
 void exclusive_scan_i64(dpf_index* h, const int32_t* in, int64_t* out, int64_t n);  // out has n+1 entries
+void exclusive_scan_u32(dpf_index* h, uint32_t* data, int64_t n);                   // in place, multi-CTA
 
 // ---- forest.cu ----------------------------------------------------------------------------------------------
 void build_forest(dpf_index* h);
@@ -241,6 +248,10 @@ int64_t finalize_candidates_sorted(dpf_index* h, int64_t q0, int64_t q1, int64_t
 void rerank_topk(dpf_index* h, const double* Qd, int64_t q0, int64_t q1, int64_t base, const int64_t* off,
                  const int32_t* cnt, const int32_t* cand, int64_t max_cnt, int64_t total_ub, int topk, int metric,
                  int32_t* ids_out, double* score_out);
+// bucket-major re-rank of queries [q0, q1) (rerank_bm.cu): top-k straight from the probe result, no candidate lists
+bool bucket_major_supported(const dpf_index* h, int metric, int topk);
+void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1,
+                       int64_t entries_ub, int topk, int metric, int32_t* ids_out, double* score_out);
 void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);
 void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt);
 void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,

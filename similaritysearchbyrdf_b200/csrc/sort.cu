@@ -126,6 +126,14 @@ __global__ void __launch_bounds__(1024) k_scan_i32_to_i64(const int32_t* __restr
     if (threadIdx.x == 0) out[n] = carry;
 }
 
+// in-place exclusive scan of n uint32 values (sum must fit 32 bits); multi-CTA, for arrays of millions of entries
+void exclusive_scan_u32(dpf_index* h, uint32_t* data, int64_t n) {
+    if (n <= 0) return;
+    h->scan_scratch.reserve(scan_scratch_elems(n));
+    scan_u32_inplace(data, n, h->scan_scratch.p, h->stream);
+    DPF_CUDA(cudaGetLastError());
+}
+
 void exclusive_scan_i64(dpf_index* h, const int32_t* in, int64_t* out, int64_t n) {
     k_scan_i32_to_i64<<<1, 1024, 0, h->stream>>>(in, out, n); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
