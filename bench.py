@@ -195,12 +195,13 @@ def run_ours(args):
         ix.set_stream(stream.cuda_stream)
         ix.set_profiling(True)
 
-        # warm-up build on a slice (separate handle): CUDA lazy module loading and first-touch allocations happen here
+        # warm-up build (separate handle, same size): CUDA lazy module loading happens here and the device memory
+        # pool the library allocates from (cudaMallocAsync) grows to its working size, as in a long-lived process
         wix = DPFIndex(d=d, L=chain.shape[0], k=chain.shape[1], pb=Ap.shape[1], device=local, rank=rank, world=world)
         wix.set_family(A, chain)
         wix.set_partitioners(Ap)
         wix.set_stream(stream.cuda_stream)
-        wix.fit_dense_dev(Xd.data_ptr(), min(n, 65536))
+        wix.fit_dense_dev(Xd.data_ptr(), n)
         wix.close()
         # ---- index build (inputs resident in HBM), device-timed ------------------------------------------------
         barrier()
@@ -308,21 +309,25 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_ms = float(te.item()) / args.steps
 
-        # ---- e2e build through the host API (fresh index, host buffer) -----------------------------------------
-        e2e_build_ms = None
+        # ---- e2e build through the host API (fresh index each time, pinned host buffer -> H2D inside the timed region)
+        # first pass = cold (the library's device memory pool grows to hold the vector store), then 3 warm passes
+        e2e_build_ms, e2e_build_cold_ms = None, None
         if world == 1:
-            ix2 = DPFIndex(d=d, L=chain.shape[0], k=chain.shape[1], pb=Ap.shape[1], device=local)
-            ix2.set_family(A, chain)
-            ix2.set_partitioners(Ap)
-            ix2.set_stream(stream.cuda_stream)
             Xh = torch.from_numpy(X).pin_memory()
-            torch.cuda.synchronize()
-            e0.record(stream)
-            ix2.fit_dense(Xh.numpy())
-            e1.record(stream)
-            torch.cuda.synchronize()
-            e2e_build_ms = e0.elapsed_time(e1)
-            ix2.close()
+            times = []
+            for _ in range(4):
+                ix2 = DPFIndex(d=d, L=chain.shape[0], k=chain.shape[1], pb=Ap.shape[1], device=local)
+                ix2.set_family(A, chain)
+                ix2.set_partitioners(Ap)
+                ix2.set_stream(stream.cuda_stream)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                ix2.fit_dense(Xh.numpy())
+                e1.record(stream)
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+                ix2.close()
+            e2e_build_cold_ms, e2e_build_ms = times[0], float(np.mean(times[1:]))
             del Xh
 
         # ---- recall@10 against exact FP64 brute force (outside every timed region) -----------------------------
@@ -394,6 +399,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "build": {"vectors_per_s": n / (build_ms * 1e-3), "ms": build_ms, "stage_ms": build_stage,
                   "e2e_vectors_per_s": n / (e2e_build_ms * 1e-3) if e2e_build_ms else None,
+                  "e2e_ms": e2e_build_ms, "e2e_cold_ms": e2e_build_cold_ms, "e2e_h2d_bytes": int(n * d * 8),
                   "near_zero_fixups": bstats["near_zero_fixups"], "splits": bstats["splits"],
                   "singleton_splits": bstats["singleton_splits"], "dir_nodes": bstats["dir_nodes"]},
         "query_stage_ms": stage_acc, "candidates_with_dups_per_query": qstats["last_cand_with_dups"] / nq,

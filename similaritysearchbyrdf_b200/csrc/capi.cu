@@ -1,7 +1,9 @@
 // capi.cu — the extern "C" boundary declared in include/dpf.h.  Every entry point takes the handle's lock,
 // selects the handle's device, runs the device pipeline on the handle's stream and converts failures into
 // DPF_ERR_* codes (no exception leaves the library, nothing aborts the process).
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -11,6 +13,7 @@ using namespace dpf;
 
 namespace dpf {
 unsigned long long g_launches = 0;
+thread_local cudaStream_t tl_stream = nullptr;
 }
 
 namespace {
@@ -27,6 +30,7 @@ int guarded(dpf_handle h, F&& f) {
     std::lock_guard<std::mutex> lk(h->mu);
     try {
         DPF_CUDA(cudaSetDevice(h->cfg.device));
+        tl_stream = h->stream;
         f();
         return DPF_OK;
     } catch (const Error& e) {
@@ -184,6 +188,8 @@ const char* dpf_strerror(int code) {
     }
 }
 
+int dpf_destroy(dpf_handle h);
+
 int dpf_create(const dpf_config* cfg, dpf_handle* out) {
     if (!cfg || !out) return DPF_ERR_INVALID;
     *out = nullptr;
@@ -210,14 +216,21 @@ int dpf_create(const dpf_config* cfg, dpf_handle* out) {
                            (1 << cfg->pb) * (1 << seg_bits), cfg->bucket_overflow};
         DPF_CUDA(cudaSetDevice(cfg->device));
         DPF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        tl_stream = h->stream;
+        {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+            cudaMemPool_t pool = nullptr;
+            DPF_CUDA(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+            unsigned long long keep = ~0ULL;
+            DPF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         DPF_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
         h->counters.reserve(64);
         h->occupancy.assign(1 << cfg->pb, 0.0);
     } catch (const Error& e) {
-        delete h;
+        dpf_destroy(h);
         return e.code;
     } catch (...) {
-        delete h;
+        dpf_destroy(h);
         return DPF_ERR_NOMEM;
     }
     *out = h;
@@ -227,11 +240,17 @@ int dpf_create(const dpf_config* cfg, dpf_handle* out) {
 int dpf_destroy(dpf_handle h) {
     if (!h) return DPF_OK;
     cudaSetDevice(h->cfg.device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->own_stream) { h->stream = h->own_stream; h->own_stream = nullptr; }
+    if (h->stream) cudaStreamSynchronize(h->stream);   // a caller stream that is already gone only returns an error
+    cudaGetLastError();
+    cudaStream_t own = h->own_stream ? h->own_stream : h->stream;
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    tl_stream = own;        // the buffers go back to the pool in the order of the handle's own stream
     delete h;
+    if (own) {
+        cudaStreamSynchronize(own);
+        cudaStreamDestroy(own);
+    }
+    tl_stream = nullptr;
     return DPF_OK;
 }
 
@@ -351,12 +370,31 @@ int dpf_hash_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, co
     });
 }
 
+// DPF_TRACE=1: host wall-clock per phase of a fit (each phase ends with a stream synchronisation), to stderr
+struct PhaseTrace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t;
+    explicit PhaseTrace(cudaStream_t s) : st(s), t(std::chrono::steady_clock::now()) {
+        const char* e = getenv("DPF_TRACE");
+        on = e && e[0] == '1';
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dpf] %-24s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_device) {
     require_ready(h, false);
     DPF_REQUIRE(n > 0 && X, DPF_ERR_INVALID, "empty fit");
     DPF_REQUIRE(h->n == 0 || h->dense, DPF_ERR_STATE, "index holds sparse vectors");
     DPF_REQUIRE(h->n + n < (1LL << 31), DPF_ERR_INVALID, "ids are int32");
     begin_profile(h);
+    PhaseTrace tr(h->stream);
     const int d = h->cfg.d;
     h->dense = true;
     const double* Xnew;
@@ -368,14 +406,19 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     } else {
         DPF_REQUIRE(!h->X_borrowed, DPF_ERR_STATE, "cannot append to a borrowed device buffer");
         h->X.grow_keep((size_t)(h->n + n) * d, (size_t)h->n * d, h->stream);
+        tr.mark("store: allocate");
         h2d(h, h->X.p + (size_t)h->n * d, X, (size_t)n * d);
+        tr.mark("store: host -> device");
         h->Xdev = h->X.p;
         Xnew = h->X.p + (size_t)h->n * d;
     }
     grow_keys(h, n);
+    tr.mark("keys: allocate");
     hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
+    tr.mark("hash");
     h->n += n;
     build_forest(h);
+    tr.mark("forest");
     h->stats[DPF_STAT_SIZE] = h->n;
     DPF_CUDA(cudaStreamSynchronize(h->stream));
     end_profile(h);

@@ -32,6 +32,13 @@ struct Error {
         if (!(cond)) throw ::dpf::Error{(code), (text)};     \
     } while (0)
 
+// Device memory is stream-ordered: every buffer of a handle is carved out of the device's default memory pool with
+// cudaMallocAsync / cudaFreeAsync on the stream the handle works on (dpf_create raises the pool's release threshold,
+// so freed blocks stay cached in the pool).  A re-build or a new handle therefore re-uses warm blocks without a
+// device-wide synchronisation, which is what cudaMalloc/cudaFree cost inside the build.  `tl_stream` is the stream
+// of the API call running on this thread (set by every entry point before it touches a buffer).
+extern thread_local cudaStream_t tl_stream;
+
 // owning device buffer (grow-only); all allocations of a handle go through these
 template <class T>
 struct DevBuf {
@@ -42,7 +49,7 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, tl_stream);
         p = nullptr;
         cap = 0;
     }
@@ -50,7 +57,7 @@ struct DevBuf {
     void reserve(size_t n) {
         if (n <= cap) return;
         release();
-        DPF_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+        DPF_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), tl_stream));
         cap = n;
     }
     // ensure capacity >= n elements, keeping the first `keep` elements
@@ -58,10 +65,9 @@ struct DevBuf {
         if (n <= cap) return;
         size_t ncap = n + n / 4;
         T* q = nullptr;
-        DPF_CUDA(cudaMalloc((void**)&q, ncap * sizeof(T)));
+        DPF_CUDA(cudaMallocAsync((void**)&q, ncap * sizeof(T), st));
         if (keep && p) DPF_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
-        DPF_CUDA(cudaStreamSynchronize(st));
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         p = q;
         cap = ncap;
     }
@@ -168,6 +174,9 @@ struct dpf_index {
     dpf::DevBuf<int32_t> pair_q;
     dpf::DevBuf<unsigned long long> pair_key, pair_key_alt;
     dpf::DevBuf<double> scores;
+    dpf::DevBuf<uint32_t> bm_flag, bm_run_start, bm_ucnt, bm_sorted_seg, bm_counts;  // runs / units of the sorted pairs
+    dpf::DevBuf<int32_t> bm_sorted_q;
+    dpf::DevBuf<char> bm_units;
     unsigned long long* bm_sorted = nullptr;   // pair keys sorted by bucket (points into pair_key_alt / sk64a)
     int64_t bm_npairs = 0;
     dpf::DevBuf<int64_t> unit_off;

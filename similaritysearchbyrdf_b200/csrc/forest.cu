@@ -29,19 +29,43 @@ __device__ __forceinline__ int slot_at(int32_t h, int level, int nb, int mask) {
     return (int)(((uint32_t)h >> (nb * level)) & (uint32_t)mask);
 }
 
-// depth-1 code of an entry: ((t*R + pid*SEG + seg) * W + slot(MAXL))
-__global__ void __launch_bounds__(256)
+// depth-1 code of an entry: ((t*R + pid*SEG + seg) * W + slot(MAXL)).  One CTA counts a chunk of one table's
+// entries: in a shared-memory histogram over the table's R*W codes when that fits (the default geometry has 4096),
+// flushed with one global atomic per non-empty bin, else with global atomics per entry.
+constexpr int CD_THREADS = 256;
+constexpr int CD_ITEMS = 64;                       // entries per thread
+constexpr int CD_CHUNK = CD_THREADS * CD_ITEMS;    // entries per CTA
+constexpr int CD_MAX_SMEM_BINS = 8192;
+
+template <bool SMEM>
+__global__ void __launch_bounds__(CD_THREADS)
 k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pids, int64_t n, int64_t ld, TreeParams tp,
                int rank, int world, int32_t* __restrict__ cnt1) {
+    extern __shared__ int32_t hist[];
     const int t = blockIdx.y;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int pid = pids[(int64_t)t * ld + i];
-    if (world > 1 && (pid % world) != rank) return;
-    const int32_t h = keys[(int64_t)t * ld + i];
-    const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
-    const int code = ((t * tp.R + pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1);
-    atomicAdd(&cnt1[code], 1);
+    const int bins = tp.R * tp.W;
+    if (SMEM) {
+        for (int b = threadIdx.x; b < bins; b += CD_THREADS) hist[b] = 0;
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * CD_CHUNK;
+    const int64_t end = min(n, base + CD_CHUNK);
+    for (int64_t i = base + threadIdx.x; i < end; i += CD_THREADS) {
+        const int pid = pids[(int64_t)t * ld + i];
+        if (world > 1 && (pid % world) != rank) continue;
+        const int32_t h = keys[(int64_t)t * ld + i];
+        const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
+        const int local = ((pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1);
+        if (SMEM) atomicAdd(&hist[local], 1);
+        else atomicAdd(&cnt1[(int64_t)t * bins + local], 1);
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < bins; b += CD_THREADS) {
+            const int c = hist[b];
+            if (c) atomicAdd(&cnt1[(int64_t)t * bins + b], c);
+        }
+    }
 }
 
 // sort keys of one table group [t0, t0+gt): field = depth-1 code relative to t0; not-owned entries get the
@@ -202,8 +226,14 @@ void build_forest(dpf_index* h) {
     {
         StageTimer tm(h, DPF_T_SORT);
         if (n > 0) {
-            const dim3 grid((unsigned)((n + 255) / 256), L);
-            k_count_depth1<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, rank, world, cnt1.p); DPF_LAUNCHED();
+            const dim3 grid((unsigned)((n + CD_CHUNK - 1) / CD_CHUNK), L);
+            const int bins = tp.R * tp.W;
+            if (bins <= CD_MAX_SMEM_BINS)
+                k_count_depth1<true><<<grid, CD_THREADS, bins * sizeof(int32_t), st>>>(h->keys.p, h->pids.p, n, ld, tp, rank,
+                                                                                      world, cnt1.p);
+            else
+                k_count_depth1<false><<<grid, CD_THREADS, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, rank, world, cnt1.p);
+            DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
         }
         exclusive_scan_i64(h, cnt1.p, start1.p, ncodes);

@@ -405,12 +405,9 @@ __device__ __forceinline__ int32_t partition_id_dev(int32_t key, const double* a
     uint32_t r = 0;
     for (int j = 0; j < pb; ++j) {
         double s = 0.0;
-        for (int i = 0; i < 32; ++i) {
-            const double a = ap[j * 32 + i];
-            if (((uint32_t)key >> i) & 1u) {
-                if (a != 0.0) s = __dadd_rn(s, a);   // a * 1.0, ascending i
-            }
-        }
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i)   // a * 1.0 for the set bits, ascending i; a clear bit adds +0.0, which leaves
+            s = __dadd_rn(s, (((uint32_t)key >> i) & 1u) ? ap[j * 32 + i] : 0.0);   // the value (and s <= 0) unchanged
         r = (r << 1) | (!(s <= 0.0) ? 1u : 0u);
     }
     int32_t pk = (int32_t)(r << (32 - pb));
@@ -442,9 +439,18 @@ k_pack_keys(const uint32_t* __restrict__ S, const int32_t* __restrict__ PQ, cons
     } else {
         const uint32_t* srow = S + i * PW;
         key = 0u;
-        for (int b = 0; b < k; ++b) {
-            const int c = ch[b];
-            key = (key << 1) | ((srow[c >> 5] >> (c & 31)) & 1u);
+        if (PW <= 4) {   // the usual case (P <= 128 distinct functions): the row's sign words live in registers
+            const uint32_t w0 = srow[0], w1 = PW > 1 ? srow[1] : 0u, w2 = PW > 2 ? srow[2] : 0u, w3 = PW > 3 ? srow[3] : 0u;
+            for (int b = 0; b < k; ++b) {
+                const int c = ch[b], wi = c >> 5;
+                const uint32_t w = wi == 0 ? w0 : (wi == 1 ? w1 : (wi == 2 ? w2 : w3));
+                key = (key << 1) | ((w >> (c & 31)) & 1u);
+            }
+        } else {
+            for (int b = 0; b < k; ++b) {
+                const int c = ch[b];
+                key = (key << 1) | ((srow[c >> 5] >> (c & 31)) & 1u);
+            }
         }
         if (k < 32) key <<= (32 - k);
     }

@@ -1,0 +1,819 @@
+// rerank_bm.cu — K5b: bucket-major re-rank on the FP64 tensor pipe.
+//
+// Replaces topKAndPrecisionScore's gather + dgemv + argsort (src/main/scala/mclab/deploy/DensevectorRDFInit.scala:
+// 472-507) for a whole query batch.  The row-major kernel in query.cu reads a candidate row once per (query,
+// candidate): 8d bytes of HBM for 2d flops.  In a batch, many queries probe the same leaf buckets (a bucket is
+// probed by every query whose key falls in it or one bit away), so the same rows are fetched again and again.
+// Here the batch is regrouped by bucket:
+//   k_probe_pairs    one (bucket, query) pair per distinct bucket a query probes (same walk as K4)
+//   radix sort       pairs by bucket start
+//   k_run_flags .. k_emit_units   runs of pairs that share a bucket, cut into units of <= 16 queries
+//   k_score_stream   a warp per unit: the unit's queries sit in registers as DMMA B fragments, the bucket's rows
+//                    stream HBM -> shared memory through a per-warp ring of TMA bulk copies (one 8d-byte copy per
+//                    row, mbarrier completion, 2 slots of 8 rows in flight per warp while a third is multiplied)
+//                    -> one score per (pair, row)
+//   k_select_pairs   per query: top-k over its score segments, de-duplicating ids reached through several tables
+//                    (their scores are bit-identical: same row, same query, same k order)
+// Per step this replaces nC_q * 8d bytes per query by ~(bucket rows * 8d) per <= 16 queries plus 16 B per (query,
+// candidate).  Candidate *sets* are unchanged (same probe), so results equal the row-major path up to summation
+// order.  Why TMA rows: tools/gather_patterns.cu — a DMMA A-fragment gather straight from HBM touches 8 rows x 64 B
+// per instruction and collapses to 2.9 TB/s at high occupancy; 1 KB bulk row copies hold 7.3 TB/s with 8 warps/SM.
+#include <cstdlib>
+
+#include "query_common.cuh"
+
+namespace dpf {
+
+constexpr int BM_QT = 32;              // pairs per group of the register-gather kernel (k_score_warps)
+constexpr int BM_KC = 128;             // largest supported d
+
+bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
+    const char* e = getenv("DPF_RERANK");
+    if (e && e[0] == 'r') return false;                        // DPF_RERANK=rowmajor forces the row-major kernel
+    return h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 &&
+           (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
+           (metric == DPF_METRIC_DOT || metric == DPF_METRIC_ANGULAR) && topk <= RR_MAXK;
+}
+
+// fill pass: pair i of (query q, table t) in (q, t, lane) order
+__global__ void __launch_bounds__(256)
+k_probe_pairs(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t q0,
+              int64_t nqc, const uint32_t* __restrict__ pair_base /* (q - q0) * L + t */,
+              unsigned long long* __restrict__ pair_key, int32_t* __restrict__ pair_q, uint32_t* __restrict__ pair_len) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= nqc * c.L) return;
+    const int64_t q = q0 + wid / c.L;
+    const int t = (int)(wid % c.L);
+    const uint32_t h = (uint32_t)qkeys[(int64_t)t * ld + q];
+    const int pid = qpids[(int64_t)t * ld + q];
+    const int seg = c.tp.seg_bits ? (int)(h >> c.tp.bucket_bits) : 0;
+    const int nprobes = probe_count(h, c.probe_mode);
+    if (nprobes < 0) return;
+    uint32_t at = pair_base[wid];
+    const long long tbase = c.f.table_base[t];
+    const int np = 1 << c.tp.pb;
+    for (int sub = 0; sub < np; ++sub) {
+        if (__popc(sub ^ pid) > c.steps) continue;
+        if (c.world > 1 && (sub % c.world) != c.rank) continue;
+        bool leader;
+        int ptr, cnt;
+        warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);
+        const uint32_t m = __ballot_sync(0xffffffffu, leader);
+        if (leader) {
+            const uint32_t i = at + __popc(m & ((1u << lane) - 1u));
+            pair_key[i] = ((unsigned long long)(tbase + ptr) << 32) | i;   // sort key: bucket start; payload: pair index
+            pair_q[i] = (int32_t)q;
+            pair_len[i] = (uint32_t)cnt;
+        }
+        at += __popc(m);
+    }
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// units: runs of sorted pairs that share a bucket, cut into pieces of <= SS_UQ queries
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SS_UQ = 16;              // queries per unit = 2 DMMA n-blocks held in registers
+constexpr int SS_WARPS = 8;            // warps per CTA, one CTA per SM
+constexpr int SS_STAGES = 3;           // ring slots per warp
+constexpr int SS_ROWS = 8;             // bucket rows per slot = DMMA M extent
+constexpr int SS_PITCH = BM_KC + 8;    // doubles; (pitch * 8 B) mod 128 == 64: conflict-free LDS.128 per quarter warp
+constexpr size_t SS_SMEM = (size_t)SS_WARPS * SS_STAGES * SS_ROWS * SS_PITCH * sizeof(double);
+
+struct __align__(16) ScoreUnit {
+    uint32_t bstart;   // bucket start in ids_sorted
+    uint32_t len;      // bucket length (rows)
+    uint32_t pos0;     // position of the unit's first pair in the sorted pair list
+    uint32_t m;        // queries in the unit (1..SS_UQ)
+};
+
+// flag[p] = 1 where a run starts; side arrays in sorted order (query index, score segment) so that the scoring
+// kernel needs one load, not a chain, per unit
+__global__ void __launch_bounds__(256)
+k_run_flags(const unsigned long long* __restrict__ sorted, int64_t npairs, const int32_t* __restrict__ pair_q,
+            const uint32_t* __restrict__ pair_seg, uint32_t* __restrict__ flag, int32_t* __restrict__ sorted_q,
+            uint32_t* __restrict__ sorted_seg) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const unsigned long long k = sorted[p];
+    flag[p] = (p == 0 || (uint32_t)(sorted[p - 1] >> 32) != (uint32_t)(k >> 32)) ? 1u : 0u;
+    const uint32_t pi = (uint32_t)k;
+    sorted_q[p] = pair_q[pi];
+    sorted_seg[p] = pair_seg[pi];
+}
+
+// run_idx = exclusive scan of flag: the flagged position p starts run run_idx[p]
+__global__ void __launch_bounds__(256)
+k_run_starts(const unsigned long long* __restrict__ sorted, int64_t npairs, const uint32_t* __restrict__ run_idx,
+             uint32_t* __restrict__ run_start, uint32_t* __restrict__ nruns_out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const bool start = p == 0 || (uint32_t)(sorted[p - 1] >> 32) != (uint32_t)(sorted[p] >> 32);
+    if (start) run_start[run_idx[p]] = (uint32_t)p;
+    if (p == npairs - 1) {
+        const uint32_t nruns = run_idx[p] + (start ? 1u : 0u);
+        run_start[nruns] = (uint32_t)npairs;
+        *nruns_out = nruns;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_run_unit_counts(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ nruns_p, int64_t cap,
+                  uint32_t* __restrict__ ucnt) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cap) return;
+    const uint32_t nruns = *nruns_p;
+    ucnt[r] = r < nruns ? (run_start[r + 1] - run_start[r] + SS_UQ - 1) / SS_UQ : 0u;
+}
+
+// uoff = exclusive scan of ucnt (cap + 1 entries: uoff[cap] = number of units)
+__global__ void __launch_bounds__(256)
+k_emit_units(const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ pair_len,
+             const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ nruns_p, const uint32_t* __restrict__ uoff,
+             int64_t cap, ScoreUnit* __restrict__ units) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cap || r >= *nruns_p) return;
+    const uint32_t p0 = run_start[r], p1 = run_start[r + 1];
+    const unsigned long long k = sorted[p0];
+    const uint32_t bstart = (uint32_t)(k >> 32), len = pair_len[(uint32_t)k];
+    uint32_t u = uoff[r];
+    for (uint32_t p = p0; p < p1; p += SS_UQ) units[u++] = ScoreUnit{bstart, len, p, min((uint32_t)SS_UQ, p1 - p)};
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk copy (sm_90+ PTX; on sm_100a: SYNCS.* and UBLKCP.S.G)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_score_stream
+//
+// Warp w of the grid walks units w, w + W, w + 2W, ... (W = warps in the grid; consecutive units — usually pieces of
+// one run — land on the warps of one CTA at the same time, so a bucket staged twice is an L2 hit the second time).
+// Each warp is its own producer and consumer: slot i of its walk (8 rows of the current unit's bucket) is fetched
+// by 8 lanes issuing one bulk copy each into ring slot i % 3, two slots ahead of the slot being multiplied.
+// Descriptor, first id window and query list of the next unit are prefetched while the current unit streams.
+// k permutation: DMMA k-step 2w takes columns 8w + 2t, k-step 2w + 1 columns 8w + 2t + 1, so that both fragment
+// elements of a thread are adjacent in memory (one LDS.128 / LDG.128 feeds two DMMAs); A and B use the same
+// permutation, the sum over k is unchanged.
+// ---------------------------------------------------------------------------------------------------------
+template <bool ANGULAR>
+__global__ void __launch_bounds__(SS_WARPS * 32, 1)
+k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q, const ScoreUnit* __restrict__ units,
+               const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ sorted_q,
+               const uint32_t* __restrict__ sorted_seg, const int32_t* __restrict__ ids_sorted, double* __restrict__ scores,
+               unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
+    constexpr int NW = BM_KC / 8;
+    extern __shared__ __align__(128) double ssm[];
+    __shared__ uint64_t bars[SS_WARPS][SS_STAGES];
+    __shared__ int4 meta[SS_WARPS][SS_STAGES];       // per slot: {unit sequence number, first row, rows, first slot of unit}
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double* ring = ssm + (size_t)warp * SS_STAGES * SS_ROWS * SS_PITCH;
+    for (int i = lane; i < SS_STAGES * SS_ROWS * SS_PITCH; i += 32) ring[i] = 0.0;   // k padding stays zero
+    if (lane == 0)
+        for (int s = 0; s < SS_STAGES; ++s) mbar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+
+    const int nw8 = (d + 7) >> 3;
+    const unsigned row_bytes = (unsigned)d * 8u;
+    const int64_t nunits = *nunits_p;
+    const int64_t W = (int64_t)gridDim.x * SS_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * SS_WARPS + warp;
+    // units of this warp: gw + k * W, k = 0 .. nmine - 1
+    const int64_t nmine = nunits > gw ? (nunits - gw + W - 1) / W : 0;
+    if (nmine == 0) return;
+
+    // ---- producer state (warp-uniform unless noted) -----------------------------------------------------------
+    int64_t p_seq = -1;                 // sequence number (k) of the unit being issued
+    uint32_t p_bstart = 0, p_len = 0, p_m = 0;
+    int p_row = 0;                      // next row of the unit to issue
+    int p_win = 0, p_win_next = 0;      // lane l: id of row p_win_base + l / + 32 + l
+    int p_win_base = 0;
+    int p_q = 0;                        // lane j < m: query index of pair j of the unit
+    uint32_t p_seg = 0;                 // lane j < m: score segment of pair j
+    // prefetched next unit (k = p_seq + 1)
+    uint4 n_desc = make_uint4(0, 0, 0, 0);
+    int n_win = 0, n_q = 0;
+    uint32_t n_seg = 0;
+    int n_state = 0;                    // 0 none, 1 descriptor requested, 2 window / query list requested
+    auto prefetch_desc = [&](int64_t k) {
+        if (k < nmine) { n_desc = __ldg(reinterpret_cast<const uint4*>(units) + (gw + k * W)); n_state = 1; }
+        else n_state = 0;
+    };
+    auto prefetch_lists = [&]() {       // needs n_desc
+        const uint32_t len = n_desc.y, pos0 = n_desc.z, m = n_desc.w;
+        n_win = __ldg(ids_sorted + n_desc.x + min((uint32_t)lane, len - 1));
+        n_q = lane < (int)m ? __ldg(sorted_q + pos0 + lane) : 0;
+        n_seg = lane < (int)m ? __ldg(sorted_seg + pos0 + lane) : 0u;
+        n_state = 2;
+    };
+    prefetch_desc(0);
+    int issued = 0, consumed = 0;
+    int64_t c_seq = -1;                 // sequence number of the unit being multiplied
+    bool p_done = false;
+    unsigned long long rows_staged = 0;
+
+    // ---- consumer state ---------------------------------------------------------------------------------------
+    double2 B[2][NW];                   // queries g (n-block 0) and 8 + g (n-block 1), columns 8w + 2t, + 1
+    uint32_t c_seg[2][2] = {{0, 0}, {0, 0}};
+    bool c_ok[2][2] = {{false, false}, {false, false}};
+    double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
+    int c_nb = 0;                       // n-blocks in use
+
+    // issue one slot; returns false when nothing can be issued now
+    auto issue = [&]() -> bool {
+        if (p_done || issued - consumed >= SS_STAGES) return false;
+        if (p_seq < 0 || p_row >= (int)p_len) {
+            // next unit; the consumer takes a unit's query list from the producer registers when it reaches the
+            // unit's first slot, so the producer stays at most one unit ahead
+            if (p_seq > c_seq) return false;
+            if (n_state == 0) { p_done = true; return false; }
+            if (n_state == 1) prefetch_lists();
+            p_seq++;
+            p_bstart = n_desc.x; p_len = n_desc.y; p_m = n_desc.w;
+            p_win = n_win; p_q = n_q; p_seg = n_seg;
+            p_row = 0; p_win_base = 0;
+            p_win_next = __ldg(ids_sorted + p_bstart + min((uint32_t)(32 + lane), p_len - 1));
+            prefetch_desc(p_seq + 1);
+        } else if (n_state == 1) {
+            prefetch_lists();
+        }
+        if (p_row >= p_win_base + 32) {
+            p_win = p_win_next;
+            p_win_base += 32;
+            p_win_next = __ldg(ids_sorted + p_bstart + min((uint32_t)(p_win_base + 32 + lane), p_len - 1));
+        }
+        const int s = issued % SS_STAGES;
+        const int nrows = min(SS_ROWS, (int)p_len - p_row);
+        if (lane == 0) {
+            meta[warp][s] = make_int4((int)p_seq, p_row, nrows, p_row == 0 ? 1 : 0);
+            mbar_expect_tx(&bars[warp][s], (unsigned)nrows * row_bytes);
+        }
+        __syncwarp();
+        const int id = __shfl_sync(0xffffffffu, p_win, (p_row - p_win_base) + (lane & 7));
+        if (lane < nrows) bulk_g2s(ring + (size_t)(s * SS_ROWS + lane) * SS_PITCH, X + (int64_t)id * d, row_bytes, &bars[warp][s]);
+        p_row += nrows;
+        rows_staged += nrows;
+        issued++;
+        return true;
+    };
+
+    for (;;) {
+        while (issue()) {}
+        if (issued == consumed) break;
+        const int s = consumed % SS_STAGES;
+        const int4 mt = meta[warp][s];
+        if (mt.w) {
+            // first slot of a unit: its query list is in the producer registers (p_seq == mt.x, see issue())
+            c_seq = mt.x;
+            const int m = (int)p_m;
+            c_nb = (m + 7) >> 3;
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                const int qi = __shfl_sync(0xffffffffu, p_q, min(8 * nb + g, m - 1));
+                const double* qsrc = Q + (int64_t)qi * d + 2 * t;
+#pragma unroll
+                for (int w = 0; w < NW; ++w)
+                    B[nb][w] = (nb < c_nb && w < nw8 && 8 * w + 2 * t < d) ? __ldg(reinterpret_cast<const double2*>(qsrc + 8 * w))
+                                                                          : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int qj = 8 * nb + 2 * t + e;
+                    c_seg[nb][e] = __shfl_sync(0xffffffffu, p_seg, min(qj, m - 1));
+                    c_ok[nb][e] = qj < m;
+                }
+            }
+            if (ANGULAR) {
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    double sq = 0.0;        // ||query 8nb + g||^2: this thread's columns, then the 4 threads of the group
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { sq = fma(B[nb][w].x, B[nb][w].x, sq); sq = fma(B[nb][w].y, B[nb][w].y, sq); }
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                    const double nrm = sqrt(sq);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) c_qn[nb][e] = __shfl_sync(0xffffffffu, nrm, (2 * t + e) * 4);
+                }
+            }
+        }
+        mbar_wait(&bars[warp][s], (unsigned)((consumed / SS_STAGES) & 1));
+        const double* ar = ring + (size_t)(s * SS_ROWS + g) * SS_PITCH + 2 * t;
+        double acc[2][2][2];                // [n-block][even / odd k-step chain][column]
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) acc[nb][c][0] = acc[nb][c][1] = 0.0;
+        double xn = 0.0;
+        if (c_nb == 2) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                if (w < nw8) {
+                    const double2 a = *reinterpret_cast<const double2*>(ar + 8 * w);
+                    dmma884(acc[0][0][0], acc[0][0][1], a.x, B[0][w].x);
+                    dmma884(acc[1][0][0], acc[1][0][1], a.x, B[1][w].x);
+                    dmma884(acc[0][1][0], acc[0][1][1], a.y, B[0][w].y);
+                    dmma884(acc[1][1][0], acc[1][1][1], a.y, B[1][w].y);
+                    if (ANGULAR) { xn = fma(a.x, a.x, xn); xn = fma(a.y, a.y, xn); }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                if (w < nw8) {
+                    const double2 a = *reinterpret_cast<const double2*>(ar + 8 * w);
+                    dmma884(acc[0][0][0], acc[0][0][1], a.x, B[0][w].x);
+                    dmma884(acc[0][1][0], acc[0][1][1], a.y, B[0][w].y);
+                    if (ANGULAR) { xn = fma(a.x, a.x, xn); xn = fma(a.y, a.y, xn); }
+                }
+            }
+        }
+        double xnr = 1.0;
+        if (ANGULAR) {
+            xn += __shfl_xor_sync(0xffffffffu, xn, 1);
+            xn += __shfl_xor_sync(0xffffffffu, xn, 2);
+            xnr = sqrt(xn);
+        }
+        // thread (g, t) holds (row mt.y + g, queries 8nb + 2t, 8nb + 2t + 1)
+        if (g < mt.z) {
+            const uint32_t row = (uint32_t)(mt.y + g);
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (c_ok[nb][e]) {
+                        const double v = acc[nb][0][e] + acc[nb][1][e];
+                        scores[(size_t)c_seg[nb][e] + row] = ANGULAR ? v / (c_qn[nb][e] * xnr) : v;
+                    }
+        }
+        __syncwarp();                       // every lane has read the slot before it is refilled
+        consumed++;
+    }
+    if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], rows_staged); }
+}
+
+// Warp-autonomous variant (d even): every warp is an independent worker that pulls groups of BM_QT sorted pairs
+// from a counter.  A-operand fragments (bucket rows) go straight from global memory to registers with LDG.128 —
+// 16 independent 128-bit loads per 8-row block, two blocks in flight per warp (register double buffering), no
+// shared-memory staging of rows and no CTA barrier — using a k permutation (k-step 2w takes columns 8w+2t, k-step
+// 2w+1 takes 8w+2t+1) so that each thread's two fragment elements are adjacent in memory; the B operand (up to
+// 8*NB queries of the run) sits in the warp's private slice of shared memory with the same permutation.
+constexpr int WQ_PITCH = BM_KC + 8;           // (pitch * 8) mod 128 == 64: conflict-free LDS.128 per quarter warp
+
+template <int NB>
+struct WarpCfg {
+    static constexpr int WQ = 8 * NB;                                               // queries per pass
+    static constexpr int WARPS = (NB == 1) ? 8 : (NB == 2 ? 8 : 6);                 // shared memory bound
+    static constexpr size_t SMEM = (size_t)WARPS * WQ * WQ_PITCH * sizeof(double);
+};
+
+template <bool ANGULAR, int NB>
+__global__ void __launch_bounds__(WarpCfg<NB>::WARPS * 32, 1)
+k_score_warps(const double* __restrict__ X, int d, const double* __restrict__ Q,
+              const unsigned long long* __restrict__ pair_key /* sorted by bucket */, int64_t npairs,
+              const int32_t* __restrict__ pair_q, const uint32_t* __restrict__ pair_len,
+              const uint32_t* __restrict__ pair_seg, const int32_t* __restrict__ ids_sorted, double* __restrict__ scores,
+              int* __restrict__ next_group, unsigned long long* __restrict__ stat /* [0] runs, [1] rows staged */) {
+    constexpr int WQ = WarpCfg<NB>::WQ;
+    constexpr int NW = BM_KC / 8;
+    extern __shared__ double wsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double* Qw = wsm + warp * WQ * WQ_PITCH;
+    for (int i = lane; i < WQ * WQ_PITCH; i += 32) Qw[i] = 0.0;     // k padding stays zero: only columns < d are written
+    __syncwarp();
+    const int nw8 = (d + 7) >> 3;                                    // 8-column windows in use
+    const int64_t ngroups = (npairs + BM_QT - 1) / BM_QT;
+    unsigned long long runs = 0, rows_staged = 0;
+    for (;;) {
+        long long grp = 0;
+        if (lane == 0) grp = atomicAdd(next_group, 1);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if (grp >= ngroups) break;
+        const int64_t p0 = grp * BM_QT;
+        const int np = (int)min((int64_t)BM_QT, npairs - p0);
+        const unsigned long long mykey = lane < np ? pair_key[p0 + lane] : ~0ULL;
+        const uint32_t mybucket = (uint32_t)(mykey >> 32);
+        int j0 = 0;
+        while (j0 < np) {
+            const uint32_t bstart = __shfl_sync(0xffffffffu, mybucket, j0);
+            const uint32_t same = __ballot_sync(0xffffffffu, lane >= j0 && lane < np && mybucket == bstart);
+            const int m = __popc(same);                              // sorted => the run is lanes j0 .. j0+m-1
+            const uint32_t first_pair = (uint32_t)__shfl_sync(0xffffffffu, mykey, j0);
+            const int blen = (int)__ldg(pair_len + first_pair);
+            const int32_t* bids = ids_sorted + bstart;
+            runs++;
+            for (int c0 = j0; c0 < j0 + m; c0 += WQ) {
+                const int mc = min(WQ, j0 + m - c0);
+                const int nbu = (mc + 7) >> 3;                       // n-blocks in use this pass
+                rows_staged += blen;
+                __syncwarp();
+                {   // stage this pass's queries (row r of Qw = pair c0 + r): lane r fetches its query index, then the
+                    // rows are copied with all loads of 4 queries in flight at a time
+                    const uint32_t mypi = (uint32_t)mykey;
+                    const int myq = (lane >= c0 && lane < c0 + mc) ? __ldg(pair_q + mypi) : 0;
+                    for (int r0 = 0; r0 < mc; r0 += 4) {
+                        double2 v[4][BM_KC / 64];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int qidx = __shfl_sync(0xffffffffu, myq, min(c0 + r0 + u, c0 + mc - 1));
+                            const double* qsrc = Q + (int64_t)qidx * d;
+#pragma unroll
+                            for (int i = 0; i < BM_KC / 64; ++i) {
+                                const int cc = 2 * lane + 64 * i;
+                                v[u][i] = (cc < d) ? __ldg(reinterpret_cast<const double2*>(qsrc + cc)) : make_double2(0.0, 0.0);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (r0 + u < mc) {
+#pragma unroll
+                                for (int i = 0; i < BM_KC / 64; ++i) {
+                                    const int cc = 2 * lane + 64 * i;
+                                    if (cc < d) *reinterpret_cast<double2*>(Qw + (r0 + u) * WQ_PITCH + cc) = v[u][i];
+                                }
+                            }
+                    }
+                }
+                // score segments of the queries this thread's accumulators belong to (columns 8nb+2t, 8nb+2t+1)
+                int64_t seg[NB][2];
+                bool qok[NB][2];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int qi = 8 * nb + 2 * t + e;
+                        const uint32_t pi = (uint32_t)__shfl_sync(0xffffffffu, mykey, min(c0 + qi, np - 1));
+                        qok[nb][e] = qi < mc;
+                        seg[nb][e] = qok[nb][e] ? (int64_t)__ldg(pair_seg + pi) : 0;
+                    }
+                __syncwarp();
+                double qn[NB][2];
+                if (ANGULAR) {
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            double s = 0;
+                            const double* qq = Qw + (8 * nb + 2 * t + e) * WQ_PITCH;
+                            for (int cc = 0; cc < d; ++cc) s = fma(qq[cc], qq[cc], s);
+                            qn[nb][e] = sqrt(s);
+                        }
+                }
+                const double* bq = Qw + g * WQ_PITCH + 2 * t;
+
+                // row ids: a 32-row window per coalesced load, the next window prefetched one window ahead
+                int idwin = __ldg(bids + min(lane, blen - 1));
+                int idwin_next = __ldg(bids + min(32 + lane, blen - 1));
+                int win_base = 0;
+                auto load_block = [&](double2 (&a)[NW], int rb) {
+                    if (rb >= win_base + 32) {            // warp-uniform
+                        idwin = idwin_next;
+                        win_base += 32;
+                        idwin_next = __ldg(bids + min(win_base + 32 + lane, blen - 1));
+                    }
+                    const int id = __shfl_sync(0xffffffffu, idwin, (rb - win_base) + g);
+                    const double* xr = X + (int64_t)id * d + 2 * t;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w)
+                        if (w < nw8)
+                            a[w] = (8 * w + 2 * t < d) ? __ldg(reinterpret_cast<const double2*>(xr + 8 * w)) : make_double2(0.0, 0.0);
+                };
+                auto compute_block = [&](const double2 (&a)[NW], int rb) {
+                    double acc[NB][2];
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+                    double xn = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        if (w < nw8) {
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) {
+                                if (nb < nbu) {
+                                    const double2 b = *reinterpret_cast<const double2*>(bq + nb * 8 * WQ_PITCH + 8 * w);
+                                    dmma884(acc[nb][0], acc[nb][1], a[w].x, b.x);
+                                    dmma884(acc[nb][0], acc[nb][1], a[w].y, b.y);
+                                }
+                            }
+                            if (ANGULAR) { xn = fma(a[w].x, a[w].x, xn); xn = fma(a[w].y, a[w].y, xn); }
+                        }
+                    }
+                    double xnr = 1.0;
+                    if (ANGULAR) {
+                        xn += __shfl_xor_sync(0xffffffffu, xn, 1);
+                        xn += __shfl_xor_sync(0xffffffffu, xn, 2);
+                        xnr = sqrt(xn);
+                    }
+                    const int row = rb + g;
+                    if (row < blen) {
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                if (qok[nb][e]) scores[seg[nb][e] + row] = ANGULAR ? acc[nb][e] / (qn[nb][e] * xnr) : acc[nb][e];
+                    }
+                };
+
+                double2 A0[NW], A1[NW];
+                load_block(A0, 0);
+                for (int rb = 0; rb < blen; rb += 16) {
+                    const bool has1 = rb + 8 < blen;
+                    if (has1) load_block(A1, rb + 8);
+                    compute_block(A0, rb);
+                    if (rb + 16 < blen) load_block(A0, rb + 16);
+                    if (has1) compute_block(A1, rb + 8);
+                }
+            }
+            j0 += m;
+        }
+    }
+    if (lane == 0) { atomicAdd(&stat[0], runs); atomicAdd(&stat[1], rows_staged); }
+}
+
+template <bool ANGULAR, int NB>
+static void launch_score_warps(dpf_index* h, const double* Qd, int64_t npairs, int metric, unsigned long long* bm_stat) {
+    (void)metric;
+    static bool attr = false;
+    if (!attr) {
+        DPF_CUDA(cudaFuncSetAttribute(k_score_warps<ANGULAR, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)WarpCfg<NB>::SMEM));
+        attr = true;
+    }
+    int* next_group = h->counters.p + 18;
+    DPF_CUDA(cudaMemsetAsync(next_group, 0, sizeof(int), h->stream));
+    const int64_t groups = (npairs + BM_QT - 1) / BM_QT;
+    const unsigned grid = (unsigned)std::min<int64_t>((groups + WarpCfg<NB>::WARPS - 1) / WarpCfg<NB>::WARPS, (int64_t)h->num_sms);
+    k_score_warps<ANGULAR, NB><<<grid, WarpCfg<NB>::WARPS * 32, WarpCfg<NB>::SMEM, h->stream>>>(
+        h->Xdev, h->cfg.d, Qd, h->bm_sorted, npairs, h->pair_q.p, h->pair_len.p, h->pair_seg.p, h->ids_sorted.p, h->scores.p,
+        next_group, bm_stat);
+}
+
+// per-query selection from its score segments: one CTA per query, a warp walks whole pairs
+__global__ void __launch_bounds__(RR_THREADS)
+k_select_pairs(int64_t q0, int L, const uint32_t* __restrict__ pair_base, const unsigned long long* __restrict__ pair_key_unsorted,
+               const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg,
+               const int32_t* __restrict__ ids_sorted, const double* __restrict__ scores, const int32_t* __restrict__ qids,
+               int self_exclude, int K, int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
+    extern __shared__ double rsm[];
+    double* lkeys = rsm;                                 // RR_WARPS x K
+    int* lids = reinterpret_cast<int*>(lkeys + RR_WARPS * K);
+    __shared__ int s_counts[RR_WARPS];
+    const int64_t ql = blockIdx.x, q = q0 + ql;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* mykeys = lkeys + warp * K;
+    int* myids = lids + warp * K;
+    const uint32_t pbeg = pair_base[ql * L], pend = pair_base[(ql + 1) * L];
+    const int qid = qids ? qids[q] : INT32_MIN;
+    const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
+    int count = 0;
+    // a warp walks whole pairs; SEL_U x 32 entries of a segment are loaded before any is examined (the loop is
+    // otherwise one dependent load per iteration), and the next pair's descriptor is fetched one pair ahead
+    constexpr int SEL_U = 4;
+    uint32_t p = pbeg + warp;
+    uint32_t n_bstart = 0, n_seg = 0;
+    int n_len = 0;
+    if (p < pend) { n_bstart = (uint32_t)(pair_key_unsorted[p] >> 32); n_len = (int)pair_len[p]; n_seg = pair_seg[p]; }
+    for (; p < pend; p += RR_WARPS) {
+        const uint32_t bstart = n_bstart;
+        const int len = n_len;
+        const double* sc = scores + n_seg;
+        const int32_t* ids = ids_sorted + bstart;
+        if (p + RR_WARPS < pend) {
+            n_bstart = (uint32_t)(pair_key_unsorted[p + RR_WARPS] >> 32);
+            n_len = (int)pair_len[p + RR_WARPS];
+            n_seg = pair_seg[p + RR_WARPS];
+        }
+        for (int j0 = 0; j0 < len; j0 += 32 * SEL_U) {
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            const int j = j0 + lane;
+            const double k0 = j < len ? sc[j] : nan, k1 = j + 32 < len ? sc[j + 32] : nan;
+            const double k2 = j + 64 < len ? sc[j + 64] : nan, k3 = j + 96 < len ? sc[j + 96] : nan;
+            const int i0 = j < len ? __ldg(ids + j) : -1, i1 = j + 32 < len ? __ldg(ids + j + 32) : -1;
+            const int i2 = j + 64 < len ? __ldg(ids + j + 64) : -1, i3 = j + 96 < len ? __ldg(ids + j + 96) : -1;
+            auto examine = [&](double key, int id) {
+                bool cand = (key == key) && !(excl && id == qid);
+                if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
+                uint32_t todo = __ballot_sync(0xffffffffu, cand);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const double kk = __shfl_sync(0xffffffffu, key, src);
+                    const int ii = __shfl_sync(0xffffffffu, id, src);
+                    // the same id reached through another table carries a bit-identical score: keep it once
+                    bool dup = false;
+                    for (int base = 0; base < count; base += 32) {
+                        const int i = base + lane;
+                        dup |= __any_sync(0xffffffffu, i < count && myids[i] == ii);
+                    }
+                    if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
+                }
+            };
+            static_assert(SEL_U == 4, "examine() calls below are written out");
+            examine(k0, i0);
+            examine(k1, i1);
+            examine(k2, i2);
+            examine(k3, i3);
+        }
+    }
+    if (lane == 0) s_counts[warp] = count;
+    __syncthreads();
+    if (warp == 0) {
+        int head = 0, last = -1;
+        const int mycount = lane < RR_WARPS ? s_counts[lane] : 0;
+        for (int r = 0; r < K; ++r) {
+            double bk;
+            int bi, bl;
+            for (;;) {
+                bk = 0; bi = 0x7fffffff; bl = -1;
+                if (lane < RR_WARPS && head < mycount) { bk = lkeys[lane * K + head]; bi = lids[lane * K + head]; bl = lane; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                    if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+                }
+                if (bl < 0) break;
+                if (lane == bl) head++;
+                if (bi != last) break;                   // duplicate across warps: skip
+            }
+            if (lane == 0) {
+                ids_out[q * K + r] = bl >= 0 ? bi : -1;
+                score_out[q * K + r] = bl >= 0 ? bk : __longlong_as_double(0x7ff8000000000000LL);
+            }
+            if (bl >= 0) last = bi;
+        }
+    }
+}
+
+__global__ void k_copy_u32(const uint32_t* __restrict__ a, uint32_t* __restrict__ b, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i];
+}
+
+
+// no bucket probed by any query of the chunk: every result row is padding (-1, NaN)
+__global__ void k_topk_select_empty(int64_t q0, int64_t nqc, int K, int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nqc * K) return;
+    ids_out[q0 * K + i] = -1;
+    score_out[q0 * K + i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+
+// runs of the sorted pair list -> h->units (device), number of units in h->bm_counts[1]
+static void build_units(dpf_index* h, int64_t npairs) {
+    cudaStream_t st = h->stream;
+    const unsigned gp = (unsigned)((npairs + 255) / 256);
+    h->bm_flag.reserve(npairs + 1);
+    h->bm_run_start.reserve(npairs + 2);
+    h->bm_ucnt.reserve(npairs + 2);
+    h->bm_sorted_q.reserve(npairs);
+    h->bm_sorted_seg.reserve(npairs);
+    h->bm_units.reserve((size_t)npairs * sizeof(ScoreUnit));
+    h->bm_counts.reserve(4);
+    k_run_flags<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->pair_q.p, h->pair_seg.p, h->bm_flag.p, h->bm_sorted_q.p,
+                                    h->bm_sorted_seg.p); DPF_LAUNCHED();
+    exclusive_scan_u32(h, h->bm_flag.p, npairs);
+    k_run_starts<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_counts.p); DPF_LAUNCHED();
+    k_run_unit_counts<<<(unsigned)((npairs + 1 + 255) / 256), 256, 0, st>>>(h->bm_run_start.p, h->bm_counts.p, npairs + 1,
+                                                                            h->bm_ucnt.p); DPF_LAUNCHED();
+    exclusive_scan_u32(h, h->bm_ucnt.p, npairs + 1);      // bm_ucnt[r] = first unit of run r; [npairs] = number of units
+    k_emit_units<<<gp, 256, 0, st>>>(h->bm_sorted, h->pair_len.p, h->bm_run_start.p, h->bm_counts.p, h->bm_ucnt.p, npairs,
+                                     reinterpret_cast<ScoreUnit*>(h->bm_units.p)); DPF_LAUNCHED();
+    DPF_CUDA(cudaMemcpyAsync(h->bm_counts.p + 1, h->bm_ucnt.p + npairs, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    DPF_CUDA(cudaGetLastError());
+}
+
+void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1,
+                       int64_t entries_ub, int topk, int metric, int32_t* ids_out, double* score_out) {
+    const ProbeCtx c = make_ctx(h, steps, probe_mode);
+    cudaStream_t st = h->stream;
+    const int64_t nqc = q1 - q0;
+    const int L = c.L, d = h->cfg.d;
+    if (nqc <= 0) return;
+    DPF_REQUIRE(h->h_table_base[L] < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: more than 2^32 forest entries");
+    DPF_REQUIRE(entries_ub < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: chunk too large");
+    const char* ev = getenv("DPF_BM_KERNEL");
+    const bool use_stream = !(ev && ev[0] == 'w') && (reinterpret_cast<uintptr_t>(Qd) & 15) == 0;   // =warps: register-gather kernel
+    // pair offsets of this chunk = exclusive scan of the per-(query, table) bucket counts from the probe pass
+    const int64_t nslots = nqc * L + 1;
+    h->pair_base.reserve(nslots);
+    {
+        StageTimer tm(h, DPF_T_EXPAND);
+        k_copy_u32<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->pair_cnt.p + q0 * L, h->pair_base.p, nslots - 1); DPF_LAUNCHED();
+        DPF_CUDA(cudaMemsetAsync(h->pair_base.p + nslots - 1, 0, sizeof(uint32_t), st));
+        exclusive_scan_u32(h, h->pair_base.p, nslots);
+        uint32_t npairs32 = 0;
+        DPF_CUDA(cudaMemcpyAsync(&npairs32, h->pair_base.p + nslots - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        DPF_CUDA(cudaStreamSynchronize(st));
+        const int64_t npairs = npairs32;
+        if (npairs == 0) {
+            // nothing probed: all rows padded
+            h->ucnt.reserve(nqc + 1);
+            h->unit_off.reserve(nqc + 2);
+            DPF_CUDA(cudaMemsetAsync(h->unit_off.p, 0, (nqc + 2) * sizeof(int64_t), st));
+            k_topk_select_empty<<<(unsigned)((nqc * topk + 255) / 256), 256, 0, st>>>(q0, nqc, topk, ids_out, score_out); DPF_LAUNCHED();
+            DPF_CUDA(cudaGetLastError());
+            return;
+        }
+        h->pair_key.reserve(npairs);
+        h->pair_key_alt.reserve(npairs);
+        h->pair_q.reserve(npairs);
+        h->pair_len.reserve(npairs + 1);
+        h->pair_seg.reserve(npairs + 1);
+        h->scores.reserve((size_t)std::max<int64_t>(entries_ub, 1));
+        const int64_t warps = nqc * L;
+        k_probe_pairs<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->pair_base.p,
+                                                                    h->pair_key.p, h->pair_q.p, h->pair_len.p); DPF_LAUNCHED();
+        DPF_CUDA(cudaGetLastError());
+        k_copy_u32<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pair_len.p, h->pair_seg.p, npairs); DPF_LAUNCHED();
+        exclusive_scan_u32(h, h->pair_seg.p, npairs);
+        // sort a copy of the keys by bucket start (bits 32..); the unsorted array stays for the selection pass
+        DPF_CUDA(cudaMemcpyAsync(h->pair_key_alt.p, h->pair_key.p, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        int ebits = 1;
+        while ((1LL << ebits) < h->h_table_base[L]) ebits++;
+        h->sk64a.reserve(npairs);
+        unsigned long long *a = h->pair_key_alt.p, *b = h->sk64a.p;
+        radix_sort_keys_u64(h, &a, &b, npairs, 32, 32 + ebits);
+        h->bm_sorted = a;
+        h->bm_npairs = npairs;
+        if (use_stream) build_units(h, npairs);
+    }
+    {
+        StageTimer tm(h, DPF_T_RERANK);
+        const int64_t npairs = h->bm_npairs;
+        unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(h->counters.p + 26);   // cleared by probe_count_all
+        h->stats[DPF_STAT_BM_PAIRS] += npairs;
+        const bool ang = metric == DPF_METRIC_ANGULAR;
+        if (use_stream) {
+            static bool attr = false;
+            if (!attr) {
+                DPF_CUDA(cudaFuncSetAttribute(k_score_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+                DPF_CUDA(cudaFuncSetAttribute(k_score_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+                attr = true;
+            }
+            const ScoreUnit* units = reinterpret_cast<const ScoreUnit*>(h->bm_units.p);
+            if (ang)
+                k_score_stream<true><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->bm_sorted_q.p,
+                                                                               h->bm_sorted_seg.p, h->ids_sorted.p, h->scores.p, bm_stat);
+            else
+                k_score_stream<false><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->bm_sorted_q.p,
+                                                                                h->bm_sorted_seg.p, h->ids_sorted.p, h->scores.p, bm_stat);
+        } else {
+            const char* nbv = getenv("DPF_BM_NB");
+            const int nb = nbv ? atoi(nbv) : 2;
+            if (nb <= 1) { if (ang) launch_score_warps<true, 1>(h, Qd, npairs, metric, bm_stat); else launch_score_warps<false, 1>(h, Qd, npairs, metric, bm_stat); }
+            else if (nb == 2) { if (ang) launch_score_warps<true, 2>(h, Qd, npairs, metric, bm_stat); else launch_score_warps<false, 2>(h, Qd, npairs, metric, bm_stat); }
+            else { if (ang) launch_score_warps<true, 4>(h, Qd, npairs, metric, bm_stat); else launch_score_warps<false, 4>(h, Qd, npairs, metric, bm_stat); }
+        }
+        DPF_LAUNCHED();
+        DPF_CUDA(cudaGetLastError());
+    }
+    {
+        StageTimer tm(h, DPF_T_SELECT);
+        const size_t smem = (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
+        k_select_pairs<<<(unsigned)nqc, RR_THREADS, smem, st>>>(q0, L, h->pair_base.p, h->pair_key.p, h->pair_len.p, h->pair_seg.p,
+                                                                 h->ids_sorted.p, h->scores.p, qk.qids,
+                                                                 h->cfg.self_exclude_small_ids, topk, ids_out, score_out); DPF_LAUNCHED();
+        DPF_CUDA(cudaGetLastError());
+    }
+}
+
+}  // namespace dpf
