@@ -245,6 +245,63 @@ def test_rerank_given_same_candidates_odd_dim():
         assert (ig[0] == -1).all() and np.isnan(sg[0]).all()
 
 
+# ---- K5b: bucket-major re-rank (rerank_bm.cu) ----------------------------------------------------------------
+@pytest.mark.parametrize("d", [8, 36, 100, 128])
+@pytest.mark.parametrize("metric", [B.METRIC_DOT, B.METRIC_ANGULAR])
+def test_topk_bucket_major_many_queries_share_buckets(d, metric):
+    """Hundreds of queries probe the same leaf buckets: runs of pairs longer than one unit (16 queries), both DMMA
+    n-blocks in use, partial last 8-column window (d = 36, 100), the smallest row a bulk copy can move (d = 8)."""
+    rng = np.random.default_rng(100 + d)
+    centres = rng.standard_normal((12, d))
+    X = np.repeat(centres, 250, axis=0) + 0.05 * rng.standard_normal((3000, d))
+    A, chain, Ap = U.make_functions(d, family_size=max(40, d), table_num=3, permutation_num=2, seed=31 + d)
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=30); ix = U.make_index(d, A, chain, Ap, bucket_overflow=30)
+    o.fit_dense(X); ix.fit_dense(X)
+    Qs = X[::5] + 0.01 * rng.standard_normal((600, d))
+    io, so = o.query_topk_dense(Qs, None, 1, 10, metric)
+    ig, sg = ix.query_topk_dense(Qs, None, 1, 10, metric)
+    U.assert_topk_close(io, so, ig, sg)
+    st = ix.stats()
+    assert st["bm_pairs"] > 0 and st["bm_runs"] > 0, "the bucket-major path did not run"
+    assert st["bm_pairs"] > 16 * 3 * 2, "expected long runs of pairs"
+
+
+def test_topk_bucket_major_equals_row_major_bitwise_on_integer_data(monkeypatch):
+    """Integer-valued data: every dot product is exact in FP64 whatever the summation order, so the bucket-major
+    kernels (DMMA) and the row-major kernel (FMA) must agree bit for bit — ids and scores."""
+    X, Q = synth.config2(n=60_000, nq=512, d=128)
+    A, chain = synth.angle_family(128, 128, 10, 3, 32, 88389)
+    Ap = synth.partitioner_family(30, 3, 88390)
+    ix = U.make_index(128, A, chain, Ap, bucket_overflow=100)
+    ix.fit_dense(X)
+    res = {}
+    for name, env in (("stream", {}), ("warps", {"DPF_BM_KERNEL": "warps"}), ("rowmajor", {"DPF_RERANK": "rowmajor"})):
+        for k_, v in env.items():
+            monkeypatch.setenv(k_, v)
+        res[name] = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
+        bm = ix.stats()["bm_pairs"]
+        assert (bm > 0) == (name != "rowmajor")
+        for k_ in env:
+            monkeypatch.delenv(k_)
+    for name in ("stream", "warps"):
+        assert np.array_equal(res[name][0], res["rowmajor"][0]), name
+        assert np.array_equal(res[name][1], res["rowmajor"][1]), name
+
+
+def test_topk_bucket_major_self_exclusion_and_qids():
+    """qids given: the Integer-cache quirk (ids -128..127 never return themselves) also holds on the bucket-major path."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((2000, 64))
+    A, chain, Ap = U.make_functions(64, family_size=64, table_num=4, permutation_num=2, seed=9)
+    o = U.make_oracle(64, A, chain, Ap, bucket_overflow=50); ix = U.make_index(64, A, chain, Ap, bucket_overflow=50)
+    o.fit_dense(X); ix.fit_dense(X)
+    qids = np.concatenate([np.arange(0, 140), np.arange(1000, 1060)]).astype(np.int32)
+    io, so = o.query_topk_dense(X[qids], qids, 2, 5, B.METRIC_DOT)
+    ig, sg = ix.query_topk_dense(X[qids], qids, 2, 5, B.METRIC_DOT)
+    U.assert_topk_close(io, so, ig, sg)
+    assert not any(qids[i] in ig[i] for i in range(128))
+
+
 # ---- error behaviour -----------------------------------------------------------------------------------------
 def test_error_codes():
     from similaritysearchbyrdf_b200 import DPFIndex
