@@ -174,8 +174,7 @@ struct dpf_index {
     dpf::DevBuf<int32_t> pair_q;
     dpf::DevBuf<unsigned long long> pair_key, pair_key_alt;
     dpf::DevBuf<double> scores;
-    dpf::DevBuf<uint32_t> bm_flag, bm_run_start, bm_ucnt, bm_sorted_seg, bm_counts;  // runs / units of the sorted pairs
-    dpf::DevBuf<int32_t> bm_sorted_q;
+    dpf::DevBuf<uint32_t> bm_flag, bm_run_start, bm_ucnt, bm_counts;   // runs / units of the sorted pairs
     dpf::DevBuf<char> bm_units;
     unsigned long long* bm_sorted = nullptr;   // pair keys sorted by bucket (points into pair_key_alt / sk64a)
     int64_t bm_npairs = 0;

@@ -261,7 +261,7 @@ void build_forest(dpf_index* h) {
             h->occupancy[p] += (double)c / L;
         }
 
-    h->ids_sorted.reserve((size_t)std::max<int64_t>(E, 1));
+    h->ids_sorted.reserve((size_t)std::max<int64_t>(E, 1) + 64);   // slack: the re-rank copies 16-byte-aligned id windows
     DevBuf<int32_t> tmp;
     tmp.reserve((size_t)std::max<int64_t>(E, 1));
 

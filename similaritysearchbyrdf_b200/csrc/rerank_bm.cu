@@ -7,11 +7,12 @@
 // Here the batch is regrouped by bucket:
 //   k_probe_pairs    one (bucket, query) pair per distinct bucket a query probes (same walk as K4)
 //   radix sort       pairs by bucket start
-//   k_run_flags .. k_emit_units   runs of pairs that share a bucket, cut into units of <= 16 queries
-//   k_score_stream   a warp per unit: the unit's queries sit in registers as DMMA B fragments, the bucket's rows
-//                    stream HBM -> shared memory through a per-warp ring of TMA bulk copies (one 8d-byte copy per
-//                    row, mbarrier completion, 2 slots of 8 rows in flight per warp while a third is multiplied)
-//                    -> one score per (pair, row)
+//   k_run_flags .. k_emit_units   runs of pairs that share a bucket, cut into units of <= 16 queries; one
+//                    self-contained record per unit (bucket, query list, score segments, first row ids)
+//   k_score_stream   a warp per unit: the unit's queries and then the bucket's rows stream L2/HBM -> shared memory
+//                    through a per-warp ring of TMA bulk copies (one 8d-byte copy per row, mbarrier completion, 2
+//                    slots of 8 rows in flight per warp while a third is consumed); queries become DMMA B fragments
+//                    in registers, rows are multiplied against them -> one score per (pair, row)
 //   k_select_pairs   per query: top-k over its score segments, de-duplicating ids reached through several tables
 //                    (their scores are bit-identical: same row, same query, same k order)
 // Per step this replaces nC_q * 8d bytes per query by ~(bucket rows * 8d) per <= 16 queries plus 16 B per (query,
@@ -83,30 +84,33 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 constexpr int SS_UQ = 16;              // queries per unit = 2 DMMA n-blocks held in registers
 constexpr int SS_WARPS = 8;            // warps per CTA, one CTA per SM
 constexpr int SS_STAGES = 3;           // ring slots per warp
-constexpr int SS_ROWS = 8;             // bucket rows per slot = DMMA M extent
+constexpr int SS_ROWS = 8;             // rows per slot = DMMA M extent (bucket rows) / N extent (query rows)
 constexpr int SS_PITCH = BM_KC + 8;    // doubles; (pitch * 8 B) mod 128 == 64: conflict-free LDS.128 per quarter warp
-constexpr size_t SS_SMEM = (size_t)SS_WARPS * SS_STAGES * SS_ROWS * SS_PITCH * sizeof(double);
+constexpr int SS_WIN = 32;             // row ids per id window
+constexpr int SS_WIN_COPY = SS_WIN + 4;   // ids copied per window: the copy starts at a 16-byte boundary <= the window
 
-struct __align__(16) ScoreUnit {
-    uint32_t bstart;   // bucket start in ids_sorted
-    uint32_t len;      // bucket length (rows)
-    uint32_t pos0;     // position of the unit's first pair in the sorted pair list
-    uint32_t m;        // queries in the unit (1..SS_UQ)
+// Everything the scoring warp needs to know about a unit, in one 16-byte-aligned record it can pull into shared
+// memory with a single bulk copy (no dependent global loads in the scoring loop).
+struct __align__(16) UnitRec {
+    uint32_t bstart;       // bucket start in ids_sorted
+    uint32_t len;          // bucket length (rows)
+    uint32_t pos0;         // position of the unit's first pair in the sorted pair list
+    uint32_t m;            // queries in the unit (1..SS_UQ)
+    int32_t q[SS_UQ];      // query index of pair j
+    uint32_t seg[SS_UQ];   // start of pair j's score segment
+    int32_t ids0[SS_WIN];  // ids of the bucket's first 32 rows (the other windows are copied from ids_sorted)
 };
+static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-// flag[p] = 1 where a run starts; side arrays in sorted order (query index, score segment) so that the scoring
-// kernel needs one load, not a chain, per unit
+constexpr size_t SS_WARP_BYTES = (size_t)SS_STAGES * SS_ROWS * SS_PITCH * sizeof(double) + 2 * sizeof(UnitRec) + 2 * SS_WIN_COPY * 4 + 32;
+constexpr size_t SS_SMEM = SS_WARPS * ((SS_WARP_BYTES + 15) / 16 * 16);
+
+// flag[p] = 1 where a run starts
 __global__ void __launch_bounds__(256)
-k_run_flags(const unsigned long long* __restrict__ sorted, int64_t npairs, const int32_t* __restrict__ pair_q,
-            const uint32_t* __restrict__ pair_seg, uint32_t* __restrict__ flag, int32_t* __restrict__ sorted_q,
-            uint32_t* __restrict__ sorted_seg) {
+k_run_flags(const unsigned long long* __restrict__ sorted, int64_t npairs, uint32_t* __restrict__ flag) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
-    const unsigned long long k = sorted[p];
-    flag[p] = (p == 0 || (uint32_t)(sorted[p - 1] >> 32) != (uint32_t)(k >> 32)) ? 1u : 0u;
-    const uint32_t pi = (uint32_t)k;
-    sorted_q[p] = pair_q[pi];
-    sorted_seg[p] = pair_seg[pi];
+    flag[p] = (p == 0 || (uint32_t)(sorted[p - 1] >> 32) != (uint32_t)(sorted[p] >> 32)) ? 1u : 0u;
 }
 
 // run_idx = exclusive scan of flag: the flagged position p starts run run_idx[p]
@@ -133,18 +137,35 @@ k_run_unit_counts(const uint32_t* __restrict__ run_start, const uint32_t* __rest
     ucnt[r] = r < nruns ? (run_start[r + 1] - run_start[r] + SS_UQ - 1) / SS_UQ : 0u;
 }
 
-// uoff = exclusive scan of ucnt (cap + 1 entries: uoff[cap] = number of units)
+// uoff = exclusive scan of ucnt.  One thread per sorted position; the positions that open a unit (every SS_UQ-th
+// of a run) write its record.
 __global__ void __launch_bounds__(256)
-k_emit_units(const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ pair_len,
-             const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ nruns_p, const uint32_t* __restrict__ uoff,
-             int64_t cap, ScoreUnit* __restrict__ units) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= cap || r >= *nruns_p) return;
+k_emit_units(const unsigned long long* __restrict__ sorted, int64_t npairs, const uint32_t* __restrict__ run_idx,
+             const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ uoff, const int32_t* __restrict__ pair_q,
+             const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg, const int32_t* __restrict__ ids_sorted,
+             UnitRec* __restrict__ units) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const unsigned long long k = sorted[p];
+    const uint32_t bstart = (uint32_t)(k >> 32);
+    const bool start = p == 0 || (uint32_t)(sorted[p - 1] >> 32) != bstart;
+    const uint32_t r = run_idx[p] + (start ? 1u : 0u) - 1u;
     const uint32_t p0 = run_start[r], p1 = run_start[r + 1];
-    const unsigned long long k = sorted[p0];
-    const uint32_t bstart = (uint32_t)(k >> 32), len = pair_len[(uint32_t)k];
-    uint32_t u = uoff[r];
-    for (uint32_t p = p0; p < p1; p += SS_UQ) units[u++] = ScoreUnit{bstart, len, p, min((uint32_t)SS_UQ, p1 - p)};
+    if ((p - p0) % SS_UQ) return;
+    UnitRec rec;
+    rec.bstart = bstart;
+    rec.len = pair_len[(uint32_t)k];
+    rec.pos0 = (uint32_t)p;
+    rec.m = min((uint32_t)SS_UQ, p1 - (uint32_t)p);
+#pragma unroll
+    for (int j = 0; j < SS_UQ; ++j) {
+        const uint32_t pi = (uint32_t)sorted[min((uint32_t)p + j, p1 - 1)];
+        rec.q[j] = pair_q[pi];
+        rec.seg[j] = pair_seg[pi];
+    }
+#pragma unroll
+    for (int j = 0; j < SS_WIN; ++j) rec.ids0[j] = ids_sorted[bstart + min((uint32_t)j, rec.len - 1)];
+    units[uoff[r] + (uint32_t)(p - p0) / SS_UQ] = rec;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -171,11 +192,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      (unsigned)__cvta_generic_to_shared(dst)),
-                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)), "l"(policy)
                  : "memory");
+}
+// L2 residency: the bucket rows stream through once per unit (evict first); the query batch (nq x d, a few MB) is
+// re-read by every unit and must not be washed out of the 126 MB L2 by the ~50 GB of rows (evict last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -183,71 +216,134 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 //
 // Warp w of the grid walks units w, w + W, w + 2W, ... (W = warps in the grid; consecutive units — usually pieces of
 // one run — land on the warps of one CTA at the same time, so a bucket staged twice is an L2 hit the second time).
-// Each warp is its own producer and consumer: slot i of its walk (8 rows of the current unit's bucket) is fetched
-// by 8 lanes issuing one bulk copy each into ring slot i % 3, two slots ahead of the slot being multiplied.
-// Descriptor, first id window and query list of the next unit are prefetched while the current unit streams.
+// Each warp is its own producer and consumer of a 3-slot ring in shared memory.  The slot sequence of a unit is
+//     [its queries 0..7] [its queries 8..15, if any] [bucket rows 0..7] [rows 8..15] ...
+// every slot filled by up to 8 bulk copies (one row each, issued by 8 lanes) that complete on the slot's mbarrier.
+// A query slot is unpacked into DMMA B fragments (registers); a row slot is multiplied against them: A fragments by
+// LDS.128, 2 x 16 k-steps of DMMA.8x8x4 per n-block, one score per (pair, row) stored to the pair's segment.
+// The warp runs the copies two slots ahead of the multiplication.  With ~128 KB of copies in flight per SM, any
+// *synchronous* global load issued from this loop waits behind them for microseconds (measured: 4 us per unit for a
+// demand load of the query rows), so nothing here loads from global memory: the unit record (descriptor, query
+// list, score segments, first 32 row ids) and the later id windows also arrive by bulk copy, one unit / one
+// window ahead.
 // k permutation: DMMA k-step 2w takes columns 8w + 2t, k-step 2w + 1 columns 8w + 2t + 1, so that both fragment
-// elements of a thread are adjacent in memory (one LDS.128 / LDG.128 feeds two DMMAs); A and B use the same
-// permutation, the sum over k is unchanged.
+// elements of a thread are adjacent in memory (one LDS.128 feeds two DMMAs); A and B use the same permutation, the
+// sum over k is unchanged.
 // ---------------------------------------------------------------------------------------------------------
 template <bool ANGULAR>
 __global__ void __launch_bounds__(SS_WARPS * 32, 1)
-k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q, const ScoreUnit* __restrict__ units,
-               const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ sorted_q,
-               const uint32_t* __restrict__ sorted_seg, const int32_t* __restrict__ ids_sorted, double* __restrict__ scores,
+k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q, const UnitRec* __restrict__ units,
+               const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, double* __restrict__ scores,
                unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
     constexpr int NW = BM_KC / 8;
-    extern __shared__ __align__(128) double ssm[];
-    __shared__ uint64_t bars[SS_WARPS][SS_STAGES];
-    __shared__ int4 meta[SS_WARPS][SS_STAGES];       // per slot: {unit sequence number, first row, rows, first slot of unit}
+    constexpr int SLOT_DOUBLES = SS_ROWS * SS_PITCH;
+    extern __shared__ __align__(128) unsigned char ssm_raw[];
+    __shared__ uint64_t bars[SS_WARPS][SS_STAGES + 4];   // ring slots, 2 unit records, 2 id windows
+    __shared__ int4 meta[SS_WARPS][SS_STAGES];           // per slot: {kind: 0/1 query block, 2 rows; first row; rows; m}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    double* ring = ssm + (size_t)warp * SS_STAGES * SS_ROWS * SS_PITCH;
-    for (int i = lane; i < SS_STAGES * SS_ROWS * SS_PITCH; i += 32) ring[i] = 0.0;   // k padding stays zero
+    unsigned char* wbase = ssm_raw + (size_t)warp * ((SS_WARP_BYTES + 15) / 16 * 16);
+    double* ring = reinterpret_cast<double*>(wbase);
+    UnitRec* recs = reinterpret_cast<UnitRec*>(wbase + (size_t)SS_STAGES * SLOT_DOUBLES * sizeof(double));
+    int32_t* wins = reinterpret_cast<int32_t*>(recs + 2);            // 2 x SS_WIN_COPY ids
+    uint64_t* bar_slot = &bars[warp][0];
+    uint64_t* bar_rec = &bars[warp][SS_STAGES];
+    uint64_t* bar_win = &bars[warp][SS_STAGES + 2];
+    for (int i = lane; i < SS_STAGES * SLOT_DOUBLES; i += 32) ring[i] = 0.0;   // k padding stays zero
     if (lane == 0)
-        for (int s = 0; s < SS_STAGES; ++s) mbar_init(&bars[warp][s], 1);
+        for (int s = 0; s < SS_STAGES + 4; ++s) mbar_init(&bars[warp][s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
 
     const int nw8 = (d + 7) >> 3;
     const unsigned row_bytes = (unsigned)d * 8u;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const int64_t nunits = *nunits_p;
     const int64_t W = (int64_t)gridDim.x * SS_WARPS;
     const int64_t gw = (int64_t)blockIdx.x * SS_WARPS + warp;
-    // units of this warp: gw + k * W, k = 0 .. nmine - 1
-    const int64_t nmine = nunits > gw ? (nunits - gw + W - 1) / W : 0;
+    const int64_t nmine = nunits > gw ? (nunits - gw + W - 1) / W : 0;   // units gw + k * W, k = 0 .. nmine - 1
     if (nmine == 0) return;
 
-    // ---- producer state (warp-uniform unless noted) -----------------------------------------------------------
-    int64_t p_seq = -1;                 // sequence number (k) of the unit being issued
+    // ---- producer state (warp-uniform) ------------------------------------------------------------------------
+    int64_t pk = 0;                    // unit being issued
+    int p_phase = -1;                  // -1 unit not opened yet, 0 / 1 next query block, 2 rows
     uint32_t p_bstart = 0, p_len = 0, p_m = 0;
-    int p_row = 0;                      // next row of the unit to issue
-    int p_win = 0, p_win_next = 0;      // lane l: id of row p_win_base + l / + 32 + l
-    int p_win_base = 0;
-    int p_q = 0;                        // lane j < m: query index of pair j of the unit
-    uint32_t p_seg = 0;                 // lane j < m: score segment of pair j
-    // prefetched next unit (k = p_seq + 1)
-    uint4 n_desc = make_uint4(0, 0, 0, 0);
-    int n_win = 0, n_q = 0;
-    uint32_t n_seg = 0;
-    int n_state = 0;                    // 0 none, 1 descriptor requested, 2 window / query list requested
-    auto prefetch_desc = [&](int64_t k) {
-        if (k < nmine) { n_desc = __ldg(reinterpret_cast<const uint4*>(units) + (gw + k * W)); n_state = 1; }
-        else n_state = 0;
-    };
-    auto prefetch_lists = [&]() {       // needs n_desc
-        const uint32_t len = n_desc.y, pos0 = n_desc.z, m = n_desc.w;
-        n_win = __ldg(ids_sorted + n_desc.x + min((uint32_t)lane, len - 1));
-        n_q = lane < (int)m ? __ldg(sorted_q + pos0 + lane) : 0;
-        n_seg = lane < (int)m ? __ldg(sorted_seg + pos0 + lane) : 0u;
-        n_state = 2;
-    };
-    prefetch_desc(0);
+    int p_row = 0;
+    unsigned win_uses0 = 0, win_uses1 = 0;   // completed waits on each id-window barrier (-> parity)
     int issued = 0, consumed = 0;
-    int64_t c_seq = -1;                 // sequence number of the unit being multiplied
-    bool p_done = false;
     unsigned long long rows_staged = 0;
+    auto fetch_rec = [&](int64_t k) {
+        if (k < nmine && lane == 0) {
+            mbar_expect_tx(&bar_rec[k & 1], (unsigned)sizeof(UnitRec));
+            bulk_g2s(&recs[k & 1], units + (gw + k * W), (unsigned)sizeof(UnitRec), &bar_rec[k & 1], pol_stream);
+        }
+    };
+    // ids of rows [32j, 32j + 32) of the current bucket -> window buffer j & 1 (the copy starts at the 16-byte
+    // boundary below and is 4 ids longer; ids_sorted is allocated with slack for the over-read)
+    auto fetch_win = [&](int j) {
+        if (lane == 0) {
+            const uint32_t e0 = p_bstart + (uint32_t)(SS_WIN * j);
+            mbar_expect_tx(&bar_win[j & 1], SS_WIN_COPY * 4);
+            bulk_g2s(wins + (j & 1) * SS_WIN_COPY, ids_sorted + (e0 & ~3u), SS_WIN_COPY * 4, &bar_win[j & 1], pol_stream);
+        }
+    };
+    fetch_rec(0);
+
+    // issue one slot; false when the ring is full or the walk is over
+    auto issue = [&]() -> bool {
+        if (pk >= nmine || issued - consumed >= SS_STAGES) return false;
+        if (p_phase < 0) {             // open unit pk: its record was requested one unit ago
+            mbar_wait(&bar_rec[pk & 1], (unsigned)((pk >> 1) & 1));
+            fetch_rec(pk + 1);
+            const UnitRec* r = &recs[pk & 1];
+            p_bstart = r->bstart; p_len = r->len; p_m = r->m;
+            p_phase = 0; p_row = 0;
+        }
+        const UnitRec* r = &recs[pk & 1];
+        const int s = issued % SS_STAGES;
+        double* slot = ring + (size_t)s * SLOT_DOUBLES;
+        if (p_phase < 2) {             // 8 query rows; each row's score segment rides in the row's padding
+            const int nrows = min(SS_ROWS, (int)p_m - SS_ROWS * p_phase);
+            if (lane == 0) {
+                meta[warp][s] = make_int4(p_phase, 0, nrows, (int)p_m);
+                mbar_expect_tx(&bar_slot[s], (unsigned)nrows * row_bytes);
+            }
+            __syncwarp();
+            if (lane < nrows) {
+                const int j = SS_ROWS * p_phase + lane;
+                reinterpret_cast<uint32_t*>(slot + (size_t)lane * SS_PITCH + BM_KC)[0] = r->seg[j];
+                bulk_g2s(slot + (size_t)lane * SS_PITCH, Q + (int64_t)r->q[j] * d, row_bytes, &bar_slot[s], pol_keep);
+            }
+            p_phase = (p_phase == 0 && p_m > SS_ROWS) ? 1 : 2;
+        } else {
+            const int j = p_row / SS_WIN;                  // id window of this slot
+            if (p_row % SS_WIN == 0) {
+                if (j >= 1) {
+                    if (j & 1) { mbar_wait(&bar_win[1], win_uses1 & 1); win_uses1++; }
+                    else { mbar_wait(&bar_win[0], win_uses0 & 1); win_uses0++; }
+                }
+                if ((uint32_t)(SS_WIN * (j + 1)) < p_len) fetch_win(j + 1);   // one window (4 slots) ahead
+            }
+            const int nrows = min(SS_ROWS, (int)p_len - p_row);
+            if (lane == 0) {
+                meta[warp][s] = make_int4(2, p_row, nrows, (int)p_m);
+                mbar_expect_tx(&bar_slot[s], (unsigned)nrows * row_bytes);
+            }
+            __syncwarp();
+            if (lane < nrows) {
+                const int w = p_row % SS_WIN + lane;
+                const int id = j == 0 ? r->ids0[w]
+                                      : wins[(j & 1) * SS_WIN_COPY + (int)((p_bstart + (uint32_t)(SS_WIN * j)) & 3u) + w];
+                bulk_g2s(slot + (size_t)lane * SS_PITCH, X + (int64_t)id * d, row_bytes, &bar_slot[s], pol_stream);
+            }
+            p_row += nrows;
+            rows_staged += nrows;
+            if (p_row >= (int)p_len) { pk++; p_phase = -1; }
+        }
+        issued++;
+        return true;
+    };
 
     // ---- consumer state ---------------------------------------------------------------------------------------
     double2 B[2][NW];                   // queries g (n-block 0) and 8 + g (n-block 1), columns 8w + 2t, + 1
@@ -256,85 +352,50 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
     double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
     int c_nb = 0;                       // n-blocks in use
 
-    // issue one slot; returns false when nothing can be issued now
-    auto issue = [&]() -> bool {
-        if (p_done || issued - consumed >= SS_STAGES) return false;
-        if (p_seq < 0 || p_row >= (int)p_len) {
-            // next unit; the consumer takes a unit's query list from the producer registers when it reaches the
-            // unit's first slot, so the producer stays at most one unit ahead
-            if (p_seq > c_seq) return false;
-            if (n_state == 0) { p_done = true; return false; }
-            if (n_state == 1) prefetch_lists();
-            p_seq++;
-            p_bstart = n_desc.x; p_len = n_desc.y; p_m = n_desc.w;
-            p_win = n_win; p_q = n_q; p_seg = n_seg;
-            p_row = 0; p_win_base = 0;
-            p_win_next = __ldg(ids_sorted + p_bstart + min((uint32_t)(32 + lane), p_len - 1));
-            prefetch_desc(p_seq + 1);
-        } else if (n_state == 1) {
-            prefetch_lists();
-        }
-        if (p_row >= p_win_base + 32) {
-            p_win = p_win_next;
-            p_win_base += 32;
-            p_win_next = __ldg(ids_sorted + p_bstart + min((uint32_t)(p_win_base + 32 + lane), p_len - 1));
-        }
-        const int s = issued % SS_STAGES;
-        const int nrows = min(SS_ROWS, (int)p_len - p_row);
-        if (lane == 0) {
-            meta[warp][s] = make_int4((int)p_seq, p_row, nrows, p_row == 0 ? 1 : 0);
-            mbar_expect_tx(&bars[warp][s], (unsigned)nrows * row_bytes);
-        }
-        __syncwarp();
-        const int id = __shfl_sync(0xffffffffu, p_win, (p_row - p_win_base) + (lane & 7));
-        if (lane < nrows) bulk_g2s(ring + (size_t)(s * SS_ROWS + lane) * SS_PITCH, X + (int64_t)id * d, row_bytes, &bars[warp][s]);
-        p_row += nrows;
-        rows_staged += nrows;
-        issued++;
-        return true;
-    };
-
     for (;;) {
         while (issue()) {}
+        __syncwarp();                       // slot meta and score segments written by single lanes are visible
         if (issued == consumed) break;
         const int s = consumed % SS_STAGES;
         const int4 mt = meta[warp][s];
-        if (mt.w) {
-            // first slot of a unit: its query list is in the producer registers (p_seq == mt.x, see issue())
-            c_seq = mt.x;
-            const int m = (int)p_m;
-            c_nb = (m + 7) >> 3;
+        const double* slot = ring + (size_t)s * SLOT_DOUBLES;
+        mbar_wait(&bar_slot[s], (unsigned)((consumed / SS_STAGES) & 1));
+        if (mt.x < 2) {
+            // query block mt.x of a unit of mt.w queries -> B fragments, score segments, norms
+            const double* br = slot + (size_t)g * SS_PITCH + 2 * t;
+            if (mt.x == 0) {
+                c_nb = (mt.w + 7) >> 3;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) B[0][w] = w < nw8 ? *reinterpret_cast<const double2*>(br + 8 * w) : make_double2(0.0, 0.0);
+            } else {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) B[1][w] = w < nw8 ? *reinterpret_cast<const double2*>(br + 8 * w) : make_double2(0.0, 0.0);
+            }
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) {
-                const int qi = __shfl_sync(0xffffffffu, p_q, min(8 * nb + g, m - 1));
-                const double* qsrc = Q + (int64_t)qi * d + 2 * t;
+                if (nb == mt.x) {
 #pragma unroll
-                for (int w = 0; w < NW; ++w)
-                    B[nb][w] = (nb < c_nb && w < nw8 && 8 * w + 2 * t < d) ? __ldg(reinterpret_cast<const double2*>(qsrc + 8 * w))
-                                                                          : make_double2(0.0, 0.0);
+                    for (int e = 0; e < 2; ++e) {
+                        c_seg[nb][e] = reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * t + e) * SS_PITCH + BM_KC)[0];
+                        c_ok[nb][e] = 8 * nb + 2 * t + e < mt.w;
+                    }
+                    if (ANGULAR) {
+                        double sq = 0.0;    // ||query 8nb + g||^2: this thread's columns, then the 4 threads of the group
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int qj = 8 * nb + 2 * t + e;
-                    c_seg[nb][e] = __shfl_sync(0xffffffffu, p_seg, min(qj, m - 1));
-                    c_ok[nb][e] = qj < m;
+                        for (int w = 0; w < NW; ++w) { sq = fma(B[nb][w].x, B[nb][w].x, sq); sq = fma(B[nb][w].y, B[nb][w].y, sq); }
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                        const double nrm = sqrt(sq);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) c_qn[nb][e] = __shfl_sync(0xffffffffu, nrm, (2 * t + e) * 4);
+                    }
                 }
             }
-            if (ANGULAR) {
-#pragma unroll
-                for (int nb = 0; nb < 2; ++nb) {
-                    double sq = 0.0;        // ||query 8nb + g||^2: this thread's columns, then the 4 threads of the group
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) { sq = fma(B[nb][w].x, B[nb][w].x, sq); sq = fma(B[nb][w].y, B[nb][w].y, sq); }
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                    const double nrm = sqrt(sq);
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) c_qn[nb][e] = __shfl_sync(0xffffffffu, nrm, (2 * t + e) * 4);
-                }
-            }
+            __syncwarp();
+            consumed++;
+            continue;
         }
-        mbar_wait(&bars[warp][s], (unsigned)((consumed / SS_STAGES) & 1));
-        const double* ar = ring + (size_t)(s * SS_ROWS + g) * SS_PITCH + 2 * t;
+        const double* ar = slot + (size_t)g * SS_PITCH + 2 * t;
         double acc[2][2][2];                // [n-block][even / odd k-step chain][column]
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
@@ -377,7 +438,7 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
             for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                    if (c_ok[nb][e]) {
+                    if (nb < c_nb && c_ok[nb][e]) {
                         const double v = acc[nb][0][e] + acc[nb][1][e];
                         scores[(size_t)c_seg[nb][e] + row] = ANGULAR ? v / (c_qn[nb][e] * xnr) : v;
                     }
@@ -698,26 +759,28 @@ __global__ void k_topk_select_empty(int64_t q0, int64_t nqc, int K, int32_t* __r
 
 
 // runs of the sorted pair list -> h->units (device), number of units in h->bm_counts[1]
+// runs of the sorted pair list -> unit records in h->bm_units (device); the number of units is also left in
+// h->bm_counts[1]
 static void build_units(dpf_index* h, int64_t npairs) {
     cudaStream_t st = h->stream;
     const unsigned gp = (unsigned)((npairs + 255) / 256);
     h->bm_flag.reserve(npairs + 1);
     h->bm_run_start.reserve(npairs + 2);
     h->bm_ucnt.reserve(npairs + 2);
-    h->bm_sorted_q.reserve(npairs);
-    h->bm_sorted_seg.reserve(npairs);
-    h->bm_units.reserve((size_t)npairs * sizeof(ScoreUnit));
     h->bm_counts.reserve(4);
-    k_run_flags<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->pair_q.p, h->pair_seg.p, h->bm_flag.p, h->bm_sorted_q.p,
-                                    h->bm_sorted_seg.p); DPF_LAUNCHED();
+    k_run_flags<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p); DPF_LAUNCHED();
     exclusive_scan_u32(h, h->bm_flag.p, npairs);
     k_run_starts<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_counts.p); DPF_LAUNCHED();
     k_run_unit_counts<<<(unsigned)((npairs + 1 + 255) / 256), 256, 0, st>>>(h->bm_run_start.p, h->bm_counts.p, npairs + 1,
                                                                             h->bm_ucnt.p); DPF_LAUNCHED();
     exclusive_scan_u32(h, h->bm_ucnt.p, npairs + 1);      // bm_ucnt[r] = first unit of run r; [npairs] = number of units
-    k_emit_units<<<gp, 256, 0, st>>>(h->bm_sorted, h->pair_len.p, h->bm_run_start.p, h->bm_counts.p, h->bm_ucnt.p, npairs,
-                                     reinterpret_cast<ScoreUnit*>(h->bm_units.p)); DPF_LAUNCHED();
     DPF_CUDA(cudaMemcpyAsync(h->bm_counts.p + 1, h->bm_ucnt.p + npairs, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    uint32_t nunits = 0;
+    DPF_CUDA(cudaMemcpyAsync(&nunits, h->bm_ucnt.p + npairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaStreamSynchronize(st));
+    h->bm_units.reserve((size_t)std::max<uint32_t>(nunits, 1) * sizeof(UnitRec));
+    k_emit_units<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_ucnt.p, h->pair_q.p, h->pair_len.p,
+                                     h->pair_seg.p, h->ids_sorted.p, reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }
 
@@ -789,13 +852,13 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                 DPF_CUDA(cudaFuncSetAttribute(k_score_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
                 attr = true;
             }
-            const ScoreUnit* units = reinterpret_cast<const ScoreUnit*>(h->bm_units.p);
+            const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
             if (ang)
-                k_score_stream<true><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->bm_sorted_q.p,
-                                                                               h->bm_sorted_seg.p, h->ids_sorted.p, h->scores.p, bm_stat);
+                k_score_stream<true><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->ids_sorted.p,
+                                                                               h->scores.p, bm_stat);
             else
-                k_score_stream<false><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->bm_sorted_q.p,
-                                                                                h->bm_sorted_seg.p, h->ids_sorted.p, h->scores.p, bm_stat);
+                k_score_stream<false><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->ids_sorted.p,
+                                                                                h->scores.p, bm_stat);
         } else {
             const char* nbv = getenv("DPF_BM_NB");
             const int nb = nbv ? atoi(nbv) : 2;
