@@ -43,6 +43,9 @@ enum { DPF_KEY_ORIGINAL = 0, DPF_KEY_SAMPLING = 1, DPF_KEY_CONTINUE_BITS = 2, DP
                                                                        /* mclab.lsh.typeOfIndex (LSH.scala:152-161) */
 enum { DPF_METRIC_DOT = 0, DPF_METRIC_ANGULAR = 1, DPF_METRIC_L2 = 2 };
 enum { DPF_PROBE_NONE = 0, DPF_PROBE_DENSE = 1 };
+/* element type of the compact vector store the re-rank kernels read (see dpf_set_store_mode) */
+enum { DPF_STORE_KIND_F64 = 0, DPF_STORE_KIND_F32 = 1, DPF_STORE_KIND_U8 = 2 };
+enum { DPF_STORE_AUTO = 0, DPF_STORE_F64_ONLY = 1 };
     /* DPF_PROBE_DENSE: getSimilarWithStepWiseFaster(key, DenseVector, steps) multi-probe (RandomDrawTreeMap.java:742-797)
        DPF_PROBE_NONE : sparse overload / id-based getSimilarWithStepWise (RandomDrawTreeMap.java:686-732, 630-675) */
 
@@ -98,6 +101,13 @@ int dpf_fit_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, con
 /* X_dev stays owned by the caller and must outlive the handle (no copy is made: 100M x 96 FP64 is 76.8 GB) */
 int dpf_fit_dense_dev(dpf_handle h, const double* X_dev, int64_t n);
 int64_t dpf_size(dpf_handle h);
+/* The reference keeps every vector as double[] (vectorIdToVector, DensevectorRDFInit.scala:35-36).  With
+ * DPF_STORE_AUTO (default) a dense fit also checks whether EVERY stored value survives a round trip through a
+ * narrower type (uint8: SIFT-like descriptors; float: fvecs data) and, if so, keeps a copy in that type for the
+ * re-rank kernels, which widen it back to FP64 in registers — the products and sums are the same FP64 operations on
+ * the same values, only 1/8 or 1/2 of the bytes cross HBM.  Lossy narrowing is never done.  DPF_STORE_F64_ONLY turns
+ * the check off (call before fit).  DPF_STAT_STORE_KIND reports the kind in use. */
+int dpf_set_store_mode(dpf_handle h, int32_t mode);
 
 /* ---- query: candidate sets = DensevectorRDFInit.NewMultiThreadQueryBatch (DensevectorRDFInit.scala:335-360),
  * SparsevectorRDFInit.NewMultiThreadQueryBatch (SparsevectorRDFInit.scala:324-348) --------------------------
@@ -152,7 +162,9 @@ enum {
     DPF_STAT_KERNEL_LAUNCHES = 8,  /* kernels launched by this library in this process (cumulative)          */
     DPF_STAT_BM_PAIRS = 9,         /* bucket-major re-rank, last batch: (bucket, query) pairs                */
     DPF_STAT_BM_RUNS = 10,         /*   runs of pairs sharing a bucket inside a CTA group                    */
-    DPF_STAT_BM_ROWS_STAGED = 11,  /*   bucket rows staged in shared memory (each 8d bytes of HBM)           */
+    DPF_STAT_BM_ROWS_STAGED = 11,  /*   bucket rows staged in shared memory (each one row of the store)      */
+    DPF_STAT_STORE_KIND = 12,      /* DPF_STORE_KIND_* of the compact store after the last dense fit         */
+    DPF_STAT_STORE_ROW_BYTES = 13, /* bytes per row the re-rank kernels fetch                                */
     DPF_STAT_COUNT = 16
 };
 int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occupancy_out /* 2^pb or NULL */);
@@ -160,7 +172,8 @@ int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occ
 /* per-stage device times of the last fit / query call, measured with CUDA events on the handle's stream */
 enum {
     DPF_T_HASH = 0, DPF_T_FIXUP = 1, DPF_T_PACK = 2, DPF_T_SORT = 3, DPF_T_SPLIT = 4,
-    DPF_T_PROBE_COUNT = 5, DPF_T_EXPAND = 6, DPF_T_RERANK = 7, DPF_T_CAND_SORT = 8, DPF_T_SELECT = 9, DPF_T_COUNT = 16
+    DPF_T_PROBE_COUNT = 5, DPF_T_EXPAND = 6, DPF_T_RERANK = 7, DPF_T_CAND_SORT = 8, DPF_T_SELECT = 9, DPF_T_NARROW = 10,
+    DPF_T_COUNT = 16
 };
 int dpf_set_profiling(dpf_handle h, int32_t enable);
 int dpf_stage_times_ms(dpf_handle h, float* ms_out /* DPF_T_COUNT */);

@@ -12,11 +12,13 @@ FAMILY_ANGLE, FAMILY_PSTABLE = 0, 1
 KEY_ORIGINAL, KEY_SAMPLING, KEY_CONTINUE_BITS, KEY_ANGLE_NEW = 0, 1, 2, 3
 METRIC_DOT, METRIC_ANGULAR, METRIC_L2 = 0, 1, 2
 PROBE_NONE, PROBE_DENSE = 0, 1
+STORE_KIND_F64, STORE_KIND_F32, STORE_KIND_U8 = 0, 1, 2
+STORE_AUTO, STORE_F64_ONLY = 0, 1
 STAT_COUNT, T_COUNT = 16, 16
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
               "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",
-              "bm_rows_staged"]
-STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select"]
+              "bm_rows_staged", "store_kind", "store_row_bytes"]
+STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select", "narrow"]
 
 # every symbol include/dpf.h declares
 EXPORTS = [
@@ -24,7 +26,7 @@ EXPORTS = [
     "dpf_set_partitioners", "dpf_hash_dense", "dpf_hash_csr", "dpf_fit_dense", "dpf_fit_csr", "dpf_fit_dense_dev",
     "dpf_size", "dpf_query_candidates_dense", "dpf_query_candidates_csr", "dpf_query_candidates_by_id",
     "dpf_query_topk_dense", "dpf_query_topk_dense_dev", "dpf_rerank_dense", "dpf_merge_topk_dev", "dpf_dump_buckets",
-    "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms",
+    "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms", "dpf_set_store_mode",
 ]
 
 
@@ -82,6 +84,7 @@ def load():
     L.dpf_stats.argtypes = [vp, vp, vp]
     L.dpf_set_profiling.argtypes = [vp, i32]
     L.dpf_stage_times_ms.argtypes = [vp, vp]
+    L.dpf_set_store_mode.argtypes = [vp, i32]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -419,9 +419,19 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     h->n += n;
     build_forest(h);
     tr.mark("forest");
+    build_compact_store(h);
+    tr.mark("compact store");
     h->stats[DPF_STAT_SIZE] = h->n;
     DPF_CUDA(cudaStreamSynchronize(h->stream));
     end_profile(h);
+}
+
+int dpf_set_store_mode(dpf_handle h, int32_t mode) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(mode == DPF_STORE_AUTO || mode == DPF_STORE_F64_ONLY, DPF_ERR_INVALID, "bad store mode");
+        DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "dpf_set_store_mode must be called before fit");
+        h->store_mode = mode;
+    });
 }
 
 int dpf_fit_dense(dpf_handle h, const double* X, int64_t n) {

@@ -135,6 +135,14 @@ struct dpf_index {
     dpf::DevBuf<double> X;        // owned dense store (n x d) unless borrowed
     const double* Xdev = nullptr; // points at X.p or at the caller's buffer (dpf_fit_dense_dev)
     bool X_borrowed = false;
+    // compact store: lossless narrow copy of the dense store for the re-rank kernels (store.cu)
+    int store_mode = DPF_STORE_AUTO;
+    int Xc_kind = DPF_STORE_KIND_F64;   // element type of Xc; F64 = no copy, the kernels read Xdev
+    int64_t Xc_row_bytes = 0;           // row pitch of Xc in bytes (multiple of 16, zero padded)
+    dpf::DevBuf<unsigned char> Xc;
+    dpf::DevBuf<unsigned char> Q8;      // uint8 copy of the current query batch, when every query value is a byte
+    dpf::DevBuf<double> qnorm8;         //   and the queries' norms
+    bool Q8_valid = false;
     dpf::DevBuf<int64_t> sp_ptr;  // CSR store
     dpf::DevBuf<int32_t> sp_idx;
     dpf::DevBuf<double> sp_val;
@@ -226,6 +234,10 @@ void hash_dense_device_exact(dpf_index* h, const double* Xd, int64_t n, int32_t*
 void hash_csr_device(dpf_index* h, const int64_t* ptr, const int32_t* idx, const double* val, int64_t n,
                      int32_t* keys_out, uint8_t* pids_out, int64_t ld);
 void prepare_family(dpf_index* h);
+
+// ---- store.cu -----------------------------------------------------------------------------------------------
+// (re)builds the compact store from Xdev[0 .. n); leaves Xc_kind = F64 when no narrower type is lossless
+void build_compact_store(dpf_index* h);
 
 // ---- sort.cu ------------------------------------------------------------------------------------------------
 // stable LSD radix sort of the bit range [lo_bit, hi_bit) — result ends in (*keys_io, *vals_io) which may be

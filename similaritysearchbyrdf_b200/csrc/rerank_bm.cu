@@ -20,20 +20,20 @@
 // order.  Why TMA rows: tools/gather_patterns.cu — a DMMA A-fragment gather straight from HBM touches 8 rows x 64 B
 // per instruction and collapses to 2.9 TB/s at high occupancy; 1 KB bulk row copies hold 7.3 TB/s with 8 warps/SM.
 #include <cstdlib>
+#include <type_traits>
 
-#include "query_common.cuh"
+#include "rerank_units.cuh"
 
 namespace dpf {
 
 constexpr int BM_QT = 32;              // pairs per group of the register-gather kernel (k_score_warps)
-constexpr int BM_KC = 128;             // largest supported d
 
 bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
     const char* e = getenv("DPF_RERANK");
     if (e && e[0] == 'r') return false;                        // DPF_RERANK=rowmajor forces the row-major kernel
     return h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 &&
            (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
-           (metric == DPF_METRIC_DOT || metric == DPF_METRIC_ANGULAR) && topk <= RR_MAXK;
+           (metric == DPF_METRIC_DOT || metric == DPF_METRIC_ANGULAR) && topk <= RR_MAXK;   // d even: the queries are FP64 rows
 }
 
 // fill pass: pair i of (query q, table t) in (q, t, lane) order
@@ -70,40 +70,6 @@ k_probe_pairs(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
         at += __popc(m);
     }
 }
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// units: runs of sorted pairs that share a bucket, cut into pieces of <= SS_UQ queries
-// ---------------------------------------------------------------------------------------------------------
-constexpr int SS_UQ = 16;              // queries per unit = 2 DMMA n-blocks held in registers
-constexpr int SS_WARPS = 8;            // warps per CTA, one CTA per SM
-constexpr int SS_STAGES = 3;           // ring slots per warp
-constexpr int SS_ROWS = 8;             // rows per slot = DMMA M extent (bucket rows) / N extent (query rows)
-constexpr int SS_PITCH = BM_KC + 8;    // doubles; (pitch * 8 B) mod 128 == 64: conflict-free LDS.128 per quarter warp
-constexpr int SS_WIN = 32;             // row ids per id window
-constexpr int SS_WIN_COPY = SS_WIN + 4;   // ids copied per window: the copy starts at a 16-byte boundary <= the window
-
-// Everything the scoring warp needs to know about a unit, in one 16-byte-aligned record it can pull into shared
-// memory with a single bulk copy (no dependent global loads in the scoring loop).
-struct __align__(16) UnitRec {
-    uint32_t bstart;       // bucket start in ids_sorted
-    uint32_t len;          // bucket length (rows)
-    uint32_t pos0;         // position of the unit's first pair in the sorted pair list
-    uint32_t m;            // queries in the unit (1..SS_UQ)
-    int32_t q[SS_UQ];      // query index of pair j
-    uint32_t seg[SS_UQ];   // start of pair j's score segment
-    int32_t ids0[SS_WIN];  // ids of the bucket's first 32 rows (the other windows are copied from ids_sorted)
-};
-static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
-
-constexpr size_t SS_WARP_BYTES = (size_t)SS_STAGES * SS_ROWS * SS_PITCH * sizeof(double) + 2 * sizeof(UnitRec) + 2 * SS_WIN_COPY * 4 + 32;
-constexpr size_t SS_SMEM = SS_WARPS * ((SS_WARP_BYTES + 15) / 16 * 16);
 
 // flag[p] = 1 where a run starts
 __global__ void __launch_bounds__(256)
@@ -230,12 +196,52 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 // elements of a thread are adjacent in memory (one LDS.128 feeds two DMMAs); A and B use the same permutation, the
 // sum over k is unchanged.
 // ---------------------------------------------------------------------------------------------------------
-template <bool ANGULAR>
+// Store kinds: the vector store is kept in the narrowest type that represents every value exactly (store.cu):
+// FP64 (E = 2 values per 16-byte chunk), FP32 (E = 4) or uint8 (E = 16).  Rows are widened to FP64 in registers
+// (exactly) and multiplied on the FP64 tensor pipe, so a score is the same FP64 sum of the same products whatever
+// the store kind; only the bytes a row costs in HBM change (8d, 4d or d).
+// k permutation, all kinds: thread t of a DMMA row group takes the 16-byte chunks 4j + t of the row (j = 0, 1, ...);
+// k-step j * E + e multiplies element e of those chunks, i.e. column (64j + 16t) / sizeof(T) + e.  A (rows) and B
+// (queries) use the same permutation, so the sum over k is unchanged.  For FP64 this is the pairing "k-step 2w
+// takes columns 8w + 2t, k-step 2w + 1 columns 8w + 2t + 1" (one LDS.128 feeds two DMMAs); for uint8 one LDS.128
+// feeds 16.  Row pitch in a slot = 64 (mod 128) bytes: the LDS.128 of a quarter warp (2 rows x 4 chunks) is
+// conflict-free.
+template <int KIND> struct StoreKind;
+template <> struct StoreKind<DPF_STORE_KIND_F64> { static constexpr int SZ = 8, E = 2, RP = SS_PITCH * 8; };
+template <> struct StoreKind<DPF_STORE_KIND_F32> { static constexpr int SZ = 4, E = 4, RP = BM_KC * 4 + 64; };
+template <> struct StoreKind<DPF_STORE_KIND_U8> { static constexpr int SZ = 1, E = 16, RP = BM_KC + 64; };
+
+template <int KIND>
+__device__ __forceinline__ void widen_chunk(const uint4& c, double (&a)[StoreKind<KIND>::E]) {
+    if constexpr (KIND == DPF_STORE_KIND_F64) {
+        a[0] = __hiloint2double((int)c.y, (int)c.x);
+        a[1] = __hiloint2double((int)c.w, (int)c.z);
+    } else if constexpr (KIND == DPF_STORE_KIND_F32) {
+        a[0] = (double)__uint_as_float(c.x);
+        a[1] = (double)__uint_as_float(c.y);
+        a[2] = (double)__uint_as_float(c.z);
+        a[3] = (double)__uint_as_float(c.w);
+    } else {
+        // byte v -> the double 2^52 + v (mantissa = v), minus 2^52: exact, one PRMT + one DADD per value
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                a[4 * i + b] = __hiloint2double(0x43300000, (int)__byte_perm(w[i], 0u, 0x4440u | (unsigned)b)) - 4503599627370496.0;
+    }
+}
+
+template <bool ANGULAR, int KIND>
 __global__ void __launch_bounds__(SS_WARPS * 32, 1)
-k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q, const UnitRec* __restrict__ units,
+k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes per stored row, multiple of 16 */, int d,
+               const double* __restrict__ Q, const UnitRec* __restrict__ units,
                const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, double* __restrict__ scores,
                unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
-    constexpr int NW = BM_KC / 8;
+    using SK = StoreKind<KIND>;
+    constexpr int E = SK::E;
+    constexpr int NJ = BM_KC * SK::SZ / 64;         // 64-byte groups (4 chunks) per row
+    constexpr int NS = NJ * E;                      // DMMA k-steps per row = BM_KC / 4
     constexpr int SLOT_DOUBLES = SS_ROWS * SS_PITCH;
     extern __shared__ __align__(128) unsigned char ssm_raw[];
     __shared__ uint64_t bars[SS_WARPS][SS_STAGES + 4];   // ring slots, 2 unit records, 2 id windows
@@ -249,15 +255,16 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
     uint64_t* bar_slot = &bars[warp][0];
     uint64_t* bar_rec = &bars[warp][SS_STAGES];
     uint64_t* bar_win = &bars[warp][SS_STAGES + 2];
-    for (int i = lane; i < SS_STAGES * SLOT_DOUBLES; i += 32) ring[i] = 0.0;   // k padding stays zero
+    for (int i = lane; i < SS_STAGES * SLOT_DOUBLES; i += 32) ring[i] = 0.0;
     if (lane == 0)
         for (int s = 0; s < SS_STAGES + 4; ++s) mbar_init(&bars[warp][s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
 
-    const int nw8 = (d + 7) >> 3;
-    const unsigned row_bytes = (unsigned)d * 8u;
+    const int nj = (d * SK::SZ + 63) >> 6;              // 64-byte groups in use
+    const bool ragged = (d * SK::SZ) & 63;              // the last group holds columns >= d: masked in registers
+    const unsigned q_bytes = (unsigned)d * 8u;
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const int64_t nunits = *nunits_p;
     const int64_t W = (int64_t)gridDim.x * SS_WARPS;
@@ -303,17 +310,17 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
         const UnitRec* r = &recs[pk & 1];
         const int s = issued % SS_STAGES;
         double* slot = ring + (size_t)s * SLOT_DOUBLES;
-        if (p_phase < 2) {             // 8 query rows; each row's score segment rides in the row's padding
+        if (p_phase < 2) {             // 8 query rows (always FP64); each row's score segment rides in the row's padding
             const int nrows = min(SS_ROWS, (int)p_m - SS_ROWS * p_phase);
             if (lane == 0) {
                 meta[warp][s] = make_int4(p_phase, 0, nrows, (int)p_m);
-                mbar_expect_tx(&bar_slot[s], (unsigned)nrows * row_bytes);
+                mbar_expect_tx(&bar_slot[s], (unsigned)nrows * q_bytes);
             }
             __syncwarp();
             if (lane < nrows) {
                 const int j = SS_ROWS * p_phase + lane;
                 reinterpret_cast<uint32_t*>(slot + (size_t)lane * SS_PITCH + BM_KC)[0] = r->seg[j];
-                bulk_g2s(slot + (size_t)lane * SS_PITCH, Q + (int64_t)r->q[j] * d, row_bytes, &bar_slot[s], pol_keep);
+                bulk_g2s(slot + (size_t)lane * SS_PITCH, Q + (int64_t)r->q[j] * d, q_bytes, &bar_slot[s], pol_keep);
             }
             p_phase = (p_phase == 0 && p_m > SS_ROWS) ? 1 : 2;
         } else {
@@ -335,7 +342,8 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
                 const int w = p_row % SS_WIN + lane;
                 const int id = j == 0 ? r->ids0[w]
                                       : wins[(j & 1) * SS_WIN_COPY + (int)((p_bstart + (uint32_t)(SS_WIN * j)) & 3u) + w];
-                bulk_g2s(slot + (size_t)lane * SS_PITCH, X + (int64_t)id * d, row_bytes, &bar_slot[s], pol_stream);
+                bulk_g2s(reinterpret_cast<unsigned char*>(slot) + (size_t)lane * SK::RP, X + (int64_t)id * row_bytes, row_bytes,
+                         &bar_slot[s], pol_stream);
             }
             p_row += nrows;
             rows_staged += nrows;
@@ -346,11 +354,12 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
     };
 
     // ---- consumer state ---------------------------------------------------------------------------------------
-    double2 B[2][NW];                   // queries g (n-block 0) and 8 + g (n-block 1), columns 8w + 2t, + 1
+    double B[2][NS];                    // queries g (n-block 0) and 8 + g (n-block 1), k-step order
     uint32_t c_seg[2][2] = {{0, 0}, {0, 0}};
     bool c_ok[2][2] = {{false, false}, {false, false}};
     double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
     int c_nb = 0;                       // n-blocks in use
+    const int col_t = 16 * t / SK::SZ;  // first column of this thread's chunk in group 0
 
     for (;;) {
         while (issue()) {}
@@ -361,19 +370,22 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
         const double* slot = ring + (size_t)s * SLOT_DOUBLES;
         mbar_wait(&bar_slot[s], (unsigned)((consumed / SS_STAGES) & 1));
         if (mt.x < 2) {
-            // query block mt.x of a unit of mt.w queries -> B fragments, score segments, norms
-            const double* br = slot + (size_t)g * SS_PITCH + 2 * t;
-            if (mt.x == 0) {
-                c_nb = (mt.w + 7) >> 3;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) B[0][w] = w < nw8 ? *reinterpret_cast<const double2*>(br + 8 * w) : make_double2(0.0, 0.0);
-            } else {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) B[1][w] = w < nw8 ? *reinterpret_cast<const double2*>(br + 8 * w) : make_double2(0.0, 0.0);
-            }
+            // query block mt.x of a unit of mt.w queries -> B fragments (columns >= d are 0), score segments, norms
+            const double* br = slot + (size_t)g * SS_PITCH;
+            if (mt.x == 0) c_nb = (mt.w + 7) >> 3;
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) {
                 if (nb == mt.x) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                        for (int e = 0; e < E; e += 2) {
+                            const int col = 64 * j / SK::SZ + col_t + e;          // even
+                            double2 v = make_double2(0.0, 0.0);
+                            if (j < nj && col < d) v = *reinterpret_cast<const double2*>(br + col);
+                            B[nb][j * E + e] = v.x;
+                            B[nb][j * E + e + 1] = col + 1 < d ? v.y : 0.0;
+                        }
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         c_seg[nb][e] = reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * t + e) * SS_PITCH + BM_KC)[0];
@@ -382,7 +394,7 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
                     if (ANGULAR) {
                         double sq = 0.0;    // ||query 8nb + g||^2: this thread's columns, then the 4 threads of the group
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) { sq = fma(B[nb][w].x, B[nb][w].x, sq); sq = fma(B[nb][w].y, B[nb][w].y, sq); }
+                        for (int w = 0; w < NS; ++w) sq = fma(B[nb][w], B[nb][w], sq);
                         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
                         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                         const double nrm = sqrt(sq);
@@ -395,36 +407,35 @@ k_score_stream(const double* __restrict__ X, int d, const double* __restrict__ Q
             consumed++;
             continue;
         }
-        const double* ar = slot + (size_t)g * SS_PITCH + 2 * t;
+        const unsigned char* ar = reinterpret_cast<const unsigned char*>(slot) + (size_t)g * SK::RP + 16 * t;
         double acc[2][2][2];                // [n-block][even / odd k-step chain][column]
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
             for (int c = 0; c < 2; ++c) acc[nb][c][0] = acc[nb][c][1] = 0.0;
         double xn = 0.0;
-        if (c_nb == 2) {
+        auto multiply = [&](auto two_blocks) {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                if (w < nw8) {
-                    const double2 a = *reinterpret_cast<const double2*>(ar + 8 * w);
-                    dmma884(acc[0][0][0], acc[0][0][1], a.x, B[0][w].x);
-                    dmma884(acc[1][0][0], acc[1][0][1], a.x, B[1][w].x);
-                    dmma884(acc[0][1][0], acc[0][1][1], a.y, B[0][w].y);
-                    dmma884(acc[1][1][0], acc[1][1][1], a.y, B[1][w].y);
-                    if (ANGULAR) { xn = fma(a.x, a.x, xn); xn = fma(a.y, a.y, xn); }
+            for (int j = 0; j < NJ; ++j) {
+                if (j < nj) {
+                    double a[E];
+                    widen_chunk<KIND>(*reinterpret_cast<const uint4*>(ar + 64 * j), a);
+                    if (ragged && j == nj - 1) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e)
+                            if (64 * j / SK::SZ + col_t + e >= d) a[e] = 0.0;
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        dmma884(acc[0][e & 1][0], acc[0][e & 1][1], a[e], B[0][j * E + e]);
+                        if (decltype(two_blocks)::value) dmma884(acc[1][e & 1][0], acc[1][e & 1][1], a[e], B[1][j * E + e]);
+                        if (ANGULAR) xn = fma(a[e], a[e], xn);
+                    }
                 }
             }
-        } else {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                if (w < nw8) {
-                    const double2 a = *reinterpret_cast<const double2*>(ar + 8 * w);
-                    dmma884(acc[0][0][0], acc[0][0][1], a.x, B[0][w].x);
-                    dmma884(acc[0][1][0], acc[0][1][1], a.y, B[0][w].y);
-                    if (ANGULAR) { xn = fma(a.x, a.x, xn); xn = fma(a.y, a.y, xn); }
-                }
-            }
-        }
+        };
+        if (c_nb == 2) multiply(std::true_type{});
+        else multiply(std::false_type{});
         double xnr = 1.0;
         if (ANGULAR) {
             xn += __shfl_xor_sync(0xffffffffu, xn, 1);
@@ -798,8 +809,10 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     // pair offsets of this chunk = exclusive scan of the per-(query, table) bucket counts from the probe pass
     const int64_t nslots = nqc * L + 1;
     h->pair_base.reserve(nslots);
+    const bool use_u8 = use_stream && score_u8_usable(h);      // byte store: register-gather kernel (rerank_u8.cu)
     {
         StageTimer tm(h, DPF_T_EXPAND);
+        if (use_u8 && q0 == 0) prepare_queries_u8(h, Qd, qk.nq);
         k_copy_u32<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->pair_cnt.p + q0 * L, h->pair_base.p, nslots - 1); DPF_LAUNCHED();
         DPF_CUDA(cudaMemsetAsync(h->pair_base.p + nslots - 1, 0, sizeof(uint32_t), st));
         exclusive_scan_u32(h, h->pair_base.p, nslots);
@@ -845,20 +858,22 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(h->counters.p + 26);   // cleared by probe_count_all
         h->stats[DPF_STAT_BM_PAIRS] += npairs;
         const bool ang = metric == DPF_METRIC_ANGULAR;
-        if (use_stream) {
-            static bool attr = false;
-            if (!attr) {
-                DPF_CUDA(cudaFuncSetAttribute(k_score_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
-                DPF_CUDA(cudaFuncSetAttribute(k_score_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
-                attr = true;
-            }
+        if (use_u8) {
+            launch_score_u8(h, Qd, h->bm_units.p, h->bm_counts.p + 1, ang, bm_stat);
+        } else if (use_stream) {
             const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
-            if (ang)
-                k_score_stream<true><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->ids_sorted.p,
-                                                                               h->scores.p, bm_stat);
-            else
-                k_score_stream<false><<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(h->Xdev, d, Qd, units, h->bm_counts.p + 1, h->ids_sorted.p,
-                                                                                h->scores.p, bm_stat);
+            // rows come from the compact store when the build found a narrower lossless type (store.cu)
+            const int kind = h->Xc_kind;
+            const unsigned char* rows = kind == DPF_STORE_KIND_F64 ? reinterpret_cast<const unsigned char*>(h->Xdev) : h->Xc.p;
+            const unsigned row_bytes = kind == DPF_STORE_KIND_F64 ? (unsigned)d * 8u : (unsigned)h->Xc_row_bytes;
+            auto launch = [&](auto kern) {
+                DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
+                kern<<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(rows, row_bytes, d, Qd, units, h->bm_counts.p + 1, h->ids_sorted.p,
+                                                                 h->scores.p, bm_stat);
+            };
+            if (kind == DPF_STORE_KIND_U8) { if (ang) launch(k_score_stream<true, DPF_STORE_KIND_U8>); else launch(k_score_stream<false, DPF_STORE_KIND_U8>); }
+            else if (kind == DPF_STORE_KIND_F32) { if (ang) launch(k_score_stream<true, DPF_STORE_KIND_F32>); else launch(k_score_stream<false, DPF_STORE_KIND_F32>); }
+            else { if (ang) launch(k_score_stream<true, DPF_STORE_KIND_F64>); else launch(k_score_stream<false, DPF_STORE_KIND_F64>); }
         } else {
             const char* nbv = getenv("DPF_BM_NB");
             const int nb = nbv ? atoi(nbv) : 2;

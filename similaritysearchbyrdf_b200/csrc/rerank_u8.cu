@@ -1,0 +1,350 @@
+// rerank_u8.cu — K5c: bucket-major scoring from the uint8 compact store (store.cu).
+//
+// Same job as k_score_stream (rerank_bm.cu): for every unit (one leaf bucket x <= 16 queries that probe it) one
+// score per (query, bucket row), replacing the gather + dgemv of topKAndPrecisionScore
+// (src/main/scala/mclab/deploy/DensevectorRDFInit.scala:472-507).  When the store is bytes a row is <= 128 B, i.e.
+// two 16-byte chunks per thread of a DMMA row group: the rows go straight from L2/HBM to registers with LDG.128
+// (a whole 8-row tile is 2 loads per thread), PF tiles in flight per warp, no shared-memory ring, no bulk copies, no
+// barriers — the per-row issue cost of the TMA pipeline, which bounds k_score_stream once the bytes are cheap, is gone.
+// Two instantiations:
+//   INTQ = false  queries are arbitrary doubles: bytes are widened to the identical doubles in registers (PRMT +
+//                 DADD) and multiplied on the FP64 tensor pipe (DMMA.8x8x4) against the FP64 query fragments.
+//   INTQ = true   every query of the batch is itself a vector of bytes (checked per batch, k_quantise_queries): all
+//                 products and partial sums are integers below 2^31, so the integer tensor pipe (IMMA.16x8x32,
+//                 u8 x u8 -> s32) computes the exact dot product and (double)dot is bit-identical to the FP64 sum in any
+//                 order.  This is the SIFT case (descriptors and queries are bytes).
+// k permutation (both): thread t of a row group holds bytes [16t, 16t+16) and [64+16t, 64+16t+16) of its row; the
+// query operand uses the same columns, so the sum over k is unchanged.
+#include <cstdlib>
+#include <type_traits>
+
+#include "rerank_units.cuh"
+
+namespace dpf {
+
+constexpr int U8_WARPS = 8;
+
+// ---------------------------------------------------------------------------------------------------------
+// queries -> bytes (when they are bytes)
+// ---------------------------------------------------------------------------------------------------------
+// warp per query: Q8[q][c] = (uint8)Q[q][c] (0 for the pad columns), qnorm[q] = sqrt(sum of squares) (exact integer
+// sum); *flag |= 1 if some value is not a byte
+__global__ void __launch_bounds__(256)
+k_quantise_queries(const double* __restrict__ Q, int64_t nq, int d, int pitch, unsigned char* __restrict__ Q8,
+                   double* __restrict__ qnorm, int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const double* x = Q + q * d;
+    unsigned long long sq = 0;
+    int bad = 0;
+    for (int c = lane; c < pitch; c += 32) {
+        unsigned char b = 0;
+        if (c < d) {
+            const double v = x[c];
+            b = (unsigned char)min(max(v, 0.0), 255.0);
+            if (__double_as_longlong((double)b) != __double_as_longlong(v)) bad = 1;
+            sq += (unsigned)b * (unsigned)b;
+        }
+        Q8[q * pitch + c] = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        qnorm[q] = sqrt((double)sq);
+        if (bad) atomicOr(flag, 1);
+    }
+}
+
+__device__ __forceinline__ void imma_u8(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int I>
+__device__ __forceinline__ unsigned word_of(const uint4& v) {
+    if constexpr (I == 0) return v.x;
+    else if constexpr (I == 1) return v.y;
+    else if constexpr (I == 2) return v.z;
+    else return v.w;
+}
+
+// byte b of w as a double: 2^52 + v has mantissa v; minus 2^52 is exact
+template <int B>
+__device__ __forceinline__ double byte_to_double(unsigned w) {
+    return __hiloint2double(0x43300000, (int)__byte_perm(w, 0u, 0x4440u | (unsigned)B)) - 4503599627370496.0;
+}
+
+__device__ __forceinline__ uint4 ldg_u4(const unsigned char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// k_score_u8
+// ---------------------------------------------------------------------------------------------------------
+template <bool ANGULAR, bool INTQ>
+__global__ void __launch_bounds__(U8_WARPS * 32, 1)
+k_score_u8(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: multiple of 16, <= 128 */, int d,
+           const double* __restrict__ Q, const unsigned char* __restrict__ Q8, const double* __restrict__ qnorm,
+           const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted,
+           double* __restrict__ scores, unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
+    constexpr int TR = INTQ ? 16 : 8;            // rows per tile (IMMA M = 16, DMMA M = 8)
+    constexpr int RPT = TR / 8;                  // rows per thread per tile
+    constexpr int TPW = 32 / TR;                 // tiles per id window
+    constexpr int PF = INTQ ? 3 : 4;             // tiles in flight per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;   // this thread's chunks exist
+    const bool two_chunks = pitch > 64;                              // warp-uniform
+    const int64_t nunits = *nunits_p;
+    const int64_t W = (int64_t)gridDim.x * U8_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * U8_WARPS + warp;
+    const int64_t nmine = nunits > gw ? (nunits - gw + W - 1) / W : 0;   // units gw + k * W
+    if (nmine == 0) return;
+    unsigned long long rows_staged = 0;
+
+    // record of the next unit, loaded one unit ahead (lane j < 16 keeps query j / segment j, every lane one first-window id)
+    uint32_t n_bstart, n_len, n_m, n_seg;
+    int n_q, n_id;
+    auto fetch_rec = [&](int64_t k) {
+        const UnitRec* r = units + (gw + k * W);
+        n_bstart = __ldg(&r->bstart); n_len = __ldg(&r->len); n_m = __ldg(&r->m);
+        n_q = __ldg(&r->q[lane & (SS_UQ - 1)]);
+        n_seg = __ldg(&r->seg[lane & (SS_UQ - 1)]);
+        n_id = __ldg(&r->ids0[lane]);
+    };
+    fetch_rec(0);
+
+    for (int64_t k = 0; k < nmine; ++k) {
+        const uint32_t bstart = n_bstart;
+        const int len = (int)n_len, m = (int)n_m;
+        const int my_q = n_q, id_first = n_id;
+        const uint32_t my_seg = n_seg;
+        if (k + 1 < nmine) fetch_rec(k + 1);
+        rows_staged += (unsigned)len;
+        const int nb_used = (m + 7) >> 3;
+
+        // ---- query operand --------------------------------------------------------------------------------------
+        uint4 bq[2][2];                      // INTQ: this thread's two chunks of queries g and 8 + g
+        double B[INTQ ? 1 : 2][INTQ ? 1 : 32];   // FP64: k-step c * 16 + e <-> column 64c + 16t + e
+        double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
+        uint32_t c_seg[2][2];
+        bool c_ok[2][2];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int qi = __shfl_sync(0xffffffffu, my_q, 8 * nb + g);
+            const bool valid = 8 * nb + g < m;
+            if constexpr (INTQ) {
+                const unsigned char* qp = Q8 + (size_t)qi * pitch + 16 * t;
+                bq[nb][0] = (valid && has0) ? ldg_u4(qp) : make_uint4(0, 0, 0, 0);
+                bq[nb][1] = (valid && has1) ? ldg_u4(qp + 64) : make_uint4(0, 0, 0, 0);
+            } else {
+                const double* qp = Q + (int64_t)qi * d;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const int col = 64 * c + 16 * t + e;          // even; d is even
+                        double2 v = make_double2(0.0, 0.0);
+                        if (valid && col < d) v = __ldg(reinterpret_cast<const double2*>(qp + col));
+                        B[nb][16 * c + e] = v.x;
+                        B[nb][16 * c + e + 1] = v.y;
+                    }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * nb + 2 * t + e;
+                c_seg[nb][e] = __shfl_sync(0xffffffffu, my_seg, j);
+                c_ok[nb][e] = j < m;
+                if (ANGULAR && INTQ) {
+                    const int qj = __shfl_sync(0xffffffffu, my_q, j);
+                    c_qn[nb][e] = c_ok[nb][e] ? __ldg(qnorm + qj) : 1.0;
+                }
+            }
+            if constexpr (ANGULAR && !INTQ) {
+                double sq = 0.0;             // ||query 8nb + g||^2: this thread's columns, then the 4 threads of the group
+#pragma unroll
+                for (int w = 0; w < 32; ++w) sq = fma(B[nb][w], B[nb][w], sq);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                const double nrm = sqrt(sq);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) c_qn[nb][e] = __shfl_sync(0xffffffffu, nrm, (2 * t + e) * 4);
+            }
+        }
+
+        // ---- rows: ids by 32-row windows (one window ahead), tiles of TR rows, PF tiles in flight ---------------------
+        const int ntiles = (len + TR - 1) / TR;
+        const int32_t* bids = ids_sorted + bstart;
+        int win_lo = 0;                      // idA = ids of window win_lo, idB = window win_lo + 1
+        int idA = id_first;
+        int idB = 32 < len ? __ldg(bids + min(32 + lane, len - 1)) : 0;
+        uint4 a[PF][RPT][2];
+        auto load_tile = [&](uint4 (&dst)[RPT][2], int tile) {
+            const int wi = tile / TPW;
+            if (wi > win_lo) {               // warp-uniform; tiles are loaded in increasing order
+                idA = idB;
+                win_lo = wi;
+                idB = 32 * (wi + 1) < len ? __ldg(bids + min(32 * (wi + 1) + lane, len - 1)) : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int row = min(tile * TR + 8 * r + g, len - 1);
+                const int id = __shfl_sync(0xffffffffu, idA, row - 32 * wi);
+                const unsigned char* xp = X8 + (size_t)id * pitch + 16 * t;
+                dst[r][0] = has0 ? ldg_u4(xp) : make_uint4(0, 0, 0, 0);
+                dst[r][1] = has1 ? ldg_u4(xp + 64) : make_uint4(0, 0, 0, 0);
+            }
+        };
+        auto store_scores = [&](int row, int nb, int e, double dot, double xnr) {
+            if (row < len && nb < nb_used && c_ok[nb][e])
+                scores[(size_t)c_seg[nb][e] + row] = ANGULAR ? dot / (c_qn[nb][e] * xnr) : dot;
+        };
+        auto compute_tile = [&](const uint4 (&src)[RPT][2], int tile) {
+            if constexpr (INTQ) {
+                int acc[2][4];
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[nb][i] = 0;
+                auto steps = [&](auto chunk) {
+                    constexpr int C = decltype(chunk)::value;
+                    imma_u8(acc[0], src[0][C].x, src[1][C].x, src[0][C].y, src[1][C].y, bq[0][C].x, bq[0][C].y);
+                    imma_u8(acc[0], src[0][C].z, src[1][C].z, src[0][C].w, src[1][C].w, bq[0][C].z, bq[0][C].w);
+                    if (nb_used == 2) {
+                        imma_u8(acc[1], src[0][C].x, src[1][C].x, src[0][C].y, src[1][C].y, bq[1][C].x, bq[1][C].y);
+                        imma_u8(acc[1], src[0][C].z, src[1][C].z, src[0][C].w, src[1][C].w, bq[1][C].z, bq[1][C].w);
+                    }
+                };
+                steps(std::integral_constant<int, 0>{});
+                if (two_chunks) steps(std::integral_constant<int, 1>{});
+                double xnr[2] = {1.0, 1.0};
+                if (ANGULAR) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        unsigned s = 0;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            s = __dp4a(src[r][c].x, src[r][c].x, s); s = __dp4a(src[r][c].y, src[r][c].y, s);
+                            s = __dp4a(src[r][c].z, src[r][c].z, s); s = __dp4a(src[r][c].w, src[r][c].w, s);
+                        }
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        xnr[r] = sqrt((double)s);
+                    }
+                }
+                // thread (g, t): c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) store_scores(tile * TR + 8 * r + g, nb, e, (double)acc[nb][2 * r + e], xnr[r]);
+            } else {
+                double acc[2][2][2];            // [n-block][even / odd k-step chain][column]
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) acc[nb][c][0] = acc[nb][c][1] = 0.0;
+                double xn = 0.0;
+                auto steps = [&](auto chunk, auto two_blocks) {
+                    constexpr int C = decltype(chunk)::value;
+                    auto word = [&](auto wi, unsigned w) {
+                        constexpr int WI = decltype(wi)::value;
+                        const double a0 = byte_to_double<0>(w), a1 = byte_to_double<1>(w);
+                        const double a2 = byte_to_double<2>(w), a3 = byte_to_double<3>(w);
+                        constexpr int S = 16 * C + 4 * WI;
+                        dmma884(acc[0][0][0], acc[0][0][1], a0, B[0][S]);
+                        if (decltype(two_blocks)::value) dmma884(acc[1][0][0], acc[1][0][1], a0, B[1][S]);
+                        dmma884(acc[0][1][0], acc[0][1][1], a1, B[0][S + 1]);
+                        if (decltype(two_blocks)::value) dmma884(acc[1][1][0], acc[1][1][1], a1, B[1][S + 1]);
+                        dmma884(acc[0][0][0], acc[0][0][1], a2, B[0][S + 2]);
+                        if (decltype(two_blocks)::value) dmma884(acc[1][0][0], acc[1][0][1], a2, B[1][S + 2]);
+                        dmma884(acc[0][1][0], acc[0][1][1], a3, B[0][S + 3]);
+                        if (decltype(two_blocks)::value) dmma884(acc[1][1][0], acc[1][1][1], a3, B[1][S + 3]);
+                        if (ANGULAR) { xn = fma(a0, a0, xn); xn = fma(a1, a1, xn); xn = fma(a2, a2, xn); xn = fma(a3, a3, xn); }
+                    };
+                    word(std::integral_constant<int, 0>{}, src[0][C].x);
+                    word(std::integral_constant<int, 1>{}, src[0][C].y);
+                    word(std::integral_constant<int, 2>{}, src[0][C].z);
+                    word(std::integral_constant<int, 3>{}, src[0][C].w);
+                };
+                if (nb_used == 2) {
+                    steps(std::integral_constant<int, 0>{}, std::true_type{});
+                    if (two_chunks) steps(std::integral_constant<int, 1>{}, std::true_type{});
+                } else {
+                    steps(std::integral_constant<int, 0>{}, std::false_type{});
+                    if (two_chunks) steps(std::integral_constant<int, 1>{}, std::false_type{});
+                }
+                double xnr = 1.0;
+                if (ANGULAR) {
+                    xn += __shfl_xor_sync(0xffffffffu, xn, 1);
+                    xn += __shfl_xor_sync(0xffffffffu, xn, 2);
+                    xnr = sqrt(xn);
+                }
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) store_scores(tile * TR + g, nb, e, acc[nb][0][e] + acc[nb][1][e], xnr);
+            }
+        };
+
+#pragma unroll
+        for (int p = 0; p < PF; ++p)
+            if (p < ntiles) load_tile(a[p], p);
+        for (int base = 0; base < ntiles; base += PF) {
+#pragma unroll
+            for (int p = 0; p < PF; ++p) {
+                const int tile = base + p;
+                if (tile < ntiles) {             // warp-uniform
+                    compute_tile(a[p], tile);
+                    if (tile + PF < ntiles) load_tile(a[p], tile + PF);
+                }
+            }
+        }
+    }
+    if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], rows_staged); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+bool score_u8_usable(const dpf_index* h) {
+    const char* e = getenv("DPF_BM_KERNEL");
+    if (e && (e[0] == 's' || e[0] == 'w')) return false;      // =stream / =warps: the other bucket-major kernels
+    return h->Xc_kind == DPF_STORE_KIND_U8 && h->Xc_row_bytes <= 128;
+}
+
+void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq) {
+    h->Q8_valid = false;
+    const char* e = getenv("DPF_U8_IMMA");
+    if (e && e[0] == '0') return;                             // DPF_U8_IMMA=0: always multiply on the FP64 tensor pipe
+    cudaStream_t st = h->stream;
+    const int pitch = (int)h->Xc_row_bytes;
+    h->Q8.reserve((size_t)nq * pitch);
+    h->qnorm8.reserve((size_t)nq);
+    int* flag = h->counters.p + 41;
+    DPF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    k_quantise_queries<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Qd, nq, h->cfg.d, pitch, h->Q8.p, h->qnorm8.p, flag); DPF_LAUNCHED();
+    int f = 1;
+    DPF_CUDA(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaStreamSynchronize(st));
+    // integer dot products must stay below 2^31: d * 255 * 255
+    h->Q8_valid = f == 0 && (int64_t)h->cfg.d * 255 * 255 < (1LL << 31);
+}
+
+void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const uint32_t* nunits_p, bool angular,
+                     unsigned long long* bm_stat) {
+    const UnitRec* units = reinterpret_cast<const UnitRec*>(units_v);
+    const unsigned pitch = (unsigned)h->Xc_row_bytes;
+    const int d = h->cfg.d;
+    cudaStream_t st = h->stream;
+    auto launch = [&](auto kern, int ctas_per_sm) {
+        kern<<<h->num_sms * ctas_per_sm, U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, d, Qd, h->Q8.p, h->qnorm8.p, units, nunits_p,
+                                                                h->ids_sorted.p, h->scores.p, bm_stat);
+    };
+    if (h->Q8_valid) { if (angular) launch(k_score_u8<true, true>, 1); else launch(k_score_u8<false, true>, 1); }
+    else { if (angular) launch(k_score_u8<true, false>, 1); else launch(k_score_u8<false, false>, 1); }
+}
+
+}  // namespace dpf

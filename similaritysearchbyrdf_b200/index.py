@@ -70,6 +70,11 @@ class DPFIndex:
         torch.cuda.current_stream().cuda_stream); 0/None restores the index's own stream."""
         self._ck(self.lib.dpf_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
+    def set_store_mode(self, mode):
+        """B.STORE_AUTO (default): keep a lossless uint8 / float32 copy of the dense store for the re-rank kernels when
+        every value round-trips; B.STORE_F64_ONLY: always read the FP64 rows.  Call before fit."""
+        self._ck(self.lib.dpf_set_store_mode(self.h, mode))
+
     # ---- hash functions -------------------------------------------------------------------------------------
     def set_family(self, A, chain_idx, b=None, w=None):
         A, chain_idx = _f64(A), _i32(chain_idx)

@@ -302,6 +302,105 @@ def test_topk_bucket_major_self_exclusion_and_qids():
     assert not any(qids[i] in ig[i] for i in range(128))
 
 
+# ---- compact store (store.cu): lossless uint8 / float32 copy of the rows for the re-rank ----------------------------
+def _store_data(kind, n, d, seed):
+    rng = np.random.default_rng(seed)
+    centres = rng.standard_normal((12, d))
+    X = np.repeat(centres, n // 12, axis=0) + 0.05 * rng.standard_normal((n // 12 * 12, d))
+    if kind == B.STORE_KIND_U8:
+        X = np.clip(np.rint(60 * X + 128), 0, 255) + 0.0          # + 0.0: rint can leave -0.0, which is not a byte
+    elif kind == B.STORE_KIND_F32:
+        X = X.astype(np.float32).astype(np.float64)
+    return X
+
+
+@pytest.mark.parametrize("d", [36, 100, 128])
+@pytest.mark.parametrize("kind", [B.STORE_KIND_F64, B.STORE_KIND_F32, B.STORE_KIND_U8])
+@pytest.mark.parametrize("metric", [B.METRIC_DOT, B.METRIC_ANGULAR])
+def test_compact_store_kinds_match_oracle(d, kind, metric):
+    """The fit picks the narrowest lossless element type; top-k through the bucket-major kernel that widens it back to
+    FP64 equals the oracle on the FP64 rows (ids exact, scores 1e-12) — ragged last chunk at d = 36, 100."""
+    X = _store_data(kind, 3000, d, 300 + d)
+    rng = np.random.default_rng(7)
+    A, chain, Ap = U.make_functions(d, family_size=max(40, d), table_num=3, permutation_num=2, seed=41 + d)
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=30); ix = U.make_index(d, A, chain, Ap, bucket_overflow=30)
+    o.fit_dense(X); ix.fit_dense(X)
+    st = ix.stats()
+    assert st["store_kind"] == kind
+    assert st["store_row_bytes"] == {B.STORE_KIND_F64: 8 * d, B.STORE_KIND_F32: 4 * d, B.STORE_KIND_U8: (d + 15) // 16 * 16}[kind]
+    Qs = X[::5] + 0.01 * rng.standard_normal((600, d))        # FP64 queries whatever the store
+    io, so = o.query_topk_dense(Qs, None, 1, 10, metric)
+    ig, sg = ix.query_topk_dense(Qs, None, 1, 10, metric)
+    U.assert_topk_close(io, so, ig, sg)
+    assert ix.stats()["bm_pairs"] > 0, "the bucket-major path did not run"
+    if kind == B.STORE_KIND_U8:
+        # byte queries against byte rows: the integer tensor pipe computes the same exact dot products
+        Qb = np.ascontiguousarray(X[3::7])
+        io, so = o.query_topk_dense(Qb, None, 1, 10, metric)
+        ig, sg = ix.query_topk_dense(Qb, None, 1, 10, metric)
+        U.assert_topk_close(io, so, ig, sg)
+        if metric == B.METRIC_DOT:
+            assert np.array_equal(so[~np.isnan(so)], sg[~np.isnan(sg)]), "integer dot products must be exact"
+
+
+def test_compact_store_bitwise_equal_to_f64_rows_on_integer_data(monkeypatch):
+    """uint8 rows widened in registers are the same doubles: with integer-valued queries every product and sum is
+    exact, so the narrow store and the FP64 store must agree bit for bit."""
+    X, Q = synth.config2(n=60_000, nq=512, d=128)
+    A, chain = synth.angle_family(128, 128, 10, 3, 32, 88389)
+    Ap = synth.partitioner_family(30, 3, 88390)
+    res = {}
+    for mode in (B.STORE_AUTO, B.STORE_F64_ONLY):
+        ix = U.make_index(128, A, chain, Ap, bucket_overflow=100)
+        ix.set_store_mode(mode)
+        ix.fit_dense(X)
+        assert ix.stats()["store_kind"] == (B.STORE_KIND_U8 if mode == B.STORE_AUTO else B.STORE_KIND_F64)
+        res[mode] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
+        if mode == B.STORE_AUTO:
+            # the same byte rows on the FP64 tensor pipe (DPF_U8_IMMA=0) and through the TMA ring kernel
+            monkeypatch.setenv("DPF_U8_IMMA", "0")
+            res["u8_dmma"] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
+            monkeypatch.delenv("DPF_U8_IMMA")
+            monkeypatch.setenv("DPF_BM_KERNEL", "stream")
+            res["u8_stream"] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
+            monkeypatch.delenv("DPF_BM_KERNEL")
+        ix.close()
+    for name in (B.STORE_AUTO, "u8_dmma", "u8_stream"):
+        for a, b in zip(res[name], res[B.STORE_F64_ONLY]):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), name
+
+
+@pytest.mark.parametrize("poison,expect", [(-0.0, B.STORE_KIND_F32), (256.0, B.STORE_KIND_F32), (0.5, B.STORE_KIND_F32),
+                                           (0.1, B.STORE_KIND_F64), (1e300, B.STORE_KIND_F64), (None, B.STORE_KIND_U8)])
+def test_compact_store_one_value_decides(poison, expect):
+    """Never lossy: a single value that does not survive the round trip (including -0.0 for uint8) widens the store."""
+    d = 32
+    X = _store_data(B.STORE_KIND_U8, 1200, d, 5)
+    if poison is not None:
+        X[777, 13] = poison
+    A, chain, Ap = U.make_functions(d, family_size=40, table_num=2, permutation_num=1, seed=3)
+    ix = U.make_index(d, A, chain, Ap, bucket_overflow=30)
+    ix.fit_dense(X)
+    assert ix.stats()["store_kind"] == expect
+
+
+def test_compact_store_append_widens():
+    """Appending vectors that are not bytes re-types the store; results still equal the oracle's."""
+    d = 64
+    X1 = _store_data(B.STORE_KIND_U8, 1800, d, 11)
+    X2 = _store_data(B.STORE_KIND_F64, 600, d, 12) * 60 + 128
+    A, chain, Ap = U.make_functions(d, family_size=64, table_num=3, permutation_num=1, seed=13)
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=30); ix = U.make_index(d, A, chain, Ap, bucket_overflow=30)
+    o.fit_dense(X1); ix.fit_dense(X1)
+    assert ix.stats()["store_kind"] == B.STORE_KIND_U8
+    o.fit_dense(X2); ix.fit_dense(X2)
+    assert ix.stats()["store_kind"] == B.STORE_KIND_F64
+    Qs = np.concatenate([X1[::30], X2[::10]]) + 0.25
+    io, so = o.query_topk_dense(Qs, None, 1, 10, B.METRIC_DOT)
+    ig, sg = ix.query_topk_dense(Qs, None, 1, 10, B.METRIC_DOT)
+    U.assert_topk_close(io, so, ig, sg)
+
+
 # ---- error behaviour -----------------------------------------------------------------------------------------
 def test_error_codes():
     from similaritysearchbyrdf_b200 import DPFIndex
