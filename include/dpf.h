@@ -45,7 +45,7 @@ enum { DPF_METRIC_DOT = 0, DPF_METRIC_ANGULAR = 1, DPF_METRIC_L2 = 2 };
 enum { DPF_PROBE_NONE = 0, DPF_PROBE_DENSE = 1 };
 /* element type of the compact vector store the re-rank kernels read (see dpf_set_store_mode) */
 enum { DPF_STORE_KIND_F64 = 0, DPF_STORE_KIND_F32 = 1, DPF_STORE_KIND_U8 = 2 };
-enum { DPF_STORE_AUTO = 0, DPF_STORE_F64_ONLY = 1 };
+enum { DPF_STORE_AUTO = 0, DPF_STORE_F64_ONLY = 1, DPF_STORE_NARROWEST = 2 };
     /* DPF_PROBE_DENSE: getSimilarWithStepWiseFaster(key, DenseVector, steps) multi-probe (RandomDrawTreeMap.java:742-797)
        DPF_PROBE_NONE : sparse overload / id-based getSimilarWithStepWise (RandomDrawTreeMap.java:686-732, 630-675) */
 
@@ -101,12 +101,13 @@ int dpf_fit_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, con
 /* X_dev stays owned by the caller and must outlive the handle (no copy is made: 100M x 96 FP64 is 76.8 GB) */
 int dpf_fit_dense_dev(dpf_handle h, const double* X_dev, int64_t n);
 int64_t dpf_size(dpf_handle h);
-/* The reference keeps every vector as double[] (vectorIdToVector, DensevectorRDFInit.scala:35-36).  With
- * DPF_STORE_AUTO (default) a dense fit also checks whether EVERY stored value survives a round trip through a
- * narrower type (uint8: SIFT-like descriptors; float: fvecs data) and, if so, keeps a copy in that type for the
- * re-rank kernels, which widen it back to FP64 in registers — the products and sums are the same FP64 operations on
- * the same values, only 1/8 or 1/2 of the bytes cross HBM.  Lossy narrowing is never done.  DPF_STORE_F64_ONLY turns
- * the check off (call before fit).  DPF_STAT_STORE_KIND reports the kind in use. */
+/* The reference keeps every vector as double[] (vectorIdToVector, DensevectorRDFInit.scala:35-36).  A dense fit also
+ * checks whether EVERY stored value survives a round trip through a narrower type and, if so, keeps a copy of the rows
+ * in that type for the re-rank kernels, which widen it back to the identical doubles in registers (or, when the queries
+ * of a batch are bytes too, multiply exact integers): the products and sums are the same, only 1/8 (1/2) of the bytes
+ * cross HBM.  Lossy narrowing is never done.  DPF_STORE_AUTO (default): uint8 when lossless (SIFT-like descriptors);
+ * DPF_STORE_NARROWEST: uint8, else float when lossless (fvecs data); DPF_STORE_F64_ONLY: no check, FP64 rows only.
+ * Call before fit.  DPF_STAT_STORE_KIND reports the kind in use. */
 int dpf_set_store_mode(dpf_handle h, int32_t mode);
 
 /* ---- query: candidate sets = DensevectorRDFInit.NewMultiThreadQueryBatch (DensevectorRDFInit.scala:335-360),
@@ -165,6 +166,7 @@ enum {
     DPF_STAT_BM_ROWS_STAGED = 11,  /*   bucket rows staged in shared memory (each one row of the store)      */
     DPF_STAT_STORE_KIND = 12,      /* DPF_STORE_KIND_* of the compact store after the last dense fit         */
     DPF_STAT_STORE_ROW_BYTES = 13, /* bytes per row the re-rank kernels fetch                                */
+    DPF_STAT_BM_SURVIVORS = 14,    /* bucket-major re-rank, last batch: scores that passed the threshold filter */
     DPF_STAT_COUNT = 16
 };
 int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occupancy_out /* 2^pb or NULL */);

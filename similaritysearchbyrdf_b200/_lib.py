@@ -13,11 +13,11 @@ KEY_ORIGINAL, KEY_SAMPLING, KEY_CONTINUE_BITS, KEY_ANGLE_NEW = 0, 1, 2, 3
 METRIC_DOT, METRIC_ANGULAR, METRIC_L2 = 0, 1, 2
 PROBE_NONE, PROBE_DENSE = 0, 1
 STORE_KIND_F64, STORE_KIND_F32, STORE_KIND_U8 = 0, 1, 2
-STORE_AUTO, STORE_F64_ONLY = 0, 1
+STORE_AUTO, STORE_F64_ONLY, STORE_NARROWEST = 0, 1, 2
 STAT_COUNT, T_COUNT = 16, 16
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
               "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",
-              "bm_rows_staged", "store_kind", "store_row_bytes"]
+              "bm_rows_staged", "store_kind", "store_row_bytes", "bm_survivors"]
 STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select", "narrow"]
 
 # every symbol include/dpf.h declares

@@ -428,7 +428,7 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
 
 int dpf_set_store_mode(dpf_handle h, int32_t mode) {
     return guarded(h, [&] {
-        DPF_REQUIRE(mode == DPF_STORE_AUTO || mode == DPF_STORE_F64_ONLY, DPF_ERR_INVALID, "bad store mode");
+        DPF_REQUIRE(mode == DPF_STORE_AUTO || mode == DPF_STORE_F64_ONLY || mode == DPF_STORE_NARROWEST, DPF_ERR_INVALID, "bad store mode");
         DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "dpf_set_store_mode must be called before fit");
         h->store_mode = mode;
     });
@@ -554,7 +554,8 @@ static void topk_device(dpf_index* h, const double* Qd, int64_t nq, const int32_
     for (int64_t q0 = 0; q0 < nq;) {   // memory-bounded chunks of queries: expand -> gather/re-rank/top-k
         const int64_t q1 = next_chunk_end(ub, q0, kCandBudget);
         const int64_t base = ub[(size_t)q0];
-        if (bucket_major_supported(h, metric, topk) && ub[(size_t)q1] - base < (1LL << 32)) {
+        if (bucket_major_supported(h, metric, topk) && (reinterpret_cast<uintptr_t>(Qd) & 15) == 0 &&
+            ub[(size_t)q1] - base < (1LL << 32)) {   // query rows are moved by 16-byte bulk copies / LDG.128
             topk_bucket_major(h, Qd, qk, steps, probe_mode, q0, q1, ub[(size_t)q1] - base, topk, metric, ids_out_dev,
                               score_out_dev);
             q0 = q1;
@@ -690,11 +691,12 @@ int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
             DPF_CUDA(cudaMemcpyAsync(&u, h->counters.p + 24, sizeof(u), cudaMemcpyDeviceToHost, h->stream));
             DPF_CUDA(cudaStreamSynchronize(h->stream));
             h->stats[DPF_STAT_LAST_CANDIDATES] = (int64_t)u;
-            unsigned long long bm[2] = {0, 0};
+            unsigned long long bm[3] = {0, 0, 0};
             DPF_CUDA(cudaMemcpyAsync(bm, h->counters.p + 26, sizeof(bm), cudaMemcpyDeviceToHost, h->stream));
             DPF_CUDA(cudaStreamSynchronize(h->stream));
             h->stats[DPF_STAT_BM_RUNS] = (int64_t)bm[0];
             h->stats[DPF_STAT_BM_ROWS_STAGED] = (int64_t)bm[1];
+            h->stats[DPF_STAT_BM_SURVIVORS] = (int64_t)bm[2];
         }
         h->stats[DPF_STAT_KERNEL_LAUNCHES] = (int64_t)g_launches;
         for (int i = 0; i < DPF_STAT_COUNT; ++i) stats_out[i] = h->stats[i];

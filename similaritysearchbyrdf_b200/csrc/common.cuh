@@ -181,7 +181,12 @@ struct dpf_index {
     dpf::DevBuf<uint32_t> scan_scratch, pair_cnt, pair_base, pair_seg, pair_len;   // bucket-major re-rank
     dpf::DevBuf<int32_t> pair_q;
     dpf::DevBuf<unsigned long long> pair_key, pair_key_alt;
-    dpf::DevBuf<double> scores;
+    dpf::DevBuf<double> scores;                // bucket-major re-rank: survivor scores / ids (Filter, rerank_units.cuh)
+    dpf::DevBuf<int32_t> surv_id;
+    dpf::DevBuf<double> bm_tau;                // per query: score threshold
+    dpf::DevBuf<uint32_t> bm_scnt, bm_sbase;   //            survivors so far, start of its list
+    dpf::DevBuf<double> bm_tl_keys;            // threshold sample lists: nq x NT x k
+    dpf::DevBuf<int> bm_tl_ids, bm_tl_cnt;
     dpf::DevBuf<uint32_t> bm_flag, bm_run_start, bm_ucnt, bm_counts;   // runs / units of the sorted pairs
     dpf::DevBuf<char> bm_units;
     unsigned long long* bm_sorted = nullptr;   // pair keys sorted by bucket (points into pair_key_alt / sk64a)

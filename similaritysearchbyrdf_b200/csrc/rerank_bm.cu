@@ -26,7 +26,6 @@
 
 namespace dpf {
 
-constexpr int BM_QT = 32;              // pairs per group of the register-gather kernel (k_score_warps)
 
 bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
     const char* e = getenv("DPF_RERANK");
@@ -108,8 +107,8 @@ k_run_unit_counts(const uint32_t* __restrict__ run_start, const uint32_t* __rest
 __global__ void __launch_bounds__(256)
 k_emit_units(const unsigned long long* __restrict__ sorted, int64_t npairs, const uint32_t* __restrict__ run_idx,
              const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ uoff, const int32_t* __restrict__ pair_q,
-             const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg, const int32_t* __restrict__ ids_sorted,
-             UnitRec* __restrict__ units) {
+             const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg, const double* __restrict__ tau /* or null */,
+             const int32_t* __restrict__ ids_sorted, UnitRec* __restrict__ units) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const unsigned long long k = sorted[p];
@@ -128,6 +127,7 @@ k_emit_units(const unsigned long long* __restrict__ sorted, int64_t npairs, cons
         const uint32_t pi = (uint32_t)sorted[min((uint32_t)p + j, p1 - 1)];
         rec.q[j] = pair_q[pi];
         rec.seg[j] = pair_seg[pi];
+        rec.tau[j] = tau ? tau[rec.q[j]] : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < SS_WIN; ++j) rec.ids0[j] = ids_sorted[bstart + min((uint32_t)j, rec.len - 1)];
@@ -310,7 +310,7 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
         const UnitRec* r = &recs[pk & 1];
         const int s = issued % SS_STAGES;
         double* slot = ring + (size_t)s * SLOT_DOUBLES;
-        if (p_phase < 2) {             // 8 query rows (always FP64); each row's score segment rides in the row's padding
+        if (p_phase < 2) {             // 8 query rows (always FP64)
             const int nrows = min(SS_ROWS, (int)p_m - SS_ROWS * p_phase);
             if (lane == 0) {
                 meta[warp][s] = make_int4(p_phase, 0, nrows, (int)p_m);
@@ -319,7 +319,7 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
             __syncwarp();
             if (lane < nrows) {
                 const int j = SS_ROWS * p_phase + lane;
-                reinterpret_cast<uint32_t*>(slot + (size_t)lane * SS_PITCH + BM_KC)[0] = r->seg[j];
+                reinterpret_cast<uint32_t*>(slot + (size_t)lane * SS_PITCH + BM_KC)[0] = r->seg[j];   // rides in the row's padding
                 bulk_g2s(slot + (size_t)lane * SS_PITCH, Q + (int64_t)r->q[j] * d, q_bytes, &bar_slot[s], pol_keep);
             }
             p_phase = (p_phase == 0 && p_m > SS_ROWS) ? 1 : 2;
@@ -460,200 +460,281 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
     if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], rows_staged); }
 }
 
-// Warp-autonomous variant (d even): every warp is an independent worker that pulls groups of BM_QT sorted pairs
-// from a counter.  A-operand fragments (bucket rows) go straight from global memory to registers with LDG.128 —
-// 16 independent 128-bit loads per 8-row block, two blocks in flight per warp (register double buffering), no
-// shared-memory staging of rows and no CTA barrier — using a k permutation (k-step 2w takes columns 8w+2t, k-step
-// 2w+1 takes 8w+2t+1) so that each thread's two fragment elements are adjacent in memory; the B operand (up to
-// 8*NB queries of the run) sits in the warp's private slice of shared memory with the same permutation.
-constexpr int WQ_PITCH = BM_KC + 8;           // (pitch * 8) mod 128 == 64: conflict-free LDS.128 per quarter warp
+// ---------------------------------------------------------------------------------------------------------
+// k_threshold — one CTA per query, one sampled table per warp: tau[q] = a score that k distinct candidates of the query are guaranteed to reach
+// in the scoring kernel.  The warp scores the rows of the first bucket the query probes in each of its first NT
+// tables (in practice its own bucket: the probe with the lowest bit flipped usually falls below the leaf's level) with
+// plain FP64 FMAs, keeps the k best distinct rows by a LOWER BOUND of their score — score minus (more than) twice the rounding
+// bound (d + 2) * 2^-53 * sum |x_c q_c| of a length-d dot product in any order, which covers the different summation
+// order of the tensor-pipe kernels — and publishes the k-th.  Fewer than k rows seen: tau = -inf (keep everything).
+// Also sets the query's survivor list: base = start of its score segment, cnt = 0.
+// ---------------------------------------------------------------------------------------------------------
+// 16 consecutive columns of a stored row: raw 16-byte vectors (loaded ahead) and their widening to doubles
+template <int KIND> struct RawRow { static constexpr int N = KIND == DPF_STORE_KIND_U8 ? 1 : (KIND == DPF_STORE_KIND_F32 ? 4 : 8); };
 
-template <int NB>
-struct WarpCfg {
-    static constexpr int WQ = 8 * NB;                                               // queries per pass
-    static constexpr int WARPS = (NB == 1) ? 8 : (NB == 2 ? 8 : 6);                 // shared memory bound
-    static constexpr size_t SMEM = (size_t)WARPS * WQ * WQ_PITCH * sizeof(double);
-};
-
-template <bool ANGULAR, int NB>
-__global__ void __launch_bounds__(WarpCfg<NB>::WARPS * 32, 1)
-k_score_warps(const double* __restrict__ X, int d, const double* __restrict__ Q,
-              const unsigned long long* __restrict__ pair_key /* sorted by bucket */, int64_t npairs,
-              const int32_t* __restrict__ pair_q, const uint32_t* __restrict__ pair_len,
-              const uint32_t* __restrict__ pair_seg, const int32_t* __restrict__ ids_sorted, double* __restrict__ scores,
-              int* __restrict__ next_group, unsigned long long* __restrict__ stat /* [0] runs, [1] rows staged */) {
-    constexpr int WQ = WarpCfg<NB>::WQ;
-    constexpr int NW = BM_KC / 8;
-    extern __shared__ double wsm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    double* Qw = wsm + warp * WQ * WQ_PITCH;
-    for (int i = lane; i < WQ * WQ_PITCH; i += 32) Qw[i] = 0.0;     // k padding stays zero: only columns < d are written
-    __syncwarp();
-    const int nw8 = (d + 7) >> 3;                                    // 8-column windows in use
-    const int64_t ngroups = (npairs + BM_QT - 1) / BM_QT;
-    unsigned long long runs = 0, rows_staged = 0;
-    for (;;) {
-        long long grp = 0;
-        if (lane == 0) grp = atomicAdd(next_group, 1);
-        grp = __shfl_sync(0xffffffffu, grp, 0);
-        if (grp >= ngroups) break;
-        const int64_t p0 = grp * BM_QT;
-        const int np = (int)min((int64_t)BM_QT, npairs - p0);
-        const unsigned long long mykey = lane < np ? pair_key[p0 + lane] : ~0ULL;
-        const uint32_t mybucket = (uint32_t)(mykey >> 32);
-        int j0 = 0;
-        while (j0 < np) {
-            const uint32_t bstart = __shfl_sync(0xffffffffu, mybucket, j0);
-            const uint32_t same = __ballot_sync(0xffffffffu, lane >= j0 && lane < np && mybucket == bstart);
-            const int m = __popc(same);                              // sorted => the run is lanes j0 .. j0+m-1
-            const uint32_t first_pair = (uint32_t)__shfl_sync(0xffffffffu, mykey, j0);
-            const int blen = (int)__ldg(pair_len + first_pair);
-            const int32_t* bids = ids_sorted + bstart;
-            runs++;
-            for (int c0 = j0; c0 < j0 + m; c0 += WQ) {
-                const int mc = min(WQ, j0 + m - c0);
-                const int nbu = (mc + 7) >> 3;                       // n-blocks in use this pass
-                rows_staged += blen;
-                __syncwarp();
-                {   // stage this pass's queries (row r of Qw = pair c0 + r): lane r fetches its query index, then the
-                    // rows are copied with all loads of 4 queries in flight at a time
-                    const uint32_t mypi = (uint32_t)mykey;
-                    const int myq = (lane >= c0 && lane < c0 + mc) ? __ldg(pair_q + mypi) : 0;
-                    for (int r0 = 0; r0 < mc; r0 += 4) {
-                        double2 v[4][BM_KC / 64];
+template <int KIND>
+__device__ __forceinline__ void raw_to_cols16(const uint4 (&raw)[RawRow<KIND>::N], double (&x)[16]) {
+    if constexpr (KIND == DPF_STORE_KIND_U8) {
+        const uint32_t w[4] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w};
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int qidx = __shfl_sync(0xffffffffu, myq, min(c0 + r0 + u, c0 + mc - 1));
-                            const double* qsrc = Q + (int64_t)qidx * d;
+        for (int i = 0; i < 16; ++i) x[i] = (double)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+    } else if constexpr (KIND == DPF_STORE_KIND_F32) {
 #pragma unroll
-                            for (int i = 0; i < BM_KC / 64; ++i) {
-                                const int cc = 2 * lane + 64 * i;
-                                v[u][i] = (cc < d) ? __ldg(reinterpret_cast<const double2*>(qsrc + cc)) : make_double2(0.0, 0.0);
-                            }
-                        }
+        for (int i = 0; i < 4; ++i) {
+            x[4 * i] = (double)__uint_as_float(raw[i].x); x[4 * i + 1] = (double)__uint_as_float(raw[i].y);
+            x[4 * i + 2] = (double)__uint_as_float(raw[i].z); x[4 * i + 3] = (double)__uint_as_float(raw[i].w);
+        }
+    } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (r0 + u < mc) {
-#pragma unroll
-                                for (int i = 0; i < BM_KC / 64; ++i) {
-                                    const int cc = 2 * lane + 64 * i;
-                                    if (cc < d) *reinterpret_cast<double2*>(Qw + (r0 + u) * WQ_PITCH + cc) = v[u][i];
-                                }
-                            }
-                    }
-                }
-                // score segments of the queries this thread's accumulators belong to (columns 8nb+2t, 8nb+2t+1)
-                int64_t seg[NB][2];
-                bool qok[NB][2];
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int qi = 8 * nb + 2 * t + e;
-                        const uint32_t pi = (uint32_t)__shfl_sync(0xffffffffu, mykey, min(c0 + qi, np - 1));
-                        qok[nb][e] = qi < mc;
-                        seg[nb][e] = qok[nb][e] ? (int64_t)__ldg(pair_seg + pi) : 0;
-                    }
-                __syncwarp();
-                double qn[NB][2];
-                if (ANGULAR) {
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            double s = 0;
-                            const double* qq = Qw + (8 * nb + 2 * t + e) * WQ_PITCH;
-                            for (int cc = 0; cc < d; ++cc) s = fma(qq[cc], qq[cc], s);
-                            qn[nb][e] = sqrt(s);
-                        }
-                }
-                const double* bq = Qw + g * WQ_PITCH + 2 * t;
-
-                // row ids: a 32-row window per coalesced load, the next window prefetched one window ahead
-                int idwin = __ldg(bids + min(lane, blen - 1));
-                int idwin_next = __ldg(bids + min(32 + lane, blen - 1));
-                int win_base = 0;
-                auto load_block = [&](double2 (&a)[NW], int rb) {
-                    if (rb >= win_base + 32) {            // warp-uniform
-                        idwin = idwin_next;
-                        win_base += 32;
-                        idwin_next = __ldg(bids + min(win_base + 32 + lane, blen - 1));
-                    }
-                    const int id = __shfl_sync(0xffffffffu, idwin, (rb - win_base) + g);
-                    const double* xr = X + (int64_t)id * d + 2 * t;
-#pragma unroll
-                    for (int w = 0; w < NW; ++w)
-                        if (w < nw8)
-                            a[w] = (8 * w + 2 * t < d) ? __ldg(reinterpret_cast<const double2*>(xr + 8 * w)) : make_double2(0.0, 0.0);
-                };
-                auto compute_block = [&](const double2 (&a)[NW], int rb) {
-                    double acc[NB][2];
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
-                    double xn = 0.0;
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) {
-                        if (w < nw8) {
-#pragma unroll
-                            for (int nb = 0; nb < NB; ++nb) {
-                                if (nb < nbu) {
-                                    const double2 b = *reinterpret_cast<const double2*>(bq + nb * 8 * WQ_PITCH + 8 * w);
-                                    dmma884(acc[nb][0], acc[nb][1], a[w].x, b.x);
-                                    dmma884(acc[nb][0], acc[nb][1], a[w].y, b.y);
-                                }
-                            }
-                            if (ANGULAR) { xn = fma(a[w].x, a[w].x, xn); xn = fma(a[w].y, a[w].y, xn); }
-                        }
-                    }
-                    double xnr = 1.0;
-                    if (ANGULAR) {
-                        xn += __shfl_xor_sync(0xffffffffu, xn, 1);
-                        xn += __shfl_xor_sync(0xffffffffu, xn, 2);
-                        xnr = sqrt(xn);
-                    }
-                    const int row = rb + g;
-                    if (row < blen) {
-#pragma unroll
-                        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e)
-                                if (qok[nb][e]) scores[seg[nb][e] + row] = ANGULAR ? acc[nb][e] / (qn[nb][e] * xnr) : acc[nb][e];
-                    }
-                };
-
-                double2 A0[NW], A1[NW];
-                load_block(A0, 0);
-                for (int rb = 0; rb < blen; rb += 16) {
-                    const bool has1 = rb + 8 < blen;
-                    if (has1) load_block(A1, rb + 8);
-                    compute_block(A0, rb);
-                    if (rb + 16 < blen) load_block(A0, rb + 16);
-                    if (has1) compute_block(A1, rb + 8);
-                }
-            }
-            j0 += m;
+        for (int i = 0; i < 8; ++i) {
+            x[2 * i] = __hiloint2double((int)raw[i].y, (int)raw[i].x);
+            x[2 * i + 1] = __hiloint2double((int)raw[i].w, (int)raw[i].z);
         }
     }
-    if (lane == 0) { atomicAdd(&stat[0], runs); atomicAdd(&stat[1], rows_staged); }
 }
 
-template <bool ANGULAR, int NB>
-static void launch_score_warps(dpf_index* h, const double* Qd, int64_t npairs, int metric, unsigned long long* bm_stat) {
-    (void)metric;
-    static bool attr = false;
-    if (!attr) {
-        DPF_CUDA(cudaFuncSetAttribute(k_score_warps<ANGULAR, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)WarpCfg<NB>::SMEM));
-        attr = true;
+// INTQ: byte rows and byte queries (Q8, qnorm from k_quantise_queries): exact integer dot products with DP4A, the
+// same value the integer tensor pipe produces, no rounding allowance needed for the dot product.
+template <bool ANGULAR, int KIND, bool INTQ>
+__global__ void __launch_bounds__(RR_THREADS)
+k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, const double* __restrict__ Q,
+            const unsigned char* __restrict__ Q8, int q8_pitch, const double* __restrict__ qnorm8, int64_t q0, int64_t nqc,
+            int L, int NT, const uint32_t* __restrict__ pair_base, const unsigned long long* __restrict__ pair_key_unsorted,
+            const uint32_t* __restrict__ pair_len, const int32_t* __restrict__ ids_sorted,
+            const int32_t* __restrict__ qids, int self_exclude, int K, double* __restrict__ tl_keys, int* __restrict__ tl_ids,
+            int* __restrict__ tl_cnt) {
+    static_assert(!INTQ || KIND == DPF_STORE_KIND_U8, "integer path needs byte rows");
+    constexpr int RN = RawRow<KIND>::N;
+    constexpr int SZ = KIND == DPF_STORE_KIND_U8 ? 1 : (KIND == DPF_STORE_KIND_F32 ? 4 : 8);
+    constexpr int PFT = KIND == DPF_STORE_KIND_U8 ? 4 : 2;     // steps (of 4 rows) whose rows are in flight per warp
+    extern __shared__ double rsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane >> 3, l8 = lane & 7;            // 4 rows per step, 8 lanes x 16 columns per row
+    double* mykeys = rsm + (size_t)warp * K;
+    int* myids = reinterpret_cast<int*>(rsm + (size_t)RR_WARPS * K) + (size_t)warp * K;
+    // one warp per (query, sampled table): the dependent loads of a sample (pair -> bucket -> ids -> rows) overlap with
+    // those of the other warps; the per-sample lists go to global memory and k_threshold_merge combines them
+    const int64_t wid = (int64_t)blockIdx.x * RR_WARPS + warp;
+    if (wid >= nqc * NT) return;
+    const int64_t ql = wid / NT;
+    const int sample = (int)(wid % NT);
+    const int64_t q = q0 + ql;
+    const int qid = qids ? qids[q] : INT32_MIN;
+    const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
+    const int c0 = 16 * l8;
+    // a lane whose columns lie beyond the row reads the row's first bytes instead (a select on a loaded value would
+    // make the load synchronous): its query values are 0
+    const unsigned off = (unsigned)c0 * SZ < row_bytes ? (unsigned)c0 * SZ : 0u;
+    double qv[INTQ ? 1 : 16];
+    uint4 q8 = make_uint4(0, 0, 0, 0);
+    double qn = 1.0;
+    if constexpr (INTQ) {
+        q8 = __ldg(reinterpret_cast<const uint4*>(Q8 + (size_t)q * q8_pitch + c0));     // zero beyond column d
+        if (ANGULAR) qn = __ldg(qnorm8 + q);
+    } else {
+        double qq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {                // d even, Q 16-byte aligned (bucket_major_supported)
+            const double2 v = c0 + i < d ? __ldg(reinterpret_cast<const double2*>(Q + q * d + c0 + i)) : make_double2(0.0, 0.0);
+            qv[i] = v.x; qv[i + 1] = v.y;
+            qq = fma(v.x, v.x, qq); qq = fma(v.y, v.y, qq);
+        }
+        if (ANGULAR) {
+            qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+            qq += __shfl_xor_sync(0xffffffffu, qq, 2);
+            qq += __shfl_xor_sync(0xffffffffu, qq, 4);
+            qn = sqrt(qq);
+        }
     }
-    int* next_group = h->counters.p + 18;
-    DPF_CUDA(cudaMemsetAsync(next_group, 0, sizeof(int), h->stream));
-    const int64_t groups = (npairs + BM_QT - 1) / BM_QT;
-    const unsigned grid = (unsigned)std::min<int64_t>((groups + WarpCfg<NB>::WARPS - 1) / WarpCfg<NB>::WARPS, (int64_t)h->num_sms);
-    k_score_warps<ANGULAR, NB><<<grid, WarpCfg<NB>::WARPS * 32, WarpCfg<NB>::SMEM, h->stream>>>(
-        h->Xdev, h->cfg.d, Qd, h->bm_sorted, npairs, h->pair_q.p, h->pair_len.p, h->pair_seg.p, h->ids_sorted.p, h->scores.p,
-        next_group, bm_stat);
+    const double slack = 4.0 * (double)(d + 8) * 1.1102230246251565e-16;     // >= twice the bound, with room for the norms
+    // tables (among the first 32) in which the query probes something; lane t holds the first pair of table t
+    const uint32_t p_mine = lane < L ? pair_base[ql * L + lane] : 0u;
+    const uint32_t p_next = lane < L ? pair_base[ql * L + lane + 1] : 0u;
+    uint32_t nonempty = __ballot_sync(0xffffffffu, lane < L && p_next > p_mine);
+    int count = 0;
+    double kth = 0.0;                        // mykeys[K - 1] once the list is full
+    for (int i = 0; i < sample && nonempty; ++i) nonempty &= nonempty - 1;
+    if (nonempty) {                          // the sample-th table that has a pair
+        const int t = __ffs(nonempty) - 1;
+        const uint32_t p = __shfl_sync(0xffffffffu, p_mine, t);
+        const uint32_t bstart = (uint32_t)(pair_key_unsorted[p] >> 32);
+        const int len = (int)pair_len[p];
+        const int32_t* bids = ids_sorted + bstart;
+        const int nmine = (len + 3) >> 2;    // steps of 4 rows; ids two groups of PFT steps ahead, rows one group ahead
+        uint4 raw[PFT][RN];
+        int id_row[PFT], id_ahead[PFT];
+        auto load_id = [&](int k) { return __ldg(bids + min(4 * k + sub, len - 1)); };
+        auto issue = [&](uint4 (&dst)[RN], int id) {
+            const unsigned char* xr = X + (size_t)id * row_bytes + off;
+#pragma unroll
+            for (int v = 0; v < RN; ++v) {
+                // vectors past the end of the row (d < 128) re-read the lane's first vector
+                const unsigned o = off + 16u * v < row_bytes ? 16u * v : 0u;
+                dst[v] = __ldg(reinterpret_cast<const uint4*>(xr + o));
+            }
+        };
+#pragma unroll
+        for (int s0 = 0; s0 < PFT; ++s0) id_row[s0] = s0 < nmine ? load_id(s0) : 0;
+#pragma unroll
+        for (int s0 = 0; s0 < PFT; ++s0) id_ahead[s0] = PFT + s0 < nmine ? load_id(PFT + s0) : 0;
+#pragma unroll
+        for (int s0 = 0; s0 < PFT; ++s0)
+            if (s0 < nmine) issue(raw[s0], id_row[s0]);
+        for (int base = 0; base < nmine; base += PFT) {
+#pragma unroll
+            for (int s0 = 0; s0 < PFT; ++s0) {
+                const int k = base + s0;
+                if (k >= nmine) break;                           // warp-uniform
+                const int id = id_row[s0];
+                const int row = 4 * k + sub;
+                double lb;                   // lower bound of the score the scoring kernel will compute for this row
+                if constexpr (INTQ) {
+                    const uint4 x = raw[s0][0];
+                    unsigned dot = 0, xx = 0;
+                    dot = __dp4a(x.x, q8.x, dot); dot = __dp4a(x.y, q8.y, dot); dot = __dp4a(x.z, q8.z, dot); dot = __dp4a(x.w, q8.w, dot);
+                    if (ANGULAR && (unsigned)c0 < row_bytes) { xx = __dp4a(x.x, x.x, xx); xx = __dp4a(x.y, x.y, xx); xx = __dp4a(x.z, x.z, xx); xx = __dp4a(x.w, x.w, xx); }
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                        if (ANGULAR) xx += __shfl_xor_sync(0xffffffffu, xx, o);
+                    }
+                    lb = (double)dot;
+                    if (ANGULAR) { lb = lb / (qn * sqrt((double)xx)); lb -= 8.0 * 1.1102230246251565e-16 * fabs(lb); }
+                } else {
+                    double x[16];
+                    raw_to_cols16<KIND>(raw[s0], x);
+                    double dot = 0.0, ab = 0.0, xx = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        dot = fma(x[c], qv[c], dot);
+                        ab = fma(fabs(x[c]), fabs(qv[c]), ab);
+                        if (ANGULAR && c0 + c < d) xx = fma(x[c], x[c], xx);
+                    }
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                        ab += __shfl_xor_sync(0xffffffffu, ab, o);
+                        if (ANGULAR) xx += __shfl_xor_sync(0xffffffffu, xx, o);
+                    }
+                    if (ANGULAR) {
+                        const double den = qn * sqrt(xx);
+                        lb = dot / den - slack * (ab / den);
+                    } else {
+                        lb = dot - slack * ab;
+                    }
+                }
+                // next rows / ids of this ring slot
+                if (k + PFT < nmine) {
+                    id_row[s0] = id_ahead[s0];
+                    issue(raw[s0], id_row[s0]);
+                    if (k + 2 * PFT < nmine) id_ahead[s0] = load_id(k + 2 * PFT);
+                }
+                // rows that can enter the list (rare once it is full): one after the other, all lanes take part
+                bool ok = l8 == 0 && row < len && lb == lb && !(excl && id == qid);
+                if (ok && count == K) ok = lb >= kth;
+                uint32_t todo = __ballot_sync(0xffffffffu, ok);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const double lb_s = __shfl_sync(0xffffffffu, lb, src);
+                    const int id_s = __shfl_sync(0xffffffffu, id, src);
+                    if (count == K && !better(lb_s, id_s, mykeys[K - 1], myids[K - 1])) continue;
+                    bool dup = false;        // the same row reached through another table: keep it once
+                    for (int b2 = 0; b2 < count; b2 += 32) dup |= __any_sync(0xffffffffu, b2 + lane < count && myids[b2 + lane] == id_s);
+                    if (!dup) warp_insert(mykeys, myids, count, K, lb_s, id_s, lane);
+                    if (count == K) kth = mykeys[K - 1];
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int r = lane; r < count; r += 32) {
+        tl_keys[wid * K + r] = mykeys[r];
+        tl_ids[wid * K + r] = myids[r];
+    }
+    if (lane == 0) tl_cnt[wid] = count;
+}
+
+// one warp per query: tau = k-th best distinct row over its NT sample lists (a row sampled through two tables has the
+// same bound in both lists, so duplicates are adjacent in the merged order); also resets the query's survivor list
+__global__ void __launch_bounds__(RR_THREADS)
+k_threshold_merge(int64_t q0, int64_t nqc, int L, int NT, int K, const double* __restrict__ tl_keys, const int* __restrict__ tl_ids,
+                  const int* __restrict__ tl_cnt, const uint32_t* __restrict__ pair_base, const uint32_t* __restrict__ pair_seg,
+                  double* __restrict__ tau, uint32_t* __restrict__ s_cnt, uint32_t* __restrict__ s_base) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
+    if (ql >= nqc) return;
+    const int64_t q = q0 + ql;
+    const double* lkeys = tl_keys + (ql * NT + lane) * K;
+    const int* lids = tl_ids + (ql * NT + lane) * K;
+    const int mycount = lane < NT ? tl_cnt[ql * NT + lane] : 0;
+    int head = 0, last = -1, found = 0;
+    double kth = 0.0;
+    while (found < K) {
+        double bk = 0.0;
+        int bi = 0x7fffffff, bl = -1;
+        if (head < mycount) { bk = lkeys[head]; bi = lids[head]; bl = lane; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+        }
+        if (bl < 0) break;                   // lists exhausted
+        if (lane == bl) head++;
+        if (bi != last) { found++; kth = bk; last = bi; }
+    }
+    if (lane == 0) {
+        tau[q] = found == K ? kth : -__longlong_as_double(0x7ff0000000000000LL);
+        const uint32_t pbeg = pair_base[ql * L], pend = pair_base[(ql + 1) * L];
+        s_cnt[q] = 0u;
+        s_base[q] = pbeg < pend ? pair_seg[pbeg] : 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_select_survivors — one warp per query: top k of its survivor list, larger score first, ties by smaller id; an id
+// reached through several tables appears several times with bit-identical scores and is kept once.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RR_THREADS)
+k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
+                   int32_t* __restrict__ ids_out, double* __restrict__ score_out, unsigned long long* __restrict__ stat) {
+    extern __shared__ double rsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* mykeys = rsm + (size_t)warp * K;
+    int* myids = reinterpret_cast<int*>(rsm + (size_t)RR_WARPS * K) + (size_t)warp * K;
+    const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + warp;
+    if (ql >= nqc) return;
+    const int64_t q = q0 + ql;
+    const uint32_t n = flt.cnt[q];
+    if (lane == 0) atomicAdd(&stat[2], (unsigned long long)n);
+    const double* sc = flt.s_score + flt.base[q];
+    const int32_t* si = flt.s_id + flt.base[q];
+    const int qid = qids ? qids[q] : INT32_MIN;
+    const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
+    int count = 0;
+    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const double key = j < n ? sc[j] : 0.0;
+        const int id = j < n ? si[j] : -1;
+        bool cand = j < n && !(excl && id == qid);
+        if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
+        uint32_t todo = __ballot_sync(0xffffffffu, cand);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double kk = __shfl_sync(0xffffffffu, key, src);
+            const int ii = __shfl_sync(0xffffffffu, id, src);
+            bool dup = false;
+            for (int base = 0; base < count; base += 32) dup |= __any_sync(0xffffffffu, base + lane < count && myids[base + lane] == ii);
+            if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
+        }
+    }
+    for (int r = lane; r < K; r += 32) {
+        ids_out[q * K + r] = r < count ? myids[r] : -1;
+        score_out[q * K + r] = r < count ? mykeys[r] : __longlong_as_double(0x7ff8000000000000LL);
+    }
 }
 
 // per-query selection from its score segments: one CTA per query, a warp walks whole pairs
@@ -769,10 +850,9 @@ __global__ void k_topk_select_empty(int64_t q0, int64_t nqc, int K, int32_t* __r
 }
 
 
-// runs of the sorted pair list -> h->units (device), number of units in h->bm_counts[1]
 // runs of the sorted pair list -> unit records in h->bm_units (device); the number of units is also left in
 // h->bm_counts[1]
-static void build_units(dpf_index* h, int64_t npairs) {
+static void build_units(dpf_index* h, int64_t npairs, bool filtered) {
     cudaStream_t st = h->stream;
     const unsigned gp = (unsigned)((npairs + 255) / 256);
     h->bm_flag.reserve(npairs + 1);
@@ -791,8 +871,26 @@ static void build_units(dpf_index* h, int64_t npairs) {
     DPF_CUDA(cudaStreamSynchronize(st));
     h->bm_units.reserve((size_t)std::max<uint32_t>(nunits, 1) * sizeof(UnitRec));
     k_emit_units<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_ucnt.p, h->pair_q.p, h->pair_len.p,
-                                     h->pair_seg.p, h->ids_sorted.p, reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
+                                     h->pair_seg.p, filtered ? h->bm_tau.p : nullptr, h->ids_sorted.p,
+                                     reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
+}
+
+// the compact store's rows when the build found a narrower lossless type (store.cu), else the FP64 rows
+static void store_rows(const dpf_index* h, int& kind, const unsigned char*& rows, unsigned& row_bytes) {
+    kind = h->Xc_kind;
+    rows = kind == DPF_STORE_KIND_F64 ? reinterpret_cast<const unsigned char*>(h->Xdev) : h->Xc.p;
+    row_bytes = kind == DPF_STORE_KIND_F64 ? (unsigned)h->cfg.d * 8u : (unsigned)h->Xc_row_bytes;
+}
+
+template <class F>
+static void dispatch_kind(int kind, bool ang, F&& f) {
+    auto k = [&](auto kc) {
+        if (ang) f(std::true_type{}, kc); else f(std::false_type{}, kc);
+    };
+    if (kind == DPF_STORE_KIND_U8) k(std::integral_constant<int, DPF_STORE_KIND_U8>{});
+    else if (kind == DPF_STORE_KIND_F32) k(std::integral_constant<int, DPF_STORE_KIND_F32>{});
+    else k(std::integral_constant<int, DPF_STORE_KIND_F64>{});
 }
 
 void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1,
@@ -804,12 +902,21 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     if (nqc <= 0) return;
     DPF_REQUIRE(h->h_table_base[L] < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: more than 2^32 forest entries");
     DPF_REQUIRE(entries_ub < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: chunk too large");
-    const char* ev = getenv("DPF_BM_KERNEL");
-    const bool use_stream = !(ev && ev[0] == 'w') && (reinterpret_cast<uintptr_t>(Qd) & 15) == 0;   // =warps: register-gather kernel
+    const bool ang = metric == DPF_METRIC_ANGULAR;
+    // Two pipelines.  Byte store: k_threshold -> k_score_u8* (filtered output: only scores that can still be among a
+    // query's best k are kept) -> k_select_survivors.  FP64 / FP32 store: k_score_stream (dense output, one score per
+    // bucket entry) -> k_select_pairs; there the threshold pass would itself read ~1 KB rows and an append from inside
+    // the TMA pipeline is a demand access that queues behind the bulk copies, so filtering does not pay.
+    const bool use_u8 = score_u8_usable(h);
+    int kind;
+    const unsigned char* rows;
+    unsigned row_bytes;
+    store_rows(h, kind, rows, row_bytes);
     // pair offsets of this chunk = exclusive scan of the per-(query, table) bucket counts from the probe pass
     const int64_t nslots = nqc * L + 1;
     h->pair_base.reserve(nslots);
-    const bool use_u8 = use_stream && score_u8_usable(h);      // byte store: register-gather kernel (rerank_u8.cu)
+    const size_t list_smem = (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
+    const unsigned qgrid = (unsigned)((nqc + RR_WARPS - 1) / RR_WARPS);
     {
         StageTimer tm(h, DPF_T_EXPAND);
         if (use_u8 && q0 == 0) prepare_queries_u8(h, Qd, qk.nq);
@@ -822,9 +929,6 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         const int64_t npairs = npairs32;
         if (npairs == 0) {
             // nothing probed: all rows padded
-            h->ucnt.reserve(nqc + 1);
-            h->unit_off.reserve(nqc + 2);
-            DPF_CUDA(cudaMemsetAsync(h->unit_off.p, 0, (nqc + 2) * sizeof(int64_t), st));
             k_topk_select_empty<<<(unsigned)((nqc * topk + 255) / 256), 256, 0, st>>>(q0, nqc, topk, ids_out, score_out); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             return;
@@ -841,6 +945,32 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         DPF_CUDA(cudaGetLastError());
         k_copy_u32<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pair_len.p, h->pair_seg.p, npairs); DPF_LAUNCHED();
         exclusive_scan_u32(h, h->pair_seg.p, npairs);
+        if (use_u8) {
+            // thresholds (and the survivor lists' bases and counters) before the units are cut: the records carry tau
+            h->surv_id.reserve((size_t)std::max<int64_t>(entries_ub, 1));
+            h->bm_tau.reserve((size_t)qk.nq);
+            h->bm_scnt.reserve((size_t)qk.nq);
+            h->bm_sbase.reserve((size_t)qk.nq);
+            const char* ntv = getenv("DPF_TAU_TABLES");
+            const int NT = std::min(32, std::max(1, ntv ? atoi(ntv) : 6));   // sampled tables per query (one warp each)
+            const bool intq = h->Q8_valid;
+            h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
+            h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
+            h->bm_tl_cnt.reserve((size_t)nqc * NT);
+            auto go = [&](auto kern) {
+                kern<<<(unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS), RR_THREADS, list_smem, st>>>(
+                    rows, row_bytes, d, Qd, h->Q8.p, u8_query_pitch(), h->qnorm8.p, q0, nqc, L, NT, h->pair_base.p, h->pair_key.p,
+                    h->pair_len.p, h->ids_sorted.p, qk.qids, h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p,
+                    h->bm_tl_cnt.p);
+            };
+            if (ang) { if (intq) go(k_threshold<true, DPF_STORE_KIND_U8, true>); else go(k_threshold<true, DPF_STORE_KIND_U8, false>); }
+            else { if (intq) go(k_threshold<false, DPF_STORE_KIND_U8, true>); else go(k_threshold<false, DPF_STORE_KIND_U8, false>); }
+            DPF_LAUNCHED();
+            k_threshold_merge<<<qgrid, RR_THREADS, 0, st>>>(q0, nqc, L, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p,
+                                                            h->pair_base.p, h->pair_seg.p, h->bm_tau.p, h->bm_scnt.p, h->bm_sbase.p);
+            DPF_LAUNCHED();
+            DPF_CUDA(cudaGetLastError());
+        }
         // sort a copy of the keys by bucket start (bits 32..); the unsorted array stays for the selection pass
         DPF_CUDA(cudaMemcpyAsync(h->pair_key_alt.p, h->pair_key.p, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         int ebits = 1;
@@ -850,46 +980,37 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         radix_sort_keys_u64(h, &a, &b, npairs, 32, 32 + ebits);
         h->bm_sorted = a;
         h->bm_npairs = npairs;
-        if (use_stream) build_units(h, npairs);
+        build_units(h, npairs, use_u8);
     }
+    unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(h->counters.p + 26);   // cleared by probe_count_all
+    const Filter flt{h->bm_scnt.p, h->bm_sbase.p, h->scores.p, h->surv_id.p};
     {
         StageTimer tm(h, DPF_T_RERANK);
-        const int64_t npairs = h->bm_npairs;
-        unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(h->counters.p + 26);   // cleared by probe_count_all
-        h->stats[DPF_STAT_BM_PAIRS] += npairs;
-        const bool ang = metric == DPF_METRIC_ANGULAR;
+        h->stats[DPF_STAT_BM_PAIRS] += h->bm_npairs;
+        const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
         if (use_u8) {
-            launch_score_u8(h, Qd, h->bm_units.p, h->bm_counts.p + 1, ang, bm_stat);
-        } else if (use_stream) {
-            const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
-            // rows come from the compact store when the build found a narrower lossless type (store.cu)
-            const int kind = h->Xc_kind;
-            const unsigned char* rows = kind == DPF_STORE_KIND_F64 ? reinterpret_cast<const unsigned char*>(h->Xdev) : h->Xc.p;
-            const unsigned row_bytes = kind == DPF_STORE_KIND_F64 ? (unsigned)d * 8u : (unsigned)h->Xc_row_bytes;
-            auto launch = [&](auto kern) {
+            launch_score_u8(h, Qd, units, h->bm_counts.p + 1, ang, flt, bm_stat);
+        } else {
+            dispatch_kind(kind, ang, [&](auto a, auto kc) {
+                auto kern = k_score_stream<decltype(a)::value, decltype(kc)::value>;
                 DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
                 kern<<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(rows, row_bytes, d, Qd, units, h->bm_counts.p + 1, h->ids_sorted.p,
                                                                  h->scores.p, bm_stat);
-            };
-            if (kind == DPF_STORE_KIND_U8) { if (ang) launch(k_score_stream<true, DPF_STORE_KIND_U8>); else launch(k_score_stream<false, DPF_STORE_KIND_U8>); }
-            else if (kind == DPF_STORE_KIND_F32) { if (ang) launch(k_score_stream<true, DPF_STORE_KIND_F32>); else launch(k_score_stream<false, DPF_STORE_KIND_F32>); }
-            else { if (ang) launch(k_score_stream<true, DPF_STORE_KIND_F64>); else launch(k_score_stream<false, DPF_STORE_KIND_F64>); }
-        } else {
-            const char* nbv = getenv("DPF_BM_NB");
-            const int nb = nbv ? atoi(nbv) : 2;
-            if (nb <= 1) { if (ang) launch_score_warps<true, 1>(h, Qd, npairs, metric, bm_stat); else launch_score_warps<false, 1>(h, Qd, npairs, metric, bm_stat); }
-            else if (nb == 2) { if (ang) launch_score_warps<true, 2>(h, Qd, npairs, metric, bm_stat); else launch_score_warps<false, 2>(h, Qd, npairs, metric, bm_stat); }
-            else { if (ang) launch_score_warps<true, 4>(h, Qd, npairs, metric, bm_stat); else launch_score_warps<false, 4>(h, Qd, npairs, metric, bm_stat); }
+            });
         }
         DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
     }
     {
         StageTimer tm(h, DPF_T_SELECT);
-        const size_t smem = (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
-        k_select_pairs<<<(unsigned)nqc, RR_THREADS, smem, st>>>(q0, L, h->pair_base.p, h->pair_key.p, h->pair_len.p, h->pair_seg.p,
-                                                                 h->ids_sorted.p, h->scores.p, qk.qids,
-                                                                 h->cfg.self_exclude_small_ids, topk, ids_out, score_out); DPF_LAUNCHED();
+        if (use_u8)
+            k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, ids_out,
+                                                                     score_out, bm_stat);
+        else
+            k_select_pairs<<<(unsigned)nqc, RR_THREADS, list_smem, st>>>(q0, L, h->pair_base.p, h->pair_key.p, h->pair_len.p,
+                                                                         h->pair_seg.p, h->ids_sorted.p, h->scores.p, qk.qids,
+                                                                         h->cfg.self_exclude_small_ids, topk, ids_out, score_out);
+        DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
     }
 }

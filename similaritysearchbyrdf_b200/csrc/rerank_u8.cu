@@ -23,6 +23,8 @@
 namespace dpf {
 
 constexpr int U8_WARPS = 8;
+constexpr int U8_INT_CTAS = 3;          // CTAs per SM of the integer variant (<= 85 registers): latency is hidden by occupancy
+constexpr int U8_QPITCH = 128;          // row pitch of the byte copy of the queries (zero padded)
 
 // ---------------------------------------------------------------------------------------------------------
 // queries -> bytes (when they are bytes)
@@ -63,14 +65,6 @@ __device__ __forceinline__ void imma_u8(int (&c)[4], unsigned a0, unsigned a1, u
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int I>
-__device__ __forceinline__ unsigned word_of(const uint4& v) {
-    if constexpr (I == 0) return v.x;
-    else if constexpr (I == 1) return v.y;
-    else if constexpr (I == 2) return v.z;
-    else return v.w;
-}
-
 // byte b of w as a double: 2^52 + v has mantissa v; minus 2^52 is exact
 template <int B>
 __device__ __forceinline__ double byte_to_double(unsigned w) {
@@ -80,22 +74,24 @@ __device__ __forceinline__ double byte_to_double(unsigned w) {
 __device__ __forceinline__ uint4 ldg_u4(const unsigned char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_score_u8
+// k_score_u8d — byte rows x FP64 queries on the FP64 tensor pipe
 // ---------------------------------------------------------------------------------------------------------
-template <bool ANGULAR, bool INTQ>
+template <bool ANGULAR>
 __global__ void __launch_bounds__(U8_WARPS * 32, 1)
-k_score_u8(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: multiple of 16, <= 128 */, int d,
-           const double* __restrict__ Q, const unsigned char* __restrict__ Q8, const double* __restrict__ qnorm,
-           const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted,
-           double* __restrict__ scores, unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
-    constexpr int TR = INTQ ? 16 : 8;            // rows per tile (IMMA M = 16, DMMA M = 8)
-    constexpr int RPT = TR / 8;                  // rows per thread per tile
+k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: multiple of 16, <= 128 */, int d,
+            const double* __restrict__ Q, const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p,
+            const int32_t* __restrict__ ids_sorted, Filter flt, unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
+    constexpr int TR = 8;                        // rows per tile = DMMA M
     constexpr int TPW = 32 / TR;                 // tiles per id window
-    constexpr int PF = INTQ ? 3 : 4;             // tiles in flight per warp
+    constexpr int PF = 3;                        // tiles in flight per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;   // this thread's chunks exist
     const bool two_chunks = pitch > 64;                              // warp-uniform
+    // every row / query load below is unconditional and its address clamped into valid memory: a select on a loaded
+    // value makes the compiler wait for the load where it is issued (measured: 40 % of the kernel), whereas a garbage
+    // operand is harmless as long as the other operand of the product is 0
+    const unsigned off0 = has0 ? 16u * t : 0u, off1 = has1 ? 64u + 16u * t : 0u;
     const int64_t nunits = *nunits_p;
     const int64_t W = (int64_t)gridDim.x * U8_WARPS;
     const int64_t gw = (int64_t)blockIdx.x * U8_WARPS + warp;
@@ -103,15 +99,21 @@ k_score_u8(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: mu
     if (nmine == 0) return;
     unsigned long long rows_staged = 0;
 
-    // record of the next unit, loaded one unit ahead (lane j < 16 keeps query j / segment j, every lane one first-window id)
-    uint32_t n_bstart, n_len, n_m, n_seg;
+    // record of the next unit, loaded one unit ahead: lane j < 16 keeps query j, every lane one first-window id and
+    // the thresholds of the four queries its accumulators belong to
+    uint32_t n_bstart, n_len, n_m;
     int n_q, n_id;
+    double n_tau[2][2];
     auto fetch_rec = [&](int64_t k) {
         const UnitRec* r = units + (gw + k * W);
         n_bstart = __ldg(&r->bstart); n_len = __ldg(&r->len); n_m = __ldg(&r->m);
         n_q = __ldg(&r->q[lane & (SS_UQ - 1)]);
-        n_seg = __ldg(&r->seg[lane & (SS_UQ - 1)]);
         n_id = __ldg(&r->ids0[lane]);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(&r->tau[8 * nb + 2 * t]));
+            n_tau[nb][0] = v.x; n_tau[nb][1] = v.y;
+        }
     };
     fetch_rec(0);
 
@@ -119,49 +121,41 @@ k_score_u8(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: mu
         const uint32_t bstart = n_bstart;
         const int len = (int)n_len, m = (int)n_m;
         const int my_q = n_q, id_first = n_id;
-        const uint32_t my_seg = n_seg;
+        const double c_tau[2][2] = {{n_tau[0][0], n_tau[0][1]}, {n_tau[1][0], n_tau[1][1]}};
         if (k + 1 < nmine) fetch_rec(k + 1);
         rows_staged += (unsigned)len;
         const int nb_used = (m + 7) >> 3;
 
-        // ---- query operand --------------------------------------------------------------------------------------
-        uint4 bq[2][2];                      // INTQ: this thread's two chunks of queries g and 8 + g
-        double B[INTQ ? 1 : 2][INTQ ? 1 : 32];   // FP64: k-step c * 16 + e <-> column 64c + 16t + e
+        // ---- query operand: k-step c * 16 + e <-> column 64c + 16t + e -----------------------------------------
+        double B[2][32];
         double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
-        uint32_t c_seg[2][2];
+        int c_q[2][2];
         bool c_ok[2][2];
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
-            const int qi = __shfl_sync(0xffffffffu, my_q, 8 * nb + g);
-            const bool valid = 8 * nb + g < m;
-            if constexpr (INTQ) {
-                const unsigned char* qp = Q8 + (size_t)qi * pitch + 16 * t;
-                bq[nb][0] = (valid && has0) ? ldg_u4(qp) : make_uint4(0, 0, 0, 0);
-                bq[nb][1] = (valid && has1) ? ldg_u4(qp + 64) : make_uint4(0, 0, 0, 0);
-            } else {
-                const double* qp = Q + (int64_t)qi * d;
+            const int qi = __shfl_sync(0xffffffffu, my_q, 8 * nb + g);      // slots >= m repeat the last query
+            const double* qp = Q + (int64_t)qi * d;
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const int col = 64 * c + 16 * t + e;          // even; d is even
-                        double2 v = make_double2(0.0, 0.0);
-                        if (valid && col < d) v = __ldg(reinterpret_cast<const double2*>(qp + col));
-                        B[nb][16 * c + e] = v.x;
-                        B[nb][16 * c + e + 1] = v.y;
-                    }
-            }
+                for (int e = 0; e < 16; e += 2) {
+                    const int col = 64 * c + 16 * t + e;          // even; d is even
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(qp + min(col, d - 2)));
+                    B[nb][16 * c + e] = v.x;
+                    B[nb][16 * c + e + 1] = v.y;
+                }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int j = 8 * nb + 2 * t + e;
-                c_seg[nb][e] = __shfl_sync(0xffffffffu, my_seg, j);
+                c_q[nb][e] = __shfl_sync(0xffffffffu, my_q, j);
                 c_ok[nb][e] = j < m;
-                if (ANGULAR && INTQ) {
-                    const int qj = __shfl_sync(0xffffffffu, my_q, j);
-                    c_qn[nb][e] = c_ok[nb][e] ? __ldg(qnorm + qj) : 1.0;
-                }
             }
-            if constexpr (ANGULAR && !INTQ) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (64 * c + 16 * t + e >= d) B[nb][16 * c + e] = 0.0;      // columns >= d: the row operand is garbage there
+            if (ANGULAR) {
                 double sq = 0.0;             // ||query 8nb + g||^2: this thread's columns, then the 4 threads of the group
 #pragma unroll
                 for (int w = 0; w < 32; ++w) sq = fma(B[nb][w], B[nb][w], sq);
@@ -173,120 +167,79 @@ k_score_u8(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: mu
             }
         }
 
-        // ---- rows: ids by 32-row windows (one window ahead), tiles of TR rows, PF tiles in flight ---------------------
+        // ---- rows: ids by 32-row windows (one window ahead), tiles of 8 rows, PF tiles in flight -------------------
         const int ntiles = (len + TR - 1) / TR;
         const int32_t* bids = ids_sorted + bstart;
         int win_lo = 0;                      // idA = ids of window win_lo, idB = window win_lo + 1
         int idA = id_first;
         int idB = 32 < len ? __ldg(bids + min(32 + lane, len - 1)) : 0;
-        uint4 a[PF][RPT][2];
-        auto load_tile = [&](uint4 (&dst)[RPT][2], int tile) {
+        uint4 a[PF][2];
+        auto load_tile = [&](uint4 (&dst)[2], int tile) {
             const int wi = tile / TPW;
             if (wi > win_lo) {               // warp-uniform; tiles are loaded in increasing order
                 idA = idB;
                 win_lo = wi;
                 idB = 32 * (wi + 1) < len ? __ldg(bids + min(32 * (wi + 1) + lane, len - 1)) : 0;
             }
-#pragma unroll
-            for (int r = 0; r < RPT; ++r) {
-                const int row = min(tile * TR + 8 * r + g, len - 1);
-                const int id = __shfl_sync(0xffffffffu, idA, row - 32 * wi);
-                const unsigned char* xp = X8 + (size_t)id * pitch + 16 * t;
-                dst[r][0] = has0 ? ldg_u4(xp) : make_uint4(0, 0, 0, 0);
-                dst[r][1] = has1 ? ldg_u4(xp + 64) : make_uint4(0, 0, 0, 0);
-            }
+            const int row = min(tile * TR + g, len - 1);
+            const int id = __shfl_sync(0xffffffffu, idA, row - 32 * wi);
+            const unsigned char* xp = X8 + (size_t)id * pitch;
+            dst[0] = ldg_u4(xp + off0);      // a chunk this thread does not have reads chunk 0 instead: its query
+            dst[1] = ldg_u4(xp + off1);      // operand is 0 there
         };
-        auto store_scores = [&](int row, int nb, int e, double dot, double xnr) {
-            if (row < len && nb < nb_used && c_ok[nb][e])
-                scores[(size_t)c_seg[nb][e] + row] = ANGULAR ? dot / (c_qn[nb][e] * xnr) : dot;
-        };
-        auto compute_tile = [&](const uint4 (&src)[RPT][2], int tile) {
-            if constexpr (INTQ) {
-                int acc[2][4];
+        auto compute_tile = [&](const uint4 (&src)[2], int tile) {
+            double acc[2][2][2];            // [n-block][even / odd k-step chain][column]
 #pragma unroll
-                for (int nb = 0; nb < 2; ++nb)
+            for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[nb][i] = 0;
-                auto steps = [&](auto chunk) {
-                    constexpr int C = decltype(chunk)::value;
-                    imma_u8(acc[0], src[0][C].x, src[1][C].x, src[0][C].y, src[1][C].y, bq[0][C].x, bq[0][C].y);
-                    imma_u8(acc[0], src[0][C].z, src[1][C].z, src[0][C].w, src[1][C].w, bq[0][C].z, bq[0][C].w);
-                    if (nb_used == 2) {
-                        imma_u8(acc[1], src[0][C].x, src[1][C].x, src[0][C].y, src[1][C].y, bq[1][C].x, bq[1][C].y);
-                        imma_u8(acc[1], src[0][C].z, src[1][C].z, src[0][C].w, src[1][C].w, bq[1][C].z, bq[1][C].w);
-                    }
+                for (int c = 0; c < 2; ++c) acc[nb][c][0] = acc[nb][c][1] = 0.0;
+            double xn = 0.0;
+            auto steps = [&](auto chunk, auto two_blocks) {
+                constexpr int C = decltype(chunk)::value;
+                auto word = [&](auto wi, unsigned w) {
+                    constexpr int WI = decltype(wi)::value;
+                    const double a0 = byte_to_double<0>(w), a1 = byte_to_double<1>(w);
+                    const double a2 = byte_to_double<2>(w), a3 = byte_to_double<3>(w);
+                    constexpr int S = 16 * C + 4 * WI;
+                    dmma884(acc[0][0][0], acc[0][0][1], a0, B[0][S]);
+                    if (decltype(two_blocks)::value) dmma884(acc[1][0][0], acc[1][0][1], a0, B[1][S]);
+                    dmma884(acc[0][1][0], acc[0][1][1], a1, B[0][S + 1]);
+                    if (decltype(two_blocks)::value) dmma884(acc[1][1][0], acc[1][1][1], a1, B[1][S + 1]);
+                    dmma884(acc[0][0][0], acc[0][0][1], a2, B[0][S + 2]);
+                    if (decltype(two_blocks)::value) dmma884(acc[1][0][0], acc[1][0][1], a2, B[1][S + 2]);
+                    dmma884(acc[0][1][0], acc[0][1][1], a3, B[0][S + 3]);
+                    if (decltype(two_blocks)::value) dmma884(acc[1][1][0], acc[1][1][1], a3, B[1][S + 3]);
+                    if (ANGULAR && (C == 0 ? has0 : has1)) { xn = fma(a0, a0, xn); xn = fma(a1, a1, xn); xn = fma(a2, a2, xn); xn = fma(a3, a3, xn); }
                 };
-                steps(std::integral_constant<int, 0>{});
-                if (two_chunks) steps(std::integral_constant<int, 1>{});
-                double xnr[2] = {1.0, 1.0};
-                if (ANGULAR) {
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        unsigned s = 0;
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            s = __dp4a(src[r][c].x, src[r][c].x, s); s = __dp4a(src[r][c].y, src[r][c].y, s);
-                            s = __dp4a(src[r][c].z, src[r][c].z, s); s = __dp4a(src[r][c].w, src[r][c].w, s);
-                        }
-                        s += __shfl_xor_sync(0xffffffffu, s, 1);
-                        s += __shfl_xor_sync(0xffffffffu, s, 2);
-                        xnr[r] = sqrt((double)s);
-                    }
-                }
-                // thread (g, t): c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries)
-#pragma unroll
-                for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-                    for (int r = 0; r < 2; ++r)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) store_scores(tile * TR + 8 * r + g, nb, e, (double)acc[nb][2 * r + e], xnr[r]);
+                word(std::integral_constant<int, 0>{}, src[C].x);
+                word(std::integral_constant<int, 1>{}, src[C].y);
+                word(std::integral_constant<int, 2>{}, src[C].z);
+                word(std::integral_constant<int, 3>{}, src[C].w);
+            };
+            if (nb_used == 2) {
+                steps(std::integral_constant<int, 0>{}, std::true_type{});
+                if (two_chunks) steps(std::integral_constant<int, 1>{}, std::true_type{});
             } else {
-                double acc[2][2][2];            // [n-block][even / odd k-step chain][column]
-#pragma unroll
-                for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) acc[nb][c][0] = acc[nb][c][1] = 0.0;
-                double xn = 0.0;
-                auto steps = [&](auto chunk, auto two_blocks) {
-                    constexpr int C = decltype(chunk)::value;
-                    auto word = [&](auto wi, unsigned w) {
-                        constexpr int WI = decltype(wi)::value;
-                        const double a0 = byte_to_double<0>(w), a1 = byte_to_double<1>(w);
-                        const double a2 = byte_to_double<2>(w), a3 = byte_to_double<3>(w);
-                        constexpr int S = 16 * C + 4 * WI;
-                        dmma884(acc[0][0][0], acc[0][0][1], a0, B[0][S]);
-                        if (decltype(two_blocks)::value) dmma884(acc[1][0][0], acc[1][0][1], a0, B[1][S]);
-                        dmma884(acc[0][1][0], acc[0][1][1], a1, B[0][S + 1]);
-                        if (decltype(two_blocks)::value) dmma884(acc[1][1][0], acc[1][1][1], a1, B[1][S + 1]);
-                        dmma884(acc[0][0][0], acc[0][0][1], a2, B[0][S + 2]);
-                        if (decltype(two_blocks)::value) dmma884(acc[1][0][0], acc[1][0][1], a2, B[1][S + 2]);
-                        dmma884(acc[0][1][0], acc[0][1][1], a3, B[0][S + 3]);
-                        if (decltype(two_blocks)::value) dmma884(acc[1][1][0], acc[1][1][1], a3, B[1][S + 3]);
-                        if (ANGULAR) { xn = fma(a0, a0, xn); xn = fma(a1, a1, xn); xn = fma(a2, a2, xn); xn = fma(a3, a3, xn); }
-                    };
-                    word(std::integral_constant<int, 0>{}, src[0][C].x);
-                    word(std::integral_constant<int, 1>{}, src[0][C].y);
-                    word(std::integral_constant<int, 2>{}, src[0][C].z);
-                    word(std::integral_constant<int, 3>{}, src[0][C].w);
-                };
-                if (nb_used == 2) {
-                    steps(std::integral_constant<int, 0>{}, std::true_type{});
-                    if (two_chunks) steps(std::integral_constant<int, 1>{}, std::true_type{});
-                } else {
-                    steps(std::integral_constant<int, 0>{}, std::false_type{});
-                    if (two_chunks) steps(std::integral_constant<int, 1>{}, std::false_type{});
-                }
-                double xnr = 1.0;
-                if (ANGULAR) {
-                    xn += __shfl_xor_sync(0xffffffffu, xn, 1);
-                    xn += __shfl_xor_sync(0xffffffffu, xn, 2);
-                    xnr = sqrt(xn);
-                }
-#pragma unroll
-                for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) store_scores(tile * TR + g, nb, e, acc[nb][0][e] + acc[nb][1][e], xnr);
+                steps(std::integral_constant<int, 0>{}, std::false_type{});
+                if (two_chunks) steps(std::integral_constant<int, 1>{}, std::false_type{});
             }
+            double xnr = 1.0;
+            if (ANGULAR) {
+                xn += __shfl_xor_sync(0xffffffffu, xn, 1);
+                xn += __shfl_xor_sync(0xffffffffu, xn, 2);
+                xnr = sqrt(xn);
+            }
+            // thread (g, t) holds (row tile * 8 + g, queries 8nb + 2t, 8nb + 2t + 1)
+            const int row = tile * TR + g;
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double v = acc[nb][0][e] + acc[nb][1][e];
+                    if (ANGULAR) v = v / (c_qn[nb][e] * xnr);
+                    if (row < len && nb < nb_used && c_ok[nb][e] && v >= c_tau[nb][e])
+                        keep_survivor(flt, c_q[nb][e], v, __ldg(ids_sorted + bstart + row));
+                }
         };
 
 #pragma unroll
@@ -307,11 +260,135 @@ k_score_u8(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: mu
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k_score_u8i — byte rows x byte queries on the integer tensor pipe.  The arithmetic is trivial and the loop is a
+// chain of dependent loads (record -> ids -> rows), so this kernel is kept lean (<= 85 registers, 24 warps per SM)
+// and hides the latency with occupancy instead of a deep per-warp pipeline.  IMMA.16x8x32: 16 rows per tile, thread
+// (g, t) loads its two chunks of rows g and 8 + g and holds (rows g, 8 + g) x (queries 2t, 2t + 1) per n-block.
+// ---------------------------------------------------------------------------------------------------------
+template <bool ANGULAR>
+__global__ void __launch_bounds__(U8_WARPS * 32, ANGULAR ? U8_INT_CTAS - 1 : U8_INT_CTAS)
+k_score_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
+            const double* __restrict__ qnorm, const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p,
+            const int32_t* __restrict__ ids_sorted, Filter flt, unsigned long long* __restrict__ stat) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;
+    const bool two_chunks = pitch > 64;
+    const unsigned off0 = has0 ? 16u * t : 0u, off1 = has1 ? 64u + 16u * t : 0u;   // clamped, see k_score_u8d
+    const uint32_t nunits = *nunits_p;
+    const uint32_t W = gridDim.x * U8_WARPS;
+    unsigned rows_staged = 0, nmine = 0;
+    for (uint32_t u = blockIdx.x * U8_WARPS + warp; u < nunits; u += W) {
+        const UnitRec* r = units + u;
+        const uint32_t bstart = __ldg(&r->bstart);
+        const int len = (int)__ldg(&r->len), m = (int)__ldg(&r->m);
+        const int my_q = __ldg(&r->q[lane & (SS_UQ - 1)]);
+        int idA = __ldg(&r->ids0[lane]);
+        rows_staged += (unsigned)len;
+        nmine++;
+        const bool two_blocks = m > 8;
+        // queries g and 8 + g (slots >= m repeat the last query: harmless, their scores are masked)
+        uint4 bq[2][2];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const unsigned char* qp = Q8 + (size_t)__shfl_sync(0xffffffffu, my_q, 8 * nb + g) * U8_QPITCH + 16 * t;   // zero beyond column d
+            bq[nb][0] = ldg_u4(qp);
+            bq[nb][1] = ldg_u4(qp + 64);
+        }
+        // thresholds of queries 8nb + 2t + e; dot: the score is an integer, compare integers
+        int c_q[2][2];
+        double c_tau[2][2];
+        int c_taui[2][2];
+        double c_qn[2][2];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * nb + 2 * t + e;
+                c_q[nb][e] = __shfl_sync(0xffffffffu, my_q, j);
+                const double tv = j < m ? __ldg(&r->tau[j]) : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
+                if (ANGULAR) { c_tau[nb][e] = tv; c_qn[nb][e] = __ldg(qnorm + c_q[nb][e]); }
+                // a dot product of bytes is below 2^31 - 1: INT_MAX masks the slot
+                else c_taui[nb][e] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
+            }
+        const int32_t* bids = ids_sorted + bstart;
+        for (int row0 = 0; row0 < len; row0 += 32) {                 // one id window = 2 tiles of 16 rows
+            if (row0) idA = __ldg(bids + min(row0 + lane, len - 1));
+            uint4 a[2][2][2];                                        // [tile][row g / 8 + g][chunk]
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = min(row0 + 16 * tl + 8 * rr + g, len - 1);
+                    const unsigned char* xp = X8 + (size_t)__shfl_sync(0xffffffffu, idA, row - row0) * pitch;
+                    a[tl][rr][0] = ldg_u4(xp + off0);
+                    a[tl][rr][1] = ldg_u4(xp + off1);
+                }
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl) {
+                if (row0 + 16 * tl >= len) break;                    // warp-uniform
+                int acc[2][4];
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[nb][i] = 0;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c == 1 && !two_chunks) break;
+                    imma_u8(acc[0], a[tl][0][c].x, a[tl][1][c].x, a[tl][0][c].y, a[tl][1][c].y, bq[0][c].x, bq[0][c].y);
+                    imma_u8(acc[0], a[tl][0][c].z, a[tl][1][c].z, a[tl][0][c].w, a[tl][1][c].w, bq[0][c].z, bq[0][c].w);
+                    if (two_blocks) {
+                        imma_u8(acc[1], a[tl][0][c].x, a[tl][1][c].x, a[tl][0][c].y, a[tl][1][c].y, bq[1][c].x, bq[1][c].y);
+                        imma_u8(acc[1], a[tl][0][c].z, a[tl][1][c].z, a[tl][0][c].w, a[tl][1][c].w, bq[1][c].z, bq[1][c].w);
+                    }
+                }
+                double xnr[2] = {1.0, 1.0};
+                if (ANGULAR) {
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        unsigned s = 0;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            unsigned sc = 0;
+                            sc = __dp4a(a[tl][rr][c].x, a[tl][rr][c].x, sc); sc = __dp4a(a[tl][rr][c].y, a[tl][rr][c].y, sc);
+                            sc = __dp4a(a[tl][rr][c].z, a[tl][rr][c].z, sc); sc = __dp4a(a[tl][rr][c].w, a[tl][rr][c].w, sc);
+                            if (c == 0 ? has0 : has1) s += sc;
+                        }
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        xnr[rr] = sqrt((double)s);
+                    }
+                }
+                // c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int row = row0 + 16 * tl + 8 * rr + g;
+                            const int dot = acc[nb][2 * rr + e];
+                            bool keep;
+                            double v = (double)dot;
+                            if (ANGULAR) { v = v / (c_qn[nb][e] * xnr[rr]); keep = v >= c_tau[nb][e]; }
+                            else keep = dot >= c_taui[nb][e];
+                            if (keep && row < len && (nb == 0 || two_blocks))
+                                keep_survivor(flt, c_q[nb][e], v, __ldg(ids_sorted + bstart + row));
+                        }
+            }
+        }
+    }
+    if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], (unsigned long long)rows_staged); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+int u8_query_pitch() { return U8_QPITCH; }
+
 bool score_u8_usable(const dpf_index* h) {
     const char* e = getenv("DPF_BM_KERNEL");
-    if (e && (e[0] == 's' || e[0] == 'w')) return false;      // =stream / =warps: the other bucket-major kernels
+    if (e && e[0] == 's') return false;                       // =stream: the TMA ring kernel on the byte rows
     return h->Xc_kind == DPF_STORE_KIND_U8 && h->Xc_row_bytes <= 128;
 }
 
@@ -320,7 +397,7 @@ void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq) {
     const char* e = getenv("DPF_U8_IMMA");
     if (e && e[0] == '0') return;                             // DPF_U8_IMMA=0: always multiply on the FP64 tensor pipe
     cudaStream_t st = h->stream;
-    const int pitch = (int)h->Xc_row_bytes;
+    const int pitch = U8_QPITCH;
     h->Q8.reserve((size_t)nq * pitch);
     h->qnorm8.reserve((size_t)nq);
     int* flag = h->counters.p + 41;
@@ -334,17 +411,22 @@ void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq) {
 }
 
 void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const uint32_t* nunits_p, bool angular,
-                     unsigned long long* bm_stat) {
+                     const Filter& flt, unsigned long long* bm_stat) {
     const UnitRec* units = reinterpret_cast<const UnitRec*>(units_v);
     const unsigned pitch = (unsigned)h->Xc_row_bytes;
-    const int d = h->cfg.d;
     cudaStream_t st = h->stream;
-    auto launch = [&](auto kern, int ctas_per_sm) {
-        kern<<<h->num_sms * ctas_per_sm, U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, d, Qd, h->Q8.p, h->qnorm8.p, units, nunits_p,
-                                                                h->ids_sorted.p, h->scores.p, bm_stat);
-    };
-    if (h->Q8_valid) { if (angular) launch(k_score_u8<true, true>, 1); else launch(k_score_u8<false, true>, 1); }
-    else { if (angular) launch(k_score_u8<true, false>, 1); else launch(k_score_u8<false, false>, 1); }
+    if (h->Q8_valid) {
+        auto launch = [&](auto kern) {
+            kern<<<h->num_sms * (angular ? U8_INT_CTAS - 1 : U8_INT_CTAS), U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, units, nunits_p,
+                                                                   h->ids_sorted.p, flt, bm_stat);
+        };
+        if (angular) launch(k_score_u8i<true>); else launch(k_score_u8i<false>);
+    } else {
+        auto launch = [&](auto kern) {
+            kern<<<h->num_sms, U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->cfg.d, Qd, units, nunits_p, h->ids_sorted.p, flt, bm_stat);
+        };
+        if (angular) launch(k_score_u8d<true>); else launch(k_score_u8d<false>);
+    }
 }
 
 }  // namespace dpf

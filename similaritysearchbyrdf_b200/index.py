@@ -71,8 +71,9 @@ class DPFIndex:
         self._ck(self.lib.dpf_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     def set_store_mode(self, mode):
-        """B.STORE_AUTO (default): keep a lossless uint8 / float32 copy of the dense store for the re-rank kernels when
-        every value round-trips; B.STORE_F64_ONLY: always read the FP64 rows.  Call before fit."""
+        """B.STORE_AUTO (default): keep a lossless uint8 copy of the dense store for the re-rank kernels when every value
+        is a byte; B.STORE_NARROWEST: uint8, else float32 when lossless; B.STORE_F64_ONLY: always read the FP64 rows.
+        Call before fit."""
         self._ck(self.lib.dpf_set_store_mode(self.h, mode))
 
     # ---- hash functions -------------------------------------------------------------------------------------

@@ -275,7 +275,8 @@ def test_topk_bucket_major_equals_row_major_bitwise_on_integer_data(monkeypatch)
     ix = U.make_index(128, A, chain, Ap, bucket_overflow=100)
     ix.fit_dense(X)
     res = {}
-    for name, env in (("stream", {}), ("warps", {"DPF_BM_KERNEL": "warps"}), ("rowmajor", {"DPF_RERANK": "rowmajor"})):
+    for name, env in (("u8", {}), ("stream", {"DPF_BM_KERNEL": "stream"}), ("u8_dmma", {"DPF_U8_IMMA": "0"}),
+                      ("rowmajor", {"DPF_RERANK": "rowmajor"})):
         for k_, v in env.items():
             monkeypatch.setenv(k_, v)
         res[name] = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
@@ -283,7 +284,7 @@ def test_topk_bucket_major_equals_row_major_bitwise_on_integer_data(monkeypatch)
         assert (bm > 0) == (name != "rowmajor")
         for k_ in env:
             monkeypatch.delenv(k_)
-    for name in ("stream", "warps"):
+    for name in ("u8", "stream", "u8_dmma"):
         assert np.array_equal(res[name][0], res["rowmajor"][0]), name
         assert np.array_equal(res[name][1], res["rowmajor"][1]), name
 
@@ -323,7 +324,8 @@ def test_compact_store_kinds_match_oracle(d, kind, metric):
     X = _store_data(kind, 3000, d, 300 + d)
     rng = np.random.default_rng(7)
     A, chain, Ap = U.make_functions(d, family_size=max(40, d), table_num=3, permutation_num=2, seed=41 + d)
-    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=30); ix = U.make_index(d, A, chain, Ap, bucket_overflow=30)
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=30)
+    ix = U.make_index(d, A, chain, Ap, bucket_overflow=30, store_mode=B.STORE_NARROWEST)
     o.fit_dense(X); ix.fit_dense(X)
     st = ix.stats()
     assert st["store_kind"] == kind
@@ -379,9 +381,36 @@ def test_compact_store_one_value_decides(poison, expect):
     if poison is not None:
         X[777, 13] = poison
     A, chain, Ap = U.make_functions(d, family_size=40, table_num=2, permutation_num=1, seed=3)
-    ix = U.make_index(d, A, chain, Ap, bucket_overflow=30)
+    ix = U.make_index(d, A, chain, Ap, bucket_overflow=30, store_mode=B.STORE_NARROWEST)
     ix.fit_dense(X)
     assert ix.stats()["store_kind"] == expect
+    ix2 = U.make_index(d, A, chain, Ap, bucket_overflow=30)          # default mode: bytes or nothing
+    ix2.fit_dense(X)
+    assert ix2.stats()["store_kind"] == (B.STORE_KIND_U8 if expect == B.STORE_KIND_U8 else B.STORE_KIND_F64)
+
+
+@pytest.mark.parametrize("metric", [B.METRIC_DOT, B.METRIC_ANGULAR])
+@pytest.mark.parametrize("byte_queries", [True, False])
+def test_threshold_filter_corner_cases(metric, byte_queries, monkeypatch):
+    """Byte store -> filtered pipeline (k_threshold, k_score_u8*, k_select_survivors).  topk larger than the sampled
+    buckets (tau = -inf: nothing may be filtered), topk larger than all candidates (padded rows), any number of sampled
+    tables, qids with the self-exclusion quirk: always the oracle's top k."""
+    d = 48
+    X = _store_data(B.STORE_KIND_U8, 2400, d, 77)
+    A, chain, Ap = U.make_functions(d, family_size=48, table_num=4, permutation_num=2, seed=78)
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=25); ix = U.make_index(d, A, chain, Ap, bucket_overflow=25)
+    o.fit_dense(X); ix.fit_dense(X)
+    assert ix.stats()["store_kind"] == B.STORE_KIND_U8
+    qids = np.arange(0, 2400, 9, dtype=np.int32)
+    Qs = X[qids] if byte_queries else X[qids] + 0.37
+    for topk, steps, nt in ((5, 0, 1), (10, 1, 3), (60, 1, 8), (200, 2, 32), (256, 0, 6)):
+        monkeypatch.setenv("DPF_TAU_TABLES", str(nt))
+        io, so = o.query_topk_dense(Qs, qids, steps, topk, metric)
+        ig, sg = ix.query_topk_dense(Qs, qids, steps, topk, metric)
+        U.assert_topk_close(io, so, ig, sg)
+        st = ix.stats()
+        assert st["bm_pairs"] > 0 and st["bm_survivors"] >= (ig >= 0).sum()
+    assert np.array_equal(ig == -1, io == -1)                 # padded rows where the candidates run out
 
 
 def test_compact_store_append_widens():

@@ -26,7 +26,10 @@ def make_index(d, A, chain, Ap, **kw):
     L, k = chain.shape
     pb = Ap.shape[1]
     b, w = kw.pop("b", None), kw.pop("w", None)
+    store_mode = kw.pop("store_mode", None)
     ix = DPFIndex(d=d, L=L, k=k, pb=pb, **kw)
+    if store_mode is not None:
+        ix.set_store_mode(store_mode)
     ix.set_family(A, chain, b, w)
     ix.set_partitioners(Ap)
     return ix

@@ -34,4 +34,4 @@ for _ in range(a.repeat + 1):
     st = ix.stats()
     print("query stage ms:", {k: round(v, 3) for k, v in ix.stage_times_ms().items() if v},
           "cand/q", st["last_candidates"] / a.nq, "dups/q", st["last_cand_with_dups"] / a.nq,
-          "bm pairs", st["bm_pairs"], "runs", st["bm_runs"], "rows staged", st["bm_rows_staged"])
+          "bm pairs", st["bm_pairs"], "runs", st["bm_runs"], "rows staged", st["bm_rows_staged"], "survivors/q", st["bm_survivors"] / a.nq)
