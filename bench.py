@@ -26,9 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_score_warps launch of this command (ncu --set full capture,
-# profiles/r1_ncu_full_bucket_major.csv); None until captured
-NCU_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the scoring kernel on this workload (ncu --set full
+# captures summarised under profiles/); kernels without a capture report null
+NCU_TRAFFIC_BYTES = {"k_score_stream": 46_793_233_000 + 4_166_460_000,       # profiles/r1_ncu_full_k_score_stream.csv
+                     "k_score_u8i": 3_160_577_000 + 103_093_000}             # profiles/r1_ncu_full_u8_pipeline.csv
 
 METRIC_NAME = "batch kNN queries/sec at fixed recall@10"
 UNIT = "queries/s"
@@ -174,6 +175,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # NCCL's version banner goes to stdout: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     metric = {"dot": B.METRIC_DOT, "angular": B.METRIC_ANGULAR, "l2": B.METRIC_L2}[args.metric]
 
@@ -256,6 +258,8 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step = float(t.item()) / args.steps
         qstats = ix.stats()
+        int_queries = bool(np.all(Q == np.floor(Q)) and Q.min() >= 0 and Q.max() <= 255)
+        unit_rec_bytes = 16 + 16 * 4 + 16 * 4 + 16 * 8 + 32 * 4                  # sizeof(UnitRec), rerank_units.cuh
         result_ids = (m_ids if world > 1 else ids_d).cpu().numpy()
         result_sc = (m_sc if world > 1 else sc_d).cpu().numpy()
 
@@ -354,10 +358,13 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
-    # Algorithmic bytes (SURVEY 8d / DESIGN 4): nC_q * (8d + 4) per query, nC_q = unique candidates.  The bucket-major
-    # kernel (k_score_warps) scores a bucket's rows once per run of queries that probe it, so its DRAM traffic is far
-    # below that figure; both are reported (dram_bytes_staged is the kernel's own count of rows fetched * 8d plus
-    # the 8-byte score it writes per (query, candidate) pair).
+    # The re-rank is bucket-major: every leaf bucket probed by the batch is scored once per unit of <= 16 queries that
+    # probe it.  `achieved` = the bytes one launch of the scoring kernel has to move for that: staged rows x
+    # (row bytes of the compact store + 4 B id) + one record per unit + the query operand of each unit + 12 B per
+    # survivor (or 8 B per score on the dense FP64 pipeline), divided by the kernel's time from CUDA events.
+    # `survey_8d` restates SURVEY 8(d)'s per-candidate figure (nC_q x (8d + 4) B per query, FP64 rows fetched once per
+    # (query, unique candidate)) for comparison: it is far above the HBM peak precisely because the kernel neither
+    # fetches a row once per query nor keeps it in FP64.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -366,19 +373,32 @@ def run_ours(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     ncand_unique = int(rowmajor["unique_candidates"])
-    alg_bytes = ncand_unique * (8 * d + 4)
     rr_ms = float(np.mean(rerank_ms)) if rerank_ms else None
-    achieved = alg_bytes / (rr_ms * 1e-3) / 1e9 if rr_ms else None
     bm = qstats["bm_pairs"] > 0
-    staged = int(qstats["bm_rows_staged"]) * 8 * d + int(qstats["last_cand_with_dups"]) * 8 if bm else None
-    roofline = {"kernel": "k_score_warps" if bm else "k_rerank_units", "bound": "hbm", "achieved": achieved,
-                "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs if achieved else None,
-                "traffic": NCU_TRAFFIC_BYTES if bm else None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": rr_ms,
+    store_kind = {0: "f64", 1: "f32", 2: "u8"}[int(qstats["store_kind"])]
+    row_bytes = int(qstats["store_row_bytes"])
+    filtered = bm and store_kind == "u8"
+    if bm:
+        kernel = ("k_score_u8i" if int_queries else "k_score_u8d") if filtered else "k_score_stream"
+        units = int(qstats["bm_runs"])
+        q_operand = 16 * (128 if (filtered and int_queries) else 8 * d)
+        out_bytes = int(qstats["bm_survivors"]) * 12 if filtered else int(qstats["last_cand_with_dups"]) * 8
+        kernel_bytes = int(qstats["bm_rows_staged"]) * (row_bytes + 4) + units * (unit_rec_bytes + q_operand) + out_bytes
+    else:
+        kernel = "k_rerank_units"
+        kernel_bytes = ncand_unique * (8 * d + 4)
+    achieved = kernel_bytes / (rr_ms * 1e-3) / 1e9 if rr_ms else None
+    survey_bytes = ncand_unique * (8 * d + 4)
+    roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs if achieved else None,
+                "traffic": NCU_TRAFFIC_BYTES.get(kernel), "peak_source": peak_src,
+                "bytes_per_launch": kernel_bytes, "kernel_ms": rr_ms, "step_share": rr_ms / ms_per_step if rr_ms else None,
+                "store_kind": store_kind, "store_row_bytes": row_bytes, "rows_staged_per_launch": int(qstats["bm_rows_staged"]),
+                "units_per_launch": int(qstats["bm_runs"]), "survivors_per_query": int(qstats["bm_survivors"]) / nq,
                 "unique_candidates_per_query": ncand_unique / nq,
-                "step_share": rr_ms / ms_per_step if rr_ms else None,
-                "dram_bytes_staged_per_launch": staged,
-                "dram_frac_of_peak": staged / (rr_ms * 1e-3) / 1e9 / peak_gbs if staged and rr_ms else None,
+                "survey_8d": {"algorithmic_bytes_per_launch": survey_bytes,
+                              "gbs": survey_bytes / (rr_ms * 1e-3) / 1e9 if rr_ms else None,
+                              "frac_of_peak": survey_bytes / (rr_ms * 1e-3) / 1e9 / peak_gbs if rr_ms else None},
                 "row_major_kernel": rowmajor}
 
     cpu = None
@@ -403,6 +423,7 @@ def run_ours(args):
                   "near_zero_fixups": bstats["near_zero_fixups"], "splits": bstats["splits"],
                   "singleton_splits": bstats["singleton_splits"], "dir_nodes": bstats["dir_nodes"]},
         "query_stage_ms": stage_acc, "candidates_with_dups_per_query": qstats["last_cand_with_dups"] / nq,
+        "store": {"kind": store_kind, "row_bytes": row_bytes},
         "datagen_s": gen_s,
     }
     print(json.dumps(line))
