@@ -67,6 +67,13 @@ JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_setPartitioners(JNIEnv* env, 
 }
 
 /* void fitDense(long h, double[] X, long n) — newMultiThreadFit / newFastFit after parsing (DensevectorRDFInit.scala:127-206) */
+JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_setStoreMode(JNIEnv* env, jclass cls, jlong jh, jint mode) {
+    (void)cls;
+    dpf_handle h = (dpf_handle)(intptr_t)jh;
+    int rc = dpf_set_store_mode(h, mode);     /* DPF_STORE_AUTO / DPF_STORE_F64_ONLY / DPF_STORE_NARROWEST, before fit */
+    if (rc != DPF_OK) throw_dpf(env, h, rc);
+}
+
 JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_fitDense(JNIEnv* env, jclass cls, jlong jh, jdoubleArray jX, jlong n) {
     (void)cls;
     dpf_handle h = (dpf_handle)(intptr_t)jh;
