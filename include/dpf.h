@@ -136,6 +136,23 @@ int dpf_query_topk_dense_dev(dpf_handle h, const double* Q_dev, int64_t nq, cons
 int dpf_rerank_dense(dpf_handle h, const double* Q, int64_t nq, const int64_t* offsets, const int32_t* cand,
                      int32_t topk, int32_t metric, int32_t* ids_out, double* score_out);
 
+/* ---- text loaders (host code, no handle): the file formats newMultiThreadFit reads — dense `[id,[v1,v2,...]]`
+ * (Vectors.parseDense, Vector.scala:215-219; read loop DensevectorRDFInit.scala:172-181) and sparse
+ * `[id, size, [i1,...], [v1,...]]` (Vectors.fromPythonString, Vector.scala:194-208; SparsevectorRDFInit.scala:164-176).
+ * Rows come back in file order (the id in the file is ignored, as in the reference), empty lines are skipped, sparse
+ * indices ascending.  Call once with NULL outputs for the sizes, then with buffers; DPF_ERR_CAPACITY if they are too
+ * small, DPF_ERR_INVALID for a line that does not parse (dense: not exactly d values). */
+int dpf_parse_dense_file(const char* path, int32_t d, double* X_out, int64_t cap_rows, int64_t* n_out);
+int dpf_parse_sparse_file(const char* path, int64_t* indptr_out, int32_t* indices_out, double* values_out,
+                          int64_t cap_rows, int64_t cap_nnz, int64_t* n_out, int64_t* nnz_out, int32_t* dim_out);
+
+/* ---- persist / reload: the replacement for the reference's RAM-threshold spill of tree pages to disk
+ * (RandomDrawTreeMap.java:2713-2773, StoreSegment.java:489-545).  dpf_save writes configuration, hash functions, the
+ * vector store and every vector's keys / sub-index ids; dpf_load restores them on `device` and re-creates the flat forest
+ * from the stored keys (no re-hashing), bit-identical to the saved index. */
+int dpf_save(dpf_handle h, const char* path);
+int dpf_load(const char* path, int32_t device, dpf_handle* out);
+
 /* ---- multi-GPU: merge per-GPU top-k lists after the NCCL all-gather -----------------------
  * gathered_*_dev: G x nq x topk as produced by all-gathering dpf_query_topk_dense_dev outputs; duplicates of
  * one id (same vector reached through tables owned by different GPUs) are collapsed. */

@@ -633,6 +633,146 @@ int dpf_rerank_dense(dpf_handle h, const double* Q, int64_t nq, const int64_t* o
     });
 }
 
+// ---- persist / reload -------------------------------------------------------------------------------------------
+// File = "DPFIDX01" | dpf_config | P, dense, has_bw, n, nnz | A | chain | [b, w] | Ap | store (X or CSR) | keys | pids.
+// The flat forest is not written: it is a pure function of (keys, pids, ids in ascending order) and build_forest
+// re-creates it at > 150M vectors/s, bit for bit (the same call an append makes) — what would be expensive to redo,
+// hashing the vectors, is what the file keeps.
+}  // extern "C"
+namespace {
+struct File {
+    FILE* f = nullptr;
+    ~File() { if (f) fclose(f); }
+};
+template <class T>
+void dev_to_file(dpf_index* h, FILE* f, const T* dev, size_t count) {
+    const size_t chunk = (64u << 20) / sizeof(T);
+    std::vector<T> buf(std::min(chunk, std::max<size_t>(count, 1)));
+    for (size_t at = 0; at < count; at += chunk) {
+        const size_t m = std::min(chunk, count - at);
+        DPF_CUDA(cudaMemcpyAsync(buf.data(), dev + at, m * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        DPF_REQUIRE(fwrite(buf.data(), sizeof(T), m, f) == m, DPF_ERR_INVALID, "dpf_save: short write");
+    }
+}
+template <class T>
+void file_to_dev(dpf_index* h, FILE* f, T* dev, size_t count) {
+    const size_t chunk = (64u << 20) / sizeof(T);
+    std::vector<T> buf(std::min(chunk, std::max<size_t>(count, 1)));
+    for (size_t at = 0; at < count; at += chunk) {
+        const size_t m = std::min(chunk, count - at);
+        DPF_REQUIRE(fread(buf.data(), sizeof(T), m, f) == m, DPF_ERR_INVALID, "dpf_load: truncated file");
+        DPF_CUDA(cudaMemcpyAsync(dev + at, buf.data(), m * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+    }
+}
+template <class T>
+void put(FILE* f, const T& v) { DPF_REQUIRE(fwrite(&v, sizeof(T), 1, f) == 1, DPF_ERR_INVALID, "dpf_save: short write"); }
+template <class T>
+void get(FILE* f, T& v) { DPF_REQUIRE(fread(&v, sizeof(T), 1, f) == 1, DPF_ERR_INVALID, "dpf_load: truncated file"); }
+const char kMagic[8] = {'D', 'P', 'F', 'I', 'D', 'X', '0', '1'};
+}  // namespace
+extern "C" {
+
+int dpf_save(dpf_handle h, const char* path) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(path, DPF_ERR_INVALID, "null path");
+        File file;
+        file.f = fopen(path, "wb");
+        DPF_REQUIRE(file.f, DPF_ERR_INVALID, std::string("dpf_save: cannot open ") + path);
+        FILE* f = file.f;
+        const int d = h->cfg.d, L = h->cfg.L, k = h->cfg.k;
+        DPF_REQUIRE(fwrite(kMagic, 1, 8, f) == 8, DPF_ERR_INVALID, "dpf_save: short write");
+        put(f, h->cfg);
+        const int32_t P = h->P, dense = h->dense ? 1 : 0, has_bw = h->cfg.family_kind == DPF_FAMILY_PSTABLE ? 1 : 0;
+        put(f, P); put(f, dense); put(f, has_bw); put(f, h->n); put(f, h->sp_nnz);
+        dev_to_file(h, f, h->A.p, (size_t)P * d);
+        dev_to_file(h, f, h->chain.p, (size_t)L * k);
+        if (has_bw) { dev_to_file(h, f, h->fb.p, (size_t)P); dev_to_file(h, f, h->fw.p, (size_t)P); }
+        dev_to_file(h, f, h->Ap.p, (size_t)L * h->cfg.pb * 32);
+        if (dense) {
+            dev_to_file(h, f, h->Xdev, (size_t)h->n * d);
+        } else {
+            dev_to_file(h, f, h->sp_ptr.p, (size_t)h->n + 1);
+            dev_to_file(h, f, h->sp_idx.p, (size_t)h->sp_nnz);
+            dev_to_file(h, f, h->sp_val.p, (size_t)h->sp_nnz);
+        }
+        for (int t = 0; t < L; ++t) dev_to_file(h, f, h->keys.p + (size_t)t * h->key_ld, (size_t)h->n);
+        for (int t = 0; t < L; ++t) dev_to_file(h, f, h->pids.p + (size_t)t * h->key_ld, (size_t)h->n);
+        DPF_REQUIRE(fflush(f) == 0, DPF_ERR_INVALID, "dpf_save: flush failed");
+    });
+}
+
+int dpf_load(const char* path, int32_t device, dpf_handle* out) {
+    if (!path || !out) return DPF_ERR_INVALID;
+    *out = nullptr;
+    File file;
+    file.f = fopen(path, "rb");
+    if (!file.f) return DPF_ERR_INVALID;
+    FILE* f = file.f;
+    char magic[8];
+    dpf_config cfg;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMagic, 8) != 0 || fread(&cfg, sizeof(cfg), 1, f) != 1) return DPF_ERR_INVALID;
+    cfg.device = device;
+    dpf_handle h = nullptr;
+    int rc = dpf_create(&cfg, &h);
+    if (rc != DPF_OK) return rc;
+    rc = guarded(h, [&] {
+        const int d = cfg.d, L = cfg.L, k = cfg.k;
+        int32_t P = 0, dense = 0, has_bw = 0;
+        int64_t n = 0, nnz = 0;
+        get(f, P); get(f, dense); get(f, has_bw); get(f, n); get(f, nnz);
+        DPF_REQUIRE(P > 0 && n > 0 && nnz >= 0 && has_bw == (cfg.family_kind == DPF_FAMILY_PSTABLE ? 1 : 0), DPF_ERR_INVALID,
+                    "dpf_load: bad header");
+        h->P = P;
+        h->PW = (P + 31) / 32;
+        h->hA.resize((size_t)P * d);
+        DPF_REQUIRE(fread(h->hA.data(), sizeof(double), h->hA.size(), f) == h->hA.size(), DPF_ERR_INVALID, "dpf_load: truncated file");
+        h->A.reserve(h->hA.size());
+        h2d(h, h->A.p, h->hA.data(), h->hA.size());
+        h->chain.reserve((size_t)L * k);
+        file_to_dev(h, f, h->chain.p, (size_t)L * k);
+        if (has_bw) {
+            h->fb.reserve(P); h->fw.reserve(P);
+            file_to_dev(h, f, h->fb.p, (size_t)P);
+            file_to_dev(h, f, h->fw.p, (size_t)P);
+        }
+        h->Ap.reserve(std::max<size_t>((size_t)L * cfg.pb * 32, 1));
+        file_to_dev(h, f, h->Ap.p, (size_t)L * cfg.pb * 32);
+        prepare_family(h);
+        h->family_set = h->part_set = true;
+        h->dense = dense != 0;
+        if (h->dense) {
+            h->X.reserve((size_t)n * d);
+            file_to_dev(h, f, h->X.p, (size_t)n * d);
+            h->Xdev = h->X.p;
+        } else {
+            h->sp_ptr.reserve((size_t)n + 1);
+            h->sp_idx.reserve((size_t)nnz + 1);
+            h->sp_val.reserve((size_t)nnz + 1);
+            file_to_dev(h, f, h->sp_ptr.p, (size_t)n + 1);
+            file_to_dev(h, f, h->sp_idx.p, (size_t)nnz);
+            file_to_dev(h, f, h->sp_val.p, (size_t)nnz);
+            h->sp_nnz = nnz;
+        }
+        grow_keys(h, n);
+        for (int t = 0; t < L; ++t) file_to_dev(h, f, h->keys.p + (size_t)t * h->key_ld, (size_t)n);
+        for (int t = 0; t < L; ++t) file_to_dev(h, f, h->pids.p + (size_t)t * h->key_ld, (size_t)n);
+        h->n = n;
+        build_forest(h);
+        if (h->dense) build_compact_store(h);
+        h->stats[DPF_STAT_SIZE] = h->n;
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+    });
+    if (rc != DPF_OK) {
+        dpf_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return DPF_OK;
+}
+
 int dpf_merge_topk_dev(dpf_handle h, const int32_t* gathered_ids_dev, const double* gathered_scores_dev, int32_t G,
                        int64_t nq, int32_t topk, int32_t metric, int32_t* ids_out_dev, double* score_out_dev) {
     return guarded(h, [&] {

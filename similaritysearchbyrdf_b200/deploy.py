@@ -164,30 +164,51 @@ class Vectors:
         return np.array([int(p.replace("[", "").replace("]", "")) for p in parts[:k]], np.int32)
 
 
-def load_dense_file(path):
-    """Fast whole-file reader of the `[id,[v...]]` format: rows in file order, ids ignored (quirk Q14)."""
-    rows = []
+def _first_line_dim(path):
     with open(path) as f:
         for line in f:
             if line.strip():
-                rows.append(Vectors.parseDense(line)[1])
-    return np.stack(rows) if rows else np.zeros((0, 0))
+                return len(Vectors.parseDense(line)[1])
+    return 0
+
+
+def load_dense_file(path, d=None):
+    """Whole-file reader of the `[id,[v...]]` format through the library's native parser (dpf_parse_dense_file):
+    rows in file order, ids ignored (quirk Q14).  d defaults to the width of the first line."""
+    import ctypes as C
+    lib = B.load()
+    d = d or _first_line_dim(path)
+    if d == 0:
+        return np.zeros((0, 0))
+    n = C.c_int64(0)
+    rc = lib.dpf_parse_dense_file(str(path).encode(), d, None, 0, C.byref(n))
+    if rc != B.OK:
+        raise ValueError(f"cannot parse {path}: {lib.dpf_strerror(rc).decode()}")
+    X = np.empty((n.value, d), np.float64)
+    rc = lib.dpf_parse_dense_file(str(path).encode(), d, C.c_void_p(X.ctypes.data), n.value, C.byref(n))
+    if rc != B.OK:
+        raise ValueError(f"cannot parse {path}: {lib.dpf_strerror(rc).decode()}")
+    return X
 
 
 def load_sparse_file(path):
-    """`[id, size, [idx], [val]]` rows -> CSR (indptr int64, indices int32, values f64), dim."""
-    indptr, idx, val, size = [0], [], [], 0
-    with open(path) as f:
-        for line in f:
-            if not line.strip():
-                continue
-            _, sz, i, v = Vectors.fromPythonString(line)
-            order = np.argsort(i, kind="stable")            # BitSet iteration is ascending (SimilarityCalculator.scala:19-25)
-            idx.append(i[order]); val.append(v[order])
-            indptr.append(indptr[-1] + len(i))
-            size = max(size, sz)
-    return (np.array(indptr, np.int64), np.concatenate(idx) if idx else np.zeros(0, np.int32),
-            np.concatenate(val) if val else np.zeros(0)), size
+    """`[id, size, [idx], [val]]` rows -> (CSR (indptr int64, indices int32, values f64), dim) through
+    dpf_parse_sparse_file; indices ascending per row (BitSet iteration order, SimilarityCalculator.scala:19-25)."""
+    import ctypes as C
+    lib = B.load()
+    n, nnz, dim = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    rc = lib.dpf_parse_sparse_file(str(path).encode(), None, None, None, 0, 0, C.byref(n), C.byref(nnz), C.byref(dim))
+    if rc != B.OK:
+        raise ValueError(f"cannot parse {path}: {lib.dpf_strerror(rc).decode()}")
+    indptr = np.zeros(n.value + 1, np.int64)
+    idx = np.empty(nnz.value, np.int32)
+    val = np.empty(nnz.value, np.float64)
+    rc = lib.dpf_parse_sparse_file(str(path).encode(), C.c_void_p(indptr.ctypes.data), C.c_void_p(idx.ctypes.data),
+                                   C.c_void_p(val.ctypes.data), n.value, max(nnz.value, 1), C.byref(n), C.byref(nnz),
+                                   C.byref(dim))
+    if rc != B.OK:
+        raise ValueError(f"cannot parse {path}: {lib.dpf_strerror(rc).decode()}")
+    return (indptr, idx, val), dim.value
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -43,6 +43,29 @@ class DPFIndex:
             raise B.DpfError(rc, self.lib.dpf_strerror(rc).decode())
         self.d, self.L, self.k, self.pb = d, L, k, pb
 
+    # ---- persist / reload ------------------------------------------------------------------------------------
+    def save(self, path):
+        """Write configuration, hash functions, vectors and keys to `path` (dpf_save)."""
+        self._ck(self.lib.dpf_save(self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path, device=0):
+        """Restore an index written by save() on `device`; the forest is re-created from the stored keys."""
+        self = cls.__new__(cls)
+        self.lib = B.load()
+        self.h = C.c_void_p()
+        rc = self.lib.dpf_load(str(path).encode(), device, C.byref(self.h))
+        if rc != B.OK:
+            raise B.DpfError(rc, self.lib.dpf_strerror(rc).decode())
+        import struct
+        with open(path, "rb") as f:
+            f.read(8)
+            vals = struct.unpack("14i", f.read(56))
+        self.cfg = B.Config(*vals)
+        self.cfg.device = device
+        self.d, self.L, self.k, self.pb = self.cfg.d, self.cfg.L, self.cfg.k, self.cfg.pb
+        return self
+
     # ---- plumbing -------------------------------------------------------------------------------------------
     def _ck(self, rc):
         if rc != B.OK:

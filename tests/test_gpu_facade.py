@@ -150,3 +150,56 @@ def test_full_size_properties_config2_sample():
     ids, sc = ix.query_topk_dense(X[1000:1064], None, 0, 10, B.METRIC_L2, B.PROBE_NONE)
     assert (ids[:, 0] == np.arange(1000, 1064)).all() and (sc[:, 0] == 0).all()
     assert np.all(np.diff(sc, axis=1) >= 0)
+
+
+# ---- persist / reload (dpf_save / dpf_load) --------------------------------------------------------------------------
+def test_save_load_dense_roundtrip(tmp_path):
+    """A reloaded index answers exactly like the one that was saved: same buckets, candidate sets, top-k, store kind."""
+    from similaritysearchbyrdf_b200 import DPFIndex
+    rng = np.random.default_rng(3)
+    d = 64
+    X = np.clip(np.rint(40 * rng.standard_normal((5000, d)) + 128), 0, 255) + 0.0      # bytes -> compact store
+    A, chain, Ap = U.make_functions(d, family_size=64, table_num=4, permutation_num=2, seed=17)
+    ix = U.make_index(d, A, chain, Ap, bucket_overflow=40)
+    ix.fit_dense(X[:3000])
+    ix.fit_dense(X[3000:])                                                         # saved after an append
+    path = tmp_path / "index.dpf"
+    ix.save(path)
+    ix2 = DPFIndex.load(path)
+    assert len(ix2) == 5000 and ix2.stats()["store_kind"] == ix.stats()["store_kind"] == B.STORE_KIND_U8
+    for t in range(chain.shape[0]):
+        for a, b in zip(ix.dump_buckets(t), ix2.dump_buckets(t)):
+            assert np.array_equal(a, b)
+    Q = X[::50] + 0.25
+    U.assert_csr_equal(ix.query_candidates_dense(Q, None, 1), ix2.query_candidates_dense(Q, None, 1))
+    for metric in (B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2):
+        i1, s1 = ix.query_topk_dense(Q, None, 1, 10, metric)
+        i2, s2 = ix2.query_topk_dense(Q, None, 1, 10, metric)
+        assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+    ix2.fit_dense(X[:100])                                                         # a reloaded index can grow
+    assert len(ix2) == 5100
+
+
+def test_save_load_sparse_roundtrip(tmp_path):
+    from similaritysearchbyrdf_b200 import DPFIndex
+    from tests.test_gpu_parity import _small_csr
+    D = 400
+    A, chain, Ap = U.make_functions(D, family_size=100, table_num=3, permutation_num=2, seed=5)
+    indptr, idx, val = _small_csr(3000, D, 6)
+    ix = U.make_index(D, A, chain, Ap, bucket_overflow=20)
+    ix.fit_csr(indptr, idx, val)
+    path = tmp_path / "sparse.dpf"
+    ix.save(path)
+    ix2 = DPFIndex.load(path)
+    qids = np.arange(0, 3000, 37, dtype=np.int32)
+    U.assert_csr_equal(ix.query_candidates_by_id(qids, 1), ix2.query_candidates_by_id(qids, 1))
+    qp, qi, qv = _small_csr(32, D, 7)
+    U.assert_csr_equal(ix.query_candidates_csr(qp, qi, qv, None, 0), ix2.query_candidates_csr(qp, qi, qv, None, 0))
+
+
+def test_load_rejects_garbage(tmp_path):
+    from similaritysearchbyrdf_b200 import DPFIndex
+    p = tmp_path / "junk.dpf"
+    p.write_bytes(b"not an index")
+    with pytest.raises(B.DpfError):
+        DPFIndex.load(p)
