@@ -183,6 +183,7 @@ struct dpf_index {
     dpf::DevBuf<unsigned long long> pair_key, pair_key_alt;
     dpf::DevBuf<double> scores;                // bucket-major re-rank: survivor scores / ids (Filter, rerank_units.cuh)
     dpf::DevBuf<int32_t> surv_id;
+    dpf::DevBuf<char> surv_pool;               // SurvRec blocks written by the scoring warps
     dpf::DevBuf<double> bm_tau;                // per query: score threshold
     dpf::DevBuf<uint32_t> bm_scnt, bm_sbase;   //            survivors so far, start of its list
     dpf::DevBuf<double> bm_tl_keys;            // threshold sample lists: nq x NT x k

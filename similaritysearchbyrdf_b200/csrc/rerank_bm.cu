@@ -693,10 +693,37 @@ k_threshold_merge(int64_t q0, int64_t nqc, int L, int NT, int K, const double* _
     }
 }
 
+// survivor records (SurvivorSink) -> per-query lists: at = base[q] + (old count of q); the row id is looked up here.
+// Survivors of one query come in bursts (a bucket near the query yields many), so the lanes of a warp that hold the
+// same query reserve their slots with one atomic.
+__global__ void __launch_bounds__(256)
+k_scatter_survivors(Filter flt, const int32_t* __restrict__ ids_sorted) {
+    const uint32_t n = *flt.pool_cursor;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n; i0 += stride) {   // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        SurvRec r;
+        r.q = -1;
+        if (i < n) r = flt.pool[i];
+        const uint32_t peers = __match_any_sync(0xffffffffu, r.q);
+        if (r.q < 0) continue;
+        const int leader = __ffs(peers) - 1;
+        uint32_t first = 0;
+        if (lane == leader) first = atomicAdd(flt.cnt + r.q, (uint32_t)__popc(peers));
+        first = __shfl_sync(peers, first, leader);
+        const uint32_t at = flt.base[r.q] + first + __popc(peers & ((1u << lane) - 1u));
+        flt.s_score[at] = r.score;
+        flt.s_id[at] = __ldg(ids_sorted + r.pos);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // k_select_survivors — one warp per query: top k of its survivor list, larger score first, ties by smaller id; an id
 // reached through several tables appears several times with bit-identical scores and is kept once.
 // ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t SEL_BIG = 1024;
+
 __global__ void __launch_bounds__(RR_THREADS)
 k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
                    int32_t* __restrict__ ids_out, double* __restrict__ score_out, unsigned long long* __restrict__ stat) {
@@ -709,6 +736,7 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
     const int64_t q = q0 + ql;
     const uint32_t n = flt.cnt[q];
     if (lane == 0) atomicAdd(&stat[2], (unsigned long long)n);
+    if (n > SEL_BIG) return;                 // a weak threshold left a long list: k_select_survivors_big (a CTA per query)
     const double* sc = flt.s_score + flt.base[q];
     const int32_t* si = flt.s_id + flt.base[q];
     const int qid = qids ? qids[q] : INT32_MIN;
@@ -734,6 +762,74 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
     for (int r = lane; r < K; r += 32) {
         ids_out[q * K + r] = r < count ? myids[r] : -1;
         score_out[q * K + r] = r < count ? mykeys[r] : __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
+// the same for the queries whose list is long (few: those whose sampled buckets held fewer than k rows, or rows far
+// from the query): one CTA per query, the warps take interleaved chunks of the list, then the per-warp lists are merged
+__global__ void __launch_bounds__(RR_THREADS)
+k_select_survivors_big(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
+                       int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
+    extern __shared__ double rsm[];
+    __shared__ int s_counts[RR_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = q0 + blockIdx.x;
+    const uint32_t n = flt.cnt[q];
+    if (n <= SEL_BIG) return;                // CTA-uniform
+    double* lkeys = rsm;
+    int* lids = reinterpret_cast<int*>(rsm + (size_t)RR_WARPS * K);
+    double* mykeys = lkeys + (size_t)warp * K;
+    int* myids = lids + (size_t)warp * K;
+    const double* sc = flt.s_score + flt.base[q];
+    const int32_t* si = flt.s_id + flt.base[q];
+    const int qid = qids ? qids[q] : INT32_MIN;
+    const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
+    int count = 0;
+    for (uint32_t j0 = 32u * warp; j0 < n; j0 += 32u * RR_WARPS) {
+        const uint32_t j = j0 + lane;
+        const double key = j < n ? sc[j] : 0.0;
+        const int id = j < n ? si[j] : -1;
+        bool cand = j < n && !(excl && id == qid);
+        if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
+        uint32_t todo = __ballot_sync(0xffffffffu, cand);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double kk = __shfl_sync(0xffffffffu, key, src);
+            const int ii = __shfl_sync(0xffffffffu, id, src);
+            bool dup = false;
+            for (int base = 0; base < count; base += 32) dup |= __any_sync(0xffffffffu, base + lane < count && myids[base + lane] == ii);
+            if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
+        }
+    }
+    if (lane == 0) s_counts[warp] = count;
+    __syncthreads();
+    if (warp == 0) {                         // merge; the same id in two lists carries the same score: adjacent, kept once
+        int head = 0, last = -1;
+        const int mycount = lane < RR_WARPS ? s_counts[lane] : 0;
+        for (int r = 0; r < K; ++r) {
+            double bk;
+            int bi, bl;
+            for (;;) {
+                bk = 0; bi = 0x7fffffff; bl = -1;
+                if (lane < RR_WARPS && head < mycount) { bk = lkeys[lane * K + head]; bi = lids[lane * K + head]; bl = lane; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                    if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+                }
+                if (bl < 0) break;
+                if (lane == bl) head++;
+                if (bi != last) break;
+            }
+            if (lane == 0) {
+                ids_out[q * K + r] = bl >= 0 ? bi : -1;
+                score_out[q * K + r] = bl >= 0 ? bk : __longlong_as_double(0x7ff8000000000000LL);
+            }
+            if (bl >= 0) last = bi;
+        }
     }
 }
 
@@ -948,6 +1044,10 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         if (use_u8) {
             // thresholds (and the survivor lists' bases and counters) before the units are cut: the records carry tau
             h->surv_id.reserve((size_t)std::max<int64_t>(entries_ub, 1));
+            // pool: every entry can survive (tau = -inf), a block switch leaves < 32 slots unused, every warp ends on a
+            // partial block
+            h->surv_pool.reserve((size_t)(entries_ub + entries_ub / 8 + (int64_t)h->num_sms * 64 * SURV_BLOCK + SURV_BLOCK) * sizeof(SurvRec));
+            DPF_CUDA(cudaMemsetAsync(h->counters.p + 42, 0, sizeof(uint32_t), st));
             h->bm_tau.reserve((size_t)qk.nq);
             h->bm_scnt.reserve((size_t)qk.nq);
             h->bm_sbase.reserve((size_t)qk.nq);
@@ -963,7 +1063,9 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                     h->pair_len.p, h->ids_sorted.p, qk.qids, h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p,
                     h->bm_tl_cnt.p);
             };
-            if (ang) { if (intq) go(k_threshold<true, DPF_STORE_KIND_U8, true>); else go(k_threshold<true, DPF_STORE_KIND_U8, false>); }
+            const char* tk = getenv("DPF_TAU_KERNEL");
+            if (intq && !(tk && tk[0] == 'd')) launch_threshold_u8i(h, ang, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
+            else if (ang) { if (intq) go(k_threshold<true, DPF_STORE_KIND_U8, true>); else go(k_threshold<true, DPF_STORE_KIND_U8, false>); }
             else { if (intq) go(k_threshold<false, DPF_STORE_KIND_U8, true>); else go(k_threshold<false, DPF_STORE_KIND_U8, false>); }
             DPF_LAUNCHED();
             k_threshold_merge<<<qgrid, RR_THREADS, 0, st>>>(q0, nqc, L, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p,
@@ -983,7 +1085,8 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         build_units(h, npairs, use_u8);
     }
     unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(h->counters.p + 26);   // cleared by probe_count_all
-    const Filter flt{h->bm_scnt.p, h->bm_sbase.p, h->scores.p, h->surv_id.p};
+    const Filter flt{h->bm_scnt.p, h->bm_sbase.p, h->scores.p, h->surv_id.p, reinterpret_cast<SurvRec*>(h->surv_pool.p),
+                     reinterpret_cast<uint32_t*>(h->counters.p + 42)};
     {
         StageTimer tm(h, DPF_T_RERANK);
         h->stats[DPF_STAT_BM_PAIRS] += h->bm_npairs;
@@ -1003,9 +1106,15 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     }
     {
         StageTimer tm(h, DPF_T_SELECT);
-        if (use_u8)
+        if (use_u8) {
+            k_scatter_survivors<<<h->num_sms * 8, 256, 0, st>>>(flt, h->ids_sorted.p); DPF_LAUNCHED();
+        }
+        if (use_u8) {
             k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, ids_out,
-                                                                     score_out, bm_stat);
+                                                                     score_out, bm_stat); DPF_LAUNCHED();
+            k_select_survivors_big<<<(unsigned)nqc, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids,
+                                                                                 topk, ids_out, score_out);
+        }
         else
             k_select_pairs<<<(unsigned)nqc, RR_THREADS, list_smem, st>>>(q0, L, h->pair_base.p, h->pair_key.p, h->pair_len.p,
                                                                          h->pair_seg.p, h->ids_sorted.p, h->scores.p, qk.qids,

@@ -98,6 +98,7 @@ k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     const int64_t nmine = nunits > gw ? (nunits - gw + W - 1) / W : 0;   // units gw + k * W
     if (nmine == 0) return;
     unsigned long long rows_staged = 0;
+    SurvivorSink sink;
 
     // record of the next unit, loaded one unit ahead: lane j < 16 keeps query j, every lane one first-window id and
     // the thresholds of the four queries its accumulators belong to
@@ -237,8 +238,7 @@ k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
                 for (int e = 0; e < 2; ++e) {
                     double v = acc[nb][0][e] + acc[nb][1][e];
                     if (ANGULAR) v = v / (c_qn[nb][e] * xnr);
-                    if (row < len && nb < nb_used && c_ok[nb][e] && v >= c_tau[nb][e])
-                        keep_survivor(flt, c_q[nb][e], v, __ldg(ids_sorted + bstart + row));
+                    sink.push(flt, row < len && nb < nb_used && c_ok[nb][e] && v >= c_tau[nb][e], c_q[nb][e], bstart + (uint32_t)row, v, lane);
                 }
         };
 
@@ -256,6 +256,7 @@ k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
             }
         }
     }
+    sink.flush(flt, lane);
     if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], rows_staged); }
 }
 
@@ -278,6 +279,7 @@ k_score_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     const uint32_t nunits = *nunits_p;
     const uint32_t W = gridDim.x * U8_WARPS;
     unsigned rows_staged = 0, nmine = 0;
+    SurvivorSink sink;
     for (uint32_t u = blockIdx.x * U8_WARPS + warp; u < nunits; u += W) {
         const UnitRec* r = units + u;
         const uint32_t bstart = __ldg(&r->bstart);
@@ -372,13 +374,358 @@ k_score_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                             double v = (double)dot;
                             if (ANGULAR) { v = v / (c_qn[nb][e] * xnr[rr]); keep = v >= c_tau[nb][e]; }
                             else keep = dot >= c_taui[nb][e];
-                            if (keep && row < len && (nb == 0 || two_blocks))
-                                keep_survivor(flt, c_q[nb][e], v, __ldg(ids_sorted + bstart + row));
+                            sink.push(flt, keep && row < len && (nb == 0 || two_blocks), c_q[nb][e], bstart + (uint32_t)row, v, lane);
                         }
             }
         }
     }
+    sink.flush(flt, lane);
     if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], (unsigned long long)rows_staged); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_score_u8s — the same computation as k_score_u8i with rows and unit records streamed through shared memory.
+// k_score_u8i keeps one id window (32 rows) of loads in flight per warp and waits for it before it multiplies: with
+// ~2 us from request to data it is latency-bound even at 24 warps per SM (ncu: 40 % of the samples on the first use of
+// a loaded row).  Here every thread copies its own 16-byte chunks with cp.async into a per-warp ring of US_D tiles (no
+// registers held while the data is in flight; a thread only reads back what it copied itself) and the ring keeps
+// running across unit boundaries: the producer side of the warp is US_D - 1 tiles — often several units — ahead of its
+// consumer side.  The unit records are copied the same way, US_D units ahead of the producer, into a ring of US_R
+// records that both sides read; id windows beyond the first (which rides in the record) are requested three windows
+// ahead, the next unit's query operand and thresholds one unit ahead.
+// cp.async groups: iteration s commits one group = tile s (+ possibly one record); the wait before tile c is consumed
+// leaves the US_D - 1 younger groups pending, so at the top of iteration s everything committed up to s - US_D is
+// complete — a record requested US_D production steps before its unit is opened has arrived.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int US_D = 5;                // tile ring depth, tiles of 16 rows (2 KB each)
+constexpr int US_R = 2 * US_D;         // record ring depth: records of units [consumer's, producer's + US_D] are live
+constexpr int US_REC_CHUNKS = sizeof(UnitRec) / 16;
+constexpr int US_CTAS = 2;             // CTAs of 8 warps per SM (<= 128 registers)
+constexpr size_t US_WARP_SMEM = (size_t)US_D * 4 * 32 * 16 + (size_t)US_R * sizeof(UnitRec);
+constexpr size_t US_SMEM = U8_WARPS * US_WARP_SMEM;
+static_assert(US_CTAS * US_SMEM <= 227 * 1024, "two CTAs per SM");
+static_assert(US_REC_CHUNKS <= 32, "one lane per 16-byte chunk of a record");
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+template <bool ANGULAR>
+__global__ void __launch_bounds__(U8_WARPS * 32, US_CTAS)
+k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
+            const double* __restrict__ qnorm, const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p,
+            const int32_t* __restrict__ ids_sorted, Filter flt, unsigned long long* __restrict__ stat) {
+    extern __shared__ __align__(16) unsigned char us_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    unsigned char* wbase = us_smem + (size_t)warp * US_WARP_SMEM;
+    uint4* ring = reinterpret_cast<uint4*>(wbase) + lane;                 // slot s, vector j: ring[(4 s + j) * 32]
+    UnitRec* recs = reinterpret_cast<UnitRec*>(wbase + (size_t)US_D * 4 * 32 * 16);
+    const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;
+    const bool two_chunks = pitch > 64;
+    const unsigned off0 = has0 ? 16u * t : 0u, off1 = has1 ? 64u + 16u * t : 0u;   // clamped, see k_score_u8d
+    const int64_t nunits = *nunits_p;
+    const int64_t W = (int64_t)gridDim.x * U8_WARPS;
+    const int64_t u0 = (int64_t)blockIdx.x * U8_WARPS + warp;
+    const int64_t nmine = nunits > u0 ? (nunits - u0 + W - 1) / W : 0;     // this warp's units: u0 + k W, k < nmine
+    if (nmine == 0) return;
+    unsigned rows_staged = 0;
+    SurvivorSink sink;
+
+    // record k -> ring slot k % US_R (joins the cp.async group that is committed next)
+    auto rec_request = [&](int64_t k) {
+        if (k < nmine && lane < US_REC_CHUNKS)
+            cp_async16(reinterpret_cast<unsigned char*>(&recs[k % US_R]) + 16 * lane,
+                       reinterpret_cast<const unsigned char*>(units + (u0 + k * W)) + 16 * lane);
+    };
+    for (int k = 0; k <= US_D; ++k) rec_request(k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+    // ---- producer side: row copies, US_D - 1 tiles ahead -----------------------------------------------------------
+    auto win_load = [&](const UnitRec* r, int w) {       // ids of rows [32w, 32w + 32) of the record's bucket, 0 past the end
+        const int len = (int)r->len;
+        return 32 * w < len ? __ldg(ids_sorted + r->bstart + min(32 * w + lane, len - 1)) : 0;
+    };
+    int64_t pk = 0;                    // unit being produced
+    int p_tile = 0, p_len = (int)recs[0].len;
+    int p_w0 = recs[0].ids0[lane], p_w1 = win_load(&recs[0], 1), p_w2 = win_load(&recs[0], 2), p_w3 = win_load(&recs[0], 3);
+    int nx_w1 = 0, nx_w2 = 0, nx_w3 = 0;                  // windows 1..3 of unit pk + 1
+    if (nmine > 1) { nx_w1 = win_load(&recs[1], 1); nx_w2 = win_load(&recs[1], 2); nx_w3 = win_load(&recs[1], 3); }
+    auto issue = [&](int slot) {
+        if (pk < nmine) {
+            uint4* dst = ring + (size_t)slot * (4 * 32);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int row = min(16 * p_tile + 8 * rr + g, p_len - 1);
+                const unsigned char* xp = X8 + (size_t)__shfl_sync(0xffffffffu, p_w0, row & 31) * pitch;
+                cp_async16(dst + (2 * rr) * 32, xp + off0);
+                cp_async16(dst + (2 * rr + 1) * 32, xp + off1);
+            }
+            ++p_tile;
+            if (16 * p_tile >= p_len) {                          // unit done: open the next one
+                ++pk;
+                p_tile = 0;
+                rec_request(pk + US_D);                          // arrives US_D production steps before it is opened
+                if (pk < nmine) {
+                    __syncwarp();                                // records copied by other lanes (complete: see header)
+                    const UnitRec* r = &recs[pk % US_R];
+                    p_len = (int)r->len;
+                    p_w0 = r->ids0[lane]; p_w1 = nx_w1; p_w2 = nx_w2; p_w3 = nx_w3;
+                    if (pk + 1 < nmine) {
+                        const UnitRec* rn = &recs[(pk + 1) % US_R];
+                        nx_w1 = win_load(rn, 1); nx_w2 = win_load(rn, 2); nx_w3 = win_load(rn, 3);
+                    }
+                }
+            } else if (!(p_tile & 1)) {                          // next id window of this unit
+                p_w0 = p_w1; p_w1 = p_w2; p_w2 = p_w3;
+                p_w3 = win_load(&recs[pk % US_R], (p_tile >> 1) + 3);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < US_D - 1; ++s) issue(s);
+
+    // ---- consumer side ----------------------------------------------------------------------------------------------
+    uint4 bq_nx[2][2];                 // query operand / thresholds / norms of the unit after the current one
+    double tau_nx[2][2], qn_nx[2][2];
+    int qj_nx[2][2];
+    auto stage2 = [&](int64_t k) {
+        const UnitRec* r = &recs[(k < nmine ? k : nmine - 1) % US_R];
+        const int m = (int)r->m;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const unsigned char* qp = Q8 + (size_t)r->q[8 * nb + g] * U8_QPITCH + 16 * t;     // slots >= m repeat the last query
+            bq_nx[nb][0] = ldg_u4(qp);
+            bq_nx[nb][1] = ldg_u4(qp + 64);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * nb + 2 * t + e;
+                qj_nx[nb][e] = r->q[j];
+                tau_nx[nb][e] = j < m ? r->tau[j] : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
+                if (ANGULAR) qn_nx[nb][e] = __ldg(qnorm + qj_nx[nb][e]);
+            }
+        }
+    };
+    stage2(0);
+    int consumed = 0;
+    for (int64_t k = 0; k < nmine; ++k) {
+        __syncwarp();                                            // records are copied by other lanes
+        const UnitRec* r = &recs[k % US_R];
+        const uint32_t bstart = r->bstart;
+        const int len = (int)r->len;
+        const bool two_blocks = r->m > 8;
+        uint4 bq[2][2];
+        int c_q[2][2], c_taui[2][2];
+        double c_tau[2][2], c_qn[2][2];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            bq[nb][0] = bq_nx[nb][0]; bq[nb][1] = bq_nx[nb][1];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                c_q[nb][e] = qj_nx[nb][e];
+                const double tv = tau_nx[nb][e];
+                c_tau[nb][e] = tv;
+                c_qn[nb][e] = ANGULAR ? qn_nx[nb][e] : 1.0;
+                // a dot product of bytes is below 2^31 - 1: INT_MAX masks the slot
+                c_taui[nb][e] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
+            }
+        }
+        rows_staged += (unsigned)len;
+        if (k + 1 < nmine) stage2(k + 1);                        // its record is in the ring since before unit k was produced
+        for (int tile = 0; 16 * tile < len; ++tile) {
+            issue((consumed + US_D - 1) % US_D);
+            asm volatile("cp.async.wait_group %0;" ::"n"(US_D - 1) : "memory");
+            const uint4* src = ring + (size_t)(consumed % US_D) * (4 * 32);
+            uint4 a[2][2];
+            a[0][0] = src[0]; a[0][1] = src[32]; a[1][0] = src[64]; a[1][1] = src[96];
+            consumed++;
+            int acc[2][4];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[nb][i] = 0;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c == 1 && !two_chunks) break;
+                imma_u8(acc[0], a[0][c].x, a[1][c].x, a[0][c].y, a[1][c].y, bq[0][c].x, bq[0][c].y);
+                imma_u8(acc[0], a[0][c].z, a[1][c].z, a[0][c].w, a[1][c].w, bq[0][c].z, bq[0][c].w);
+                if (two_blocks) {
+                    imma_u8(acc[1], a[0][c].x, a[1][c].x, a[0][c].y, a[1][c].y, bq[1][c].x, bq[1][c].y);
+                    imma_u8(acc[1], a[0][c].z, a[1][c].z, a[0][c].w, a[1][c].w, bq[1][c].z, bq[1][c].w);
+                }
+            }
+            double xnr[2] = {1.0, 1.0};
+            if (ANGULAR) {
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    unsigned sq = 0;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        unsigned sc = 0;
+                        sc = __dp4a(a[rr][c].x, a[rr][c].x, sc); sc = __dp4a(a[rr][c].y, a[rr][c].y, sc);
+                        sc = __dp4a(a[rr][c].z, a[rr][c].z, sc); sc = __dp4a(a[rr][c].w, a[rr][c].w, sc);
+                        if (c == 0 ? has0 : has1) sq += sc;
+                    }
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                    xnr[rr] = sqrt((double)sq);
+                }
+            }
+            // c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int row = 16 * tile + 8 * rr + g;
+                        const int dot = acc[nb][2 * rr + e];
+                        bool keep;
+                        double v = (double)dot;
+                        if (ANGULAR) { v = v / (c_qn[nb][e] * xnr[rr]); keep = v >= c_tau[nb][e]; }
+                        else keep = dot >= c_taui[nb][e];
+                        sink.push(flt, keep && row < len && (nb == 0 || two_blocks), c_q[nb][e], bstart + (uint32_t)row, v, lane);
+                    }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    sink.flush(flt, lane);
+    if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], (unsigned long long)rows_staged); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_threshold_u8i — the threshold samples (see k_threshold, rerank_bm.cu) for byte rows and byte queries on the integer
+// tensor pipe: one warp per (query, sampled table), the query in column 0 of the B operand (the other 7 columns are 0),
+// 16 rows per IMMA tile exactly as in k_score_u8i, so a sample row costs 1/20 of the instructions of the DP4A /
+// shuffle-reduction form and the kernel is bound by the row gather alone.  The dot products are the exact integers the
+// scoring kernel will produce; cosines are computed with the same operations.
+// ---------------------------------------------------------------------------------------------------------
+template <bool ANGULAR>
+__global__ void __launch_bounds__(RR_THREADS)
+k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
+                const double* __restrict__ qnorm, int64_t q0, int64_t nqc, int L, int NT, const uint32_t* __restrict__ pair_base,
+                const unsigned long long* __restrict__ pair_key_unsorted, const uint32_t* __restrict__ pair_len,
+                const int32_t* __restrict__ ids_sorted, const int32_t* __restrict__ qids, int self_exclude, int K,
+                double* __restrict__ tl_keys, int* __restrict__ tl_ids, int* __restrict__ tl_cnt) {
+    extern __shared__ double rsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double* mykeys = rsm + (size_t)warp * K;
+    int* myids = reinterpret_cast<int*>(rsm + (size_t)RR_WARPS * K) + (size_t)warp * K;
+    const int64_t wid = (int64_t)blockIdx.x * RR_WARPS + warp;
+    if (wid >= nqc * NT) return;
+    const int64_t ql = wid / NT;
+    const int sample = (int)(wid % NT);
+    const int64_t q = q0 + ql;
+    const int qid = qids ? qids[q] : INT32_MIN;
+    const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
+    const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;
+    const bool two_chunks = pitch > 64;
+    const unsigned off0 = has0 ? 16u * t : 0u, off1 = has1 ? 64u + 16u * t : 0u;   // clamped, see k_score_u8d
+    // B operand: column g = 0 is the query, the rest 0
+    uint4 bq0 = make_uint4(0, 0, 0, 0), bq1 = make_uint4(0, 0, 0, 0);
+    if (g == 0) {
+        const unsigned char* qp = Q8 + (size_t)q * U8_QPITCH + 16 * t;            // zero beyond column d
+        bq0 = ldg_u4(qp);
+        bq1 = ldg_u4(qp + 64);
+    }
+    const double qn = ANGULAR ? __ldg(qnorm + q) : 1.0;
+    // the sample-th table (among the first 32) in which the query probes something
+    const uint32_t p_mine = lane < L ? pair_base[ql * L + lane] : 0u;
+    const uint32_t p_next = lane < L ? pair_base[ql * L + lane + 1] : 0u;
+    uint32_t nonempty = __ballot_sync(0xffffffffu, lane < L && p_next > p_mine);
+    for (int i = 0; i < sample && nonempty; ++i) nonempty &= nonempty - 1;
+    int count = 0;
+    double kth = 0.0;
+    if (nonempty) {
+        const uint32_t p = __shfl_sync(0xffffffffu, p_mine, __ffs(nonempty) - 1);
+        const uint32_t bstart = (uint32_t)(pair_key_unsorted[p] >> 32);
+        const int len = (int)pair_len[p];
+        const int32_t* bids = ids_sorted + bstart;
+        int idA = __ldg(bids + min(lane, len - 1));
+        for (int row0 = 0; row0 < len; row0 += 32) {                 // one id window = 2 tiles of 16 rows
+            int id_next = 0;
+            if (row0 + 32 < len) id_next = __ldg(bids + min(row0 + 32 + lane, len - 1));
+            uint4 a[2][2][2];                                        // [tile][row g / 8 + g][chunk]
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = min(row0 + 16 * tl + 8 * rr + g, len - 1);
+                    const unsigned char* xp = X8 + (size_t)__shfl_sync(0xffffffffu, idA, row - row0) * pitch;
+                    a[tl][rr][0] = ldg_u4(xp + off0);
+                    a[tl][rr][1] = ldg_u4(xp + off1);
+                }
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl) {
+                if (row0 + 16 * tl >= len) break;                    // warp-uniform
+                int acc[4] = {0, 0, 0, 0};
+                imma_u8(acc, a[tl][0][0].x, a[tl][1][0].x, a[tl][0][0].y, a[tl][1][0].y, bq0.x, bq0.y);
+                imma_u8(acc, a[tl][0][0].z, a[tl][1][0].z, a[tl][0][0].w, a[tl][1][0].w, bq0.z, bq0.w);
+                if (two_chunks) {
+                    imma_u8(acc, a[tl][0][1].x, a[tl][1][1].x, a[tl][0][1].y, a[tl][1][1].y, bq1.x, bq1.y);
+                    imma_u8(acc, a[tl][0][1].z, a[tl][1][1].z, a[tl][0][1].w, a[tl][1][1].w, bq1.z, bq1.w);
+                }
+                double xnr[2] = {1.0, 1.0};
+                if (ANGULAR) {
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        unsigned sq = 0;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            unsigned sc = 0;
+                            sc = __dp4a(a[tl][rr][c].x, a[tl][rr][c].x, sc); sc = __dp4a(a[tl][rr][c].y, a[tl][rr][c].y, sc);
+                            sc = __dp4a(a[tl][rr][c].z, a[tl][rr][c].z, sc); sc = __dp4a(a[tl][rr][c].w, a[tl][rr][c].w, sc);
+                            if (c == 0 ? has0 : has1) sq += sc;
+                        }
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                        xnr[rr] = sqrt((double)sq);
+                    }
+                }
+                // lanes t = 0 hold column 0: acc[0] = row g, acc[2] = row 8 + g
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = row0 + 16 * tl + 8 * rr + g;
+                    double lb = (double)acc[2 * rr];
+                    if (ANGULAR) { lb = lb / (qn * xnr[rr]); lb -= 8.0 * 1.1102230246251565e-16 * fabs(lb); }
+                    const int id = __shfl_sync(0xffffffffu, idA, min(row, len - 1) - row0);
+                    bool ok = t == 0 && row < len && lb == lb && !(excl && id == qid);
+                    if (ok && count == K) ok = lb >= kth;
+                    uint32_t todo = __ballot_sync(0xffffffffu, ok);
+                    while (todo) {                                   // rare once the list is full
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const double lb_s = __shfl_sync(0xffffffffu, lb, src);
+                        const int id_s = __shfl_sync(0xffffffffu, id, src);
+                        if (count == K && !better(lb_s, id_s, mykeys[K - 1], myids[K - 1])) continue;
+                        warp_insert(mykeys, myids, count, K, lb_s, id_s, lane);      // rows of one bucket are distinct
+                        if (count == K) kth = mykeys[K - 1];
+                    }
+                }
+            }
+            idA = id_next;
+        }
+    }
+    __syncwarp();
+    for (int r = lane; r < count; r += 32) {
+        tl_keys[wid * K + r] = mykeys[r];
+        tl_ids[wid * K + r] = myids[r];
+    }
+    if (lane == 0) tl_cnt[wid] = count;
+}
+
+void launch_threshold_u8i(dpf_index* h, bool angular, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk, size_t list_smem) {
+    const unsigned grid = (unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS);
+    auto go = [&](auto kern) {
+        kern<<<grid, RR_THREADS, list_smem, h->stream>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, h->Q8.p, h->qnorm8.p, q0, nqc, h->cfg.L, NT,
+                                                         h->pair_base.p, h->pair_key.p, h->pair_len.p, h->ids_sorted.p, qids,
+                                                         h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p);
+    };
+    if (angular) go(k_threshold_u8i<true>); else go(k_threshold_u8i<false>);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -420,7 +767,17 @@ void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const 
             kern<<<h->num_sms * (angular ? U8_INT_CTAS - 1 : U8_INT_CTAS), U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, units, nunits_p,
                                                                    h->ids_sorted.p, flt, bm_stat);
         };
-        if (angular) launch(k_score_u8i<true>); else launch(k_score_u8i<false>);
+        const char* ev = getenv("DPF_U8I_KERNEL");
+        if (ev && ev[0] == 'l') {                                  // =lean: the occupancy-based variant
+            if (angular) launch(k_score_u8i<true>); else launch(k_score_u8i<false>);
+        } else {
+            auto launch_s = [&](auto kern) {
+                DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US_SMEM));
+                kern<<<h->num_sms * US_CTAS, U8_WARPS * 32, US_SMEM, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, units, nunits_p,
+                                                                         h->ids_sorted.p, flt, bm_stat);
+            };
+            if (angular) launch_s(k_score_u8s<true>); else launch_s(k_score_u8s<false>);
+        }
     } else {
         auto launch = [&](auto kern) {
             kern<<<h->num_sms, U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->cfg.d, Qd, units, nunits_p, h->ids_sorted.p, flt, bm_stat);

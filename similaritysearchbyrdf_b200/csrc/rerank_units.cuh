@@ -44,19 +44,54 @@ static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes
 // only keep a score that can still be among the query's best k: before scoring, k_threshold scores the rows of the
 // first buckets each query probes (its own bucket in the first tables) and takes the k-th best of them, minus a
 // rounding allowance, as tau[q] — k distinct rows score >= tau, hence no row below tau can be in the result.  The
-// kernels append (score, id) of the rows with score >= tau to the query's survivor list (a few hundred entries);
-// k_select_survivors finishes.  The result is exactly the top k of all candidates.
+// kernels emit (query, row, score) of the rows with score >= tau (a few hundred per query, SurvivorSink);
+// k_scatter_survivors sorts them into per-query lists and k_select_survivors finishes.  The result is exactly the top k of all candidates.
+struct __align__(16) SurvRec {
+    int32_t q;             // query, or -1 for an unused slot
+    uint32_t pos;          // position of the row in ids_sorted
+    double score;
+};
 struct Filter {
-    uint32_t* cnt;         // per query of the chunk: survivors appended so far
+    uint32_t* cnt;         // per query: survivors in its list so far
     const uint32_t* base;  // per query: start of its survivor list (capacity = all its bucket entries)
     double* s_score;
     int32_t* s_id;
+    SurvRec* pool;         // survivors in the order the scoring warps found them, blocks of SURV_BLOCK per warp
+    uint32_t* pool_cursor;
 };
-__device__ __forceinline__ void keep_survivor(const Filter& f, int q, double score, int id) {
-    const uint32_t at = f.base[q] + atomicAdd(f.cnt + q, 1u);
-    f.s_score[at] = score;
-    f.s_id[at] = id;
-}
+constexpr int SURV_BLOCK = 256;
+
+// Per-warp survivor output.  An append straight into the query's list needs the old value of a global atomic before
+// it can store: the scoring warp sits out a full memory round trip per survivor (measured: 22 % of k_score_u8s).
+// Instead the warp writes (query, row position, score) records into blocks it reserves from one pool — one atomic per
+// 256 survivors — and k_scatter_survivors, a streaming kernel with parallelism to hide that latency, moves the
+// records into the per-query lists.  push() must be called by all 32 lanes.
+struct SurvivorSink {
+    uint32_t wpos = 0;
+    int wleft = 0;
+    __device__ __forceinline__ void push(const Filter& f, bool keep, int q, uint32_t pos, double score, int lane) {
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (!mask) return;
+        const int n = __popc(mask);
+        if (n > wleft) {                                   // open a new block; the rest of the old one stays unused
+            if (lane < wleft) f.pool[wpos + lane].q = -1;
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(f.pool_cursor, (uint32_t)SURV_BLOCK);
+            wpos = __shfl_sync(0xffffffffu, b, 0);
+            wleft = SURV_BLOCK;
+        }
+        if (keep) {
+            SurvRec r;
+            r.q = q; r.pos = pos; r.score = score;
+            f.pool[wpos + __popc(mask & ((1u << lane) - 1u))] = r;
+        }
+        wpos += n;
+        wleft -= n;
+    }
+    __device__ __forceinline__ void flush(const Filter& f, int lane) {
+        for (int i = lane; i < wleft; i += 32) f.pool[wpos + i].q = -1;
+    }
+};
 
 constexpr size_t SS_WARP_BYTES = (size_t)SS_STAGES * SS_ROWS * SS_PITCH * sizeof(double) + 2 * sizeof(UnitRec) + 2 * SS_WIN_COPY * 4 + 32;
 constexpr size_t SS_SMEM = SS_WARPS * ((SS_WARP_BYTES + 15) / 16 * 16);
@@ -64,6 +99,8 @@ constexpr size_t SS_SMEM = SS_WARPS * ((SS_WARP_BYTES + 15) / 16 * 16);
 
 // rerank_u8.cu: scores of every unit from the uint8 compact store (register gather, DMMA or IMMA)
 bool score_u8_usable(const dpf_index* h);
+void launch_threshold_u8i(dpf_index* h, bool angular, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
+                          size_t list_smem);                          // threshold samples on the integer tensor pipe
 int u8_query_pitch();                                                      // row pitch of dpf_index::Q8
 void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq);       // queries -> uint8 copy if they are bytes
 void launch_score_u8(dpf_index* h, const double* Qd, const void* units, const uint32_t* nunits_p, bool angular,
