@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the scoring kernel on this workload (ncu --set full
 # captures summarised under profiles/); kernels without a capture report null
 NCU_TRAFFIC_BYTES = {"k_score_stream": 46_793_233_000 + 4_166_460_000,       # profiles/r1_ncu_full_k_score_stream.csv
-                     "k_score_u8i": 3_160_577_000 + 103_093_000}             # profiles/r1_ncu_full_u8_pipeline.csv
+                     "k_score_u8s": 2_912_332_000 + 60_095_000}              # profiles/r1_ncu_full_u8_pipeline.csv
 
 METRIC_NAME = "batch kNN queries/sec at fixed recall@10"
 UNIT = "queries/s"
@@ -360,7 +360,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     # The re-rank is bucket-major: every leaf bucket probed by the batch is scored once per unit of <= 16 queries that
     # probe it.  `achieved` = the bytes one launch of the scoring kernel has to move for that: staged rows x
-    # (row bytes of the compact store + 4 B id) + one record per unit + the query operand of each unit + 12 B per
+    # (row bytes of the compact store + 4 B id) + one record per unit + the query operand of each unit + 16 B per
     # survivor (or 8 B per score on the dense FP64 pipeline), divided by the kernel's time from CUDA events.
     # `survey_8d` restates SURVEY 8(d)'s per-candidate figure (nC_q x (8d + 4) B per query, FP64 rows fetched once per
     # (query, unique candidate)) for comparison: it is far above the HBM peak precisely because the kernel neither
@@ -379,10 +379,10 @@ def run_ours(args):
     row_bytes = int(qstats["store_row_bytes"])
     filtered = bm and store_kind == "u8"
     if bm:
-        kernel = ("k_score_u8i" if int_queries else "k_score_u8d") if filtered else "k_score_stream"
+        kernel = ("k_score_u8s" if int_queries else "k_score_u8d") if filtered else "k_score_stream"
         units = int(qstats["bm_runs"])
         q_operand = 16 * (128 if (filtered and int_queries) else 8 * d)
-        out_bytes = int(qstats["bm_survivors"]) * 12 if filtered else int(qstats["last_cand_with_dups"]) * 8
+        out_bytes = int(qstats["bm_survivors"]) * 16 if filtered else int(qstats["last_cand_with_dups"]) * 8
         kernel_bytes = int(qstats["bm_rows_staged"]) * (row_bytes + 4) + units * (unit_rec_bytes + q_operand) + out_bytes
     else:
         kernel = "k_rerank_units"

@@ -773,9 +773,11 @@ k_select_survivors_big(int64_t q0, int64_t nqc, Filter flt, const int32_t* __res
     extern __shared__ double rsm[];
     __shared__ int s_counts[RR_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q = q0 + blockIdx.x;
+    for (int64_t ql = blockIdx.x; ql < nqc; ql += gridDim.x) {       // a few CTAs look through all queries for the long lists
+    const int64_t q = q0 + ql;
     const uint32_t n = flt.cnt[q];
-    if (n <= SEL_BIG) return;                // CTA-uniform
+    if (n <= SEL_BIG) continue;              // CTA-uniform
+    __syncthreads();                         // the lists in shared memory are reused
     double* lkeys = rsm;
     int* lids = reinterpret_cast<int*>(rsm + (size_t)RR_WARPS * K);
     double* mykeys = lkeys + (size_t)warp * K;
@@ -830,6 +832,7 @@ k_select_survivors_big(int64_t q0, int64_t nqc, Filter flt, const int32_t* __res
             }
             if (bl >= 0) last = bi;
         }
+    }
     }
 }
 
@@ -1112,7 +1115,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         if (use_u8) {
             k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, ids_out,
                                                                      score_out, bm_stat); DPF_LAUNCHED();
-            k_select_survivors_big<<<(unsigned)nqc, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids,
+            k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, (int64_t)h->num_sms * 2), RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids,
                                                                                  topk, ids_out, score_out);
         }
         else
