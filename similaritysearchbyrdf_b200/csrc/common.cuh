@@ -186,6 +186,7 @@ struct dpf_index {
     dpf::DevBuf<char> surv_pool;               // SurvRec blocks written by the scoring warps
     dpf::DevBuf<double> bm_tau;                // per query: score threshold
     dpf::DevBuf<uint32_t> bm_scnt, bm_sbase;   //            survivors so far, start of its list
+    dpf::DevBuf<uint32_t> bm_big;              // queries whose survivor list is long
     dpf::DevBuf<double> bm_tl_keys;            // threshold sample lists: nq x NT x k
     dpf::DevBuf<int> bm_tl_ids, bm_tl_cnt;
     dpf::DevBuf<uint32_t> bm_flag, bm_run_start, bm_ucnt, bm_counts;   // runs / units of the sorted pairs

@@ -726,7 +726,8 @@ constexpr uint32_t SEL_BIG = 1024;
 
 __global__ void __launch_bounds__(RR_THREADS)
 k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
-                   int32_t* __restrict__ ids_out, double* __restrict__ score_out, unsigned long long* __restrict__ stat) {
+                   int32_t* __restrict__ ids_out, double* __restrict__ score_out, unsigned long long* __restrict__ stat,
+                   uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
     extern __shared__ double rsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* mykeys = rsm + (size_t)warp * K;
@@ -736,7 +737,10 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
     const int64_t q = q0 + ql;
     const uint32_t n = flt.cnt[q];
     if (lane == 0) atomicAdd(&stat[2], (unsigned long long)n);
-    if (n > SEL_BIG) return;                 // a weak threshold left a long list: k_select_survivors_big (a CTA per query)
+    if (n > SEL_BIG) {                       // a weak threshold left a long list: k_select_survivors_big (a CTA per query)
+        if (lane == 0) big_list[atomicAdd(big_count, 1u)] = (uint32_t)ql;
+        return;
+    }
     const double* sc = flt.s_score + flt.base[q];
     const int32_t* si = flt.s_id + flt.base[q];
     const int qid = qids ? qids[q] : INT32_MIN;
@@ -768,15 +772,16 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
 // the same for the queries whose list is long (few: those whose sampled buckets held fewer than k rows, or rows far
 // from the query): one CTA per query, the warps take interleaved chunks of the list, then the per-warp lists are merged
 __global__ void __launch_bounds__(RR_THREADS)
-k_select_survivors_big(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
-                       int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
+k_select_survivors_big(int64_t q0, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
+                       int32_t* __restrict__ ids_out, double* __restrict__ score_out, const uint32_t* __restrict__ big_list,
+                       const uint32_t* __restrict__ big_count) {
     extern __shared__ double rsm[];
     __shared__ int s_counts[RR_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t ql = blockIdx.x; ql < nqc; ql += gridDim.x) {       // a few CTAs look through all queries for the long lists
-    const int64_t q = q0 + ql;
+    const uint32_t nbig = *big_count;
+    for (uint32_t bi_ = blockIdx.x; bi_ < nbig; bi_ += gridDim.x) {  // the long lists k_select_survivors set aside
+    const int64_t q = q0 + big_list[bi_];
     const uint32_t n = flt.cnt[q];
-    if (n <= SEL_BIG) continue;              // CTA-uniform
     __syncthreads();                         // the lists in shared memory are reused
     double* lkeys = rsm;
     int* lids = reinterpret_cast<int*>(rsm + (size_t)RR_WARPS * K);
@@ -1113,10 +1118,12 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             k_scatter_survivors<<<h->num_sms * 8, 256, 0, st>>>(flt, h->ids_sorted.p); DPF_LAUNCHED();
         }
         if (use_u8) {
+            h->bm_big.reserve((size_t)nqc + 1);                  // [0] = count, then the queries with long lists
+            DPF_CUDA(cudaMemsetAsync(h->bm_big.p, 0, sizeof(uint32_t), st));
             k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, ids_out,
-                                                                     score_out, bm_stat); DPF_LAUNCHED();
-            k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, (int64_t)h->num_sms * 2), RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids,
-                                                                                 topk, ids_out, score_out);
+                                                                     score_out, bm_stat, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
+            k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
+                q0, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, ids_out, score_out, h->bm_big.p + 1, h->bm_big.p);
         }
         else
             k_select_pairs<<<(unsigned)nqc, RR_THREADS, list_smem, st>>>(q0, L, h->pair_base.p, h->pair_key.p, h->pair_len.p,
