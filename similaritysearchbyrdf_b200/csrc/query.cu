@@ -22,7 +22,7 @@ namespace dpf {
 // pass A: upper bound of the candidate count per query (sum of distinct bucket sizes over tables)
 __global__ void __launch_bounds__(256)
 k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t nq,
-              int32_t* __restrict__ q_ub, unsigned long long* __restrict__ stat /* [0] nlz>28, [1] with-dups */,
+              int32_t* __restrict__ q_ub, unsigned long long* __restrict__ stat /* [0] nlz>28 */,
               uint32_t* __restrict__ pair_cnt /* nq x L distinct buckets per (query, table), may be null */) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -51,10 +51,7 @@ k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (lane == 0 && pair_cnt) pair_cnt[wid] = (uint32_t)nbuckets;
-    if (lane == 0 && total > 0) {
-        atomicAdd(&q_ub[q], total);
-        atomicAdd(&stat[1], (unsigned long long)total);
-    }
+    if (lane == 0 && total > 0) atomicAdd(&q_ub[q], total);      // (the batch total is the last scanned offset: no global counter)
 }
 
 // pass B: expansion + de-dup.  Persistent CTAs pull queries from a counter; bitmap in shared memory (SMEM_BM)
@@ -192,7 +189,7 @@ void probe_count_all(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
     DPF_CUDA(cudaMemcpyAsync(hstat, stat, sizeof(hstat), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaStreamSynchronize(st));
     h->stats[DPF_STAT_NLZ_GT28] = (int64_t)hstat[0];
-    h->stats[DPF_STAT_LAST_CAND_WITH_DUPS] = (int64_t)hstat[1];
+    h->stats[DPF_STAT_LAST_CAND_WITH_DUPS] = off_host[(size_t)nq];
 }
 
 // end of the chunk starting at q0 whose candidate upper bound fits `budget` ids (always at least one query)
