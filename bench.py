@@ -67,7 +67,7 @@ def config_dict(args, n_gpus):
         "n_vectors": args.n, "dim": args.d, "n_queries": args.nq, "topk": args.topk, "steps": args.qsteps,
         "rerank_metric": args.metric, "tables": 30, "chain_length": 32, "partition_bits": 3, "bucket_overflow": 500,
         "dir_node_size": 32, "probe": "dense multi-probe",
-        "partitioning": f"sub-indexes p%{n_gpus}==rank per GPU, vectors replicated" if n_gpus > 1 else "single GPU",
+        "partitioning": f"8 sub-indexes per table dealt to {n_gpus} GPUs by occupancy, vectors replicated" if n_gpus > 1 else "single GPU",
         "cache": "inputs larger than L2 (vector store 1.0 GB vs 126 MB L2); no explicit flush",
     }
 
@@ -175,8 +175,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to stdout: keep it to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / debug lines off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     metric = {"dot": B.METRIC_DOT, "angular": B.METRIC_ANGULAR, "l2": B.METRIC_L2}[args.metric]
 
@@ -193,6 +192,7 @@ def run_ours(args):
         Xd = torch.from_numpy(X).to(dev)
         Qd = torch.from_numpy(Q).to(dev)
         ix = DPFIndex(d=d, L=chain.shape[0], k=chain.shape[1], pb=Ap.shape[1], device=local, rank=rank, world=world)
+        ix.set_balanced_partition(world > 1)         # sub-indexes dealt to the GPUs by occupancy (same split on every rank)
         ix.set_family(A, chain)
         ix.set_partitioners(Ap)
         ix.set_stream(stream.cuda_stream)

@@ -153,6 +153,12 @@ int dpf_parse_sparse_file(const char* path, int64_t* indptr_out, int32_t* indice
 int dpf_save(dpf_handle h, const char* path);
 int dpf_load(const char* path, int32_t device, dpf_handle* out);
 
+/* ---- multi-GPU: which sub-indexes a rank owns.  Default: sub-index p of every table lives on GPU p mod world.  The
+ * content-based partition is skewed (sub-indexes hold 64k..224k of 1M ids in configs[1]), so with enable != 0 the first
+ * dense fit deals the sub-indexes to the GPUs by occupancy instead (largest first, to the least loaded GPU); every rank
+ * derives the same assignment from the replicated vectors.  Results are unaffected.  Call before fit. */
+int dpf_set_balanced_partition(dpf_handle h, int32_t enable);
+
 /* ---- multi-GPU: merge per-GPU top-k lists after the NCCL all-gather -----------------------
  * gathered_*_dev: G x nq x topk as produced by all-gathering dpf_query_topk_dense_dev outputs; duplicates of
  * one id (same vector reached through tables owned by different GPUs) are collapsed. */

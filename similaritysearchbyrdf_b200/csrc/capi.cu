@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" boundary declared in include/dpf.h.  Every entry point takes the handle's lock,
 // selects the handle's device, runs the device pipeline on the handle's stream and converts failures into
 // DPF_ERR_* codes (no exception leaves the library, nothing aborts the process).
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -226,6 +227,8 @@ int dpf_create(const dpf_config* cfg, dpf_handle* out) {
         DPF_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
         h->counters.reserve(64);
         h->occupancy.assign(1 << cfg->pb, 0.0);
+        for (int p = 0; p < (1 << cfg->pb); ++p)      // Partitioner scheme on G GPUs: sub-index p lives on GPU p mod G
+            if (cfg->world <= 1 || p % cfg->world == cfg->rank) h->own.w[p >> 5] |= 1u << (p & 31);
     } catch (const Error& e) {
         dpf_destroy(h);
         return e.code;
@@ -388,6 +391,48 @@ struct PhaseTrace {
     }
 };
 
+// dpf_set_balanced_partition: at the first fit, sub-indexes are dealt to the GPUs largest first, each to the GPU with the
+// fewest ids so far (occupancy summed over the tables).  Vectors and hash functions are replicated, so every rank
+// computes the same assignment from the same pids; it is then kept for the life of the handle.
+__global__ void __launch_bounds__(256) k_pid_histogram(const uint8_t* __restrict__ pids, int64_t n, int64_t ld, int L,
+                                                       unsigned long long* __restrict__ hist /* 256 */) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[pids[(int64_t)t * ld + i]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+    (void)L;
+}
+
+static void assign_balanced_partition(dpf_index* h, int64_t n_new) {
+    if (!h->balance_partition || h->own_fixed || h->cfg.world <= 1) return;
+    const int np = 1 << h->cfg.pb, G = h->cfg.world;
+    DevBuf<unsigned long long> hist;
+    hist.reserve(256);
+    DPF_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
+    const dim3 grid((unsigned)std::min<int64_t>((n_new + 255) / 256, 1024), h->cfg.L);
+    k_pid_histogram<<<grid, 256, 0, h->stream>>>(h->pids.p, n_new, h->key_ld, h->cfg.L, hist.p); DPF_LAUNCHED();
+    unsigned long long occ[256];
+    DPF_CUDA(cudaMemcpyAsync(occ, hist.p, sizeof(occ), cudaMemcpyDeviceToHost, h->stream));
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<int> order(np);
+    for (int p = 0; p < np; ++p) order[p] = p;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return occ[a] > occ[b]; });
+    std::vector<unsigned long long> load(G, 0);
+    h->own = OwnMask{};
+    for (int p : order) {
+        int best = 0;
+        for (int g = 1; g < G; ++g)
+            if (load[g] < load[best]) best = g;
+        load[best] += occ[p];
+        if (best == h->cfg.rank) h->own.w[p >> 5] |= 1u << (p & 31);
+    }
+    h->own_fixed = true;
+}
+
 static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_device) {
     require_ready(h, false);
     DPF_REQUIRE(n > 0 && X, DPF_ERR_INVALID, "empty fit");
@@ -416,6 +461,7 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     tr.mark("keys: allocate");
     hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
     tr.mark("hash");
+    if (h->n == 0) assign_balanced_partition(h, n);
     h->n += n;
     build_forest(h);
     tr.mark("forest");
@@ -424,6 +470,13 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     h->stats[DPF_STAT_SIZE] = h->n;
     DPF_CUDA(cudaStreamSynchronize(h->stream));
     end_profile(h);
+}
+
+int dpf_set_balanced_partition(dpf_handle h, int32_t enable) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "dpf_set_balanced_partition must be called before fit");
+        h->balance_partition = enable != 0;
+    });
 }
 
 int dpf_set_store_mode(dpf_handle h, int32_t mode) {

@@ -98,6 +98,12 @@ struct ForestView {
 
 enum : int { kMaxTables = 256, kMaxChain = 32, kMaxPb = 8 };
 
+// the sub-indexes (partition ids, < 2^pb <= 256) this handle owns on a multi-GPU box
+struct OwnMask {
+    uint32_t w[8];
+    __host__ __device__ bool has(int pid) const { return (w[pid >> 5] >> (pid & 31)) & 1u; }
+};
+
 // process-wide count of kernel launches issued by this library (reported through dpf_stats)
 extern unsigned long long g_launches;
 #define DPF_LAUNCHED() (++::dpf::g_launches)
@@ -118,6 +124,9 @@ struct dpf_index {
     std::string last_error;
     bool family_set = false, part_set = false, dense = true, fitted = false;
     int num_sms = 148;
+    dpf::OwnMask own{};                  // sub-indexes owned by this rank (all of them when world <= 1)
+    bool balance_partition = false;      // dpf_set_balanced_partition: ownership by occupancy instead of p % world
+    bool own_fixed = false;              // the balanced assignment is made once, at the first fit
 
     // hash functions
     dpf::DevBuf<double> A;        // P x d row-major

@@ -40,7 +40,7 @@ constexpr int CD_MAX_SMEM_BINS = 8192;
 template <bool SMEM>
 __global__ void __launch_bounds__(CD_THREADS)
 k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pids, int64_t n, int64_t ld, TreeParams tp,
-               int rank, int world, int32_t* __restrict__ cnt1) {
+               OwnMask own, int32_t* __restrict__ cnt1) {
     extern __shared__ int32_t hist[];
     const int t = blockIdx.y;
     const int bins = tp.R * tp.W;
@@ -52,7 +52,7 @@ k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pid
     const int64_t end = min(n, base + CD_CHUNK);
     for (int64_t i = base + threadIdx.x; i < end; i += CD_THREADS) {
         const int pid = pids[(int64_t)t * ld + i];
-        if (world > 1 && (pid % world) != rank) continue;
+        if (!own.has(pid)) continue;
         const int32_t h = keys[(int64_t)t * ld + i];
         const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
         const int local = ((pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1);
@@ -72,7 +72,7 @@ k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pid
 // bit above the field set so that a 1-bit stable pass moves them behind the owned ones
 __global__ void __launch_bounds__(256)
 k_make_sort_keys(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pids, int64_t n, int64_t ld,
-                 TreeParams tp, int t0, int rank, int world, int field_bits, uint32_t* __restrict__ sk,
+                 TreeParams tp, int t0, OwnMask own, int field_bits, uint32_t* __restrict__ sk,
                  uint32_t* __restrict__ sv) {
     const int tl = blockIdx.y;
     const int t = t0 + tl;
@@ -82,7 +82,7 @@ k_make_sort_keys(const int32_t* __restrict__ keys, const uint8_t* __restrict__ p
     const int32_t h = keys[(int64_t)t * ld + i];
     const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
     uint32_t code = (uint32_t)(((tl * tp.R + pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1));
-    if (world > 1 && (pid % world) != rank) code |= 1u << field_bits;
+    if (!own.has(pid)) code |= 1u << field_bits;
     sk[(int64_t)tl * n + i] = code;
     sv[(int64_t)tl * n + i] = (uint32_t)i;
 }
@@ -211,7 +211,8 @@ void build_forest(dpf_index* h) {
     const TreeParams tp = h->tp;
     const int L = h->cfg.L;
     const int64_t n = h->n, ld = h->key_ld;
-    const int world = h->cfg.world > 1 ? h->cfg.world : 1, rank = world > 1 ? h->cfg.rank : 0;
+    const int world = h->cfg.world > 1 ? h->cfg.world : 1;
+    const OwnMask own = h->own;
     DPF_REQUIRE(tp.W <= SP_MAXW, DPF_ERR_INVALID, "dirNodeSize above 256 is not supported");
     const int64_t ncodes = (int64_t)L * tp.R * tp.W;
     DPF_REQUIRE(ncodes < (1LL << 30), DPF_ERR_INVALID, "L * 2^pb * SEG * dirNodeSize too large");
@@ -229,10 +230,10 @@ void build_forest(dpf_index* h) {
             const dim3 grid((unsigned)((n + CD_CHUNK - 1) / CD_CHUNK), L);
             const int bins = tp.R * tp.W;
             if (bins <= CD_MAX_SMEM_BINS)
-                k_count_depth1<true><<<grid, CD_THREADS, bins * sizeof(int32_t), st>>>(h->keys.p, h->pids.p, n, ld, tp, rank,
-                                                                                      world, cnt1.p);
+                k_count_depth1<true><<<grid, CD_THREADS, bins * sizeof(int32_t), st>>>(h->keys.p, h->pids.p, n, ld, tp, own,
+                                                                                      cnt1.p);
             else
-                k_count_depth1<false><<<grid, CD_THREADS, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, rank, world, cnt1.p);
+                k_count_depth1<false><<<grid, CD_THREADS, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, own, cnt1.p);
             DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
         }
@@ -281,7 +282,7 @@ void build_forest(dpf_index* h) {
             const int64_t items = (int64_t)gt * n;
             h->sk0.reserve(items); h->sk1.reserve(items); h->sv0.reserve(items); h->sv1.reserve(items);
             const dim3 grid((unsigned)((n + 255) / 256), gt);
-            k_make_sort_keys<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, t0, rank, world, field_bits, h->sk0.p,
+            k_make_sort_keys<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, t0, own, field_bits, h->sk0.p,
                                                    h->sv0.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             uint32_t *k0 = h->sk0.p, *k1 = h->sk1.p, *v0 = h->sv0.p, *v1 = h->sv1.p;

@@ -12,7 +12,8 @@ namespace dpf {
 struct ProbeCtx {
     ForestView f;
     TreeParams tp;
-    int L, steps, probe_mode, rank, world, self_exclude;
+    int L, steps, probe_mode, world, self_exclude;
+    OwnMask own;       // this GPU's sub-forest
 };
 
 // bucket lookup for one probe key (RandomDrawTreeMap.java:940-994): empty slot -> nothing; leaf -> (ptr,cnt);
@@ -101,7 +102,7 @@ inline ProbeCtx make_ctx(dpf_index* h, int steps, int probe_mode) {
     c.steps = steps;
     c.probe_mode = probe_mode;
     c.world = h->cfg.world > 1 ? h->cfg.world : 1;
-    c.rank = c.world > 1 ? h->cfg.rank : 0;
+    c.own = h->own;
     c.self_exclude = h->cfg.self_exclude_small_ids;
     return c;
 }

@@ -55,7 +55,7 @@ k_probe_pairs(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
     const int np = 1 << c.tp.pb;
     for (int sub = 0; sub < np; ++sub) {
         if (__popc(sub ^ pid) > c.steps) continue;
-        if (c.world > 1 && (sub % c.world) != c.rank) continue;
+        if (!c.own.has(sub)) continue;
         bool leader;
         int ptr, cnt;
         warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);

@@ -99,6 +99,10 @@ class DPFIndex:
         Call before fit."""
         self._ck(self.lib.dpf_set_store_mode(self.h, mode))
 
+    def set_balanced_partition(self, on=True):
+        """Multi-GPU: deal the sub-indexes to the ranks by occupancy at the first fit instead of p % world."""
+        self._ck(self.lib.dpf_set_balanced_partition(self.h, 1 if on else 0))
+
     # ---- hash functions -------------------------------------------------------------------------------------
     def set_family(self, A, chain_idx, b=None, w=None):
         A, chain_idx = _f64(A), _i32(chain_idx)

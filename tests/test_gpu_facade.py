@@ -152,6 +152,48 @@ def test_full_size_properties_config2_sample():
     assert np.all(np.diff(sc, axis=1) >= 0)
 
 
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_balanced_partition_ranks_merge_to_the_unsharded_result(world):
+    """dpf_set_balanced_partition: sub-indexes dealt to the ranks by occupancy.  Every sub-index is owned by exactly one
+    rank (candidate sets are disjoint and their union is the unsharded set), the merged top-k equals the single-handle
+    result, and the load is no worse than p % world."""
+    import torch
+    X, Q = synth.config1(n=8000)
+    A, chain, Ap = U.make_functions(100)
+    Qs = np.concatenate([Q, X[:100] + 0.01])
+    nq, K = len(Qs), 10
+    full = U.make_index(100, A, chain, Ap, bucket_overflow=40)
+    full.fit_dense(X)
+    f_ids, f_sc = full.query_topk_dense(Qs, None, 1, K, B.METRIC_DOT)
+    f_off, f_cand = full.query_candidates_dense(Qs, None, 1)
+    loads = {}
+    for balanced in (False, True):
+        shards = [U.make_index(100, A, chain, Ap, bucket_overflow=40, rank=r, world=world) for r in range(world)]
+        per, cands, sizes = [], [], []
+        for s in shards:
+            s.set_balanced_partition(balanced)
+            s.fit_dense(X)
+            per.append(s.query_topk_dense(Qs, None, 1, K, B.METRIC_DOT))
+            cands.append(s.query_candidates_dense(Qs, None, 1))
+            sizes.append(sum(len(s.dump_buckets(t)[2]) for t in range(chain.shape[0])))
+        assert sum(sizes) == 8000 * chain.shape[0]                   # every (table, id) entry lives on exactly one rank
+        loads[balanced] = max(sizes)
+        g_ids = torch.from_numpy(np.stack([p[0] for p in per])).cuda()
+        g_sc = torch.from_numpy(np.stack([p[1] for p in per])).cuda()
+        m_ids = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+        m_sc = torch.empty((nq, K), dtype=torch.float64, device="cuda")
+        shards[0].merge_topk_dev(g_ids.data_ptr(), g_sc.data_ptr(), world, nq, K, B.METRIC_DOT, m_ids.data_ptr(), m_sc.data_ptr())
+        shards[0].sync()
+        torch.cuda.synchronize()
+        assert np.array_equal(m_ids.cpu().numpy(), f_ids)
+        assert np.array_equal(m_sc.cpu().numpy(), f_sc, equal_nan=True)
+        for i in range(nq):                                              # union of the ranks' candidate sets
+            u = np.unique(np.concatenate([c[1][c[0][i]:c[0][i + 1]] for c in cands]))
+            assert np.array_equal(u, f_cand[f_off[i]:f_off[i + 1]])
+    ideal = 8000 * chain.shape[0] / world
+    assert loads[True] <= max(1.02 * loads[False], 4 / 3 * ideal)           # greedy largest-first: within 4/3 of the optimum
+
+
 # ---- persist / reload (dpf_save / dpf_load) --------------------------------------------------------------------------
 def test_save_load_dense_roundtrip(tmp_path):
     """A reloaded index answers exactly like the one that was saved: same buckets, candidate sets, top-k, store kind."""
