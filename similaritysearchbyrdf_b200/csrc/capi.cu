@@ -601,6 +601,8 @@ static void topk_device(dpf_index* h, const double* Qd, int64_t nq, const int32_
     h->qpids.reserve((size_t)L * nq);
     hash_dense_any(h, Qd, nq, h->qkeys.p, h->qpids.p, nq);
     const QueryKeys qk{h->qkeys.p, nq, nq, qids_dev};
+    h->Q8_valid = false;
+    if (score_u8_usable(h) && (reinterpret_cast<uintptr_t>(Qd) & 15) == 0) prepare_queries_u8(h, Qd, nq);   // byte queries? (per batch)
     std::vector<int64_t> ub;
     probe_count_all(h, qk, steps, probe_mode, ub);
     reserve_candidate_scratch(h, ub);

@@ -151,6 +151,7 @@ struct dpf_index {
     dpf::DevBuf<unsigned char> Xc;
     dpf::DevBuf<unsigned char> Q8;      // uint8 copy of the current query batch, when every query value is a byte
     dpf::DevBuf<double> qnorm8;         //   and the queries' norms
+    dpf::DevBuf<int32_t> qsq8;          //   and squared norms (integers)
     bool Q8_valid = false;
     dpf::DevBuf<int64_t> sp_ptr;  // CSR store
     dpf::DevBuf<int32_t> sp_idx;
@@ -286,6 +287,8 @@ void rerank_topk(dpf_index* h, const double* Qd, int64_t q0, int64_t q1, int64_t
                  int32_t* ids_out, double* score_out);
 // bucket-major re-rank of queries [q0, q1) (rerank_bm.cu): top-k straight from the probe result, no candidate lists
 bool bucket_major_supported(const dpf_index* h, int metric, int topk);
+bool score_u8_usable(const dpf_index* h);                                  // rerank_u8.cu: byte store present and enabled
+void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq);       // sets h->Q8_valid when the batch is bytes
 void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1,
                        int64_t entries_ub, int topk, int metric, int32_t* ids_out, double* score_out);
 void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);

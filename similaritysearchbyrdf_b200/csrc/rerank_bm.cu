@@ -30,9 +30,13 @@ namespace dpf {
 bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
     const char* e = getenv("DPF_RERANK");
     if (e && e[0] == 'r') return false;                        // DPF_RERANK=rowmajor forces the row-major kernel
-    return h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 &&
-           (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
-           (metric == DPF_METRIC_DOT || metric == DPF_METRIC_ANGULAR) && topk <= RR_MAXK;   // d even: the queries are FP64 rows
+    if (!(h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 && (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
+          topk <= RR_MAXK))                                    // d even: the queries are FP64 rows moved in 16-byte pieces
+        return false;
+    if (metric == DPF_METRIC_DOT || metric == DPF_METRIC_ANGULAR) return true;
+    // squared L2 = |q|^2 + |x|^2 - 2 q.x cancels in floating point; it is exact — and then identical to the reference's
+    // sum of squared differences — only on the integer pipeline: byte rows and a batch of byte queries
+    return metric == DPF_METRIC_L2 && score_u8_usable(h) && h->Q8_valid;
 }
 
 // fill pass: pair i of (query q, table t) in (q, t, lane) order
@@ -725,7 +729,7 @@ k_scatter_survivors(Filter flt, const int32_t* __restrict__ ids_sorted) {
 constexpr uint32_t SEL_BIG = 1024;
 
 __global__ void __launch_bounds__(RR_THREADS)
-k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
+k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K, bool negate,
                    int32_t* __restrict__ ids_out, double* __restrict__ score_out, unsigned long long* __restrict__ stat,
                    uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
     extern __shared__ double rsm[];
@@ -765,14 +769,14 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
     }
     for (int r = lane; r < K; r += 32) {
         ids_out[q * K + r] = r < count ? myids[r] : -1;
-        score_out[q * K + r] = r < count ? mykeys[r] : __longlong_as_double(0x7ff8000000000000LL);
+        score_out[q * K + r] = r < count ? (negate ? -mykeys[r] : mykeys[r]) : __longlong_as_double(0x7ff8000000000000LL);
     }
 }
 
 // the same for the queries whose list is long (few: those whose sampled buckets held fewer than k rows, or rows far
 // from the query): one CTA per query, the warps take interleaved chunks of the list, then the per-warp lists are merged
 __global__ void __launch_bounds__(RR_THREADS)
-k_select_survivors_big(int64_t q0, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K,
+k_select_survivors_big(int64_t q0, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K, bool negate,
                        int32_t* __restrict__ ids_out, double* __restrict__ score_out, const uint32_t* __restrict__ big_list,
                        const uint32_t* __restrict__ big_count) {
     extern __shared__ double rsm[];
@@ -833,7 +837,7 @@ k_select_survivors_big(int64_t q0, Filter flt, const int32_t* __restrict__ qids,
             }
             if (lane == 0) {
                 ids_out[q * K + r] = bl >= 0 ? bi : -1;
-                score_out[q * K + r] = bl >= 0 ? bk : __longlong_as_double(0x7ff8000000000000LL);
+                score_out[q * K + r] = bl >= 0 ? (negate ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
             }
             if (bl >= 0) last = bi;
         }
@@ -1007,6 +1011,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     DPF_REQUIRE(h->h_table_base[L] < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: more than 2^32 forest entries");
     DPF_REQUIRE(entries_ub < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: chunk too large");
     const bool ang = metric == DPF_METRIC_ANGULAR;
+    const bool l2 = metric == DPF_METRIC_L2;                    // byte pipeline only; keys are -distance, negated on output
     // Two pipelines.  Byte store: k_threshold -> k_score_u8* (filtered output: only scores that can still be among a
     // query's best k are kept) -> k_select_survivors.  FP64 / FP32 store: k_score_stream (dense output, one score per
     // bucket entry) -> k_select_pairs; there the threshold pass would itself read ~1 KB rows and an append from inside
@@ -1023,7 +1028,6 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     const unsigned qgrid = (unsigned)((nqc + RR_WARPS - 1) / RR_WARPS);
     {
         StageTimer tm(h, DPF_T_EXPAND);
-        if (use_u8 && q0 == 0) prepare_queries_u8(h, Qd, qk.nq);
         k_copy_u32<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->pair_cnt.p + q0 * L, h->pair_base.p, nslots - 1); DPF_LAUNCHED();
         DPF_CUDA(cudaMemsetAsync(h->pair_base.p + nslots - 1, 0, sizeof(uint32_t), st));
         exclusive_scan_u32(h, h->pair_base.p, nslots);
@@ -1072,7 +1076,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                     h->bm_tl_cnt.p);
             };
             const char* tk = getenv("DPF_TAU_KERNEL");
-            if (intq && !(tk && tk[0] == 'd')) launch_threshold_u8i(h, ang, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
+            if (intq && (l2 || !(tk && tk[0] == 'd'))) launch_threshold_u8i(h, metric, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
             else if (ang) { if (intq) go(k_threshold<true, DPF_STORE_KIND_U8, true>); else go(k_threshold<true, DPF_STORE_KIND_U8, false>); }
             else { if (intq) go(k_threshold<false, DPF_STORE_KIND_U8, true>); else go(k_threshold<false, DPF_STORE_KIND_U8, false>); }
             DPF_LAUNCHED();
@@ -1100,7 +1104,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         h->stats[DPF_STAT_BM_PAIRS] += h->bm_npairs;
         const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
         if (use_u8) {
-            launch_score_u8(h, Qd, units, h->bm_counts.p + 1, ang, flt, bm_stat);
+            launch_score_u8(h, Qd, units, h->bm_counts.p + 1, metric, flt, bm_stat);
         } else {
             dispatch_kind(kind, ang, [&](auto a, auto kc) {
                 auto kern = k_score_stream<decltype(a)::value, decltype(kc)::value>;
@@ -1120,10 +1124,10 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         if (use_u8) {
             h->bm_big.reserve((size_t)nqc + 1);                  // [0] = count, then the queries with long lists
             DPF_CUDA(cudaMemsetAsync(h->bm_big.p, 0, sizeof(uint32_t), st));
-            k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, ids_out,
+            k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, l2, ids_out,
                                                                      score_out, bm_stat, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
             k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
-                q0, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, ids_out, score_out, h->bm_big.p + 1, h->bm_big.p);
+                q0, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, l2, ids_out, score_out, h->bm_big.p + 1, h->bm_big.p);
         }
         else
             k_select_pairs<<<(unsigned)nqc, RR_THREADS, list_smem, st>>>(q0, L, h->pair_base.p, h->pair_key.p, h->pair_len.p,

@@ -29,11 +29,11 @@ constexpr int U8_QPITCH = 128;          // row pitch of the byte copy of the que
 // ---------------------------------------------------------------------------------------------------------
 // queries -> bytes (when they are bytes)
 // ---------------------------------------------------------------------------------------------------------
-// warp per query: Q8[q][c] = (uint8)Q[q][c] (0 for the pad columns), qnorm[q] = sqrt(sum of squares) (exact integer
-// sum); *flag |= 1 if some value is not a byte
+// warp per query: Q8[q][c] = (uint8)Q[q][c] (0 for the pad columns), qsq[q] = sum of squares (exact integer), qnorm[q] =
+// its square root; *flag |= 1 if some value is not a byte
 __global__ void __launch_bounds__(256)
 k_quantise_queries(const double* __restrict__ Q, int64_t nq, int d, int pitch, unsigned char* __restrict__ Q8,
-                   double* __restrict__ qnorm, int* __restrict__ flag) {
+                   double* __restrict__ qnorm, int32_t* __restrict__ qsq, int* __restrict__ flag) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -55,6 +55,7 @@ k_quantise_queries(const double* __restrict__ Q, int64_t nq, int d, int pitch, u
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
         qnorm[q] = sqrt((double)sq);
+        qsq[q] = (int32_t)sq;                          // < 2^31 for d * 255^2 < 2^31 (checked by the caller)
         if (bad) atomicOr(flag, 1);
     }
 }
@@ -410,11 +411,14 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
-template <bool ANGULAR>
+template <int METRIC>
 __global__ void __launch_bounds__(U8_WARPS * 32, US_CTAS)
 k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
-            const double* __restrict__ qnorm, const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p,
-            const int32_t* __restrict__ ids_sorted, Filter flt, unsigned long long* __restrict__ stat) {
+            const double* __restrict__ qnorm, const int32_t* __restrict__ qsq, const UnitRec* __restrict__ units,
+            const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, Filter flt,
+            unsigned long long* __restrict__ stat) {
+    // DOT: key = dot.  ANGULAR: key = dot / (|q| |x|).  L2: key = -|q - x|^2 = 2 dot - |x|^2 - |q|^2, an exact integer.
+    constexpr bool ANGULAR = METRIC == DPF_METRIC_ANGULAR, L2 = METRIC == DPF_METRIC_L2;
     extern __shared__ __align__(16) unsigned char us_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -491,7 +495,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     // ---- consumer side ----------------------------------------------------------------------------------------------
     uint4 bq_nx[2][2];                 // query operand / thresholds / norms of the unit after the current one
     double tau_nx[2][2], qn_nx[2][2];
-    int qj_nx[2][2];
+    int qj_nx[2][2], qq_nx[2][2];
     auto stage2 = [&](int64_t k) {
         const UnitRec* r = &recs[(k < nmine ? k : nmine - 1) % US_R];
         const int m = (int)r->m;
@@ -506,6 +510,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                 qj_nx[nb][e] = r->q[j];
                 tau_nx[nb][e] = j < m ? r->tau[j] : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
                 if (ANGULAR) qn_nx[nb][e] = __ldg(qnorm + qj_nx[nb][e]);
+                if (L2) qq_nx[nb][e] = __ldg(qsq + qj_nx[nb][e]);
             }
         }
     };
@@ -518,7 +523,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
         const int len = (int)r->len;
         const bool two_blocks = r->m > 8;
         uint4 bq[2][2];
-        int c_q[2][2], c_taui[2][2];
+        int c_q[2][2], c_taui[2][2], c_qq[2][2];
         double c_tau[2][2], c_qn[2][2];
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
@@ -529,6 +534,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                 const double tv = tau_nx[nb][e];
                 c_tau[nb][e] = tv;
                 c_qn[nb][e] = ANGULAR ? qn_nx[nb][e] : 1.0;
+                c_qq[nb][e] = L2 ? qq_nx[nb][e] : 0;
                 // a dot product of bytes is below 2^31 - 1: INT_MAX masks the slot
                 c_taui[nb][e] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
             }
@@ -558,7 +564,8 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                 }
             }
             double xnr[2] = {1.0, 1.0};
-            if (ANGULAR) {
+            int xx[2] = {0, 0};
+            if (ANGULAR || L2) {
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     unsigned sq = 0;
@@ -571,7 +578,8 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                     }
                     sq += __shfl_xor_sync(0xffffffffu, sq, 1);
                     sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                    xnr[rr] = sqrt((double)sq);
+                    if (ANGULAR) xnr[rr] = sqrt((double)sq);
+                    xx[rr] = (int)sq;
                 }
             }
             // c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries)
@@ -582,7 +590,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int row = 16 * tile + 8 * rr + g;
-                        const int dot = acc[nb][2 * rr + e];
+                        const int dot = L2 ? 2 * acc[nb][2 * rr + e] - xx[rr] - c_qq[nb][e] : acc[nb][2 * rr + e];
                         bool keep;
                         double v = (double)dot;
                         if (ANGULAR) { v = v / (c_qn[nb][e] * xnr[rr]); keep = v >= c_tau[nb][e]; }
@@ -603,13 +611,14 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
 // shuffle-reduction form and the kernel is bound by the row gather alone.  The dot products are the exact integers the
 // scoring kernel will produce; cosines are computed with the same operations.
 // ---------------------------------------------------------------------------------------------------------
-template <bool ANGULAR>
+template <int METRIC>
 __global__ void __launch_bounds__(RR_THREADS)
 k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
-                const double* __restrict__ qnorm, int64_t q0, int64_t nqc, int L, int NT, const uint32_t* __restrict__ pair_base,
+                const double* __restrict__ qnorm, const int32_t* __restrict__ qsq, int64_t q0, int64_t nqc, int L, int NT, const uint32_t* __restrict__ pair_base,
                 const unsigned long long* __restrict__ pair_key_unsorted, const uint32_t* __restrict__ pair_len,
                 const int32_t* __restrict__ ids_sorted, const int32_t* __restrict__ qids, int self_exclude, int K,
                 double* __restrict__ tl_keys, int* __restrict__ tl_ids, int* __restrict__ tl_cnt) {
+    constexpr bool ANGULAR = METRIC == DPF_METRIC_ANGULAR, L2 = METRIC == DPF_METRIC_L2;
     extern __shared__ double rsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -633,6 +642,7 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
         bq1 = ldg_u4(qp + 64);
     }
     const double qn = ANGULAR ? __ldg(qnorm + q) : 1.0;
+    const int qq = L2 ? __ldg(qsq + q) : 0;
     // the sample-th table (among the first 32) in which the query probes something
     const uint32_t p_mine = lane < L ? pair_base[ql * L + lane] : 0u;
     const uint32_t p_next = lane < L ? pair_base[ql * L + lane + 1] : 0u;
@@ -670,7 +680,8 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
                     imma_u8(acc, a[tl][0][1].z, a[tl][1][1].z, a[tl][0][1].w, a[tl][1][1].w, bq1.z, bq1.w);
                 }
                 double xnr[2] = {1.0, 1.0};
-                if (ANGULAR) {
+                int xx[2] = {0, 0};
+                if (ANGULAR || L2) {
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
                         unsigned sq = 0;
@@ -683,14 +694,15 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
                         }
                         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
                         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                        xnr[rr] = sqrt((double)sq);
+                        if (ANGULAR) xnr[rr] = sqrt((double)sq);
+                        xx[rr] = (int)sq;
                     }
                 }
                 // lanes t = 0 hold column 0: acc[0] = row g, acc[2] = row 8 + g
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int row = row0 + 16 * tl + 8 * rr + g;
-                    double lb = (double)acc[2 * rr];
+                    double lb = (double)(L2 ? 2 * acc[2 * rr] - xx[rr] - qq : acc[2 * rr]);
                     if (ANGULAR) { lb = lb / (qn * xnr[rr]); lb -= 8.0 * 1.1102230246251565e-16 * fabs(lb); }
                     const int id = __shfl_sync(0xffffffffu, idA, min(row, len - 1) - row0);
                     bool ok = t == 0 && row < len && lb == lb && !(excl && id == qid);
@@ -718,14 +730,16 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
     if (lane == 0) tl_cnt[wid] = count;
 }
 
-void launch_threshold_u8i(dpf_index* h, bool angular, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk, size_t list_smem) {
+void launch_threshold_u8i(dpf_index* h, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk, size_t list_smem) {
     const unsigned grid = (unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS);
     auto go = [&](auto kern) {
-        kern<<<grid, RR_THREADS, list_smem, h->stream>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, h->Q8.p, h->qnorm8.p, q0, nqc, h->cfg.L, NT,
+        kern<<<grid, RR_THREADS, list_smem, h->stream>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, h->Q8.p, h->qnorm8.p, h->qsq8.p, q0, nqc, h->cfg.L, NT,
                                                          h->pair_base.p, h->pair_key.p, h->pair_len.p, h->ids_sorted.p, qids,
                                                          h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p);
     };
-    if (angular) go(k_threshold_u8i<true>); else go(k_threshold_u8i<false>);
+    if (metric == DPF_METRIC_ANGULAR) go(k_threshold_u8i<DPF_METRIC_ANGULAR>);
+    else if (metric == DPF_METRIC_L2) go(k_threshold_u8i<DPF_METRIC_L2>);
+    else go(k_threshold_u8i<DPF_METRIC_DOT>);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -747,9 +761,10 @@ void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq) {
     const int pitch = U8_QPITCH;
     h->Q8.reserve((size_t)nq * pitch);
     h->qnorm8.reserve((size_t)nq);
+    h->qsq8.reserve((size_t)nq);
     int* flag = h->counters.p + 41;
     DPF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-    k_quantise_queries<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Qd, nq, h->cfg.d, pitch, h->Q8.p, h->qnorm8.p, flag); DPF_LAUNCHED();
+    k_quantise_queries<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Qd, nq, h->cfg.d, pitch, h->Q8.p, h->qnorm8.p, h->qsq8.p, flag); DPF_LAUNCHED();
     int f = 1;
     DPF_CUDA(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaStreamSynchronize(st));
@@ -757,8 +772,9 @@ void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq) {
     h->Q8_valid = f == 0 && (int64_t)h->cfg.d * 255 * 255 < (1LL << 31);
 }
 
-void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const uint32_t* nunits_p, bool angular,
+void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const uint32_t* nunits_p, int metric,
                      const Filter& flt, unsigned long long* bm_stat) {
+    const bool angular = metric == DPF_METRIC_ANGULAR;
     const UnitRec* units = reinterpret_cast<const UnitRec*>(units_v);
     const unsigned pitch = (unsigned)h->Xc_row_bytes;
     cudaStream_t st = h->stream;
@@ -768,15 +784,17 @@ void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const 
                                                                    h->ids_sorted.p, flt, bm_stat);
         };
         const char* ev = getenv("DPF_U8I_KERNEL");
-        if (ev && ev[0] == 'l') {                                  // =lean: the occupancy-based variant
+        if (ev && ev[0] == 'l' && metric != DPF_METRIC_L2) {       // =lean: the occupancy-based variant (dot / angular)
             if (angular) launch(k_score_u8i<true>); else launch(k_score_u8i<false>);
         } else {
             auto launch_s = [&](auto kern) {
                 DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US_SMEM));
-                kern<<<h->num_sms * US_CTAS, U8_WARPS * 32, US_SMEM, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, units, nunits_p,
+                kern<<<h->num_sms * US_CTAS, U8_WARPS * 32, US_SMEM, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, h->qsq8.p, units, nunits_p,
                                                                          h->ids_sorted.p, flt, bm_stat);
             };
-            if (angular) launch_s(k_score_u8s<true>); else launch_s(k_score_u8s<false>);
+            if (angular) launch_s(k_score_u8s<DPF_METRIC_ANGULAR>);
+            else if (metric == DPF_METRIC_L2) launch_s(k_score_u8s<DPF_METRIC_L2>);
+            else launch_s(k_score_u8s<DPF_METRIC_DOT>);
         }
     } else {
         auto launch = [&](auto kern) {

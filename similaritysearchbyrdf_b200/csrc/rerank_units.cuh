@@ -98,12 +98,10 @@ constexpr size_t SS_SMEM = SS_WARPS * ((SS_WARP_BYTES + 15) / 16 * 16);
 
 
 // rerank_u8.cu: scores of every unit from the uint8 compact store (register gather, DMMA or IMMA)
-bool score_u8_usable(const dpf_index* h);
-void launch_threshold_u8i(dpf_index* h, bool angular, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
+void launch_threshold_u8i(dpf_index* h, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
                           size_t list_smem);                          // threshold samples on the integer tensor pipe
 int u8_query_pitch();                                                      // row pitch of dpf_index::Q8
-void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq);       // queries -> uint8 copy if they are bytes
-void launch_score_u8(dpf_index* h, const double* Qd, const void* units, const uint32_t* nunits_p, bool angular,
+void launch_score_u8(dpf_index* h, const double* Qd, const void* units, const uint32_t* nunits_p, int metric,
                      const Filter& flt, unsigned long long* bm_stat);
 
 }  // namespace dpf

@@ -70,6 +70,15 @@ def test_full_size_topk_properties_and_kernel_agreement(full, monkeypatch):
     ir, sr = ix.query_topk_dense(Q[:2000], None, 0, K, B.METRIC_ANGULAR)
     monkeypatch.delenv("DPF_RERANK")
     U.assert_topk_close(ir, sr, ia, sa)
+    # squared L2 on the integer pipeline: exact, ascending, equal to the row-major kernel bit for bit
+    il, sl = ix.query_topk_dense(Q, None, 0, K, B.METRIC_L2)
+    assert ix.stats()["bm_survivors"] >= NQ * K, "L2 on byte rows and byte queries runs the filtered pipeline"
+    assert (np.diff(sl, axis=1) >= 0).all()
+    assert np.array_equal(((X[il[:512]] - Q[:512, None, :]) ** 2).sum(axis=2), sl[:512])
+    monkeypatch.setenv("DPF_RERANK", "rowmajor")
+    ir, sr = ix.query_topk_dense(Q, None, 0, K, B.METRIC_L2)
+    monkeypatch.delenv("DPF_RERANK")
+    assert np.array_equal(il, ir) and np.array_equal(sl, sr)
 
 
 def test_full_size_self_retrieval_and_candidate_sets(full):

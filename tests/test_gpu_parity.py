@@ -389,7 +389,7 @@ def test_compact_store_one_value_decides(poison, expect):
     assert ix2.stats()["store_kind"] == (B.STORE_KIND_U8 if expect == B.STORE_KIND_U8 else B.STORE_KIND_F64)
 
 
-@pytest.mark.parametrize("metric", [B.METRIC_DOT, B.METRIC_ANGULAR])
+@pytest.mark.parametrize("metric", [B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2])
 @pytest.mark.parametrize("byte_queries", [True, False])
 def test_threshold_filter_corner_cases(metric, byte_queries, monkeypatch):
     """Byte store -> filtered pipeline (k_threshold, k_score_u8*, k_select_survivors).  topk larger than the sampled
@@ -409,7 +409,12 @@ def test_threshold_filter_corner_cases(metric, byte_queries, monkeypatch):
         ig, sg = ix.query_topk_dense(Qs, qids, steps, topk, metric)
         U.assert_topk_close(io, so, ig, sg)
         st = ix.stats()
-        assert st["bm_pairs"] > 0 and st["bm_survivors"] >= (ig >= 0).sum()
+        if metric == B.METRIC_L2 and not byte_queries:        # squared L2 is exact only on the integer pipeline
+            assert st["bm_pairs"] == 0, "expected the row-major kernel"
+        else:
+            assert st["bm_pairs"] > 0 and st["bm_survivors"] >= (ig >= 0).sum()
+        if metric == B.METRIC_L2 and byte_queries:
+            assert np.array_equal(so[~np.isnan(so)], sg[~np.isnan(sg)]), "integer squared distances must be exact"
     assert np.array_equal(ig == -1, io == -1)                 # padded rows where the candidates run out
 
 
