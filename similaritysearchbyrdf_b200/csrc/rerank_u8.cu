@@ -424,6 +424,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     const int g = lane >> 2, t = lane & 3;
     unsigned char* wbase = us_smem + (size_t)warp * US_WARP_SMEM;
     uint4* ring = reinterpret_cast<uint4*>(wbase) + lane;                 // slot s, vector j: ring[(4 s + j) * 32]
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);      // the same as a shared-window address
     UnitRec* recs = reinterpret_cast<UnitRec*>(wbase + (size_t)US_D * 4 * 32 * 16);
     const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;
     const bool two_chunks = pitch > 64;
@@ -437,12 +438,12 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     SurvivorSink sink;
 
     // record k -> ring slot k % US_R (joins the cp.async group that is committed next)
-    auto rec_request = [&](int64_t k) {
+    auto rec_request = [&](int64_t k, int rslot) {
         if (k < nmine && lane < US_REC_CHUNKS)
-            cp_async16(reinterpret_cast<unsigned char*>(&recs[k % US_R]) + 16 * lane,
+            cp_async16(reinterpret_cast<unsigned char*>(&recs[rslot]) + 16 * lane,
                        reinterpret_cast<const unsigned char*>(units + (u0 + k * W)) + 16 * lane);
     };
-    for (int k = 0; k <= US_D; ++k) rec_request(k);
+    for (int k = 0; k <= US_D; ++k) rec_request(k, k);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -453,38 +454,40 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
         return 32 * w < len ? __ldg(ids_sorted + r->bstart + min(32 * w + lane, len - 1)) : 0;
     };
     int64_t pk = 0;                    // unit being produced
+    int p_rslot = 0;                   // = pk % US_R; the record requested when pk is opened goes to (p_rslot + US_D) % US_R
     int p_tile = 0, p_len = (int)recs[0].len;
     int p_w0 = recs[0].ids0[lane], p_w1 = win_load(&recs[0], 1), p_w2 = win_load(&recs[0], 2), p_w3 = win_load(&recs[0], 3);
     int nx_w1 = 0, nx_w2 = 0, nx_w3 = 0;                  // windows 1..3 of unit pk + 1
     if (nmine > 1) { nx_w1 = win_load(&recs[1], 1); nx_w2 = win_load(&recs[1], 2); nx_w3 = win_load(&recs[1], 3); }
     auto issue = [&](int slot) {
         if (pk < nmine) {
-            uint4* dst = ring + (size_t)slot * (4 * 32);
+            const unsigned dst = ring_s + (unsigned)slot * (4 * 32 * 16);
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int row = min(16 * p_tile + 8 * rr + g, p_len - 1);
-                const unsigned char* xp = X8 + (size_t)__shfl_sync(0xffffffffu, p_w0, row & 31) * pitch;
-                cp_async16(dst + (2 * rr) * 32, xp + off0);
-                cp_async16(dst + (2 * rr + 1) * 32, xp + off1);
+                const unsigned char* xp = X8 + (unsigned long long)(unsigned)__shfl_sync(0xffffffffu, p_w0, row & 31) * pitch;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * rr) * 512), "l"(xp + off0) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * rr + 1) * 512), "l"(xp + off1) : "memory");
             }
             ++p_tile;
             if (16 * p_tile >= p_len) {                          // unit done: open the next one
                 ++pk;
                 p_tile = 0;
-                rec_request(pk + US_D);                          // arrives US_D production steps before it is opened
+                p_rslot = p_rslot + 1 == US_R ? 0 : p_rslot + 1;
+                rec_request(pk + US_D, p_rslot >= US_D ? p_rslot - US_D : p_rslot + US_D);   // arrives US_D steps before it is opened
                 if (pk < nmine) {
                     __syncwarp();                                // records copied by other lanes (complete: see header)
-                    const UnitRec* r = &recs[pk % US_R];
+                    const UnitRec* r = &recs[p_rslot];
                     p_len = (int)r->len;
                     p_w0 = r->ids0[lane]; p_w1 = nx_w1; p_w2 = nx_w2; p_w3 = nx_w3;
                     if (pk + 1 < nmine) {
-                        const UnitRec* rn = &recs[(pk + 1) % US_R];
+                        const UnitRec* rn = &recs[p_rslot + 1 == US_R ? 0 : p_rslot + 1];
                         nx_w1 = win_load(rn, 1); nx_w2 = win_load(rn, 2); nx_w3 = win_load(rn, 3);
                     }
                 }
             } else if (!(p_tile & 1)) {                          // next id window of this unit
                 p_w0 = p_w1; p_w1 = p_w2; p_w2 = p_w3;
-                p_w3 = win_load(&recs[pk % US_R], (p_tile >> 1) + 3);
+                p_w3 = win_load(&recs[p_rslot], (p_tile >> 1) + 3);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -496,8 +499,8 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     uint4 bq_nx[2][2];                 // query operand / thresholds / norms of the unit after the current one
     double tau_nx[2][2], qn_nx[2][2];
     int qj_nx[2][2], qq_nx[2][2];
-    auto stage2 = [&](int64_t k) {
-        const UnitRec* r = &recs[(k < nmine ? k : nmine - 1) % US_R];
+    auto stage2 = [&](int rslot) {
+        const UnitRec* r = &recs[rslot];
         const int m = (int)r->m;
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
@@ -515,10 +518,10 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
         }
     };
     stage2(0);
-    int consumed = 0;
+    int c_slot = 0, c_rslot = 0;       // consumer's tile slot and record slot; the producer writes tile slot c_slot - 1
     for (int64_t k = 0; k < nmine; ++k) {
         __syncwarp();                                            // records are copied by other lanes
-        const UnitRec* r = &recs[k % US_R];
+        const UnitRec* r = &recs[c_rslot];
         const uint32_t bstart = r->bstart;
         const int len = (int)r->len;
         const bool two_blocks = r->m > 8;
@@ -540,14 +543,15 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
             }
         }
         rows_staged += (unsigned)len;
-        if (k + 1 < nmine) stage2(k + 1);                        // its record is in the ring since before unit k was produced
+        c_rslot = c_rslot + 1 == US_R ? 0 : c_rslot + 1;
+        if (k + 1 < nmine) stage2(c_rslot);                      // its record is in the ring since before unit k was produced
         for (int tile = 0; 16 * tile < len; ++tile) {
-            issue((consumed + US_D - 1) % US_D);
+            issue(c_slot == 0 ? US_D - 1 : c_slot - 1);
             asm volatile("cp.async.wait_group %0;" ::"n"(US_D - 1) : "memory");
-            const uint4* src = ring + (size_t)(consumed % US_D) * (4 * 32);
+            const uint4* src = ring + c_slot * (4 * 32);
             uint4 a[2][2];
             a[0][0] = src[0]; a[0][1] = src[32]; a[1][0] = src[64]; a[1][1] = src[96];
-            consumed++;
+            c_slot = c_slot + 1 == US_D ? 0 : c_slot + 1;
             int acc[2][4];
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb)
@@ -582,21 +586,45 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                     xx[rr] = (int)sq;
                 }
             }
-            // c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries)
+            // c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries).  Nearly every tile has no score
+            // above its thresholds: one vote over all eight scores of the thread decides whether to look closer.
+            int key[2][2][2];
+            bool pass[2][2][2];
+            bool any = false;
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int row = 16 * tile + 8 * rr + g;
-                        const int dot = L2 ? 2 * acc[nb][2 * rr + e] - xx[rr] - c_qq[nb][e] : acc[nb][2 * rr + e];
-                        bool keep;
-                        double v = (double)dot;
-                        if (ANGULAR) { v = v / (c_qn[nb][e] * xnr[rr]); keep = v >= c_tau[nb][e]; }
-                        else keep = dot >= c_taui[nb][e];
-                        sink.push(flt, keep && row < len && (nb == 0 || two_blocks), c_q[nb][e], bstart + (uint32_t)row, v, lane);
+                        const int dot = acc[nb][2 * rr + e];
+                        key[nb][rr][e] = L2 ? 2 * dot - xx[rr] - c_qq[nb][e] : dot;
+                        bool p;
+                        if (ANGULAR) {
+                            // dot / den >= tau  <=  dot >= tau * den up to rounding: a slightly lower bar here, the exact
+                            // quotient decides below
+                            const double bar = c_tau[nb][e] * (c_qn[nb][e] * xnr[rr]);
+                            p = (double)dot >= bar - 1e-12 * fabs(bar) || !(bar == bar);
+                        } else {
+                            p = key[nb][rr][e] >= c_taui[nb][e];
+                        }
+                        p = p && 16 * tile + 8 * rr + g < len && (nb == 0 || two_blocks);
+                        pass[nb][rr][e] = p;
+                        any |= p;
                     }
+            if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            double v = (double)key[nb][rr][e];
+                            bool keep = pass[nb][rr][e];
+                            if (ANGULAR) { v = v / (c_qn[nb][e] * xnr[rr]); keep = keep && v >= c_tau[nb][e]; }
+                            sink.push(flt, keep, c_q[nb][e], bstart + (uint32_t)(16 * tile + 8 * rr + g), v, lane);
+                        }
+            }
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
