@@ -496,25 +496,26 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     for (int s = 0; s < US_D - 1; ++s) issue(s);
 
     // ---- consumer side ----------------------------------------------------------------------------------------------
-    uint4 bq_nx[2][2];                 // query operand / thresholds / norms of the unit after the current one
-    double tau_nx[2][2], qn_nx[2][2];
-    int qj_nx[2][2], qq_nx[2][2];
+    // IMMA.16x8x32 with the QUERIES as the 16-row A operand (queries g and 8 + g of the unit, kept in registers) and 8
+    // bucket rows as the B operand: thread (g, t) supplies row g of the group, and the two B registers of a k-step are
+    // two consecutive words of one of its 16-byte chunks — an LDS.128 feeds two IMMAs with no register shuffling.
+    // Results: c0, c1 = (query g, rows 2t, 2t + 1), c2, c3 = (query 8 + g, same rows).
+    uint4 bq_nx[2][2];                 // [query g / 8 + g][chunk] of the unit after the current one
+    double tau_nx[2], qn_nx[2];
+    int qj_nx[2], qq_nx[2];
     auto stage2 = [&](int rslot) {
         const UnitRec* r = &recs[rslot];
         const int m = (int)r->m;
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
-            const unsigned char* qp = Q8 + (size_t)r->q[8 * nb + g] * U8_QPITCH + 16 * t;     // slots >= m repeat the last query
+            const int j = 8 * nb + g;
+            qj_nx[nb] = r->q[j];                                 // slots >= m repeat the last query
+            const unsigned char* qp = Q8 + (size_t)qj_nx[nb] * U8_QPITCH + 16 * t;
             bq_nx[nb][0] = ldg_u4(qp);
             bq_nx[nb][1] = ldg_u4(qp + 64);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = 8 * nb + 2 * t + e;
-                qj_nx[nb][e] = r->q[j];
-                tau_nx[nb][e] = j < m ? r->tau[j] : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
-                if (ANGULAR) qn_nx[nb][e] = __ldg(qnorm + qj_nx[nb][e]);
-                if (L2) qq_nx[nb][e] = __ldg(qsq + qj_nx[nb][e]);
-            }
+            tau_nx[nb] = j < m ? r->tau[j] : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
+            if (ANGULAR) qn_nx[nb] = __ldg(qnorm + qj_nx[nb]);
+            if (L2) qq_nx[nb] = __ldg(qsq + qj_nx[nb]);
         }
     };
     stage2(0);
@@ -525,22 +526,24 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
         const uint32_t bstart = r->bstart;
         const int len = (int)r->len;
         const bool two_blocks = r->m > 8;
-        uint4 bq[2][2];
-        int c_q[2][2], c_taui[2][2], c_qq[2][2];
-        double c_tau[2][2], c_qn[2][2];
+        // A fragments of the four k-steps (chunk c, half h): {Qg.w[2h], Q8g.w[2h], Qg.w[2h+1], Q8g.w[2h+1]}
+        unsigned A[2][2][4];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            A[c][0][0] = bq_nx[0][c].x; A[c][0][1] = bq_nx[1][c].x; A[c][0][2] = bq_nx[0][c].y; A[c][0][3] = bq_nx[1][c].y;
+            A[c][1][0] = bq_nx[0][c].z; A[c][1][1] = bq_nx[1][c].z; A[c][1][2] = bq_nx[0][c].w; A[c][1][3] = bq_nx[1][c].w;
+        }
+        int c_q[2], c_taui[2], c_qq[2];
+        double c_tau[2], c_qn[2];
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
-            bq[nb][0] = bq_nx[nb][0]; bq[nb][1] = bq_nx[nb][1];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                c_q[nb][e] = qj_nx[nb][e];
-                const double tv = tau_nx[nb][e];
-                c_tau[nb][e] = tv;
-                c_qn[nb][e] = ANGULAR ? qn_nx[nb][e] : 1.0;
-                c_qq[nb][e] = L2 ? qq_nx[nb][e] : 0;
-                // a dot product of bytes is below 2^31 - 1: INT_MAX masks the slot
-                c_taui[nb][e] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
-            }
+            c_q[nb] = qj_nx[nb];
+            const double tv = tau_nx[nb];
+            c_tau[nb] = tv;
+            c_qn[nb] = ANGULAR ? qn_nx[nb] : 1.0;
+            c_qq[nb] = L2 ? qq_nx[nb] : 0;
+            // a dot product of bytes is below 2^31 - 1: INT_MAX masks the slot
+            c_taui[nb] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
         }
         rows_staged += (unsigned)len;
         c_rslot = c_rslot + 1 == US_R ? 0 : c_rslot + 1;
@@ -549,46 +552,42 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
             issue(c_slot == 0 ? US_D - 1 : c_slot - 1);
             asm volatile("cp.async.wait_group %0;" ::"n"(US_D - 1) : "memory");
             const uint4* src = ring + c_slot * (4 * 32);
-            uint4 a[2][2];
-            a[0][0] = src[0]; a[0][1] = src[32]; a[1][0] = src[64]; a[1][1] = src[96];
             c_slot = c_slot + 1 == US_D ? 0 : c_slot + 1;
-            int acc[2][4];
+            int acc[2][4];                                       // [row half][c0..c3]
+            int xx[2][2];                                        // |row|^2 of rows 8rr + 2t + e
+            double xnr[2][2];
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb)
+            for (int rr = 0; rr < 2; ++rr) {
+                const uint4 b0 = src[(2 * rr) * 32], b1 = src[(2 * rr + 1) * 32];     // row 8rr + g: chunks t and 4 + t
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[nb][i] = 0;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (c == 1 && !two_chunks) break;
-                imma_u8(acc[0], a[0][c].x, a[1][c].x, a[0][c].y, a[1][c].y, bq[0][c].x, bq[0][c].y);
-                imma_u8(acc[0], a[0][c].z, a[1][c].z, a[0][c].w, a[1][c].w, bq[0][c].z, bq[0][c].w);
-                if (two_blocks) {
-                    imma_u8(acc[1], a[0][c].x, a[1][c].x, a[0][c].y, a[1][c].y, bq[1][c].x, bq[1][c].y);
-                    imma_u8(acc[1], a[0][c].z, a[1][c].z, a[0][c].w, a[1][c].w, bq[1][c].z, bq[1][c].w);
+                for (int i = 0; i < 4; ++i) acc[rr][i] = 0;
+                imma_u8(acc[rr], A[0][0][0], A[0][0][1], A[0][0][2], A[0][0][3], b0.x, b0.y);
+                imma_u8(acc[rr], A[0][1][0], A[0][1][1], A[0][1][2], A[0][1][3], b0.z, b0.w);
+                if (two_chunks) {
+                    imma_u8(acc[rr], A[1][0][0], A[1][0][1], A[1][0][2], A[1][0][3], b1.x, b1.y);
+                    imma_u8(acc[rr], A[1][1][0], A[1][1][1], A[1][1][2], A[1][1][3], b1.z, b1.w);
                 }
-            }
-            double xnr[2] = {1.0, 1.0};
-            int xx[2] = {0, 0};
-            if (ANGULAR || L2) {
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    unsigned sq = 0;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        unsigned sc = 0;
-                        sc = __dp4a(a[rr][c].x, a[rr][c].x, sc); sc = __dp4a(a[rr][c].y, a[rr][c].y, sc);
-                        sc = __dp4a(a[rr][c].z, a[rr][c].z, sc); sc = __dp4a(a[rr][c].w, a[rr][c].w, sc);
-                        if (c == 0 ? has0 : has1) sq += sc;
-                    }
+                xx[rr][0] = xx[rr][1] = 0;
+                xnr[rr][0] = xnr[rr][1] = 1.0;
+                if (ANGULAR || L2) {                             // this thread loaded row 8rr + g; its results are rows 2t, 2t + 1
+                    unsigned sq = 0, sc = 0;
+                    sc = __dp4a(b0.x, b0.x, sc); sc = __dp4a(b0.y, b0.y, sc); sc = __dp4a(b0.z, b0.z, sc); sc = __dp4a(b0.w, b0.w, sc);
+                    if (has0) sq += sc;
+                    sc = 0;
+                    sc = __dp4a(b1.x, b1.x, sc); sc = __dp4a(b1.y, b1.y, sc); sc = __dp4a(b1.z, b1.z, sc); sc = __dp4a(b1.w, b1.w, sc);
+                    if (has1) sq += sc;
                     sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                    if (ANGULAR) xnr[rr] = sqrt((double)sq);
-                    xx[rr] = (int)sq;
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);   // lanes with the same g hold |row 8rr + g|^2
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        xx[rr][e] = (int)__shfl_sync(0xffffffffu, sq, (2 * t + e) * 4);
+                        if (ANGULAR) xnr[rr][e] = sqrt((double)xx[rr][e]);
+                    }
                 }
             }
-            // c0, c1 = (row g, queries 2t, 2t + 1), c2, c3 = (row 8 + g, same queries).  Nearly every tile has no score
-            // above its thresholds: one vote over all eight scores of the thread decides whether to look closer.
-            int key[2][2][2];
+            // Nearly every tile has no score above its thresholds: one vote over all eight scores of the thread decides
+            // whether to look closer.
+            int key[2][2][2];                                    // [query g / 8 + g][row half][row 2t + e]
             bool pass[2][2][2];
             bool any = false;
 #pragma unroll
@@ -597,18 +596,18 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                 for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int dot = acc[nb][2 * rr + e];
-                        key[nb][rr][e] = L2 ? 2 * dot - xx[rr] - c_qq[nb][e] : dot;
+                        const int dot = acc[rr][2 * nb + e];
+                        key[nb][rr][e] = L2 ? 2 * dot - xx[rr][e] - c_qq[nb] : dot;
                         bool p;
                         if (ANGULAR) {
                             // dot / den >= tau  <=  dot >= tau * den up to rounding: a slightly lower bar here, the exact
                             // quotient decides below
-                            const double bar = c_tau[nb][e] * (c_qn[nb][e] * xnr[rr]);
+                            const double bar = c_tau[nb] * (c_qn[nb] * xnr[rr][e]);
                             p = (double)dot >= bar - 1e-12 * fabs(bar) || !(bar == bar);
                         } else {
-                            p = key[nb][rr][e] >= c_taui[nb][e];
+                            p = key[nb][rr][e] >= c_taui[nb];
                         }
-                        p = p && 16 * tile + 8 * rr + g < len && (nb == 0 || two_blocks);
+                        p = p && 16 * tile + 8 * rr + 2 * t + e < len && (nb == 0 || two_blocks);
                         pass[nb][rr][e] = p;
                         any |= p;
                     }
@@ -621,8 +620,8 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                         for (int e = 0; e < 2; ++e) {
                             double v = (double)key[nb][rr][e];
                             bool keep = pass[nb][rr][e];
-                            if (ANGULAR) { v = v / (c_qn[nb][e] * xnr[rr]); keep = keep && v >= c_tau[nb][e]; }
-                            sink.push(flt, keep, c_q[nb][e], bstart + (uint32_t)(16 * tile + 8 * rr + g), v, lane);
+                            if (ANGULAR) { v = v / (c_qn[nb] * xnr[rr][e]); keep = keep && v >= c_tau[nb]; }
+                            sink.push(flt, keep, c_q[nb], bstart + (uint32_t)(16 * tile + 8 * rr + 2 * t + e), v, lane);
                         }
             }
         }
