@@ -217,6 +217,13 @@ int dpf_create(const dpf_config* cfg, dpf_handle* out) {
                            (1 << cfg->pb) * (1 << seg_bits), cfg->bucket_overflow};
         DPF_CUDA(cudaSetDevice(cfg->device));
         DPF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        {   // lowest priority: its (large) kernels fill the gaps of the main stream's chain of small ones, not the reverse
+            int lo = 0, hi = 0;
+            DPF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            DPF_CUDA(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, lo));
+        }
+        DPF_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        DPF_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         tl_stream = h->stream;
         {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
             cudaMemPool_t pool = nullptr;
@@ -247,6 +254,9 @@ int dpf_destroy(dpf_handle h) {
     cudaGetLastError();
     cudaStream_t own = h->own_stream ? h->own_stream : h->stream;
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     tl_stream = own;        // the buffers go back to the pool in the order of the handle's own stream
     delete h;
     if (own) {

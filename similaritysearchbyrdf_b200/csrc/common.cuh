@@ -120,6 +120,8 @@ struct dpf_index {
     int PW = 0;  // sign words per vector = ceil(P/32)
     cudaStream_t stream = nullptr;      // stream all work of this handle runs on
     cudaStream_t own_stream = nullptr;  // the handle's own stream while a caller stream is installed
+    cudaStream_t aux_stream = nullptr;  // second stream for work that can overlap the main one (thresholds ‖ pair sort)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::mutex mu;
     std::string last_error;
     bool family_set = false, part_set = false, dense = true, fitted = false;

@@ -978,6 +978,7 @@ static void build_units(dpf_index* h, int64_t npairs, bool filtered) {
     DPF_CUDA(cudaMemcpyAsync(&nunits, h->bm_ucnt.p + npairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaStreamSynchronize(st));
     h->bm_units.reserve((size_t)std::max<uint32_t>(nunits, 1) * sizeof(UnitRec));
+    if (filtered) DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));      // thresholds from the second stream
     k_emit_units<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_ucnt.p, h->pair_q.p, h->pair_len.p,
                                      h->pair_seg.p, filtered ? h->bm_tau.p : nullptr, h->ids_sorted.p,
                                      reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
@@ -1069,21 +1070,28 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
             h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
             h->bm_tl_cnt.reserve((size_t)nqc * NT);
+            // The threshold kernels (row gather) run on the handle's second stream next to the pair sort and the run /
+            // unit bookkeeping (a chain of small latency-bound kernels) on the main one; k_emit_units, which puts tau into
+            // the unit records, waits for them (build_units).
+            cudaStream_t st2 = h->aux_stream;
+            DPF_CUDA(cudaEventRecord(h->ev_fork, st));
+            DPF_CUDA(cudaStreamWaitEvent(st2, h->ev_fork, 0));
             auto go = [&](auto kern) {
-                kern<<<(unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS), RR_THREADS, list_smem, st>>>(
+                kern<<<(unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS), RR_THREADS, list_smem, st2>>>(
                     rows, row_bytes, d, Qd, h->Q8.p, u8_query_pitch(), h->qnorm8.p, q0, nqc, L, NT, h->pair_base.p, h->pair_key.p,
                     h->pair_len.p, h->ids_sorted.p, qk.qids, h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p,
                     h->bm_tl_cnt.p);
             };
             const char* tk = getenv("DPF_TAU_KERNEL");
-            if (intq && (l2 || !(tk && tk[0] == 'd'))) launch_threshold_u8i(h, metric, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
+            if (intq && (l2 || !(tk && tk[0] == 'd'))) launch_threshold_u8i(h, st2, metric, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
             else if (ang) { if (intq) go(k_threshold<true, DPF_STORE_KIND_U8, true>); else go(k_threshold<true, DPF_STORE_KIND_U8, false>); }
             else { if (intq) go(k_threshold<false, DPF_STORE_KIND_U8, true>); else go(k_threshold<false, DPF_STORE_KIND_U8, false>); }
             DPF_LAUNCHED();
-            k_threshold_merge<<<qgrid, RR_THREADS, 0, st>>>(q0, nqc, L, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p,
-                                                            h->pair_base.p, h->pair_seg.p, h->bm_tau.p, h->bm_scnt.p, h->bm_sbase.p);
+            k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(q0, nqc, L, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p,
+                                                             h->pair_base.p, h->pair_seg.p, h->bm_tau.p, h->bm_scnt.p, h->bm_sbase.p);
             DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
+            DPF_CUDA(cudaEventRecord(h->ev_join, st2));
         }
         // sort a copy of the keys by bucket start (bits 32..); the unsorted array stays for the selection pass
         DPF_CUDA(cudaMemcpyAsync(h->pair_key_alt.p, h->pair_key.p, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));

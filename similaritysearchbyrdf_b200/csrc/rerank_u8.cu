@@ -757,10 +757,11 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
     if (lane == 0) tl_cnt[wid] = count;
 }
 
-void launch_threshold_u8i(dpf_index* h, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk, size_t list_smem) {
+void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
+                          size_t list_smem) {
     const unsigned grid = (unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS);
     auto go = [&](auto kern) {
-        kern<<<grid, RR_THREADS, list_smem, h->stream>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, h->Q8.p, h->qnorm8.p, h->qsq8.p, q0, nqc, h->cfg.L, NT,
+        kern<<<grid, RR_THREADS, list_smem, st>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, h->Q8.p, h->qnorm8.p, h->qsq8.p, q0, nqc, h->cfg.L, NT,
                                                          h->pair_base.p, h->pair_key.p, h->pair_len.p, h->ids_sorted.p, qids,
                                                          h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p);
     };

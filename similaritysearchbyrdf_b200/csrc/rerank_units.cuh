@@ -98,7 +98,7 @@ constexpr size_t SS_SMEM = SS_WARPS * ((SS_WARP_BYTES + 15) / 16 * 16);
 
 
 // rerank_u8.cu: scores of every unit from the uint8 compact store (register gather, DMMA or IMMA)
-void launch_threshold_u8i(dpf_index* h, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
+void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
                           size_t list_smem);                          // threshold samples on the integer tensor pipe
 int u8_query_pitch();                                                      // row pitch of dpf_index::Q8
 void launch_score_u8(dpf_index* h, const double* Qd, const void* units, const uint32_t* nunits_p, int metric,
