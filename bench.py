@@ -175,8 +175,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / debug lines off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created: point fd 1 at stderr until the first
+        # collective is through, so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     metric = {"dot": B.METRIC_DOT, "angular": B.METRIC_ANGULAR, "l2": B.METRIC_L2}[args.metric]
 
     X, Q, A, chain, Ap, gen_s = workload(args)

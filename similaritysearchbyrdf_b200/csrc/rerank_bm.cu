@@ -1065,7 +1065,10 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             h->bm_scnt.reserve((size_t)qk.nq);
             h->bm_sbase.reserve((size_t)qk.nq);
             const char* ntv = getenv("DPF_TAU_TABLES");
-            const int NT = std::min(32, std::max(1, ntv ? atoi(ntv) : 6));   // sampled tables per query (one warp each)
+            // sampled tables per query (one warp each): 6 on one GPU; a rank of G sees 1/G of every query's buckets, so
+            // its lists stay short with fewer samples
+            const int nt_default = c.world <= 1 ? 6 : std::max(2, 6 / c.world);
+            const int NT = std::min(32, std::max(1, ntv ? atoi(ntv) : nt_default));
             const bool intq = h->Q8_valid;
             h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
             h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
