@@ -131,7 +131,7 @@ k_emit_units(const unsigned long long* __restrict__ sorted, int64_t npairs, cons
         const uint32_t pi = (uint32_t)sorted[min((uint32_t)p + j, p1 - 1)];
         rec.q[j] = pair_q[pi];
         rec.seg[j] = pair_seg[pi];
-        rec.tau[j] = tau ? tau[rec.q[j]] : 0.0;
+        if (tau) rec.tau[j] = tau[rec.q[j]];
     }
 #pragma unroll
     for (int j = 0; j < SS_WIN; ++j) rec.ids0[j] = ids_sorted[bstart + min((uint32_t)j, rec.len - 1)];
@@ -286,8 +286,8 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
     unsigned long long rows_staged = 0;
     auto fetch_rec = [&](int64_t k) {
         if (k < nmine && lane == 0) {
-            mbar_expect_tx(&bar_rec[k & 1], (unsigned)sizeof(UnitRec));
-            bulk_g2s(&recs[k & 1], units + (gw + k * W), (unsigned)sizeof(UnitRec), &bar_rec[k & 1], pol_stream);
+            mbar_expect_tx(&bar_rec[k & 1], SS_REC_COPY);
+            bulk_g2s(&recs[k & 1], units + (gw + k * W), SS_REC_COPY, &bar_rec[k & 1], pol_stream);
         }
     };
     // ids of rows [32j, 32j + 32) of the current bucket -> window buffer j & 1 (the copy starts at the 16-byte
@@ -386,9 +386,15 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
                         for (int e = 0; e < E; e += 2) {
                             const int col = 64 * j / SK::SZ + col_t + e;          // even
                             double2 v = make_double2(0.0, 0.0);
-                            if (j < nj && col < d) v = *reinterpret_cast<const double2*>(br + col);
+                            if constexpr (KIND == DPF_STORE_KIND_F64) {
+                                // FP64 rows and query rows share one slot layout: the k padding is never written, stays 0
+                                if (j < nj) v = *reinterpret_cast<const double2*>(br + col);
+                            } else {
+                                if (j < nj && col < d) v = *reinterpret_cast<const double2*>(br + col);
+                                if (col + 1 >= d) v.y = 0.0;
+                            }
                             B[nb][j * E + e] = v.x;
-                            B[nb][j * E + e + 1] = col + 1 < d ? v.y : 0.0;
+                            B[nb][j * E + e + 1] = v.y;
                         }
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -424,10 +430,12 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
                 if (j < nj) {
                     double a[E];
                     widen_chunk<KIND>(*reinterpret_cast<const uint4*>(ar + 64 * j), a);
-                    if (ragged && j == nj - 1) {
+                    if constexpr (KIND != DPF_STORE_KIND_F64) {      // narrow rows: the slot padding holds query bytes
+                        if (ragged && j == nj - 1) {
 #pragma unroll
-                        for (int e = 0; e < E; ++e)
-                            if (64 * j / SK::SZ + col_t + e >= d) a[e] = 0.0;
+                            for (int e = 0; e < E; ++e)
+                                if (64 * j / SK::SZ + col_t + e >= d) a[e] = 0.0;
+                        }
                     }
 #pragma unroll
                     for (int e = 0; e < E; ++e) {

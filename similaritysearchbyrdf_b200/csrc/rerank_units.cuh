@@ -1,6 +1,8 @@
 // rerank_units.cuh — declarations shared by the bucket-major re-rank kernels (rerank_bm.cu, rerank_u8.cu): the unit
 // record, the FP64 tensor-pipe instruction wrapper and the geometry constants.
 #pragma once
+#include <cstddef>
+
 #include "query_common.cuh"
 
 namespace dpf {
@@ -34,10 +36,13 @@ struct __align__(16) UnitRec {
     uint32_t m;            // queries in the unit (1..SS_UQ)
     int32_t q[SS_UQ];      // query index of pair j
     uint32_t seg[SS_UQ];   // start of pair j's score segment (dense output: k_score_stream)
-    double tau[SS_UQ];     // that query's score threshold (filtered output: k_score_u8*, see Filter)
     int32_t ids0[SS_WIN];  // ids of the bucket's first 32 rows (the other windows are copied from ids_sorted)
+    double tau[SS_UQ];     // that query's score threshold (filtered output: k_score_u8*, see Filter); last, so that
+                           // k_score_stream, which does not filter, copies only the part before it
 };
 static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
+constexpr unsigned SS_REC_COPY = 16 + SS_UQ * 8 + SS_WIN * 4;      // = offsetof(UnitRec, tau)
+static_assert(SS_REC_COPY == offsetof(UnitRec, tau) && SS_REC_COPY % 16 == 0, "prefix copied by k_score_stream");
 
 // Threshold filter.  A batch produces ~50k (query, candidate) scores per query of which k survive.  Writing them all
 // and reading them back for the selection costs as many bytes as the byte rows themselves, so the scoring kernels
