@@ -272,7 +272,7 @@ def run_ours(args):
         ms_per_step = float(t.item()) / args.steps
         qstats = ix.stats()
         int_queries = bool(np.all(Q == np.floor(Q)) and Q.min() >= 0 and Q.max() <= 255)
-        unit_rec_bytes = 16 + 16 * 4 + 16 * 4 + 16 * 8 + 32 * 4                  # sizeof(UnitRec), rerank_units.cuh
+        unit_rec_bytes = 16 + 16 * 4 + 16 * 4 + 32 * 4                           # sizeof(UnitRec), rerank_units.cuh
         result_ids = (m_ids if world > 1 else ids_d).cpu().numpy()
         result_sc = (m_sc if world > 1 else sc_d).cpu().numpy()
 

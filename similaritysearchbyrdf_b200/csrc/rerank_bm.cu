@@ -111,8 +111,8 @@ k_run_unit_counts(const uint32_t* __restrict__ run_start, const uint32_t* __rest
 __global__ void __launch_bounds__(256)
 k_emit_units(const unsigned long long* __restrict__ sorted, int64_t npairs, const uint32_t* __restrict__ run_idx,
              const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ uoff, const int32_t* __restrict__ pair_q,
-             const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg, const double* __restrict__ tau /* or null */,
-             const int32_t* __restrict__ ids_sorted, UnitRec* __restrict__ units) {
+             const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg, const int32_t* __restrict__ ids_sorted,
+             UnitRec* __restrict__ units) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const unsigned long long k = sorted[p];
@@ -131,7 +131,6 @@ k_emit_units(const unsigned long long* __restrict__ sorted, int64_t npairs, cons
         const uint32_t pi = (uint32_t)sorted[min((uint32_t)p + j, p1 - 1)];
         rec.q[j] = pair_q[pi];
         rec.seg[j] = pair_seg[pi];
-        if (tau) rec.tau[j] = tau[rec.q[j]];
     }
 #pragma unroll
     for (int j = 0; j < SS_WIN; ++j) rec.ids0[j] = ids_sorted[bstart + min((uint32_t)j, rec.len - 1)];
@@ -286,8 +285,8 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
     unsigned long long rows_staged = 0;
     auto fetch_rec = [&](int64_t k) {
         if (k < nmine && lane == 0) {
-            mbar_expect_tx(&bar_rec[k & 1], SS_REC_COPY);
-            bulk_g2s(&recs[k & 1], units + (gw + k * W), SS_REC_COPY, &bar_rec[k & 1], pol_stream);
+            mbar_expect_tx(&bar_rec[k & 1], (unsigned)sizeof(UnitRec));
+            bulk_g2s(&recs[k & 1], units + (gw + k * W), (unsigned)sizeof(UnitRec), &bar_rec[k & 1], pol_stream);
         }
     };
     // ids of rows [32j, 32j + 32) of the current bucket -> window buffer j & 1 (the copy starts at the 16-byte
@@ -968,7 +967,7 @@ __global__ void k_topk_select_empty(int64_t q0, int64_t nqc, int K, int32_t* __r
 
 // runs of the sorted pair list -> unit records in h->bm_units (device); the number of units is also left in
 // h->bm_counts[1]
-static void build_units(dpf_index* h, int64_t npairs, bool filtered) {
+static void build_units(dpf_index* h, int64_t npairs) {
     cudaStream_t st = h->stream;
     const unsigned gp = (unsigned)((npairs + 255) / 256);
     h->bm_flag.reserve(npairs + 1);
@@ -986,10 +985,8 @@ static void build_units(dpf_index* h, int64_t npairs, bool filtered) {
     DPF_CUDA(cudaMemcpyAsync(&nunits, h->bm_ucnt.p + npairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaStreamSynchronize(st));
     h->bm_units.reserve((size_t)std::max<uint32_t>(nunits, 1) * sizeof(UnitRec));
-    if (filtered) DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));      // thresholds from the second stream
     k_emit_units<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_ucnt.p, h->pair_q.p, h->pair_len.p,
-                                     h->pair_seg.p, filtered ? h->bm_tau.p : nullptr, h->ids_sorted.p,
-                                     reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
+                                     h->pair_seg.p, h->ids_sorted.p, reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }
 
@@ -1063,7 +1060,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         k_copy_u32<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pair_len.p, h->pair_seg.p, npairs); DPF_LAUNCHED();
         exclusive_scan_u32(h, h->pair_seg.p, npairs);
         if (use_u8) {
-            // thresholds (and the survivor lists' bases and counters) before the units are cut: the records carry tau
+            // thresholds, and the survivor lists' bases and counters
             h->surv_id.reserve((size_t)std::max<int64_t>(entries_ub, 1));
             // pool: every entry can survive (tau = -inf), a block switch leaves < 32 slots unused, every warp ends on a
             // partial block
@@ -1082,8 +1079,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
             h->bm_tl_cnt.reserve((size_t)nqc * NT);
             // The threshold kernels (row gather) run on the handle's second stream next to the pair sort and the run /
-            // unit bookkeeping (a chain of small latency-bound kernels) on the main one; k_emit_units, which puts tau into
-            // the unit records, waits for them (build_units).
+            // unit bookkeeping (a chain of small latency-bound kernels) on the main one; the scoring kernel waits for both.
             cudaStream_t st2 = h->aux_stream;
             DPF_CUDA(cudaEventRecord(h->ev_fork, st));
             DPF_CUDA(cudaStreamWaitEvent(st2, h->ev_fork, 0));
@@ -1113,16 +1109,17 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         radix_sort_keys_u64(h, &a, &b, npairs, 32, 32 + ebits);
         h->bm_sorted = a;
         h->bm_npairs = npairs;
-        build_units(h, npairs, use_u8);
+        build_units(h, npairs);
     }
     unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(h->counters.p + 26);   // cleared by probe_count_all
-    const Filter flt{h->bm_scnt.p, h->bm_sbase.p, h->scores.p, h->surv_id.p, reinterpret_cast<SurvRec*>(h->surv_pool.p),
+    const Filter flt{h->bm_tau.p, h->bm_scnt.p, h->bm_sbase.p, h->scores.p, h->surv_id.p, reinterpret_cast<SurvRec*>(h->surv_pool.p),
                      reinterpret_cast<uint32_t*>(h->counters.p + 42)};
     {
         StageTimer tm(h, DPF_T_RERANK);
         h->stats[DPF_STAT_BM_PAIRS] += h->bm_npairs;
         const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
         if (use_u8) {
+            DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));    // thresholds from the second stream
             launch_score_u8(h, Qd, units, h->bm_counts.p + 1, metric, flt, bm_stat);
         } else {
             dispatch_kind(kind, ang, [&](auto a, auto kc) {

@@ -101,21 +101,14 @@ k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     unsigned long long rows_staged = 0;
     SurvivorSink sink;
 
-    // record of the next unit, loaded one unit ahead: lane j < 16 keeps query j, every lane one first-window id and
-    // the thresholds of the four queries its accumulators belong to
+    // record of the next unit, loaded one unit ahead: lane j < 16 keeps query j, every lane one first-window id
     uint32_t n_bstart, n_len, n_m;
     int n_q, n_id;
-    double n_tau[2][2];
     auto fetch_rec = [&](int64_t k) {
         const UnitRec* r = units + (gw + k * W);
         n_bstart = __ldg(&r->bstart); n_len = __ldg(&r->len); n_m = __ldg(&r->m);
         n_q = __ldg(&r->q[lane & (SS_UQ - 1)]);
         n_id = __ldg(&r->ids0[lane]);
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(&r->tau[8 * nb + 2 * t]));
-            n_tau[nb][0] = v.x; n_tau[nb][1] = v.y;
-        }
     };
     fetch_rec(0);
 
@@ -123,14 +116,13 @@ k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         const uint32_t bstart = n_bstart;
         const int len = (int)n_len, m = (int)n_m;
         const int my_q = n_q, id_first = n_id;
-        const double c_tau[2][2] = {{n_tau[0][0], n_tau[0][1]}, {n_tau[1][0], n_tau[1][1]}};
         if (k + 1 < nmine) fetch_rec(k + 1);
         rows_staged += (unsigned)len;
         const int nb_used = (m + 7) >> 3;
 
         // ---- query operand: k-step c * 16 + e <-> column 64c + 16t + e -----------------------------------------
         double B[2][32];
-        double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
+        double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}}, c_tau[2][2];
         int c_q[2][2];
         bool c_ok[2][2];
 #pragma unroll
@@ -151,6 +143,7 @@ k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
                 const int j = 8 * nb + 2 * t + e;
                 c_q[nb][e] = __shfl_sync(0xffffffffu, my_q, j);
                 c_ok[nb][e] = j < m;
+                c_tau[nb][e] = __ldg(flt.tau + c_q[nb][e]);
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c)
@@ -309,7 +302,7 @@ k_score_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
             for (int e = 0; e < 2; ++e) {
                 const int j = 8 * nb + 2 * t + e;
                 c_q[nb][e] = __shfl_sync(0xffffffffu, my_q, j);
-                const double tv = j < m ? __ldg(&r->tau[j]) : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
+                const double tv = j < m ? __ldg(flt.tau + c_q[nb][e]) : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
                 if (ANGULAR) { c_tau[nb][e] = tv; c_qn[nb][e] = __ldg(qnorm + c_q[nb][e]); }
                 // a dot product of bytes is below 2^31 - 1: INT_MAX masks the slot
                 else c_taui[nb][e] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
@@ -513,7 +506,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
             const unsigned char* qp = Q8 + (size_t)qj_nx[nb] * U8_QPITCH + 16 * t;
             bq_nx[nb][0] = ldg_u4(qp);
             bq_nx[nb][1] = ldg_u4(qp + 64);
-            tau_nx[nb] = j < m ? r->tau[j] : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
+            tau_nx[nb] = j < m ? __ldg(flt.tau + qj_nx[nb]) : __longlong_as_double(0x7ff0000000000000LL);   // +inf: masked
             if (ANGULAR) qn_nx[nb] = __ldg(qnorm + qj_nx[nb]);
             if (L2) qq_nx[nb] = __ldg(qsq + qj_nx[nb]);
         }

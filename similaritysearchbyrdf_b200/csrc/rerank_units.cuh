@@ -37,12 +37,8 @@ struct __align__(16) UnitRec {
     int32_t q[SS_UQ];      // query index of pair j
     uint32_t seg[SS_UQ];   // start of pair j's score segment (dense output: k_score_stream)
     int32_t ids0[SS_WIN];  // ids of the bucket's first 32 rows (the other windows are copied from ids_sorted)
-    double tau[SS_UQ];     // that query's score threshold (filtered output: k_score_u8*, see Filter); last, so that
-                           // k_score_stream, which does not filter, copies only the part before it
 };
 static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
-constexpr unsigned SS_REC_COPY = 16 + SS_UQ * 8 + SS_WIN * 4;      // = offsetof(UnitRec, tau)
-static_assert(SS_REC_COPY == offsetof(UnitRec, tau) && SS_REC_COPY % 16 == 0, "prefix copied by k_score_stream");
 
 // Threshold filter.  A batch produces ~50k (query, candidate) scores per query of which k survive.  Writing them all
 // and reading them back for the selection costs as many bytes as the byte rows themselves, so the scoring kernels
@@ -57,6 +53,7 @@ struct __align__(16) SurvRec {
     double score;
 };
 struct Filter {
+    const double* tau;     // per query: score threshold (k_threshold*)
     uint32_t* cnt;         // per query: survivors in its list so far
     const uint32_t* base;  // per query: start of its survivor list (capacity = all its bucket entries)
     double* s_score;

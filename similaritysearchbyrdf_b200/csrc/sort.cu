@@ -13,7 +13,8 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_STEPS = 16;                       // 32-item steps per warp
 constexpr int RS_TILE = RS_THREADS * RS_STEPS;     // 4096 items per CTA
-constexpr int RS_MAXBINS = 256;
+constexpr int RS_MAXBITS = 9;                      // digit width: 17 key bits of the build sort = 2 passes, 25 of the pair sort = 3
+constexpr int RS_MAXBINS = 1 << RS_MAXBITS;
 
 // ---- exclusive scan (uint32, in place) ---------------------------------------------------------------------
 constexpr int SC_THREADS = 256, SC_ITEMS = 8, SC_TILE = SC_THREADS * SC_ITEMS;
@@ -221,7 +222,7 @@ static void radix_sort_impl(dpf_index* h, K** keys, K** keys_alt, uint32_t** val
     if (n <= 1 || hi_bit <= lo_bit) return;
     DPF_REQUIRE(n < (1LL << 32), DPF_ERR_INVALID, "radix sort: more than 2^32 items in one call");
     const int total = hi_bit - lo_bit;
-    const int passes = (total + 7) / 8;
+    const int passes = (total + RS_MAXBITS - 1) / RS_MAXBITS;
     const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
     const size_t hist_elems = (size_t)RS_MAXBINS * ntiles;
     h->hist.reserve(hist_elems + scan_scratch_elems((int64_t)hist_elems));
