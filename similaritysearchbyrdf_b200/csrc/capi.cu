@@ -467,6 +467,16 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
         h->Xdev = h->X.p;
         Xnew = h->X.p + (size_t)h->n * d;
     }
+    if (h->store_mode != DPF_STORE_F64_ONLY && h->Xc_kind != DPF_STORE_KIND_F32) {
+        // room for a byte copy of the rows, taken before the build's scratch buffers carve up the pool's free blocks
+        // (allocated last it regularly cost a pool growth of several ms); released again if the data are not bytes
+        try {
+            h->Xc.grow_keep((size_t)(h->n + n) * (size_t)((h->cfg.d + 15) / 16 * 16), 0, h->stream);
+        } catch (const Error& err) {
+            if (err.code != DPF_ERR_NOMEM) throw;
+            cudaGetLastError();
+        }
+    }
     grow_keys(h, n);
     tr.mark("keys: allocate");
     hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
