@@ -118,7 +118,13 @@ void pids_to_host(dpf_index* h, const uint8_t* dev, int64_t count, int32_t* out)
     for (int64_t i = 0; i < count; ++i) out[i] = tmp[(size_t)i];
 }
 
-constexpr int64_t kCandBudget = 1LL << 29;   // ids of candidate scratch per chunk of queries (2 GiB)
+// ids of candidate scratch per chunk of queries (2 GiB); DPF_CAND_BUDGET overrides it (tests force many small chunks)
+static int64_t cand_budget() {
+    const char* e = getenv("DPF_CAND_BUDGET");
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? (int64_t)v : (1LL << 29);
+}
+#define kCandBudget cand_budget()
 
 // allocate the candidate scratch once for the largest chunk (a reallocation between chunks would serialise the
 // stream on cudaFree)

@@ -418,6 +418,29 @@ def test_threshold_filter_corner_cases(metric, byte_queries, monkeypatch):
     assert np.array_equal(ig == -1, io == -1)                 # padded rows where the candidates run out
 
 
+@pytest.mark.parametrize("store", ["u8", "f64"])
+def test_query_batch_cut_into_memory_bounded_chunks(store, monkeypatch):
+    """A tiny candidate budget forces the batch through dozens of chunks (expand / re-rank / select per chunk): results
+    must not depend on where the batch is cut — candidate sets and top-k, byte pipeline and FP64 pipeline."""
+    d = 64
+    X = _store_data(B.STORE_KIND_U8 if store == "u8" else B.STORE_KIND_F64, 3600, d, 91)
+    A, chain, Ap = U.make_functions(d, family_size=64, table_num=4, permutation_num=2, seed=92)
+    ix = U.make_index(d, A, chain, Ap, bucket_overflow=30)
+    ix.fit_dense(X)
+    Qs = X[::7] if store == "u8" else X[::7] + 0.01
+    ref_c = ix.query_candidates_dense(Qs, None, 1)
+    ref = [ix.query_topk_dense(Qs, None, 1, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2)]
+    monkeypatch.setenv("DPF_CAND_BUDGET", "20000")
+    U.assert_csr_equal(ref_c, ix.query_candidates_dense(Qs, None, 1))
+    for m, (ri, rs) in zip((B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2), ref):
+        gi, gs = ix.query_topk_dense(Qs, None, 1, 10, m)
+        assert np.array_equal(ri, gi) and np.array_equal(rs, gs, equal_nan=True), m
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=30)
+    o.fit_dense(X)
+    io, so = o.query_topk_dense(Qs, None, 1, 10, B.METRIC_DOT)
+    U.assert_topk_close(io, so, *ix.query_topk_dense(Qs, None, 1, 10, B.METRIC_DOT))
+
+
 def test_compact_store_append_widens():
     """Appending vectors that are not bytes re-types the store; results still equal the oracle's."""
     d = 64
