@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the scoring kernel on this workload (ncu --set full
 # captures summarised under profiles/); kernels without a capture report null
 NCU_TRAFFIC_BYTES = {"k_score_stream": 46_793_233_000 + 4_166_460_000,       # profiles/r1_ncu_full_k_score_stream.csv
-                     "k_score_u8s": 2_921_713_000 + 60_652_000}              # profiles/r1_ncu_full_u8_pipeline.csv
+                     "k_score_u8s": 2_820_156_000 + 60_886_000}              # profiles/r1_ncu_full_u8_pipeline.csv
 
 METRIC_NAME = "batch kNN queries/sec at fixed recall@10"
 UNIT = "queries/s"
