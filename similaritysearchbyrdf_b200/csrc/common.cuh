@@ -192,6 +192,8 @@ struct dpf_index {
     dpf::DevBuf<int32_t> ucnt, part_id;        // re-rank work units / partial top-k lists
     dpf::DevBuf<uint32_t> scan_scratch, pair_cnt, pair_base, pair_seg, pair_len;   // bucket-major re-rank
     dpf::DevBuf<int32_t> pair_q;
+    dpf::DevBuf<int2> probe_cache;             // distinct buckets per (query, table) from the probe pass
+    int probe_cache_cap = 0;                   //   slots per (query, table); 0 = not cached
     dpf::DevBuf<unsigned long long> pair_key, pair_key_alt;
     dpf::DevBuf<double> scores;                // bucket-major re-rank: survivor scores / ids (Filter, rerank_units.cuh)
     dpf::DevBuf<int32_t> surv_id;

@@ -23,7 +23,9 @@ namespace dpf {
 __global__ void __launch_bounds__(256)
 k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t nq,
               int32_t* __restrict__ q_ub, unsigned long long* __restrict__ stat /* [0] nlz>28 */,
-              uint32_t* __restrict__ pair_cnt /* nq x L distinct buckets per (query, table), may be null */) {
+              uint32_t* __restrict__ pair_cnt /* nq x L distinct buckets per (query, table), may be null */,
+              int2* __restrict__ cache /* (bucket ptr, size) of those buckets, `cache_cap` slots per (query, table), or null */,
+              int cache_cap) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= nq * c.L) return;
@@ -46,7 +48,9 @@ k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
         int ptr, cnt;
         warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);
         total += leader ? cnt : 0;
-        nbuckets += __popc(__ballot_sync(0xffffffffu, leader));
+        const uint32_t m = __ballot_sync(0xffffffffu, leader);
+        if (cache && leader) cache[wid * cache_cap + nbuckets + __popc(m & ((1u << lane) - 1u))] = make_int2(ptr, cnt);
+        nbuckets += __popc(m);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -175,11 +179,21 @@ void probe_count_all(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
     DPF_CUDA(cudaMemsetAsync(h->q_cnt.p, 0, (nq + 1) * sizeof(int32_t), st));
     h->pair_cnt.reserve((size_t)nq * c.L + 1);
     DPF_CUDA(cudaMemsetAsync(h->pair_cnt.p, 0, ((size_t)nq * c.L + 1) * sizeof(uint32_t), st));
+    // the distinct buckets found here are kept for the bucket-major re-rank (its pair list is exactly these), so that the
+    // forest is not walked a second time: <= (sub-indexes within `steps`) x 28 probe keys per (query, table)
+    int nsub = 0;
+    for (int sub = 0; sub < (1 << c.tp.pb); ++sub) nsub += __builtin_popcount((unsigned)sub) <= steps ? 1 : 0;
+    h->probe_cache_cap = nsub * (probe_mode == DPF_PROBE_NONE ? 1 : 28);
+    const size_t cache_elems = (size_t)nq * c.L * h->probe_cache_cap;
+    const bool use_cache = cache_elems * sizeof(int2) <= (512u << 20);
+    if (use_cache) h->probe_cache.reserve(cache_elems);
+    else h->probe_cache_cap = 0;
     {
         StageTimer tm(h, DPF_T_PROBE_COUNT);
         const int64_t warps = nq * c.L;
         k_probe_count<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, h->q_cnt.p, stat,
-                                                                    h->pair_cnt.p); DPF_LAUNCHED();
+                                                                    h->pair_cnt.p, use_cache ? h->probe_cache.p : nullptr,
+                                                                    h->probe_cache_cap); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         exclusive_scan_i64(h, h->q_cnt.p, h->q_off.p, nq);
     }

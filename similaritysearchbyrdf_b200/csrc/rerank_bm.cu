@@ -74,6 +74,27 @@ k_probe_pairs(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
     }
 }
 
+// the same fill from the buckets the probe pass cached (k_probe_count): no second walk of the forest
+__global__ void __launch_bounds__(256)
+k_pairs_from_cache(const int2* __restrict__ cache, int cap, const int64_t* __restrict__ table_base, int L, int64_t q0, int64_t nqc,
+                   const uint32_t* __restrict__ pair_base, unsigned long long* __restrict__ pair_key, int32_t* __restrict__ pair_q,
+                   uint32_t* __restrict__ pair_len) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wl = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wl >= nqc * L) return;
+    const int64_t q = q0 + wl / L;
+    const int t = (int)(wl % L);
+    const uint32_t at = pair_base[wl], nb = pair_base[wl + 1] - at;
+    const long long tbase = table_base[t];
+    const int2* src = cache + (q * L + t) * cap;
+    for (uint32_t i = lane; i < nb; i += 32) {
+        const int2 e = src[i];
+        pair_key[at + i] = ((unsigned long long)(tbase + e.x) << 32) | (at + i);
+        pair_q[at + i] = (int32_t)q;
+        pair_len[at + i] = (uint32_t)e.y;
+    }
+}
+
 // flag[p] = 1 where a run starts
 __global__ void __launch_bounds__(256)
 k_run_flags(const unsigned long long* __restrict__ sorted, int64_t npairs, uint32_t* __restrict__ flag) {
@@ -1054,8 +1075,14 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         h->pair_seg.reserve(npairs + 1);
         h->scores.reserve((size_t)std::max<int64_t>(entries_ub, 1));
         const int64_t warps = nqc * L;
-        k_probe_pairs<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->pair_base.p,
-                                                                    h->pair_key.p, h->pair_q.p, h->pair_len.p); DPF_LAUNCHED();
+        if (h->probe_cache_cap > 0)
+            k_pairs_from_cache<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(h->probe_cache.p, h->probe_cache_cap, c.f.table_base, L, q0,
+                                                                             nqc, h->pair_base.p, h->pair_key.p, h->pair_q.p,
+                                                                             h->pair_len.p);
+        else
+            k_probe_pairs<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->pair_base.p,
+                                                                        h->pair_key.p, h->pair_q.p, h->pair_len.p);
+        DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         k_copy_u32<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pair_len.p, h->pair_seg.p, npairs); DPF_LAUNCHED();
         exclusive_scan_u32(h, h->pair_seg.p, npairs);
