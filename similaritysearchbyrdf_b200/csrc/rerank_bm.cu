@@ -1,24 +1,29 @@
-// rerank_bm.cu — K5b: bucket-major re-rank on the FP64 tensor pipe.
+// rerank_bm.cu — K5b: bucket-major re-rank.
 //
 // Replaces topKAndPrecisionScore's gather + dgemv + argsort (src/main/scala/mclab/deploy/DensevectorRDFInit.scala:
 // 472-507) for a whole query batch.  The row-major kernel in query.cu reads a candidate row once per (query,
 // candidate): 8d bytes of HBM for 2d flops.  In a batch, many queries probe the same leaf buckets (a bucket is
 // probed by every query whose key falls in it or one bit away), so the same rows are fetched again and again.
 // Here the batch is regrouped by bucket:
-//   k_probe_pairs    one (bucket, query) pair per distinct bucket a query probes (same walk as K4)
+//   k_pairs_from_cache / k_probe_pairs   one (bucket, query) pair per distinct bucket a query probes: the buckets the
+//                    probe pass (K4, k_probe_count) found, or the same walk again when they were not cached
 //   radix sort       pairs by bucket start
 //   k_run_flags .. k_emit_units   runs of pairs that share a bucket, cut into units of <= 16 queries; one
 //                    self-contained record per unit (bucket, query list, score segments, first row ids)
-//   k_score_stream   a warp per unit: the unit's queries and then the bucket's rows stream L2/HBM -> shared memory
-//                    through a per-warp ring of TMA bulk copies (one 8d-byte copy per row, mbarrier completion, 2
-//                    slots of 8 rows in flight per warp while a third is consumed); queries become DMMA B fragments
-//                    in registers, rows are multiplied against them -> one score per (pair, row)
-//   k_select_pairs   per query: top-k over its score segments, de-duplicating ids reached through several tables
-//                    (their scores are bit-identical: same row, same query, same k order)
-// Per step this replaces nC_q * 8d bytes per query by ~(bucket rows * 8d) per <= 16 queries plus 16 B per (query,
-// candidate).  Candidate *sets* are unchanged (same probe), so results equal the row-major path up to summation
-// order.  Why TMA rows: tools/gather_patterns.cu — a DMMA A-fragment gather straight from HBM touches 8 rows x 64 B
-// per instruction and collapses to 2.9 TB/s at high occupancy; 1 KB bulk row copies hold 7.3 TB/s with 8 warps/SM.
+// and scored unit by unit, in one of two pipelines chosen by the store (store.cu):
+//   FP64 (float) rows   k_score_stream: a warp per unit; the unit's queries and then the bucket's rows stream L2/HBM ->
+//                    shared memory through a per-warp ring of TMA bulk copies (one copy per row, mbarrier completion, 2
+//                    slots of 8 rows in flight per warp while a third is consumed); queries become DMMA B fragments in
+//                    registers, rows are multiplied against them -> one score per (pair, row), dense;
+//                    k_select_pairs: per query, top-k over its score segments
+//   byte rows        k_threshold* (here / rerank_u8.cu): per query a score that k distinct candidates provably reach;
+//                    k_score_u8s / k_score_u8d (rerank_u8.cu): integer / FP64 tensor pipe, only scores >= the threshold
+//                    are emitted (SurvivorSink); k_scatter_survivors, k_select_survivors(_big): per-query lists, top-k
+// Both de-duplicate ids reached through several tables (their scores are bit-identical: same row, same query, same k
+// order).  Candidate *sets* are unchanged (same probe), so results equal the row-major path up to summation order
+// (exactly, on integer data).  Why TMA rows for FP64: tools/gather_patterns.cu — a DMMA A-fragment gather straight from
+// HBM touches 8 rows x 64 B per instruction and collapses to 2.9 TB/s at high occupancy; 1 KB bulk row copies hold
+// 7.3 TB/s with 8 warps/SM.
 #include <cstdlib>
 #include <type_traits>
 
