@@ -441,6 +441,26 @@ def test_query_batch_cut_into_memory_bounded_chunks(store, monkeypatch):
     U.assert_topk_close(io, so, *ix.query_topk_dense(Qs, None, 1, 10, B.METRIC_DOT))
 
 
+@pytest.mark.parametrize("kind", [B.STORE_KIND_U8, B.STORE_KIND_F64])
+def test_tiny_batches_and_tiny_indexes(kind):
+    """One query, two queries, an index smaller than k: grids of one CTA, lists that never fill, padded results."""
+    d = 32
+    A, chain, Ap = U.make_functions(d, family_size=40, table_num=3, permutation_num=1, seed=55)
+    for n in (12, 300):
+        X = _store_data(kind, n, d, 60 + n)
+        o = U.make_oracle(d, A, chain, Ap, bucket_overflow=10); ix = U.make_index(d, A, chain, Ap, bucket_overflow=10)
+        o.fit_dense(X); ix.fit_dense(X)
+        assert ix.stats()["store_kind"] == kind
+        for nq in (1, 2, 5):
+            Qs = np.ascontiguousarray(X[:nq]) if kind == B.STORE_KIND_U8 else X[:nq] + 0.125
+            for metric in (B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2):
+                for steps in (0, 3):
+                    io, so = o.query_topk_dense(Qs, None, steps, 10, metric)
+                    ig, sg = ix.query_topk_dense(Qs, None, steps, 10, metric)
+                    U.assert_topk_close(io, so, ig, sg)
+            U.assert_csr_equal(o.query_candidates_dense(Qs, None, 1), ix.query_candidates_dense(Qs, None, 1))
+
+
 def test_compact_store_append_widens():
     """Appending vectors that are not bytes re-types the store; results still equal the oracle's."""
     d = 64
