@@ -57,35 +57,91 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_tile(uint32_t* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(SC_THREADS) k_scan_add(uint32_t* __restrict__ data, int64_t n,
-                                                         const uint32_t* __restrict__ partials) {
-    const uint32_t add = partials[blockIdx.x];
-    const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+// Single-pass scan for arrays of more than one tile: tiles take their index from a counter (so a tile only ever waits
+// for tiles that are already running), publish their aggregate, and warp 0 looks back over the predecessors' status
+// words 32 at a time — (flag << 32 | value), flag 1 = aggregate of that tile, 2 = inclusive prefix up to and including
+// it — until it meets a prefix.  One read and one write of the data instead of the three kernels of the tile / add form.
+constexpr int SL_ITEMS = 16, SL_TILE = SC_THREADS * SL_ITEMS;
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_lookback(uint32_t* __restrict__ data, int64_t n, unsigned int* __restrict__ counter,
+                                                              volatile unsigned long long* __restrict__ status) {
+    __shared__ uint32_t wsum[SC_THREADS / 32];
+    __shared__ uint32_t s_tile, s_total, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * SL_TILE + (int64_t)threadIdx.x * SL_ITEMS;
+    uint32_t v[SL_ITEMS], s = 0;
 #pragma unroll
-    for (int i = 0; i < SC_ITEMS; ++i)
-        if (base + i < n) data[base + i] += add;
+    for (int i = 0; i < SL_ITEMS; ++i) {
+        v[i] = (base + i < n) ? data[base + i] : 0u;
+        s += v[i];
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t ws = lane < SC_THREADS / 32 ? wsum[lane] : 0u, wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        if (lane < SC_THREADS / 32) wsum[lane] = wi - ws;
+        const uint32_t total = __shfl_sync(0xffffffffu, wi, SC_THREADS / 32 - 1);
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) status[0] = (2ULL << 32) | total;
+        } else {
+            if (lane == 0) status[tile] = (1ULL << 32) | total;
+            long long p = (long long)tile - 1;                        // look back: lane l reads tile p - l
+            for (;;) {
+                const long long mine = p - lane;
+                unsigned long long st = mine >= 0 ? 0ULL : (2ULL << 32);   // before tile 0: an empty prefix
+                if (mine >= 0)
+                    do { st = status[mine]; } while ((st >> 32) == 0ULL);
+                const uint32_t has_prefix = __ballot_sync(0xffffffffu, (st >> 32) == 2ULL);
+                const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest predecessor with a full prefix
+                uint32_t part = lane <= first ? (uint32_t)st : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (has_prefix) break;
+                p -= 32;
+            }
+            if (lane == 0) status[tile] = (2ULL << 32) | (unsigned long long)(prefix + total);
+        }
+        if (lane == 0) { s_prefix = prefix; s_total = total; }
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + wsum[w] + inc - s;
+#pragma unroll
+    for (int i = 0; i < SL_ITEMS; ++i) {
+        if (base + i < n) data[base + i] = run;
+        run += v[i];
+    }
 }
 
-// scratch must hold ceil(n/SC_TILE) + ceil(that/SC_TILE) + ... entries
+// scratch: see scan_scratch_elems
 static void scan_u32_inplace(uint32_t* data, int64_t n, uint32_t* scratch, cudaStream_t st) {
-    const int64_t nb = (n + SC_TILE - 1) / SC_TILE;
-    if (nb <= 1) {
+    if (n <= SC_TILE) {
         k_scan_tile<<<1, SC_THREADS, 0, st>>>(data, n, nullptr); DPF_LAUNCHED();
         return;
     }
-    k_scan_tile<<<(unsigned)nb, SC_THREADS, 0, st>>>(data, n, scratch); DPF_LAUNCHED();
-    scan_u32_inplace(scratch, nb, scratch + nb, st);
-    k_scan_add<<<(unsigned)nb, SC_THREADS, 0, st>>>(data, n, scratch); DPF_LAUNCHED();
+    const int64_t nb = (n + SL_TILE - 1) / SL_TILE;
+    // [0..1] tile counter (+ pad to 8 bytes), then one 64-bit status word per tile
+    cudaMemsetAsync(scratch, 0, (size_t)(2 + 2 * nb) * sizeof(uint32_t), st);
+    k_scan_lookback<<<(unsigned)nb, SC_THREADS, 0, st>>>(data, n, scratch, reinterpret_cast<unsigned long long*>(scratch + 2)); DPF_LAUNCHED();
 }
 
 static size_t scan_scratch_elems(int64_t n) {
-    size_t tot = 0;
-    while (n > 1) {
-        n = (n + SC_TILE - 1) / SC_TILE;
-        tot += (size_t)n;
-        if (n <= 1) break;
-    }
-    return tot + 8;
+    return (size_t)(2 + 2 * ((n + SL_TILE - 1) / SL_TILE)) + 8;
 }
 
 // int32 counts -> int64 exclusive offsets (n+1 entries), single CTA chained over tiles; used for per-query
