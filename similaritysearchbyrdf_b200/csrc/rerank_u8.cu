@@ -2,18 +2,20 @@
 //
 // Same job as k_score_stream (rerank_bm.cu): for every unit (one leaf bucket x <= 16 queries that probe it) one
 // score per (query, bucket row), replacing the gather + dgemv of topKAndPrecisionScore
-// (src/main/scala/mclab/deploy/DensevectorRDFInit.scala:472-507).  When the store is bytes a row is <= 128 B, i.e.
-// two 16-byte chunks per thread of a DMMA row group: the rows go straight from L2/HBM to registers with LDG.128
-// (a whole 8-row tile is 2 loads per thread), PF tiles in flight per warp, no shared-memory ring, no bulk copies, no
-// barriers — the per-row issue cost of the TMA pipeline, which bounds k_score_stream once the bytes are cheap, is gone.
-// Two instantiations:
-//   INTQ = false  queries are arbitrary doubles: bytes are widened to the identical doubles in registers (PRMT +
-//                 DADD) and multiplied on the FP64 tensor pipe (DMMA.8x8x4) against the FP64 query fragments.
-//   INTQ = true   every query of the batch is itself a vector of bytes (checked per batch, k_quantise_queries): all
-//                 products and partial sums are integers below 2^31, so the integer tensor pipe (IMMA.16x8x32,
-//                 u8 x u8 -> s32) computes the exact dot product and (double)dot is bit-identical to the FP64 sum in any
-//                 order.  This is the SIFT case (descriptors and queries are bytes).
-// k permutation (both): thread t of a row group holds bytes [16t, 16t+16) and [64+16t, 64+16t+16) of its row; the
+// (src/main/scala/mclab/deploy/DensevectorRDFInit.scala:472-507) — but only scores that can still be among the query's
+// best k leave the kernel (threshold filter, rerank_units.cuh).  When the store is bytes a row is <= 128 B, i.e. two
+// 16-byte chunks per thread of a tensor-pipe row group, and the per-row issue cost of the TMA pipeline, which bounds
+// k_score_stream once the bytes are cheap, can go.  Kernels:
+//   k_score_u8s   every query of the batch is itself a vector of bytes (checked per batch, k_quantise_queries): all
+//                 products and partial sums are integers below 2^31, so the integer tensor pipe (IMMA.16x8x32, u8 x u8 ->
+//                 s32) computes the exact dot product and (double)dot is bit-identical to the FP64 sum in any order.
+//                 This is the SIFT case (descriptors and queries are bytes).  Rows and unit records stream through
+//                 shared memory with cp.async; dot, angular and (exactly, as integers) squared L2.
+//   k_score_u8i   the same arithmetic with the rows loaded into registers, kept for comparison (DPF_U8I_KERNEL=lean).
+//   k_score_u8d   queries are arbitrary doubles: bytes are widened to the identical doubles in registers (PRMT + DADD)
+//                 and multiplied on the FP64 tensor pipe (DMMA.8x8x4) against the FP64 query fragments.
+//   k_threshold_u8i   the threshold samples for byte queries, also on the integer tensor pipe.
+// k permutation (all): thread t of a row group holds bytes [16t, 16t+16) and [64+16t, 64+16t+16) of its row; the
 // query operand uses the same columns, so the sum over k is unchanged.
 #include <cstdlib>
 #include <type_traits>
