@@ -265,7 +265,8 @@ def run_ours(args):
         barrier()
         clk = clocks.stop()
         dt_ms = e0.elapsed_time(e1)
-        launches = (ix.stats()["kernel_launches"] - launches0) // max(args.steps, 1)
+        launches_total = ix.stats()["kernel_launches"] - launches0          # this library's kernels inside the timed region
+        launches = launches_total // max(args.steps, 1)
         t = torch.tensor([dt_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -432,7 +433,7 @@ def run_ours(args):
         "recall_at_10": recall, "clocks": clk,
         "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nq * d * 8),
                 "d2h_bytes_per_step": int(nq * K * 12), "ms_per_step": e2e_ms},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "build": {"vectors_per_s": n / (build_ms * 1e-3), "ms": build_ms, "stage_ms": build_stage,
                   "e2e_vectors_per_s": n / (e2e_build_ms * 1e-3) if e2e_build_ms else None,
