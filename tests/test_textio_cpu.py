@@ -75,3 +75,25 @@ def test_sparse_file_matches_line_parser(tmp_path):
     bad.write_text("[0, 10, [1, 2, 3], [1.0, 2.0]]\n")
     with pytest.raises(ValueError):
         deploy.load_sparse_file(bad)
+
+
+def test_dense_parser_number_formats(tmp_path):
+    """Java's toDouble and strtod accept the same decimal / scientific spellings; every spelling must give the identical
+    double, whatever the spacing around brackets and commas."""
+    from hypothesis import given, settings, strategies as st
+
+    fmts = ["{!r}", "{:.17g}", "{:.17e}", "{:+.17e}", "{:.20f}"]
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.floats(allow_nan=False, allow_infinity=False, width=64), min_size=3, max_size=3), st.integers(0, len(fmts) - 1),
+           st.sampled_from(["", " ", "  "]))
+    def check(vals, f, sp):
+        if fmts[f] == "{:.20f}" and any(v != 0 and not (1e-2 <= abs(v) <= 1e15) for v in vals):
+            return                                              # 20 decimals do not round-trip outside this range
+        p = tmp_path / "f.txt"
+        p.write_text(f"[{sp}7,{sp}[" + f",{sp}".join(fmts[f].format(v) for v in vals) + f"]{sp}]\n")
+        got = deploy.load_dense_file(p, d=3)
+        assert got.shape == (1, 3)
+        assert np.array_equal(got[0].view(np.uint64), np.array(vals, np.float64).view(np.uint64)), (vals, fmts[f])
+
+    check()
