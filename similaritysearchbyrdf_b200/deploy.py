@@ -269,6 +269,24 @@ class LSH:
     def family_kind(self):
         return B.FAMILY_PSTABLE if self.name == "pStable" else B.FAMILY_ANGLE
 
+    def calculateIndex(self, vector, tableId=-1):
+        """LSH.calculateIndex (LSH.scala:93-166): keys of all tables (tableId < 0) or `Array(key)` of one table, with the
+        configured typeOfIndex transform.  Evaluated by the library (dpf_hash_dense / dpf_hash_csr) on a private handle
+        that holds only the hash functions."""
+        if getattr(self, "_hasher", None) is None:
+            d = self.conf.getInt("mclab.lsh.vectorDim")
+            self._hasher = DPFIndex(d=d, L=self.chain.shape[0], k=self.chain.shape[1], pb=0, family_kind=self.family_kind,
+                                    key_transform=_TRANSFORMS[self.typeOfIndex],
+                                    device=int(self.conf.get("mclab.gpu.device", 0)))
+            self._hasher.set_family(self.A, self.chain, self.b, self.w)
+        if isinstance(vector, SparseVector):
+            keys, _ = self._hasher.hash_csr(np.array([0, len(vector.indices)], np.int64), vector.indices, vector.values)
+        else:
+            values = vector.values if isinstance(vector, DenseVector) else np.asarray(vector, np.float64)
+            keys, _ = self._hasher.hash_dense(values[None, :])
+        keys = keys[:, 0]
+        return keys.copy() if tableId < 0 else keys[tableId:tableId + 1].copy()
+
 
 class LSHServer:
     """Global engine holder (LSHServer.scala:5-18)."""
@@ -320,6 +338,21 @@ class _RDFInit:
         self.index.set_family(lsh.A, lsh.chain, lsh.b, lsh.w)
         self.index.set_partitioners(Ap)
         self.partitioners = Ap
+
+    @property
+    def vectorIdToVector(self):
+        """The reference's dataTable (id -> vector), here the list of vectors in id order (get = indexing, size = len)."""
+        return self.vectors
+
+    @property
+    def vectorDatabase(self):
+        """The reference's `Array[RandomDrawTreeMap]`, one per table: here per-table views of the flat forest
+        (`dump()` = canonical leaf buckets of that table)."""
+        if self.index is None:
+            return []
+        ix = self.index
+        return [type("TableView", (), {"tableId": t, "dump": (lambda self_, t=t: ix.dump_buckets(t)),
+                                       "size": (lambda self_: len(ix))})() for t in range(ix.L)]
 
     def close(self):
         if self.index is not None:

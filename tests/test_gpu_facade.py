@@ -152,6 +152,34 @@ def test_full_size_properties_config2_sample():
     assert np.all(np.diff(sc, axis=1) >= 0)
 
 
+def test_deploy_lsh_calculate_index_and_views(tmp_path):
+    """LSHServer.lshEngine.calculateIndex (LSH.scala:93-166) and the public vars vectorDatabase / vectorIdToVector."""
+    from similaritysearchbyrdf_b200 import deploy
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((500, 16))
+    path = tmp_path / "dense.txt"
+    with open(path, "w") as f:
+        for i, row in enumerate(X):
+            f.write(f"[{i},[" + ",".join(repr(float(v)) for v in row) + "]]\n")
+    conf = deploy.Config.parseString("mclab.lsh.vectorDim=16\nmclab.lsh.tableNum=3\nmclab.lsh.permutationNum=2\n"
+                                     "mclab.lsh.familySize=40\nmclab.lshTable.bufferOverflow=20").withFallback(deploy.testBaseConf)
+    deploy.LSHServer.lshEngine = None
+    vecs = deploy.DensevectorRDFInit.newMultiThreadFit(str(path), conf)
+    try:
+        lsh = deploy.LSHServer.getLSHEngine()
+        o = U.make_oracle(16, lsh.A, lsh.chain, deploy.DensevectorRDFInit.partitioners, bucket_overflow=20)
+        ko, _ = o.hash_dense(X[:7])
+        for i in range(7):
+            assert np.array_equal(lsh.calculateIndex(vecs[i], -1), ko[:, i])
+            assert lsh.calculateIndex(vecs[i], 4)[0] == ko[4, i]
+        assert len(deploy.DensevectorRDFInit.vectorIdToVector) == 500
+        tables = deploy.DensevectorRDFInit.vectorDatabase
+        assert len(tables) == 6 and tables[0].size() == 500 and len(tables[2].dump()[2]) == 500
+    finally:
+        deploy.DensevectorRDFInit.clearAndClose()
+        deploy.LSHServer.lshEngine = None
+
+
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_balanced_partition_ranks_merge_to_the_unsharded_result(world):
     """dpf_set_balanced_partition: sub-indexes dealt to the ranks by occupancy.  Every sub-index is owned by exactly one
