@@ -158,6 +158,8 @@ int dpf_load(const char* path, int32_t device, dpf_handle* out);
  * dense fit deals the sub-indexes to the GPUs by occupancy instead (largest first, to the least loaded GPU); every rank
  * derives the same assignment from the replicated vectors.  Results are unaffected.  Call before fit. */
 int dpf_set_balanced_partition(dpf_handle h, int32_t enable);
+/* owned_out[p] = 1 for the 2^pb sub-indexes this handle owns (after the first fit when the assignment is balanced) */
+int dpf_owned_subindexes(dpf_handle h, uint8_t* owned_out);
 
 /* ---- multi-GPU: merge per-GPU top-k lists after the NCCL all-gather -----------------------
  * gathered_*_dev: G x nq x topk as produced by all-gathering dpf_query_topk_dense_dev outputs; duplicates of

@@ -265,6 +265,11 @@ struct dpfo {
     std::vector<int64_t> cand_off;
     std::vector<int32_t> cand_ids;
     std::atomic<int64_t> nlz_gt28{0};
+    std::vector<uint8_t> owned;       // explicit ownership of sub-indexes (dpfo_set_owned); empty = p % world == rank
+    bool owns(int p) const {
+        if (!owned.empty()) return owned[(size_t)p] != 0;
+        return cfg.world <= 1 || (p % cfg.world) == cfg.rank;
+    }
 };
 
 namespace {
@@ -444,7 +449,7 @@ void table_query(dpfo* o, const Table& T, int table, int32_t h, int32_t qid, int
     for (int pi = 0; pi < nprobes; ++pi) {
         for (int s = 0; s < np; ++s) {                       // findStepWiseSubIndexIDs :613-621
             if (java_bitcount(s ^ pid) > steps) continue;
-            if (o->cfg.world > 1 && (s % o->cfg.world) != o->cfg.rank) continue;   // another shard owns it
+            if (!o->owns(s)) continue;                       // another shard owns it
             const std::vector<int32_t>* b = table_lookup(o, T, s, seg, probes[pi]);
             if (!b) continue;
             for (int32_t y : *b) {
@@ -539,6 +544,15 @@ int dpfo_set_family(dpfo* o, const double* A, const int32_t* chain_idx, const do
     return 0;
 }
 
+/* explicit shard: owned[p] != 0 for the 2^pb sub-indexes this instance builds and searches (the GPU library's balanced
+ * assignment, dpf_set_balanced_partition); NULL restores p % world == rank */
+int dpfo_set_owned(dpfo* o, const uint8_t* owned) {
+    if (!o) return 1;
+    if (!owned) { o->owned.clear(); return 0; }
+    o->owned.assign(owned, owned + ((size_t)1 << o->cfg.pb));
+    return 0;
+}
+
 int dpfo_set_partitioners(dpfo* o, const double* Ap) {
     o->Ap.assign(Ap, Ap + (size_t)o->cfg.L * o->cfg.pb * 32);
     return 0;
@@ -600,7 +614,7 @@ static int fit_common(dpfo* o, const std::vector<int32_t>& keys, const std::vect
                     Tb.pids[base + i] = pids[(size_t)t * n + i];
                 }
                 for (int64_t i = 0; i < n; ++i) {
-                    if (o->cfg.world > 1 && (pids[(size_t)t * n + i] % o->cfg.world) != o->cfg.rank) continue;
+                    if (!o->owns(pids[(size_t)t * n + i])) continue;
                     table_insert(o, Tb, (int32_t)(base + i), keys[(size_t)t * n + i], pids[(size_t)t * n + i]);
                 }
             }

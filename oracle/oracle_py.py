@@ -44,6 +44,7 @@ def lib():
         L.dpfo_destroy.argtypes = [vp]
         L.dpfo_set_family.argtypes = [vp, vp, vp, vp, vp]
         L.dpfo_set_partitioners.argtypes = [vp, vp]
+        L.dpfo_set_owned.argtypes = [vp, vp]
         L.dpfo_hash_dense.argtypes = [vp, vp, i64, vp, vp, C.c_int]
         L.dpfo_hash_csr.argtypes = [vp, vp, vp, vp, i64, vp, vp, C.c_int]
         L.dpfo_fit_dense.argtypes = [vp, vp, i64, C.c_int]
@@ -200,6 +201,11 @@ class Oracle:
         Ap = _f64(Ap)
         assert Ap.shape == (self.L, self.pb, 32)
         lib().dpfo_set_partitioners(self.h, _p(Ap))
+
+    def set_owned(self, owned):
+        """Explicit shard: flags of the sub-indexes this instance owns (None = p % world == rank)."""
+        owned = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+        lib().dpfo_set_owned(self.h, _p(owned))
 
     def hash_dense(self, X, nthreads=0):
         X = _f64(X)

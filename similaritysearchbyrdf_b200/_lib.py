@@ -26,7 +26,7 @@ EXPORTS = [
     "dpf_set_partitioners", "dpf_hash_dense", "dpf_hash_csr", "dpf_fit_dense", "dpf_fit_csr", "dpf_fit_dense_dev",
     "dpf_size", "dpf_query_candidates_dense", "dpf_query_candidates_csr", "dpf_query_candidates_by_id",
     "dpf_query_topk_dense", "dpf_query_topk_dense_dev", "dpf_rerank_dense", "dpf_merge_topk_dev", "dpf_dump_buckets",
-    "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms", "dpf_set_store_mode", "dpf_save", "dpf_load", "dpf_set_balanced_partition", "dpf_parse_dense_file", "dpf_parse_sparse_file",
+    "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms", "dpf_set_store_mode", "dpf_save", "dpf_load", "dpf_set_balanced_partition", "dpf_owned_subindexes", "dpf_parse_dense_file", "dpf_parse_sparse_file",
 ]
 
 
@@ -86,6 +86,7 @@ def load():
     L.dpf_stage_times_ms.argtypes = [vp, vp]
     L.dpf_set_store_mode.argtypes = [vp, i32]
     L.dpf_set_balanced_partition.argtypes = [vp, i32]
+    L.dpf_owned_subindexes.argtypes = [vp, vp]
     L.dpf_save.argtypes = [vp, C.c_char_p]
     L.dpf_parse_dense_file.argtypes = [C.c_char_p, i32, vp, i64, vp]
     L.dpf_parse_sparse_file.argtypes = [C.c_char_p, vp, vp, vp, i64, i64, vp, vp, vp]

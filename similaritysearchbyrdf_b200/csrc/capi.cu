@@ -505,6 +505,13 @@ int dpf_set_balanced_partition(dpf_handle h, int32_t enable) {
     });
 }
 
+int dpf_owned_subindexes(dpf_handle h, uint8_t* owned_out) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(owned_out, DPF_ERR_INVALID, "null buffer");
+        for (int p = 0; p < (1 << h->cfg.pb); ++p) owned_out[p] = h->own.has(p) ? 1 : 0;
+    });
+}
+
 int dpf_set_store_mode(dpf_handle h, int32_t mode) {
     return guarded(h, [&] {
         DPF_REQUIRE(mode == DPF_STORE_AUTO || mode == DPF_STORE_F64_ONLY || mode == DPF_STORE_NARROWEST, DPF_ERR_INVALID, "bad store mode");

@@ -103,6 +103,12 @@ class DPFIndex:
         """Multi-GPU: deal the sub-indexes to the ranks by occupancy at the first fit instead of p % world."""
         self._ck(self.lib.dpf_set_balanced_partition(self.h, 1 if on else 0))
 
+    def owned_subindexes(self):
+        """Flags (uint8, 2^pb) of the sub-indexes this handle owns."""
+        out = np.zeros(1 << self.pb, np.uint8)
+        self._ck(self.lib.dpf_owned_subindexes(self.h, _p(out)))
+        return out
+
     # ---- hash functions -------------------------------------------------------------------------------------
     def set_family(self, A, chain_idx, b=None, w=None):
         A, chain_idx = _f64(A), _i32(chain_idx)

@@ -205,6 +205,15 @@ def test_balanced_partition_ranks_merge_to_the_unsharded_result(world):
             cands.append(s.query_candidates_dense(Qs, None, 1))
             sizes.append(sum(len(s.dump_buckets(t)[2]) for t in range(chain.shape[0])))
         assert sum(sizes) == 8000 * chain.shape[0]                   # every (table, id) entry lives on exactly one rank
+        owned = np.stack([s.owned_subindexes() for s in shards])
+        assert (owned.sum(axis=0) == 1).all()                          # every sub-index has exactly one owner
+        if balanced:                                                   # each shard = the oracle restricted to the same sub-indexes
+            for r, s in enumerate(shards):
+                o = U.make_oracle(100, A, chain, Ap, bucket_overflow=40)
+                o.set_owned(owned[r])
+                o.fit_dense(X)
+                U.assert_buckets_equal(o, s, chain.shape[0])
+                U.assert_csr_equal(o.query_candidates_dense(Qs, None, 1), cands[r])
         loads[balanced] = max(sizes)
         g_ids = torch.from_numpy(np.stack([p[0] for p in per])).cuda()
         g_sc = torch.from_numpy(np.stack([p[1] for p in per])).cuda()

@@ -72,3 +72,29 @@ def test_merge_host_dedups_and_orders():
     gsc = np.array([[[9.0, 7.0, np.nan]], [[7.0, 6.0, 2.0]]])
     i, s = merge_topk_host(gids, gsc)
     assert i.tolist() == [[5, 3, 9]] and s.tolist() == [[9.0, 7.0, 6.0]]
+
+
+def test_oracle_explicit_ownership_partitions_the_forest():
+    """dpfo_set_owned (the checker of the library's balanced assignment): shards with complementary sub-index sets hold
+    disjoint parts of every table and their candidate sets unite to the unsharded ones."""
+    from similaritysearchbyrdf_b200 import synth
+    from tests import util as U
+    X, Q = synth.config1(n=3000)
+    A, chain, Ap = U.make_functions(100)
+    full = U.make_oracle(100, A, chain, Ap, bucket_overflow=40)
+    full.fit_dense(X)
+    Qs = np.concatenate([Q, X[:40] + 0.01])
+    f_off, f_cand = full.query_candidates_dense(Qs, None, 1)
+    masks = [np.array([1, 0, 0, 1, 1, 0, 0, 0], np.uint8), np.array([0, 1, 0, 0, 0, 0, 1, 1], np.uint8),
+             np.array([0, 0, 1, 0, 0, 1, 0, 0], np.uint8)]
+    cands, sizes = [], []
+    for m in masks:
+        o = U.make_oracle(100, A, chain, Ap, bucket_overflow=40)
+        o.set_owned(m)
+        o.fit_dense(X)
+        cands.append(o.query_candidates_dense(Qs, None, 1))
+        sizes.append(sum(len(o.dump_buckets(t)[2]) for t in range(chain.shape[0])))
+    assert sum(sizes) == 3000 * chain.shape[0]
+    for i in range(len(Qs)):
+        u = np.unique(np.concatenate([c[1][c[0][i]:c[0][i + 1]] for c in cands]))
+        assert np.array_equal(u, f_cand[f_off[i]:f_off[i + 1]])
