@@ -203,6 +203,26 @@ enum {
     DPF_T_COUNT = 16
 };
 int dpf_set_profiling(dpf_handle h, int32_t enable);
+
+/* ---- test / profiling hooks.  The product path reads no environment variable: which kernel variant runs is a
+ * property of the handle, changed only through this call (defaults = the product path).  Tests use it to compare the
+ * independent kernels with each other and with the oracle. */
+enum {
+    DPF_DBG_RERANK = 0,       /* 0 bucket-major when supported (default), 1 always the row-major kernel              */
+    DPF_DBG_BM_KERNEL = 1,    /* 0 default, 1 the TMA-ring FP64 kernel (k_score_stream) even on byte rows             */
+    DPF_DBG_U8_IMMA = 2,      /* 1 default: integer tensor pipe on byte rows x byte queries; 0: FP64 tensor pipe      */
+    DPF_DBG_U8I_KERNEL = 3,   /* 0 default (tcgen05 when the shape allows, else mma.sync ring), 1 lean register
+                                 gather, 2 mma.sync cp.async ring, 3 tcgen05                                          */
+    DPF_DBG_TAU_TABLES = 4,   /* threshold samples per query; 0 = default                                             */
+    DPF_DBG_TAU_KERNEL = 5,   /* 0 default (tensor pipe), 1 CUDA-core DP4A / FMA form                                 */
+    DPF_DBG_HASH_EXACT = 6,   /* 1: angle keys from the reference-order CUDA-core kernel instead of DMMA + fix-up     */
+    DPF_DBG_CAND_BUDGET = 7,  /* candidate ids per chunk of a query batch (row-major / candidate-set paths); 0 default */
+    DPF_DBG_TRACE = 8,        /* 1: host wall-clock per phase of a fit, to stderr                                     */
+    DPF_DBG_STORE = 9,        /* 0 default, 1 keep FP64 rows only, 2 force a float copy (skips the byte check)        */
+    DPF_DBG_POOL_RECORDS = 10,/* capacity of the survivor pool in records; 0 = default (tests force the overflow path) */
+    DPF_DBG_COUNT = 16
+};
+int dpf_set_debug_option(dpf_handle h, int32_t option, int64_t value);
 int dpf_stage_times_ms(dpf_handle h, float* ms_out /* DPF_T_COUNT */);
 
 #ifdef __cplusplus

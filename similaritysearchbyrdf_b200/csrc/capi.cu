@@ -100,13 +100,9 @@ void grow_keys(dpf_index* h, int64_t add) {
     h->key_ld = nld;
 }
 
-bool use_exact_hash() {
-    const char* e = getenv("DPF_HASH_EXACT");
-    return e && e[0] == '1';
-}
 
 void hash_dense_any(dpf_index* h, const double* Xd, int64_t n, int32_t* keys, uint8_t* pids, int64_t ld) {
-    if (use_exact_hash() && h->cfg.family_kind == DPF_FAMILY_ANGLE) hash_dense_device_exact(h, Xd, n, keys, pids, ld);
+    if (h->dbg[DPF_DBG_HASH_EXACT] == 1 && h->cfg.family_kind == DPF_FAMILY_ANGLE) hash_dense_device_exact(h, Xd, n, keys, pids, ld);
     else hash_dense_device(h, Xd, n, keys, pids, ld);
 }
 
@@ -119,12 +115,11 @@ void pids_to_host(dpf_index* h, const uint8_t* dev, int64_t count, int32_t* out)
 }
 
 // ids of candidate scratch per chunk of queries (2 GiB); DPF_CAND_BUDGET overrides it (tests force many small chunks)
-static int64_t cand_budget() {
-    const char* e = getenv("DPF_CAND_BUDGET");
-    const long long v = e ? atoll(e) : 0;
-    return v > 0 ? (int64_t)v : (1LL << 29);
+static int64_t cand_budget(const dpf_index* h) {
+    const int64_t v = h->dbg[DPF_DBG_CAND_BUDGET];
+    return v > 0 ? v : (1LL << 29);
 }
-#define kCandBudget cand_budget()
+#define kCandBudget cand_budget(h)
 
 // allocate the candidate scratch once for the largest chunk (a reallocation between chunks would serialise the
 // stream on cudaFree)
@@ -394,10 +389,7 @@ struct PhaseTrace {
     bool on;
     cudaStream_t st;
     std::chrono::steady_clock::time_point t;
-    explicit PhaseTrace(cudaStream_t s) : st(s), t(std::chrono::steady_clock::now()) {
-        const char* e = getenv("DPF_TRACE");
-        on = e && e[0] == '1';
-    }
+    PhaseTrace(const dpf_index* h, cudaStream_t s) : on(h->dbg[DPF_DBG_TRACE] == 1), st(s), t(std::chrono::steady_clock::now()) {}
     void mark(const char* what) {
         if (!on) return;
         cudaStreamSynchronize(st);
@@ -455,7 +447,7 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     DPF_REQUIRE(h->n == 0 || h->dense, DPF_ERR_STATE, "index holds sparse vectors");
     DPF_REQUIRE(h->n + n < (1LL << 31), DPF_ERR_INVALID, "ids are int32");
     begin_profile(h);
-    PhaseTrace tr(h->stream);
+    PhaseTrace tr(h, h->stream);
     const int d = h->cfg.d;
     h->dense = true;
     const double* Xnew;
@@ -935,6 +927,13 @@ int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
 
 int dpf_set_profiling(dpf_handle h, int32_t enable) {
     return guarded(h, [&] { h->profiling = enable != 0; });
+}
+
+int dpf_set_debug_option(dpf_handle h, int32_t option, int64_t value) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(option >= 0 && option < DPF_DBG_COUNT, DPF_ERR_INVALID, "unknown debug option");
+        h->dbg[option] = value;
+    });
 }
 
 int dpf_stage_times_ms(dpf_handle h, float* ms_out) {

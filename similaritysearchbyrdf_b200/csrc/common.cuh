@@ -212,6 +212,9 @@ struct dpf_index {
     dpf::DevBuf<double> out_scores;
     dpf::DevBuf<char> stage;                   // generic staging
 
+    // test / profiling hooks (dpf_set_debug_option); the product path never reads the environment
+    int64_t dbg[DPF_DBG_COUNT] = {0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
     // stats / profiling
     int64_t stats[DPF_STAT_COUNT] = {0};
     bool profiling = false;

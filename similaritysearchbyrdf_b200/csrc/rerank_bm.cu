@@ -33,8 +33,7 @@ namespace dpf {
 
 
 bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
-    const char* e = getenv("DPF_RERANK");
-    if (e && e[0] == 'r') return false;                        // DPF_RERANK=rowmajor forces the row-major kernel
+    if (h->dbg[DPF_DBG_RERANK] == 1) return false;             // test hook: force the row-major kernel
     if (!(h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 && (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
           topk <= RR_MAXK))                                    // d even: the queries are FP64 rows moved in 16-byte pieces
         return false;
@@ -1101,11 +1100,10 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             h->bm_tau.reserve((size_t)qk.nq);
             h->bm_scnt.reserve((size_t)qk.nq);
             h->bm_sbase.reserve((size_t)qk.nq);
-            const char* ntv = getenv("DPF_TAU_TABLES");
             // sampled tables per query (one warp each): 6 on one GPU; a rank of G sees 1/G of every query's buckets, so
             // its lists stay short with fewer samples
             const int nt_default = c.world <= 1 ? 6 : std::max(2, 6 / c.world);
-            const int NT = std::min(32, std::max(1, ntv ? atoi(ntv) : nt_default));
+            const int NT = std::min(32, std::max(1, h->dbg[DPF_DBG_TAU_TABLES] > 0 ? (int)h->dbg[DPF_DBG_TAU_TABLES] : nt_default));
             const bool intq = h->Q8_valid;
             h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
             h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
@@ -1121,8 +1119,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                     h->pair_len.p, h->ids_sorted.p, qk.qids, h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p,
                     h->bm_tl_cnt.p);
             };
-            const char* tk = getenv("DPF_TAU_KERNEL");
-            if (intq && (l2 || !(tk && tk[0] == 'd'))) launch_threshold_u8i(h, st2, metric, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
+            if (intq && (l2 || h->dbg[DPF_DBG_TAU_KERNEL] != 1)) launch_threshold_u8i(h, st2, metric, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
             else if (ang) { if (intq) go(k_threshold<true, DPF_STORE_KIND_U8, true>); else go(k_threshold<true, DPF_STORE_KIND_U8, false>); }
             else { if (intq) go(k_threshold<false, DPF_STORE_KIND_U8, true>); else go(k_threshold<false, DPF_STORE_KIND_U8, false>); }
             DPF_LAUNCHED();

@@ -771,15 +771,13 @@ void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, int64_t q0,
 int u8_query_pitch() { return U8_QPITCH; }
 
 bool score_u8_usable(const dpf_index* h) {
-    const char* e = getenv("DPF_BM_KERNEL");
-    if (e && e[0] == 's') return false;                       // =stream: the TMA ring kernel on the byte rows
+    if (h->dbg[DPF_DBG_BM_KERNEL] == 1) return false;         // test hook: the TMA ring kernel on the byte rows
     return h->Xc_kind == DPF_STORE_KIND_U8 && h->Xc_row_bytes <= 128;
 }
 
 void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq) {
     h->Q8_valid = false;
-    const char* e = getenv("DPF_U8_IMMA");
-    if (e && e[0] == '0') return;                             // DPF_U8_IMMA=0: always multiply on the FP64 tensor pipe
+    if (h->dbg[DPF_DBG_U8_IMMA] == 0) return;                 // test hook: always multiply on the FP64 tensor pipe
     cudaStream_t st = h->stream;
     const int pitch = U8_QPITCH;
     h->Q8.reserve((size_t)nq * pitch);
@@ -806,8 +804,7 @@ void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const 
             kern<<<h->num_sms * (angular ? U8_INT_CTAS - 1 : U8_INT_CTAS), U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, units, nunits_p,
                                                                    h->ids_sorted.p, flt, bm_stat);
         };
-        const char* ev = getenv("DPF_U8I_KERNEL");
-        if (ev && ev[0] == 'l' && metric != DPF_METRIC_L2) {       // =lean: the occupancy-based variant (dot / angular)
+        if (h->dbg[DPF_DBG_U8I_KERNEL] == 1 && metric != DPF_METRIC_L2) {       // =lean: the occupancy-based variant (dot / angular)
             if (angular) launch(k_score_u8i<true>); else launch(k_score_u8i<false>);
         } else {
             auto launch_s = [&](auto kern) {

@@ -57,8 +57,7 @@ void build_compact_store(dpf_index* h) {
     h->Xc_row_bytes = (int64_t)h->cfg.d * 8;
     h->stats[DPF_STAT_STORE_KIND] = DPF_STORE_KIND_F64;
     h->stats[DPF_STAT_STORE_ROW_BYTES] = h->Xc_row_bytes;
-    const char* e = getenv("DPF_STORE");
-    if (h->store_mode == DPF_STORE_F64_ONLY || (e && e[0] == 'f' && e[1] == '6') || !h->dense || !h->Xdev || h->n == 0) {
+    if (h->store_mode == DPF_STORE_F64_ONLY || h->dbg[DPF_DBG_STORE] == 1 || !h->dense || !h->Xdev || h->n == 0) {
         h->Xc.release();
         return;
     }
@@ -77,7 +76,7 @@ void build_compact_store(dpf_index* h) {
     // (DPF_STORE_NARROWEST, or DPF_STORE=f32 which also skips the byte check): the FP64 tensor-pipe kernels are bound
     // by instruction issue, not by the bytes of a row, and the extra float -> double conversions make them slower
     // (measured: 11.2 ms against 10.2 ms per 10k queries at d = 128).
-    const bool force32 = e && e[0] == 'f' && e[1] == '3';
+    const bool force32 = h->dbg[DPF_DBG_STORE] == 2;
     int kind = DPF_STORE_KIND_F64;
     if (!(f & 1) && !force32) kind = DPF_STORE_KIND_U8;
     else if (!(f & 2) && (force32 || h->store_mode == DPF_STORE_NARROWEST)) kind = DPF_STORE_KIND_F32;

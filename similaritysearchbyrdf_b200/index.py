@@ -99,6 +99,26 @@ class DPFIndex:
         Call before fit."""
         self._ck(self.lib.dpf_set_store_mode(self.h, mode))
 
+    def set_debug_option(self, option, value):
+        """Test / profiling hook (B.DBG_*): selects a kernel variant on this handle; the library reads no environment."""
+        self._ck(self.lib.dpf_set_debug_option(self.h, option, int(value)))
+
+    def debug_options(self, **kw):
+        """Context manager: set B.DBG_<NAME>=value for the duration of a with-block, then restore the default."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            keys = {getattr(B, "DBG_" + k.upper()): v for k, v in kw.items()}
+            for k, v in keys.items():
+                self.set_debug_option(k, v)
+            try:
+                yield self
+            finally:
+                for k in keys:
+                    self.set_debug_option(k, B.DBG_DEFAULTS.get(k, 0))
+        return cm()
+
     def set_balanced_partition(self, on=True):
         """Multi-GPU: deal the sub-indexes to the ranks by occupancy at the first fit instead of p % world."""
         self._ck(self.lib.dpf_set_balanced_partition(self.h, 1 if on else 0))

@@ -275,16 +275,13 @@ def test_topk_bucket_major_equals_row_major_bitwise_on_integer_data(monkeypatch)
     ix = U.make_index(128, A, chain, Ap, bucket_overflow=100)
     ix.fit_dense(X)
     res = {}
-    for name, env in (("u8", {}), ("stream", {"DPF_BM_KERNEL": "stream"}), ("u8_dmma", {"DPF_U8_IMMA": "0"}),
-                      ("rowmajor", {"DPF_RERANK": "rowmajor"})):
-        for k_, v in env.items():
-            monkeypatch.setenv(k_, v)
-        res[name] = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
+    for name, opt in (("u8", {}), ("stream", {"bm_kernel": 1}), ("u8_dmma", {"u8_imma": 0}), ("rowmajor", {"rerank": 1}),
+                      ("u8_ring", {"u8i_kernel": 2}), ("u8_lean", {"u8i_kernel": 1})):
+        with ix.debug_options(**opt):
+            res[name] = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
         bm = ix.stats()["bm_pairs"]
         assert (bm > 0) == (name != "rowmajor")
-        for k_ in env:
-            monkeypatch.delenv(k_)
-    for name in ("u8", "stream", "u8_dmma"):
+    for name in ("u8", "stream", "u8_dmma", "u8_ring", "u8_lean"):
         assert np.array_equal(res[name][0], res["rowmajor"][0]), name
         assert np.array_equal(res[name][1], res["rowmajor"][1]), name
 
@@ -360,12 +357,10 @@ def test_compact_store_bitwise_equal_to_f64_rows_on_integer_data(monkeypatch):
         res[mode] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
         if mode == B.STORE_AUTO:
             # the same byte rows on the FP64 tensor pipe (DPF_U8_IMMA=0) and through the TMA ring kernel
-            monkeypatch.setenv("DPF_U8_IMMA", "0")
-            res["u8_dmma"] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
-            monkeypatch.delenv("DPF_U8_IMMA")
-            monkeypatch.setenv("DPF_BM_KERNEL", "stream")
-            res["u8_stream"] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
-            monkeypatch.delenv("DPF_BM_KERNEL")
+            with ix.debug_options(u8_imma=0):
+                res["u8_dmma"] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
+            with ix.debug_options(bm_kernel=1):
+                res["u8_stream"] = [ix.query_topk_dense(Q, None, 0, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR)]
         ix.close()
     for name in (B.STORE_AUTO, "u8_dmma", "u8_stream"):
         for a, b in zip(res[name], res[B.STORE_F64_ONLY]):
@@ -404,7 +399,7 @@ def test_threshold_filter_corner_cases(metric, byte_queries, monkeypatch):
     qids = np.arange(0, 2400, 9, dtype=np.int32)
     Qs = X[qids] if byte_queries else X[qids] + 0.37
     for topk, steps, nt in ((5, 0, 1), (10, 1, 3), (60, 1, 8), (200, 2, 32), (256, 0, 6)):
-        monkeypatch.setenv("DPF_TAU_TABLES", str(nt))
+        ix.set_debug_option(B.DBG_TAU_TABLES, nt)
         io, so = o.query_topk_dense(Qs, qids, steps, topk, metric)
         ig, sg = ix.query_topk_dense(Qs, qids, steps, topk, metric)
         U.assert_topk_close(io, so, ig, sg)
@@ -430,7 +425,7 @@ def test_query_batch_cut_into_memory_bounded_chunks(store, monkeypatch):
     Qs = X[::7] if store == "u8" else X[::7] + 0.01
     ref_c = ix.query_candidates_dense(Qs, None, 1)
     ref = [ix.query_topk_dense(Qs, None, 1, 10, m) for m in (B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2)]
-    monkeypatch.setenv("DPF_CAND_BUDGET", "20000")
+    ix.set_debug_option(B.DBG_CAND_BUDGET, 20000)
     U.assert_csr_equal(ref_c, ix.query_candidates_dense(Qs, None, 1))
     for m, (ri, rs) in zip((B.METRIC_DOT, B.METRIC_ANGULAR, B.METRIC_L2), ref):
         gi, gs = ix.query_topk_dense(Qs, None, 1, 10, m)
