@@ -187,11 +187,13 @@ enum {
     DPF_STAT_LAST_CAND_WITH_DUPS = 7, /* bucket entries visited by the last query batch                      */
     DPF_STAT_KERNEL_LAUNCHES = 8,  /* kernels launched by this library in this process (cumulative)          */
     DPF_STAT_BM_PAIRS = 9,         /* bucket-major re-rank, last batch: (bucket, query) pairs                */
-    DPF_STAT_BM_RUNS = 10,         /*   runs of pairs sharing a bucket inside a CTA group                    */
+    DPF_STAT_BM_RUNS = 10,         /*   units scored (<= 16 queries sharing a bucket)                         */
     DPF_STAT_BM_ROWS_STAGED = 11,  /*   bucket rows staged in shared memory (each one row of the store)      */
     DPF_STAT_STORE_KIND = 12,      /* DPF_STORE_KIND_* of the compact store after the last dense fit         */
     DPF_STAT_STORE_ROW_BYTES = 13, /* bytes per row the re-rank kernels fetch                                */
     DPF_STAT_BM_SURVIVORS = 14,    /* bucket-major re-rank, last batch: scores that passed the threshold filter */
+    DPF_STAT_BM_DIRECT = 15,       /*   queries answered by the exhaustive per-query kernel (no threshold could be
+                                        guaranteed from the samples, or their survivors did not fit the pool)         */
     DPF_STAT_COUNT = 16
 };
 int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occupancy_out /* 2^pb or NULL */);

@@ -21,7 +21,7 @@ STAT_COUNT, T_COUNT = 16, 16
 DBG_DEFAULTS = {DBG_U8_IMMA: 1}
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
               "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",
-              "bm_rows_staged", "store_kind", "store_row_bytes", "bm_survivors"]
+              "bm_rows_staged", "store_kind", "store_row_bytes", "bm_survivors", "bm_direct"]
 STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select", "narrow"]
 
 # every symbol include/dpf.h declares

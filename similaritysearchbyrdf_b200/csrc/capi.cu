@@ -73,6 +73,11 @@ void d2h(dpf_index* h, T* dst, const T* src, size_t n) {
     if (n) DPF_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 }
 
+// clears the per-batch device counters (one memset); every query entry point starts with it
+void begin_batch(dpf_index* h) {
+    DPF_CUDA(cudaMemsetAsync(h->counters.p + CTR_BATCH_FIRST, 0, (CTR_BATCH_END - CTR_BATCH_FIRST) * sizeof(int32_t), h->stream));
+}
+
 void require_ready(dpf_index* h, bool need_fit) {
     DPF_REQUIRE(h->family_set, DPF_ERR_STATE, "dpf_set_family has not been called");
     DPF_REQUIRE(h->part_set || h->cfg.pb == 0, DPF_ERR_STATE, "dpf_set_partitioners has not been called");
@@ -139,6 +144,7 @@ void run_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode
                     int64_t cap, int64_t* total_out) {
     const int64_t nq = qk.nq;
     std::vector<int64_t> ub;
+    begin_batch(h);
     probe_count_all(h, qk, steps, probe_mode, ub);
     reserve_candidate_scratch(h, ub);
     DevBuf<int64_t> off;
@@ -159,7 +165,6 @@ void run_candidates(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode
     DPF_CUDA(cudaStreamSynchronize(h->stream));
     offsets_out[0] = 0;
     for (int64_t i = 0; i < nq; ++i) offsets_out[i + 1] = offsets_out[i] + cnt[(size_t)i];
-    h->stats[DPF_STAT_LAST_CANDIDATES] = total;
     if (total_out) *total_out = total;
     DPF_REQUIRE(total <= cap, DPF_ERR_CAPACITY, "candidate buffer too small");
 }
@@ -233,7 +238,8 @@ int dpf_create(const dpf_config* cfg, dpf_handle* out) {
             DPF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         }
         DPF_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-        h->counters.reserve(64);
+        h->counters.reserve(CTR_COUNT);
+        DPF_CUDA(cudaMemsetAsync(h->counters.p, 0, CTR_COUNT * sizeof(int32_t), h->stream));
         h->occupancy.assign(1 << cfg->pb, 0.0);
         for (int p = 0; p < (1 << cfg->pb); ++p)      // Partitioner scheme on G GPUs: sub-index p lives on GPU p mod G
             if (cfg->world <= 1 || p % cfg->world == cfg->rank) h->own.w[p >> 5] |= 1u << (p & 31);
@@ -480,11 +486,20 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
     tr.mark("hash");
     if (h->n == 0) assign_balanced_partition(h, n);
+    // the new vectors count only once the forest and the store have been rebuilt: a failure in between (out of memory,
+    // node capacity) leaves the handle un-fitted with its old size instead of fitted with stale arrays
+    h->fitted = false;
     h->n += n;
-    build_forest(h);
-    tr.mark("forest");
-    build_compact_store(h);
-    tr.mark("compact store");
+    try {
+        build_forest(h);
+        tr.mark("forest");
+        build_compact_store(h);
+        tr.mark("compact store");
+    } catch (...) {
+        h->n -= n;
+        h->fitted = false;
+        throw;
+    }
     h->stats[DPF_STAT_SIZE] = h->n;
     DPF_CUDA(cudaStreamSynchronize(h->stream));
     end_profile(h);
@@ -543,9 +558,16 @@ int dpf_fit_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, con
         grow_keys(h, n);
         hash_csr_device(h, h->sp_ptr.p + h->n, h->sp_idx.p, h->sp_val.p, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
         DPF_CUDA(cudaStreamSynchronize(h->stream));   // `rebased` must outlive the copy
+        h->fitted = false;
         h->sp_nnz += nnz;
         h->n += n;
-        build_forest(h);
+        try {
+            build_forest(h);
+        } catch (...) {
+            h->sp_nnz -= nnz;
+            h->n -= n;
+            throw;
+        }
         h->stats[DPF_STAT_SIZE] = h->n;
         DPF_CUDA(cudaStreamSynchronize(h->stream));
         end_profile(h);
@@ -624,23 +646,27 @@ static void topk_device(dpf_index* h, const double* Qd, int64_t nq, const int32_
     const int L = h->cfg.L;
     h->qkeys.reserve((size_t)L * nq);
     h->qpids.reserve((size_t)L * nq);
+    begin_batch(h);
     hash_dense_any(h, Qd, nq, h->qkeys.p, h->qpids.p, nq);
     const QueryKeys qk{h->qkeys.p, nq, nq, qids_dev};
     h->Q8_valid = false;
-    if (score_u8_usable(h) && (reinterpret_cast<uintptr_t>(Qd) & 15) == 0) prepare_queries_u8(h, Qd, nq);   // byte queries? (per batch)
+    const bool aligned = (reinterpret_cast<uintptr_t>(Qd) & 15) == 0;   // query rows are moved by 16-byte bulk copies / LDG.128
+    if (score_u8_usable(h) && aligned) prepare_queries_u8(h, Qd, nq, metric == DPF_METRIC_L2);
+    if (aligned && bucket_major_supported(h, metric, topk)) {
+        // bucket-major: chunks of queries whose worst-case pair count fits the scratch; nothing is read back
+        int cap = 1;
+        const int64_t chunk = bm_chunk_queries(h, steps, probe_mode, &cap);
+        for (int64_t q0 = 0; q0 < nq; q0 += chunk)
+            topk_bucket_major(h, Qd, qk, steps, probe_mode, q0, std::min(nq, q0 + chunk), cap, topk, metric, ids_out_dev, score_out_dev);
+        return;
+    }
+    // row-major (d > 128, squared L2 on real-valued data, k > 256): candidate lists, memory-bounded chunks of queries
     std::vector<int64_t> ub;
     probe_count_all(h, qk, steps, probe_mode, ub);
     reserve_candidate_scratch(h, ub);
-    for (int64_t q0 = 0; q0 < nq;) {   // memory-bounded chunks of queries: expand -> gather/re-rank/top-k
+    for (int64_t q0 = 0; q0 < nq;) {
         const int64_t q1 = next_chunk_end(ub, q0, kCandBudget);
         const int64_t base = ub[(size_t)q0];
-        if (bucket_major_supported(h, metric, topk) && (reinterpret_cast<uintptr_t>(Qd) & 15) == 0 &&
-            ub[(size_t)q1] - base < (1LL << 32)) {   // query rows are moved by 16-byte bulk copies / LDG.128
-            topk_bucket_major(h, Qd, qk, steps, probe_mode, q0, q1, ub[(size_t)q1] - base, topk, metric, ids_out_dev,
-                              score_out_dev);
-            q0 = q1;
-            continue;
-        }
         expand_range(h, qk, steps, probe_mode, q0, q1, base, ub[(size_t)q1] - base);
         int64_t max_cnt = 1;
         for (int64_t q = q0; q < q1; ++q) max_cnt = std::max(max_cnt, ub[(size_t)q + 1] - ub[(size_t)q]);
@@ -656,6 +682,7 @@ int dpf_query_topk_dense(dpf_handle h, const double* Q, int64_t nq, const int32_
         require_ready(h, true);
         DPF_REQUIRE(nq > 0 && Q && ids_out && score_out, DPF_ERR_INVALID, "null buffer");
         DPF_REQUIRE(steps >= 0 && metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad steps/metric");
+        DPF_REQUIRE(topk >= 1 && topk <= 256, DPF_ERR_INVALID, "topk must be in 1..256");
         begin_profile(h);
         upload_queries_dense(h, Q, nq, qids);
         h->out_ids.reserve((size_t)nq * topk);
@@ -676,6 +703,7 @@ int dpf_query_topk_dense_dev(dpf_handle h, const double* Q_dev, int64_t nq, cons
         require_ready(h, true);
         DPF_REQUIRE(nq > 0 && Q_dev && ids_out_dev && score_out_dev, DPF_ERR_INVALID, "null buffer");
         DPF_REQUIRE(steps >= 0 && metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad steps/metric");
+        DPF_REQUIRE(topk >= 1 && topk <= 256, DPF_ERR_INVALID, "topk must be in 1..256");
         begin_profile(h);
         topk_device(h, Q_dev, nq, qids_dev, steps, probe_mode, topk, metric, ids_out_dev, score_out_dev);
         end_profile(h);
@@ -688,10 +716,15 @@ int dpf_rerank_dense(dpf_handle h, const double* Q, int64_t nq, const int64_t* o
         require_ready(h, true);
         DPF_REQUIRE(nq > 0 && Q && offsets && ids_out && score_out, DPF_ERR_INVALID, "null buffer");
         DPF_REQUIRE(metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad metric");
+        DPF_REQUIRE(topk >= 1 && topk <= 256, DPF_ERR_INVALID, "topk must be in 1..256");
+        DPF_REQUIRE(offsets[0] == 0, DPF_ERR_INVALID, "offsets must start at 0");
+        for (int64_t q = 0; q < nq; ++q) DPF_REQUIRE(offsets[q + 1] >= offsets[q], DPF_ERR_INVALID, "offsets must be non-decreasing");
         const int64_t total = offsets[nq];
+        DPF_REQUIRE(total == 0 || cand, DPF_ERR_INVALID, "null candidate buffer");
         for (int64_t i = 0; i < total; ++i)
             DPF_REQUIRE(cand[i] >= 0 && cand[i] < h->n, DPF_ERR_INVALID, "candidate id out of range");
         begin_profile(h);
+        begin_batch(h);
         const int d = h->cfg.d;
         h->qbuf.reserve((size_t)nq * d);
         h2d(h, h->qbuf.p, Q, (size_t)nq * d);
@@ -906,17 +939,20 @@ int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
     return guarded(h, [&] {
         DPF_REQUIRE(stats_out, DPF_ERR_INVALID, "null buffer");
         h->stats[DPF_STAT_SIZE] = h->n;
-        if (h->fitted && h->counters.cap >= 32) {   // unique candidates of the last batch (device counter)
-            unsigned long long u = 0;
-            DPF_CUDA(cudaMemcpyAsync(&u, h->counters.p + 24, sizeof(u), cudaMemcpyDeviceToHost, h->stream));
+        {   // the counters of the last batch live on the device (a batch never synchronises to report them)
+            int32_t c[CTR_COUNT];
+            DPF_CUDA(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
             DPF_CUDA(cudaStreamSynchronize(h->stream));
-            h->stats[DPF_STAT_LAST_CANDIDATES] = (int64_t)u;
-            unsigned long long bm[3] = {0, 0, 0};
-            DPF_CUDA(cudaMemcpyAsync(bm, h->counters.p + 26, sizeof(bm), cudaMemcpyDeviceToHost, h->stream));
-            DPF_CUDA(cudaStreamSynchronize(h->stream));
-            h->stats[DPF_STAT_BM_RUNS] = (int64_t)bm[0];
-            h->stats[DPF_STAT_BM_ROWS_STAGED] = (int64_t)bm[1];
-            h->stats[DPF_STAT_BM_SURVIVORS] = (int64_t)bm[2];
+            auto u64 = [&](int slot) { unsigned long long v; memcpy(&v, c + slot, sizeof(v)); return (int64_t)v; };
+            h->stats[DPF_STAT_NLZ_GT28] = u64(CTR_STAT_NLZ);
+            h->stats[DPF_STAT_LAST_CANDIDATES] = u64(CTR_STAT_UNIQUE);
+            h->stats[DPF_STAT_LAST_CAND_WITH_DUPS] = u64(CTR_ENTRIES);
+            h->stats[DPF_STAT_BM_PAIRS] = u64(CTR_BM_PAIRS_TOTAL);
+            h->stats[DPF_STAT_BM_RUNS] = u64(CTR_BM_STAT);
+            h->stats[DPF_STAT_BM_ROWS_STAGED] = u64(CTR_BM_STAT + 2);
+            h->stats[DPF_STAT_BM_SURVIVORS] = u64(CTR_BM_STAT + 4);
+            h->stats[DPF_STAT_BM_DIRECT] = c[CTR_DIRECT];
+            h->stats[DPF_STAT_NEAR_ZERO_FIXUPS] = u64(CTR_FIX_TOTAL);
         }
         h->stats[DPF_STAT_KERNEL_LAUNCHES] = (int64_t)g_launches;
         for (int i = 0; i < DPF_STAT_COUNT; ++i) stats_out[i] = h->stats[i];

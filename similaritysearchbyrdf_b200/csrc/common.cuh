@@ -94,9 +94,40 @@ struct ForestView {
     const int32_t* ids_sorted;
     const int64_t* table_base;  // L+1
     int32_t num_nodes;
+    // leaf table (bucket-major re-rank): every leaf bucket has a dense number; child_leaf[slot] = that number for a
+    // leaf slot, leaf_pos / leaf_len = its range in ids_sorted (global position, < 2^32 when the table is built)
+    const uint32_t* child_leaf;
+    const uint32_t* leaf_pos;
+    const int32_t* leaf_len;
+    int32_t num_leaves;
 };
 
 enum : int { kMaxTables = 256, kMaxChain = 32, kMaxPb = 8 };
+
+// int32 slots of dpf_index::counters (device).  [0, 16) belong to whichever of hash / build is running; the rest are
+// per-query-batch counters, cleared at the start of a batch by one memset of [CTR_BATCH_FIRST, CTR_BATCH_END).
+enum : int {
+    CTR_FIX_COUNT = 0,        // hash: length of the near-zero list of the current chunk
+    CTR_BAD_ID = 16,          // by-id queries: some id is not in the index   (also k_expand's query cursor)
+    CTR_NEXT_UNIT = 17,       // row-major re-rank: unit cursor
+    CTR_STAT_NLZ = 20,        // u64: (query, table) pairs with nlz(h) > 28
+    CTR_STAT_UNIQUE = 24,     // u64: unique candidates of the batch (candidate-set path)
+    CTR_BM_STAT = 26,         // 3 x u64: units scored, rows staged, survivors selected from
+    CTR_STORE_FLAGS = 40,     // fit: representability scan
+    CTR_Q8_BAD = 41,          // != 0: some query value of the batch is not a byte
+    CTR_POOL = 42,            // survivor pool cursor (records)
+    CTR_NPAIRS = 44,          // bucket-major: (bucket, query) pairs / units of the current chunk
+    CTR_NUNITS = 45,
+    CTR_SCAN_TILE = 46,       // tile cursor of the leaf-count scan
+    CTR_POOL_OVERFLOW = 47,   // != 0: the survivor pool was too small for some warp (its queries are answered directly)
+    CTR_DIRECT = 48,          // queries answered by k_topk_direct in this batch
+    CTR_BM_PAIRS_TOTAL = 50,  // u64: pairs over all chunks of the batch
+    CTR_ENTRIES = 52,         // u64: bucket entries visited by the batch (candidates with duplicates)
+    CTR_BATCH_FIRST = 16,
+    CTR_BATCH_END = 64,
+    CTR_FIX_TOTAL = 64,       // u64, cumulative: near-zero projections recomputed in reference order
+    CTR_COUNT = 128
+};
 
 // the sub-indexes (partition ids, < 2^pb <= 256) this handle owns on a multi-GPU box
 struct OwnMask {
@@ -167,6 +198,13 @@ struct dpf_index {
 
     // forest
     dpf::DevBuf<int32_t> child_ptr, child_cnt, ids_sorted;
+    dpf::DevBuf<int32_t> node_table;            // table of every directory node
+    dpf::DevBuf<uint32_t> child_leaf, leaf_pos; // leaf table (see ForestView)
+    dpf::DevBuf<int32_t> leaf_len;
+    dpf::DevBuf<uint32_t> leaf_cnt;             // per leaf: pairs of the current query chunk (all zero between batches)
+    dpf::DevBuf<uint32_t> leaf_off, leaf_unit_off;   //           first pair / first unit
+    int32_t num_leaves = 0;
+    bool leaf_table = false;                    // false when the forest has >= 2^32 entries (row-major re-rank only)
     dpf::DevBuf<int64_t> table_base;
     std::vector<int64_t> h_table_base;
     std::vector<double> occupancy;   // 2^pb: ids per sub-index averaged over tables (last build)
@@ -192,8 +230,7 @@ struct dpf_index {
     dpf::DevBuf<int32_t> ucnt, part_id;        // re-rank work units / partial top-k lists
     dpf::DevBuf<uint32_t> scan_scratch, pair_cnt, pair_base, pair_seg, pair_len;   // bucket-major re-rank
     dpf::DevBuf<int32_t> pair_q;
-    dpf::DevBuf<int2> probe_cache;             // distinct buckets per (query, table) from the probe pass
-    int probe_cache_cap = 0;                   //   slots per (query, table); 0 = not cached
+    dpf::DevBuf<uint32_t> probe_cache;         // leaf numbers of the distinct buckets per (query, table) (k_probe_leaves)
     dpf::DevBuf<unsigned long long> pair_key, pair_key_alt;
     dpf::DevBuf<double> scores;                // bucket-major re-rank: survivor scores / ids (Filter, rerank_units.cuh)
     dpf::DevBuf<int32_t> surv_id;
@@ -295,9 +332,10 @@ void rerank_topk(dpf_index* h, const double* Qd, int64_t q0, int64_t q1, int64_t
 // bucket-major re-rank of queries [q0, q1) (rerank_bm.cu): top-k straight from the probe result, no candidate lists
 bool bucket_major_supported(const dpf_index* h, int metric, int topk);
 bool score_u8_usable(const dpf_index* h);                                  // rerank_u8.cu: byte store present and enabled
-void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq);       // sets h->Q8_valid when the batch is bytes
+void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq, bool need_host_flag);   // byte copy of the batch + device flag
 void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1,
-                       int64_t entries_ub, int topk, int metric, int32_t* ids_out, double* score_out);
+                       int cap, int topk, int metric, int32_t* ids_out, double* score_out);
+int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);   // bm_group.cu
 void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);
 void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt);
 void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256)
 k_init_depth1(const int32_t* __restrict__ cnt1, const int64_t* __restrict__ start1, const int64_t* __restrict__ table_base,
               int64_t ncodes, TreeParams tp, int32_t* __restrict__ child_ptr, int32_t* __restrict__ child_cnt,
               int32_t* __restrict__ counters /* [0]=node counter, [1]=work count */, WorkItem* __restrict__ work,
-              int node_cap) {
+              int node_cap, int32_t* __restrict__ node_table) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncodes) return;
     const int cnt = cnt1[c];
@@ -104,6 +104,7 @@ k_init_depth1(const int32_t* __restrict__ cnt1, const int64_t* __restrict__ star
         if (node < node_cap) {
             child_ptr[c] = node;
             child_cnt[c] = -1;
+            node_table[node] = t;
             const int w = atomicAdd(&counters[1], 1);
             work[w] = WorkItem{start1[c], cnt, 0, node, t};
             return;
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__(SP_THREADS)
 k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ keys, int64_t ld, TreeParams tp, int level,
               const int64_t* __restrict__ table_base, int32_t* __restrict__ ids_sorted, int32_t* __restrict__ tmp,
               int32_t* __restrict__ child_ptr, int32_t* __restrict__ child_cnt, int32_t* __restrict__ counters,
-              WorkItem* __restrict__ work_next, int node_cap, unsigned long long* __restrict__ stat_singleton) {
+              WorkItem* __restrict__ work_next, int node_cap, unsigned long long* __restrict__ stat_singleton,
+              int32_t* __restrict__ node_table) {
     __shared__ int32_t cntW[SP_MAXW], c0W[SP_MAXW], offW[SP_MAXW], runW[SP_MAXW];
     __shared__ int32_t wcnt[SP_THREADS / 32][SP_MAXW];
     __shared__ int trigger_slot;
@@ -191,6 +193,7 @@ k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ key
             if (node < node_cap) {
                 child_ptr[ci] = node;
                 child_cnt[ci] = -1;
+                node_table[node] = it.table;
                 const int wi = atomicAdd(&counters[2], 1);
                 work_next[wi] = WorkItem{it.start + offW[sl], cnt, c0, node, it.table};
                 made_dir = true;
@@ -203,8 +206,61 @@ k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ key
     }
 }
 
+// ---- leaf table: a dense number for every leaf bucket, its range in ids_sorted ---------------------------------
+// (the bucket-major re-rank groups the (bucket, query) pairs of a batch with a counting sort over these numbers)
+__global__ void __launch_bounds__(256)
+k_leaf_flags(const int32_t* __restrict__ child_cnt, int64_t nslots, uint32_t* __restrict__ child_leaf) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nslots) child_leaf[i] = (i < nslots && child_cnt[i] > 0) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_leaf_table(const int32_t* __restrict__ child_ptr, const int32_t* __restrict__ child_cnt, const uint32_t* __restrict__ child_leaf,
+             const int32_t* __restrict__ node_table, const int64_t* __restrict__ table_base, int64_t nslots, int W, int64_t roots,
+             int R, uint32_t* __restrict__ leaf_pos, int32_t* __restrict__ leaf_len) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    const int cnt = child_cnt[i];
+    if (cnt <= 0) return;
+    const int64_t node = i / W;
+    const int t = node < roots ? (int)(node / R) : node_table[node];
+    const uint32_t leaf = child_leaf[i];
+    leaf_pos[leaf] = (uint32_t)(table_base[t] + child_ptr[i]);
+    leaf_len[leaf] = cnt;
+}
+
+static void build_leaf_table(dpf_index* h) {
+    const TreeParams tp = h->tp;
+    cudaStream_t st = h->stream;
+    h->leaf_table = false;
+    h->num_leaves = 0;
+    if (h->h_table_base[h->cfg.L] >= (1LL << 32)) return;   // positions are 32-bit: such an index re-ranks row-major
+    const int64_t nslots = (int64_t)h->num_nodes * tp.W;
+    h->child_leaf.reserve((size_t)nslots + 1);
+    k_leaf_flags<<<(unsigned)((nslots + 256) / 256), 256, 0, st>>>(h->child_cnt.p, nslots, h->child_leaf.p); DPF_LAUNCHED();
+    exclusive_scan_u32(h, h->child_leaf.p, nslots + 1);
+    uint32_t nl = 0;
+    DPF_CUDA(cudaMemcpyAsync(&nl, h->child_leaf.p + nslots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaStreamSynchronize(st));
+    h->leaf_pos.reserve((size_t)nl + 1);
+    h->leaf_len.reserve((size_t)nl + 1);
+    h->leaf_cnt.reserve((size_t)nl + 1);
+    h->leaf_off.reserve((size_t)nl + 2);
+    h->leaf_unit_off.reserve((size_t)nl + 2);
+    DPF_CUDA(cudaMemsetAsync(h->leaf_cnt.p, 0, ((size_t)nl + 1) * sizeof(uint32_t), st));
+    if (nslots > 0) {
+        k_leaf_table<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->child_ptr.p, h->child_cnt.p, h->child_leaf.p, h->node_table.p,
+                                                                       h->table_base.p, nslots, tp.W, (int64_t)h->cfg.L * tp.R, tp.R,
+                                                                       h->leaf_pos.p, h->leaf_len.p); DPF_LAUNCHED();
+    }
+    DPF_CUDA(cudaGetLastError());
+    h->num_leaves = (int32_t)nl;
+    h->leaf_table = true;
+}
+
 ForestView forest_view(const dpf_index* h) {
-    return ForestView{h->child_ptr.p, h->child_cnt.p, h->ids_sorted.p, h->table_base.p, h->num_nodes};
+    return ForestView{h->child_ptr.p, h->child_cnt.p, h->ids_sorted.p, h->table_base.p, h->num_nodes,
+                      h->child_leaf.p, h->leaf_pos.p, h->leaf_len.p, h->num_leaves};
 }
 
 void build_forest(dpf_index* h) {
@@ -303,7 +359,8 @@ void build_forest(dpf_index* h) {
     h->node_cap = (int32_t)node_cap64;
     h->child_ptr.reserve((size_t)node_cap64 * tp.W);
     h->child_cnt.reserve((size_t)node_cap64 * tp.W);
-    h->counters.reserve(64);
+    h->node_table.reserve((size_t)node_cap64);
+    h->counters.reserve(CTR_COUNT);
     int32_t init_counters[4] = {(int32_t)roots, 0, 0, 0};
     DPF_CUDA(cudaMemcpyAsync(h->counters.p, init_counters, sizeof(init_counters), cudaMemcpyHostToDevice, st));
     unsigned long long* stat_dev = reinterpret_cast<unsigned long long*>(h->counters.p + 8);
@@ -317,7 +374,7 @@ void build_forest(dpf_index* h) {
         StageTimer tm(h, DPF_T_SPLIT);
         k_init_depth1<<<(unsigned)((ncodes + 255) / 256), 256, 0, st>>>(cnt1.p, start1.p, h->table_base.p, ncodes, tp,
                                                                          h->child_ptr.p, h->child_cnt.p, h->counters.p,
-                                                                         workA.p, h->node_cap); DPF_LAUNCHED();
+                                                                         workA.p, h->node_cap, h->node_table.p); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         int32_t hc[4];
         DPF_CUDA(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -330,7 +387,7 @@ void build_forest(dpf_index* h) {
             DPF_CUDA(cudaMemsetAsync(h->counters.p + 2, 0, sizeof(int32_t), st));
             k_split_level<<<nwork, SP_THREADS, 0, st>>>(cur, h->keys.p, ld, tp, level, h->table_base.p, h->ids_sorted.p,
                                                         tmp.p, h->child_ptr.p, h->child_cnt.p, h->counters.p, nxt,
-                                                        h->node_cap, stat_dev); DPF_LAUNCHED();
+                                                        h->node_cap, stat_dev, h->node_table.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             DPF_CUDA(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
             DPF_CUDA(cudaStreamSynchronize(st));
@@ -346,6 +403,7 @@ void build_forest(dpf_index* h) {
     h->stats[DPF_STAT_SINGLETON_SPLITS] = (int64_t)single;
     h->stats[DPF_STAT_SPLITS] = total_splits;
     h->stats[DPF_STAT_DIR_NODES] = h->num_nodes;
+    build_leaf_table(h);
     h->fitted = true;
 }
 

@@ -257,8 +257,9 @@ k_project_dmma(const double* __restrict__ X, const double* __restrict__ A, const
 // s = s + a[j]*x[j], j ascending, product and sum rounded separately (SimilarityCalculator.scala:45-47)
 __global__ void k_fixup_exact(const double* __restrict__ X, const double* __restrict__ A, int d, int PW,
                               const int2* __restrict__ fix_list, const int* __restrict__ fix_count, int fix_cap,
-                              uint32_t* __restrict__ S) {
+                              uint32_t* __restrict__ S, unsigned long long* __restrict__ total) {
     const int m = min(*fix_count, fix_cap);
+    if (m > 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total, (unsigned long long)m);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         const int2 e = fix_list[i];
         const double* x = X + (int64_t)e.x * d;
@@ -474,11 +475,9 @@ void prepare_family(dpf_index* h) {
     h->Anorm.reserve(P);
     DPF_CUDA(cudaMemcpyAsync(h->Anorm.p, nrm.data(), P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     DPF_CUDA(cudaStreamSynchronize(h->stream));
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // function attributes are per device: set for this handle's device (dpf_set_family runs once per handle)
         const int smem = (2 * BM + 2 * BN) * LDS_ * (int)sizeof(double);
         DPF_CUDA(cudaFuncSetAttribute(k_project_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
 }
 
@@ -512,8 +511,9 @@ void hash_dense_device(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_
     const int64_t chunk = hash_chunk_rows(h);
     h->signs.reserve((size_t)std::min(n, chunk) * PW);
     if (pst) h->pq.reserve((size_t)std::min(n, chunk) * P);
-    h->counters.reserve(64);
-    if (h->fix_list.cap == 0) h->fix_list.reserve(1 << 20);
+    h->counters.reserve(CTR_COUNT);
+    if (h->fix_list.cap == 0) h->fix_list.reserve(4 << 20);
+    unsigned long long* fix_total = reinterpret_cast<unsigned long long*>(h->counters.p + CTR_FIX_TOTAL);
     const double coef = 4.0 * (double)(d + 8) * 1.1102230246251565e-16;   // 4 (d+8) 2^-53 >= 2 * 2 gamma_d
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t m = std::min(chunk, n - r0);
@@ -538,6 +538,15 @@ void hash_dense_device(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_
                                                                           (int)h->fix_list.cap); DPF_LAUNCHED();
                     DPF_CUDA(cudaGetLastError());
                 }
+                if ((size_t)m * (size_t)P <= h->fix_list.cap) {
+                    // the list cannot overflow (a query batch, a small fit): no need to read its length back — the
+                    // fix-up kernel takes it from the device and returns at once when it is empty
+                    StageTimer tm(h, DPF_T_FIXUP);
+                    k_fixup_exact<<<32, 128, 0, h->stream>>>(Xc, h->A.p, d, PW, h->fix_list.p, h->counters.p,
+                                                            (int)h->fix_list.cap, h->signs.p, fix_total); DPF_LAUNCHED();
+                    DPF_CUDA(cudaGetLastError());
+                    break;
+                }
                 int32_t cnt = 0;
                 DPF_CUDA(cudaMemcpyAsync(&cnt, h->counters.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
                 DPF_CUDA(cudaStreamSynchronize(h->stream));
@@ -545,11 +554,10 @@ void hash_dense_device(dpf_index* h, const double* Xd, int64_t n, int32_t* keys_
                     h->fix_list.reserve((size_t)cnt + 1024);
                     continue;
                 }
-                h->stats[DPF_STAT_NEAR_ZERO_FIXUPS] += cnt;
                 if (cnt > 0) {
                     StageTimer tm(h, DPF_T_FIXUP);
                     k_fixup_exact<<<std::min(1024, (cnt + 127) / 128), 128, 0, h->stream>>>(
-                        Xc, h->A.p, d, PW, h->fix_list.p, h->counters.p, (int)h->fix_list.cap, h->signs.p); DPF_LAUNCHED();
+                        Xc, h->A.p, d, PW, h->fix_list.p, h->counters.p, (int)h->fix_list.cap, h->signs.p, fix_total); DPF_LAUNCHED();
                     DPF_CUDA(cudaGetLastError());
                 }
                 break;

@@ -15,17 +15,14 @@
 // against the query held in shared memory, warp-shuffle reduction, per-warp top-k lists merged per query.
 #include <cstdlib>
 
-#include "query_common.cuh"
+#include "rerank_units.cuh"
 
 namespace dpf {
 
 // pass A: upper bound of the candidate count per query (sum of distinct bucket sizes over tables)
 __global__ void __launch_bounds__(256)
 k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t nq,
-              int32_t* __restrict__ q_ub, unsigned long long* __restrict__ stat /* [0] nlz>28 */,
-              uint32_t* __restrict__ pair_cnt /* nq x L distinct buckets per (query, table), may be null */,
-              int2* __restrict__ cache /* (bucket ptr, size) of those buckets, `cache_cap` slots per (query, table), or null */,
-              int cache_cap) {
+              int32_t* __restrict__ q_ub, unsigned long long* __restrict__ stat /* [0] nlz>28 */) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= nq * c.L) return;
@@ -39,7 +36,7 @@ k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
         if (lane == 0) atomicAdd(&stat[0], 1ULL);
         return;
     }
-    int total = 0, nbuckets = 0;
+    int total = 0;
     const int np = 1 << c.tp.pb;
     for (int sub = 0; sub < np; ++sub) {       // findStepWiseSubIndexIDs (RandomDrawTreeMap.java:613-621)
         if (__popc(sub ^ pid) > c.steps) continue;
@@ -48,13 +45,9 @@ k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
         int ptr, cnt;
         warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);
         total += leader ? cnt : 0;
-        const uint32_t m = __ballot_sync(0xffffffffu, leader);
-        if (cache && leader) cache[wid * cache_cap + nbuckets + __popc(m & ((1u << lane) - 1u))] = make_int2(ptr, cnt);
-        nbuckets += __popc(m);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0 && pair_cnt) pair_cnt[wid] = (uint32_t)nbuckets;
     if (lane == 0 && total > 0) atomicAdd(&q_ub[q], total);      // (the batch total is the last scanned offset: no global counter)
 }
 
@@ -151,7 +144,7 @@ __global__ void k_gather_query_keys(const int32_t* __restrict__ keys, const uint
 }
 
 void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq) {
-    h->counters.reserve(64);
+    h->counters.reserve(CTR_COUNT);
     DPF_CUDA(cudaMemsetAsync(h->counters.p + 16, 0, sizeof(int32_t), h->stream));
     const int64_t tot = nq * h->cfg.L;
     k_gather_query_keys<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
@@ -172,38 +165,20 @@ void probe_count_all(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
     cudaStream_t st = h->stream;
     h->q_cnt.reserve(nq + 1);
     h->q_off.reserve(nq + 1);
-    h->counters.reserve(64);
-    unsigned long long* stat = reinterpret_cast<unsigned long long*>(h->counters.p + 20);
-    DPF_CUDA(cudaMemsetAsync(h->counters.p + 16, 0, 16 * sizeof(int32_t), st));
-    h->stats[DPF_STAT_BM_PAIRS] = 0;
+    h->counters.reserve(CTR_COUNT);
+    unsigned long long* stat = reinterpret_cast<unsigned long long*>(h->counters.p + CTR_STAT_NLZ);
     DPF_CUDA(cudaMemsetAsync(h->q_cnt.p, 0, (nq + 1) * sizeof(int32_t), st));
-    h->pair_cnt.reserve((size_t)nq * c.L + 1);
-    DPF_CUDA(cudaMemsetAsync(h->pair_cnt.p, 0, ((size_t)nq * c.L + 1) * sizeof(uint32_t), st));
-    // the distinct buckets found here are kept for the bucket-major re-rank (its pair list is exactly these), so that the
-    // forest is not walked a second time: <= (sub-indexes within `steps`) x 28 probe keys per (query, table)
-    int nsub = 0;
-    for (int sub = 0; sub < (1 << c.tp.pb); ++sub) nsub += __builtin_popcount((unsigned)sub) <= steps ? 1 : 0;
-    h->probe_cache_cap = nsub * (probe_mode == DPF_PROBE_NONE ? 1 : 28);
-    const size_t cache_elems = (size_t)nq * c.L * h->probe_cache_cap;
-    const bool use_cache = cache_elems * sizeof(int2) <= (512u << 20);
-    if (use_cache) h->probe_cache.reserve(cache_elems);
-    else h->probe_cache_cap = 0;
     {
         StageTimer tm(h, DPF_T_PROBE_COUNT);
         const int64_t warps = nq * c.L;
-        k_probe_count<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, h->q_cnt.p, stat,
-                                                                    h->pair_cnt.p, use_cache ? h->probe_cache.p : nullptr,
-                                                                    h->probe_cache_cap); DPF_LAUNCHED();
+        k_probe_count<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, nq, h->q_cnt.p, stat); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         exclusive_scan_i64(h, h->q_cnt.p, h->q_off.p, nq);
     }
     off_host.resize((size_t)nq + 1);
-    unsigned long long hstat[2];
     DPF_CUDA(cudaMemcpyAsync(off_host.data(), h->q_off.p, (nq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    DPF_CUDA(cudaMemcpyAsync(hstat, stat, sizeof(hstat), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaMemcpyAsync(h->counters.p + CTR_ENTRIES, h->q_off.p + nq, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     DPF_CUDA(cudaStreamSynchronize(st));
-    h->stats[DPF_STAT_NLZ_GT28] = (int64_t)hstat[0];
-    h->stats[DPF_STAT_LAST_CAND_WITH_DUPS] = off_host[(size_t)nq];
 }
 
 // end of the chunk starting at q0 whose candidate upper bound fits `budget` ids (always at least one query)
@@ -229,11 +204,8 @@ void expand_range(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, 
     DPF_CUDA(cudaMemsetAsync(next_query, 0, sizeof(int), st));
     const bool use_smem = smem_need <= 200 * 1024;
     if (use_smem) {
-        static size_t attr = 0;
-        if (smem_need > attr) {
+        if (smem_need > 48 * 1024)   // per device, hence per launch
             DPF_CUDA(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
-            attr = smem_need;
-        }
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem_need, 1)));
         const int grid = (int)std::min<int64_t>(nqc, (int64_t)h->num_sms * per_sm);
         k_expand<true><<<grid, EXP_THREADS, smem_need, st>>>(c, qk.keys, h->qpids.p, qk.ld, q0, q1, base, qk.qids, h->q_off.p,
@@ -493,6 +465,134 @@ k_topk_select(const int64_t* __restrict__ unit_off, int64_t q0, int K, int metri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_topk_direct — exhaustive top k of one query over the buckets it probes, straight from the probe result (leaf numbers
+// per table): the answer for the queries the threshold filter cannot serve (fewer than k sampled rows, or survivors that
+// did not fit the pool; flagged `dirty` on the device), with no scratch that depends on the data.  One CTA per dirty
+// query, a warp per bucket, FP64 rows scored like the row-major kernel; an id reached through several tables has the
+// same score every time and is kept once.
+// ---------------------------------------------------------------------------------------------------------
+template <bool VEC2, int METRIC>
+__global__ void __launch_bounds__(RR_THREADS)
+k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const uint32_t* __restrict__ leaf_pos,
+              const int32_t* __restrict__ leaf_len, const int32_t* __restrict__ ids_sorted, const uint32_t* __restrict__ dirty,
+              int self_exclude, int K, int32_t* __restrict__ ids_out, double* __restrict__ score_out, int* __restrict__ stat_direct) {
+    extern __shared__ double rsm[];
+    double* qs = rsm;                                    // d (padded to even)
+    double* lkeys = rsm + ((d + 1) & ~1);                // RR_WARPS x K
+    int* lids = reinterpret_cast<int*>(lkeys + RR_WARPS * K);
+    __shared__ int s_counts[RR_WARPS];
+    __shared__ double s_qn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* mykeys = lkeys + warp * K;
+    int* myids = lids + warp * K;
+    for (int64_t q = blockIdx.x; q < cv.nqc; q += gridDim.x) {
+        if (!dirty[q]) continue;                         // block-uniform
+        __syncthreads();                                 // shared lists and query of the previous round are free
+        for (int j = tid; j < d; j += RR_THREADS) qs[j] = cv.Q[q * d + j];
+        if (tid == 0) atomicAdd(stat_direct, 1);
+        __syncthreads();
+        if (METRIC == DPF_METRIC_ANGULAR) {
+            if (warp == 0) {
+                double s = 0;
+                for (int j = lane; j < d; j += 32) s = fma(qs[j], qs[j], s);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) s_qn = sqrt(s);
+            }
+            __syncthreads();
+        }
+        const double qn = (METRIC == DPF_METRIC_ANGULAR) ? s_qn : 1.0;
+        const int qid = cv.qids ? cv.qids[q] : INT32_MIN;
+        const bool excl = self_exclude && cv.qids && qid >= -128 && qid <= 127;
+        int count = 0, item = 0;
+        for (int t = 0; t < L; ++t) {
+            const uint32_t nb = cv.pair_cnt[q * L + t];
+            for (uint32_t e = 0; e < nb; ++e, ++item) {
+                if (item % RR_WARPS != warp) continue;   // warp-uniform
+                const uint32_t leaf = cv.cache[(q * L + t) * cv.cap + e];
+                const int32_t* bids = ids_sorted + leaf_pos[leaf];
+                const int len = leaf_len[leaf];
+                for (int c0 = 0; c0 < len; c0 += 32) {
+                    const int nloc = min(32, len - c0);
+                    const int myid = (lane < nloc) ? __ldg(bids + c0 + lane) : 0;
+                    for (int r0 = 0; r0 < nloc; r0 += RR_ROWS) {
+                        int id[RR_ROWS];
+#pragma unroll
+                        for (int r = 0; r < RR_ROWS; ++r) id[r] = __shfl_sync(0xffffffffu, myid, min(r0 + r, nloc - 1));
+                        double s[RR_ROWS], xn[RR_ROWS];
+                        score_rows<VEC2, METRIC>(X, d, qs, id, lane, s, xn);
+#pragma unroll
+                        for (int r = 0; r < RR_ROWS; ++r) {
+                            if (r0 + r >= nloc) continue;
+                            double v = s[r];
+                            if (METRIC == DPF_METRIC_ANGULAR) v = v / (qn * sqrt(xn[r]));
+                            const double key = (METRIC == DPF_METRIC_L2) ? -v : v;
+                            if (!(key == key) || (excl && id[r] == qid)) continue;            // NaN is never ranked
+                            if (count == K && !better(key, id[r], mykeys[K - 1], myids[K - 1])) continue;
+                            bool dup = false;
+                            for (int b2 = 0; b2 < count; b2 += 32) dup |= __any_sync(0xffffffffu, b2 + lane < count && myids[b2 + lane] == id[r]);
+                            if (!dup) warp_insert(mykeys, myids, count, K, key, id[r], lane);
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) s_counts[warp] = count;
+        __syncthreads();
+        if (warp == 0) {                                 // merge; the same id in two lists carries the same score: adjacent, kept once
+            int head = 0, last = -1;
+            const int mycount = lane < RR_WARPS ? s_counts[lane] : 0;
+            for (int r = 0; r < K; ++r) {
+                double bk;
+                int bi, bl;
+                for (;;) {
+                    bk = 0; bi = 0x7fffffff; bl = -1;
+                    if (lane < RR_WARPS && head < mycount) { bk = lkeys[lane * K + head]; bi = lids[lane * K + head]; bl = lane; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                        if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+                    }
+                    if (bl < 0) break;
+                    if (lane == bl) head++;
+                    if (bi != last) break;
+                }
+                if (lane == 0) {
+                    ids_out[q * K + r] = bl >= 0 ? bi : -1;
+                    score_out[q * K + r] = bl >= 0 ? (METRIC == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
+                }
+                if (bl >= 0) last = bi;
+            }
+        }
+    }
+}
+
+void topk_direct(dpf_index* h, const ChunkView& cv, const uint32_t* dirty, int topk, int metric, int32_t* ids_out, double* score_out) {
+    const int d = h->cfg.d;
+    const size_t smem = (size_t)((d + 1) & ~1) * sizeof(double) + (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
+    const bool vec2 = (d % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0);
+    const int grid = (int)std::min<int64_t>(cv.nqc, (int64_t)h->num_sms * 4);
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024) DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, RR_THREADS, smem, h->stream>>>(h->Xdev, d, cv, h->cfg.L, h->leaf_pos.p, h->leaf_len.p, h->ids_sorted.p, dirty,
+                                                    h->cfg.self_exclude_small_ids, topk, ids_out, score_out, h->counters.p + CTR_DIRECT);
+        DPF_LAUNCHED();
+        DPF_CUDA(cudaGetLastError());
+    };
+    if (vec2) {
+        if (metric == DPF_METRIC_DOT) go(k_topk_direct<true, DPF_METRIC_DOT>);
+        else if (metric == DPF_METRIC_ANGULAR) go(k_topk_direct<true, DPF_METRIC_ANGULAR>);
+        else go(k_topk_direct<true, DPF_METRIC_L2>);
+    } else {
+        if (metric == DPF_METRIC_DOT) go(k_topk_direct<false, DPF_METRIC_DOT>);
+        else if (metric == DPF_METRIC_ANGULAR) go(k_topk_direct<false, DPF_METRIC_ANGULAR>);
+        else go(k_topk_direct<false, DPF_METRIC_L2>);
+    }
+}
+
 __global__ void k_counts_from_offsets(const int64_t* __restrict__ off, int64_t nq, int32_t* __restrict__ cnt) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq) cnt[i] = (int32_t)(off[i + 1] - off[i]);
@@ -502,11 +602,9 @@ template <bool VEC2, int METRIC>
 static void launch_rerank_units(dpf_index* h, int grid, size_t smem, const double* Qd, int64_t q0, int64_t nqc, int64_t base,
                                 const int64_t* off, const int32_t* cnt, const int32_t* cand, int seg, int topk,
                                 int* next_unit) {
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
+    // (function attributes are per device: set per launch, not once per process)
+    if (smem > 48 * 1024)
         DPF_CUDA(cudaFuncSetAttribute(k_rerank_units<VEC2, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
     k_rerank_units<VEC2, METRIC><<<grid, RR_THREADS, smem, h->stream>>>(h->Xdev, h->cfg.d, Qd, q0, nqc, base, off, cnt, cand,
                                                                         h->unit_off.p, seg, topk, h->part_key.p,
                                                                         h->part_id.p, next_unit);
@@ -531,7 +629,7 @@ void rerank_topk(dpf_index* h, const double* Qd, int64_t q0, int64_t q1, int64_t
     h->unit_off.reserve(nqc + 1);
     h->part_key.reserve((size_t)units_ub * topk);
     h->part_id.reserve((size_t)units_ub * topk);
-    h->counters.reserve(64);
+    h->counters.reserve(CTR_COUNT);
     int* next_unit = h->counters.p + 17;
     DPF_CUDA(cudaMemsetAsync(next_unit, 0, sizeof(int), st));
     k_unit_counts<<<(unsigned)((nqc + 255) / 256), 256, 0, st>>>(cnt, q0, nqc, seg, h->ucnt.p); DPF_LAUNCHED();

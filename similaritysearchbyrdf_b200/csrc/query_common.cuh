@@ -19,7 +19,7 @@ struct ProbeCtx {
 // bucket lookup for one probe key (RandomDrawTreeMap.java:940-994): empty slot -> nothing; leaf -> (ptr,cnt);
 // directory -> descend; falling off level 0 -> nothing
 __device__ __forceinline__ bool descend(const ForestView& f, const TreeParams& tp, int root_node, uint32_t probe,
-                                        int& ptr, int& cnt) {
+                                        int& ptr, int& cnt, int64_t* slot_index = nullptr) {
     int node = root_node;
     for (int level = tp.MAXL; level >= 0; --level) {
         const int slot = (int)((probe >> (tp.nb * level)) & (uint32_t)(tp.W - 1));
@@ -27,7 +27,7 @@ __device__ __forceinline__ bool descend(const ForestView& f, const TreeParams& t
         const int c = __ldg(f.child_cnt + idx);
         const int p = __ldg(f.child_ptr + idx);
         if (c == 0) return false;
-        if (c > 0) { ptr = p; cnt = c; return true; }
+        if (c > 0) { ptr = p; cnt = c; if (slot_index) *slot_index = idx; return true; }
         node = p;
     }
     return false;
@@ -55,6 +55,24 @@ __device__ __forceinline__ void warp_lookup(const ProbeCtx& c, int t, int sub, i
     const int key = ok ? ptr : (-1 - lane);
     const uint32_t peers = __match_any_sync(0xffffffffu, key);
     leader = ok && ((__ffs(peers) - 1) == lane);
+}
+
+// The same, returning the dense leaf number (ForestView::child_leaf) of every distinct bucket instead of its range.
+__device__ __forceinline__ void warp_lookup_leaf(const ProbeCtx& c, int t, int sub, int seg, uint32_t h, int nprobes,
+                                                 int lane, bool& leader, uint32_t& leaf, int& cnt) {
+    int ptr = 0;
+    cnt = 0;
+    leaf = 0;
+    bool ok = false;
+    int64_t idx = 0;
+    if (lane < nprobes) {
+        const uint32_t probe = (c.probe_mode == DPF_PROBE_NONE) ? h : (h ^ (1u << lane));
+        ok = descend(c.f, c.tp, t * c.tp.R + sub * c.tp.SEG + seg, probe, ptr, cnt, &idx);
+    }
+    const int key = ok ? ptr : (-1 - lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    leader = ok && ((__ffs(peers) - 1) == lane);
+    if (leader) leaf = __ldg(c.f.child_leaf + idx);
 }
 
 constexpr int RR_THREADS = 256;

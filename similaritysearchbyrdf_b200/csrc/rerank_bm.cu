@@ -34,132 +34,14 @@ namespace dpf {
 
 bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
     if (h->dbg[DPF_DBG_RERANK] == 1) return false;             // test hook: force the row-major kernel
-    if (!(h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 && (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
+    if (!(h->leaf_table && h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 && (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
           topk <= RR_MAXK))                                    // d even: the queries are FP64 rows moved in 16-byte pieces
         return false;
     if (metric == DPF_METRIC_DOT || metric == DPF_METRIC_ANGULAR) return true;
     // squared L2 = |q|^2 + |x|^2 - 2 q.x cancels in floating point; it is exact — and then identical to the reference's
-    // sum of squared differences — only on the integer pipeline: byte rows and a batch of byte queries
+    // sum of squared differences — only on the integer pipeline: byte rows and a batch of byte queries (the one case in
+    // which the host has to read the batch's byte flag back before it can choose the path)
     return metric == DPF_METRIC_L2 && score_u8_usable(h) && h->Q8_valid;
-}
-
-// fill pass: pair i of (query q, table t) in (q, t, lane) order
-__global__ void __launch_bounds__(256)
-k_probe_pairs(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t q0,
-              int64_t nqc, const uint32_t* __restrict__ pair_base /* (q - q0) * L + t */,
-              unsigned long long* __restrict__ pair_key, int32_t* __restrict__ pair_q, uint32_t* __restrict__ pair_len) {
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= nqc * c.L) return;
-    const int64_t q = q0 + wid / c.L;
-    const int t = (int)(wid % c.L);
-    const uint32_t h = (uint32_t)qkeys[(int64_t)t * ld + q];
-    const int pid = qpids[(int64_t)t * ld + q];
-    const int seg = c.tp.seg_bits ? (int)(h >> c.tp.bucket_bits) : 0;
-    const int nprobes = probe_count(h, c.probe_mode);
-    if (nprobes < 0) return;
-    uint32_t at = pair_base[wid];
-    const long long tbase = c.f.table_base[t];
-    const int np = 1 << c.tp.pb;
-    for (int sub = 0; sub < np; ++sub) {
-        if (__popc(sub ^ pid) > c.steps) continue;
-        if (!c.own.has(sub)) continue;
-        bool leader;
-        int ptr, cnt;
-        warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);
-        const uint32_t m = __ballot_sync(0xffffffffu, leader);
-        if (leader) {
-            const uint32_t i = at + __popc(m & ((1u << lane) - 1u));
-            pair_key[i] = ((unsigned long long)(tbase + ptr) << 32) | i;   // sort key: bucket start; payload: pair index
-            pair_q[i] = (int32_t)q;
-            pair_len[i] = (uint32_t)cnt;
-        }
-        at += __popc(m);
-    }
-}
-
-// the same fill from the buckets the probe pass cached (k_probe_count): no second walk of the forest
-__global__ void __launch_bounds__(256)
-k_pairs_from_cache(const int2* __restrict__ cache, int cap, const int64_t* __restrict__ table_base, int L, int64_t q0, int64_t nqc,
-                   const uint32_t* __restrict__ pair_base, unsigned long long* __restrict__ pair_key, int32_t* __restrict__ pair_q,
-                   uint32_t* __restrict__ pair_len) {
-    const int lane = threadIdx.x & 31;
-    const int64_t wl = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wl >= nqc * L) return;
-    const int64_t q = q0 + wl / L;
-    const int t = (int)(wl % L);
-    const uint32_t at = pair_base[wl], nb = pair_base[wl + 1] - at;
-    const long long tbase = table_base[t];
-    const int2* src = cache + (q * L + t) * cap;
-    for (uint32_t i = lane; i < nb; i += 32) {
-        const int2 e = src[i];
-        pair_key[at + i] = ((unsigned long long)(tbase + e.x) << 32) | (at + i);
-        pair_q[at + i] = (int32_t)q;
-        pair_len[at + i] = (uint32_t)e.y;
-    }
-}
-
-// flag[p] = 1 where a run starts
-__global__ void __launch_bounds__(256)
-k_run_flags(const unsigned long long* __restrict__ sorted, int64_t npairs, uint32_t* __restrict__ flag) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    flag[p] = (p == 0 || (uint32_t)(sorted[p - 1] >> 32) != (uint32_t)(sorted[p] >> 32)) ? 1u : 0u;
-}
-
-// run_idx = exclusive scan of flag: the flagged position p starts run run_idx[p]
-__global__ void __launch_bounds__(256)
-k_run_starts(const unsigned long long* __restrict__ sorted, int64_t npairs, const uint32_t* __restrict__ run_idx,
-             uint32_t* __restrict__ run_start, uint32_t* __restrict__ nruns_out) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    const bool start = p == 0 || (uint32_t)(sorted[p - 1] >> 32) != (uint32_t)(sorted[p] >> 32);
-    if (start) run_start[run_idx[p]] = (uint32_t)p;
-    if (p == npairs - 1) {
-        const uint32_t nruns = run_idx[p] + (start ? 1u : 0u);
-        run_start[nruns] = (uint32_t)npairs;
-        *nruns_out = nruns;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_run_unit_counts(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ nruns_p, int64_t cap,
-                  uint32_t* __restrict__ ucnt) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= cap) return;
-    const uint32_t nruns = *nruns_p;
-    ucnt[r] = r < nruns ? (run_start[r + 1] - run_start[r] + SS_UQ - 1) / SS_UQ : 0u;
-}
-
-// uoff = exclusive scan of ucnt.  One thread per sorted position; the positions that open a unit (every SS_UQ-th
-// of a run) write its record.
-__global__ void __launch_bounds__(256)
-k_emit_units(const unsigned long long* __restrict__ sorted, int64_t npairs, const uint32_t* __restrict__ run_idx,
-             const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ uoff, const int32_t* __restrict__ pair_q,
-             const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg, const int32_t* __restrict__ ids_sorted,
-             UnitRec* __restrict__ units) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    const unsigned long long k = sorted[p];
-    const uint32_t bstart = (uint32_t)(k >> 32);
-    const bool start = p == 0 || (uint32_t)(sorted[p - 1] >> 32) != bstart;
-    const uint32_t r = run_idx[p] + (start ? 1u : 0u) - 1u;
-    const uint32_t p0 = run_start[r], p1 = run_start[r + 1];
-    if ((p - p0) % SS_UQ) return;
-    UnitRec rec;
-    rec.bstart = bstart;
-    rec.len = pair_len[(uint32_t)k];
-    rec.pos0 = (uint32_t)p;
-    rec.m = min((uint32_t)SS_UQ, p1 - (uint32_t)p);
-#pragma unroll
-    for (int j = 0; j < SS_UQ; ++j) {
-        const uint32_t pi = (uint32_t)sorted[min((uint32_t)p + j, p1 - 1)];
-        rec.q[j] = pair_q[pi];
-        rec.seg[j] = pair_seg[pi];
-    }
-#pragma unroll
-    for (int j = 0; j < SS_WIN; ++j) rec.ids0[j] = ids_sorted[bstart + min((uint32_t)j, rec.len - 1)];
-    units[uoff[r] + (uint32_t)(p - p0) / SS_UQ] = rec;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -264,7 +146,7 @@ template <bool ANGULAR, int KIND>
 __global__ void __launch_bounds__(SS_WARPS * 32, 1)
 k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes per stored row, multiple of 16 */, int d,
                const double* __restrict__ Q, const UnitRec* __restrict__ units,
-               const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, double* __restrict__ scores,
+               const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, Filter flt,
                unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
     using SK = StoreKind<KIND>;
     constexpr int E = SK::E;
@@ -273,7 +155,7 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
     constexpr int SLOT_DOUBLES = SS_ROWS * SS_PITCH;
     extern __shared__ __align__(128) unsigned char ssm_raw[];
     __shared__ uint64_t bars[SS_WARPS][SS_STAGES + 4];   // ring slots, 2 unit records, 2 id windows
-    __shared__ int4 meta[SS_WARPS][SS_STAGES];           // per slot: {kind: 0/1 query block, 2 rows; first row; rows; m}
+    __shared__ int4 meta[SS_WARPS][SS_STAGES];           // per slot: {kind: 0/1 query block, 2 rows; first row; rows | m << 8; bucket start}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     unsigned char* wbase = ssm_raw + (size_t)warp * ((SS_WARP_BYTES + 15) / 16 * 16);
@@ -308,6 +190,7 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
     unsigned win_uses0 = 0, win_uses1 = 0;   // completed waits on each id-window barrier (-> parity)
     int issued = 0, consumed = 0;
     unsigned long long rows_staged = 0;
+    SurvivorSink sink;
     auto fetch_rec = [&](int64_t k) {
         if (k < nmine && lane == 0) {
             mbar_expect_tx(&bar_rec[k & 1], (unsigned)sizeof(UnitRec));
@@ -341,14 +224,18 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
         if (p_phase < 2) {             // 8 query rows (always FP64)
             const int nrows = min(SS_ROWS, (int)p_m - SS_ROWS * p_phase);
             if (lane == 0) {
-                meta[warp][s] = make_int4(p_phase, 0, nrows, (int)p_m);
-                mbar_expect_tx(&bar_slot[s], (unsigned)nrows * q_bytes);
+                meta[warp][s] = make_int4(p_phase, 0, nrows | ((int)p_m << 8), (int)p_bstart);
+                mbar_expect_tx(&bar_slot[s], (unsigned)nrows * (q_bytes + 16u));
             }
             __syncwarp();
             if (lane < nrows) {
                 const int j = SS_ROWS * p_phase + lane;
-                reinterpret_cast<uint32_t*>(slot + (size_t)lane * SS_PITCH + BM_KC)[0] = r->seg[j];   // rides in the row's padding
-                bulk_g2s(slot + (size_t)lane * SS_PITCH, Q + (int64_t)r->q[j] * d, q_bytes, &bar_slot[s], pol_keep);
+                const int qj = r->q[j];
+                // the query's index and its threshold ride in the row's padding: the index by a plain store, the threshold
+                // (with its 16-byte neighbour) by a bulk copy — no demand load from this loop
+                reinterpret_cast<int32_t*>(slot + (size_t)lane * SS_PITCH + BM_KC)[0] = qj;
+                bulk_g2s(slot + (size_t)lane * SS_PITCH + BM_KC + 2, flt.tau + (qj & ~1), 16u, &bar_slot[s], pol_keep);
+                bulk_g2s(slot + (size_t)lane * SS_PITCH, Q + (int64_t)qj * d, q_bytes, &bar_slot[s], pol_keep);
             }
             p_phase = (p_phase == 0 && p_m > SS_ROWS) ? 1 : 2;
         } else {
@@ -362,7 +249,7 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
             }
             const int nrows = min(SS_ROWS, (int)p_len - p_row);
             if (lane == 0) {
-                meta[warp][s] = make_int4(2, p_row, nrows, (int)p_m);
+                meta[warp][s] = make_int4(2, p_row, nrows | ((int)p_m << 8), (int)p_bstart);
                 mbar_expect_tx(&bar_slot[s], (unsigned)nrows * row_bytes);
             }
             __syncwarp();
@@ -383,7 +270,8 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
 
     // ---- consumer state ---------------------------------------------------------------------------------------
     double B[2][NS];                    // queries g (n-block 0) and 8 + g (n-block 1), k-step order
-    uint32_t c_seg[2][2] = {{0, 0}, {0, 0}};
+    int c_q[2][2] = {{0, 0}, {0, 0}};
+    double c_tau[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     bool c_ok[2][2] = {{false, false}, {false, false}};
     double c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
     int c_nb = 0;                       // n-blocks in use
@@ -397,10 +285,11 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
         const int4 mt = meta[warp][s];
         const double* slot = ring + (size_t)s * SLOT_DOUBLES;
         mbar_wait(&bar_slot[s], (unsigned)((consumed / SS_STAGES) & 1));
+        const int mt_rows = mt.z & 0xff, mt_m = mt.z >> 8;
         if (mt.x < 2) {
-            // query block mt.x of a unit of mt.w queries -> B fragments (columns >= d are 0), score segments, norms
+            // query block mt.x of a unit of mt_m queries -> B fragments (columns >= d are 0), query indices, thresholds, norms
             const double* br = slot + (size_t)g * SS_PITCH;
-            if (mt.x == 0) c_nb = (mt.w + 7) >> 3;
+            if (mt.x == 0) c_nb = (mt_m + 7) >> 3;
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) {
                 if (nb == mt.x) {
@@ -422,8 +311,10 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
                         }
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        c_seg[nb][e] = reinterpret_cast<const uint32_t*>(slot + (size_t)(2 * t + e) * SS_PITCH + BM_KC)[0];
-                        c_ok[nb][e] = 8 * nb + 2 * t + e < mt.w;
+                        const double* pad = slot + (size_t)(2 * t + e) * SS_PITCH + BM_KC;
+                        c_ok[nb][e] = 8 * nb + 2 * t + e < mt_m;
+                        c_q[nb][e] = c_ok[nb][e] ? reinterpret_cast<const int32_t*>(pad)[0] : 0;
+                        c_tau[nb][e] = pad[2 + (c_q[nb][e] & 1)];
                     }
                     if (ANGULAR) {
                         double sq = 0.0;    // ||query 8nb + g||^2: this thread's columns, then the 4 threads of the group
@@ -478,21 +369,23 @@ k_score_stream(const unsigned char* __restrict__ X, unsigned row_bytes /* bytes 
             xn += __shfl_xor_sync(0xffffffffu, xn, 2);
             xnr = sqrt(xn);
         }
-        // thread (g, t) holds (row mt.y + g, queries 8nb + 2t, 8nb + 2t + 1)
-        if (g < mt.z) {
-            const uint32_t row = (uint32_t)(mt.y + g);
+        // thread (g, t) holds (row mt.y + g, queries 8nb + 2t, 8nb + 2t + 1); only scores that reach the query's
+        // threshold leave the kernel
+        {
+            const uint32_t pos = (uint32_t)mt.w + (uint32_t)(mt.y + g);
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    if (nb < c_nb && c_ok[nb][e]) {
-                        const double v = acc[nb][0][e] + acc[nb][1][e];
-                        scores[(size_t)c_seg[nb][e] + row] = ANGULAR ? v / (c_qn[nb][e] * xnr) : v;
-                    }
+                for (int e = 0; e < 2; ++e) {
+                    double v = acc[nb][0][e] + acc[nb][1][e];
+                    if (ANGULAR) v = v / (c_qn[nb][e] * xnr);
+                    sink.push(flt, g < mt_rows && nb < c_nb && c_ok[nb][e] && v >= c_tau[nb][e], c_q[nb][e], pos, v, lane);
+                }
         }
         __syncwarp();                       // every lane has read the slot before it is refilled
         consumed++;
     }
+    sink.flush(flt, lane);
     if (lane == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], rows_staged); }
 }
 
@@ -533,13 +426,19 @@ __device__ __forceinline__ void raw_to_cols16(const uint4 (&raw)[RawRow<KIND>::N
 // same value the integer tensor pipe produces, no rounding allowance needed for the dot product.
 template <bool ANGULAR, int KIND, bool INTQ>
 __global__ void __launch_bounds__(RR_THREADS)
-k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, const double* __restrict__ Q,
-            const unsigned char* __restrict__ Q8, int q8_pitch, const double* __restrict__ qnorm8, int64_t q0, int64_t nqc,
-            int L, int NT, const uint32_t* __restrict__ pair_base, const unsigned long long* __restrict__ pair_key_unsorted,
-            const uint32_t* __restrict__ pair_len, const int32_t* __restrict__ ids_sorted,
-            const int32_t* __restrict__ qids, int self_exclude, int K, double* __restrict__ tl_keys, int* __restrict__ tl_ids,
-            int* __restrict__ tl_cnt) {
+k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, ChunkView cv, int q8_pitch, int gate,
+            int L, int NT, const uint32_t* __restrict__ leaf_pos, const int32_t* __restrict__ leaf_len,
+            const int32_t* __restrict__ ids_sorted, int self_exclude, int K, double* __restrict__ tl_keys,
+            int* __restrict__ tl_ids, int* __restrict__ tl_cnt) {
     static_assert(!INTQ || KIND == DPF_STORE_KIND_U8, "integer path needs byte rows");
+    // gate: 0 always; 1 only when the whole batch is byte vectors; 2 only when it is not (the host launches both forms
+    // for a byte store and the batch's flag, still on the device, picks one)
+    if (gate && ((*cv.q8_bad != 0) != (gate == 2))) return;
+    const double* __restrict__ Q = cv.Q;
+    const unsigned char* __restrict__ Q8 = cv.Q8;
+    const double* __restrict__ qnorm8 = cv.qnorm8;
+    const int32_t* __restrict__ qids = cv.qids;
+    const int64_t nqc = cv.nqc;
     constexpr int RN = RawRow<KIND>::N;
     constexpr int SZ = KIND == DPF_STORE_KIND_U8 ? 1 : (KIND == DPF_STORE_KIND_F32 ? 4 : 8);
     constexpr int PFT = KIND == DPF_STORE_KIND_U8 ? 4 : 2;     // steps (of 4 rows) whose rows are in flight per warp
@@ -554,7 +453,7 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, cons
     if (wid >= nqc * NT) return;
     const int64_t ql = wid / NT;
     const int sample = (int)(wid % NT);
-    const int64_t q = q0 + ql;
+    const int64_t q = ql;
     const int qid = qids ? qids[q] : INT32_MIN;
     const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
     const int c0 = 16 * l8;
@@ -583,18 +482,16 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, cons
         }
     }
     const double slack = 4.0 * (double)(d + 8) * 1.1102230246251565e-16;     // >= twice the bound, with room for the norms
-    // tables (among the first 32) in which the query probes something; lane t holds the first pair of table t
-    const uint32_t p_mine = lane < L ? pair_base[ql * L + lane] : 0u;
-    const uint32_t p_next = lane < L ? pair_base[ql * L + lane + 1] : 0u;
-    uint32_t nonempty = __ballot_sync(0xffffffffu, lane < L && p_next > p_mine);
+    // tables (among the first 32) in which the query probes something
+    uint32_t nonempty = __ballot_sync(0xffffffffu, lane < L && cv.pair_cnt[ql * L + min(lane, L - 1)] > 0u);
     int count = 0;
     double kth = 0.0;                        // mykeys[K - 1] once the list is full
     for (int i = 0; i < sample && nonempty; ++i) nonempty &= nonempty - 1;
-    if (nonempty) {                          // the sample-th table that has a pair
+    if (nonempty) {                          // the sample-th table that has a pair: the first bucket the query probes there
         const int t = __ffs(nonempty) - 1;
-        const uint32_t p = __shfl_sync(0xffffffffu, p_mine, t);
-        const uint32_t bstart = (uint32_t)(pair_key_unsorted[p] >> 32);
-        const int len = (int)pair_len[p];
+        const uint32_t leaf = cv.cache[(ql * L + t) * cv.cap];
+        const uint32_t bstart = leaf_pos[leaf];
+        const int len = leaf_len[leaf];
         const int32_t* bids = ids_sorted + bstart;
         const int nmine = (len + 3) >> 2;    // steps of 4 rows; ids two groups of PFT steps ahead, rows one group ahead
         uint4 raw[PFT][RN];
@@ -692,15 +589,15 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, cons
 }
 
 // one warp per query: tau = k-th best distinct row over its NT sample lists (a row sampled through two tables has the
-// same bound in both lists, so duplicates are adjacent in the merged order); also resets the query's survivor list
+// same bound in both lists, so duplicates are adjacent in the merged order).  Fewer than k distinct rows in the samples:
+// no threshold can be guaranteed, the query is flagged for k_topk_direct and tau = +inf keeps it out of the pool.
 __global__ void __launch_bounds__(RR_THREADS)
-k_threshold_merge(int64_t q0, int64_t nqc, int L, int NT, int K, const double* __restrict__ tl_keys, const int* __restrict__ tl_ids,
-                  const int* __restrict__ tl_cnt, const uint32_t* __restrict__ pair_base, const uint32_t* __restrict__ pair_seg,
-                  double* __restrict__ tau, uint32_t* __restrict__ s_cnt, uint32_t* __restrict__ s_base) {
+k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys, const int* __restrict__ tl_ids,
+                  const int* __restrict__ tl_cnt, double* __restrict__ tau, uint32_t* __restrict__ dirty) {
     const int lane = threadIdx.x & 31;
     const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
     if (ql >= nqc) return;
-    const int64_t q = q0 + ql;
+    const int64_t q = ql;
     const double* lkeys = tl_keys + (ql * NT + lane) * K;
     const int* lids = tl_ids + (ql * NT + lane) * K;
     const int mycount = lane < NT ? tl_cnt[ql * NT + lane] : 0;
@@ -722,35 +619,8 @@ k_threshold_merge(int64_t q0, int64_t nqc, int L, int NT, int K, const double* _
         if (bi != last) { found++; kth = bk; last = bi; }
     }
     if (lane == 0) {
-        tau[q] = found == K ? kth : -__longlong_as_double(0x7ff0000000000000LL);
-        const uint32_t pbeg = pair_base[ql * L], pend = pair_base[(ql + 1) * L];
-        s_cnt[q] = 0u;
-        s_base[q] = pbeg < pend ? pair_seg[pbeg] : 0u;
-    }
-}
-
-// survivor records (SurvivorSink) -> per-query lists: at = base[q] + (old count of q); the row id is looked up here.
-// Survivors of one query come in bursts (a bucket near the query yields many), so the lanes of a warp that hold the
-// same query reserve their slots with one atomic.
-__global__ void __launch_bounds__(256)
-k_scatter_survivors(Filter flt, const int32_t* __restrict__ ids_sorted) {
-    const uint32_t n = *flt.pool_cursor;
-    const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n; i0 += stride) {   // warp-uniform trip count
-        const uint32_t i = i0 + lane;
-        SurvRec r;
-        r.q = -1;
-        if (i < n) r = flt.pool[i];
-        const uint32_t peers = __match_any_sync(0xffffffffu, r.q);
-        if (r.q < 0) continue;
-        const int leader = __ffs(peers) - 1;
-        uint32_t first = 0;
-        if (lane == leader) first = atomicAdd(flt.cnt + r.q, (uint32_t)__popc(peers));
-        first = __shfl_sync(peers, first, leader);
-        const uint32_t at = flt.base[r.q] + first + __popc(peers & ((1u << lane) - 1u));
-        flt.s_score[at] = r.score;
-        flt.s_id[at] = __ldg(ids_sorted + r.pos);
+        tau[q] = found == K ? kth : __longlong_as_double(0x7ff0000000000000LL);
+        if (found < K) dirty[q] = 1u;
     }
 }
 
@@ -771,6 +641,7 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
     const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + warp;
     if (ql >= nqc) return;
     const int64_t q = q0 + ql;
+    if (flt.dirty[q]) return;                // answered by k_topk_direct
     const uint32_t n = flt.cnt[q];
     if (lane == 0) atomicAdd(&stat[2], (unsigned long long)n);
     if (n > SEL_BIG) {                       // a weak threshold left a long list: k_select_survivors_big (a CTA per query)
@@ -877,144 +748,6 @@ k_select_survivors_big(int64_t q0, Filter flt, const int32_t* __restrict__ qids,
     }
 }
 
-// per-query selection from its score segments: one CTA per query, a warp walks whole pairs
-__global__ void __launch_bounds__(RR_THREADS)
-k_select_pairs(int64_t q0, int L, const uint32_t* __restrict__ pair_base, const unsigned long long* __restrict__ pair_key_unsorted,
-               const uint32_t* __restrict__ pair_len, const uint32_t* __restrict__ pair_seg,
-               const int32_t* __restrict__ ids_sorted, const double* __restrict__ scores, const int32_t* __restrict__ qids,
-               int self_exclude, int K, int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
-    extern __shared__ double rsm[];
-    double* lkeys = rsm;                                 // RR_WARPS x K
-    int* lids = reinterpret_cast<int*>(lkeys + RR_WARPS * K);
-    __shared__ int s_counts[RR_WARPS];
-    const int64_t ql = blockIdx.x, q = q0 + ql;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* mykeys = lkeys + warp * K;
-    int* myids = lids + warp * K;
-    const uint32_t pbeg = pair_base[ql * L], pend = pair_base[(ql + 1) * L];
-    const int qid = qids ? qids[q] : INT32_MIN;
-    const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
-    int count = 0;
-    // a warp walks whole pairs; SEL_U x 32 entries of a segment are loaded before any is examined (the loop is
-    // otherwise one dependent load per iteration), and the next pair's descriptor is fetched one pair ahead
-    constexpr int SEL_U = 4;
-    uint32_t p = pbeg + warp;
-    uint32_t n_bstart = 0, n_seg = 0;
-    int n_len = 0;
-    if (p < pend) { n_bstart = (uint32_t)(pair_key_unsorted[p] >> 32); n_len = (int)pair_len[p]; n_seg = pair_seg[p]; }
-    for (; p < pend; p += RR_WARPS) {
-        const uint32_t bstart = n_bstart;
-        const int len = n_len;
-        const double* sc = scores + n_seg;
-        const int32_t* ids = ids_sorted + bstart;
-        if (p + RR_WARPS < pend) {
-            n_bstart = (uint32_t)(pair_key_unsorted[p + RR_WARPS] >> 32);
-            n_len = (int)pair_len[p + RR_WARPS];
-            n_seg = pair_seg[p + RR_WARPS];
-        }
-        for (int j0 = 0; j0 < len; j0 += 32 * SEL_U) {
-            const double nan = __longlong_as_double(0x7ff8000000000000LL);
-            const int j = j0 + lane;
-            const double k0 = j < len ? sc[j] : nan, k1 = j + 32 < len ? sc[j + 32] : nan;
-            const double k2 = j + 64 < len ? sc[j + 64] : nan, k3 = j + 96 < len ? sc[j + 96] : nan;
-            const int i0 = j < len ? __ldg(ids + j) : -1, i1 = j + 32 < len ? __ldg(ids + j + 32) : -1;
-            const int i2 = j + 64 < len ? __ldg(ids + j + 64) : -1, i3 = j + 96 < len ? __ldg(ids + j + 96) : -1;
-            auto examine = [&](double key, int id) {
-                bool cand = (key == key) && !(excl && id == qid);
-                if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
-                uint32_t todo = __ballot_sync(0xffffffffu, cand);
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const double kk = __shfl_sync(0xffffffffu, key, src);
-                    const int ii = __shfl_sync(0xffffffffu, id, src);
-                    // the same id reached through another table carries a bit-identical score: keep it once
-                    bool dup = false;
-                    for (int base = 0; base < count; base += 32) {
-                        const int i = base + lane;
-                        dup |= __any_sync(0xffffffffu, i < count && myids[i] == ii);
-                    }
-                    if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
-                }
-            };
-            static_assert(SEL_U == 4, "examine() calls below are written out");
-            examine(k0, i0);
-            examine(k1, i1);
-            examine(k2, i2);
-            examine(k3, i3);
-        }
-    }
-    if (lane == 0) s_counts[warp] = count;
-    __syncthreads();
-    if (warp == 0) {
-        int head = 0, last = -1;
-        const int mycount = lane < RR_WARPS ? s_counts[lane] : 0;
-        for (int r = 0; r < K; ++r) {
-            double bk;
-            int bi, bl;
-            for (;;) {
-                bk = 0; bi = 0x7fffffff; bl = -1;
-                if (lane < RR_WARPS && head < mycount) { bk = lkeys[lane * K + head]; bi = lids[lane * K + head]; bl = lane; }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                    if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
-                }
-                if (bl < 0) break;
-                if (lane == bl) head++;
-                if (bi != last) break;                   // duplicate across warps: skip
-            }
-            if (lane == 0) {
-                ids_out[q * K + r] = bl >= 0 ? bi : -1;
-                score_out[q * K + r] = bl >= 0 ? bk : __longlong_as_double(0x7ff8000000000000LL);
-            }
-            if (bl >= 0) last = bi;
-        }
-    }
-}
-
-__global__ void k_copy_u32(const uint32_t* __restrict__ a, uint32_t* __restrict__ b, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) b[i] = a[i];
-}
-
-
-// no bucket probed by any query of the chunk: every result row is padding (-1, NaN)
-__global__ void k_topk_select_empty(int64_t q0, int64_t nqc, int K, int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nqc * K) return;
-    ids_out[q0 * K + i] = -1;
-    score_out[q0 * K + i] = __longlong_as_double(0x7ff8000000000000LL);
-}
-
-
-// runs of the sorted pair list -> unit records in h->bm_units (device); the number of units is also left in
-// h->bm_counts[1]
-static void build_units(dpf_index* h, int64_t npairs) {
-    cudaStream_t st = h->stream;
-    const unsigned gp = (unsigned)((npairs + 255) / 256);
-    h->bm_flag.reserve(npairs + 1);
-    h->bm_run_start.reserve(npairs + 2);
-    h->bm_ucnt.reserve(npairs + 2);
-    h->bm_counts.reserve(4);
-    k_run_flags<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p); DPF_LAUNCHED();
-    exclusive_scan_u32(h, h->bm_flag.p, npairs);
-    k_run_starts<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_counts.p); DPF_LAUNCHED();
-    k_run_unit_counts<<<(unsigned)((npairs + 1 + 255) / 256), 256, 0, st>>>(h->bm_run_start.p, h->bm_counts.p, npairs + 1,
-                                                                            h->bm_ucnt.p); DPF_LAUNCHED();
-    exclusive_scan_u32(h, h->bm_ucnt.p, npairs + 1);      // bm_ucnt[r] = first unit of run r; [npairs] = number of units
-    DPF_CUDA(cudaMemcpyAsync(h->bm_counts.p + 1, h->bm_ucnt.p + npairs, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    uint32_t nunits = 0;
-    DPF_CUDA(cudaMemcpyAsync(&nunits, h->bm_ucnt.p + npairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    DPF_CUDA(cudaStreamSynchronize(st));
-    h->bm_units.reserve((size_t)std::max<uint32_t>(nunits, 1) * sizeof(UnitRec));
-    k_emit_units<<<gp, 256, 0, st>>>(h->bm_sorted, npairs, h->bm_flag.p, h->bm_run_start.p, h->bm_ucnt.p, h->pair_q.p, h->pair_len.p,
-                                     h->pair_seg.p, h->ids_sorted.p, reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
-    DPF_CUDA(cudaGetLastError());
-}
-
 // the compact store's rows when the build found a narrower lossless type (store.cu), else the FP64 rows
 static void store_rows(const dpf_index* h, int& kind, const unsigned char*& rows, unsigned& row_bytes) {
     kind = h->Xc_kind;
@@ -1032,153 +765,138 @@ static void dispatch_kind(int kind, bool ang, F&& f) {
     else k(std::integral_constant<int, DPF_STORE_KIND_F64>{});
 }
 
+
+// One chunk of a query batch, bucket-major: probe -> pairs grouped by bucket -> units -> thresholds -> scoring (only
+// scores that can still be among a query's best k leave the kernel) -> per-query lists -> top k.  Nothing is read back
+// by the host: scratch is sized by worst cases known up front, counts stay on the device, and the few queries the
+// filter cannot serve are answered by k_topk_direct.  Every per-query array below is indexed inside the chunk.
 void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1,
-                       int64_t entries_ub, int topk, int metric, int32_t* ids_out, double* score_out) {
-    const ProbeCtx c = make_ctx(h, steps, probe_mode);
+                       int cap, int topk, int metric, int32_t* ids_out, double* score_out) {
     cudaStream_t st = h->stream;
     const int64_t nqc = q1 - q0;
-    const int L = c.L, d = h->cfg.d;
+    const int L = h->cfg.L, d = h->cfg.d;
     if (nqc <= 0) return;
-    DPF_REQUIRE(h->h_table_base[L] < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: more than 2^32 forest entries");
-    DPF_REQUIRE(entries_ub < (1LL << 32), DPF_ERR_INVALID, "bucket-major re-rank: chunk too large");
     const bool ang = metric == DPF_METRIC_ANGULAR;
     const bool l2 = metric == DPF_METRIC_L2;                    // byte pipeline only; keys are -distance, negated on output
-    // Two pipelines.  Byte store: k_threshold -> k_score_u8* (filtered output: only scores that can still be among a
-    // query's best k are kept) -> k_select_survivors.  FP64 / FP32 store: k_score_stream (dense output, one score per
-    // bucket entry) -> k_select_pairs; there the threshold pass would itself read ~1 KB rows and an append from inside
-    // the TMA pipeline is a demand access that queues behind the bulk copies, so filtering does not pay.
     const bool use_u8 = score_u8_usable(h);
     int kind;
     const unsigned char* rows;
     unsigned row_bytes;
     store_rows(h, kind, rows, row_bytes);
-    // pair offsets of this chunk = exclusive scan of the per-(query, table) bucket counts from the probe pass
-    const int64_t nslots = nqc * L + 1;
-    h->pair_base.reserve(nslots);
+    int32_t* ctr = h->counters.p;
+
+    // ---- scratch, all worst case ------------------------------------------------------------------------------------
+    const int64_t pairs_ub = nqc * L * cap;
+    const int64_t units_ub = std::min<int64_t>(pairs_ub, (int64_t)h->num_leaves + pairs_ub / SS_UQ) + 1;
+    h->bm_units.reserve((size_t)units_ub * sizeof(UnitRec));
+    int64_t pool_cap = h->dbg[DPF_DBG_POOL_RECORDS] > 0 ? h->dbg[DPF_DBG_POOL_RECORDS]
+                                                        : std::min<int64_t>(std::max<int64_t>(nqc * 2048, 1 << 20), 1LL << 28);
+    pool_cap = std::max<int64_t>(SURV_BLOCK, pool_cap / SURV_BLOCK * SURV_BLOCK);
+    h->surv_pool.reserve((size_t)pool_cap * sizeof(SurvRec));
+    h->scores.reserve((size_t)pool_cap);
+    h->surv_id.reserve((size_t)pool_cap);
+    h->bm_tau.reserve((size_t)nqc + 2);
+    // one block cleared per chunk: survivor counts, list cursors, dirty flags
+    h->bm_scnt.reserve((size_t)nqc * 3 + 4);
+    uint32_t* s_cnt = h->bm_scnt.p;
+    uint32_t* s_fill = s_cnt + nqc;
+    uint32_t* s_dirty = s_fill + nqc;
+    h->bm_sbase.reserve((size_t)nqc + 1);
+    DPF_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t)nqc * 3 * sizeof(uint32_t), st));
+    DPF_CUDA(cudaMemsetAsync(ctr + CTR_POOL, 0, 6 * sizeof(int32_t), st));      // pool cursor, chunk counts, overflow flag
+
+    probe_and_group(h, qk, steps, probe_mode, q0, nqc, cap);
+
+    ChunkView cv;
+    cv.Q = Qd + q0 * d;
+    cv.Q8 = h->Q8.p ? h->Q8.p + q0 * u8_query_pitch() : nullptr;
+    cv.qnorm8 = h->qnorm8.p ? h->qnorm8.p + q0 : nullptr;
+    cv.qsq8 = h->qsq8.p ? h->qsq8.p + q0 : nullptr;
+    cv.qids = qk.qids ? qk.qids + q0 : nullptr;
+    cv.nqc = nqc;
+    cv.q8_bad = ctr + CTR_Q8_BAD;
+    cv.pair_cnt = h->pair_cnt.p;
+    cv.cache = h->probe_cache.p;
+    cv.cap = cap;
+    const Filter flt{h->bm_tau.p, s_cnt, h->bm_sbase.p, s_fill, s_dirty, h->scores.p, h->surv_id.p,
+                     reinterpret_cast<SurvRec*>(h->surv_pool.p), reinterpret_cast<uint32_t*>(ctr + CTR_POOL), (uint32_t)pool_cap,
+                     ctr + CTR_POOL_OVERFLOW};
     const size_t list_smem = (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
     const unsigned qgrid = (unsigned)((nqc + RR_WARPS - 1) / RR_WARPS);
+
+    // ---- thresholds: a row gather, on the handle's second stream beside the grouping chain on the main one --------------
     {
-        StageTimer tm(h, DPF_T_EXPAND);
-        k_copy_u32<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->pair_cnt.p + q0 * L, h->pair_base.p, nslots - 1); DPF_LAUNCHED();
-        DPF_CUDA(cudaMemsetAsync(h->pair_base.p + nslots - 1, 0, sizeof(uint32_t), st));
-        exclusive_scan_u32(h, h->pair_base.p, nslots);
-        uint32_t npairs32 = 0;
-        DPF_CUDA(cudaMemcpyAsync(&npairs32, h->pair_base.p + nslots - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        DPF_CUDA(cudaStreamSynchronize(st));
-        const int64_t npairs = npairs32;
-        if (npairs == 0) {
-            // nothing probed: all rows padded
-            k_topk_select_empty<<<(unsigned)((nqc * topk + 255) / 256), 256, 0, st>>>(q0, nqc, topk, ids_out, score_out); DPF_LAUNCHED();
-            DPF_CUDA(cudaGetLastError());
-            return;
-        }
-        h->pair_key.reserve(npairs);
-        h->pair_key_alt.reserve(npairs);
-        h->pair_q.reserve(npairs);
-        h->pair_len.reserve(npairs + 1);
-        h->pair_seg.reserve(npairs + 1);
-        h->scores.reserve((size_t)std::max<int64_t>(entries_ub, 1));
-        const int64_t warps = nqc * L;
-        if (h->probe_cache_cap > 0)
-            k_pairs_from_cache<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(h->probe_cache.p, h->probe_cache_cap, c.f.table_base, L, q0,
-                                                                             nqc, h->pair_base.p, h->pair_key.p, h->pair_q.p,
-                                                                             h->pair_len.p);
-        else
-            k_probe_pairs<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->pair_base.p,
-                                                                        h->pair_key.p, h->pair_q.p, h->pair_len.p);
-        DPF_LAUNCHED();
-        DPF_CUDA(cudaGetLastError());
-        k_copy_u32<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pair_len.p, h->pair_seg.p, npairs); DPF_LAUNCHED();
-        exclusive_scan_u32(h, h->pair_seg.p, npairs);
+        // sampled tables per query (one warp each): 6 on one GPU; a rank of G sees 1/G of every query's buckets, so its
+        // lists stay short with fewer samples
+        const int world = h->cfg.world > 1 ? h->cfg.world : 1;
+        const int nt_default = world <= 1 ? 6 : std::max(2, 6 / world);
+        const int NT = std::min(32, std::max(1, h->dbg[DPF_DBG_TAU_TABLES] > 0 ? (int)h->dbg[DPF_DBG_TAU_TABLES] : nt_default));
+        h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
+        h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
+        h->bm_tl_cnt.reserve((size_t)nqc * NT);
+        cudaStream_t st2 = h->aux_stream;
+        DPF_CUDA(cudaEventRecord(h->ev_fork, st));
+        DPF_CUDA(cudaStreamWaitEvent(st2, h->ev_fork, 0));
+        const unsigned tgrid = (unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS);
+        auto go = [&](auto kern, int gate) {
+            kern<<<tgrid, RR_THREADS, list_smem, st2>>>(rows, row_bytes, d, cv, u8_query_pitch(), gate, L, NT, h->leaf_pos.p,
+                                                         h->leaf_len.p, h->ids_sorted.p, h->cfg.self_exclude_small_ids, topk,
+                                                         h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p);
+            DPF_LAUNCHED();
+        };
         if (use_u8) {
-            // thresholds, and the survivor lists' bases and counters
-            h->surv_id.reserve((size_t)std::max<int64_t>(entries_ub, 1));
-            // pool: every entry can survive (tau = -inf), a block switch leaves < 32 slots unused, every warp ends on a
-            // partial block
-            h->surv_pool.reserve((size_t)(entries_ub + entries_ub / 8 + (int64_t)h->num_sms * 64 * SURV_BLOCK + SURV_BLOCK) * sizeof(SurvRec));
-            DPF_CUDA(cudaMemsetAsync(h->counters.p + 42, 0, sizeof(uint32_t), st));
-            h->bm_tau.reserve((size_t)qk.nq);
-            h->bm_scnt.reserve((size_t)qk.nq);
-            h->bm_sbase.reserve((size_t)qk.nq);
-            // sampled tables per query (one warp each): 6 on one GPU; a rank of G sees 1/G of every query's buckets, so
-            // its lists stay short with fewer samples
-            const int nt_default = c.world <= 1 ? 6 : std::max(2, 6 / c.world);
-            const int NT = std::min(32, std::max(1, h->dbg[DPF_DBG_TAU_TABLES] > 0 ? (int)h->dbg[DPF_DBG_TAU_TABLES] : nt_default));
-            const bool intq = h->Q8_valid;
-            h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
-            h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
-            h->bm_tl_cnt.reserve((size_t)nqc * NT);
-            // The threshold kernels (row gather) run on the handle's second stream next to the pair sort and the run /
-            // unit bookkeeping (a chain of small latency-bound kernels) on the main one; the scoring kernel waits for both.
-            cudaStream_t st2 = h->aux_stream;
-            DPF_CUDA(cudaEventRecord(h->ev_fork, st));
-            DPF_CUDA(cudaStreamWaitEvent(st2, h->ev_fork, 0));
-            auto go = [&](auto kern) {
-                kern<<<(unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS), RR_THREADS, list_smem, st2>>>(
-                    rows, row_bytes, d, Qd, h->Q8.p, u8_query_pitch(), h->qnorm8.p, q0, nqc, L, NT, h->pair_base.p, h->pair_key.p,
-                    h->pair_len.p, h->ids_sorted.p, qk.qids, h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p,
-                    h->bm_tl_cnt.p);
-            };
-            if (intq && (l2 || h->dbg[DPF_DBG_TAU_KERNEL] != 1)) launch_threshold_u8i(h, st2, metric, q0, nqc, NT, qk.qids, topk, list_smem);   // =dp4a: the CUDA-core form
-            else if (ang) { if (intq) go(k_threshold<true, DPF_STORE_KIND_U8, true>); else go(k_threshold<true, DPF_STORE_KIND_U8, false>); }
-            else { if (intq) go(k_threshold<false, DPF_STORE_KIND_U8, true>); else go(k_threshold<false, DPF_STORE_KIND_U8, false>); }
-            DPF_LAUNCHED();
-            k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(q0, nqc, L, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p,
-                                                             h->pair_base.p, h->pair_seg.p, h->bm_tau.p, h->bm_scnt.p, h->bm_sbase.p);
-            DPF_LAUNCHED();
-            DPF_CUDA(cudaGetLastError());
-            DPF_CUDA(cudaEventRecord(h->ev_join, st2));
+            // byte rows: the integer form when the whole batch is bytes, the FP64 form otherwise; which one applies is a
+            // flag on the device, so both are launched and one of them returns at once
+            const bool try_int = h->dbg[DPF_DBG_U8_IMMA] != 0 && (int64_t)d * 255 * 255 < (1LL << 31);
+            if (try_int) {
+                if (h->dbg[DPF_DBG_TAU_KERNEL] != 1 || l2) launch_threshold_u8i(h, st2, metric, cv, NT, topk, list_smem);
+                else if (ang) go(k_threshold<true, DPF_STORE_KIND_U8, true>, 1);
+                else go(k_threshold<false, DPF_STORE_KIND_U8, true>, 1);
+            }
+            if (!l2) {
+                if (ang) go(k_threshold<true, DPF_STORE_KIND_U8, false>, try_int ? 2 : 0);
+                else go(k_threshold<false, DPF_STORE_KIND_U8, false>, try_int ? 2 : 0);
+            }
+        } else {
+            dispatch_kind(kind, ang, [&](auto a, auto kc) { go(k_threshold<decltype(a)::value, decltype(kc)::value, false>, 0); });
         }
-        // sort a copy of the keys by bucket start (bits 32..); the unsorted array stays for the selection pass
-        DPF_CUDA(cudaMemcpyAsync(h->pair_key_alt.p, h->pair_key.p, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-        int ebits = 1;
-        while ((1LL << ebits) < h->h_table_base[L]) ebits++;
-        h->sk64a.reserve(npairs);
-        unsigned long long *a = h->pair_key_alt.p, *b = h->sk64a.p;
-        radix_sort_keys_u64(h, &a, &b, npairs, 32, 32 + ebits);
-        h->bm_sorted = a;
-        h->bm_npairs = npairs;
-        build_units(h, npairs);
+        k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(nqc, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p, h->bm_tau.p,
+                                                         s_dirty); DPF_LAUNCHED();
+        DPF_CUDA(cudaGetLastError());
+        DPF_CUDA(cudaEventRecord(h->ev_join, st2));
     }
-    unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(h->counters.p + 26);   // cleared by probe_count_all
-    const Filter flt{h->bm_tau.p, h->bm_scnt.p, h->bm_sbase.p, h->scores.p, h->surv_id.p, reinterpret_cast<SurvRec*>(h->surv_pool.p),
-                     reinterpret_cast<uint32_t*>(h->counters.p + 42)};
+    emit_units(h);
+
+    unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(ctr + CTR_BM_STAT);
+    const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
+    const uint32_t* nunits_p = reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS);
     {
         StageTimer tm(h, DPF_T_RERANK);
-        h->stats[DPF_STAT_BM_PAIRS] += h->bm_npairs;
-        const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
+        DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));        // thresholds from the second stream
         if (use_u8) {
-            DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));    // thresholds from the second stream
-            launch_score_u8(h, Qd, units, h->bm_counts.p + 1, metric, flt, bm_stat);
+            launch_score_u8(h, cv, units, nunits_p, metric, flt, bm_stat);
         } else {
             dispatch_kind(kind, ang, [&](auto a, auto kc) {
                 auto kern = k_score_stream<decltype(a)::value, decltype(kc)::value>;
                 DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM));
-                kern<<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(rows, row_bytes, d, Qd, units, h->bm_counts.p + 1, h->ids_sorted.p,
-                                                                 h->scores.p, bm_stat);
+                kern<<<h->num_sms, SS_WARPS * 32, SS_SMEM, st>>>(rows, row_bytes, d, cv.Q, units, nunits_p, h->ids_sorted.p, flt, bm_stat);
+                DPF_LAUNCHED();
             });
         }
-        DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
     }
     {
         StageTimer tm(h, DPF_T_SELECT);
-        if (use_u8) {
-            k_scatter_survivors<<<h->num_sms * 8, 256, 0, st>>>(flt, h->ids_sorted.p); DPF_LAUNCHED();
-        }
-        if (use_u8) {
-            h->bm_big.reserve((size_t)nqc + 1);                  // [0] = count, then the queries with long lists
-            DPF_CUDA(cudaMemsetAsync(h->bm_big.p, 0, sizeof(uint32_t), st));
-            k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(q0, nqc, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, l2, ids_out,
-                                                                     score_out, bm_stat, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
-            k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
-                q0, flt, qk.qids, h->cfg.self_exclude_small_ids, topk, l2, ids_out, score_out, h->bm_big.p + 1, h->bm_big.p);
-        }
-        else
-            k_select_pairs<<<(unsigned)nqc, RR_THREADS, list_smem, st>>>(q0, L, h->pair_base.p, h->pair_key.p, h->pair_len.p,
-                                                                         h->pair_seg.p, h->ids_sorted.p, h->scores.p, qk.qids,
-                                                                         h->cfg.self_exclude_small_ids, topk, ids_out, score_out);
-        DPF_LAUNCHED();
+        survivor_lists(h, flt, nqc);
+        h->bm_big.reserve((size_t)nqc + 1);                      // [0] = count, then the queries with long lists
+        DPF_CUDA(cudaMemsetAsync(h->bm_big.p, 0, sizeof(uint32_t), st));
+        int32_t* io = ids_out + q0 * topk;
+        double* so = score_out + q0 * topk;
+        k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(0, nqc, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so,
+                                                                 bm_stat, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
+        k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
+            0, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
+        topk_direct(h, cv, s_dirty, topk, metric, io, so);
         DPF_CUDA(cudaGetLastError());
     }
 }

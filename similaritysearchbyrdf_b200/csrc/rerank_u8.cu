@@ -82,8 +82,10 @@ __device__ __forceinline__ uint4 ldg_u4(const unsigned char* p) { return __ldg(r
 template <bool ANGULAR>
 __global__ void __launch_bounds__(U8_WARPS * 32, 1)
 k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: multiple of 16, <= 128 */, int d,
-            const double* __restrict__ Q, const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p,
-            const int32_t* __restrict__ ids_sorted, Filter flt, unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
+            const double* __restrict__ Q, const int* __restrict__ q8_bad, int gate, const UnitRec* __restrict__ units,
+            const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, Filter flt,
+            unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
+    if (gate && *q8_bad == 0) return;            // the batch is byte vectors: the integer kernel scores it
     constexpr int TR = 8;                        // rows per tile = DMMA M
     constexpr int TPW = 32 / TR;                 // tiles per id window
     constexpr int PF = 3;                        // tiles in flight per warp
@@ -265,8 +267,10 @@ k_score_u8d(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
 template <bool ANGULAR>
 __global__ void __launch_bounds__(U8_WARPS * 32, ANGULAR ? U8_INT_CTAS - 1 : U8_INT_CTAS)
 k_score_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
-            const double* __restrict__ qnorm, const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p,
-            const int32_t* __restrict__ ids_sorted, Filter flt, unsigned long long* __restrict__ stat) {
+            const double* __restrict__ qnorm, const int* __restrict__ q8_bad, const UnitRec* __restrict__ units,
+            const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, Filter flt,
+            unsigned long long* __restrict__ stat) {
+    if (*q8_bad != 0) return;                    // some query is not a byte vector: k_score_u8d scores the batch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;
@@ -409,9 +413,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 template <int METRIC>
 __global__ void __launch_bounds__(U8_WARPS * 32, US_CTAS)
 k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
-            const double* __restrict__ qnorm, const int32_t* __restrict__ qsq, const UnitRec* __restrict__ units,
-            const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, Filter flt,
-            unsigned long long* __restrict__ stat) {
+            const double* __restrict__ qnorm, const int32_t* __restrict__ qsq, const int* __restrict__ q8_bad,
+            const UnitRec* __restrict__ units, const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted,
+            Filter flt, unsigned long long* __restrict__ stat) {
+    if (*q8_bad != 0) return;                    // some query is not a byte vector: k_score_u8d scores the batch
     // DOT: key = dot.  ANGULAR: key = dot / (|q| |x|).  L2: key = -|q - x|^2 = 2 dot - |x|^2 - |q|^2, an exact integer.
     constexpr bool ANGULAR = METRIC == DPF_METRIC_ANGULAR, L2 = METRIC == DPF_METRIC_L2;
     extern __shared__ __align__(16) unsigned char us_smem[];
@@ -635,12 +640,17 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
 // ---------------------------------------------------------------------------------------------------------
 template <int METRIC>
 __global__ void __launch_bounds__(RR_THREADS)
-k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned char* __restrict__ Q8,
-                const double* __restrict__ qnorm, const int32_t* __restrict__ qsq, int64_t q0, int64_t nqc, int L, int NT, const uint32_t* __restrict__ pair_base,
-                const unsigned long long* __restrict__ pair_key_unsorted, const uint32_t* __restrict__ pair_len,
-                const int32_t* __restrict__ ids_sorted, const int32_t* __restrict__ qids, int self_exclude, int K,
+k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView cv, int L, int NT,
+                const uint32_t* __restrict__ leaf_pos, const int32_t* __restrict__ leaf_len,
+                const int32_t* __restrict__ ids_sorted, int self_exclude, int K,
                 double* __restrict__ tl_keys, int* __restrict__ tl_ids, int* __restrict__ tl_cnt) {
     constexpr bool ANGULAR = METRIC == DPF_METRIC_ANGULAR, L2 = METRIC == DPF_METRIC_L2;
+    if (*cv.q8_bad != 0) return;                 // some query is not a byte vector: k_threshold<.., false> samples the batch
+    const unsigned char* __restrict__ Q8 = cv.Q8;
+    const double* __restrict__ qnorm = cv.qnorm8;
+    const int32_t* __restrict__ qsq = cv.qsq8;
+    const int32_t* __restrict__ qids = cv.qids;
+    const int64_t nqc = cv.nqc;
     extern __shared__ double rsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -650,7 +660,7 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
     if (wid >= nqc * NT) return;
     const int64_t ql = wid / NT;
     const int sample = (int)(wid % NT);
-    const int64_t q = q0 + ql;
+    const int64_t q = ql;
     const int qid = qids ? qids[q] : INT32_MIN;
     const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
     const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;
@@ -666,16 +676,14 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
     const double qn = ANGULAR ? __ldg(qnorm + q) : 1.0;
     const int qq = L2 ? __ldg(qsq + q) : 0;
     // the sample-th table (among the first 32) in which the query probes something
-    const uint32_t p_mine = lane < L ? pair_base[ql * L + lane] : 0u;
-    const uint32_t p_next = lane < L ? pair_base[ql * L + lane + 1] : 0u;
-    uint32_t nonempty = __ballot_sync(0xffffffffu, lane < L && p_next > p_mine);
+    uint32_t nonempty = __ballot_sync(0xffffffffu, lane < L && cv.pair_cnt[ql * L + min(lane, L - 1)] > 0u);
     for (int i = 0; i < sample && nonempty; ++i) nonempty &= nonempty - 1;
     int count = 0;
     double kth = 0.0;
     if (nonempty) {
-        const uint32_t p = __shfl_sync(0xffffffffu, p_mine, __ffs(nonempty) - 1);
-        const uint32_t bstart = (uint32_t)(pair_key_unsorted[p] >> 32);
-        const int len = (int)pair_len[p];
+        const uint32_t leaf = cv.cache[(ql * L + (__ffs(nonempty) - 1)) * cv.cap];   // the first bucket the query probes there
+        const uint32_t bstart = leaf_pos[leaf];
+        const int len = leaf_len[leaf];
         const int32_t* bids = ids_sorted + bstart;
         int idA = __ldg(bids + min(lane, len - 1));
         for (int row0 = 0; row0 < len; row0 += 32) {                 // one id window = 2 tiles of 16 rows
@@ -752,13 +760,13 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, const unsi
     if (lane == 0) tl_cnt[wid] = count;
 }
 
-void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
-                          size_t list_smem) {
-    const unsigned grid = (unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS);
+void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, const ChunkView& cv, int NT, int topk, size_t list_smem) {
+    const unsigned grid = (unsigned)((cv.nqc * NT + RR_WARPS - 1) / RR_WARPS);
     auto go = [&](auto kern) {
-        kern<<<grid, RR_THREADS, list_smem, st>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, h->Q8.p, h->qnorm8.p, h->qsq8.p, q0, nqc, h->cfg.L, NT,
-                                                         h->pair_base.p, h->pair_key.p, h->pair_len.p, h->ids_sorted.p, qids,
-                                                         h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p);
+        kern<<<grid, RR_THREADS, list_smem, st>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, cv, h->cfg.L, NT, h->leaf_pos.p, h->leaf_len.p,
+                                                  h->ids_sorted.p, h->cfg.self_exclude_small_ids, topk, h->bm_tl_keys.p,
+                                                  h->bm_tl_ids.p, h->bm_tl_cnt.p);
+        DPF_LAUNCHED();
     };
     if (metric == DPF_METRIC_ANGULAR) go(k_threshold_u8i<DPF_METRIC_ANGULAR>);
     else if (metric == DPF_METRIC_L2) go(k_threshold_u8i<DPF_METRIC_L2>);
@@ -775,50 +783,60 @@ bool score_u8_usable(const dpf_index* h) {
     return h->Xc_kind == DPF_STORE_KIND_U8 && h->Xc_row_bytes <= 128;
 }
 
-void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq) {
+// byte copy of the batch's queries + the device flag "some value is not a byte" (CTR_Q8_BAD).  The flag stays on the
+// device: the kernels of both forms are launched and read it.  Only squared L2 needs it on the host (`need_host_flag`),
+// because there the alternative to the integer pipeline is a different path altogether (row-major).
+void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq, bool need_host_flag) {
     h->Q8_valid = false;
     if (h->dbg[DPF_DBG_U8_IMMA] == 0) return;                 // test hook: always multiply on the FP64 tensor pipe
+    if ((int64_t)h->cfg.d * 255 * 255 >= (1LL << 31)) return;  // integer dot products must stay below 2^31
     cudaStream_t st = h->stream;
     const int pitch = U8_QPITCH;
     h->Q8.reserve((size_t)nq * pitch);
     h->qnorm8.reserve((size_t)nq);
     h->qsq8.reserve((size_t)nq);
-    int* flag = h->counters.p + 41;
-    DPF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    int* flag = h->counters.p + CTR_Q8_BAD;
     k_quantise_queries<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(Qd, nq, h->cfg.d, pitch, h->Q8.p, h->qnorm8.p, h->qsq8.p, flag); DPF_LAUNCHED();
+    DPF_CUDA(cudaGetLastError());
+    if (!need_host_flag) return;
     int f = 1;
     DPF_CUDA(cudaMemcpyAsync(&f, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     DPF_CUDA(cudaStreamSynchronize(st));
-    // integer dot products must stay below 2^31: d * 255 * 255
-    h->Q8_valid = f == 0 && (int64_t)h->cfg.d * 255 * 255 < (1LL << 31);
+    h->Q8_valid = f == 0;
 }
 
-void launch_score_u8(dpf_index* h, const double* Qd, const void* units_v, const uint32_t* nunits_p, int metric,
+void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units_v, const uint32_t* nunits_p, int metric,
                      const Filter& flt, unsigned long long* bm_stat) {
     const bool angular = metric == DPF_METRIC_ANGULAR;
     const UnitRec* units = reinterpret_cast<const UnitRec*>(units_v);
     const unsigned pitch = (unsigned)h->Xc_row_bytes;
     cudaStream_t st = h->stream;
-    if (h->Q8_valid) {
-        auto launch = [&](auto kern) {
-            kern<<<h->num_sms * (angular ? U8_INT_CTAS - 1 : U8_INT_CTAS), U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, units, nunits_p,
-                                                                   h->ids_sorted.p, flt, bm_stat);
-        };
-        if (h->dbg[DPF_DBG_U8I_KERNEL] == 1 && metric != DPF_METRIC_L2) {       // =lean: the occupancy-based variant (dot / angular)
+    const bool try_int = h->dbg[DPF_DBG_U8_IMMA] != 0 && (int64_t)h->cfg.d * 255 * 255 < (1LL << 31);
+    if (try_int) {                                                // runs when the batch is byte vectors (device flag)
+        if (h->dbg[DPF_DBG_U8I_KERNEL] == 1 && metric != DPF_METRIC_L2) {       // test hook: the occupancy-based variant
+            auto launch = [&](auto kern) {
+                kern<<<h->num_sms * (angular ? U8_INT_CTAS - 1 : U8_INT_CTAS), U8_WARPS * 32, 0, st>>>(
+                    h->Xc.p, pitch, cv.Q8, cv.qnorm8, cv.q8_bad, units, nunits_p, h->ids_sorted.p, flt, bm_stat);
+                DPF_LAUNCHED();
+            };
             if (angular) launch(k_score_u8i<true>); else launch(k_score_u8i<false>);
         } else {
             auto launch_s = [&](auto kern) {
                 DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US_SMEM));
-                kern<<<h->num_sms * US_CTAS, U8_WARPS * 32, US_SMEM, st>>>(h->Xc.p, pitch, h->Q8.p, h->qnorm8.p, h->qsq8.p, units, nunits_p,
-                                                                         h->ids_sorted.p, flt, bm_stat);
+                kern<<<h->num_sms * US_CTAS, U8_WARPS * 32, US_SMEM, st>>>(h->Xc.p, pitch, cv.Q8, cv.qnorm8, cv.qsq8, cv.q8_bad, units,
+                                                                         nunits_p, h->ids_sorted.p, flt, bm_stat);
+                DPF_LAUNCHED();
             };
             if (angular) launch_s(k_score_u8s<DPF_METRIC_ANGULAR>);
             else if (metric == DPF_METRIC_L2) launch_s(k_score_u8s<DPF_METRIC_L2>);
             else launch_s(k_score_u8s<DPF_METRIC_DOT>);
         }
-    } else {
+    }
+    if (metric != DPF_METRIC_L2) {                                // runs when some query is not a byte vector
         auto launch = [&](auto kern) {
-            kern<<<h->num_sms, U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->cfg.d, Qd, units, nunits_p, h->ids_sorted.p, flt, bm_stat);
+            kern<<<h->num_sms, U8_WARPS * 32, 0, st>>>(h->Xc.p, pitch, h->cfg.d, cv.Q, cv.q8_bad, try_int ? 1 : 0, units, nunits_p,
+                                                       h->ids_sorted.p, flt, bm_stat);
+            DPF_LAUNCHED();
         };
         if (angular) launch(k_score_u8d<true>); else launch(k_score_u8d<false>);
     }

@@ -17,7 +17,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 
 // ---------------------------------------------------------------------------------------------------------
-// units: runs of sorted pairs that share a bucket, cut into pieces of <= SS_UQ queries
+// units: the (bucket, query) pairs of a batch grouped by bucket (counting sort over the leaf numbers, bm_group.cu),
+// every bucket's list cut into pieces of <= SS_UQ queries
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SS_UQ = 16;              // queries per unit = 2 DMMA n-blocks held in registers
 constexpr int SS_WARPS = 8;            // warps per CTA, one CTA per SM
@@ -32,10 +33,9 @@ constexpr int SS_WIN_COPY = SS_WIN + 4;   // ids copied per window: the copy sta
 struct __align__(16) UnitRec {
     uint32_t bstart;       // bucket start in ids_sorted
     uint32_t len;          // bucket length (rows)
-    uint32_t pos0;         // position of the unit's first pair in the sorted pair list
+    uint32_t pos0;         // position of the unit's first pair in the grouped pair list
     uint32_t m;            // queries in the unit (1..SS_UQ)
-    int32_t q[SS_UQ];      // query index of pair j
-    uint32_t seg[SS_UQ];   // start of pair j's score segment (dense output: k_score_stream)
+    int32_t q[SS_UQ];      // query (index inside the chunk) of pair j; slots >= m repeat the last query
     int32_t ids0[SS_WIN];  // ids of the bucket's first 32 rows (the other windows are copied from ids_sorted)
 };
 static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -47,19 +47,27 @@ static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes
 // rounding allowance, as tau[q] — k distinct rows score >= tau, hence no row below tau can be in the result.  The
 // kernels emit (query, row, score) of the rows with score >= tau (a few hundred per query, SurvivorSink);
 // k_scatter_survivors sorts them into per-query lists and k_select_survivors finishes.  The result is exactly the top k of all candidates.
+// Nothing here is sized by a number the host would have to read back: the pool has a fixed capacity, the per-query lists
+// are laid out from the counts the scoring kernel leaves behind, and a query whose survivors did not fit (or whose
+// samples held fewer than k rows: tau = +inf, nothing survives) is flagged `dirty` and answered by k_topk_direct, which
+// walks the query's own buckets and needs no scratch — so a batch runs without a single host synchronisation.
 struct __align__(16) SurvRec {
     int32_t q;             // query, or -1 for an unused slot
     uint32_t pos;          // position of the row in ids_sorted
     double score;
 };
 struct Filter {
-    const double* tau;     // per query: score threshold (k_threshold*)
-    uint32_t* cnt;         // per query: survivors in its list so far
-    const uint32_t* base;  // per query: start of its survivor list (capacity = all its bucket entries)
+    const double* tau;     // per query: score threshold (k_threshold*); +inf for a dirty query
+    uint32_t* cnt;         // per query: survivors stored in the pool
+    uint32_t* base;        // per query: start of its survivor list = exclusive scan of cnt (k_survivor_offsets)
+    uint32_t* fill;        // per query: list entries written so far (k_scatter_survivors)
+    uint32_t* dirty;       // per query: != 0 -> answered by k_topk_direct
     double* s_score;
     int32_t* s_id;
     SurvRec* pool;         // survivors in the order the scoring warps found them, blocks of SURV_BLOCK per warp
     uint32_t* pool_cursor;
+    uint32_t pool_cap;     // records, a multiple of SURV_BLOCK
+    int* overflow;         // set when a warp could not get a block
 };
 constexpr int SURV_BLOCK = 256;
 
@@ -71,26 +79,38 @@ constexpr int SURV_BLOCK = 256;
 struct SurvivorSink {
     uint32_t wpos = 0;
     int wleft = 0;
+    bool full = false;                                     // the pool ran out: everything further marks its query dirty
     __device__ __forceinline__ void push(const Filter& f, bool keep, int q, uint32_t pos, double score, int lane) {
         const uint32_t mask = __ballot_sync(0xffffffffu, keep);
         if (!mask) return;
         const int n = __popc(mask);
-        if (n > wleft) {                                   // open a new block; the rest of the old one stays unused
+        if (n > wleft && !full) {                          // open a new block; the rest of the old one stays unused
             if (lane < wleft) f.pool[wpos + lane].q = -1;
             uint32_t b = 0;
             if (lane == 0) b = atomicAdd(f.pool_cursor, (uint32_t)SURV_BLOCK);
             wpos = __shfl_sync(0xffffffffu, b, 0);
             wleft = SURV_BLOCK;
+            if (wpos > f.pool_cap - (uint32_t)SURV_BLOCK) {
+                full = true;
+                wleft = 0;
+                if (lane == 0) *f.overflow = 1;
+            }
+        }
+        if (full) {
+            if (keep) f.dirty[q] = 1u;
+            return;
         }
         if (keep) {
             SurvRec r;
             r.q = q; r.pos = pos; r.score = score;
             f.pool[wpos + __popc(mask & ((1u << lane) - 1u))] = r;
+            atomicAdd(f.cnt + q, 1u);
         }
         wpos += n;
         wleft -= n;
     }
     __device__ __forceinline__ void flush(const Filter& f, int lane) {
+        if (full) return;
         for (int i = lane; i < wleft; i += 32) f.pool[wpos + i].q = -1;
     }
 };
@@ -100,10 +120,32 @@ constexpr size_t SS_SMEM = SS_WARPS * ((SS_WARP_BYTES + 15) / 16 * 16);
 
 
 // rerank_u8.cu: scores of every unit from the uint8 compact store (register gather, DMMA or IMMA)
-void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, int64_t q0, int64_t nqc, int NT, const int32_t* qids, int topk,
-                          size_t list_smem);                          // threshold samples on the integer tensor pipe
+// one chunk of a query batch as the bucket-major kernels see it: every per-query array starts at the chunk's first query
+struct ChunkView {
+    const double* Q;             // nqc x d
+    const unsigned char* Q8;     // byte copy of the queries (valid when *q8_bad == 0)
+    const double* qnorm8;
+    const int32_t* qsq8;
+    const int32_t* qids;         // may be null
+    int64_t nqc;
+    const int* q8_bad;           // device flag: some query of the BATCH is not a byte vector
+    // probe result: distinct leaves per (query, table)
+    const uint32_t* pair_cnt;    // nqc x L
+    const uint32_t* cache;       // nqc x L x cap leaf numbers
+    int cap;
+};
+
+// rerank_u8.cu: scores of every unit from the uint8 compact store (register gather, DMMA or IMMA)
+void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, const ChunkView& cv, int NT, int topk, size_t list_smem);
 int u8_query_pitch();                                                      // row pitch of dpf_index::Q8
-void launch_score_u8(dpf_index* h, const double* Qd, const void* units, const uint32_t* nunits_p, int metric,
+void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units, const uint32_t* nunits_p, int metric,
                      const Filter& flt, unsigned long long* bm_stat);
+// bm_group.cu: probe -> pairs grouped by leaf -> unit records, all sized on the host without reading anything back
+void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap);
+void emit_units(dpf_index* h);
+void survivor_lists(dpf_index* h, const Filter& flt, int64_t nqc);         // offsets + scatter
+int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);
+// query.cu: exhaustive per-query top-k over the query's own buckets for the queries flagged dirty
+void topk_direct(dpf_index* h, const ChunkView& cv, const uint32_t* dirty, int topk, int metric, int32_t* ids_out, double* score_out);
 
 }  // namespace dpf
