@@ -935,6 +935,18 @@ int dpf_dump_buckets(dpf_handle h, int32_t table, int64_t* nbuckets_out, int64_t
     });
 }
 
+int dpf_debug_leaf_pairs(dpf_handle h, int64_t* nleaves_out, uint32_t* pair_off_out, int32_t* leaf_len_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nleaves_out, DPF_ERR_INVALID, "null buffer");
+        *nleaves_out = h->num_leaves;
+        if (!h->leaf_table || h->num_leaves == 0) return;
+        if (pair_off_out) d2h(h, pair_off_out, h->leaf_off.p, (size_t)h->num_leaves + 1);
+        if (leaf_len_out) d2h(h, leaf_len_out, h->leaf_len.p, (size_t)h->num_leaves);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
 int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
     return guarded(h, [&] {
         DPF_REQUIRE(stats_out, DPF_ERR_INVALID, "null buffer");

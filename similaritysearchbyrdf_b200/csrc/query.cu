@@ -669,7 +669,7 @@ k_merge_topk(const int32_t* __restrict__ gids, const double* __restrict__ gsc, i
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
     // lane g < G walks list g (each list is already in result order)
-    int head = 0, last = -1;
+    int head = 0;
     for (int r = 0; r < K; ++r) {
         double bk;
         int bi, bl;
@@ -694,18 +694,23 @@ k_merge_topk(const int32_t* __restrict__ gids, const double* __restrict__ gsc, i
             }
             if (bl < 0) break;
             if (lane == bl) head++;
-            if (bi != last) break;                     // duplicate of the id just emitted: skip it
+            // the same id from two GPUs: emitted once.  Its two scores are the same dot product, but not necessarily from
+            // the same kernel (one GPU may have answered the query exhaustively, the other through the filter), so they can
+            // differ in the last bits and need not be neighbours in the merged order: look the id up in what was emitted
+            bool dup = false;
+            for (int j = lane; j < r; j += 32) dup |= ids_out[q * K + j] == bi;
+            if (!__any_sync(0xffffffffu, dup)) break;
         }
         if (lane == 0) {
             ids_out[q * K + r] = bl >= 0 ? bi : -1;
             score_out[q * K + r] = bl >= 0 ? (metric == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
         }
+        __syncwarp();
         if (bl < 0) {
             for (int r2 = r + 1; r2 < K; ++r2)
                 if (lane == 0) { ids_out[q * K + r2] = -1; score_out[q * K + r2] = __longlong_as_double(0x7ff8000000000000LL); }
             break;
         }
-        last = bi;
     }
 }
 

@@ -245,6 +245,15 @@ class DPFIndex:
         self._ck(self.lib.dpf_dump_buckets(self.h, table, C.byref(nb), C.byref(nid), _p(desc), _p(off), _p(ids)))
         return desc[:nb.value], off, ids[:nid.value]
 
+    def leaf_pairs(self):
+        """(pair_off[nleaves + 1], leaf_len[nleaves]) of the last bucket-major query chunk (dpf_debug_leaf_pairs)."""
+        n = C.c_int64(0)
+        self._ck(self.lib.dpf_debug_leaf_pairs(self.h, C.byref(n), None, None))
+        off = np.zeros(n.value + 1, np.uint32)
+        ln = np.zeros(max(n.value, 1), np.int32)
+        self._ck(self.lib.dpf_debug_leaf_pairs(self.h, C.byref(n), _p(off), _p(ln)))
+        return off, ln[:n.value]
+
     def stats(self):
         s = np.zeros(B.STAT_COUNT, np.int64)
         occ = np.zeros(1 << self.pb, np.float64)

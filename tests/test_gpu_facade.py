@@ -113,8 +113,9 @@ def test_two_rank_emulation_on_one_gpu():
         shards[0].merge_topk_dev(g_ids.data_ptr(), g_sc.data_ptr(), 2, nq, K, metric, m_ids.data_ptr(), m_sc.data_ptr())
         shards[0].sync()
         torch.cuda.synchronize()
-        assert np.array_equal(m_ids.cpu().numpy(), f_ids)
-        assert np.array_equal(m_sc.cpu().numpy(), f_sc, equal_nan=True)
+        # (real-valued data: a query may be answered by different kernels on a shard and on the full index — the filter
+        # or the exhaustive per-query kernel — so scores agree to the north-star tolerance, not bit for bit)
+        U.assert_topk_close(f_ids, f_sc, m_ids.cpu().numpy(), m_sc.cpu().numpy())
         # each shard equals the oracle restricted to the same sub-indexes
         for r, s in enumerate(shards):
             o = U.make_oracle(100, A, chain, Ap, bucket_overflow=40, rank=r, world=2)
@@ -222,8 +223,7 @@ def test_balanced_partition_ranks_merge_to_the_unsharded_result(world):
         shards[0].merge_topk_dev(g_ids.data_ptr(), g_sc.data_ptr(), world, nq, K, B.METRIC_DOT, m_ids.data_ptr(), m_sc.data_ptr())
         shards[0].sync()
         torch.cuda.synchronize()
-        assert np.array_equal(m_ids.cpu().numpy(), f_ids)
-        assert np.array_equal(m_sc.cpu().numpy(), f_sc, equal_nan=True)
+        U.assert_topk_close(f_ids, f_sc, m_ids.cpu().numpy(), m_sc.cpu().numpy())
         for i in range(nq):                                              # union of the ranks' candidate sets
             u = np.unique(np.concatenate([c[1][c[0][i]:c[0][i + 1]] for c in cands]))
             assert np.array_equal(u, f_cand[f_off[i]:f_off[i + 1]])

@@ -35,3 +35,14 @@ for _ in range(a.repeat + 1):
     print("query stage ms:", {k: round(v, 3) for k, v in ix.stage_times_ms().items() if v},
           "cand/q", st["last_candidates"] / a.nq, "dups/q", st["last_cand_with_dups"] / a.nq,
           "bm pairs", st["bm_pairs"], "runs", st["bm_runs"], "rows staged", st["bm_rows_staged"], "survivors/q", st["bm_survivors"] / a.nq)
+
+# how many bucket rows a batch stages as a function of the unit width (queries scored per pass over a bucket)
+off, ln = ix.leaf_pairs()
+cnt = np.diff(off.astype(np.int64))
+print("leaves", len(ln), "probed", int((cnt > 0).sum()), "pairs", int(cnt.sum()), "pairs/probed leaf mean", cnt[cnt > 0].mean(),
+      "p50/p90/p99/max", np.percentile(cnt[cnt > 0], [50, 90, 99]).tolist(), int(cnt.max()))
+for uq in (8, 16, 32, 64, 128, 256):
+    units = -(-cnt // uq)
+    rows = int((units * ln).sum())
+    rows128 = int((units * (-(-ln // 128)) * 128).sum())
+    print(f"unit width {uq:4d}: units {int(units.sum()):9d} rows staged {rows:11d} (padded to 128-row tiles {rows128:11d})")
