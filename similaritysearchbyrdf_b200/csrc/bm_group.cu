@@ -78,9 +78,10 @@ constexpr int LS_THREADS = 256, LS_ITEMS = 16, LS_TILE = LS_THREADS * LS_ITEMS;
 constexpr unsigned long long LS_VALUE_MASK = (1ULL << 62) - 1ULL;
 
 __global__ void __launch_bounds__(LS_THREADS)
-k_scan_leaves(const uint32_t* __restrict__ leaf_cnt, int64_t nleaves, uint32_t* __restrict__ leaf_off, uint32_t* __restrict__ unit_off,
+k_scan_leaves(const uint32_t* __restrict__ leaf_cnt, int64_t nleaves, uint32_t uq /* queries per unit */,
+              uint32_t* __restrict__ leaf_off, uint32_t* __restrict__ unit_off,
               unsigned int* __restrict__ tile_counter, volatile unsigned long long* __restrict__ status,
-              uint32_t* __restrict__ totals /* [0] pairs, [1] units */, unsigned long long* __restrict__ pairs_total) {
+              uint32_t* __restrict__ totals /* [0] pairs, [1] units */, unsigned long long* __restrict__ pairs_total /* or null */) {
     __shared__ unsigned long long wsum[LS_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ uint32_t s_tile;
@@ -92,7 +93,7 @@ k_scan_leaves(const uint32_t* __restrict__ leaf_cnt, int64_t nleaves, uint32_t* 
 #pragma unroll
     for (int i = 0; i < LS_ITEMS; ++i) {
         const uint32_t c = base + i < nleaves ? leaf_cnt[base + i] : 0u;
-        v[i] = (unsigned long long)c | ((unsigned long long)((c + SS_UQ - 1) / SS_UQ) << 32);
+        v[i] = (unsigned long long)c | ((unsigned long long)((c + uq - 1) / uq) << 32);
         s += v[i];
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -143,7 +144,7 @@ k_scan_leaves(const uint32_t* __restrict__ leaf_cnt, int64_t nleaves, uint32_t* 
                 totals[1] = (uint32_t)(all >> 32);
                 leaf_off[nleaves] = (uint32_t)all;
                 unit_off[nleaves] = (uint32_t)(all >> 32);
-                atomicAdd(pairs_total, all & 0xffffffffULL);
+                if (pairs_total) atomicAdd(pairs_total, all & 0xffffffffULL);
             }
         }
     }
@@ -174,11 +175,26 @@ k_fill_pairs(const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__
     }
 }
 
-// warp per leaf: one record per SS_UQ pairs of its list
+// thread per leaf: one 16-byte descriptor per TC_TQ pairs of its list (the tcgen05 kernel's units)
+__global__ void __launch_bounds__(256)
+k_emit_unit_descs(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict__ unit_off, const uint32_t* __restrict__ leaf_pos,
+                  const int32_t* __restrict__ leaf_len, int64_t nleaves, UnitDesc* __restrict__ descs) {
+    const int64_t leaf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= nleaves) return;
+    const uint32_t p0 = leaf_off[leaf], p1 = leaf_off[leaf + 1];
+    if (p0 == p1) return;
+    const uint32_t bstart = leaf_pos[leaf], len = (uint32_t)leaf_len[leaf];
+    uint4* out = reinterpret_cast<uint4*>(descs + unit_off[leaf]);
+    for (uint32_t p = p0; p < p1; p += TC_TQ, ++out) *out = make_uint4(bstart, len, p, min((uint32_t)TC_TQ, p1 - p));
+}
+
+// warp per leaf: one record per SS_UQ pairs of its list.  gate != 0: only when some query of the batch is not a byte
+// vector (the records are then what k_score_u8d reads; a batch of byte vectors is scored from the descriptors above)
 __global__ void __launch_bounds__(256)
 k_emit_units(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict__ unit_off, const uint32_t* __restrict__ leaf_pos,
              const int32_t* __restrict__ leaf_len, int64_t nleaves, const int32_t* __restrict__ pair_q,
-             const int32_t* __restrict__ ids_sorted, UnitRec* __restrict__ units) {
+             const int32_t* __restrict__ ids_sorted, UnitRec* __restrict__ units, const int* __restrict__ q8_bad, int gate) {
+    if (gate && *q8_bad == 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t leaf = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (leaf >= nleaves) return;
@@ -270,7 +286,7 @@ int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap
     return std::max<int64_t>(1, kMaxPairs / ((int64_t)h->cfg.L * cap));
 }
 
-void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap) {
+void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc) {
     const ProbeCtx c = make_ctx(h, steps, probe_mode);
     cudaStream_t st = h->stream;
     const int L = c.L;
@@ -281,7 +297,7 @@ void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
     h->probe_cache.reserve((size_t)pairs_ub);
     h->pair_q.reserve((size_t)pairs_ub);
     const int64_t ntiles = (nleaves + LS_TILE - 1) / LS_TILE;
-    h->scan_scratch.reserve((size_t)(2 * ntiles + 8));
+    h->scan_scratch.reserve((size_t)(4 * ntiles + 16));
     int32_t* ctr = h->counters.p;
     {
         StageTimer tm(h, DPF_T_PROBE_COUNT);
@@ -292,13 +308,20 @@ void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
     }
     {
         StageTimer tm(h, DPF_T_EXPAND);
-        DPF_CUDA(cudaMemsetAsync(h->scan_scratch.p, 0, (size_t)(2 * ntiles + 2) * sizeof(uint32_t), st));
-        DPF_CUDA(cudaMemsetAsync(ctr + CTR_SCAN_TILE, 0, sizeof(int32_t), st));
+        DPF_CUDA(cudaMemsetAsync(h->scan_scratch.p, 0, (size_t)(4 * ntiles + 8) * sizeof(uint32_t), st));
+        DPF_CUDA(cudaMemsetAsync(ctr + CTR_NPAIRS_TC, 0, 3 * sizeof(int32_t), st));
         if (ntiles > 0) {
             k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
-                h->leaf_cnt.p, nleaves, h->leaf_off.p, h->leaf_unit_off.p, reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE),
+                h->leaf_cnt.p, nleaves, (uint32_t)SS_UQ, h->leaf_off.p, h->leaf_unit_off.p, reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE),
                 reinterpret_cast<unsigned long long*>(h->scan_scratch.p + 2), reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS),
                 reinterpret_cast<unsigned long long*>(ctr + CTR_BM_PAIRS_TOTAL)); DPF_LAUNCHED();
+        }
+        if (ntiles > 0 && use_tc) {            // the same histogram once more, at the tcgen05 kernel's unit width
+            uint32_t* status2 = h->scan_scratch.p + 2 * ntiles + 4;
+            k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
+                h->leaf_cnt.p, nleaves, (uint32_t)TC_TQ, h->leaf_off.p, h->leaf_unit_off_tc.p,
+                reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE_TC), reinterpret_cast<unsigned long long*>(status2),
+                reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS_TC), nullptr); DPF_LAUNCHED();
         }
         k_fill_pairs<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(h->pair_cnt.p, h->probe_cache.p, cap, warps, h->leaf_cnt.p,
                                                                   h->leaf_off.p, L, h->pair_q.p); DPF_LAUNCHED();
@@ -307,13 +330,25 @@ void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
 }
 
 // unit records of the grouped pairs: at most one partial unit per leaf plus one per SS_UQ pairs
-void emit_units(dpf_index* h) {
+void emit_units(dpf_index* h, bool only_if_fp64_queries) {
     StageTimer tm(h, DPF_T_EXPAND);
     const int64_t nleaves = h->num_leaves;
     if (nleaves > 0) {
         k_emit_units<<<(unsigned)((nleaves + 7) / 8), 256, 0, h->stream>>>(h->leaf_off.p, h->leaf_unit_off.p, h->leaf_pos.p, h->leaf_len.p,
                                                                           nleaves, h->pair_q.p, h->ids_sorted.p,
-                                                                          reinterpret_cast<UnitRec*>(h->bm_units.p)); DPF_LAUNCHED();
+                                                                          reinterpret_cast<UnitRec*>(h->bm_units.p),
+                                                                          h->counters.p + CTR_Q8_BAD, only_if_fp64_queries ? 1 : 0); DPF_LAUNCHED();
+    }
+    DPF_CUDA(cudaGetLastError());
+}
+
+void emit_unit_descs(dpf_index* h) {
+    StageTimer tm(h, DPF_T_EXPAND);
+    const int64_t nleaves = h->num_leaves;
+    if (nleaves > 0) {
+        k_emit_unit_descs<<<(unsigned)((nleaves + 255) / 256), 256, 0, h->stream>>>(h->leaf_off.p, h->leaf_unit_off_tc.p, h->leaf_pos.p,
+                                                                                   h->leaf_len.p, nleaves,
+                                                                                   reinterpret_cast<UnitDesc*>(h->bm_descs.p)); DPF_LAUNCHED();
     }
     DPF_CUDA(cudaGetLastError());
 }

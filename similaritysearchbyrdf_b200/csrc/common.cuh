@@ -121,6 +121,9 @@ enum : int {
     CTR_SCAN_TILE = 46,       // tile cursor of the leaf-count scan
     CTR_POOL_OVERFLOW = 47,   // != 0: the survivor pool was too small for some warp (its queries are answered directly)
     CTR_DIRECT = 48,          // queries answered by k_topk_direct in this batch
+    CTR_NPAIRS_TC = 54,       // the same two totals from the scan at the tcgen05 kernel's unit width
+    CTR_NUNITS_TC = 55,
+    CTR_SCAN_TILE_TC = 56,
     CTR_BM_PAIRS_TOTAL = 50,  // u64: pairs over all chunks of the batch
     CTR_ENTRIES = 52,         // u64: bucket entries visited by the batch (candidates with duplicates)
     CTR_BATCH_FIRST = 16,
@@ -203,6 +206,8 @@ struct dpf_index {
     dpf::DevBuf<int32_t> leaf_len;
     dpf::DevBuf<uint32_t> leaf_cnt;             // per leaf: pairs of the current query chunk (all zero between batches)
     dpf::DevBuf<uint32_t> leaf_off, leaf_unit_off;   //           first pair / first unit
+    dpf::DevBuf<uint32_t> leaf_unit_off_tc;          //           first unit at the tcgen05 kernel's unit width
+    dpf::DevBuf<char> bm_descs;                      // UnitDesc records
     int32_t num_leaves = 0;
     bool leaf_table = false;                    // false when the forest has >= 2^32 entries (row-major re-rank only)
     dpf::DevBuf<int64_t> table_base;

@@ -247,6 +247,7 @@ static void build_leaf_table(dpf_index* h) {
     h->leaf_cnt.reserve((size_t)nl + 1);
     h->leaf_off.reserve((size_t)nl + 2);
     h->leaf_unit_off.reserve((size_t)nl + 2);
+    h->leaf_unit_off_tc.reserve((size_t)nl + 2);
     DPF_CUDA(cudaMemsetAsync(h->leaf_cnt.p, 0, ((size_t)nl + 1) * sizeof(uint32_t), st));
     if (nslots > 0) {
         k_leaf_table<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->child_ptr.p, h->child_cnt.p, h->child_leaf.p, h->node_table.p,

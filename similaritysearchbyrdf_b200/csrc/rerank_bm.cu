@@ -789,6 +789,11 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     const int64_t pairs_ub = nqc * L * cap;
     const int64_t units_ub = std::min<int64_t>(pairs_ub, (int64_t)h->num_leaves + pairs_ub / SS_UQ) + 1;
     h->bm_units.reserve((size_t)units_ub * sizeof(UnitRec));
+    // byte rows x byte queries, dot product: the tcgen05 kernel with its own, wider units
+    const bool try_int = use_u8 && h->dbg[DPF_DBG_U8_IMMA] != 0 && (int64_t)d * 255 * 255 < (1LL << 31);
+    const bool use_tc = try_int && score_u8t_usable(h, metric);
+    if (use_tc)
+        h->bm_descs.reserve((size_t)(std::min<int64_t>(pairs_ub, (int64_t)h->num_leaves + pairs_ub / TC_TQ) + 1) * sizeof(UnitDesc));
     int64_t pool_cap = h->dbg[DPF_DBG_POOL_RECORDS] > 0 ? h->dbg[DPF_DBG_POOL_RECORDS]
                                                         : std::min<int64_t>(std::max<int64_t>(nqc * 2048, 1 << 20), 1LL << 28);
     pool_cap = std::max<int64_t>(SURV_BLOCK, pool_cap / SURV_BLOCK * SURV_BLOCK);
@@ -805,7 +810,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     DPF_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t)nqc * 3 * sizeof(uint32_t), st));
     DPF_CUDA(cudaMemsetAsync(ctr + CTR_POOL, 0, 6 * sizeof(int32_t), st));      // pool cursor, chunk counts, overflow flag
 
-    probe_and_group(h, qk, steps, probe_mode, q0, nqc, cap);
+    probe_and_group(h, qk, steps, probe_mode, q0, nqc, cap, use_tc);
 
     ChunkView cv;
     cv.Q = Qd + q0 * d;
@@ -847,7 +852,6 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         if (use_u8) {
             // byte rows: the integer form when the whole batch is bytes, the FP64 form otherwise; which one applies is a
             // flag on the device, so both are launched and one of them returns at once
-            const bool try_int = h->dbg[DPF_DBG_U8_IMMA] != 0 && (int64_t)d * 255 * 255 < (1LL << 31);
             if (try_int) {
                 if (h->dbg[DPF_DBG_TAU_KERNEL] != 1 || l2) launch_threshold_u8i(h, st2, metric, cv, NT, topk, list_smem);
                 else if (ang) go(k_threshold<true, DPF_STORE_KIND_U8, true>, 1);
@@ -865,7 +869,8 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         DPF_CUDA(cudaGetLastError());
         DPF_CUDA(cudaEventRecord(h->ev_join, st2));
     }
-    emit_units(h);
+    if (use_tc) emit_unit_descs(h);
+    emit_units(h, use_tc);               // with the tcgen05 kernel the records only serve a batch that is not byte vectors
 
     unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(ctr + CTR_BM_STAT);
     const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
@@ -874,7 +879,10 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         StageTimer tm(h, DPF_T_RERANK);
         DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));        // thresholds from the second stream
         if (use_u8) {
-            launch_score_u8(h, cv, units, nunits_p, metric, flt, bm_stat);
+            if (use_tc)
+                launch_score_u8t(h, cv, reinterpret_cast<const UnitDesc*>(h->bm_descs.p),
+                                 reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS_TC), flt, bm_stat);
+            launch_score_u8(h, cv, units, nunits_p, metric, flt, bm_stat, try_int && !use_tc);
         } else {
             dispatch_kind(kind, ang, [&](auto a, auto kc) {
                 auto kern = k_score_stream<decltype(a)::value, decltype(kc)::value>;

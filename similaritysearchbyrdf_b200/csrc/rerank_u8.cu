@@ -805,14 +805,16 @@ void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq, bool need_ho
     h->Q8_valid = f == 0;
 }
 
+// int_kernel: also launch the mma.sync integer kernel (it runs when the batch is byte vectors; false when the tcgen05
+// kernel has that case); the FP64-query kernel is launched for dot / angular and runs when the batch is not bytes
 void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units_v, const uint32_t* nunits_p, int metric,
-                     const Filter& flt, unsigned long long* bm_stat) {
+                     const Filter& flt, unsigned long long* bm_stat, bool int_kernel) {
     const bool angular = metric == DPF_METRIC_ANGULAR;
     const UnitRec* units = reinterpret_cast<const UnitRec*>(units_v);
     const unsigned pitch = (unsigned)h->Xc_row_bytes;
     cudaStream_t st = h->stream;
     const bool try_int = h->dbg[DPF_DBG_U8_IMMA] != 0 && (int64_t)h->cfg.d * 255 * 255 < (1LL << 31);
-    if (try_int) {                                                // runs when the batch is byte vectors (device flag)
+    if (int_kernel) {                                             // runs when the batch is byte vectors (device flag)
         if (h->dbg[DPF_DBG_U8I_KERNEL] == 1 && metric != DPF_METRIC_L2) {       // test hook: the occupancy-based variant
             auto launch = [&](auto kern) {
                 kern<<<h->num_sms * (angular ? U8_INT_CTAS - 1 : U8_INT_CTAS), U8_WARPS * 32, 0, st>>>(

@@ -40,6 +40,16 @@ struct __align__(16) UnitRec {
 };
 static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
+// The tcgen05 kernel (rerank_tc.cu) takes wider units — up to TC_TQ queries of one bucket, the N extent of its MMA —
+// and only a 16-byte descriptor per unit: its producer warps fetch the query list and the row ids themselves.
+constexpr int TC_TQ = 64;
+struct __align__(16) UnitDesc {
+    uint32_t bstart;       // bucket start in ids_sorted
+    uint32_t len;          // bucket length (rows)
+    uint32_t pair0;        // first pair of the unit in the grouped pair list
+    uint32_t m;            // queries in the unit (1..TC_TQ)
+};
+
 // Threshold filter.  A batch produces ~50k (query, candidate) scores per query of which k survive.  Writing them all
 // and reading them back for the selection costs as many bytes as the byte rows themselves, so the scoring kernels
 // only keep a score that can still be among the query's best k: before scoring, k_threshold scores the rows of the
@@ -139,10 +149,15 @@ struct ChunkView {
 void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, const ChunkView& cv, int NT, int topk, size_t list_smem);
 int u8_query_pitch();                                                      // row pitch of dpf_index::Q8
 void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units, const uint32_t* nunits_p, int metric,
-                     const Filter& flt, unsigned long long* bm_stat);
+                     const Filter& flt, unsigned long long* bm_stat, bool int_kernel);
 // bm_group.cu: probe -> pairs grouped by leaf -> unit records, all sized on the host without reading anything back
-void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap);
-void emit_units(dpf_index* h);
+void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc);
+void emit_units(dpf_index* h, bool only_if_fp64_queries);
+void emit_unit_descs(dpf_index* h);                                        // second grouping width for the tcgen05 kernel
+// rerank_tc.cu
+bool score_u8t_usable(const dpf_index* h, int metric);
+void launch_score_u8t(dpf_index* h, const ChunkView& cv, const UnitDesc* descs, const uint32_t* nunits_p, const Filter& flt,
+                      unsigned long long* bm_stat);
 void survivor_lists(dpf_index* h, const Filter& flt, int64_t nqc);         // offsets + scatter
 int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);
 // query.cu: exhaustive per-query top-k over the query's own buckets for the queries flagged dirty
