@@ -199,6 +199,10 @@ enum {
 int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occupancy_out /* 2^pb or NULL */);
 /* introspection of the last bucket-major query chunk: for every leaf bucket of the forest, the start of its list in
  * the grouped (bucket, query) pair array (nleaves + 1 offsets) and its length in rows.  Pass NULLs to get the count. */
+/* watchdog record of the tcgen05 scoring kernel: all zero unless some role of some CTA waited ~1 s for a barrier
+ * ([0] = first barrier tag << 32 | CTA, [1..5] = time-outs per barrier: tile full, accumulator empty, accumulator
+ * full, tile empty, operand empty) */
+int dpf_debug_tc_diag(dpf_handle h, uint64_t* out8);
 int dpf_debug_leaf_pairs(dpf_handle h, int64_t* nleaves_out, uint32_t* pair_off_out, int32_t* leaf_len_out);
 
 /* per-stage device times of the last fit / query call, measured with CUDA events on the handle's stream */

@@ -31,7 +31,7 @@ EXPORTS = [
     "dpf_size", "dpf_query_candidates_dense", "dpf_query_candidates_csr", "dpf_query_candidates_by_id",
     "dpf_query_topk_dense", "dpf_query_topk_dense_dev", "dpf_rerank_dense", "dpf_merge_topk_dev", "dpf_dump_buckets",
     "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms", "dpf_set_store_mode", "dpf_save", "dpf_load", "dpf_set_balanced_partition", "dpf_owned_subindexes", "dpf_parse_dense_file", "dpf_parse_sparse_file",
-    "dpf_set_debug_option", "dpf_debug_leaf_pairs",
+    "dpf_set_debug_option", "dpf_debug_leaf_pairs", "dpf_debug_tc_diag",
 ]
 
 
@@ -92,6 +92,7 @@ def load():
     L.dpf_set_store_mode.argtypes = [vp, i32]
     L.dpf_set_debug_option.argtypes = [vp, i32, i64]
     L.dpf_debug_leaf_pairs.argtypes = [vp, vp, vp, vp]
+    L.dpf_debug_tc_diag.argtypes = [vp, vp]
     L.dpf_set_balanced_partition.argtypes = [vp, i32]
     L.dpf_owned_subindexes.argtypes = [vp, vp]
     L.dpf_save.argtypes = [vp, C.c_char_p]

@@ -947,6 +947,16 @@ int dpf_debug_leaf_pairs(dpf_handle h, int64_t* nleaves_out, uint32_t* pair_off_
     });
 }
 
+int dpf_debug_tc_diag(dpf_handle h, uint64_t* out8) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(out8, DPF_ERR_INVALID, "null buffer");
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        unsigned long long v[8];
+        tc_diag_read(v);
+        for (int i = 0; i < 8; ++i) out8[i] = v[i];
+    });
+}
+
 int dpf_stats(dpf_handle h, int64_t* stats_out, double* occupancy_out) {
     return guarded(h, [&] {
         DPF_REQUIRE(stats_out, DPF_ERR_INVALID, "null buffer");

@@ -340,6 +340,7 @@ bool score_u8_usable(const dpf_index* h);                                  // re
 void prepare_queries_u8(dpf_index* h, const double* Qd, int64_t nq, bool need_host_flag);   // byte copy of the batch + device flag
 void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t q1,
                        int cap, int topk, int metric, int32_t* ids_out, double* score_out);
+void tc_diag_read(unsigned long long* out8);   // rerank_tc.cu
 int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);   // bm_group.cu
 void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);
 void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt);

@@ -51,18 +51,32 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "TC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra TC_DONE;\n"
-        "bra TC_WAIT;\n"
-        "TC_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+// Every wait in this kernel is bounded: a role that waits longer than ~1 s for a barrier (a protocol error — it never
+// happens in a correct run) records which barrier it was in g_tc_diag, raises the CTA's abort flag and every role of
+// the CTA leaves its loops, so a bug shows up as a wrong result and a non-zero dpf_debug_tc_diag, not as a hung GPU.
+__device__ unsigned long long g_tc_diag[8];
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int tag, volatile int* abort_flag) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+        if (*abort_flag) return false;
+        if (clock64() - t0 > 2000000000LL) {
+            *abort_flag = 1;
+            atomicAdd(&g_tc_diag[tag], 1ULL);
+            atomicCAS(&g_tc_diag[0], 0ULL, ((unsigned long long)tag << 32) | (unsigned long long)blockIdx.x);
+            return false;
+        }
+    }
 }
 __device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -111,6 +125,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     extern __shared__ unsigned char tc_smem_raw[];
     __shared__ uint64_t a_full[TC_S], a_empty[TC_S], b_empty[TC_NB], acc_full[TC_NACC], acc_empty[TC_NACC];
     __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* a_tiles = base;                                         // TC_S x 16 KB, 1024-byte aligned
@@ -124,6 +139,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     for (int i = tid; i < (TC_S * TC_A_BYTES + TC_NB * TC_B_BYTES) / 16; i += TC_THREADS)
         reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
+        s_abort = 0;
         for (int i = 0; i < TC_S; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS * 32); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TC_NB; ++i) mbar_init(&b_empty[i], 1);
         for (int i = 0; i < TC_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TC_EPI_WARPS); }
@@ -166,7 +182,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         };
         request(0);
         int64_t g = 0;
-        for (int64_t k = 0; k < nmine; ++k) {
+        for (int64_t k = 0; k < nmine && !s_abort; ++k) {
             const TcUnit u = nx;
             int* taui = meta + (k & 1) * (2 * TC_TQ);
             int* qv = taui + TC_TQ;
@@ -185,7 +201,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
             if (half == 0) rows_scored += u.len;
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int a = (int)(g % TC_NACC);
-                mbar_wait(&acc_full[a], (unsigned)((g / TC_NACC) & 1));
+                if (!mbar_wait(&acc_full[a], (unsigned)((g / TC_NACC) & 1), 3, &s_abort)) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const int row = t * TC_ROWS + 32 * quarter + lane;
                 const bool valid = row < (int)u.len;
@@ -228,7 +244,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         if (lane == 0 && nmine > 0) {
             TcUnit nx = unit_at(0);
             int64_t g = 0;
-            for (int64_t k = 0; k < nmine; ++k) {
+            for (int64_t k = 0; k < nmine && !s_abort; ++k) {
                 const TcUnit u = nx;
                 if (k + 1 < nmine) nx = unit_at(k + 1);
                 const int ntiles = (int)((u.len + TC_ROWS - 1) / TC_ROWS);
@@ -237,8 +253,8 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
                 const uint64_t bdesc = smem_desc_sw128(smem_u32(b_tiles + (size_t)bslot * TC_B_BYTES));
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const int s = (int)(g % TC_S), a = (int)(g % TC_NACC);
-                    mbar_wait(&a_full[s], (unsigned)((g / TC_S) & 1));
-                    if (g >= TC_NACC) mbar_wait(&acc_empty[a], (unsigned)(((g / TC_NACC) - 1) & 1));
+                    if (!mbar_wait(&a_full[s], (unsigned)((g / TC_S) & 1), 1, &s_abort)) break;
+                    if (g >= TC_NACC && !mbar_wait(&acc_empty[a], (unsigned)(((g / TC_NACC) - 1) & 1), 2, &s_abort)) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t adesc = smem_desc_sw128(smem_u32(a_tiles + (size_t)s * TC_A_BYTES));
                     for (int kk = 0; kk < nk; ++kk)                       // + 32 bytes along K = + 2 in the 16-byte address field
@@ -274,20 +290,20 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
             load_q(u0, qi);
             load_ids(u0, 0, id);
             int64_t g = 0;
-            for (int64_t k = 0; k < nmine; ++k) {
+            for (int64_t k = 0; k < nmine && !s_abort; ++k) {
                 if (k + 2 < nmine) u2 = unit_at(k + 2);
                 if (k + 1 < nmine) load_q(u1, qn);
                 const int ntiles = (int)((u0.len + TC_ROWS - 1) / TC_ROWS);
                 // the unit's queries -> operand buffer k % TC_NB (free once the MMAs of unit k - TC_NB are done)
                 const int bslot = (int)(k % TC_NB);
-                if (k >= TC_NB) mbar_wait(&b_empty[bslot], (unsigned)(((k / TC_NB) - 1) & 1));
+                if (k >= TC_NB && !mbar_wait(&b_empty[bslot], (unsigned)(((k / TC_NB) - 1) & 1), 5, &s_abort)) break;
                 const int npad = (int)((u0.m + 15) & ~15u);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (rg + 16 * i < npad) cp16(b0 + (uint32_t)bslot * TC_B_BYTES + (uint32_t)i * 2048u, qsrc + (size_t)qi[i] * 128);
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const int s = (int)(g % TC_S);
-                    if (g >= TC_S) mbar_wait(&a_empty[s], (unsigned)(((g / TC_S) - 1) & 1));
+                    if (g >= TC_S && !mbar_wait(&a_empty[s], (unsigned)(((g / TC_S) - 1) & 1), 4, &s_abort)) break;
                     if (has_chunk) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
@@ -322,6 +338,10 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
     }
+}
+
+void tc_diag_read(unsigned long long* out8) {
+    DPF_CUDA(cudaMemcpyFromSymbol(out8, tc::g_tc_diag, 8 * sizeof(unsigned long long)));
 }
 
 bool score_u8t_usable(const dpf_index* h, int metric) {

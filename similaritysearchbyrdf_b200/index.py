@@ -254,6 +254,12 @@ class DPFIndex:
         self._ck(self.lib.dpf_debug_leaf_pairs(self.h, C.byref(n), _p(off), _p(ln)))
         return off, ln[:n.value]
 
+    def tc_diag(self):
+        """Watchdog record of the tcgen05 scoring kernel (all zero in a correct run)."""
+        out = np.zeros(8, np.uint64)
+        self._ck(self.lib.dpf_debug_tc_diag(self.h, _p(out)))
+        return out
+
     def stats(self):
         s = np.zeros(B.STAT_COUNT, np.int64)
         occ = np.zeros(1 << self.pb, np.float64)
