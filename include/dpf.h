@@ -161,6 +161,28 @@ int dpf_set_balanced_partition(dpf_handle h, int32_t enable);
 /* owned_out[p] = 1 for the 2^pb sub-indexes this handle owns (after the first fit when the assignment is balanced) */
 int dpf_owned_subindexes(dpf_handle h, uint8_t* owned_out);
 
+/* ---- multi-GPU data plane inside the library: one handle (rank) per GPU, NCCL over NVLink between them (the library
+ * binds libnccl.so.2 at run time).  Replaces the in-process partition scheme of the reference (Partitioner.scala:27-64,
+ * RandomDrawTreeMap.java:613-621, 1430-1459) for the GPUs of one box, whether the ranks are threads of one process or
+ * one process each.  Rank 0 obtains an id, the caller hands it to every rank (any channel), every rank calls
+ * dpf_comm_init (collective).  After that:
+ *   dpf_fit_dense_sharded[_dev]   collective fit: every rank passes the same vectors, hashes 1/world of them, and one
+ *                                 all-gather of the keys (5 L bytes per vector) lets each build the sub-forests it owns;
+ *   dpf_query_topk_dense_all[_dev] collective query: same queries on every rank, per-rank top k -> one all-gather of
+ *                                 12-byte entries -> merge; every rank gets the global result.  No host synchronisation
+ *                                 in the _dev form. */
+#define DPF_COMM_ID_BYTES 128
+int dpf_comm_unique_id(uint8_t* id_out /* DPF_COMM_ID_BYTES */);
+int dpf_comm_init(dpf_handle h, const uint8_t* id /* DPF_COMM_ID_BYTES */);
+int dpf_comm_destroy(dpf_handle h);
+int dpf_fit_dense_sharded(dpf_handle h, const double* X, int64_t n);
+int dpf_fit_dense_sharded_dev(dpf_handle h, const double* X_dev, int64_t n);
+int dpf_query_topk_dense_all(dpf_handle h, const double* Q, int64_t nq, const int32_t* qids, int32_t steps,
+                             int32_t probe_mode, int32_t topk, int32_t metric, int32_t* ids_out, double* score_out);
+int dpf_query_topk_dense_all_dev(dpf_handle h, const double* Q_dev, int64_t nq, const int32_t* qids_dev, int32_t steps,
+                                 int32_t probe_mode, int32_t topk, int32_t metric, int32_t* ids_out_dev,
+                                 double* score_out_dev);
+
 /* ---- multi-GPU: merge per-GPU top-k lists after the NCCL all-gather -----------------------
  * gathered_*_dev: G x nq x topk as produced by all-gathering dpf_query_topk_dense_dev outputs; duplicates of
  * one id (same vector reached through tables owned by different GPUs) are collapsed. */
@@ -209,6 +231,7 @@ int dpf_debug_leaf_pairs(dpf_handle h, int64_t* nleaves_out, uint32_t* pair_off_
 enum {
     DPF_T_HASH = 0, DPF_T_FIXUP = 1, DPF_T_PACK = 2, DPF_T_SORT = 3, DPF_T_SPLIT = 4,
     DPF_T_PROBE_COUNT = 5, DPF_T_EXPAND = 6, DPF_T_RERANK = 7, DPF_T_CAND_SORT = 8, DPF_T_SELECT = 9, DPF_T_NARROW = 10,
+    DPF_T_COMM = 11,
     DPF_T_COUNT = 16
 };
 int dpf_set_profiling(dpf_handle h, int32_t enable);

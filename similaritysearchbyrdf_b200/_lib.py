@@ -22,7 +22,9 @@ DBG_DEFAULTS = {DBG_U8_IMMA: 1}
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
               "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",
               "bm_rows_staged", "store_kind", "store_row_bytes", "bm_survivors", "bm_direct"]
-STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select", "narrow"]
+STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select", "narrow",
+               "comm"]
+COMM_ID_BYTES = 128
 
 # every symbol include/dpf.h declares
 EXPORTS = [
@@ -31,7 +33,8 @@ EXPORTS = [
     "dpf_size", "dpf_query_candidates_dense", "dpf_query_candidates_csr", "dpf_query_candidates_by_id",
     "dpf_query_topk_dense", "dpf_query_topk_dense_dev", "dpf_rerank_dense", "dpf_merge_topk_dev", "dpf_dump_buckets",
     "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms", "dpf_set_store_mode", "dpf_save", "dpf_load", "dpf_set_balanced_partition", "dpf_owned_subindexes", "dpf_parse_dense_file", "dpf_parse_sparse_file",
-    "dpf_set_debug_option", "dpf_debug_leaf_pairs", "dpf_debug_tc_diag",
+    "dpf_set_debug_option", "dpf_debug_leaf_pairs", "dpf_debug_tc_diag", "dpf_comm_unique_id", "dpf_comm_init", "dpf_comm_destroy",
+    "dpf_fit_dense_sharded", "dpf_fit_dense_sharded_dev", "dpf_query_topk_dense_all", "dpf_query_topk_dense_all_dev",
 ]
 
 
@@ -93,6 +96,13 @@ def load():
     L.dpf_set_debug_option.argtypes = [vp, i32, i64]
     L.dpf_debug_leaf_pairs.argtypes = [vp, vp, vp, vp]
     L.dpf_debug_tc_diag.argtypes = [vp, vp]
+    L.dpf_comm_unique_id.argtypes = [vp]
+    L.dpf_comm_init.argtypes = [vp, vp]
+    L.dpf_comm_destroy.argtypes = [vp]
+    L.dpf_fit_dense_sharded.argtypes = [vp, vp, i64]
+    L.dpf_fit_dense_sharded_dev.argtypes = [vp, vp, i64]
+    L.dpf_query_topk_dense_all.argtypes = [vp, vp, i64, vp, i32, i32, i32, i32, vp, vp]
+    L.dpf_query_topk_dense_all_dev.argtypes = [vp, vp, i64, vp, i32, i32, i32, i32, vp, vp]
     L.dpf_set_balanced_partition.argtypes = [vp, i32]
     L.dpf_owned_subindexes.argtypes = [vp, vp]
     L.dpf_save.argtypes = [vp, C.c_char_p]

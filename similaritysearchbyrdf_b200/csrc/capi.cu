@@ -260,6 +260,7 @@ int dpf_destroy(dpf_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);   // a caller stream that is already gone only returns an error
     cudaGetLastError();
     cudaStream_t own = h->own_stream ? h->own_stream : h->stream;
+    try { comm_destroy(h); } catch (...) {}
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -447,7 +448,7 @@ static void assign_balanced_partition(dpf_index* h, int64_t n_new) {
     h->own_fixed = true;
 }
 
-static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_device) {
+static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_device, bool sharded_hash = false) {
     require_ready(h, false);
     DPF_REQUIRE(n > 0 && X, DPF_ERR_INVALID, "empty fit");
     DPF_REQUIRE(h->n == 0 || h->dense, DPF_ERR_STATE, "index holds sparse vectors");
@@ -483,7 +484,8 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     }
     grow_keys(h, n);
     tr.mark("keys: allocate");
-    hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
+    if (sharded_hash) hash_dense_sharded(h, Xnew, n, h->n);      // this rank's slice + one all-gather of the keys
+    else hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
     tr.mark("hash");
     if (h->n == 0) assign_balanced_partition(h, n);
     // the new vectors count only once the forest and the store have been rebuilt: a failure in between (out of memory,
@@ -532,6 +534,35 @@ int dpf_fit_dense(dpf_handle h, const double* X, int64_t n) {
 }
 int dpf_fit_dense_dev(dpf_handle h, const double* X_dev, int64_t n) {
     return guarded(h, [&] { fit_dense_common(h, X_dev, n, true); });
+}
+
+int dpf_fit_dense_sharded(dpf_handle h, const double* X, int64_t n) {
+    return guarded(h, [&] { fit_dense_common(h, X, n, false, true); });
+}
+int dpf_fit_dense_sharded_dev(dpf_handle h, const double* X_dev, int64_t n) {
+    return guarded(h, [&] { fit_dense_common(h, X_dev, n, true, true); });
+}
+
+int dpf_comm_unique_id(uint8_t* id_out) {
+    if (!id_out) return DPF_ERR_INVALID;
+    try {
+        comm_unique_id(id_out);
+        return DPF_OK;
+    } catch (const Error& e) {
+        return e.code;
+    }
+}
+int dpf_comm_init(dpf_handle h, const uint8_t* id) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(id, DPF_ERR_INVALID, "null id");
+        comm_init(h, id);
+    });
+}
+int dpf_comm_destroy(dpf_handle h) {
+    return guarded(h, [&] {
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        comm_destroy(h);
+    });
 }
 
 int dpf_fit_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values, int64_t n) {
@@ -706,6 +737,47 @@ int dpf_query_topk_dense_dev(dpf_handle h, const double* Q_dev, int64_t nq, cons
         DPF_REQUIRE(topk >= 1 && topk <= 256, DPF_ERR_INVALID, "topk must be in 1..256");
         begin_profile(h);
         topk_device(h, Q_dev, nq, qids_dev, steps, probe_mode, topk, metric, ids_out_dev, score_out_dev);
+        end_profile(h);
+    });
+}
+
+// collective over the ranks of the handle's communicator: every rank passes the same queries and gets the global top k
+int dpf_query_topk_dense_all_dev(dpf_handle h, const double* Q_dev, int64_t nq, const int32_t* qids_dev, int32_t steps,
+                                 int32_t probe_mode, int32_t topk, int32_t metric, int32_t* ids_out_dev, double* score_out_dev) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && Q_dev && ids_out_dev && score_out_dev, DPF_ERR_INVALID, "null buffer");
+        DPF_REQUIRE(steps >= 0 && metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad steps/metric");
+        DPF_REQUIRE(topk >= 1 && topk <= 256, DPF_ERR_INVALID, "topk must be in 1..256");
+        begin_profile(h);
+        int32_t* ids_seg;
+        double* sc_seg;
+        comm_topk_buffers(h, nq, topk, &ids_seg, &sc_seg);
+        topk_device(h, Q_dev, nq, qids_dev, steps, probe_mode, topk, metric, ids_seg, sc_seg);
+        comm_gather_merge_topk(h, nq, topk, metric, ids_out_dev, score_out_dev);
+        end_profile(h);
+    });
+}
+
+int dpf_query_topk_dense_all(dpf_handle h, const double* Q, int64_t nq, const int32_t* qids, int32_t steps, int32_t probe_mode,
+                             int32_t topk, int32_t metric, int32_t* ids_out, double* score_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(nq > 0 && Q && ids_out && score_out, DPF_ERR_INVALID, "null buffer");
+        DPF_REQUIRE(steps >= 0 && metric >= 0 && metric <= 2, DPF_ERR_INVALID, "bad steps/metric");
+        DPF_REQUIRE(topk >= 1 && topk <= 256, DPF_ERR_INVALID, "topk must be in 1..256");
+        begin_profile(h);
+        upload_queries_dense(h, Q, nq, qids);
+        h->out_ids.reserve((size_t)nq * topk);
+        h->out_scores.reserve((size_t)nq * topk);
+        int32_t* ids_seg;
+        double* sc_seg;
+        comm_topk_buffers(h, nq, topk, &ids_seg, &sc_seg);
+        topk_device(h, h->qbuf.p, nq, qids ? h->qidbuf.p : nullptr, steps, probe_mode, topk, metric, ids_seg, sc_seg);
+        comm_gather_merge_topk(h, nq, topk, metric, h->out_ids.p, h->out_scores.p);
+        d2h(h, ids_out, h->out_ids.p, (size_t)nq * topk);
+        d2h(h, score_out, h->out_scores.p, (size_t)nq * topk);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
         end_profile(h);
     });
 }

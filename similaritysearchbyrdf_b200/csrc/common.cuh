@@ -257,6 +257,10 @@ struct dpf_index {
     // test / profiling hooks (dpf_set_debug_option); the product path never reads the environment
     int64_t dbg[DPF_DBG_COUNT] = {0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
+    // multi-GPU plane (comm.cu): NCCL communicator of this rank, staging of the key all-gather, the top-k gather buffer
+    void* comm = nullptr;
+    dpf::DevBuf<char> comm_stage, comm_topk;
+
     // stats / profiling
     int64_t stats[DPF_STAT_COUNT] = {0};
     bool profiling = false;
@@ -346,5 +350,18 @@ void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);
 void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt);
 void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,
                 int32_t* ids_out, double* score_out);
+// list g of the gathered results starts at gids + g * stride_ids / gsc + g * stride_sc (elements)
+void merge_topk_strided(dpf_index* h, const int32_t* gids, const double* gsc, int64_t stride_ids, int64_t stride_sc, int G, int64_t nq,
+                        int topk, int metric, int32_t* ids_out, double* score_out);
+
+// ---- comm.cu ------------------------------------------------------------------------------------------------
+void comm_unique_id(uint8_t* out);
+void comm_init(dpf_index* h, const uint8_t* id_bytes);
+void comm_destroy(dpf_index* h);
+// keys / sub-index ids of n new vectors (ids n_old ..): this rank hashes its slice, one all-gather, every rank has all
+void hash_dense_sharded(dpf_index* h, const double* Xnew, int64_t n, int64_t n_old);
+// this rank's segment of the top-k gather buffer; after the local top k was written there: all-gather + merge
+void comm_topk_buffers(dpf_index* h, int64_t nq, int topk, int32_t** ids_seg, double** sc_seg);
+void comm_gather_merge_topk(dpf_index* h, int64_t nq, int topk, int metric, int32_t* ids_out, double* score_out);
 
 }  // namespace dpf

@@ -663,8 +663,8 @@ void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* 
 // tables whose sub-index lives on different GPUs) with a bit-identical score, and is kept once.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_merge_topk(const int32_t* __restrict__ gids, const double* __restrict__ gsc, int G, int64_t nq, int K, int metric,
-             int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
+k_merge_topk(const int32_t* __restrict__ gids, const double* __restrict__ gsc, int64_t stride_ids, int64_t stride_sc, int G,
+             int64_t nq, int K, int metric, int32_t* __restrict__ ids_out, double* __restrict__ score_out) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -678,9 +678,9 @@ k_merge_topk(const int32_t* __restrict__ gids, const double* __restrict__ gsc, i
             for (int g0 = 0; g0 < G; g0 += 32) {       // G <= 32 in practice; loop kept for generality
                 const int g = g0 + lane;
                 if (g < G && head < K) {
-                    const int id = gids[((int64_t)g * nq + q) * K + head];
+                    const int id = gids[(int64_t)g * stride_ids + q * K + head];
                     if (id >= 0) {
-                        const double s = gsc[((int64_t)g * nq + q) * K + head];
+                        const double s = gsc[(int64_t)g * stride_sc + q * K + head];
                         bk = (metric == DPF_METRIC_L2) ? -s : s; bi = id; bl = lane;
                     }
                 }
@@ -714,12 +714,18 @@ k_merge_topk(const int32_t* __restrict__ gids, const double* __restrict__ gsc, i
     }
 }
 
-void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,
-                int32_t* ids_out, double* score_out) {
+void merge_topk_strided(dpf_index* h, const int32_t* gids, const double* gsc, int64_t stride_ids, int64_t stride_sc, int G, int64_t nq,
+                        int topk, int metric, int32_t* ids_out, double* score_out) {
     DPF_REQUIRE(G >= 1 && G <= 32, DPF_ERR_INVALID, "merge supports 1..32 lists");
     if (nq <= 0) return;
-    k_merge_topk<<<(unsigned)((nq + 3) / 4), 128, 0, h->stream>>>(gids, gsc, G, nq, topk, metric, ids_out, score_out); DPF_LAUNCHED();
+    k_merge_topk<<<(unsigned)((nq + 3) / 4), 128, 0, h->stream>>>(gids, gsc, stride_ids, stride_sc, G, nq, topk, metric, ids_out,
+                                                                  score_out); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
+}
+
+void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,
+                int32_t* ids_out, double* score_out) {
+    merge_topk_strided(h, gids, gsc, nq * topk, nq * topk, G, nq, topk, metric, ids_out, score_out);
 }
 
 

@@ -32,7 +32,9 @@ namespace dpf {
 constexpr int TC_ROWS = 128;                      // rows per tile = UMMA M
 constexpr int TC_S = 8;                           // row-tile ring
 constexpr int TC_D = 7;                           // cp.async groups a producer thread keeps in flight (< TC_S)
-constexpr int TC_NB = 4;                          // query-operand buffers
+constexpr int TC_NB = 8;                          // query-operand buffers: >= TC_D, because a thread's arrival for a tile lags its
+                                                  // copies by TC_D - 1 tiles and buffer k % TC_NB is only free once the tiles of
+                                                  // unit k - TC_NB have been multiplied (units can be one tile long)
 constexpr int TC_NACC = 4;                        // accumulator stages
 constexpr int TC_TMEM_COLS = TC_NACC * TC_TQ;     // 256 of the 512 columns
 constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 4;
@@ -40,6 +42,7 @@ constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;
 constexpr int TC_A_BYTES = TC_ROWS * 128, TC_B_BYTES = TC_TQ * 128;
 constexpr size_t TC_SMEM = 1024 /* alignment slack */ + (size_t)TC_S * TC_A_BYTES + (size_t)TC_NB * TC_B_BYTES +
                            (size_t)TC_EPI_WARPS * 2 * TC_TQ * 8 + 256;
+static_assert(TC_NB >= TC_D && TC_D < TC_S, "see TC_NB");
 static_assert(TC_TQ % 16 == 0 && TC_TQ <= 256 && TC_TMEM_COLS <= 512, "UMMA N / tensor-memory budget");
 static_assert((TC_TMEM_COLS & (TC_TMEM_COLS - 1)) == 0 && TC_TMEM_COLS >= 32, "tensor memory is allocated in powers of two");
 

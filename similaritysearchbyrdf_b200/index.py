@@ -129,6 +129,51 @@ class DPFIndex:
         self._ck(self.lib.dpf_owned_subindexes(self.h, _p(out)))
         return out
 
+    # ---- multi-GPU plane (NCCL inside the library) ------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """Rank 0: the id every rank passes to comm_init (bytes of length B.COMM_ID_BYTES)."""
+        lib = B.load()
+        buf = np.zeros(B.COMM_ID_BYTES, np.uint8)
+        rc = lib.dpf_comm_unique_id(_p(buf))
+        if rc != B.OK:
+            raise B.DpfError(rc, lib.dpf_strerror(rc).decode())
+        return buf
+
+    def comm_init(self, unique_id):
+        """Collective over the `world` ranks of this index's configuration."""
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == B.COMM_ID_BYTES
+        self._ck(self.lib.dpf_comm_init(self.h, _p(uid)))
+
+    def comm_destroy(self):
+        self._ck(self.lib.dpf_comm_destroy(self.h))
+
+    def fit_dense_sharded(self, X):
+        """Collective fit: same X on every rank, hashing split across the ranks, keys all-gathered."""
+        X = _f64(X)
+        self._ck(self.lib.dpf_fit_dense_sharded(self.h, _p(X), X.shape[0]))
+
+    def fit_dense_sharded_dev(self, dev_ptr, n):
+        self._ck(self.lib.dpf_fit_dense_sharded_dev(self.h, C.c_void_p(dev_ptr), n))
+
+    def query_topk_dense_all(self, Q, qids=None, steps=0, topk=10, metric=B.METRIC_DOT, probe_mode=B.PROBE_DENSE):
+        """Collective query: same Q on every rank, the merged global top k on every rank."""
+        Q = _f64(Q)
+        qids = None if qids is None else _i32(qids)
+        nq = Q.shape[0]
+        ids = np.empty((nq, topk), np.int32)
+        sc = np.empty((nq, topk), np.float64)
+        self._ck(self.lib.dpf_query_topk_dense_all(self.h, _p(Q), nq, _p(qids), steps, probe_mode, topk, metric, _p(ids),
+                                                   _p(sc)))
+        return ids, sc
+
+    def query_topk_dense_all_dev(self, q_ptr, nq, qids_ptr, steps, topk, metric, ids_ptr, score_ptr,
+                                 probe_mode=B.PROBE_DENSE):
+        self._ck(self.lib.dpf_query_topk_dense_all_dev(self.h, C.c_void_p(q_ptr), nq,
+                                                       C.c_void_p(qids_ptr) if qids_ptr else None, steps, probe_mode,
+                                                       topk, metric, C.c_void_p(ids_ptr), C.c_void_p(score_ptr)))
+
     # ---- hash functions -------------------------------------------------------------------------------------
     def set_family(self, A, chain_idx, b=None, w=None):
         A, chain_idx = _f64(A), _i32(chain_idx)
