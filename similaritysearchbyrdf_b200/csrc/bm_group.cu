@@ -79,6 +79,7 @@ constexpr unsigned long long LS_VALUE_MASK = (1ULL << 62) - 1ULL;
 
 __global__ void __launch_bounds__(LS_THREADS)
 k_scan_leaves(const uint32_t* __restrict__ leaf_cnt, int64_t nleaves, uint32_t uq /* queries per unit */,
+              const int32_t* __restrict__ leaf_len, uint32_t rows_per_unit /* 0: a unit takes the whole bucket */,
               uint32_t* __restrict__ leaf_off, uint32_t* __restrict__ unit_off,
               unsigned int* __restrict__ tile_counter, volatile unsigned long long* __restrict__ status,
               uint32_t* __restrict__ totals /* [0] pairs, [1] units */, unsigned long long* __restrict__ pairs_total /* or null */) {
@@ -93,7 +94,9 @@ k_scan_leaves(const uint32_t* __restrict__ leaf_cnt, int64_t nleaves, uint32_t u
 #pragma unroll
     for (int i = 0; i < LS_ITEMS; ++i) {
         const uint32_t c = base + i < nleaves ? leaf_cnt[base + i] : 0u;
-        v[i] = (unsigned long long)c | ((unsigned long long)((c + uq - 1) / uq) << 32);
+        uint32_t units = (c + uq - 1) / uq;
+        if (rows_per_unit && c) units *= ((uint32_t)leaf_len[base + i] + rows_per_unit - 1) / rows_per_unit;
+        v[i] = (unsigned long long)c | ((unsigned long long)units << 32);
         s += v[i];
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -175,17 +178,31 @@ k_fill_pairs(const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__
     }
 }
 
-// thread per leaf: one 16-byte descriptor per TC_TQ pairs of its list (the tcgen05 kernel's units)
+// warp per leaf: the tcgen05 kernel's units — one record per (<= TC_TQ pairs of the leaf's list) x (<= 128 of its rows)
 __global__ void __launch_bounds__(256)
-k_emit_unit_descs(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict__ unit_off, const uint32_t* __restrict__ leaf_pos,
-                  const int32_t* __restrict__ leaf_len, int64_t nleaves, UnitDesc* __restrict__ descs) {
-    const int64_t leaf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (leaf >= nleaves) return;
-    const uint32_t p0 = leaf_off[leaf], p1 = leaf_off[leaf + 1];
-    if (p0 == p1) return;
-    const uint32_t bstart = leaf_pos[leaf], len = (uint32_t)leaf_len[leaf];
-    uint4* out = reinterpret_cast<uint4*>(descs + unit_off[leaf]);
-    for (uint32_t p = p0; p < p1; p += TC_TQ, ++out) *out = make_uint4(bstart, len, p, min((uint32_t)TC_TQ, p1 - p));
+k_emit_tc_recs(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict__ unit_off, const uint32_t* __restrict__ leaf_pos,
+               const int32_t* __restrict__ leaf_len, int64_t nleaves, const int32_t* __restrict__ pair_q,
+               const int32_t* __restrict__ ids_sorted, TcRec* __restrict__ recs, const int* __restrict__ q8_bad) {
+    if (*q8_bad != 0) return;                       // a batch that is not byte vectors is scored from the UnitRecs
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t leaf = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); leaf < nleaves; leaf += nwarps) {
+        const uint32_t p0 = leaf_off[leaf], p1 = leaf_off[leaf + 1];
+        if (p0 == p1) continue;
+        const uint32_t bstart = leaf_pos[leaf], len = (uint32_t)leaf_len[leaf];
+        TcRec* rec = recs + unit_off[leaf];
+        for (uint32_t p = p0; p < p1; p += TC_TQ) {
+            const uint32_t m = min((uint32_t)TC_TQ, p1 - p);
+            const int32_t qv = pair_q[p + min((uint32_t)lane, m - 1u)];
+            for (uint32_t r0 = 0; r0 < len; r0 += 128, ++rec) {
+                const uint32_t nrows = min(128u, len - r0);
+                if (lane == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(bstart, nrows, m, r0);
+                rec->q[lane] = qv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rec->ids[lane + 32 * i] = ids_sorted[bstart + r0 + min((uint32_t)(lane + 32 * i), nrows - 1u)];
+            }
+        }
+    }
 }
 
 // warp per leaf: one record per SS_UQ pairs of its list.  gate != 0: only when some query of the batch is not a byte
@@ -196,19 +213,20 @@ k_emit_units(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict__
              const int32_t* __restrict__ ids_sorted, UnitRec* __restrict__ units, const int* __restrict__ q8_bad, int gate) {
     if (gate && *q8_bad == 0) return;
     const int lane = threadIdx.x & 31;
-    const int64_t leaf = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (leaf >= nleaves) return;
-    const uint32_t p0 = leaf_off[leaf], p1 = leaf_off[leaf + 1];
-    if (p0 == p1) return;
-    const uint32_t bstart = leaf_pos[leaf];
-    const int len = leaf_len[leaf];
-    const int32_t id0 = ids_sorted[bstart + min(lane, len - 1)];
-    UnitRec* rec = units + unit_off[leaf];
-    for (uint32_t p = p0; p < p1; p += SS_UQ, ++rec) {
-        const uint32_t m = min((uint32_t)SS_UQ, p1 - p);
-        if (lane == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(bstart, (uint32_t)len, p, m);
-        if (lane < SS_UQ) rec->q[lane] = pair_q[p + min((uint32_t)lane, m - 1u)];
-        rec->ids0[lane] = id0;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t leaf = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); leaf < nleaves; leaf += nwarps) {
+        const uint32_t p0 = leaf_off[leaf], p1 = leaf_off[leaf + 1];
+        if (p0 == p1) continue;
+        const uint32_t bstart = leaf_pos[leaf];
+        const int len = leaf_len[leaf];
+        const int32_t id0 = ids_sorted[bstart + min(lane, len - 1)];
+        UnitRec* rec = units + unit_off[leaf];
+        for (uint32_t p = p0; p < p1; p += SS_UQ, ++rec) {
+            const uint32_t m = min((uint32_t)SS_UQ, p1 - p);
+            if (lane == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(bstart, (uint32_t)len, p, m);
+            if (lane < SS_UQ) rec->q[lane] = pair_q[p + min((uint32_t)lane, m - 1u)];
+            rec->ids0[lane] = id0;
+        }
     }
 }
 
@@ -312,14 +330,15 @@ void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
         DPF_CUDA(cudaMemsetAsync(ctr + CTR_NPAIRS_TC, 0, 3 * sizeof(int32_t), st));
         if (ntiles > 0) {
             k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
-                h->leaf_cnt.p, nleaves, (uint32_t)SS_UQ, h->leaf_off.p, h->leaf_unit_off.p, reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE),
+                h->leaf_cnt.p, nleaves, (uint32_t)SS_UQ, h->leaf_len.p, 0u, h->leaf_off.p, h->leaf_unit_off.p,
+                reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE),
                 reinterpret_cast<unsigned long long*>(h->scan_scratch.p + 2), reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS),
                 reinterpret_cast<unsigned long long*>(ctr + CTR_BM_PAIRS_TOTAL)); DPF_LAUNCHED();
         }
         if (ntiles > 0 && use_tc) {            // the same histogram once more, at the tcgen05 kernel's unit width
             uint32_t* status2 = h->scan_scratch.p + 2 * ntiles + 4;
             k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
-                h->leaf_cnt.p, nleaves, (uint32_t)TC_TQ, h->leaf_off.p, h->leaf_unit_off_tc.p,
+                h->leaf_cnt.p, nleaves, (uint32_t)TC_TQ, h->leaf_len.p, 128u, h->leaf_off.p, h->leaf_unit_off_tc.p,
                 reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE_TC), reinterpret_cast<unsigned long long*>(status2),
                 reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS_TC), nullptr); DPF_LAUNCHED();
         }
@@ -334,7 +353,8 @@ void emit_units(dpf_index* h, bool only_if_fp64_queries) {
     StageTimer tm(h, DPF_T_EXPAND);
     const int64_t nleaves = h->num_leaves;
     if (nleaves > 0) {
-        k_emit_units<<<(unsigned)((nleaves + 7) / 8), 256, 0, h->stream>>>(h->leaf_off.p, h->leaf_unit_off.p, h->leaf_pos.p, h->leaf_len.p,
+        const unsigned grid = (unsigned)std::min<int64_t>((nleaves + 7) / 8, (int64_t)h->num_sms * 16);   // grid-stride: a gated launch costs ~nothing
+        k_emit_units<<<grid, 256, 0, h->stream>>>(h->leaf_off.p, h->leaf_unit_off.p, h->leaf_pos.p, h->leaf_len.p,
                                                                           nleaves, h->pair_q.p, h->ids_sorted.p,
                                                                           reinterpret_cast<UnitRec*>(h->bm_units.p),
                                                                           h->counters.p + CTR_Q8_BAD, only_if_fp64_queries ? 1 : 0); DPF_LAUNCHED();
@@ -342,13 +362,14 @@ void emit_units(dpf_index* h, bool only_if_fp64_queries) {
     DPF_CUDA(cudaGetLastError());
 }
 
-void emit_unit_descs(dpf_index* h) {
+void emit_tc_recs(dpf_index* h) {
     StageTimer tm(h, DPF_T_EXPAND);
     const int64_t nleaves = h->num_leaves;
     if (nleaves > 0) {
-        k_emit_unit_descs<<<(unsigned)((nleaves + 255) / 256), 256, 0, h->stream>>>(h->leaf_off.p, h->leaf_unit_off_tc.p, h->leaf_pos.p,
-                                                                                   h->leaf_len.p, nleaves,
-                                                                                   reinterpret_cast<UnitDesc*>(h->bm_descs.p)); DPF_LAUNCHED();
+        const unsigned grid = (unsigned)std::min<int64_t>((nleaves + 7) / 8, (int64_t)h->num_sms * 16);
+        k_emit_tc_recs<<<grid, 256, 0, h->stream>>>(h->leaf_off.p, h->leaf_unit_off_tc.p, h->leaf_pos.p, h->leaf_len.p, nleaves,
+                                                    h->pair_q.p, h->ids_sorted.p, reinterpret_cast<TcRec*>(h->bm_descs.p),
+                                                    h->counters.p + CTR_Q8_BAD); DPF_LAUNCHED();
     }
     DPF_CUDA(cudaGetLastError());
 }

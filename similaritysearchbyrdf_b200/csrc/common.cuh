@@ -207,7 +207,9 @@ struct dpf_index {
     dpf::DevBuf<uint32_t> leaf_cnt;             // per leaf: pairs of the current query chunk (all zero between batches)
     dpf::DevBuf<uint32_t> leaf_off, leaf_unit_off;   //           first pair / first unit
     dpf::DevBuf<uint32_t> leaf_unit_off_tc;          //           first unit at the tcgen05 kernel's unit width
-    dpf::DevBuf<char> bm_descs;                      // UnitDesc records
+    dpf::DevBuf<char> bm_descs;                      // TcRec records (the tcgen05 kernel's units)
+    dpf::DevBuf<int32_t> bm_taui;                    // per query: integer score threshold
+    int64_t max_leaf_len = 0, total_leaf_tiles = 0;  // largest leaf bucket; sum over leaves of ceil(len / 128)
     int32_t num_leaves = 0;
     bool leaf_table = false;                    // false when the forest has >= 2^32 entries (row-major re-rank only)
     dpf::DevBuf<int64_t> table_base;

@@ -229,6 +229,18 @@ k_leaf_table(const int32_t* __restrict__ child_ptr, const int32_t* __restrict__ 
     leaf_len[leaf] = cnt;
 }
 
+__global__ void __launch_bounds__(256)
+k_leaf_shape(const int32_t* __restrict__ leaf_len, int64_t nleaves, unsigned long long* __restrict__ out /* [0] max len, [1] tiles */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long len = i < nleaves ? (unsigned long long)leaf_len[i] : 0ULL, tiles = (len + 127) / 128;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+        tiles += __shfl_xor_sync(0xffffffffu, tiles, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], len); atomicAdd(&out[1], tiles); }
+}
+
 static void build_leaf_table(dpf_index* h) {
     const TreeParams tp = h->tp;
     cudaStream_t st = h->stream;
@@ -255,6 +267,16 @@ static void build_leaf_table(dpf_index* h) {
                                                                        h->leaf_pos.p, h->leaf_len.p); DPF_LAUNCHED();
     }
     DPF_CUDA(cudaGetLastError());
+    {   // shape of the leaves: sizes the tcgen05 kernel's unit records without reading anything back at query time
+        unsigned long long* shape = reinterpret_cast<unsigned long long*>(h->counters.p + 8);
+        DPF_CUDA(cudaMemsetAsync(shape, 0, 2 * sizeof(unsigned long long), st));
+        if (nl > 0) { k_leaf_shape<<<(unsigned)((nl + 255) / 256), 256, 0, st>>>(h->leaf_len.p, nl, shape); DPF_LAUNCHED(); }
+        unsigned long long hs[2] = {0, 0};
+        DPF_CUDA(cudaMemcpyAsync(hs, shape, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        DPF_CUDA(cudaStreamSynchronize(st));
+        h->max_leaf_len = (int64_t)hs[0];
+        h->total_leaf_tiles = (int64_t)hs[1];
+    }
     h->num_leaves = (int32_t)nl;
     h->leaf_table = true;
 }

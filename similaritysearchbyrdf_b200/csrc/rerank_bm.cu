@@ -593,7 +593,7 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, Chun
 // no threshold can be guaranteed, the query is flagged for k_topk_direct and tau = +inf keeps it out of the pool.
 __global__ void __launch_bounds__(RR_THREADS)
 k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys, const int* __restrict__ tl_ids,
-                  const int* __restrict__ tl_cnt, double* __restrict__ tau, uint32_t* __restrict__ dirty) {
+                  const int* __restrict__ tl_cnt, double* __restrict__ tau, int32_t* __restrict__ taui, uint32_t* __restrict__ dirty) {
     const int lane = threadIdx.x & 31;
     const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
     if (ql >= nqc) return;
@@ -619,7 +619,10 @@ k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys
         if (bi != last) { found++; kth = bk; last = bi; }
     }
     if (lane == 0) {
-        tau[q] = found == K ? kth : __longlong_as_double(0x7ff0000000000000LL);
+        const double tv = found == K ? kth : __longlong_as_double(0x7ff0000000000000LL);
+        tau[q] = tv;
+        // the same threshold for integer scores (a dot product of bytes is below 2^31 - 1: INT_MAX masks the query)
+        taui[q] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
         if (found < K) dirty[q] = 1u;
     }
 }
@@ -791,9 +794,12 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     h->bm_units.reserve((size_t)units_ub * sizeof(UnitRec));
     // byte rows x byte queries, dot product: the tcgen05 kernel with its own, wider units
     const bool try_int = use_u8 && h->dbg[DPF_DBG_U8_IMMA] != 0 && (int64_t)d * 255 * 255 < (1LL << 31);
-    const bool use_tc = try_int && score_u8t_usable(h, metric);
-    if (use_tc)
-        h->bm_descs.reserve((size_t)(std::min<int64_t>(pairs_ub, (int64_t)h->num_leaves + pairs_ub / TC_TQ) + 1) * sizeof(UnitDesc));
+    // its units: (<= 32 pairs of a leaf) x (<= 128 of its rows); worst case from the forest's largest leaf and tile count
+    const int64_t max_tiles = std::max<int64_t>(1, (h->max_leaf_len + 127) / 128);
+    const int64_t tc_units_ub = std::min(pairs_ub * max_tiles, pairs_ub / TC_TQ * max_tiles + h->total_leaf_tiles) + 1;
+    const bool use_tc = try_int && score_u8t_usable(h, metric) && tc_units_ub * (int64_t)sizeof(TcRec) <= (2LL << 30);
+    if (use_tc) h->bm_descs.reserve((size_t)tc_units_ub * sizeof(TcRec));
+    h->bm_taui.reserve((size_t)nqc + 2);
     int64_t pool_cap = h->dbg[DPF_DBG_POOL_RECORDS] > 0 ? h->dbg[DPF_DBG_POOL_RECORDS]
                                                         : std::min<int64_t>(std::max<int64_t>(nqc * 2048, 1 << 20), 1LL << 28);
     pool_cap = std::max<int64_t>(SURV_BLOCK, pool_cap / SURV_BLOCK * SURV_BLOCK);
@@ -865,11 +871,11 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             dispatch_kind(kind, ang, [&](auto a, auto kc) { go(k_threshold<decltype(a)::value, decltype(kc)::value, false>, 0); });
         }
         k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(nqc, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p, h->bm_tau.p,
-                                                         s_dirty); DPF_LAUNCHED();
+                                                         h->bm_taui.p, s_dirty); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         DPF_CUDA(cudaEventRecord(h->ev_join, st2));
     }
-    if (use_tc) emit_unit_descs(h);
+    if (use_tc) emit_tc_recs(h);
     emit_units(h, use_tc);               // with the tcgen05 kernel the records only serve a batch that is not byte vectors
 
     unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(ctr + CTR_BM_STAT);
@@ -880,8 +886,8 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));        // thresholds from the second stream
         if (use_u8) {
             if (use_tc)
-                launch_score_u8t(h, cv, reinterpret_cast<const UnitDesc*>(h->bm_descs.p),
-                                 reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS_TC), flt, bm_stat);
+                launch_score_u8t(h, cv, reinterpret_cast<const TcRec*>(h->bm_descs.p),
+                                 reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS_TC), h->bm_taui.p, flt, bm_stat);
             launch_score_u8(h, cv, units, nunits_p, metric, flt, bm_stat, try_int && !use_tc);
         } else {
             dispatch_kind(kind, ang, [&](auto a, auto kc) {

@@ -40,15 +40,18 @@ struct __align__(16) UnitRec {
 };
 static_assert(sizeof(UnitRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-// The tcgen05 kernel (rerank_tc.cu) takes wider units — up to TC_TQ queries of one bucket, the N extent of its MMA —
-// and only a 16-byte descriptor per unit: its producer warps fetch the query list and the row ids themselves.
-constexpr int TC_TQ = 64;
-struct __align__(16) UnitDesc {
+// The tcgen05 kernel (rerank_tc.cu) takes other units: <= TC_TQ queries of one bucket x <= 128 of its rows (the N and M
+// extents of its MMA), one self-contained record each, streamed into shared memory ahead of use.
+constexpr int TC_TQ = 32;
+struct __align__(16) TcRec {
     uint32_t bstart;       // bucket start in ids_sorted
-    uint32_t len;          // bucket length (rows)
-    uint32_t pair0;        // first pair of the unit in the grouped pair list
+    uint32_t nrows;        // rows of this unit (1..128)
     uint32_t m;            // queries in the unit (1..TC_TQ)
+    uint32_t row0;         // first row of the unit inside the bucket (multiple of 128)
+    int32_t q[TC_TQ];      // query (index inside the chunk) of column j; slots >= m repeat the last query
+    int32_t ids[128];      // row ids; slots >= nrows repeat the last row
 };
+static_assert(sizeof(TcRec) == 16 + 4 * TC_TQ + 512, "record layout");
 
 // Threshold filter.  A batch produces ~50k (query, candidate) scores per query of which k survive.  Writing them all
 // and reading them back for the selection costs as many bytes as the byte rows themselves, so the scoring kernels
@@ -153,11 +156,11 @@ void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units, const
 // bm_group.cu: probe -> pairs grouped by leaf -> unit records, all sized on the host without reading anything back
 void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc);
 void emit_units(dpf_index* h, bool only_if_fp64_queries);
-void emit_unit_descs(dpf_index* h);                                        // second grouping width for the tcgen05 kernel
+void emit_tc_recs(dpf_index* h);                                           // the tcgen05 kernel's units
 // rerank_tc.cu
 bool score_u8t_usable(const dpf_index* h, int metric);
-void launch_score_u8t(dpf_index* h, const ChunkView& cv, const UnitDesc* descs, const uint32_t* nunits_p, const Filter& flt,
-                      unsigned long long* bm_stat);
+void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, const int32_t* taui,
+                      const Filter& flt, unsigned long long* bm_stat);
 void survivor_lists(dpf_index* h, const Filter& flt, int64_t nqc);         // offsets + scatter
 int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);
 // query.cu: exhaustive per-query top-k over the query's own buckets for the queries flagged dirty
