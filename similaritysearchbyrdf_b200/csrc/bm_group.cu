@@ -182,7 +182,8 @@ k_fill_pairs(const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__
 __global__ void __launch_bounds__(256)
 k_emit_tc_recs(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict__ unit_off, const uint32_t* __restrict__ leaf_pos,
                const int32_t* __restrict__ leaf_len, int64_t nleaves, const int32_t* __restrict__ pair_q,
-               const int32_t* __restrict__ ids_sorted, TcRec* __restrict__ recs, const int* __restrict__ q8_bad) {
+               const int32_t* __restrict__ ids_sorted, TcRec* __restrict__ recs, const int* __restrict__ q8_bad,
+               uint32_t cap /* records that fit */, uint32_t* __restrict__ dirty) {
     if (*q8_bad != 0) return;                       // a batch that is not byte vectors is scored from the UnitRecs
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -190,11 +191,16 @@ k_emit_tc_recs(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict
         const uint32_t p0 = leaf_off[leaf], p1 = leaf_off[leaf + 1];
         if (p0 == p1) continue;
         const uint32_t bstart = leaf_pos[leaf], len = (uint32_t)leaf_len[leaf];
-        TcRec* rec = recs + unit_off[leaf];
+        uint32_t u = unit_off[leaf];
+        TcRec* rec = recs + u;
         for (uint32_t p = p0; p < p1; p += TC_TQ) {
             const uint32_t m = min((uint32_t)TC_TQ, p1 - p);
             const int32_t qv = pair_q[p + min((uint32_t)lane, m - 1u)];
-            for (uint32_t r0 = 0; r0 < len; r0 += 128, ++rec) {
+            for (uint32_t r0 = 0; r0 < len; r0 += 128, ++rec, ++u) {
+                if (u >= cap) {                      // the record array is sized for any realistic batch, not for the worst
+                    dirty[qv] = 1u;                  // case: the queries of a unit that does not fit are answered exhaustively
+                    continue;
+                }
                 const uint32_t nrows = min(128u, len - r0);
                 if (lane == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(bstart, nrows, m, r0);
                 rec->q[lane] = qv;
@@ -362,14 +368,14 @@ void emit_units(dpf_index* h, bool only_if_fp64_queries) {
     DPF_CUDA(cudaGetLastError());
 }
 
-void emit_tc_recs(dpf_index* h) {
+void emit_tc_recs(dpf_index* h, int64_t cap, uint32_t* dirty) {
     StageTimer tm(h, DPF_T_EXPAND);
     const int64_t nleaves = h->num_leaves;
     if (nleaves > 0) {
         const unsigned grid = (unsigned)std::min<int64_t>((nleaves + 7) / 8, (int64_t)h->num_sms * 16);
         k_emit_tc_recs<<<grid, 256, 0, h->stream>>>(h->leaf_off.p, h->leaf_unit_off_tc.p, h->leaf_pos.p, h->leaf_len.p, nleaves,
                                                     h->pair_q.p, h->ids_sorted.p, reinterpret_cast<TcRec*>(h->bm_descs.p),
-                                                    h->counters.p + CTR_Q8_BAD); DPF_LAUNCHED();
+                                                    h->counters.p + CTR_Q8_BAD, (uint32_t)cap, dirty); DPF_LAUNCHED();
     }
     DPF_CUDA(cudaGetLastError());
 }

@@ -795,10 +795,13 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     // byte rows x byte queries, dot product: the tcgen05 kernel with its own, wider units
     const bool try_int = use_u8 && h->dbg[DPF_DBG_U8_IMMA] != 0 && (int64_t)d * 255 * 255 < (1LL << 31);
     // its units: (<= 32 pairs of a leaf) x (<= 128 of its rows); worst case from the forest's largest leaf and tile count
+    // Every probed leaf contributes one unit per 128 of its rows, plus one per further group of 32 pairs: the record
+    // array holds that with room to spare; the true worst case (every group of every leaf multiplied by the largest
+    // leaf's tile count) is never approached, and a unit that does not fit hands its queries to k_topk_direct.
     const int64_t max_tiles = std::max<int64_t>(1, (h->max_leaf_len + 127) / 128);
-    const int64_t tc_units_ub = std::min(pairs_ub * max_tiles, pairs_ub / TC_TQ * max_tiles + h->total_leaf_tiles) + 1;
-    const bool use_tc = try_int && score_u8t_usable(h, metric) && tc_units_ub * (int64_t)sizeof(TcRec) <= (2LL << 30);
-    if (use_tc) h->bm_descs.reserve((size_t)tc_units_ub * sizeof(TcRec));
+    const int64_t tc_cap = std::min(pairs_ub / TC_TQ * max_tiles + h->total_leaf_tiles, h->total_leaf_tiles + pairs_ub / 16 + 1024) + 1;
+    const bool use_tc = try_int && score_u8t_usable(h, metric) && tc_cap < (1LL << 31);
+    if (use_tc) h->bm_descs.reserve((size_t)tc_cap * sizeof(TcRec));
     h->bm_taui.reserve((size_t)nqc + 2);
     int64_t pool_cap = h->dbg[DPF_DBG_POOL_RECORDS] > 0 ? h->dbg[DPF_DBG_POOL_RECORDS]
                                                         : std::min<int64_t>(std::max<int64_t>(nqc * 2048, 1 << 20), 1LL << 28);
@@ -875,7 +878,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         DPF_CUDA(cudaGetLastError());
         DPF_CUDA(cudaEventRecord(h->ev_join, st2));
     }
-    if (use_tc) emit_tc_recs(h);
+    if (use_tc) emit_tc_recs(h, tc_cap, s_dirty);
     emit_units(h, use_tc);               // with the tcgen05 kernel the records only serve a batch that is not byte vectors
 
     unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(ctr + CTR_BM_STAT);
@@ -887,7 +890,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         if (use_u8) {
             if (use_tc)
                 launch_score_u8t(h, cv, reinterpret_cast<const TcRec*>(h->bm_descs.p),
-                                 reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS_TC), h->bm_taui.p, flt, bm_stat);
+                                 reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS_TC), tc_cap, h->bm_taui.p, flt, bm_stat);
             launch_score_u8(h, cv, units, nunits_p, metric, flt, bm_stat, try_int && !use_tc);
         } else {
             dispatch_kind(kind, ang, [&](auto a, auto kc) {

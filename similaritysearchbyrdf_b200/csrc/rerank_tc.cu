@@ -121,8 +121,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: multiple of 16, <= 128 */,
             const unsigned char* __restrict__ Q8 /* pitch 128, zero padded */, const int* __restrict__ q8_bad,
-            const TcRec* __restrict__ recs, const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ taui, Filter flt,
-            unsigned long long* __restrict__ stat) {
+            const TcRec* __restrict__ recs, const uint32_t* __restrict__ nunits_p, uint32_t cap, const int32_t* __restrict__ taui,
+            Filter flt, unsigned long long* __restrict__ stat) {
     using namespace tc;
     if (*q8_bad != 0) return;                    // some query is not a byte vector: k_score_u8d scores the batch
     extern __shared__ unsigned char tc_smem_raw[];
@@ -135,7 +135,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     TcRec* ring = reinterpret_cast<TcRec*>(base + (size_t)TC_S * TC_STAGE_BYTES);   // TC_R unit records
     int* epi_tau = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ring) + (size_t)TC_R * sizeof(TcRec));   // per epilogue warp: taui[TQ]
 
-    const int64_t nunits = *nunits_p;
+    const int64_t nunits = min(*nunits_p, cap);
     const int64_t G = gridDim.x;
     const int64_t nmine = nunits > blockIdx.x ? (nunits - blockIdx.x + G - 1) / G : 0;   // units blockIdx.x + k G
     // rows narrower than 128 bytes: the chunks beyond the row are never copied and must read as zero
@@ -327,11 +327,11 @@ bool score_u8t_usable(const dpf_index* h, int metric) {
     return sel == 0 || sel == 3;
 }
 
-void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, const int32_t* taui,
+void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, int64_t cap, const int32_t* taui,
                       const Filter& flt, unsigned long long* bm_stat) {
     DPF_CUDA(cudaFuncSetAttribute(k_score_u8t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    k_score_u8t<<<h->num_sms, TC_THREADS, TC_SMEM, h->stream>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, cv.Q8, cv.q8_bad, recs, nunits_p, taui,
-                                                               flt, bm_stat);
+    k_score_u8t<<<h->num_sms, TC_THREADS, TC_SMEM, h->stream>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, cv.Q8, cv.q8_bad, recs, nunits_p, (uint32_t)cap,
+                                                               taui, flt, bm_stat);
     DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }

@@ -156,10 +156,10 @@ void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units, const
 // bm_group.cu: probe -> pairs grouped by leaf -> unit records, all sized on the host without reading anything back
 void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc);
 void emit_units(dpf_index* h, bool only_if_fp64_queries);
-void emit_tc_recs(dpf_index* h);                                           // the tcgen05 kernel's units
+void emit_tc_recs(dpf_index* h, int64_t cap, uint32_t* dirty);                                           // the tcgen05 kernel's units
 // rerank_tc.cu
 bool score_u8t_usable(const dpf_index* h, int metric);
-void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, const int32_t* taui,
+void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, int64_t cap, const int32_t* taui,
                       const Filter& flt, unsigned long long* bm_stat);
 void survivor_lists(dpf_index* h, const Filter& flt, int64_t nqc);         // offsets + scatter
 int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);
