@@ -10,16 +10,16 @@
 //
 // A unit here = <= 128 rows of one bucket x <= 32 of the queries that probe it, described by one self-contained record
 // (k_emit_tc_recs: header, query list, row ids).  One persistent CTA per SM, four roles connected by mbarrier rings:
-//   record loader (1 warp) streams the CTA's unit records into a ring of TC_R slots with cp.async, TC_LR - 1 units ahead
-//                         of the arrival that publishes them — every index the other roles need is in shared memory
+//   record loader (1 warp) streams the CTA's unit records into a ring of TC_R slots with cp.async, as far ahead as the
+//                         ring allows — every index the other roles need is in shared memory
 //                         long before they need it (the first version fetched descriptors, query lists and row ids with
 //                         ordinary loads one unit ahead and spent 1.5 us per unit waiting for them)
 //   row producers (4 warps) gather the unit's rows by id from the byte store into shared memory in the UMMA K-major
 //                         128-byte-swizzle layout: a row is 128 bytes = one swizzle row, thread (row group, chunk c)
 //                         copies the 16-byte chunks c of 8 rows with cp.async to chunk position c ^ (row & 7); the unit's
-//                         queries (rows of the byte copy of the batch) go behind them the same way; TC_S stages, TC_D - 1
-//                         in flight per thread.  A thread waits for its own copies of a stage (cp.async.wait_group),
-//                         fences them towards the async proxy and arrives on the stage's mbarrier.
+//                         queries (rows of the byte copy of the batch) go behind them the same way; TC_S stages, all of
+//                         them in flight; the stage's mbarrier gets a thread's arrival when its copies have landed
+//                         (cp.async.mbarrier.arrive), so nobody waits for data it does not need yet.
 //   MMA issuer (1 thread) waits for a stage, issues <= 4 tcgen05.mma (K = 32 bytes each) into one of TC_NACC accumulator
 //                         stages of tensor memory (128 lanes = rows, <= 32 columns = queries), and commits the stage's
 //                         shared memory back to the producers and the accumulator to the epilogue (tcgen05.commit).
@@ -31,10 +31,8 @@
 namespace dpf {
 
 constexpr int TC_ROWS = 128;                      // rows per unit = UMMA M
-constexpr int TC_S = 8;                           // stage ring: a unit's rows (16 KB) + its queries (4 KB)
-constexpr int TC_D = 7;                           // cp.async groups a producer thread keeps in flight (< TC_S)
-constexpr int TC_R = 32;                          // unit-record ring (loader -> producers -> MMA -> epilogue)
-constexpr int TC_LR = 8;                          // record copies the loader keeps in flight
+constexpr int TC_S = 8;                           // stage ring: a unit's rows (16 KB) + its queries (4 KB), all of them in flight
+constexpr int TC_R = 32;                          // unit-record ring (loader -> producers -> epilogue)
 constexpr int TC_P = 4;                           // units ahead the epilogue requests its thresholds
 constexpr int TC_NACC = 8;                        // accumulator stages
 constexpr int TC_TMEM_COLS = TC_NACC * TC_TQ;     // 256 of the 512 columns
@@ -43,7 +41,7 @@ constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;
 constexpr int TC_A_BYTES = TC_ROWS * 128, TC_B_BYTES = TC_TQ * 128, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr size_t TC_SMEM = 1024 /* alignment slack */ + (size_t)TC_S * TC_STAGE_BYTES + (size_t)TC_R * sizeof(TcRec) +
                            (size_t)TC_EPI_WARPS * TC_TQ * 4 + 256;
-static_assert(TC_D < TC_S && TC_LR + TC_D + TC_NACC + TC_P + 2 <= TC_R, "ring depths");
+static_assert(TC_S + TC_NACC + TC_P + 2 <= TC_R, "ring depths");
 static_assert(TC_TQ == 32, "one threshold per epilogue lane, two column groups, two query rows per producer thread");
 static_assert(TC_STAGE_BYTES % 1024 == 0 && sizeof(TcRec) % 16 == 0, "swizzle atoms / 16-byte record chunks");
 static_assert((TC_TMEM_COLS & (TC_TMEM_COLS - 1)) == 0 && TC_TMEM_COLS >= 32 && TC_TMEM_COLS <= 512, "tensor memory is allocated in powers of two");
@@ -82,6 +80,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int ta
             return false;
         }
     }
+}
+// the mbarrier gets one arrival from this thread when all its cp.async issued so far have landed (.noinc: the arrival
+// is one of the barrier's expected count, not an extra one)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -231,14 +234,15 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         if (lane == 0) {
             for (int64_t k = 0; k < nmine && !s_abort; ++k) {
                 const int s = (int)(k % TC_S), a = (int)(k % TC_NACC);
-                if (!mbar_wait(&rec_full[k % TC_R], (unsigned)((k / TC_R) & 1), 6, &s_abort)) break;
-                const uint32_t m = ring[k % TC_R].m;
                 if (!mbar_wait(&a_full[s], (unsigned)((k / TC_S) & 1), 1, &s_abort)) break;
                 if (k >= TC_NACC && !mbar_wait(&acc_empty[a], (unsigned)(((k / TC_NACC) - 1) & 1), 2, &s_abort)) break;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the producers' cp.async writes -> the tensor core's reads
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
                 const uint64_t adesc = smem_desc_sw128(sbase), bdesc = smem_desc_sw128(sbase + TC_A_BYTES);
-                const uint32_t idesc = idesc_u8((int)((m + 15) & ~15u));
+                // N = TC_TQ always: the columns past the unit's queries multiply whatever the stage held before and are
+                // never read (the issuer then needs nothing from the unit's record)
+                const uint32_t idesc = idesc_u8(TC_TQ);
                 for (int kk = 0; kk < nk; ++kk)                           // + 32 bytes along K = + 2 in the 16-byte address field
                     umma_i8(tmem_base + (uint32_t)(a * TC_TQ), adesc + 2 * kk, bdesc + 2 * kk, idesc, kk > 0 ? 1u : 0u);
                 umma_commit(&a_empty[s]);                                 // the stage's shared memory, back to the producers
@@ -247,8 +251,8 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         }
     } else if (warp == TC_EPI_WARPS + 1) {
         // ================================ record loader ===================================================================
-        // unit records stream into the ring with cp.async, TC_LR - 1 units ahead of the arrival that publishes them:
-        // nothing downstream ever waits for a global load of an index
+        // unit records stream into the ring with cp.async as far ahead as the ring allows (its slots are freed by the
+        // epilogue): nothing downstream ever waits for a global load of an index
         constexpr int CH = (int)(sizeof(TcRec) / 16);
         static_assert(CH > 32 && CH <= 64, "two chunks per lane at most");
         int64_t k = 0;
@@ -259,14 +263,9 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
             const uint32_t dst = smem_u32(&ring[slot]);
             cp16(dst + 16 * lane, src + 16 * lane);
             if (lane + 32 < CH) cp16(dst + 16 * (lane + 32), src + 16 * (lane + 32));
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (k >= TC_LR - 1) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(TC_LR - 1) : "memory");
-                mbar_arrive(&rec_full[(k - (TC_LR - 1)) % TC_R]);
-            }
+            cp_async_arrive(&rec_full[slot]);                             // published the moment the copies land
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        for (int64_t kk = k > TC_LR - 1 ? k - (TC_LR - 1) : 0; kk < k; ++kk) mbar_arrive(&rec_full[kk % TC_R]);
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ================================ row producers ===================================================================
         const int p = tid - (TC_EPI_WARPS + 2) * 32;                      // 0 .. 127
@@ -295,16 +294,12 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
             // the unit's queries: rows rg and rg + 16 of the B operand (N = m rounded up to 16)
             if ((uint32_t)rg < ((m + 15) & ~15u)) cp16(sa + TC_A_BYTES, qsrc + (size_t)q0 * 128);
             if ((uint32_t)(rg + 16) < ((m + 15) & ~15u)) cp16(sa + TC_A_BYTES + 2048u, qsrc + (size_t)q1 * 128);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (k >= TC_D - 1) {                                          // unit k - (TC_D - 1): this thread's copies have landed
-                asm volatile("cp.async.wait_group %0;" ::"n"(TC_D - 1) : "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&a_full[(k - (TC_D - 1)) % TC_S]);
-            }
+            // the stage is published when this thread's copies have landed; all TC_S stages can be in flight, and the
+            // producer never waits for its own data (an arrival that lags the copies would leave the MMA -> a_empty loop
+            // only TC_S - lag stages of slack: the first version ran at one memory latency per unit because of that)
+            cp_async_arrive(&a_full[s]);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int64_t kk = k > TC_D - 1 ? k - (TC_D - 1) : 0; kk < k; ++kk) mbar_arrive(&a_full[kk % TC_S]);
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     // ---- teardown: everything issued has been consumed (the epilogue waited for every accumulator) ------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
