@@ -224,7 +224,8 @@ int dpf_stats(dpf_handle h, int64_t* stats_out /* DPF_STAT_COUNT */, double* occ
 /* watchdog record of the tcgen05 scoring kernel: all zero unless some role of some CTA waited ~1 s for a barrier
  * ([0] = first barrier tag << 32 | CTA, [1..5] = time-outs per barrier: tile full, accumulator empty, accumulator
  * full, tile empty, operand empty) */
-int dpf_debug_tc_diag(dpf_handle h, uint64_t* out8);
+int dpf_debug_tc_diag(dpf_handle h, uint64_t* out24 /* 8 watchdog words, then 16 cycle counters: [8 + tag] = cycles
+                                                          warps spent waiting on that barrier, [23] = kernel cycles x CTAs */);
 int dpf_debug_leaf_pairs(dpf_handle h, int64_t* nleaves_out, uint32_t* pair_off_out, int32_t* leaf_len_out);
 
 /* per-stage device times of the last fit / query call, measured with CUDA events on the handle's stream */

@@ -1023,9 +1023,9 @@ int dpf_debug_tc_diag(dpf_handle h, uint64_t* out8) {
     return guarded(h, [&] {
         DPF_REQUIRE(out8, DPF_ERR_INVALID, "null buffer");
         DPF_CUDA(cudaStreamSynchronize(h->stream));
-        unsigned long long v[8];
+        unsigned long long v[24];
         tc_diag_read(v);
-        for (int i = 0; i < 8; ++i) out8[i] = v[i];
+        for (int i = 0; i < 24; ++i) out8[i] = v[i];
     });
 }
 

@@ -596,6 +596,7 @@ k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys
                   const int* __restrict__ tl_cnt, double* __restrict__ tau, int32_t* __restrict__ taui, uint32_t* __restrict__ dirty) {
     const int lane = threadIdx.x & 31;
     const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) taui[nqc] = 0x7fffffff;      // sentinel: "no query" for the tcgen05 kernel's padding
     if (ql >= nqc) return;
     const int64_t q = ql;
     const double* lkeys = tl_keys + (ql * NT + lane) * K;

@@ -23,9 +23,9 @@
 //   MMA issuer (1 thread) waits for a stage, issues <= 4 tcgen05.mma (K = 32 bytes each) into one of TC_NACC accumulator
 //                         stages of tensor memory (128 lanes = rows, <= 32 columns = queries), and commits the stage's
 //                         shared memory back to the producers and the accumulator to the epilogue (tcgen05.commit).
-//   epilogue (8 warps)    tcgen05.ld the accumulator (warp w reads lanes 32 (w % 4) .., the two warps of a lane quarter
-//                         take 16 columns each), compare with the integer thresholds of the unit's queries (requested
-//                         TC_P units ahead, one per lane), push the few survivors, and free the unit's record.
+//   epilogue (16 warps)   four sets of four warps take the units round-robin: tcgen05.ld the accumulator (warp w reads
+//                         lanes 32 (w % 4) .., all 32 columns), compare with the integer thresholds of the unit's queries
+//                         (gathered next to the record by the loader), push the few survivors, free the unit's record.
 #include "rerank_units.cuh"
 
 namespace dpf {
@@ -33,16 +33,20 @@ namespace dpf {
 constexpr int TC_ROWS = 128;                      // rows per unit = UMMA M
 constexpr int TC_S = 8;                           // stage ring: a unit's rows (16 KB) + its queries (4 KB), all of them in flight
 constexpr int TC_R = 32;                          // unit-record ring (loader -> producers -> epilogue)
-constexpr int TC_P = 4;                           // units ahead the epilogue requests its thresholds
+constexpr int TC_TL = 6;                          // units the threshold gather trails the record copy by
 constexpr int TC_NACC = 8;                        // accumulator stages
 constexpr int TC_TMEM_COLS = TC_NACC * TC_TQ;     // 256 of the 512 columns
-constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 4;
+constexpr int TC_EPI_SETS = 4;                    // epilogue warp sets; set j takes the units k = j (mod 4) of the CTA
+constexpr int TC_EPI_WARPS = 4 * TC_EPI_SETS, TC_PROD_WARPS = 4;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;
 constexpr int TC_A_BYTES = TC_ROWS * 128, TC_B_BYTES = TC_TQ * 128, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr size_t TC_SMEM = 1024 /* alignment slack */ + (size_t)TC_S * TC_STAGE_BYTES + (size_t)TC_R * sizeof(TcRec) +
-                           (size_t)TC_EPI_WARPS * TC_TQ * 4 + 256;
-static_assert(TC_S + TC_NACC + TC_P + 2 <= TC_R, "ring depths");
-static_assert(TC_TQ == 32, "one threshold per epilogue lane, two column groups, two query rows per producer thread");
+struct __align__(16) TcSlot {                     // a unit's record in shared memory + the thresholds of its queries
+    TcRec rec;
+    int32_t tau[TC_TQ];
+};
+constexpr size_t TC_SMEM = 1024 /* alignment slack */ + (size_t)TC_S * TC_STAGE_BYTES + (size_t)TC_R * sizeof(TcSlot) + 256;
+static_assert(TC_S + TC_NACC + TC_TL + TC_EPI_SETS + 2 <= TC_R, "ring depths");
+static_assert(TC_TQ == 32, "one threshold per loader lane, one tcgen05.ld.x32 per epilogue warp, two query rows per producer thread");
 static_assert(TC_STAGE_BYTES % 1024 == 0 && sizeof(TcRec) % 16 == 0, "swizzle atoms / 16-byte record chunks");
 static_assert((TC_TMEM_COLS & (TC_TMEM_COLS - 1)) == 0 && TC_TMEM_COLS >= 32 && TC_TMEM_COLS <= 512, "tensor memory is allocated in powers of two");
 
@@ -58,8 +62,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // happens in a correct run) records which barrier it was in g_tc_diag, raises the CTA's abort flag and every role of
 // the CTA leaves its loops, so a bug shows up as a wrong result and a non-zero dpf_debug_tc_diag, not as a hung GPU.
 __device__ unsigned long long g_tc_diag[8];
+// cycles spent waiting, per barrier tag (lane 0 of every warp), and [15] = cycles of the kernel summed over CTAs:
+// which role is the bottleneck is the one that does not wait (dpf_debug_tc_diag returns these after the watchdog words)
+__device__ unsigned long long g_tc_prof[16];
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int tag, volatile int* abort_flag) {
     const long long t0 = clock64();
+    struct Acc {
+        long long t0; int tag;
+        __device__ ~Acc() { if ((threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[tag], (unsigned long long)(clock64() - t0)); }
+    } acc{t0, tag};
     for (;;) {
         unsigned ok;
         asm volatile(
@@ -111,6 +122,20 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -124,19 +149,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: multiple of 16, <= 128 */,
             const unsigned char* __restrict__ Q8 /* pitch 128, zero padded */, const int* __restrict__ q8_bad,
-            const TcRec* __restrict__ recs, const uint32_t* __restrict__ nunits_p, uint32_t cap, const int32_t* __restrict__ taui,
-            Filter flt, unsigned long long* __restrict__ stat) {
+            const TcRec* __restrict__ recs, const uint32_t* __restrict__ nunits_p, uint32_t cap,
+            const int32_t* __restrict__ taui /* per query, [tau_sentinel] = INT_MAX */, int tau_sentinel, Filter flt,
+            unsigned long long* __restrict__ stat) {
     using namespace tc;
     if (*q8_bad != 0) return;                    // some query is not a byte vector: k_score_u8d scores the batch
     extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ uint64_t rec_full[TC_R], rec_empty[TC_R], a_full[TC_S], a_empty[TC_S], acc_full[TC_NACC], acc_empty[TC_NACC];
+    __shared__ uint64_t rec_full[TC_R], tau_full[TC_R], rec_empty[TC_R], a_full[TC_S], a_empty[TC_S], acc_full[TC_NACC], acc_empty[TC_NACC];
     __shared__ uint32_t s_tmem;
     __shared__ int s_abort;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* stages = base;                                          // TC_S x (16 KB rows + 4 KB queries), 1024-byte aligned
-    TcRec* ring = reinterpret_cast<TcRec*>(base + (size_t)TC_S * TC_STAGE_BYTES);   // TC_R unit records
-    int* epi_tau = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ring) + (size_t)TC_R * sizeof(TcRec));   // per epilogue warp: taui[TQ]
+    TcSlot* ring = reinterpret_cast<TcSlot*>(base + (size_t)TC_S * TC_STAGE_BYTES);  // TC_R unit records + thresholds
 
     const int64_t nunits = min(*nunits_p, cap);
     const int64_t G = gridDim.x;
@@ -145,9 +170,9 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     for (int i = tid; i < TC_S * TC_STAGE_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         s_abort = 0;
-        for (int i = 0; i < TC_R; ++i) { mbar_init(&rec_full[i], 32); mbar_init(&rec_empty[i], TC_EPI_WARPS); }
+        for (int i = 0; i < TC_R; ++i) { mbar_init(&rec_full[i], 32); mbar_init(&tau_full[i], 32); mbar_init(&rec_empty[i], 4); }
         for (int i = 0; i < TC_S; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS * 32); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TC_EPI_WARPS); }
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                             // tensor memory: allocated and released by warp 0
@@ -159,76 +184,51 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
+    const long long t_start = clock64();
     const int nk = (int)((pitch + 31) / 32);                               // K steps of 32 bytes that hold data
 
     if (warp < TC_EPI_WARPS) {
         // ================================ epilogue ========================================================================
-        const int quarter = warp & 3, half = warp >> 2;                   // TMEM lane quarter, column group
-        int* my_tau = epi_tau + warp * TC_TQ;
+        // A unit's epilogue is a chain of dependent long-latency steps (barrier check, TMEM load, threshold compare) that one
+        // warp cannot overlap with itself — measured ~2400 cycles per unit — so TC_EPI_SETS sets of 4 warps take the CTA's
+        // units round-robin; warp (set, quarter) reads TMEM lanes 32 quarter .. of the units k = set (mod TC_EPI_SETS).
+        const int quarter = warp & 3, set = warp >> 2;
         SurvivorSink sink;
         unsigned long long rows_scored = 0;
-        // thresholds of the queries of unit k + j (lane = column), requested TC_P units ahead from the record ring
-        int tq[TC_P], qq[TC_P];
-#pragma unroll
-        for (int j = 0; j < TC_P; ++j) { tq[j] = 0x7fffffff; qq[j] = 0; }
-        auto request = [&](int64_t k, int& t_out, int& q_out) {
-            t_out = 0x7fffffff; q_out = 0;
-            if (k >= nmine) return true;
-            if (!mbar_wait(&rec_full[k % TC_R], (unsigned)((k / TC_R) & 1), 6, &s_abort)) return false;
-            const TcRec* r = &ring[k % TC_R];
-            q_out = r->q[lane];
-            if ((uint32_t)lane < r->m) t_out = __ldg(taui + q_out);      // slots >= m stay masked (INT_MAX)
-            return true;
-        };
-        bool ok = true;
-#pragma unroll
-        for (int j = 0; j < TC_P; ++j) ok = ok && request(j, tq[j], qq[j]);
-        for (int64_t k = 0; k < nmine && ok && !s_abort; ++k) {
-            const TcRec* r = &ring[k % TC_R];
-            const uint32_t bstart = r->bstart, nrows = r->nrows, m = r->m, row0 = r->row0;
-            const int my_q = qq[0];
-            __syncwarp();                                                 // the previous unit's thresholds have been read
-            my_tau[lane] = tq[0];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j + 1 < TC_P; ++j) { tq[j] = tq[j + 1]; qq[j] = qq[j + 1]; }
-            ok = request(k + TC_P, tq[TC_P - 1], qq[TC_P - 1]);
-            if (!ok) break;
-            const int a = (int)(k % TC_NACC);
+        for (int64_t k = set; k < nmine && !s_abort; k += TC_EPI_SETS) {
+            const int slot = (int)(k % TC_R), a = (int)(k % TC_NACC);
+            if (!mbar_wait(&tau_full[slot], (unsigned)((k / TC_R) & 1), 6, &s_abort)) break;   // record and thresholds are in
+            const TcSlot* r = &ring[slot];
+            const uint32_t bstart = r->rec.bstart, nrows = r->rec.nrows, row0 = r->rec.row0;
             if (!mbar_wait(&acc_full[a], (unsigned)((k / TC_NACC) & 1), 3, &s_abort)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = 32 * quarter + lane;
             const bool valid = (uint32_t)row < nrows;
             const uint32_t pos = bstart + row0 + (uint32_t)row;
-            int v[16];
-            const bool mine = (uint32_t)(16 * half) < m;                  // warp-uniform: this warp's column group is in use
-            if (mine) tmem_ld16(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * TC_TQ + 16 * half), v);
+            int v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(a * TC_TQ), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);                   // the accumulator stage is free again
-            if (mine) {
-                bool any = false;
+            bool any = false;                                            // columns past the unit's queries carry INT_MAX
 #pragma unroll
-                for (int jj = 0; jj < 16; jj += 4) {
-                    const int4 t4 = *reinterpret_cast<const int4*>(my_tau + 16 * half + jj);
-                    any |= v[jj] >= t4.x || v[jj + 1] >= t4.y || v[jj + 2] >= t4.z || v[jj + 3] >= t4.w;
-                }
-                // survivors cluster in the few buckets near a query: most tiles have none
-                if (__any_sync(0xffffffffu, any && valid)) {
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int qj = __shfl_sync(0xffffffffu, my_q, 16 * half + jj);
-                        sink.push(flt, valid && v[jj] >= my_tau[16 * half + jj], qj, pos, (double)v[jj], lane);
-                    }
-                }
+            for (int jj = 0; jj < 32; jj += 4) {
+                const int4 t4 = *reinterpret_cast<const int4*>(r->tau + jj);
+                any |= v[jj] >= t4.x || v[jj + 1] >= t4.y || v[jj + 2] >= t4.z || v[jj + 3] >= t4.w;
             }
-            if (quarter == 0 && half == 0) rows_scored += nrows;
+            // survivors cluster in the few buckets near a query: most units have none
+            if (__any_sync(0xffffffffu, any && valid)) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj)
+                    sink.push(flt, valid && v[jj] >= r->tau[jj], r->rec.q[jj], pos, (double)v[jj], lane);
+            }
+            if (quarter == 0) rows_scored += nrows;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&rec_empty[k % TC_R]);            // the last reader of the unit's record
+            if (lane == 0) mbar_arrive(&rec_empty[slot]);                // the last readers of the unit's record
         }
         sink.flush(flt, lane);
-        if (lane == 0 && quarter == 0 && half == 0) { atomicAdd(&stat[0], (unsigned long long)nmine); atomicAdd(&stat[1], rows_scored); }
+        if (lane == 0 && quarter == 0) { atomicAdd(&stat[0], (unsigned long long)((nmine + TC_EPI_SETS - 1 - set) / TC_EPI_SETS)); atomicAdd(&stat[1], rows_scored); }
     } else if (warp == TC_EPI_WARPS) {
         // ================================ MMA issuer ======================================================================
         if (lane == 0) {
@@ -252,19 +252,33 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     } else if (warp == TC_EPI_WARPS + 1) {
         // ================================ record loader ===================================================================
         // unit records stream into the ring with cp.async as far ahead as the ring allows (its slots are freed by the
-        // epilogue): nothing downstream ever waits for a global load of an index
+        // epilogue); TC_TL units behind, lane j gathers the integer threshold of the unit's query j next to the record
+        // (4-byte cp.async; slots past the unit's queries take the sentinel INT_MAX at taui[nq]).  Nothing downstream ever
+        // waits for a global load of an index or a threshold.
         constexpr int CH = (int)(sizeof(TcRec) / 16);
         static_assert(CH > 32 && CH <= 64, "two chunks per lane at most");
+        auto gather_tau = [&](int64_t k) {
+            const int slot = (int)(k % TC_R);
+            if (!mbar_wait(&rec_full[slot], (unsigned)((k / TC_R) & 1), 6, &s_abort)) return false;
+            const TcSlot* r = &ring[slot];
+            const int qj = (uint32_t)lane < r->rec.m ? r->rec.q[lane] : tau_sentinel;
+            cp4(smem_u32(&ring[slot].tau[lane]), taui + qj);
+            cp_async_arrive(&tau_full[slot]);
+            return true;
+        };
         int64_t k = 0;
         for (; k < nmine && !s_abort; ++k) {
             const int slot = (int)(k % TC_R);
             if (k >= TC_R && !mbar_wait(&rec_empty[slot], (unsigned)(((k / TC_R) - 1) & 1), 7, &s_abort)) break;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(recs + (blockIdx.x + k * G));
-            const uint32_t dst = smem_u32(&ring[slot]);
+            const uint32_t dst = smem_u32(&ring[slot].rec);
             cp16(dst + 16 * lane, src + 16 * lane);
             if (lane + 32 < CH) cp16(dst + 16 * (lane + 32), src + 16 * (lane + 32));
             cp_async_arrive(&rec_full[slot]);                             // published the moment the copies land
+            if (k >= TC_TL && !gather_tau(k - TC_TL)) break;
         }
+        for (int64_t kk = k > TC_TL ? k - TC_TL : 0; kk < k && !s_abort; ++kk)
+            if (!gather_tau(kk)) break;
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ================================ row producers ===================================================================
@@ -278,7 +292,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         int64_t k = 0;
         for (; k < nmine && !s_abort; ++k) {
             if (!mbar_wait(&rec_full[k % TC_R], (unsigned)((k / TC_R) & 1), 6, &s_abort)) break;
-            const TcRec* r = &ring[k % TC_R];
+            const TcRec* r = &ring[k % TC_R].rec;
             int id[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) id[i] = r->ids[rg + 16 * i];
@@ -301,6 +315,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    if (tid == 0) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - t_start));
     // ---- teardown: everything issued has been consumed (the epilogue waited for every accumulator) ------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -310,8 +325,9 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     }
 }
 
-void tc_diag_read(unsigned long long* out8) {
-    DPF_CUDA(cudaMemcpyFromSymbol(out8, tc::g_tc_diag, 8 * sizeof(unsigned long long)));
+void tc_diag_read(unsigned long long* out24) {
+    DPF_CUDA(cudaMemcpyFromSymbol(out24, tc::g_tc_diag, 8 * sizeof(unsigned long long)));
+    DPF_CUDA(cudaMemcpyFromSymbol(out24 + 8, tc::g_tc_prof, 16 * sizeof(unsigned long long)));
 }
 
 bool score_u8t_usable(const dpf_index* h, int metric) {
@@ -326,7 +342,7 @@ void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, cons
                       const Filter& flt, unsigned long long* bm_stat) {
     DPF_CUDA(cudaFuncSetAttribute(k_score_u8t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     k_score_u8t<<<h->num_sms, TC_THREADS, TC_SMEM, h->stream>>>(h->Xc.p, (unsigned)h->Xc_row_bytes, cv.Q8, cv.q8_bad, recs, nunits_p, (uint32_t)cap,
-                                                               taui, flt, bm_stat);
+                                                               taui, (int)cv.nqc, flt, bm_stat);
     DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }

@@ -301,7 +301,7 @@ class DPFIndex:
 
     def tc_diag(self):
         """Watchdog record of the tcgen05 scoring kernel (all zero in a correct run)."""
-        out = np.zeros(8, np.uint64)
+        out = np.zeros(24, np.uint64)
         self._ck(self.lib.dpf_debug_tc_diag(self.h, _p(out)))
         return out
 

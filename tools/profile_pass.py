@@ -36,6 +36,10 @@ for _ in range(a.repeat + 1):
           "cand/q", st["last_candidates"] / a.nq, "dups/q", st["last_cand_with_dups"] / a.nq,
           "bm pairs", st["bm_pairs"], "runs", st["bm_runs"], "rows staged", st["bm_rows_staged"], "survivors/q", st["bm_survivors"] / a.nq)
 
+d = ix.tc_diag()
+print("tc watchdog", d[:8].tolist())
+print("tc wait cycles by barrier tag (1 a_full@mma 2 acc_empty@mma 3 acc_full@epi 4 a_empty@prod 6 rec_full 7 rec_empty@loader), kernel cycles x CTAs:",
+      d[8:].tolist())
 # how many bucket rows a batch stages as a function of the unit width (queries scored per pass over a bucket)
 off, ln = ix.leaf_pairs()
 cnt = np.diff(off.astype(np.int64))

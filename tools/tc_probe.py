@@ -16,7 +16,7 @@ with ix.debug_options(u8i_kernel=2):
     ref = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
 print("ring ok", ix.stats()["bm_survivors"], flush=True)
 got = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
-print("tc diag", ix.tc_diag().tolist(), "stats", {k: v for k, v in ix.stats().items() if k.startswith("bm_")}, flush=True)
+print("tc diag", ix.tc_diag()[:8].tolist(), "stats", {k: v for k, v in ix.stats().items() if k.startswith("bm_")}, flush=True)
 print("ids equal", float((ref[0] == got[0]).mean()), "scores equal", float((ref[1] == got[1]).mean()))
 bad = np.nonzero((ref[0] != got[0]).any(axis=1))[0]
 print("bad queries", len(bad), bad[:10].tolist())
