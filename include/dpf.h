@@ -244,8 +244,8 @@ enum {
     DPF_DBG_RERANK = 0,       /* 0 bucket-major when supported (default), 1 always the row-major kernel              */
     DPF_DBG_BM_KERNEL = 1,    /* 0 default, 1 the TMA-ring FP64 kernel (k_score_stream) even on byte rows             */
     DPF_DBG_U8_IMMA = 2,      /* 1 default: integer tensor pipe on byte rows x byte queries; 0: FP64 tensor pipe      */
-    DPF_DBG_U8I_KERNEL = 3,   /* 0 default (tcgen05 when the shape allows, else mma.sync ring), 1 lean register
-                                 gather, 2 mma.sync cp.async ring, 3 tcgen05                                          */
+    DPF_DBG_U8I_KERNEL = 3,   /* byte rows x byte queries: 0 default (mma.sync, cp.async ring), 1 lean register gather,
+                                 2 = 0, 3 tcgen05 / TMEM kernel (dot product)                                         */
     DPF_DBG_TAU_TABLES = 4,   /* threshold samples per query; 0 = default                                             */
     DPF_DBG_TAU_KERNEL = 5,   /* 0 default (tensor pipe), 1 CUDA-core DP4A / FMA form                                 */
     DPF_DBG_HASH_EXACT = 6,   /* 1: angle keys from the reference-order CUDA-core kernel instead of DMMA + fix-up     */

@@ -65,12 +65,20 @@ __device__ unsigned long long g_tc_diag[8];
 // cycles spent waiting, per barrier tag (lane 0 of every warp), and [15] = cycles of the kernel summed over CTAs:
 // which role is the bottleneck is the one that does not wait (dpf_debug_tc_diag returns these after the watchdog words)
 __device__ unsigned long long g_tc_prof[16];
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int tag, volatile int* abort_flag) {
+struct WaitClock {                       // per-thread wait cycles by barrier tag; lane 0 of a warp reports them once, at the end
+    long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    __device__ void report() {
+        if ((threadIdx.x & 31) == 0)
+            for (int i = 0; i < 8; ++i)
+                if (c[i]) atomicAdd(&g_tc_prof[i], (unsigned long long)c[i]);
+    }
+};
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int tag, volatile int* abort_flag, WaitClock& wc) {
     const long long t0 = clock64();
     struct Acc {
-        long long t0; int tag;
-        __device__ ~Acc() { if ((threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[tag], (unsigned long long)(clock64() - t0)); }
-    } acc{t0, tag};
+        long long t0; long long& dst;
+        __device__ ~Acc() { dst += clock64() - t0; }
+    } acc{t0, wc.c[tag]};
     for (;;) {
         unsigned ok;
         asm volatile(
@@ -185,6 +193,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
     const long long t_start = clock64();
+    WaitClock wc;
     const int nk = (int)((pitch + 31) / 32);                               // K steps of 32 bytes that hold data
 
     if (warp < TC_EPI_WARPS) {
@@ -197,10 +206,10 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         unsigned long long rows_scored = 0;
         for (int64_t k = set; k < nmine && !s_abort; k += TC_EPI_SETS) {
             const int slot = (int)(k % TC_R), a = (int)(k % TC_NACC);
-            if (!mbar_wait(&tau_full[slot], (unsigned)((k / TC_R) & 1), 6, &s_abort)) break;   // record and thresholds are in
+            if (!mbar_wait(&tau_full[slot], (unsigned)((k / TC_R) & 1), 6, &s_abort, wc)) break;   // record and thresholds are in
             const TcSlot* r = &ring[slot];
             const uint32_t bstart = r->rec.bstart, nrows = r->rec.nrows, row0 = r->rec.row0;
-            if (!mbar_wait(&acc_full[a], (unsigned)((k / TC_NACC) & 1), 3, &s_abort)) break;
+            if (!mbar_wait(&acc_full[a], (unsigned)((k / TC_NACC) & 1), 3, &s_abort, wc)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = 32 * quarter + lane;
             const bool valid = (uint32_t)row < nrows;
@@ -234,9 +243,11 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         if (lane == 0) {
             for (int64_t k = 0; k < nmine && !s_abort; ++k) {
                 const int s = (int)(k % TC_S), a = (int)(k % TC_NACC);
-                if (!mbar_wait(&a_full[s], (unsigned)((k / TC_S) & 1), 1, &s_abort)) break;
-                if (k >= TC_NACC && !mbar_wait(&acc_empty[a], (unsigned)(((k / TC_NACC) - 1) & 1), 2, &s_abort)) break;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the producers' cp.async writes -> the tensor core's reads
+                if (!mbar_wait(&a_full[s], (unsigned)((k / TC_S) & 1), 1, &s_abort, wc)) break;
+                if (k >= TC_NACC && !mbar_wait(&acc_empty[a], (unsigned)(((k / TC_NACC) - 1) & 1), 2, &s_abort, wc)) break;
+                // (no proxy fence between the producers' cp.async writes and the tensor core's reads: the stage's mbarrier
+                // completes when the copies have landed — the same protocol as CUTLASS's sm100 cp.async mainloop; the
+                // full-batch bit-exactness tests against the mma.sync kernels guard it)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
                 const uint64_t adesc = smem_desc_sw128(sbase), bdesc = smem_desc_sw128(sbase + TC_A_BYTES);
@@ -259,7 +270,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         static_assert(CH > 32 && CH <= 64, "two chunks per lane at most");
         auto gather_tau = [&](int64_t k) {
             const int slot = (int)(k % TC_R);
-            if (!mbar_wait(&rec_full[slot], (unsigned)((k / TC_R) & 1), 6, &s_abort)) return false;
+            if (!mbar_wait(&rec_full[slot], (unsigned)((k / TC_R) & 1), 6, &s_abort, wc)) return false;
             const TcSlot* r = &ring[slot];
             const int qj = (uint32_t)lane < r->rec.m ? r->rec.q[lane] : tau_sentinel;
             cp4(smem_u32(&ring[slot].tau[lane]), taui + qj);
@@ -269,7 +280,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         int64_t k = 0;
         for (; k < nmine && !s_abort; ++k) {
             const int slot = (int)(k % TC_R);
-            if (k >= TC_R && !mbar_wait(&rec_empty[slot], (unsigned)(((k / TC_R) - 1) & 1), 7, &s_abort)) break;
+            if (k >= TC_R && !mbar_wait(&rec_empty[slot], (unsigned)(((k / TC_R) - 1) & 1), 7, &s_abort, wc)) break;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(recs + (blockIdx.x + k * G));
             const uint32_t dst = smem_u32(&ring[slot].rec);
             cp16(dst + 16 * lane, src + 16 * lane);
@@ -291,7 +302,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         const unsigned char* qsrc = Q8 + 16 * c;
         int64_t k = 0;
         for (; k < nmine && !s_abort; ++k) {
-            if (!mbar_wait(&rec_full[k % TC_R], (unsigned)((k / TC_R) & 1), 6, &s_abort)) break;
+            if (!mbar_wait(&rec_full[k % TC_R], (unsigned)((k / TC_R) & 1), 6, &s_abort, wc)) break;
             const TcRec* r = &ring[k % TC_R].rec;
             int id[8];
 #pragma unroll
@@ -299,7 +310,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
             const uint32_t m = r->m;
             const int q0 = r->q[rg], q1 = r->q[rg + 16];
             const int s = (int)(k % TC_S);
-            if (k >= TC_S && !mbar_wait(&a_empty[s], (unsigned)(((k / TC_S) - 1) & 1), 4, &s_abort)) break;
+            if (k >= TC_S && !mbar_wait(&a_empty[s], (unsigned)(((k / TC_S) - 1) & 1), 4, &s_abort, wc)) break;
             const uint32_t sa = a0 + (uint32_t)s * TC_STAGE_BYTES;
             if (has_chunk) {
 #pragma unroll
@@ -315,6 +326,7 @@ k_score_u8t(const unsigned char* __restrict__ X8, unsigned pitch /* row bytes: m
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    wc.report();
     if (tid == 0) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - t_start));
     // ---- teardown: everything issued has been consumed (the epilogue waited for every accumulator) ------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -332,10 +344,10 @@ void tc_diag_read(unsigned long long* out24) {
 
 bool score_u8t_usable(const dpf_index* h, int metric) {
     // dot product only (the reference's re-rank metric); angular and squared L2 need the row norms next to the
-    // accumulator and stay on the mma.sync kernel
-    if (metric != DPF_METRIC_DOT) return false;
-    const int64_t sel = h->dbg[DPF_DBG_U8I_KERNEL];
-    return sel == 0 || sel == 3;
+    // accumulator and stay on the mma.sync kernel.  Opt-in (DPF_DBG_U8I_KERNEL = 3): on configs[1] this kernel is
+    // correct but slower than k_score_u8s — the units of this workload are small (58 rows x 6 queries on average), and
+    // every role of the asynchronous pipeline pays ~1000 cycles of barrier hand-offs per unit (profiles/r2_tcgen05_*).
+    return metric == DPF_METRIC_DOT && h->dbg[DPF_DBG_U8I_KERNEL] == 3;
 }
 
 void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, int64_t cap, const int32_t* taui,

@@ -55,7 +55,7 @@ def test_full_size_topk_properties_and_kernel_agreement(full, monkeypatch):
     ids2, sc2 = ix.query_topk_dense(Q, None, 0, K, B.METRIC_DOT)
     assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
     # independent kernels: integer tensor pipe + threshold filter / FP64 tensor pipe on byte rows / TMA ring / row-major
-    for opt in ({"u8_imma": 0}, {"bm_kernel": 1}, {"rerank": 1}, {"u8i_kernel": 1}, {"u8i_kernel": 2}, {"tau_tables": 1},
+    for opt in ({"u8_imma": 0}, {"bm_kernel": 1}, {"rerank": 1}, {"u8i_kernel": 1}, {"u8i_kernel": 3}, {"tau_tables": 1},
                 {"tau_tables": 30}):
         with ix.debug_options(**opt):
             i3, s3 = ix.query_topk_dense(Q, None, 0, K, B.METRIC_DOT)

@@ -276,12 +276,12 @@ def test_topk_bucket_major_equals_row_major_bitwise_on_integer_data(monkeypatch)
     ix.fit_dense(X)
     res = {}
     for name, opt in (("u8", {}), ("stream", {"bm_kernel": 1}), ("u8_dmma", {"u8_imma": 0}), ("rowmajor", {"rerank": 1}),
-                      ("u8_ring", {"u8i_kernel": 2}), ("u8_lean", {"u8i_kernel": 1})):
+                      ("u8_tcgen05", {"u8i_kernel": 3}), ("u8_lean", {"u8i_kernel": 1})):
         with ix.debug_options(**opt):
             res[name] = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
         bm = ix.stats()["bm_pairs"]
         assert (bm > 0) == (name != "rowmajor")
-    for name in ("u8", "stream", "u8_dmma", "u8_ring", "u8_lean"):
+    for name in ("u8", "stream", "u8_dmma", "u8_tcgen05", "u8_lean"):
         assert np.array_equal(res[name][0], res["rowmajor"][0]), name
         assert np.array_equal(res[name][1], res["rowmajor"][1]), name
     # a survivor pool far too small for the batch: the warps that find it full flag their queries, which are then answered
@@ -348,6 +348,10 @@ def test_compact_store_kinds_match_oracle(d, kind, metric):
         U.assert_topk_close(io, so, ig, sg)
         if metric == B.METRIC_DOT:
             assert np.array_equal(so[~np.isnan(so)], sg[~np.isnan(sg)]), "integer dot products must be exact"
+            with ix.debug_options(u8i_kernel=3):                  # the tcgen05 / TMEM kernel: rows narrower than 128 bytes too
+                it, st_ = ix.query_topk_dense(Qb, None, 1, 10, metric)
+            assert np.array_equal(it, ig) and np.array_equal(st_, sg, equal_nan=True)
+            assert not ix.tc_diag()[:8].any(), "tcgen05 kernel watchdog fired"
 
 
 def test_compact_store_bitwise_equal_to_f64_rows_on_integer_data(monkeypatch):

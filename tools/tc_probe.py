@@ -12,10 +12,10 @@ A, chain = synth.angle_family(d, 128, 10, 3, 32, 88389)
 Ap = synth.partitioner_family(30, 3, 88390)
 ix = U.make_index(d, A, chain, Ap, bucket_overflow=100)
 ix.fit_dense(X)
-with ix.debug_options(u8i_kernel=2):
-    ref = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
+ref = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
 print("ring ok", ix.stats()["bm_survivors"], flush=True)
-got = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
+with ix.debug_options(u8i_kernel=3):
+    got = ix.query_topk_dense(Q, None, 0, 10, B.METRIC_DOT)
 print("tc diag", ix.tc_diag()[:8].tolist(), "stats", {k: v for k, v in ix.stats().items() if k.startswith("bm_")}, flush=True)
 print("ids equal", float((ref[0] == got[0]).mean()), "scores equal", float((ref[1] == got[1]).mean()))
 bad = np.nonzero((ref[0] != got[0]).any(axis=1))[0]
