@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256)
 k_emit_tc_recs(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict__ unit_off, const uint32_t* __restrict__ leaf_pos,
                const int32_t* __restrict__ leaf_len, int64_t nleaves, const int32_t* __restrict__ pair_q,
                const int32_t* __restrict__ ids_sorted, TcRec* __restrict__ recs, const int* __restrict__ q8_bad,
-               uint32_t cap /* records that fit */, uint32_t* __restrict__ dirty) {
+               uint32_t cap /* records that fit */, DirtySet dirty) {
     if (*q8_bad != 0) return;                       // a batch that is not byte vectors is scored from the UnitRecs
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -198,7 +198,7 @@ k_emit_tc_recs(const uint32_t* __restrict__ leaf_off, const uint32_t* __restrict
             const int32_t qv = pair_q[p + min((uint32_t)lane, m - 1u)];
             for (uint32_t r0 = 0; r0 < len; r0 += 128, ++rec, ++u) {
                 if (u >= cap) {                      // the record array is sized for any realistic batch, not for the worst
-                    dirty[qv] = 1u;                  // case: the queries of a unit that does not fit are answered exhaustively
+                    if ((uint32_t)lane < m) dirty.mark(qv);   // case: the queries of a unit that does not fit are answered exhaustively
                     continue;
                 }
                 const uint32_t nrows = min(128u, len - r0);
@@ -368,7 +368,7 @@ void emit_units(dpf_index* h, bool only_if_fp64_queries) {
     DPF_CUDA(cudaGetLastError());
 }
 
-void emit_tc_recs(dpf_index* h, int64_t cap, uint32_t* dirty) {
+void emit_tc_recs(dpf_index* h, int64_t cap, const DirtySet& dirty) {
     StageTimer tm(h, DPF_T_EXPAND);
     const int64_t nleaves = h->num_leaves;
     if (nleaves > 0) {

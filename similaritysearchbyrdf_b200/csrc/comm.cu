@@ -36,9 +36,15 @@ static NcclApi& nccl() {
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (api.lib) return api;
+    // a copy that is already in the process (PyTorch's, for one) is the one to use: loading a second NCCL of another
+    // version under the same soname would break whoever loads theirs later
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-        api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        api.lib = dlopen(name, RTLD_NOW | RTLD_NOLOAD);
         if (api.lib) break;
+    }
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        if (api.lib) break;
+        api.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     }
     DPF_REQUIRE(api.lib, DPF_ERR_STATE, "libnccl.so.2 not found: the multi-GPU plane needs NCCL");
     auto sym = [&](const char* n) {
@@ -77,6 +83,10 @@ void comm_init(dpf_index* h, const uint8_t* id_bytes) {
     ncclComm_t c = nullptr;
     DPF_NCCL(nccl().CommInitRank(&c, world, id, rank));
     h->comm = c;
+    // NCCL connects its channels at the first collective (hundreds of ms): do that here, not inside the first fit
+    h->comm_stage.reserve(64 * (size_t)world);
+    DPF_NCCL(nccl().AllGather(h->comm_stage.p + 64 * rank, h->comm_stage.p, 64, ncclChar, c, h->stream));
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
 }
 
 void comm_destroy(dpf_index* h) {

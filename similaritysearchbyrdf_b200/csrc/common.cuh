@@ -120,7 +120,8 @@ enum : int {
     CTR_NUNITS = 45,
     CTR_SCAN_TILE = 46,       // tile cursor of the leaf-count scan
     CTR_POOL_OVERFLOW = 47,   // != 0: the survivor pool was too small for some warp (its queries are answered directly)
-    CTR_DIRECT = 48,          // queries answered by k_topk_direct in this batch
+    CTR_NDIRTY = 48,          // queries of the current chunk flagged for k_topk_direct
+    CTR_DIRECT = 49,          // queries answered by k_topk_direct in this batch
     CTR_NPAIRS_TC = 54,       // the same two totals from the scan at the tcgen05 kernel's unit width
     CTR_NUNITS_TC = 55,
     CTR_SCAN_TILE_TC = 56,
@@ -245,6 +246,8 @@ struct dpf_index {
     dpf::DevBuf<double> bm_tau;                // per query: score threshold
     dpf::DevBuf<uint32_t> bm_scnt, bm_sbase;   //            survivors so far, start of its list
     dpf::DevBuf<uint32_t> bm_big;              // queries whose survivor list is long
+    dpf::DevBuf<double> direct_keys;           // k_topk_direct: partial lists per (dirty query, table group)
+    dpf::DevBuf<int32_t> direct_ids;
     dpf::DevBuf<double> bm_tl_keys;            // threshold sample lists: nq x NT x k
     dpf::DevBuf<int> bm_tl_ids, bm_tl_cnt;
     dpf::DevBuf<uint32_t> bm_flag, bm_run_start, bm_ucnt, bm_counts;   // runs / units of the sorted pairs

@@ -467,16 +467,21 @@ k_topk_select(const int64_t* __restrict__ unit_off, int64_t q0, int K, int metri
 
 // ---------------------------------------------------------------------------------------------------------
 // k_topk_direct — exhaustive top k of one query over the buckets it probes, straight from the probe result (leaf numbers
-// per table): the answer for the queries the threshold filter cannot serve (fewer than k sampled rows, or survivors that
-// did not fit the pool; flagged `dirty` on the device), with no scratch that depends on the data.  One CTA per dirty
-// query, a warp per bucket, FP64 rows scored like the row-major kernel; an id reached through several tables has the
-// same score every time and is kept once.
+// per table): the answer for the queries the threshold filter cannot serve (fewer than k sampled rows, survivors that
+// did not fit the pool, unit records that did not fit; listed in a DirtySet on the device), with no scratch that depends
+// on the data.  Work item = (dirty query, table group): persistent CTAs pull items, a warp per bucket, FP64 rows scored
+// like the row-major kernel, one sorted partial list per item; k_merge_topk then merges a query's DIRECT_PARTS lists
+// (an id reached through several tables has the same score every time and is kept once).  An empty dirty list costs two
+// launches that return at once; a single dirty query is spread over DIRECT_PARTS CTAs instead of occupying one for
+// milliseconds.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int DIRECT_PARTS = 32;
+
 template <bool VEC2, int METRIC>
 __global__ void __launch_bounds__(RR_THREADS)
 k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const uint32_t* __restrict__ leaf_pos,
-              const int32_t* __restrict__ leaf_len, const int32_t* __restrict__ ids_sorted, const uint32_t* __restrict__ dirty,
-              int self_exclude, int K, int32_t* __restrict__ ids_out, double* __restrict__ score_out, int* __restrict__ stat_direct) {
+              const int32_t* __restrict__ leaf_len, const int32_t* __restrict__ ids_sorted, DirtySet dirty, int first, int cap,
+              int self_exclude, int K, double* __restrict__ part_key, int32_t* __restrict__ part_id) {
     extern __shared__ double rsm[];
     double* qs = rsm;                                    // d (padded to even)
     double* lkeys = rsm + ((d + 1) & ~1);                // RR_WARPS x K
@@ -486,11 +491,12 @@ k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const ui
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* mykeys = lkeys + warp * K;
     int* myids = lids + warp * K;
-    for (int64_t q = blockIdx.x; q < cv.nqc; q += gridDim.x) {
-        if (!dirty[q]) continue;                         // block-uniform
-        __syncthreads();                                 // shared lists and query of the previous round are free
+    const int ndirty = min(*dirty.count - first, cap);   // this round's slice of the list
+    for (int item = blockIdx.x; item < ndirty * DIRECT_PARTS; item += gridDim.x) {
+        const int di = item / DIRECT_PARTS, part = item % DIRECT_PARTS;
+        const int64_t q = dirty.list[first + di];
+        __syncthreads();                                 // shared lists and query of the previous item are free
         for (int j = tid; j < d; j += RR_THREADS) qs[j] = cv.Q[q * d + j];
-        if (tid == 0) atomicAdd(stat_direct, 1);
         __syncthreads();
         if (METRIC == DPF_METRIC_ANGULAR) {
             if (warp == 0) {
@@ -505,11 +511,11 @@ k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const ui
         const double qn = (METRIC == DPF_METRIC_ANGULAR) ? s_qn : 1.0;
         const int qid = cv.qids ? cv.qids[q] : INT32_MIN;
         const bool excl = self_exclude && cv.qids && qid >= -128 && qid <= 127;
-        int count = 0, item = 0;
-        for (int t = 0; t < L; ++t) {
+        int count = 0, bucket = 0;
+        for (int t = part; t < L; t += DIRECT_PARTS) {
             const uint32_t nb = cv.pair_cnt[q * L + t];
-            for (uint32_t e = 0; e < nb; ++e, ++item) {
-                if (item % RR_WARPS != warp) continue;   // warp-uniform
+            for (uint32_t e = 0; e < nb; ++e, ++bucket) {
+                if (bucket % RR_WARPS != warp) continue;   // warp-uniform
                 const uint32_t leaf = cv.cache[(q * L + t) * cv.cap + e];
                 const int32_t* bids = ids_sorted + leaf_pos[leaf];
                 const int len = leaf_len[leaf];
@@ -540,9 +546,11 @@ k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const ui
         }
         if (lane == 0) s_counts[warp] = count;
         __syncthreads();
-        if (warp == 0) {                                 // merge; the same id in two lists carries the same score: adjacent, kept once
+        if (warp == 0) {                                 // merge the warps' lists into the item's sorted partial list
             int head = 0, last = -1;
             const int mycount = lane < RR_WARPS ? s_counts[lane] : 0;
+            double* ok_out = part_key + (size_t)item * K;
+            int32_t* oi_out = part_id + (size_t)item * K;
             for (int r = 0; r < K; ++r) {
                 double bk;
                 int bi, bl;
@@ -561,8 +569,8 @@ k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const ui
                     if (bi != last) break;
                 }
                 if (lane == 0) {
-                    ids_out[q * K + r] = bl >= 0 ? bi : -1;
-                    score_out[q * K + r] = bl >= 0 ? (METRIC == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
+                    oi_out[r] = bl >= 0 ? bi : -1;
+                    ok_out[r] = bl >= 0 ? (METRIC == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
                 }
                 if (bl >= 0) last = bi;
             }
@@ -570,26 +578,80 @@ k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const ui
     }
 }
 
-void topk_direct(dpf_index* h, const ChunkView& cv, const uint32_t* dirty, int topk, int metric, int32_t* ids_out, double* score_out) {
+// warp per dirty query of the round: merge its DIRECT_PARTS partial lists into the query's row of the output
+__global__ void __launch_bounds__(128)
+k_direct_merge(const int32_t* __restrict__ part_id, const double* __restrict__ part_key, DirtySet dirty, int first, int cap, int K,
+               int metric, int32_t* __restrict__ ids_out, double* __restrict__ score_out, int* __restrict__ stat_direct) {
+    const int lane = threadIdx.x & 31;
+    const int ndirty = min(*dirty.count - first, cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ndirty > 0) atomicAdd(stat_direct, ndirty);
+    for (int di = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); di < ndirty; di += gridDim.x * (blockDim.x >> 5)) {
+        const int64_t q = dirty.list[first + di];
+        const int32_t* lids = part_id + ((size_t)di * DIRECT_PARTS + lane) * K;
+        const double* lsc = part_key + ((size_t)di * DIRECT_PARTS + lane) * K;
+        int head = 0;
+        for (int r = 0; r < K; ++r) {
+            double bk;
+            int bi, bl;
+            for (;;) {
+                bk = 0; bi = 0x7fffffff; bl = -1;
+                if (head < K) {
+                    const int id = lids[head];
+                    if (id >= 0) { const double s = lsc[head]; bk = (metric == DPF_METRIC_L2) ? -s : s; bi = id; bl = lane; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ok_ = __shfl_xor_sync(0xffffffffu, bk, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                    if (ol >= 0 && (bl < 0 || better(ok_, oi, bk, bi) || (ok_ == bk && oi == bi && ol < bl))) { bk = ok_; bi = oi; bl = ol; }
+                }
+                if (bl < 0) break;
+                if (lane == bl) head++;
+                bool dup = false;                        // the same id through tables of two groups: same score, kept once
+                for (int j = lane; j < r; j += 32) dup |= ids_out[q * K + j] == bi;
+                if (!__any_sync(0xffffffffu, dup)) break;
+            }
+            if (lane == 0) {
+                ids_out[q * K + r] = bl >= 0 ? bi : -1;
+                score_out[q * K + r] = bl >= 0 ? (metric == DPF_METRIC_L2 ? -bk : bk) : __longlong_as_double(0x7ff8000000000000LL);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+void topk_direct(dpf_index* h, const ChunkView& cv, const DirtySet& dirty, int topk, int metric, int32_t* ids_out, double* score_out) {
+    static_assert(DIRECT_PARTS == 32, "one lane per partial list in k_direct_merge");
     const int d = h->cfg.d;
     const size_t smem = (size_t)((d + 1) & ~1) * sizeof(double) + (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
     const bool vec2 = (d % 2 == 0) && ((reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0);
-    const int grid = (int)std::min<int64_t>(cv.nqc, (int64_t)h->num_sms * 4);
-    auto go = [&](auto kern) {
-        if (smem > 48 * 1024) DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, RR_THREADS, smem, h->stream>>>(h->Xdev, d, cv, h->cfg.L, h->leaf_pos.p, h->leaf_len.p, h->ids_sorted.p, dirty,
-                                                    h->cfg.self_exclude_small_ids, topk, ids_out, score_out, h->counters.p + CTR_DIRECT);
+    // partial lists for `cap` dirty queries per round (<= 128 MB); the rounds beyond the list's length return at once
+    const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(cv.nqc, (128LL << 20) / ((int64_t)DIRECT_PARTS * topk * 12)));
+    h->direct_keys.reserve((size_t)cap * DIRECT_PARTS * topk);
+    h->direct_ids.reserve((size_t)cap * DIRECT_PARTS * topk);
+    const int grid = (int)std::min<int64_t>(cap * DIRECT_PARTS, (int64_t)h->num_sms * 4);
+    for (int64_t first = 0; first < cv.nqc; first += cap) {
+        auto go = [&](auto kern) {
+            if (smem > 48 * 1024) DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, RR_THREADS, smem, h->stream>>>(h->Xdev, d, cv, h->cfg.L, h->leaf_pos.p, h->leaf_len.p, h->ids_sorted.p, dirty,
+                                                        (int)first, (int)cap, h->cfg.self_exclude_small_ids, topk, h->direct_keys.p,
+                                                        h->direct_ids.p);
+            DPF_LAUNCHED();
+        };
+        if (vec2) {
+            if (metric == DPF_METRIC_DOT) go(k_topk_direct<true, DPF_METRIC_DOT>);
+            else if (metric == DPF_METRIC_ANGULAR) go(k_topk_direct<true, DPF_METRIC_ANGULAR>);
+            else go(k_topk_direct<true, DPF_METRIC_L2>);
+        } else {
+            if (metric == DPF_METRIC_DOT) go(k_topk_direct<false, DPF_METRIC_DOT>);
+            else if (metric == DPF_METRIC_ANGULAR) go(k_topk_direct<false, DPF_METRIC_ANGULAR>);
+            else go(k_topk_direct<false, DPF_METRIC_L2>);
+        }
+        k_direct_merge<<<(unsigned)std::min<int64_t>((cap + 3) / 4, 1024), 128, 0, h->stream>>>(
+            h->direct_ids.p, h->direct_keys.p, dirty, (int)first, (int)cap, topk, metric, ids_out, score_out, h->counters.p + CTR_DIRECT);
         DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
-    };
-    if (vec2) {
-        if (metric == DPF_METRIC_DOT) go(k_topk_direct<true, DPF_METRIC_DOT>);
-        else if (metric == DPF_METRIC_ANGULAR) go(k_topk_direct<true, DPF_METRIC_ANGULAR>);
-        else go(k_topk_direct<true, DPF_METRIC_L2>);
-    } else {
-        if (metric == DPF_METRIC_DOT) go(k_topk_direct<false, DPF_METRIC_DOT>);
-        else if (metric == DPF_METRIC_ANGULAR) go(k_topk_direct<false, DPF_METRIC_ANGULAR>);
-        else go(k_topk_direct<false, DPF_METRIC_L2>);
     }
 }
 

@@ -593,7 +593,7 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, Chun
 // no threshold can be guaranteed, the query is flagged for k_topk_direct and tau = +inf keeps it out of the pool.
 __global__ void __launch_bounds__(RR_THREADS)
 k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys, const int* __restrict__ tl_ids,
-                  const int* __restrict__ tl_cnt, double* __restrict__ tau, int32_t* __restrict__ taui, uint32_t* __restrict__ dirty) {
+                  const int* __restrict__ tl_cnt, double* __restrict__ tau, int32_t* __restrict__ taui, DirtySet dirty) {
     const int lane = threadIdx.x & 31;
     const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) taui[nqc] = 0x7fffffff;      // sentinel: "no query" for the tcgen05 kernel's padding
@@ -624,7 +624,7 @@ k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys
         tau[q] = tv;
         // the same threshold for integer scores (a dot product of bytes is below 2^31 - 1: INT_MAX masks the query)
         taui[q] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
-        if (found < K) dirty[q] = 1u;
+        if (found < K) dirty.mark((int)q);
     }
 }
 
@@ -645,7 +645,7 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
     const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + warp;
     if (ql >= nqc) return;
     const int64_t q = q0 + ql;
-    if (flt.dirty[q]) return;                // answered by k_topk_direct
+    if (flt.dirty.flag[q]) return;           // answered by k_topk_direct
     const uint32_t n = flt.cnt[q];
     if (lane == 0) atomicAdd(&stat[2], (unsigned long long)n);
     if (n > SEL_BIG) {                       // a weak threshold left a long list: k_select_survivors_big (a CTA per query)
@@ -812,13 +812,14 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     h->surv_id.reserve((size_t)pool_cap);
     h->bm_tau.reserve((size_t)nqc + 2);
     // one block cleared per chunk: survivor counts, list cursors, dirty flags
-    h->bm_scnt.reserve((size_t)nqc * 3 + 4);
+    h->bm_scnt.reserve((size_t)nqc * 4 + 4);
     uint32_t* s_cnt = h->bm_scnt.p;
     uint32_t* s_fill = s_cnt + nqc;
     uint32_t* s_dirty = s_fill + nqc;
+    const DirtySet dirty{s_dirty, reinterpret_cast<int32_t*>(s_dirty + nqc), ctr + CTR_NDIRTY};   // (the list needs no clearing)
     h->bm_sbase.reserve((size_t)nqc + 1);
     DPF_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t)nqc * 3 * sizeof(uint32_t), st));
-    DPF_CUDA(cudaMemsetAsync(ctr + CTR_POOL, 0, 6 * sizeof(int32_t), st));      // pool cursor, chunk counts, overflow flag
+    DPF_CUDA(cudaMemsetAsync(ctr + CTR_POOL, 0, 7 * sizeof(int32_t), st));      // pool cursor, chunk counts, overflow flag, dirty count
 
     probe_and_group(h, qk, steps, probe_mode, q0, nqc, cap, use_tc);
 
@@ -833,7 +834,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     cv.pair_cnt = h->pair_cnt.p;
     cv.cache = h->probe_cache.p;
     cv.cap = cap;
-    const Filter flt{h->bm_tau.p, s_cnt, h->bm_sbase.p, s_fill, s_dirty, h->scores.p, h->surv_id.p,
+    const Filter flt{h->bm_tau.p, s_cnt, h->bm_sbase.p, s_fill, dirty, h->scores.p, h->surv_id.p,
                      reinterpret_cast<SurvRec*>(h->surv_pool.p), reinterpret_cast<uint32_t*>(ctr + CTR_POOL), (uint32_t)pool_cap,
                      ctr + CTR_POOL_OVERFLOW};
     const size_t list_smem = (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
@@ -875,11 +876,11 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             dispatch_kind(kind, ang, [&](auto a, auto kc) { go(k_threshold<decltype(a)::value, decltype(kc)::value, false>, 0); });
         }
         k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(nqc, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p, h->bm_tau.p,
-                                                         h->bm_taui.p, s_dirty); DPF_LAUNCHED();
+                                                         h->bm_taui.p, dirty); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
         DPF_CUDA(cudaEventRecord(h->ev_join, st2));
     }
-    if (use_tc) emit_tc_recs(h, tc_cap, s_dirty);
+    if (use_tc) emit_tc_recs(h, tc_cap, dirty);
     emit_units(h, use_tc);               // with the tcgen05 kernel the records only serve a batch that is not byte vectors
 
     unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(ctr + CTR_BM_STAT);
@@ -914,7 +915,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                                                                  bm_stat, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
         k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
             0, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
-        topk_direct(h, cv, s_dirty, topk, metric, io, so);
+        topk_direct(h, cv, dirty, topk, metric, io, so);
         DPF_CUDA(cudaGetLastError());
     }
 }

@@ -69,12 +69,23 @@ struct __align__(16) SurvRec {
     uint32_t pos;          // position of the row in ids_sorted
     double score;
 };
+// the queries the filter cannot serve, answered by k_topk_direct: a flag per query, and a list so that the exhaustive
+// kernel can spread every such query over many CTAs (and costs nothing when the list is empty)
+struct DirtySet {
+    uint32_t* flag;        // per query
+    int32_t* list;         // dirty queries in the order they were found
+    int* count;
+    __device__ __forceinline__ void mark(int q) const {
+        if (atomicExch(flag + q, 1u) == 0u) list[atomicAdd(count, 1)] = q;
+    }
+};
+
 struct Filter {
     const double* tau;     // per query: score threshold (k_threshold*); +inf for a dirty query
     uint32_t* cnt;         // per query: survivors stored in the pool
     uint32_t* base;        // per query: start of its survivor list = exclusive scan of cnt (k_survivor_offsets)
     uint32_t* fill;        // per query: list entries written so far (k_scatter_survivors)
-    uint32_t* dirty;       // per query: != 0 -> answered by k_topk_direct
+    DirtySet dirty;        // queries answered by k_topk_direct
     double* s_score;
     int32_t* s_id;
     SurvRec* pool;         // survivors in the order the scoring warps found them, blocks of SURV_BLOCK per warp
@@ -110,7 +121,7 @@ struct SurvivorSink {
             }
         }
         if (full) {
-            if (keep) f.dirty[q] = 1u;
+            if (keep) f.dirty.mark(q);
             return;
         }
         if (keep) {
@@ -156,7 +167,7 @@ void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units, const
 // bm_group.cu: probe -> pairs grouped by leaf -> unit records, all sized on the host without reading anything back
 void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc);
 void emit_units(dpf_index* h, bool only_if_fp64_queries);
-void emit_tc_recs(dpf_index* h, int64_t cap, uint32_t* dirty);                                           // the tcgen05 kernel's units
+void emit_tc_recs(dpf_index* h, int64_t cap, const DirtySet& dirty);                                           // the tcgen05 kernel's units
 // rerank_tc.cu
 bool score_u8t_usable(const dpf_index* h, int metric);
 void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, int64_t cap, const int32_t* taui,
@@ -164,6 +175,6 @@ void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, cons
 void survivor_lists(dpf_index* h, const Filter& flt, int64_t nqc);         // offsets + scatter
 int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);
 // query.cu: exhaustive per-query top-k over the query's own buckets for the queries flagged dirty
-void topk_direct(dpf_index* h, const ChunkView& cv, const uint32_t* dirty, int topk, int metric, int32_t* ids_out, double* score_out);
+void topk_direct(dpf_index* h, const ChunkView& cv, const DirtySet& dirty, int topk, int metric, int32_t* ids_out, double* score_out);
 
 }  // namespace dpf

@@ -134,6 +134,10 @@ class DPFIndex:
     def comm_unique_id():
         """Rank 0: the id every rank passes to comm_init (bytes of length B.COMM_ID_BYTES)."""
         lib = B.load()
+        try:                       # in a PyTorch process the library must bind the NCCL torch ships, so torch loads it first
+            import torch           # noqa: F401
+        except ImportError:
+            pass
         buf = np.zeros(B.COMM_ID_BYTES, np.uint8)
         rc = lib.dpf_comm_unique_id(_p(buf))
         if rc != B.OK:

@@ -6,6 +6,7 @@ import threading
 
 import numpy as np
 import pytest
+import torch  # noqa: F401  (first: the library binds the NCCL that is already in the process)
 
 from similaritysearchbyrdf_b200 import DPFIndex, synth
 from similaritysearchbyrdf_b200 import _lib as B

@@ -14,6 +14,9 @@ ap.add_argument("--nq", type=int, default=1000)
 ap.add_argument("--d", type=int, default=128)
 ap.add_argument("--topk", type=int, default=10)
 ap.add_argument("--repeat", type=int, default=1)
+ap.add_argument("--world", type=int, default=1, help="emulate one rank of a multi-GPU partition on this GPU")
+ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--tc", type=int, default=0, help="1: the tcgen05 scoring kernel")
 a = ap.parse_args()
 X, Q = synth.config2(a.n, a.nq, a.d)
 A, chain = synth.angle_family(a.d, max(100, a.d), 10, 3, 32, 88387 + 2)
@@ -24,8 +27,11 @@ ix.set_partitioners(Ap)
 ix.set_profiling(True)
 Xd = torch.from_numpy(X).cuda()
 for _ in range(a.repeat):
-    ix2 = DPFIndex(d=a.d, L=30, k=32, pb=3)
+    ix2 = DPFIndex(d=a.d, L=30, k=32, pb=3, rank=a.rank, world=a.world)
+    ix2.set_balanced_partition(a.world > 1)
     ix2.set_family(A, chain); ix2.set_partitioners(Ap); ix2.set_profiling(True)
+    if a.tc:
+        ix2.set_debug_option(3, 3)
     ix2.fit_dense_dev(Xd.data_ptr(), a.n)
     print("build stage ms:", {k: round(v, 3) for k, v in ix2.stage_times_ms().items() if v}, ix2.stats())
     ix = ix2
@@ -34,7 +40,8 @@ for _ in range(a.repeat + 1):
     st = ix.stats()
     print("query stage ms:", {k: round(v, 3) for k, v in ix.stage_times_ms().items() if v},
           "cand/q", st["last_candidates"] / a.nq, "dups/q", st["last_cand_with_dups"] / a.nq,
-          "bm pairs", st["bm_pairs"], "runs", st["bm_runs"], "rows staged", st["bm_rows_staged"], "survivors/q", st["bm_survivors"] / a.nq)
+          "bm pairs", st["bm_pairs"], "runs", st["bm_runs"], "rows staged", st["bm_rows_staged"], "survivors/q", st["bm_survivors"] / a.nq,
+          "direct", st["bm_direct"])
 
 d = ix.tc_diag()
 print("tc watchdog", d[:8].tolist())
