@@ -26,10 +26,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the scoring kernel on this workload (ncu --set full
-# captures summarised under profiles/); kernels without a capture report null
-NCU_TRAFFIC_BYTES = {"k_score_stream": 46_793_233_000 + 4_166_460_000,       # profiles/r1_ncu_full_k_score_stream.csv
-                     "k_score_u8s": 2_820_156_000 + 60_886_000}              # profiles/r1_ncu_full_u8_pipeline.csv
+# ncu figures of the scoring kernels (dram__bytes_read.sum + dram__bytes_write.sum per launch, tensor-pipe and L2
+# percentages) are NOT typed in here: tools/ncu_traffic.py extracts them from an `ncu --set full` capture of this
+# workload into profiles/r2_ncu_kernels.json, with the command and commit it was taken at; a kernel without a capture
+# of the same workload reports null
+NCU_FILE = os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")
+
+
+def ncu_record(kernel, workload_key):
+    try:
+        rec = json.load(open(NCU_FILE))
+    except Exception:
+        return None
+    if rec.get("workload_key") != workload_key:
+        return None
+    k = rec.get("kernels", {}).get(kernel)
+    if k is not None:
+        k = dict(k, commit=rec.get("commit"), command=rec.get("command"))
+    return k
 
 METRIC_NAME = "batch kNN queries/sec at fixed recall@10"
 UNIT = "queries/s"
@@ -68,18 +82,21 @@ def config_dict(args, n_gpus):
         "rerank_metric": args.metric, "tables": 30, "chain_length": 32, "partition_bits": 3, "bucket_overflow": 500,
         "dir_node_size": 32, "probe": "dense multi-probe",
         "partitioning": f"8 sub-indexes per table dealt to {n_gpus} GPUs by occupancy, vectors replicated" if n_gpus > 1 else "single GPU",
-        "cache": "inputs larger than L2 (vector store 1.0 GB vs 126 MB L2); no explicit flush",
+        "cache": "no explicit flush: a step reads the 128 MB byte store, 120 MB of bucket ids, 8 MB of forest nodes and ~0.3 GB of "
+                 "per-batch scratch (> 126 MB L2); rows are re-staged many times inside a step by design",
     }
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's algorithm on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_arm(args, X, Q, A, chain, Ap, sample, steps, warmup):
-    """Builds the full index with the CPU oracle, then times `steps` passes over a bounded query sample."""
+def cpu_arm(args, X, Q, A, chain, Ap, sample, steps, warmup, threads=None):
+    """Builds the full index with the CPU oracle, then times `steps` passes over a bounded query sample.  `threads`:
+    None = every host core; 5 = the reference's own insertThreadNum / queryThreadNum (table-sliced workers,
+    DensevectorRDFInit.scala:183-188, 344-349; src/test/scala/mclab/TestSettings.scala:43-44)."""
     from oracle import oracle_py as O
     metric = {"dot": 0, "angular": 1, "l2": 2}[args.metric]
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     o = O.Oracle(d=args.d, L=chain.shape[0], k=chain.shape[1], P=A.shape[0], pb=Ap.shape[1])
     o.set_family(A, chain)
     o.set_partitioners(Ap)
@@ -93,9 +110,10 @@ def cpu_arm(args, X, Q, A, chain, Ap, sample, steps, warmup):
     for _ in range(steps):
         ids, _ = o.query_topk_dense(Qs, None, args.qsteps, args.topk, metric, nthreads=cores)
     dt = (time.time() - t0) / steps
+    _, sc = o.query_topk_dense(Qs, None, args.qsteps, args.topk, metric, nthreads=cores)
     return {"qps": sample / dt, "ms_per_step": dt * 1e3, "build_vectors_per_s": len(X) / build_s, "cores": cores,
             "sample": f"{sample} of the {len(Q)} queries per step against the full {len(X)}-vector index "
-                      f"(index built by the same oracle in {build_s:.1f} s)", "ids": ids}
+                      f"(index built by the same oracle in {build_s:.1f} s)", "ids": ids, "scores": sc}
 
 
 def run_reference(args):
@@ -104,12 +122,15 @@ def run_reference(args):
         return
     X, Q, A, chain, Ap, _ = workload(args)
     r = cpu_arm(args, X, Q, A, chain, Ap, min(args.cpu_sample, args.nq), args.steps, min(args.warmup, 1))
+    r5 = cpu_arm(args, X, Q, A, chain, Ap, min(args.cpu_sample, args.nq) // 4, 1, 0, threads=5)
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": r["qps"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, 1),
         "cpu_baseline": {"value": r["qps"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                         "reference_thread_counts": {"value": r5["qps"], "cores": 5, "build_vectors_per_s": r5["build_vectors_per_s"],
+                                                     "note": "insertThreadNum = queryThreadNum = 5, table-sliced as in the reference"},
                          "note": "C++ restatement of the reference algorithm (no JVM in the image); omits the "
                                  "reference's (de)serialisation/boxing, so it is faster than the JVM path"},
         "e2e": {"value": r["qps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -304,6 +325,36 @@ def run_ours(args):
         result_ids = (m_ids if world > 1 else ids_d).cpu().numpy()
         result_sc = (m_sc if world > 1 else sc_d).cpu().numpy()
 
+        # ---- the same batch on the FP64 rows only (what real-valued data take): second index, same timing recipe ------
+        f64 = None
+        if world == 1 and qstats["store_kind"] != B.STORE_KIND_F64:
+            ixf = DPFIndex(d=d, L=chain.shape[0], k=chain.shape[1], pb=Ap.shape[1], device=local)
+            ixf.set_store_mode(B.STORE_F64_ONLY)
+            ixf.set_family(A, chain)
+            ixf.set_partitioners(Ap)
+            ixf.set_stream(stream.cuda_stream)
+            ixf.fit_dense_dev(Xd.data_ptr(), n)
+            idf = torch.empty((nq, K), dtype=torch.int32, device=dev)
+            scf = torch.empty((nq, K), dtype=torch.float64, device=dev)
+            for _ in range(max(args.warmup, 3)):
+                ixf.query_topk_dense_dev(Qd.data_ptr(), nq, 0, args.qsteps, K, metric, idf.data_ptr(), scf.data_ptr())
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(args.steps):
+                ixf.query_topk_dense_dev(Qd.data_ptr(), nq, 0, args.qsteps, K, metric, idf.data_ptr(), scf.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            msf = e0.elapsed_time(e1) / args.steps
+            ixf.set_profiling(True)
+            ixf.query_topk_dense_dev(Qd.data_ptr(), nq, 0, args.qsteps, K, metric, idf.data_ptr(), scf.data_ptr())
+            stf = ixf.stage_times_ms()
+            f64 = {"value": nq / (msf * 1e-3), "ms_per_step": msf, "kernel": "k_score_stream", "kernel_ms": stf["rerank"],
+                   "stage_ms": {k_: v for k_, v in stf.items() if v},
+                   "ids_equal_to_byte_store": bool(np.array_equal(idf.cpu().numpy(), result_ids)),
+                   "scores_equal_to_byte_store": bool(np.array_equal(scf.cpu().numpy(), result_sc))}
+            ixf.close()
+            del idf, scf
+
         # ---- cross-check outside the timed region: the row-major gather/re-rank kernel over the same batch --------
         # (per-candidate-row kernel of DESIGN 4; gives the unique-candidate count the roofline is quoted on, its own
         # HBM rate, and a full-size parity check of the bucket-major path: ids equal, scores within 1e-12 relative)
@@ -411,45 +462,71 @@ def run_ours(args):
     bm = qstats["bm_pairs"] > 0
     store_kind = {0: "f64", 1: "f32", 2: "u8"}[int(qstats["store_kind"])]
     row_bytes = int(qstats["store_row_bytes"])
-    filtered = bm and store_kind == "u8"
+    filtered = bm
+    units, rows_staged, survivors = int(qstats["bm_runs"]), int(qstats["bm_rows_staged"]), int(qstats["bm_survivors"])
     if bm:
-        kernel = ("k_score_u8s" if int_queries else "k_score_u8d") if filtered else "k_score_stream"
-        units = int(qstats["bm_runs"])
-        q_operand = 16 * (128 if (filtered and int_queries) else 8 * d)
-        out_bytes = int(qstats["bm_survivors"]) * 16 if filtered else int(qstats["last_cand_with_dups"]) * 8
-        kernel_bytes = int(qstats["bm_rows_staged"]) * (row_bytes + 4) + units * (unit_rec_bytes + q_operand) + out_bytes
+        kernel = ("k_score_u8s" if int_queries else "k_score_u8d") if store_kind == "u8" else "k_score_stream"
+        q_operand = 16 * (128 if (store_kind == "u8" and int_queries) else 8 * d)
+        # bytes the kernel REQUESTS per launch (every staged row, its id, the unit records, the query operands, the survivors)
+        requested = rows_staged * (row_bytes + 4) + units * (unit_rec_bytes + q_operand) + survivors * 16
+        # bytes it MUST move per launch = the algorithmic bytes of the roofline: every row of the store and every entry of
+        # ids_sorted once (a row staged again for another unit is a re-read the L2 is there to absorb), the unit records,
+        # the batch's queries once, the survivors out
+        entries = int(chain.shape[0]) * n if world == 1 else None
+        algorithmic = (n * row_bytes + (entries or rows_staged) * 4 + units * unit_rec_bytes + nq * (128 if store_kind == "u8" else 8 * d)
+                       + survivors * 16)
     else:
         kernel = "k_rerank_units"
-        kernel_bytes = ncand_unique * (8 * d + 4)
-    achieved = kernel_bytes / (rr_ms * 1e-3) / 1e9 if rr_ms else None
+        requested = algorithmic = ncand_unique * (8 * d + 4)
+    workload_key = f"configs[1] n={n} d={d} nq={nq} k={K} steps={args.qsteps} metric={args.metric} gpus={world}"
+    ncu = ncu_record(kernel, workload_key)
+    traffic = ncu["dram_bytes"] if ncu else None
+    achieved = algorithmic / (rr_ms * 1e-3) / 1e9 if rr_ms else None
     survey_bytes = ncand_unique * (8 * d + 4)
     roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs if achieved else None,
-                "traffic": NCU_TRAFFIC_BYTES.get(kernel), "peak_source": peak_src,
-                "dram_gbs_from_ncu_traffic": NCU_TRAFFIC_BYTES[kernel] / (rr_ms * 1e-3) / 1e9 if kernel in NCU_TRAFFIC_BYTES and rr_ms else None,
-                "note": ("bytes_per_launch counts what the kernel requests; with the byte store (128 MB for 1M x 128, the L2 "
-                         "holds 126 MB) more than half of it is served by the L2, so `achieved` can exceed the HBM peak while "
-                         "the DRAM traffic measured by ncu (`traffic`) stays far below it") if filtered else None,
-                "bytes_per_launch": kernel_bytes, "kernel_ms": rr_ms, "step_share": rr_ms / ms_per_step if rr_ms else None,
-                "store_kind": store_kind, "store_row_bytes": row_bytes, "rows_staged_per_launch": int(qstats["bm_rows_staged"]),
-                "units_per_launch": int(qstats["bm_runs"]), "survivors_per_query": int(qstats["bm_survivors"]) / nq,
+                "frac": achieved / peak_gbs if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algorithmic, "kernel_ms": rr_ms, "step_share": rr_ms / ms_per_step if rr_ms else None,
+                "note": "achieved = algorithmic (compulsory) bytes / CUDA-event time of the scoring kernel: the kernel is not HBM-bound — "
+                        "it is bound by the L2 row gather and by instruction issue (every bucket row is staged once per unit of "
+                        "<= 16 queries that probe its bucket; the 128 MB byte store is mostly L2-resident), which is what "
+                        "requested_gbs / dram_gbs / l2_hit / tensor_pct describe",
+                "requested_bytes_per_launch": requested, "requested_gbs": requested / (rr_ms * 1e-3) / 1e9 if rr_ms else None,
+                "dram_gbs": traffic / (rr_ms * 1e-3) / 1e9 if traffic and rr_ms else None,
+                "dram_frac": traffic / (rr_ms * 1e-3) / 1e9 / peak_gbs if traffic and rr_ms else None,
+                "ncu": ncu,
+                "store_kind": store_kind, "store_row_bytes": row_bytes, "rows_staged_per_launch": rows_staged,
+                "units_per_launch": units, "survivors_per_query": survivors / nq, "queries_answered_exhaustively": int(qstats["bm_direct"]),
                 "unique_candidates_per_query": ncand_unique / nq,
                 "survey_8d": {"algorithmic_bytes_per_launch": survey_bytes,
                               "gbs": survey_bytes / (rr_ms * 1e-3) / 1e9 if rr_ms else None,
-                              "frac_of_peak": survey_bytes / (rr_ms * 1e-3) / 1e9 / peak_gbs if rr_ms else None},
+                              "frac_of_peak": survey_bytes / (rr_ms * 1e-3) / 1e9 / peak_gbs if rr_ms else None,
+                              "note": "SURVEY 8(d)'s per-candidate figure nC_q x (8d + 4) B: what a row-major FP64 gather would move"},
                 "row_major_kernel": rowmajor}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_arm(args, X, Q, A, chain, Ap, min(args.cpu_sample, nq), 1, 1)
-        agree = float(np.mean([len(set(r["ids"][i]) & set(result_ids[i])) / K for i in range(len(r["ids"]))]))
+        r5 = cpu_arm(args, X, Q, A, chain, Ap, min(args.cpu_sample, nq) // 4, 1, 0, threads=5)
+        m = len(r["ids"])
+        ids_equal = bool(np.array_equal(r["ids"], result_ids[:m]))
+        sc_close = bool(np.all(np.abs(r["scores"] - result_sc[:m]) <= 1e-12 * np.maximum(np.abs(r["scores"]), 1e-300)))
+        if not (ids_equal and sc_close):
+            raise SystemExit("bench.py: the GPU top-k differs from the oracle's on the CPU-baseline sample")
         cpu = {"value": r["qps"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
-               "build_vectors_per_s": r["build_vectors_per_s"], "topk_overlap_with_gpu": agree}
+               "build_vectors_per_s": r["build_vectors_per_s"],
+               "reference_thread_counts": {"value": r5["qps"], "cores": 5, "build_vectors_per_s": r5["build_vectors_per_s"],
+                                           "note": "insertThreadNum = queryThreadNum = 5, table-sliced as in the reference "
+                                                   "(DensevectorRDFInit.scala:183-188, 344-349)"},
+               "gpu_topk_ids_equal_oracle": ids_equal, "gpu_topk_scores_within_1e-12": sc_close}
 
     line = {
         "metric": METRIC_NAME, "value": nq / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+        "vs_baseline": None,
+        # what the scoring kernel multiplies: exact u8 x u8 -> s32 on the byte copy of the FP64 store (scores are the exact
+        # FP64 dot products), FP64 otherwise; `value_f64_store` is the same batch with the byte copy switched off
+        "dtype": "u8" if (store_kind == "u8" and int_queries) else "f64", "value_f64_store": f64["value"] if f64 else None,
+        "f64_store": f64, "data": "synthetic", "config": config_dict(args, world),
         "recall_at_10": recall, "clocks": clk,
         "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nq * d * 8),
                 "d2h_bytes_per_step": int(nq * K * 12), "ms_per_step": e2e_ms},

@@ -232,7 +232,7 @@ int dpf_debug_leaf_pairs(dpf_handle h, int64_t* nleaves_out, uint32_t* pair_off_
 enum {
     DPF_T_HASH = 0, DPF_T_FIXUP = 1, DPF_T_PACK = 2, DPF_T_SORT = 3, DPF_T_SPLIT = 4,
     DPF_T_PROBE_COUNT = 5, DPF_T_EXPAND = 6, DPF_T_RERANK = 7, DPF_T_CAND_SORT = 8, DPF_T_SELECT = 9, DPF_T_NARROW = 10,
-    DPF_T_COMM = 11,
+    DPF_T_COMM = 11, DPF_T_THRESHOLD = 12,   /* THRESHOLD runs on the handle's second stream, beside EXPAND */
     DPF_T_COUNT = 16
 };
 int dpf_set_profiling(dpf_handle h, int32_t enable);

@@ -23,7 +23,7 @@ STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nod
               "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",
               "bm_rows_staged", "store_kind", "store_row_bytes", "bm_survivors", "bm_direct"]
 STAGE_NAMES = ["hash", "fixup", "pack", "sort", "split", "probe_count", "expand", "rerank", "cand_sort", "select", "narrow",
-               "comm"]
+               "comm", "threshold"]
 COMM_ID_BYTES = 128
 
 # every symbol include/dpf.h declares

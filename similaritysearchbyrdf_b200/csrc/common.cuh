@@ -283,7 +283,8 @@ struct StageTimer {
     dpf_index* h;
     size_t slot = 0;
     bool on;
-    StageTimer(dpf_index* h_, int id) : h(h_), on(h_->profiling) {
+    cudaStream_t st;
+    StageTimer(dpf_index* h_, int id, cudaStream_t stream = nullptr) : h(h_), on(h_->profiling), st(stream ? stream : h_->stream) {
         if (!on) return;
         slot = h->ev_used++;
         if (h->ev_pool.size() < 2 * (slot + 1)) {
@@ -295,10 +296,10 @@ struct StageTimer {
             h->ev_stage.push_back(id);
         }
         h->ev_stage[slot] = id;
-        cudaEventRecord(h->ev_pool[2 * slot], h->stream);
+        cudaEventRecord(h->ev_pool[2 * slot], st);
     }
     ~StageTimer() {
-        if (on) cudaEventRecord(h->ev_pool[2 * slot + 1], h->stream);
+        if (on) cudaEventRecord(h->ev_pool[2 * slot + 1], st);
     }
 };
 

@@ -511,15 +511,14 @@ k_topk_direct(const double* __restrict__ X, int d, ChunkView cv, int L, const ui
         const double qn = (METRIC == DPF_METRIC_ANGULAR) ? s_qn : 1.0;
         const int qid = cv.qids ? cv.qids[q] : INT32_MIN;
         const bool excl = self_exclude && cv.qids && qid >= -128 && qid <= 127;
-        int count = 0, bucket = 0;
+        int count = 0;
         for (int t = part; t < L; t += DIRECT_PARTS) {
             const uint32_t nb = cv.pair_cnt[q * L + t];
-            for (uint32_t e = 0; e < nb; ++e, ++bucket) {
-                if (bucket % RR_WARPS != warp) continue;   // warp-uniform
-                const uint32_t leaf = cv.cache[(q * L + t) * cv.cap + e];
+            for (uint32_t e = 0; e < nb; ++e) {          // every warp takes 32-row slices of every bucket: balanced whatever
+                const uint32_t leaf = cv.cache[(q * L + t) * cv.cap + e];   // the bucket sizes
                 const int32_t* bids = ids_sorted + leaf_pos[leaf];
                 const int len = leaf_len[leaf];
-                for (int c0 = 0; c0 < len; c0 += 32) {
+                for (int c0 = 32 * warp; c0 < len; c0 += 32 * RR_WARPS) {
                     const int nloc = min(32, len - c0);
                     const int myid = (lane < nloc) ? __ldg(bids + c0 + lane) : 0;
                     for (int r0 = 0; r0 < nloc; r0 += RR_ROWS) {

@@ -853,6 +853,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         cudaStream_t st2 = h->aux_stream;
         DPF_CUDA(cudaEventRecord(h->ev_fork, st));
         DPF_CUDA(cudaStreamWaitEvent(st2, h->ev_fork, 0));
+        StageTimer tmt(h, DPF_T_THRESHOLD, st2);
         const unsigned tgrid = (unsigned)((nqc * NT + RR_WARPS - 1) / RR_WARPS);
         auto go = [&](auto kern, int gate) {
             kern<<<tgrid, RR_THREADS, list_smem, st2>>>(rows, row_bytes, d, cv, u8_query_pitch(), gate, L, NT, h->leaf_pos.p,
@@ -878,17 +879,17 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(nqc, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p, h->bm_tau.p,
                                                          h->bm_taui.p, dirty); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
-        DPF_CUDA(cudaEventRecord(h->ev_join, st2));
     }
+    DPF_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
     if (use_tc) emit_tc_recs(h, tc_cap, dirty);
     emit_units(h, use_tc);               // with the tcgen05 kernel the records only serve a batch that is not byte vectors
 
     unsigned long long* bm_stat = reinterpret_cast<unsigned long long*>(ctr + CTR_BM_STAT);
     const UnitRec* units = reinterpret_cast<const UnitRec*>(h->bm_units.p);
     const uint32_t* nunits_p = reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS);
+    DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));            // thresholds from the second stream
     {
         StageTimer tm(h, DPF_T_RERANK);
-        DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));        // thresholds from the second stream
         if (use_u8) {
             if (use_tc)
                 launch_score_u8t(h, cv, reinterpret_cast<const TcRec*>(h->bm_descs.p),
