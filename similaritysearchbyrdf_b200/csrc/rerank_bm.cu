@@ -424,7 +424,7 @@ __device__ __forceinline__ void raw_to_cols16(const uint4 (&raw)[RawRow<KIND>::N
 
 // INTQ: byte rows and byte queries (Q8, qnorm from k_quantise_queries): exact integer dot products with DP4A, the
 // same value the integer tensor pipe produces, no rounding allowance needed for the dot product.
-template <bool ANGULAR, int KIND, bool INTQ>
+template <bool ANGULAR, int KIND, bool INTQ, bool REG /* K <= 32: the sample list lives in registers */>
 __global__ void __launch_bounds__(RR_THREADS)
 k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, ChunkView cv, int q8_pitch, int gate,
             int L, int NT, const uint32_t* __restrict__ leaf_pos, const int32_t* __restrict__ leaf_len,
@@ -486,6 +486,7 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, Chun
     uint32_t nonempty = __ballot_sync(0xffffffffu, lane < L && cv.pair_cnt[ql * L + min(lane, L - 1)] > 0u);
     int count = 0;
     double kth = 0.0;                        // mykeys[K - 1] once the list is full
+    RegList rl;
     for (int i = 0; i < sample && nonempty; ++i) nonempty &= nonempty - 1;
     if (nonempty) {                          // the sample-th table that has a pair: the first bucket the query probes there
         const int t = __ffs(nonempty) - 1;
@@ -571,6 +572,12 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, Chun
                     todo &= todo - 1;
                     const double lb_s = __shfl_sync(0xffffffffu, lb, src);
                     const int id_s = __shfl_sync(0xffffffffu, id, src);
+                    if (REG) {
+                        if (!rl.contains(id_s, lane)) rl.insert(K, lb_s, id_s, lane);
+                        count = rl.count;
+                        if (count == K) kth = __shfl_sync(0xffffffffu, rl.key, K - 1);
+                        continue;
+                    }
                     if (count == K && !better(lb_s, id_s, mykeys[K - 1], myids[K - 1])) continue;
                     bool dup = false;        // the same row reached through another table: keep it once
                     for (int b2 = 0; b2 < count; b2 += 32) dup |= __any_sync(0xffffffffu, b2 + lane < count && myids[b2 + lane] == id_s);
@@ -581,9 +588,13 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, Chun
         }
     }
     __syncwarp();
-    for (int r = lane; r < count; r += 32) {
-        tl_keys[wid * K + r] = mykeys[r];
-        tl_ids[wid * K + r] = myids[r];
+    if (REG) {
+        if (lane < count) { tl_keys[wid * K + lane] = rl.key; tl_ids[wid * K + lane] = rl.id; }
+    } else {
+        for (int r = lane; r < count; r += 32) {
+            tl_keys[wid * K + r] = mykeys[r];
+            tl_ids[wid * K + r] = myids[r];
+        }
     }
     if (lane == 0) tl_cnt[wid] = count;
 }
@@ -634,6 +645,7 @@ k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t SEL_BIG = 1024;
 
+template <bool REG /* K <= 32: the list lives in registers */>
 __global__ void __launch_bounds__(RR_THREADS)
 k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K, bool negate,
                    int32_t* __restrict__ ids_out, double* __restrict__ score_out, unsigned long long* __restrict__ stat,
@@ -657,26 +669,43 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
     const int qid = qids ? qids[q] : INT32_MIN;
     const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
     int count = 0;
+    RegList rl;
+    double kth_k = 0.0;
+    int kth_i = 0;
     for (uint32_t j0 = 0; j0 < n; j0 += 32) {
         const uint32_t j = j0 + lane;
         const double key = j < n ? sc[j] : 0.0;
         const int id = j < n ? si[j] : -1;
         bool cand = j < n && !(excl && id == qid);
-        if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
+        if (REG) { if (cand && count == K) cand = better(key, id, kth_k, kth_i); }
+        else if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
         uint32_t todo = __ballot_sync(0xffffffffu, cand);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             const double kk = __shfl_sync(0xffffffffu, key, src);
             const int ii = __shfl_sync(0xffffffffu, id, src);
-            bool dup = false;
-            for (int base = 0; base < count; base += 32) dup |= __any_sync(0xffffffffu, base + lane < count && myids[base + lane] == ii);
-            if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
+            if (REG) {
+                if (!rl.contains(ii, lane)) rl.insert(K, kk, ii, lane);
+                count = rl.count;
+                if (count == K) rl.kth(K, kth_k, kth_i);
+            } else {
+                bool dup = false;
+                for (int base = 0; base < count; base += 32) dup |= __any_sync(0xffffffffu, base + lane < count && myids[base + lane] == ii);
+                if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
+            }
         }
     }
-    for (int r = lane; r < K; r += 32) {
-        ids_out[q * K + r] = r < count ? myids[r] : -1;
-        score_out[q * K + r] = r < count ? (negate ? -mykeys[r] : mykeys[r]) : __longlong_as_double(0x7ff8000000000000LL);
+    if (REG) {
+        if (lane < K) {
+            ids_out[q * K + lane] = lane < count ? rl.id : -1;
+            score_out[q * K + lane] = lane < count ? (negate ? -rl.key : rl.key) : __longlong_as_double(0x7ff8000000000000LL);
+        }
+    } else {
+        for (int r = lane; r < K; r += 32) {
+            ids_out[q * K + r] = r < count ? myids[r] : -1;
+            score_out[q * K + r] = r < count ? (negate ? -mykeys[r] : mykeys[r]) : __longlong_as_double(0x7ff8000000000000LL);
+        }
     }
 }
 
@@ -866,15 +895,19 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             // flag on the device, so both are launched and one of them returns at once
             if (try_int) {
                 if (h->dbg[DPF_DBG_TAU_KERNEL] != 1 || l2) launch_threshold_u8i(h, st2, metric, cv, NT, topk, list_smem);
-                else if (ang) go(k_threshold<true, DPF_STORE_KIND_U8, true>, 1);
-                else go(k_threshold<false, DPF_STORE_KIND_U8, true>, 1);
+                else if (ang) { if (topk <= 32) go(k_threshold<true, DPF_STORE_KIND_U8, true, true>, 1); else go(k_threshold<true, DPF_STORE_KIND_U8, true, false>, 1); }
+                else { if (topk <= 32) go(k_threshold<false, DPF_STORE_KIND_U8, true, true>, 1); else go(k_threshold<false, DPF_STORE_KIND_U8, true, false>, 1); }
             }
             if (!l2) {
-                if (ang) go(k_threshold<true, DPF_STORE_KIND_U8, false>, try_int ? 2 : 0);
-                else go(k_threshold<false, DPF_STORE_KIND_U8, false>, try_int ? 2 : 0);
+                const int gate = try_int ? 2 : 0;
+                if (ang) { if (topk <= 32) go(k_threshold<true, DPF_STORE_KIND_U8, false, true>, gate); else go(k_threshold<true, DPF_STORE_KIND_U8, false, false>, gate); }
+                else { if (topk <= 32) go(k_threshold<false, DPF_STORE_KIND_U8, false, true>, gate); else go(k_threshold<false, DPF_STORE_KIND_U8, false, false>, gate); }
             }
         } else {
-            dispatch_kind(kind, ang, [&](auto a, auto kc) { go(k_threshold<decltype(a)::value, decltype(kc)::value, false>, 0); });
+            dispatch_kind(kind, ang, [&](auto a, auto kc) {
+                if (topk <= 32) go(k_threshold<decltype(a)::value, decltype(kc)::value, false, true>, 0);
+                else go(k_threshold<decltype(a)::value, decltype(kc)::value, false, false>, 0);
+            });
         }
         k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(nqc, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p, h->bm_tau.p,
                                                          h->bm_taui.p, dirty); DPF_LAUNCHED();
@@ -912,8 +945,13 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         DPF_CUDA(cudaMemsetAsync(h->bm_big.p, 0, sizeof(uint32_t), st));
         int32_t* io = ids_out + q0 * topk;
         double* so = score_out + q0 * topk;
-        k_select_survivors<<<qgrid, RR_THREADS, list_smem, st>>>(0, nqc, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so,
-                                                                 bm_stat, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
+        if (topk <= 32)
+            k_select_survivors<true><<<qgrid, RR_THREADS, list_smem, st>>>(0, nqc, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io,
+                                                                           so, bm_stat, h->bm_big.p + 1, h->bm_big.p);
+        else
+            k_select_survivors<false><<<qgrid, RR_THREADS, list_smem, st>>>(0, nqc, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io,
+                                                                            so, bm_stat, h->bm_big.p + 1, h->bm_big.p);
+        DPF_LAUNCHED();
         k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
             0, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
         topk_direct(h, cv, dirty, topk, metric, io, so);

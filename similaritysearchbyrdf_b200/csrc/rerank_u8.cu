@@ -638,7 +638,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
 // shuffle-reduction form and the kernel is bound by the row gather alone.  The dot products are the exact integers the
 // scoring kernel will produce; cosines are computed with the same operations.
 // ---------------------------------------------------------------------------------------------------------
-template <int METRIC>
+template <int METRIC, bool REG /* K <= 32: the sample list lives in registers */>
 __global__ void __launch_bounds__(RR_THREADS)
 k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView cv, int L, int NT,
                 const uint32_t* __restrict__ leaf_pos, const int32_t* __restrict__ leaf_len,
@@ -680,6 +680,7 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView 
     for (int i = 0; i < sample && nonempty; ++i) nonempty &= nonempty - 1;
     int count = 0;
     double kth = 0.0;
+    RegList rl;
     if (nonempty) {
         const uint32_t leaf = cv.cache[(ql * L + (__ffs(nonempty) - 1)) * cv.cap];   // the first bucket the query probes there
         const uint32_t bstart = leaf_pos[leaf];
@@ -743,9 +744,15 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView 
                         todo &= todo - 1;
                         const double lb_s = __shfl_sync(0xffffffffu, lb, src);
                         const int id_s = __shfl_sync(0xffffffffu, id, src);
-                        if (count == K && !better(lb_s, id_s, mykeys[K - 1], myids[K - 1])) continue;
-                        warp_insert(mykeys, myids, count, K, lb_s, id_s, lane);      // rows of one bucket are distinct
-                        if (count == K) kth = mykeys[K - 1];
+                        if (REG) {
+                            rl.insert(K, lb_s, id_s, lane);          // rows of one bucket are distinct; a row that is not among
+                            count = rl.count;                        // the K best leaves the list unchanged
+                            if (count == K) kth = __shfl_sync(0xffffffffu, rl.key, K - 1);
+                        } else {
+                            if (count == K && !better(lb_s, id_s, mykeys[K - 1], myids[K - 1])) continue;
+                            warp_insert(mykeys, myids, count, K, lb_s, id_s, lane);
+                            if (count == K) kth = mykeys[K - 1];
+                        }
                     }
                 }
             }
@@ -753,9 +760,13 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView 
         }
     }
     __syncwarp();
-    for (int r = lane; r < count; r += 32) {
-        tl_keys[wid * K + r] = mykeys[r];
-        tl_ids[wid * K + r] = myids[r];
+    if (REG) {
+        if (lane < count) { tl_keys[wid * K + lane] = rl.key; tl_ids[wid * K + lane] = rl.id; }
+    } else {
+        for (int r = lane; r < count; r += 32) {
+            tl_keys[wid * K + r] = mykeys[r];
+            tl_ids[wid * K + r] = myids[r];
+        }
     }
     if (lane == 0) tl_cnt[wid] = count;
 }
@@ -768,9 +779,15 @@ void launch_threshold_u8i(dpf_index* h, cudaStream_t st, int metric, const Chunk
                                                   h->bm_tl_ids.p, h->bm_tl_cnt.p);
         DPF_LAUNCHED();
     };
-    if (metric == DPF_METRIC_ANGULAR) go(k_threshold_u8i<DPF_METRIC_ANGULAR>);
-    else if (metric == DPF_METRIC_L2) go(k_threshold_u8i<DPF_METRIC_L2>);
-    else go(k_threshold_u8i<DPF_METRIC_DOT>);
+    if (topk <= 32) {
+        if (metric == DPF_METRIC_ANGULAR) go(k_threshold_u8i<DPF_METRIC_ANGULAR, true>);
+        else if (metric == DPF_METRIC_L2) go(k_threshold_u8i<DPF_METRIC_L2, true>);
+        else go(k_threshold_u8i<DPF_METRIC_DOT, true>);
+    } else {
+        if (metric == DPF_METRIC_ANGULAR) go(k_threshold_u8i<DPF_METRIC_ANGULAR, false>);
+        else if (metric == DPF_METRIC_L2) go(k_threshold_u8i<DPF_METRIC_L2, false>);
+        else go(k_threshold_u8i<DPF_METRIC_DOT, false>);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
