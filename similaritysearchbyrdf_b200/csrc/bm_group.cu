@@ -273,6 +273,21 @@ k_survivor_offsets(const uint32_t* __restrict__ cnt, int64_t n, uint32_t* __rest
     }
 }
 
+// survivors per query: one pass over the pool (the scoring kernels do not count — an atomic per survivor inside their
+// loop cost them ~10 %); lanes of a warp that hold the same query add once
+__global__ void __launch_bounds__(256)
+k_count_survivors(Filter flt) {
+    const uint32_t n = min(*flt.pool_cursor, flt.pool_cap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n; i0 += stride) {   // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        const int q = i < n ? flt.pool[i].q : -1;
+        const uint32_t peers = __match_any_sync(0xffffffffu, q);
+        if (q >= 0 && lane == __ffs(peers) - 1) atomicAdd(flt.cnt + q, (uint32_t)__popc(peers));
+    }
+}
+
 // survivor records (SurvivorSink) -> per-query lists: at = base[q] + (entries of q written so far); the row id is looked
 // up here.  Survivors of one query come in bursts (a bucket near the query yields many), so the lanes of a warp that
 // hold the same query reserve their slots with one atomic.
@@ -382,6 +397,7 @@ void emit_tc_recs(dpf_index* h, int64_t cap, const DirtySet& dirty) {
 
 void survivor_lists(dpf_index* h, const Filter& flt, int64_t nqc) {
     cudaStream_t st = h->stream;
+    k_count_survivors<<<h->num_sms * 8, 256, 0, st>>>(flt); DPF_LAUNCHED();
     k_survivor_offsets<<<1, 1024, 0, st>>>(flt.cnt, nqc, flt.base); DPF_LAUNCHED();
     k_scatter_survivors<<<h->num_sms * 8, 256, 0, st>>>(flt, h->ids_sorted.p); DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());

@@ -82,7 +82,7 @@ struct DirtySet {
 
 struct Filter {
     const double* tau;     // per query: score threshold (k_threshold*); +inf for a dirty query
-    uint32_t* cnt;         // per query: survivors stored in the pool
+    uint32_t* cnt;         // per query: survivors stored in the pool (k_count_survivors)
     uint32_t* base;        // per query: start of its survivor list = exclusive scan of cnt (k_survivor_offsets)
     uint32_t* fill;        // per query: list entries written so far (k_scatter_survivors)
     DirtySet dirty;        // queries answered by k_topk_direct
@@ -128,7 +128,6 @@ struct SurvivorSink {
             SurvRec r;
             r.q = q; r.pos = pos; r.score = score;
             f.pool[wpos + __popc(mask & ((1u << lane) - 1u))] = r;
-            atomicAdd(f.cnt + q, 1u);
         }
         wpos += n;
         wleft -= n;
