@@ -20,17 +20,36 @@
 
 namespace dpf {
 
+// A CTA takes 256 consecutive (query, table) pairs.  Phase 1, a thread per pair: does this rank own a sub-index the pair
+// searches (on G GPUs 1 - 1/G of the pairs do not: they cost one thread a load, not a warp a launch)?  The others go to a
+// list in shared memory.  Phase 2, a warp per listed pair: the pair's probe keys, one per lane.
 __global__ void __launch_bounds__(256)
 k_probe_leaves(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restrict__ qpids, int64_t ld, int64_t q0,
                int64_t nqc, uint32_t* __restrict__ leaf_cnt, uint32_t* __restrict__ pair_cnt, uint32_t* __restrict__ cache,
-               int cap, unsigned long long* __restrict__ stat_nlz, unsigned long long* __restrict__ stat_entries) {
+               int cap, uint32_t* __restrict__ q_entries /* per query: bucket entries it visits on this rank */,
+               unsigned long long* __restrict__ stat_nlz, unsigned long long* __restrict__ stat_entries) {
     __shared__ unsigned long long s_entries;
-    __shared__ unsigned int s_nlz;
-    if (threadIdx.x == 0) { s_entries = 0ULL; s_nlz = 0u; }
+    __shared__ unsigned int s_nlz, s_n;
+    __shared__ uint16_t s_list[256];
+    if (threadIdx.x == 0) { s_entries = 0ULL; s_nlz = 0u; s_n = 0u; }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid < nqc * c.L) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t wid0 = (int64_t)blockIdx.x * 256;
+    const int np = 1 << c.tp.pb;
+    {
+        const int64_t wid = wid0 + threadIdx.x;
+        if (wid < nqc * c.L) {
+            const int pid = qpids[(int64_t)(wid % c.L) * ld + q0 + wid / c.L];
+            bool any = false;
+            for (int sub = 0; sub < np; ++sub) any |= __popc(sub ^ pid) <= c.steps && c.own.has(sub);
+            if (any) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)threadIdx.x;
+            else pair_cnt[wid] = 0u;
+        }
+    }
+    __syncthreads();
+    const unsigned n_listed = s_n;
+    for (unsigned li = warp; li < n_listed; li += 8) {
+        const int64_t wid = wid0 + s_list[li];
         const int64_t q = q0 + wid / c.L;
         const int t = (int)(wid % c.L);
         const uint32_t h = (uint32_t)qkeys[(int64_t)t * ld + q];
@@ -41,7 +60,6 @@ k_probe_leaves(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __r
         if (nprobes < 0) {
             if (lane == 0) atomicAdd(&s_nlz, 1u);
         } else {
-            const int np = 1 << c.tp.pb;
             for (int sub = 0; sub < np; ++sub) {       // findStepWiseSubIndexIDs (RandomDrawTreeMap.java:613-621)
                 if (__popc(sub ^ pid) > c.steps) continue;
                 if (!c.own.has(sub)) continue;         // this GPU's sub-forest only
@@ -62,7 +80,10 @@ k_probe_leaves(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __r
         }
         if (lane == 0) {
             pair_cnt[wid] = (uint32_t)nbuckets;
-            if (total > 0) atomicAdd(&s_entries, (unsigned long long)total);
+            if (total > 0) {
+                atomicAdd(&s_entries, (unsigned long long)total);
+                atomicAdd(q_entries + wid / c.L, (uint32_t)total);
+            }
         }
     }
     __syncthreads();
@@ -325,7 +346,8 @@ int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap
     return std::max<int64_t>(1, kMaxPairs / ((int64_t)h->cfg.L * cap));
 }
 
-void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc) {
+void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc,
+                     uint32_t* q_entries) {
     const ProbeCtx c = make_ctx(h, steps, probe_mode);
     cudaStream_t st = h->stream;
     const int L = c.L;
@@ -340,8 +362,8 @@ void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mod
     int32_t* ctr = h->counters.p;
     {
         StageTimer tm(h, DPF_T_PROBE_COUNT);
-        k_probe_leaves<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
-            c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->leaf_cnt.p, h->pair_cnt.p, h->probe_cache.p, cap,
+        k_probe_leaves<<<(unsigned)((warps + 255) / 256), 256, 0, st>>>(
+            c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->leaf_cnt.p, h->pair_cnt.p, h->probe_cache.p, cap, q_entries,
             reinterpret_cast<unsigned long long*>(ctr + CTR_STAT_NLZ), reinterpret_cast<unsigned long long*>(ctr + CTR_ENTRIES)); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
     }

@@ -601,10 +601,14 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, Chun
 
 // one warp per query: tau = k-th best distinct row over its NT sample lists (a row sampled through two tables has the
 // same bound in both lists, so duplicates are adjacent in the merged order).  Fewer than k distinct rows in the samples:
-// no threshold can be guaranteed, the query is flagged for k_topk_direct and tau = +inf keeps it out of the pool.
+// no threshold can be guaranteed.  A query that visits few entries anyway (<= SMALL_QUERY_ENTRIES on this rank: common on
+// a multi-GPU shard, where a rank holds one of eight sub-indexes) simply keeps them all (tau = -inf); a heavy one is
+// flagged for k_topk_direct and tau = +inf keeps it out of the pool.
+constexpr uint32_t SMALL_QUERY_ENTRIES = 4096;
 __global__ void __launch_bounds__(RR_THREADS)
 k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys, const int* __restrict__ tl_ids,
-                  const int* __restrict__ tl_cnt, double* __restrict__ tau, int32_t* __restrict__ taui, DirtySet dirty) {
+                  const int* __restrict__ tl_cnt, const uint32_t* __restrict__ q_entries, double* __restrict__ tau,
+                  int32_t* __restrict__ taui, DirtySet dirty) {
     const int lane = threadIdx.x & 31;
     const int64_t ql = (int64_t)blockIdx.x * RR_WARPS + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) taui[nqc] = 0x7fffffff;      // sentinel: "no query" for the tcgen05 kernel's padding
@@ -631,11 +635,12 @@ k_threshold_merge(int64_t nqc, int NT, int K, const double* __restrict__ tl_keys
         if (bi != last) { found++; kth = bk; last = bi; }
     }
     if (lane == 0) {
-        const double tv = found == K ? kth : __longlong_as_double(0x7ff0000000000000LL);
+        const bool small = q_entries[q] <= SMALL_QUERY_ENTRIES;
+        const double tv = found == K ? kth : (small ? -__longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff0000000000000LL));
         tau[q] = tv;
         // the same threshold for integer scores (a dot product of bytes is below 2^31 - 1: INT_MAX masks the query)
         taui[q] = tv >= 2147483647.0 ? 0x7fffffff : (tv <= -2147483648.0 ? (int)0x80000000 : (int)ceil(tv));
-        if (found < K) dirty.mark((int)q);
+        if (found < K && !small) dirty.mark((int)q);
     }
 }
 
@@ -711,6 +716,7 @@ k_select_survivors(int64_t q0, int64_t nqc, Filter flt, const int32_t* __restric
 
 // the same for the queries whose list is long (few: those whose sampled buckets held fewer than k rows, or rows far
 // from the query): one CTA per query, the warps take interleaved chunks of the list, then the per-warp lists are merged
+template <bool REG>
 __global__ void __launch_bounds__(RR_THREADS)
 k_select_survivors_big(int64_t q0, Filter flt, const int32_t* __restrict__ qids, int self_exclude, int K, bool negate,
                        int32_t* __restrict__ ids_out, double* __restrict__ score_out, const uint32_t* __restrict__ big_list,
@@ -732,23 +738,34 @@ k_select_survivors_big(int64_t q0, Filter flt, const int32_t* __restrict__ qids,
     const int qid = qids ? qids[q] : INT32_MIN;
     const bool excl = self_exclude && qids && qid >= -128 && qid <= 127;
     int count = 0;
+    RegList rl;
+    double kth_k = 0.0;
+    int kth_i = 0;
     for (uint32_t j0 = 32u * warp; j0 < n; j0 += 32u * RR_WARPS) {
         const uint32_t j = j0 + lane;
         const double key = j < n ? sc[j] : 0.0;
         const int id = j < n ? si[j] : -1;
         bool cand = j < n && !(excl && id == qid);
-        if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
+        if (REG) { if (cand && count == K) cand = better(key, id, kth_k, kth_i); }
+        else if (cand && count == K) cand = better(key, id, mykeys[K - 1], myids[K - 1]);
         uint32_t todo = __ballot_sync(0xffffffffu, cand);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             const double kk = __shfl_sync(0xffffffffu, key, src);
             const int ii = __shfl_sync(0xffffffffu, id, src);
-            bool dup = false;
-            for (int base = 0; base < count; base += 32) dup |= __any_sync(0xffffffffu, base + lane < count && myids[base + lane] == ii);
-            if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
+            if (REG) {
+                if (!rl.contains(ii, lane)) rl.insert(K, kk, ii, lane);
+                count = rl.count;
+                if (count == K) rl.kth(K, kth_k, kth_i);
+            } else {
+                bool dup = false;
+                for (int base = 0; base < count; base += 32) dup |= __any_sync(0xffffffffu, base + lane < count && myids[base + lane] == ii);
+                if (!dup) warp_insert(mykeys, myids, count, K, kk, ii, lane);
+            }
         }
     }
+    if (REG && lane < count) { mykeys[lane] = rl.key; myids[lane] = rl.id; }   // the merge below reads the lists from shared memory
     if (lane == 0) s_counts[warp] = count;
     __syncthreads();
     if (warp == 0) {                         // merge; the same id in two lists carries the same score: adjacent, kept once
@@ -841,16 +858,17 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     h->surv_id.reserve((size_t)pool_cap);
     h->bm_tau.reserve((size_t)nqc + 2);
     // one block cleared per chunk: survivor counts, list cursors, dirty flags
-    h->bm_scnt.reserve((size_t)nqc * 4 + 4);
+    h->bm_scnt.reserve((size_t)nqc * 5 + 4);
     uint32_t* s_cnt = h->bm_scnt.p;
     uint32_t* s_fill = s_cnt + nqc;
     uint32_t* s_dirty = s_fill + nqc;
-    const DirtySet dirty{s_dirty, reinterpret_cast<int32_t*>(s_dirty + nqc), ctr + CTR_NDIRTY};   // (the list needs no clearing)
+    uint32_t* q_entries = s_dirty + nqc;
+    const DirtySet dirty{s_dirty, reinterpret_cast<int32_t*>(q_entries + nqc), ctr + CTR_NDIRTY};   // (the list needs no clearing)
     h->bm_sbase.reserve((size_t)nqc + 1);
-    DPF_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t)nqc * 3 * sizeof(uint32_t), st));
+    DPF_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t)nqc * 4 * sizeof(uint32_t), st));
     DPF_CUDA(cudaMemsetAsync(ctr + CTR_POOL, 0, 7 * sizeof(int32_t), st));      // pool cursor, chunk counts, overflow flag, dirty count
 
-    probe_and_group(h, qk, steps, probe_mode, q0, nqc, cap, use_tc);
+    probe_and_group(h, qk, steps, probe_mode, q0, nqc, cap, use_tc, q_entries);
 
     ChunkView cv;
     cv.Q = Qd + q0 * d;
@@ -909,8 +927,8 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                 else go(k_threshold<decltype(a)::value, decltype(kc)::value, false, false>, 0);
             });
         }
-        k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(nqc, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p, h->bm_tau.p,
-                                                         h->bm_taui.p, dirty); DPF_LAUNCHED();
+        k_threshold_merge<<<qgrid, RR_THREADS, 0, st2>>>(nqc, NT, topk, h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p, q_entries,
+                                                         h->bm_tau.p, h->bm_taui.p, dirty); DPF_LAUNCHED();
         DPF_CUDA(cudaGetLastError());
     }
     DPF_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
@@ -952,8 +970,13 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
             k_select_survivors<false><<<qgrid, RR_THREADS, list_smem, st>>>(0, nqc, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io,
                                                                             so, bm_stat, h->bm_big.p + 1, h->bm_big.p);
         DPF_LAUNCHED();
-        k_select_survivors_big<<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
-            0, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so, h->bm_big.p + 1, h->bm_big.p); DPF_LAUNCHED();
+        if (topk <= 32)
+            k_select_survivors_big<true><<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
+                0, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so, h->bm_big.p + 1, h->bm_big.p);
+        else
+            k_select_survivors_big<false><<<(unsigned)std::min<int64_t>(nqc, 1024), RR_THREADS, list_smem, st>>>(
+                0, flt, cv.qids, h->cfg.self_exclude_small_ids, topk, l2, io, so, h->bm_big.p + 1, h->bm_big.p);
+        DPF_LAUNCHED();
         topk_direct(h, cv, dirty, topk, metric, io, so);
         DPF_CUDA(cudaGetLastError());
     }

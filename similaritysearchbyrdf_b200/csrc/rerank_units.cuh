@@ -164,7 +164,8 @@ int u8_query_pitch();                                                      // ro
 void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units, const uint32_t* nunits_p, int metric,
                      const Filter& flt, unsigned long long* bm_stat, bool int_kernel);
 // bm_group.cu: probe -> pairs grouped by leaf -> unit records, all sized on the host without reading anything back
-void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc);
+void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc,
+                     uint32_t* q_entries);
 void emit_units(dpf_index* h, bool only_if_fp64_queries);
 void emit_tc_recs(dpf_index* h, int64_t cap, const DirtySet& dirty);                                           // the tcgen05 kernel's units
 // rerank_tc.cu
