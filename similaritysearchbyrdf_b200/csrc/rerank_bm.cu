@@ -488,11 +488,16 @@ k_threshold(const unsigned char* __restrict__ X, unsigned row_bytes, int d, Chun
     double kth = 0.0;                        // mykeys[K - 1] once the list is full
     RegList rl;
     for (int i = 0; i < sample && nonempty; ++i) nonempty &= nonempty - 1;
-    if (nonempty) {                          // the sample-th table that has a pair: the first bucket the query probes there
-        const int t = __ffs(nonempty) - 1;
-        const uint32_t leaf = cv.cache[(ql * L + t) * cv.cap];
+    // the sample-th table that has a pair: the first bucket the query probes there (in practice its own bucket) and, should
+    // it hold fewer than K rows, the next ones until K rows have been seen
+    const int t = nonempty ? __ffs(nonempty) - 1 : 0;
+    const uint32_t nb_ = nonempty ? cv.pair_cnt[ql * L + t] : 0u;
+    int seen = 0;
+    for (uint32_t e_ = 0; e_ < nb_ && (e_ == 0 || seen < K); ++e_) {
+        const uint32_t leaf = cv.cache[(ql * L + t) * cv.cap + e_];
         const uint32_t bstart = leaf_pos[leaf];
         const int len = leaf_len[leaf];
+        seen += len;
         const int32_t* bids = ids_sorted + bstart;
         const int nmine = (len + 3) >> 2;    // steps of 4 rows; ids two groups of PFT steps ahead, rows one group ahead
         uint4 raw[PFT][RN];

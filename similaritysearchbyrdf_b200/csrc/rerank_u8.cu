@@ -681,10 +681,16 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView 
     int count = 0;
     double kth = 0.0;
     RegList rl;
-    if (nonempty) {
-        const uint32_t leaf = cv.cache[(ql * L + (__ffs(nonempty) - 1)) * cv.cap];   // the first bucket the query probes there
+    // the first bucket the query probes in that table (in practice its own bucket); should it hold fewer than K rows, the
+    // next ones too, until K rows have been seen (a sample that cannot reach K rows would leave the query without a threshold)
+    const int st_ = nonempty ? __ffs(nonempty) - 1 : 0;
+    const uint32_t nb_ = nonempty ? cv.pair_cnt[ql * L + st_] : 0u;
+    int seen = 0;
+    for (uint32_t e_ = 0; e_ < nb_ && (e_ == 0 || seen < K); ++e_) {
+        const uint32_t leaf = cv.cache[(ql * L + st_) * cv.cap + e_];
         const uint32_t bstart = leaf_pos[leaf];
         const int len = leaf_len[leaf];
+        seen += len;
         const int32_t* bids = ids_sorted + bstart;
         int idA = __ldg(bids + min(lane, len - 1));
         for (int row0 = 0; row0 < len; row0 += 32) {                 // one id window = 2 tiles of 16 rows
@@ -745,7 +751,7 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView 
                         const double lb_s = __shfl_sync(0xffffffffu, lb, src);
                         const int id_s = __shfl_sync(0xffffffffu, id, src);
                         if (REG) {
-                            rl.insert(K, lb_s, id_s, lane);          // rows of one bucket are distinct; a row that is not among
+                            rl.insert(K, lb_s, id_s, lane);          // rows of one table are distinct; a row that is not among
                             count = rl.count;                        // the K best leaves the list unchanged
                             if (count == K) kth = __shfl_sync(0xffffffffu, rl.key, K - 1);
                         } else {
