@@ -286,12 +286,11 @@ def run_ours(args):
         uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
         clocks = ClockSampler(f"GPU-{uuid}" if uuid is not None else local)
         clocks.start()                          # sampled from the warm-up steps to the end of the stage pass: the same
-        t_w = time.time()                       # steps throughout, so every sample is "under load"
-        nw = 0
-        while nw < args.warmup or (time.time() - t_w < 0.6 and nw < 400):   # >= W steps, and long enough for nvidia-smi to sample
+        # steps throughout, so every sample is "under load".  The number of warm-up steps is the same on every rank (the
+        # steps are collective at N > 1): >= W, and enough of them (~0.5 s) for nvidia-smi to take a few samples
+        for nw in range(max(args.warmup, 200)):
             step_device()
-            nw += 1
-            if nw % 8 == 0:
+            if nw % 8 == 7:
                 stream.synchronize()
         launches0 = ix.stats()["kernel_launches"]
         barrier()
