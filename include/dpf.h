@@ -100,7 +100,15 @@ int dpf_fit_dense(dpf_handle h, const double* X, int64_t n);
 int dpf_fit_csr(dpf_handle h, const int64_t* indptr, const int32_t* indices, const double* values, int64_t n);
 /* X_dev stays owned by the caller and must outlive the handle (no copy is made: 100M x 96 FP64 is 76.8 GB) */
 int dpf_fit_dense_dev(dpf_handle h, const double* X_dev, int64_t n);
-int64_t dpf_size(dpf_handle h);
+int64_t dpf_size(dpf_handle h);    /* ids handed out so far (removed ids are not reused) */
+/* RandomDrawTreeMap.remove (RandomDrawTreeMap.java:1817-1932) for a batch of ids, in every table: an id leaves its bucket,
+ * an emptied bucket frees its slot, a directory node left without children is deleted from its parent (the roots stay) —
+ * with the configured tree geometry, not the reference's hard-coded 4 levels x 7 bits.
+ * removed_entries_out: (table, id) entries that were found and removed.  Ids that are not in the index are ignored.
+ * A small dpf_fit_dense afterwards is PUT id by id into the forest as it is (exactly the reference's sequence); an append
+ * so large that the forest is rebuilt re-inserts the surviving ids in ascending order, which the reference's history-
+ * dependent tree need not equal bucket for bucket (results are the same sets whenever no bucket is at the split limit). */
+int dpf_remove(dpf_handle h, const int32_t* ids, int64_t m, int64_t* removed_entries_out);
 /* The reference keeps every vector as double[] (vectorIdToVector, DensevectorRDFInit.scala:35-36).  A dense fit also
  * checks whether EVERY stored value survives a round trip through a narrower type and, if so, keeps a copy of the rows
  * in that type for the re-rank kernels, which widen it back to the identical doubles in registers (or, when the queries
@@ -253,6 +261,8 @@ enum {
     DPF_DBG_TRACE = 8,        /* 1: host wall-clock per phase of a fit, to stderr                                     */
     DPF_DBG_STORE = 9,        /* 0 default, 1 keep FP64 rows only, 2 force a float copy (skips the byte check)        */
     DPF_DBG_POOL_RECORDS = 10,/* capacity of the survivor pool in records; 0 = default (tests force the overflow path) */
+    DPF_DBG_APPEND = 11,      /* appending fit: 0 put small batches incrementally, rebuild for large ones (default);
+                                 1 always rebuild; 2 always put incrementally (rebuild only when out of head-room)     */
     DPF_DBG_COUNT = 16
 };
 int dpf_set_debug_option(dpf_handle h, int32_t option, int64_t value);

@@ -417,6 +417,42 @@ void table_insert(const dpfo* o, Table& T, int32_t id, int32_t h, int32_t pid) {
     }
 }
 
+// RandomDrawTreeMap.java:1817-1932 (remove / removeInternal / recursiveDirDelete), with the tree geometry of the
+// configuration instead of the hard-coded 4 levels x 7 bits (quirk Q12): the id leaves its bucket (the order of the others
+// is kept); a bucket that becomes empty frees its slot; a directory node that becomes empty is deleted from its parent,
+// recursively — except a root, which stays (":1913 parent is segment ... just update to null").
+bool table_remove(const dpfo* o, Table& T, int32_t id) {
+    const TreeParams& tp = o->tp;
+    if (id < 0 || (size_t)id >= T.keys.size()) return false;
+    const int32_t h = T.keys[id], pid = T.pids[id];
+    int32_t dir = pid * tp.SEG + seg_of(tp, h);
+    int level = tp.MAXL;
+    std::vector<std::pair<int32_t, int>> path;               // (parent dir, slot) of the dirs descended into
+    while (true) {
+        const int slot = slot_of(tp, h, level);
+        const int32_t e = T.dirs[dir][slot];
+        if (e < 0) { path.emplace_back(dir, slot); dir = -e - 1; level--; if (level < 0) return false; continue; }
+        if (e == 0) return false;
+        std::vector<int32_t>& b = T.buckets[e - 1];
+        auto it = std::find(b.begin(), b.end(), id);
+        if (it == b.end()) return false;
+        b.erase(it);
+        T.occupancy[pid]--;
+        if (b.empty()) {
+            T.dirs[dir][slot] = 0;
+            while (!path.empty()) {                           // recursiveDirDelete
+                bool empty = true;
+                for (int32_t v : T.dirs[dir]) if (v != 0) { empty = false; break; }
+                if (!empty) break;
+                dir = path.back().first;
+                T.dirs[dir][path.back().second] = 0;
+                path.pop_back();
+            }
+        }
+        return true;
+    }
+}
+
 // RandomDrawTreeMap.java:940-994 searchWithSimilarity (+ getInnerWithSimilarity :1106-1121)
 inline const std::vector<int32_t>* table_lookup(const dpfo* o, const Table& T, int pid, int seg, int32_t probe) {
     const TreeParams& tp = o->tp;
@@ -650,6 +686,17 @@ int dpfo_fit_csr(dpfo* o, const int64_t* indptr, const int32_t* indices, const d
 }
 
 int64_t dpfo_size(dpfo* o) { return o->n; }
+
+// removes the ids from every table (sequentially, in the order given); returns how many (table, id) entries went
+int64_t dpfo_remove(dpfo* o, const int32_t* ids, int64_t m) {
+    int64_t gone = 0;
+    for (int t = 0; t < o->cfg.L; ++t)
+        for (int64_t j = 0; j < m; ++j)
+            if (o->owns(o->tables[t].pids.size() > (size_t)ids[j] && ids[j] >= 0 ? o->tables[t].pids[ids[j]] : 0) &&
+                table_remove(o, o->tables[t], ids[j]))
+                gone++;
+    return gone;
+}
 
 int64_t dpfo_query_candidates_dense(dpfo* o, const double* Q, int64_t nq, const int32_t* qids, int steps,
                                     int probe_mode, int nthreads) {

@@ -61,6 +61,8 @@ int    dpfo_hash_csr(dpfo* o, const int64_t* indptr, const int32_t* indices, con
 int    dpfo_fit_dense(dpfo* o, const double* X, int64_t n, int nthreads);
 int    dpfo_fit_csr(dpfo* o, const int64_t* indptr, const int32_t* indices, const double* values, int64_t n, int nthreads);
 int64_t dpfo_size(dpfo* o);
+/* RandomDrawTreeMap.remove for every table (RandomDrawTreeMap.java:1817-1932); returns the (table, id) entries removed */
+int64_t dpfo_remove(dpfo* o, const int32_t* ids, int64_t m);
 
 /* candidate sets (sorted unique ids per query).  Result is held inside the oracle; returns total ids or <0. */
 int64_t dpfo_query_candidates_dense(dpfo* o, const double* Q, int64_t nq, const int32_t* qids, int steps,

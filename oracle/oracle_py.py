@@ -51,6 +51,8 @@ def lib():
         L.dpfo_fit_csr.argtypes = [vp, vp, vp, vp, i64, C.c_int]
         L.dpfo_size.restype = i64
         L.dpfo_size.argtypes = [vp]
+        L.dpfo_remove.restype = i64
+        L.dpfo_remove.argtypes = [vp, vp, i64]
         L.dpfo_query_candidates_dense.restype = i64
         L.dpfo_query_candidates_dense.argtypes = [vp, vp, i64, vp, C.c_int, C.c_int, C.c_int]
         L.dpfo_query_candidates_csr.restype = i64
@@ -235,6 +237,10 @@ class Oracle:
 
     def size(self):
         return lib().dpfo_size(self.h)
+
+    def remove(self, ids):
+        ids = _i32(ids)
+        return lib().dpfo_remove(self.h, _p(ids), len(ids))
 
     def _fetch(self, nq, total):
         assert total >= 0, total

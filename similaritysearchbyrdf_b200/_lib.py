@@ -17,7 +17,7 @@ STORE_AUTO, STORE_F64_ONLY, STORE_NARROWEST = 0, 1, 2
 STAT_COUNT, T_COUNT = 16, 16
 # dpf_set_debug_option keys (include/dpf.h): test / profiling hooks, defaults are the product path
 (DBG_RERANK, DBG_BM_KERNEL, DBG_U8_IMMA, DBG_U8I_KERNEL, DBG_TAU_TABLES, DBG_TAU_KERNEL, DBG_HASH_EXACT, DBG_CAND_BUDGET,
- DBG_TRACE, DBG_STORE, DBG_POOL_RECORDS) = range(11)
+ DBG_TRACE, DBG_STORE, DBG_POOL_RECORDS, DBG_APPEND) = range(12)
 DBG_DEFAULTS = {DBG_U8_IMMA: 1}
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
               "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",
@@ -33,7 +33,7 @@ EXPORTS = [
     "dpf_size", "dpf_query_candidates_dense", "dpf_query_candidates_csr", "dpf_query_candidates_by_id",
     "dpf_query_topk_dense", "dpf_query_topk_dense_dev", "dpf_rerank_dense", "dpf_merge_topk_dev", "dpf_dump_buckets",
     "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms", "dpf_set_store_mode", "dpf_save", "dpf_load", "dpf_set_balanced_partition", "dpf_owned_subindexes", "dpf_parse_dense_file", "dpf_parse_sparse_file",
-    "dpf_set_debug_option", "dpf_debug_leaf_pairs", "dpf_debug_tc_diag", "dpf_comm_unique_id", "dpf_comm_init", "dpf_comm_destroy",
+    "dpf_set_debug_option", "dpf_debug_leaf_pairs", "dpf_debug_tc_diag", "dpf_remove", "dpf_comm_unique_id", "dpf_comm_init", "dpf_comm_destroy",
     "dpf_fit_dense_sharded", "dpf_fit_dense_sharded_dev", "dpf_query_topk_dense_all", "dpf_query_topk_dense_all_dev",
 ]
 
@@ -96,6 +96,7 @@ def load():
     L.dpf_set_debug_option.argtypes = [vp, i32, i64]
     L.dpf_debug_leaf_pairs.argtypes = [vp, vp, vp, vp]
     L.dpf_debug_tc_diag.argtypes = [vp, vp]
+    L.dpf_remove.argtypes = [vp, vp, i64, vp]
     L.dpf_comm_unique_id.argtypes = [vp]
     L.dpf_comm_init.argtypes = [vp, vp]
     L.dpf_comm_destroy.argtypes = [vp]

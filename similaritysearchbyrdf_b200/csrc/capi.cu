@@ -490,12 +490,26 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     if (h->n == 0) assign_balanced_partition(h, n);
     // the new vectors count only once the forest and the store have been rebuilt: a failure in between (out of memory,
     // node capacity) leaves the handle un-fitted with its old size instead of fitted with stale arrays
+    // A small batch on top of a fitted index is PUT into the existing forest (O(batch): RandomDrawTreeMap.put one id
+    // after the other, incremental.cu); anything else — or a put that runs out of head-room — rebuilds from the keys.
+    const int64_t n_old = h->n;
+    const int64_t mode = h->dbg[DPF_DBG_APPEND];
+    bool incremental = h->fitted && n_old > 0 && mode != 1 && (mode == 2 || n <= std::max<int64_t>(n_old / 256, 64));
     h->fitted = false;
     h->n += n;
     try {
-        build_forest(h);
-        tr.mark("forest");
-        build_compact_store(h);
+        if (incremental) {
+            incremental = forest_insert_incremental(h, n_old, n);
+            if (incremental) rebuild_leaf_table(h);
+            tr.mark("forest (incremental put)");
+        }
+        if (!incremental) {
+            DPF_REQUIRE(h->n_removed == 0 || mode != 3, DPF_ERR_STATE, "rebuild after remove refused (debug option)");
+            build_forest(h);
+            tr.mark("forest");
+        }
+        h->fitted = true;
+        if (!(incremental && append_compact_store(h, n_old, n))) build_compact_store(h);
         tr.mark("compact store");
     } catch (...) {
         h->n -= n;
@@ -562,6 +576,35 @@ int dpf_comm_destroy(dpf_handle h) {
     return guarded(h, [&] {
         DPF_CUDA(cudaStreamSynchronize(h->stream));
         comm_destroy(h);
+    });
+}
+
+// RandomDrawTreeMap.remove (RandomDrawTreeMap.java:1817-1932) for a batch of ids, in every table
+int dpf_remove(dpf_handle h, const int32_t* ids, int64_t m, int64_t* removed_entries_out) {
+    return guarded(h, [&] {
+        require_ready(h, true);
+        DPF_REQUIRE(m >= 0 && (m == 0 || ids), DPF_ERR_INVALID, "null buffer");
+        if (removed_entries_out) *removed_entries_out = 0;
+        if (m == 0) return;
+        const int64_t gone = forest_remove(h, ids, m);
+        rebuild_leaf_table(h);
+        // a later rebuild (large append) must not bring the ids back
+        if (h->removed.cap < (size_t)h->key_ld) {
+            DevBuf<uint8_t> nr;
+            nr.reserve((size_t)h->key_ld);
+            DPF_CUDA(cudaMemsetAsync(nr.p, 0, (size_t)h->key_ld, h->stream));
+            if (h->removed.p) DPF_CUDA(cudaMemcpyAsync(nr.p, h->removed.p, h->removed.cap, cudaMemcpyDeviceToDevice, h->stream));
+            DPF_CUDA(cudaStreamSynchronize(h->stream));
+            std::swap(h->removed.p, nr.p);
+            std::swap(h->removed.cap, nr.cap);
+        }
+        const uint8_t one = 1;
+        for (int64_t j = 0; j < m; ++j)
+            if (ids[j] >= 0 && ids[j] < h->n)
+                DPF_CUDA(cudaMemcpyAsync(h->removed.p + ids[j], &one, 1, cudaMemcpyHostToDevice, h->stream));
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        h->n_removed += m;
+        if (removed_entries_out) *removed_entries_out = gone;
     });
 }
 
@@ -976,7 +1019,8 @@ int dpf_dump_buckets(dpf_handle h, int32_t table, int64_t* nbuckets_out, int64_t
         std::vector<int32_t> cp((size_t)slots), cc((size_t)slots);
         d2h(h, cp.data(), h->child_ptr.p, (size_t)slots);
         d2h(h, cc.data(), h->child_cnt.p, (size_t)slots);
-        const int64_t tb = h->h_table_base[table], tn = h->h_table_base[table + 1] - tb;
+        // the table's own range, and behind all tables the buckets an incremental put has moved (incremental.cu)
+        const int64_t tb = h->h_table_base[table], tn = h->arena_used - tb;
         std::vector<int32_t> ids((size_t)tn);
         d2h(h, ids.data(), h->ids_sorted.p + tb, (size_t)tn);
         DPF_CUDA(cudaStreamSynchronize(h->stream));

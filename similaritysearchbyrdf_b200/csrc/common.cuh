@@ -211,6 +211,9 @@ struct dpf_index {
     dpf::DevBuf<char> bm_descs;                      // TcRec records (the tcgen05 kernel's units)
     dpf::DevBuf<int32_t> bm_taui;                    // per query: integer score threshold
     int64_t max_leaf_len = 0, total_leaf_tiles = 0;  // largest leaf bucket; sum over leaves of ceil(len / 128)
+    int64_t arena_used = 0;                     // entries of ids_sorted in use: the tables, then buckets moved by put
+    dpf::DevBuf<uint8_t> removed;               // per id: removed (a rebuild skips it); empty until the first remove
+    int64_t n_removed = 0;
     int32_t num_leaves = 0;
     bool leaf_table = false;                    // false when the forest has >= 2^32 entries (row-major re-rank only)
     dpf::DevBuf<int64_t> table_base;
@@ -314,6 +317,7 @@ void prepare_family(dpf_index* h);
 // ---- store.cu -----------------------------------------------------------------------------------------------
 // (re)builds the compact store from Xdev[0 .. n); leaves Xc_kind = F64 when no narrower type is lossless
 void build_compact_store(dpf_index* h);
+bool append_compact_store(dpf_index* h, int64_t n_old, int64_t m);
 
 // ---- sort.cu ------------------------------------------------------------------------------------------------
 // stable LSD radix sort of the bit range [lo_bit, hi_bit) — result ends in (*keys_io, *vals_io) which may be
@@ -327,6 +331,10 @@ void exclusive_scan_u32(dpf_index* h, uint32_t* data, int64_t n);               
 
 // ---- forest.cu ----------------------------------------------------------------------------------------------
 void build_forest(dpf_index* h);
+void rebuild_leaf_table(dpf_index* h);
+// ---- incremental.cu -------------------------------------------------------------------------------------------
+bool forest_insert_incremental(dpf_index* h, int64_t n_old, int64_t m);   // false: no room, rebuild
+int64_t forest_remove(dpf_index* h, const int32_t* ids_host, int64_t m);  // (table, id) entries removed
 ForestView forest_view(const dpf_index* h);
 
 // ---- query.cu -----------------------------------------------------------------------------------------------

@@ -40,7 +40,7 @@ constexpr int CD_MAX_SMEM_BINS = 8192;
 template <bool SMEM>
 __global__ void __launch_bounds__(CD_THREADS)
 k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pids, int64_t n, int64_t ld, TreeParams tp,
-               OwnMask own, int32_t* __restrict__ cnt1) {
+               OwnMask own, const uint8_t* __restrict__ removed, int32_t* __restrict__ cnt1) {
     extern __shared__ int32_t hist[];
     const int t = blockIdx.y;
     const int bins = tp.R * tp.W;
@@ -52,7 +52,7 @@ k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pid
     const int64_t end = min(n, base + CD_CHUNK);
     for (int64_t i = base + threadIdx.x; i < end; i += CD_THREADS) {
         const int pid = pids[(int64_t)t * ld + i];
-        if (!own.has(pid)) continue;
+        if (!own.has(pid) || (removed && removed[i])) continue;
         const int32_t h = keys[(int64_t)t * ld + i];
         const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
         const int local = ((pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1);
@@ -72,8 +72,8 @@ k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pid
 // bit above the field set so that a 1-bit stable pass moves them behind the owned ones
 __global__ void __launch_bounds__(256)
 k_make_sort_keys(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pids, int64_t n, int64_t ld,
-                 TreeParams tp, int t0, OwnMask own, int field_bits, uint32_t* __restrict__ sk,
-                 uint32_t* __restrict__ sv) {
+                 TreeParams tp, int t0, OwnMask own, const uint8_t* __restrict__ removed, int field_bits,
+                 uint32_t* __restrict__ sk, uint32_t* __restrict__ sv) {
     const int tl = blockIdx.y;
     const int t = t0 + tl;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,7 +82,7 @@ k_make_sort_keys(const int32_t* __restrict__ keys, const uint8_t* __restrict__ p
     const int32_t h = keys[(int64_t)t * ld + i];
     const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
     uint32_t code = (uint32_t)(((tl * tp.R + pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1));
-    if (!own.has(pid)) code |= 1u << field_bits;
+    if (!own.has(pid) || (removed && removed[i])) code |= 1u << field_bits;
     sk[(int64_t)tl * n + i] = code;
     sv[(int64_t)tl * n + i] = (uint32_t)i;
 }
@@ -241,12 +241,14 @@ k_leaf_shape(const int32_t* __restrict__ leaf_len, int64_t nleaves, unsigned lon
     if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], len); atomicAdd(&out[1], tiles); }
 }
 
-static void build_leaf_table(dpf_index* h) {
+void rebuild_leaf_table(dpf_index* h);
+static void build_leaf_table(dpf_index* h) { rebuild_leaf_table(h); }
+void rebuild_leaf_table(dpf_index* h) {
     const TreeParams tp = h->tp;
     cudaStream_t st = h->stream;
     h->leaf_table = false;
     h->num_leaves = 0;
-    if (h->h_table_base[h->cfg.L] >= (1LL << 32)) return;   // positions are 32-bit: such an index re-ranks row-major
+    if ((int64_t)h->ids_sorted.cap >= (1LL << 32)) return;   // positions are 32-bit: such an index re-ranks row-major
     const int64_t nslots = (int64_t)h->num_nodes * tp.W;
     h->child_leaf.reserve((size_t)nslots + 1);
     k_leaf_flags<<<(unsigned)((nslots + 256) / 256), 256, 0, st>>>(h->child_cnt.p, nslots, h->child_leaf.p); DPF_LAUNCHED();
@@ -310,9 +312,9 @@ void build_forest(dpf_index* h) {
             const int bins = tp.R * tp.W;
             if (bins <= CD_MAX_SMEM_BINS)
                 k_count_depth1<true><<<grid, CD_THREADS, bins * sizeof(int32_t), st>>>(h->keys.p, h->pids.p, n, ld, tp, own,
-                                                                                      cnt1.p);
+                                                                                      h->removed.p, cnt1.p);
             else
-                k_count_depth1<false><<<grid, CD_THREADS, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, own, cnt1.p);
+                k_count_depth1<false><<<grid, CD_THREADS, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, own, h->removed.p, cnt1.p);
             DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
         }
@@ -341,7 +343,10 @@ void build_forest(dpf_index* h) {
             h->occupancy[p] += (double)c / L;
         }
 
-    h->ids_sorted.reserve((size_t)std::max<int64_t>(E, 1) + 64);   // slack: the re-rank copies 16-byte-aligned id windows
+    // head-room behind the tables: buckets that grow by an incremental put move there (incremental.cu); + slack: the
+    // re-rank copies 16-byte-aligned id windows
+    h->ids_sorted.reserve((size_t)std::max<int64_t>(E, 1) + (size_t)(E / 4) + (1 << 20) + 64);
+    h->arena_used = E;
     DevBuf<int32_t> tmp;
     tmp.reserve((size_t)std::max<int64_t>(E, 1));
 
@@ -361,12 +366,12 @@ void build_forest(dpf_index* h) {
             const int64_t items = (int64_t)gt * n;
             h->sk0.reserve(items); h->sk1.reserve(items); h->sv0.reserve(items); h->sv1.reserve(items);
             const dim3 grid((unsigned)((n + 255) / 256), gt);
-            k_make_sort_keys<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, t0, own, field_bits, h->sk0.p,
+            k_make_sort_keys<<<grid, 256, 0, st>>>(h->keys.p, h->pids.p, n, ld, tp, t0, own, h->removed.p, field_bits, h->sk0.p,
                                                    h->sv0.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             uint32_t *k0 = h->sk0.p, *k1 = h->sk1.p, *v0 = h->sv0.p, *v1 = h->sv1.p;
             const int64_t owned = h->h_table_base[t0 + gt] - h->h_table_base[t0];
-            if (world > 1) radix_sort_pairs_u32(h, &k0, &k1, &v0, &v1, items, field_bits, field_bits + 1);
+            if (world > 1 || h->n_removed > 0) radix_sort_pairs_u32(h, &k0, &k1, &v0, &v1, items, field_bits, field_bits + 1);
             radix_sort_pairs_u32(h, &k0, &k1, &v0, &v1, owned, 0, field_bits);
             if (owned > 0)
                 DPF_CUDA(cudaMemcpyAsync(h->ids_sorted.p + h->h_table_base[t0], v0, owned * sizeof(int32_t),
@@ -377,7 +382,7 @@ void build_forest(dpf_index* h) {
     // ---- nodes ----------------------------------------------------------------------------------------------
     const int64_t roots = (int64_t)L * tp.R;
     int64_t split_bound = tp.MAXL >= 1 ? (int64_t)tp.MAXL * (E / (tp.T + 1)) : 0;
-    const int64_t node_cap64 = roots + split_bound + 1;
+    const int64_t node_cap64 = roots + split_bound + split_bound / 4 + 4096;   // head-room for incremental puts
     DPF_REQUIRE(node_cap64 * tp.W < (1LL << 31), DPF_ERR_NOMEM, "forest would need more than 2^31 child slots");
     h->node_cap = (int32_t)node_cap64;
     h->child_ptr.reserve((size_t)node_cap64 * tp.W);

@@ -52,6 +52,36 @@ k_narrow_rows(const double* __restrict__ X, int64_t n, int d, int groups /* padd
     }
 }
 
+// rows [n_old, n_old + m) join the compact store when they fit its element type (one pass over the NEW rows only);
+// false = the caller rebuilds the store (the new rows need a wider type, or there is no room)
+bool append_compact_store(dpf_index* h, int64_t n_old, int64_t m) {
+    if (h->Xc_kind == DPF_STORE_KIND_F64) return h->store_mode == DPF_STORE_F64_ONLY || h->dbg[DPF_DBG_STORE] == 1 || n_old > 0;
+    const int d = h->cfg.d;
+    const int64_t row_bytes = h->Xc_row_bytes;
+    if ((size_t)((n_old + m) * row_bytes) > h->Xc.cap) return false;
+    cudaStream_t st = h->stream;
+    int* flags = h->counters.p + CTR_STORE_FLAGS;
+    DPF_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), st));
+    const int64_t total = m * d;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
+    k_scan_representable<<<grid, 256, 0, st>>>(h->Xdev + n_old * d, total, flags); DPF_LAUNCHED();
+    int f = 3;
+    DPF_CUDA(cudaMemcpyAsync(&f, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DPF_CUDA(cudaStreamSynchronize(st));
+    const int bad = h->Xc_kind == DPF_STORE_KIND_U8 ? 1 : 2;
+    if (f & bad) return false;
+    const int sz = h->Xc_kind == DPF_STORE_KIND_U8 ? 1 : 4;
+    const int groups = (int)(row_bytes / sz / 4);
+    const unsigned g2 = (unsigned)((m * groups + 255) / 256);
+    if (h->Xc_kind == DPF_STORE_KIND_U8)
+        k_narrow_rows<unsigned char><<<g2, 256, 0, st>>>(h->Xdev + n_old * d, m, d, groups, h->Xc.p + n_old * row_bytes);
+    else
+        k_narrow_rows<float><<<g2, 256, 0, st>>>(h->Xdev + n_old * d, m, d, groups, reinterpret_cast<float*>(h->Xc.p + n_old * row_bytes));
+    DPF_LAUNCHED();
+    DPF_CUDA(cudaGetLastError());
+    return true;
+}
+
 void build_compact_store(dpf_index* h) {
     h->Xc_kind = DPF_STORE_KIND_F64;
     h->Xc_row_bytes = (int64_t)h->cfg.d * 8;

@@ -224,6 +224,13 @@ class DPFIndex:
         indptr, indices, values = _i64(indptr), _i32(indices), _f64(values)
         self._ck(self.lib.dpf_fit_csr(self.h, _p(indptr), _p(indices), _p(values), len(indptr) - 1))
 
+    def remove(self, ids):
+        """RandomDrawTreeMap.remove for a batch of ids in every table; returns the (table, id) entries removed."""
+        ids = _i32(ids)
+        gone = C.c_int64(0)
+        self._ck(self.lib.dpf_remove(self.h, _p(ids), len(ids), C.byref(gone)))
+        return int(gone.value)
+
     # ---- queries --------------------------------------------------------------------------------------------
     def _cand_call(self, fn, nq, *args):
         off = np.empty(nq + 1, np.int64)
