@@ -156,8 +156,11 @@ int dpf_parse_sparse_file(const char* path, int64_t* indptr_out, int32_t* indice
 
 /* ---- persist / reload: the replacement for the reference's RAM-threshold spill of tree pages to disk
  * (RandomDrawTreeMap.java:2713-2773, StoreSegment.java:489-545).  dpf_save writes configuration, hash functions, the
- * vector store and every vector's keys / sub-index ids; dpf_load restores them on `device` and re-creates the flat forest
- * from the stored keys (no re-hashing), bit-identical to the saved index. */
+ * vector store, every vector's keys / sub-index ids and the flat forest; dpf_load restores them on `device` (no re-hashing,
+ * no rebuild), bit-identical to the saved index — also after incremental puts and removes. */
+/* A file is the shard of the rank that wrote it: configuration, hash functions, ownership of sub-indexes (also a
+ * balanced one), store mode, vectors, keys, removed ids and the forest arrays as they stand; every rank of a multi-GPU
+ * index saves and loads its own file. */
 int dpf_save(dpf_handle h, const char* path);
 int dpf_load(const char* path, int32_t device, dpf_handle* out);
 

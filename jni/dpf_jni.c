@@ -215,3 +215,69 @@ JNIEXPORT jintArray JNICALL Java_mclab_deploy_NativeDPF_hashDense(JNIEnv* env, j
     free(keys);
     return out;
 }
+
+/* long remove(long h, int[] ids) — RandomDrawTreeMap.remove for a batch of ids in every table
+ * (RandomDrawTreeMap.java:1817-1932); returns the (table, id) entries removed */
+JNIEXPORT jlong JNICALL Java_mclab_deploy_NativeDPF_remove(JNIEnv* env, jclass cls, jlong jh, jintArray jids) {
+    (void)cls;
+    dpf_handle h = (dpf_handle)(intptr_t)jh;
+    const jsize m = (*env)->GetArrayLength(env, jids);
+    jint* ids = (jint*)(*env)->GetPrimitiveArrayCritical(env, jids, 0);
+    int64_t gone = 0;
+    int rc = dpf_remove(h, ids, m, &gone);
+    (*env)->ReleasePrimitiveArrayCritical(env, jids, ids, JNI_ABORT);
+    if (rc != DPF_OK) throw_dpf(env, h, rc);
+    return (jlong)gone;
+}
+
+/* ---- multi-GPU: one handle per GPU, NCCL inside the library (Partitioner.scala:27-64 mapped onto the GPUs) ---------- */
+/* byte[] commUniqueId() — rank 0; the caller hands the 128 bytes to the other ranks */
+JNIEXPORT jbyteArray JNICALL Java_mclab_deploy_NativeDPF_commUniqueId(JNIEnv* env, jclass cls) {
+    (void)cls;
+    uint8_t id[DPF_COMM_ID_BYTES];
+    int rc = dpf_comm_unique_id(id);
+    if (rc != DPF_OK) { throw_dpf(env, 0, rc); return 0; }
+    jbyteArray out = (*env)->NewByteArray(env, DPF_COMM_ID_BYTES);
+    (*env)->SetByteArrayRegion(env, out, 0, DPF_COMM_ID_BYTES, (const jbyte*)id);
+    return out;
+}
+
+/* void commInit(long h, byte[] id) — collective over the `world` ranks of the handle's configuration */
+JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_commInit(JNIEnv* env, jclass cls, jlong jh, jbyteArray jid) {
+    (void)cls;
+    dpf_handle h = (dpf_handle)(intptr_t)jh;
+    uint8_t id[DPF_COMM_ID_BYTES];
+    (*env)->GetByteArrayRegion(env, jid, 0, DPF_COMM_ID_BYTES, (jbyte*)id);
+    int rc = dpf_comm_init(h, id);
+    if (rc != DPF_OK) throw_dpf(env, h, rc);
+}
+
+/* void fitDenseSharded(long h, double[] X, long n) — collective newMultiThreadFit: every rank hashes n / world vectors */
+JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_fitDenseSharded(JNIEnv* env, jclass cls, jlong jh, jdoubleArray jX, jlong n) {
+    (void)cls;
+    dpf_handle h = (dpf_handle)(intptr_t)jh;
+    double* X = (double*)(*env)->GetPrimitiveArrayCritical(env, jX, 0);
+    int rc = dpf_fit_dense_sharded(h, X, n);
+    (*env)->ReleasePrimitiveArrayCritical(env, jX, X, JNI_ABORT);
+    if (rc != DPF_OK) throw_dpf(env, h, rc);
+}
+
+/* void queryTopKAll(long h, double[] Q, int[] qids, int steps, int topK, int metric, int[] idsOut, double[] scoresOut)
+ * — collective: the same queries on every rank, the merged global top k on every rank */
+JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_queryTopKAll(JNIEnv* env, jclass cls, jlong jh, jdoubleArray jQ,
+                                                                 jintArray jqids, jint steps, jint topk, jint metric,
+                                                                 jintArray jids, jdoubleArray jsc) {
+    (void)cls;
+    dpf_handle h = (dpf_handle)(intptr_t)jh;
+    const jsize nq = (*env)->GetArrayLength(env, jids) / topk;
+    double* Q = (double*)(*env)->GetPrimitiveArrayCritical(env, jQ, 0);
+    jint* qids = jqids ? (jint*)(*env)->GetPrimitiveArrayCritical(env, jqids, 0) : 0;
+    jint* ids = (jint*)(*env)->GetPrimitiveArrayCritical(env, jids, 0);
+    double* sc = (double*)(*env)->GetPrimitiveArrayCritical(env, jsc, 0);
+    int rc = dpf_query_topk_dense_all(h, Q, nq, qids, steps, DPF_PROBE_DENSE, topk, metric, ids, sc);
+    (*env)->ReleasePrimitiveArrayCritical(env, jsc, sc, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, jids, ids, 0);
+    if (qids) (*env)->ReleasePrimitiveArrayCritical(env, jqids, qids, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jQ, Q, JNI_ABORT);
+    if (rc != DPF_OK) throw_dpf(env, h, rc);
+}

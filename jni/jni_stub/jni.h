@@ -8,6 +8,7 @@ typedef int32_t jint;
 typedef int64_t jlong;
 typedef double jdouble;
 typedef uint8_t jboolean;
+typedef int8_t jbyte;
 typedef jint jsize;
 typedef void* jobject;
 typedef jobject jclass;
@@ -15,6 +16,7 @@ typedef jobject jarray;
 typedef jarray jintArray;
 typedef jarray jlongArray;
 typedef jarray jdoubleArray;
+typedef jarray jbyteArray;
 typedef jobject jstring;
 struct JNINativeInterface_;
 typedef const struct JNINativeInterface_* JNIEnv;
@@ -29,6 +31,9 @@ struct JNINativeInterface_ {
     jclass (*FindClass)(JNIEnv*, const char*);
     jint (*ThrowNew)(JNIEnv*, jclass, const char*);
     void* (*GetDirectBufferAddress)(JNIEnv*, jobject);
+    jbyteArray (*NewByteArray)(JNIEnv*, jsize);
+    void (*SetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, const jbyte*);
+    void (*GetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, jbyte*);
 };
 #define JNIEXPORT __attribute__((visibility("default")))
 #define JNICALL

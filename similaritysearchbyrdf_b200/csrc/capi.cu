@@ -862,7 +862,12 @@ int dpf_rerank_dense(dpf_handle h, const double* Q, int64_t nq, const int64_t* o
 }
 
 // ---- persist / reload -------------------------------------------------------------------------------------------
-// File = "DPFIDX01" | dpf_config | P, dense, has_bw, n, nnz | A | chain | [b, w] | Ap | store (X or CSR) | keys | pids.
+// File = "DPFIDX02" | dpf_config | P, dense, has_bw, n, nnz | shard (store mode, balanced flag, ownership mask, removed
+// count) | A | chain | [b, w] | Ap | store (X or CSR) | keys | pids | [removed flags].
+// A file holds the shard of the rank that saved it: on G GPUs every rank saves and loads its own file, and gets back the
+// sub-indexes it owned (also when they were dealt by occupancy) and the store mode it was fitted with.  The forest
+// arrays are written as they stand (nodes, bucket ranges, the arena of buckets moved by incremental puts): after puts
+// and removes the tree is no longer a function of the keys alone, and a reload must be the same tree.
 // The flat forest is not written: it is a pure function of (keys, pids, ids in ascending order) and build_forest
 // re-creates it at > 150M vectors/s, bit for bit (the same call an append makes) — what would be expensive to redo,
 // hashing the vectors, is what the file keeps.
@@ -898,7 +903,12 @@ template <class T>
 void put(FILE* f, const T& v) { DPF_REQUIRE(fwrite(&v, sizeof(T), 1, f) == 1, DPF_ERR_INVALID, "dpf_save: short write"); }
 template <class T>
 void get(FILE* f, T& v) { DPF_REQUIRE(fread(&v, sizeof(T), 1, f) == 1, DPF_ERR_INVALID, "dpf_load: truncated file"); }
-const char kMagic[8] = {'D', 'P', 'F', 'I', 'D', 'X', '0', '1'};
+const char kMagic[8] = {'D', 'P', 'F', 'I', 'D', 'X', '0', '2'};
+struct ShardHeader {
+    int32_t store_mode, balance_partition, own_fixed, reserved;
+    uint32_t own[8];
+    int64_t n_removed;
+};
 }  // namespace
 extern "C" {
 
@@ -915,6 +925,13 @@ int dpf_save(dpf_handle h, const char* path) {
         put(f, h->cfg);
         const int32_t P = h->P, dense = h->dense ? 1 : 0, has_bw = h->cfg.family_kind == DPF_FAMILY_PSTABLE ? 1 : 0;
         put(f, P); put(f, dense); put(f, has_bw); put(f, h->n); put(f, h->sp_nnz);
+        ShardHeader sh{};
+        sh.store_mode = h->store_mode;
+        sh.balance_partition = h->balance_partition ? 1 : 0;
+        sh.own_fixed = h->own_fixed ? 1 : 0;
+        for (int i = 0; i < 8; ++i) sh.own[i] = h->own.w[i];
+        sh.n_removed = h->n_removed;
+        put(f, sh);
         dev_to_file(h, f, h->A.p, (size_t)P * d);
         dev_to_file(h, f, h->chain.p, (size_t)L * k);
         if (has_bw) { dev_to_file(h, f, h->fb.p, (size_t)P); dev_to_file(h, f, h->fw.p, (size_t)P); }
@@ -928,6 +945,17 @@ int dpf_save(dpf_handle h, const char* path) {
         }
         for (int t = 0; t < L; ++t) dev_to_file(h, f, h->keys.p + (size_t)t * h->key_ld, (size_t)h->n);
         for (int t = 0; t < L; ++t) dev_to_file(h, f, h->pids.p + (size_t)t * h->key_ld, (size_t)h->n);
+        if (h->n_removed > 0) dev_to_file(h, f, h->removed.p, (size_t)h->n);
+        // the forest itself, as it stands (after incremental puts and removes it is not a function of the keys alone)
+        const int64_t slots = (int64_t)h->num_nodes * h->tp.W;
+        put(f, h->num_nodes); put(f, h->arena_used);
+        for (int t = 0; t <= L; ++t) put(f, h->h_table_base[(size_t)t]);
+        for (int i : {DPF_STAT_SINGLETON_SPLITS, DPF_STAT_SPLITS}) put(f, h->stats[i]);
+        for (double v : h->occupancy) put(f, v);
+        dev_to_file(h, f, h->child_ptr.p, (size_t)slots);
+        dev_to_file(h, f, h->child_cnt.p, (size_t)slots);
+        dev_to_file(h, f, h->node_table.p, (size_t)h->num_nodes);
+        dev_to_file(h, f, h->ids_sorted.p, (size_t)h->arena_used);
         DPF_REQUIRE(fflush(f) == 0, DPF_ERR_INVALID, "dpf_save: flush failed");
     });
 }
@@ -953,6 +981,12 @@ int dpf_load(const char* path, int32_t device, dpf_handle* out) {
         get(f, P); get(f, dense); get(f, has_bw); get(f, n); get(f, nnz);
         DPF_REQUIRE(P > 0 && n > 0 && nnz >= 0 && has_bw == (cfg.family_kind == DPF_FAMILY_PSTABLE ? 1 : 0), DPF_ERR_INVALID,
                     "dpf_load: bad header");
+        ShardHeader sh{};
+        get(f, sh);
+        h->store_mode = sh.store_mode;
+        h->balance_partition = sh.balance_partition != 0;
+        h->own_fixed = sh.own_fixed != 0;
+        for (int i = 0; i < 8; ++i) h->own.w[i] = sh.own[i];
         h->P = P;
         h->PW = (P + 31) / 32;
         h->hA.resize((size_t)P * d);
@@ -987,8 +1021,41 @@ int dpf_load(const char* path, int32_t device, dpf_handle* out) {
         grow_keys(h, n);
         for (int t = 0; t < L; ++t) file_to_dev(h, f, h->keys.p + (size_t)t * h->key_ld, (size_t)n);
         for (int t = 0; t < L; ++t) file_to_dev(h, f, h->pids.p + (size_t)t * h->key_ld, (size_t)n);
+        if (sh.n_removed > 0) {
+            h->removed.reserve((size_t)h->key_ld);
+            DPF_CUDA(cudaMemsetAsync(h->removed.p, 0, (size_t)h->key_ld, h->stream));
+            file_to_dev(h, f, h->removed.p, (size_t)n);
+            h->n_removed = sh.n_removed;
+        }
         h->n = n;
-        build_forest(h);
+        {   // the forest as it was saved, with the head-room a build leaves for incremental puts
+            int32_t num_nodes = 0;
+            int64_t arena_used = 0;
+            get(f, num_nodes); get(f, arena_used);
+            DPF_REQUIRE(num_nodes > 0 && arena_used >= 0, DPF_ERR_INVALID, "dpf_load: bad forest header");
+            h->h_table_base.assign((size_t)L + 1, 0);
+            for (int t = 0; t <= L; ++t) get(f, h->h_table_base[(size_t)t]);
+            for (int i : {DPF_STAT_SINGLETON_SPLITS, DPF_STAT_SPLITS}) get(f, h->stats[i]);
+            for (double& v : h->occupancy) get(f, v);
+            h->num_nodes = num_nodes;
+            h->node_cap = num_nodes + num_nodes / 4 + 4096;
+            const int64_t slots = (int64_t)num_nodes * h->tp.W;
+            h->child_ptr.reserve((size_t)h->node_cap * h->tp.W);
+            h->child_cnt.reserve((size_t)h->node_cap * h->tp.W);
+            h->node_table.reserve((size_t)h->node_cap);
+            h->ids_sorted.reserve((size_t)arena_used + (size_t)(arena_used / 4) + (1 << 20) + 64);
+            file_to_dev(h, f, h->child_ptr.p, (size_t)slots);
+            file_to_dev(h, f, h->child_cnt.p, (size_t)slots);
+            file_to_dev(h, f, h->node_table.p, (size_t)num_nodes);
+            file_to_dev(h, f, h->ids_sorted.p, (size_t)arena_used);
+            h->arena_used = arena_used;
+            h->table_base.reserve((size_t)L + 1);
+            h2d(h, h->table_base.p, h->h_table_base.data(), (size_t)L + 1);
+            DPF_CUDA(cudaStreamSynchronize(h->stream));
+            h->stats[DPF_STAT_DIR_NODES] = num_nodes;
+            rebuild_leaf_table(h);
+            h->fitted = true;
+        }
         if (h->dense) build_compact_store(h);
         h->stats[DPF_STAT_SIZE] = h->n;
         DPF_CUDA(cudaStreamSynchronize(h->stream));

@@ -282,3 +282,33 @@ def test_load_rejects_garbage(tmp_path):
     p.write_bytes(b"not an index")
     with pytest.raises(B.DpfError):
         DPFIndex.load(p)
+
+
+def test_save_load_keeps_the_shard_the_store_mode_and_the_removed_ids(tmp_path):
+    """A file holds the shard of the rank that saved it (ownership mask — also a balanced one —, store mode, removed ids):
+    two ranks save, two fresh handles load, and the reloaded shards answer exactly like the saved ones."""
+    from similaritysearchbyrdf_b200 import DPFIndex
+    X, Q = synth.config2(n=20_000, nq=100, d=128)
+    A, chain = synth.angle_family(128, 128, 10, 3, 32, 88389)
+    Ap = synth.partitioner_family(30, 3, 88390)
+    gone = np.arange(100, 3000, 7, dtype=np.int32)
+    shards, loaded = [], []
+    for r in range(2):
+        s = U.make_index(128, A, chain, Ap, bucket_overflow=60, rank=r, world=2, store_mode=B.STORE_F64_ONLY)
+        s.set_balanced_partition(True)
+        s.fit_dense(X)
+        s.remove(gone)
+        s.save(tmp_path / f"shard{r}.dpf")
+        shards.append(s)
+        loaded.append(DPFIndex.load(tmp_path / f"shard{r}.dpf"))
+    owned = np.stack([s.owned_subindexes() for s in loaded])
+    assert (owned.sum(axis=0) == 1).all() and np.array_equal(owned, np.stack([s.owned_subindexes() for s in shards]))
+    for s, l in zip(shards, loaded):
+        assert l.stats()["store_kind"] == s.stats()["store_kind"] == B.STORE_KIND_F64          # the mode came back, not AUTO
+        for t in (0, 11, 29):
+            for a, b in zip(s.dump_buckets(t), l.dump_buckets(t)):
+                assert np.array_equal(a, b)
+        i1, s1 = s.query_topk_dense(Q, None, 1, 10, B.METRIC_DOT)
+        i2, s2 = l.query_topk_dense(Q, None, 1, 10, B.METRIC_DOT)
+        assert np.array_equal(i1, i2) and np.array_equal(s1, s2, equal_nan=True)
+        assert not np.isin(i2, gone).any()
