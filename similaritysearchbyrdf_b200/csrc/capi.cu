@@ -500,7 +500,7 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     try {
         if (incremental) {
             incremental = forest_insert_incremental(h, n_old, n);
-            if (incremental) rebuild_leaf_table(h);
+            if (incremental) { rebuild_leaf_table(h); update_occupancy(h); }
             tr.mark("forest (incremental put)");
         }
         if (!incremental) {
@@ -604,6 +604,7 @@ int dpf_remove(dpf_handle h, const int32_t* ids, int64_t m, int64_t* removed_ent
                 DPF_CUDA(cudaMemcpyAsync(h->removed.p + ids[j], &one, 1, cudaMemcpyHostToDevice, h->stream));
         DPF_CUDA(cudaStreamSynchronize(h->stream));
         h->n_removed += m;
+        update_occupancy(h);
         if (removed_entries_out) *removed_entries_out = gone;
     });
 }

@@ -335,6 +335,7 @@ void rebuild_leaf_table(dpf_index* h);
 // ---- incremental.cu -------------------------------------------------------------------------------------------
 bool forest_insert_incremental(dpf_index* h, int64_t n_old, int64_t m);   // false: no room, rebuild
 int64_t forest_remove(dpf_index* h, const int32_t* ids_host, int64_t m);  // (table, id) entries removed
+void update_occupancy(dpf_index* h);                                      // sub-index occupancy after a put / remove
 ForestView forest_view(const dpf_index* h);
 
 // ---- query.cu -----------------------------------------------------------------------------------------------

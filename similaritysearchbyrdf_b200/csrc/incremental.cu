@@ -271,6 +271,35 @@ k_collapse_dirs(TreeParams tp, int64_t roots, int32_t* __restrict__ child_ptr, i
     }
 }
 
+// ids per sub-index (numberOfObjectsInEachPartition, RandomDrawTreeMap.java:1572-1573), owned and not removed, summed
+// over the tables: the build derives it from its histogram, a put / remove recounts the sub-index ids (L bytes per id)
+__global__ void __launch_bounds__(256)
+k_occupancy(const uint8_t* __restrict__ pids, const uint8_t* __restrict__ removed, int64_t n, int64_t ld, OwnMask own,
+            unsigned long long* __restrict__ hist /* 256 */) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pid = pids[(int64_t)t * ld + i];
+        if (own.has(pid) && !(removed && removed[i])) atomicAdd(&sh[pid], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+void update_occupancy(dpf_index* h) {
+    DevBuf<unsigned long long> hist;
+    hist.reserve(256);
+    DPF_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
+    const dim3 grid((unsigned)std::min<int64_t>((h->n + 255) / 256, 1024), h->cfg.L);
+    k_occupancy<<<grid, 256, 0, h->stream>>>(h->pids.p, h->removed.p, h->n, h->key_ld, h->own, hist.p); DPF_LAUNCHED();
+    unsigned long long occ[256];
+    DPF_CUDA(cudaMemcpyAsync(occ, hist.p, sizeof(occ), cudaMemcpyDeviceToHost, h->stream));
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t p = 0; p < h->occupancy.size(); ++p) h->occupancy[p] = (double)occ[p] / h->cfg.L;
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 // sorted (slot, id) keys of the batch in h->sk64a / sk64b, run heads in h->work0; returns the pointer to the sorted keys
 static unsigned long long* locate_and_group(dpf_index* h, const int32_t* ids_dev, int64_t m) {
