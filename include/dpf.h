@@ -166,10 +166,12 @@ int dpf_load(const char* path, int32_t device, dpf_handle* out);
 
 /* ---- multi-GPU: which sub-indexes a rank owns.  Default: sub-index p of every table lives on GPU p mod world.  The
  * content-based partition is skewed (sub-indexes hold 64k..224k of 1M ids in configs[1]), so with enable != 0 the first
- * dense fit deals the sub-indexes to the GPUs by occupancy instead (largest first, to the least loaded GPU); every rank
- * derives the same assignment from the replicated vectors.  Results are unaffected.  Call before fit. */
+ * dense fit deals the L x 2^pb (table, sub-index) cells — each one of the reference's per-partition stores — to the GPUs
+ * by occupancy instead (largest first, to the least loaded GPU); every rank derives the same assignment from the
+ * replicated vectors.  Results are unaffected.  Call before fit. */
 int dpf_set_balanced_partition(dpf_handle h, int32_t enable);
-/* owned_out[p] = 1 for the 2^pb sub-indexes this handle owns (after the first fit when the assignment is balanced) */
+/* owned_out[t * 2^pb + p] = 1 for the cells (sub-index p of table t) this handle owns, L x 2^pb flags (after the first
+ * fit when the assignment is balanced; p mod world == rank in every table otherwise) */
 int dpf_owned_subindexes(dpf_handle h, uint8_t* owned_out);
 
 /* ---- multi-GPU data plane inside the library: one handle (rank) per GPU, NCCL over NVLink between them (the library
@@ -260,6 +262,7 @@ enum {
     DPF_DBG_TAU_TABLES = 4,   /* threshold samples per query; 0 = default                                             */
     DPF_DBG_TAU_KERNEL = 5,   /* 0 default (tensor pipe), 1 CUDA-core DP4A / FMA form                                 */
     DPF_DBG_HASH_EXACT = 6,   /* 1: angle keys from the reference-order CUDA-core kernel instead of DMMA + fix-up     */
+                              /* 2: keys packed by the bit-by-bit kernel instead of the table-driven one             */
     DPF_DBG_CAND_BUDGET = 7,  /* candidate ids per chunk of a query batch (row-major / candidate-set paths); 0 default */
     DPF_DBG_TRACE = 8,        /* 1: host wall-clock per phase of a fit, to stderr                                     */
     DPF_DBG_STORE = 9,        /* 0 default, 1 keep FP64 rows only, 2 force a float copy (skips the byte check)        */

@@ -265,9 +265,10 @@ struct dpfo {
     std::vector<int64_t> cand_off;
     std::vector<int32_t> cand_ids;
     std::atomic<int64_t> nlz_gt28{0};
-    std::vector<uint8_t> owned;       // explicit ownership of sub-indexes (dpfo_set_owned); empty = p % world == rank
-    bool owns(int p) const {
-        if (!owned.empty()) return owned[(size_t)p] != 0;
+    std::vector<uint8_t> owned;       // explicit ownership of (table, sub-index) cells, L x 2^pb (dpfo_set_owned[_cells]);
+                                      // empty = p % world == rank in every table
+    bool owns(int t, int p) const {
+        if (!owned.empty()) return owned[((size_t)t << cfg.pb) + (size_t)p] != 0;
         return cfg.world <= 1 || (p % cfg.world) == cfg.rank;
     }
 };
@@ -485,7 +486,7 @@ void table_query(dpfo* o, const Table& T, int table, int32_t h, int32_t qid, int
     for (int pi = 0; pi < nprobes; ++pi) {
         for (int s = 0; s < np; ++s) {                       // findStepWiseSubIndexIDs :613-621
             if (java_bitcount(s ^ pid) > steps) continue;
-            if (!o->owns(s)) continue;                       // another shard owns it
+            if (!o->owns(table, s)) continue;                // another shard owns it
             const std::vector<int32_t>* b = table_lookup(o, T, s, seg, probes[pi]);
             if (!b) continue;
             for (int32_t y : *b) {
@@ -584,8 +585,19 @@ int dpfo_set_family(dpfo* o, const double* A, const int32_t* chain_idx, const do
  * assignment, dpf_set_balanced_partition); NULL restores p % world == rank */
 int dpfo_set_owned(dpfo* o, const uint8_t* owned) {
     if (!o) return 1;
-    if (!owned) { o->owned.clear(); return 0; }
-    o->owned.assign(owned, owned + ((size_t)1 << o->cfg.pb));
+    o->owned.clear();
+    if (!owned) return 0;
+    for (int t = 0; t < o->cfg.L; ++t) o->owned.insert(o->owned.end(), owned, owned + ((size_t)1 << o->cfg.pb));
+    return 0;
+}
+
+/* the same per (table, sub-index) cell: owned[t * 2^pb + p].  Each cell is one of the reference's per-partition stores
+ * (RandomDrawTreeMap.java:1430-1459); which instance holds it does not change what a search over all instances finds */
+int dpfo_set_owned_cells(dpfo* o, const uint8_t* owned) {
+    if (!o) return 1;
+    o->owned.clear();
+    if (!owned) return 0;
+    o->owned.assign(owned, owned + ((size_t)o->cfg.L << o->cfg.pb));
     return 0;
 }
 
@@ -650,7 +662,7 @@ static int fit_common(dpfo* o, const std::vector<int32_t>& keys, const std::vect
                     Tb.pids[base + i] = pids[(size_t)t * n + i];
                 }
                 for (int64_t i = 0; i < n; ++i) {
-                    if (!o->owns(pids[(size_t)t * n + i])) continue;
+                    if (!o->owns(t, pids[(size_t)t * n + i])) continue;
                     table_insert(o, Tb, (int32_t)(base + i), keys[(size_t)t * n + i], pids[(size_t)t * n + i]);
                 }
             }
@@ -692,7 +704,7 @@ int64_t dpfo_remove(dpfo* o, const int32_t* ids, int64_t m) {
     int64_t gone = 0;
     for (int t = 0; t < o->cfg.L; ++t)
         for (int64_t j = 0; j < m; ++j)
-            if (o->owns(o->tables[t].pids.size() > (size_t)ids[j] && ids[j] >= 0 ? o->tables[t].pids[ids[j]] : 0) &&
+            if (o->owns(t, o->tables[t].pids.size() > (size_t)ids[j] && ids[j] >= 0 ? o->tables[t].pids[ids[j]] : 0) &&
                 table_remove(o, o->tables[t], ids[j]))
                 gone++;
     return gone;

@@ -49,6 +49,7 @@ int    dpfo_set_family(dpfo* o, const double* A, const int32_t* chain_idx, const
 /* Ap: L x pb x 32 row-major — per-table private partitioner functions (Partitioner.scala:27-64) */
 int    dpfo_set_partitioners(dpfo* o, const double* Ap);
 int    dpfo_set_owned(dpfo* o, const uint8_t* owned /* 2^pb flags or NULL */);
+int    dpfo_set_owned_cells(dpfo* o, const uint8_t* owned /* L x 2^pb flags or NULL */);
 
 /* keys_out / pids_out: L x n (table-major).  nthreads<=0 => hardware_concurrency */
 int    dpfo_hash_dense(dpfo* o, const double* X, int64_t n, int32_t* keys_out, int32_t* pids_out, int nthreads);

@@ -45,6 +45,7 @@ def lib():
         L.dpfo_set_family.argtypes = [vp, vp, vp, vp, vp]
         L.dpfo_set_partitioners.argtypes = [vp, vp]
         L.dpfo_set_owned.argtypes = [vp, vp]
+        L.dpfo_set_owned_cells.argtypes = [vp, vp]
         L.dpfo_hash_dense.argtypes = [vp, vp, i64, vp, vp, C.c_int]
         L.dpfo_hash_csr.argtypes = [vp, vp, vp, vp, i64, vp, vp, C.c_int]
         L.dpfo_fit_dense.argtypes = [vp, vp, i64, C.c_int]
@@ -205,9 +206,18 @@ class Oracle:
         lib().dpfo_set_partitioners(self.h, _p(Ap))
 
     def set_owned(self, owned):
-        """Explicit shard: flags of the sub-indexes this instance owns (None = p % world == rank)."""
-        owned = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
-        lib().dpfo_set_owned(self.h, _p(owned))
+        """Explicit shard: flags of the sub-indexes (shape 2^pb: the same in every table) or of the (table, sub-index)
+        cells (shape L x 2^pb) this instance owns; None = p % world == rank."""
+        if owned is None:
+            lib().dpfo_set_owned(self.h, None)
+            return
+        owned = np.ascontiguousarray(owned, dtype=np.uint8)
+        if owned.ndim == 2:
+            assert owned.shape == (self.L, 1 << self.pb)
+            lib().dpfo_set_owned_cells(self.h, _p(owned))
+        else:
+            assert owned.shape == (1 << self.pb,)
+            lib().dpfo_set_owned(self.h, _p(owned))
 
     def hash_dense(self, X, nthreads=0):
         X = _f64(X)

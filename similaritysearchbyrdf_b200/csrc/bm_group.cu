@@ -41,7 +41,7 @@ k_probe_leaves(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __r
         if (wid < nqc * c.L) {
             const int pid = qpids[(int64_t)(wid % c.L) * ld + q0 + wid / c.L];
             bool any = false;
-            for (int sub = 0; sub < np; ++sub) any |= __popc(sub ^ pid) <= c.steps && c.own.has(sub);
+            for (int sub = 0; sub < np; ++sub) any |= __popc(sub ^ pid) <= c.steps && c.own.has((int)(wid % c.L), sub);
             if (any) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)threadIdx.x;
             else pair_cnt[wid] = 0u;
         }
@@ -62,7 +62,7 @@ k_probe_leaves(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __r
         } else {
             for (int sub = 0; sub < np; ++sub) {       // findStepWiseSubIndexIDs (RandomDrawTreeMap.java:613-621)
                 if (__popc(sub ^ pid) > c.steps) continue;
-                if (!c.own.has(sub)) continue;         // this GPU's sub-forest only
+                if (!c.own.has(t, sub)) continue;      // this GPU's sub-forest only
                 bool leader;
                 uint32_t leaf;
                 int cnt;

@@ -73,6 +73,14 @@ void d2h(dpf_index* h, T* dst, const T* src, size_t n) {
     if (n) DPF_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 }
 
+// the ownership table on the device follows the host copy (pageable source: the copy is staged before the call returns)
+void upload_ownership(dpf_index* h) {
+    h->own_dev.reserve(h->own_cells.size());
+    h2d(h, h->own_dev.p, h->own_cells.data(), h->own_cells.size());
+    DPF_CUDA(cudaStreamSynchronize(h->stream));
+    h->own.cells = h->own_dev.p;
+}
+
 // clears the per-batch device counters (one memset); every query entry point starts with it
 void begin_batch(dpf_index* h) {
     DPF_CUDA(cudaMemsetAsync(h->counters.p + CTR_BATCH_FIRST, 0, (CTR_BATCH_END - CTR_BATCH_FIRST) * sizeof(int32_t), h->stream));
@@ -241,8 +249,11 @@ int dpf_create(const dpf_config* cfg, dpf_handle* out) {
         h->counters.reserve(CTR_COUNT);
         DPF_CUDA(cudaMemsetAsync(h->counters.p, 0, CTR_COUNT * sizeof(int32_t), h->stream));
         h->occupancy.assign(1 << cfg->pb, 0.0);
-        for (int p = 0; p < (1 << cfg->pb); ++p)      // Partitioner scheme on G GPUs: sub-index p lives on GPU p mod G
-            if (cfg->world <= 1 || p % cfg->world == cfg->rank) h->own.w[p >> 5] |= 1u << (p & 31);
+        h->own_cells.assign((size_t)cfg->L * kOwnWords, 0u);
+        for (int t = 0; t < cfg->L; ++t)
+            for (int p = 0; p < (1 << cfg->pb); ++p)  // Partitioner scheme on G GPUs: sub-index p lives on GPU p mod G
+                if (cfg->world <= 1 || p % cfg->world == cfg->rank) h->own_cells[(size_t)t * kOwnWords + (p >> 5)] |= 1u << (p & 31);
+        upload_ownership(h);
     } catch (const Error& e) {
         dpf_destroy(h);
         return e.code;
@@ -406,11 +417,14 @@ struct PhaseTrace {
     }
 };
 
-// dpf_set_balanced_partition: at the first fit, sub-indexes are dealt to the GPUs largest first, each to the GPU with the
-// fewest ids so far (occupancy summed over the tables).  Vectors and hash functions are replicated, so every rank
-// computes the same assignment from the same pids; it is then kept for the life of the handle.
+// dpf_set_balanced_partition: at the first fit, the (table, sub-index) cells are dealt to the GPUs largest first, each to
+// the GPU with the fewest ids so far.  A cell is one of the reference's per-partition stores
+// (RandomDrawTreeMap.java:1430-1459), so this only chooses where each store lives: with 8 sub-indexes whose sizes differ
+// by 3.5x (configs[1]) whole sub-indexes cannot be spread evenly over 8 GPUs, their 240 cells can.  Vectors and hash
+// functions are replicated, so every rank computes the same assignment from the same pids; it is then kept for the life
+// of the handle.
 __global__ void __launch_bounds__(256) k_pid_histogram(const uint8_t* __restrict__ pids, int64_t n, int64_t ld, int L,
-                                                       unsigned long long* __restrict__ hist /* 256 */) {
+                                                       unsigned long long* __restrict__ hist /* L x 256 */) {
     __shared__ unsigned int sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
@@ -418,33 +432,37 @@ __global__ void __launch_bounds__(256) k_pid_histogram(const uint8_t* __restrict
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(&sh[pids[(int64_t)t * ld + i]], 1u);
     __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+    if (sh[threadIdx.x]) atomicAdd(&hist[(size_t)t * 256 + threadIdx.x], (unsigned long long)sh[threadIdx.x]);
     (void)L;
 }
 
 static void assign_balanced_partition(dpf_index* h, int64_t n_new) {
     if (!h->balance_partition || h->own_fixed || h->cfg.world <= 1) return;
     const int np = 1 << h->cfg.pb, G = h->cfg.world;
+    const int L = h->cfg.L;
     DevBuf<unsigned long long> hist;
-    hist.reserve(256);
-    DPF_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
-    const dim3 grid((unsigned)std::min<int64_t>((n_new + 255) / 256, 1024), h->cfg.L);
-    k_pid_histogram<<<grid, 256, 0, h->stream>>>(h->pids.p, n_new, h->key_ld, h->cfg.L, hist.p); DPF_LAUNCHED();
-    unsigned long long occ[256];
-    DPF_CUDA(cudaMemcpyAsync(occ, hist.p, sizeof(occ), cudaMemcpyDeviceToHost, h->stream));
+    hist.reserve((size_t)L * 256);
+    DPF_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)L * 256 * sizeof(unsigned long long), h->stream));
+    const dim3 grid((unsigned)std::min<int64_t>((n_new + 255) / 256, 1024), L);
+    k_pid_histogram<<<grid, 256, 0, h->stream>>>(h->pids.p, n_new, h->key_ld, L, hist.p); DPF_LAUNCHED();
+    std::vector<unsigned long long> occ((size_t)L * 256);
+    DPF_CUDA(cudaMemcpyAsync(occ.data(), hist.p, occ.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     DPF_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<int> order(np);
-    for (int p = 0; p < np; ++p) order[p] = p;
+    std::vector<int> order;                      // cell = t * 256 + p
+    for (int t = 0; t < L; ++t)
+        for (int p = 0; p < np; ++p) order.push_back(t * 256 + p);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return occ[a] > occ[b]; });
     std::vector<unsigned long long> load(G, 0);
-    h->own = OwnMask{};
-    for (int p : order) {
+    std::fill(h->own_cells.begin(), h->own_cells.end(), 0u);
+    for (int cell : order) {
         int best = 0;
         for (int g = 1; g < G; ++g)
             if (load[g] < load[best]) best = g;
-        load[best] += occ[p];
-        if (best == h->cfg.rank) h->own.w[p >> 5] |= 1u << (p & 31);
+        load[best] += occ[cell];
+        const int t = cell >> 8, p = cell & 255;
+        if (best == h->cfg.rank) h->own_cells[(size_t)t * kOwnWords + (p >> 5)] |= 1u << (p & 31);
     }
+    upload_ownership(h);
     h->own_fixed = true;
 }
 
@@ -531,7 +549,9 @@ int dpf_set_balanced_partition(dpf_handle h, int32_t enable) {
 int dpf_owned_subindexes(dpf_handle h, uint8_t* owned_out) {
     return guarded(h, [&] {
         DPF_REQUIRE(owned_out, DPF_ERR_INVALID, "null buffer");
-        for (int p = 0; p < (1 << h->cfg.pb); ++p) owned_out[p] = h->own.has(p) ? 1 : 0;
+        const int np = 1 << h->cfg.pb;
+        for (int t = 0; t < h->cfg.L; ++t)
+            for (int p = 0; p < np; ++p) owned_out[(size_t)t * np + p] = h->owns(t, p) ? 1 : 0;
     });
 }
 
@@ -904,10 +924,9 @@ template <class T>
 void put(FILE* f, const T& v) { DPF_REQUIRE(fwrite(&v, sizeof(T), 1, f) == 1, DPF_ERR_INVALID, "dpf_save: short write"); }
 template <class T>
 void get(FILE* f, T& v) { DPF_REQUIRE(fread(&v, sizeof(T), 1, f) == 1, DPF_ERR_INVALID, "dpf_load: truncated file"); }
-const char kMagic[8] = {'D', 'P', 'F', 'I', 'D', 'X', '0', '2'};
+const char kMagic[8] = {'D', 'P', 'F', 'I', 'D', 'X', '0', '3'};
 struct ShardHeader {
     int32_t store_mode, balance_partition, own_fixed, reserved;
-    uint32_t own[8];
     int64_t n_removed;
 };
 }  // namespace
@@ -930,9 +949,10 @@ int dpf_save(dpf_handle h, const char* path) {
         sh.store_mode = h->store_mode;
         sh.balance_partition = h->balance_partition ? 1 : 0;
         sh.own_fixed = h->own_fixed ? 1 : 0;
-        for (int i = 0; i < 8; ++i) sh.own[i] = h->own.w[i];
         sh.n_removed = h->n_removed;
         put(f, sh);
+        DPF_REQUIRE(fwrite(h->own_cells.data(), sizeof(uint32_t), h->own_cells.size(), f) == h->own_cells.size(), DPF_ERR_INVALID,
+                    "dpf_save: short write");
         dev_to_file(h, f, h->A.p, (size_t)P * d);
         dev_to_file(h, f, h->chain.p, (size_t)L * k);
         if (has_bw) { dev_to_file(h, f, h->fb.p, (size_t)P); dev_to_file(h, f, h->fw.p, (size_t)P); }
@@ -987,7 +1007,9 @@ int dpf_load(const char* path, int32_t device, dpf_handle* out) {
         h->store_mode = sh.store_mode;
         h->balance_partition = sh.balance_partition != 0;
         h->own_fixed = sh.own_fixed != 0;
-        for (int i = 0; i < 8; ++i) h->own.w[i] = sh.own[i];
+        DPF_REQUIRE(fread(h->own_cells.data(), sizeof(uint32_t), h->own_cells.size(), f) == h->own_cells.size(), DPF_ERR_INVALID,
+                    "dpf_load: truncated file");
+        upload_ownership(h);
         h->P = P;
         h->PW = (P + 31) / 32;
         h->hA.resize((size_t)P * d);

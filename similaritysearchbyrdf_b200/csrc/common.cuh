@@ -133,10 +133,14 @@ enum : int {
     CTR_COUNT = 128
 };
 
-// the sub-indexes (partition ids, < 2^pb <= 256) this handle owns on a multi-GPU box
+// the (table, sub-index) cells this handle owns on a multi-GPU box: L rows of 256 bits in device memory (partition ids
+// are < 2^pb <= 256).  The reference keeps one store per (table, partition) (RandomDrawTreeMap.java:1430-1459), so a
+// cell is the unit a placement can move; the plain scheme gives rank g the cells with p mod G == g in every table, the
+// balanced one deals cells out by their size.
+constexpr int kOwnWords = 8;
 struct OwnMask {
-    uint32_t w[8];
-    __host__ __device__ bool has(int pid) const { return (w[pid >> 5] >> (pid & 31)) & 1u; }
+    const uint32_t* cells;
+    __device__ bool has(int t, int pid) const { return (cells[t * kOwnWords + (pid >> 5)] >> (pid & 31)) & 1u; }
 };
 
 // process-wide count of kernel launches issued by this library (reported through dpf_stats)
@@ -161,7 +165,10 @@ struct dpf_index {
     std::string last_error;
     bool family_set = false, part_set = false, dense = true, fitted = false;
     int num_sms = 148;
-    dpf::OwnMask own{};                  // sub-indexes owned by this rank (all of them when world <= 1)
+    dpf::OwnMask own{};                  // cells owned by this rank (all of them when world <= 1): view of own_dev
+    std::vector<uint32_t> own_cells;     // host copy, L x kOwnWords
+    dpf::DevBuf<uint32_t> own_dev;
+    bool owns(int t, int p) const { return (own_cells[(size_t)t * dpf::kOwnWords + (p >> 5)] >> (p & 31)) & 1u; }
     bool balance_partition = false;      // dpf_set_balanced_partition: ownership by occupancy instead of p % world
     bool own_fixed = false;              // the balanced assignment is made once, at the first fit
 

@@ -52,7 +52,7 @@ k_count_depth1(const int32_t* __restrict__ keys, const uint8_t* __restrict__ pid
     const int64_t end = min(n, base + CD_CHUNK);
     for (int64_t i = base + threadIdx.x; i < end; i += CD_THREADS) {
         const int pid = pids[(int64_t)t * ld + i];
-        if (!own.has(pid) || (removed && removed[i])) continue;
+        if (!own.has(t, pid) || (removed && removed[i])) continue;
         const int32_t h = keys[(int64_t)t * ld + i];
         const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
         const int local = ((pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1);
@@ -82,7 +82,7 @@ k_make_sort_keys(const int32_t* __restrict__ keys, const uint8_t* __restrict__ p
     const int32_t h = keys[(int64_t)t * ld + i];
     const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
     uint32_t code = (uint32_t)(((tl * tp.R + pid * tp.SEG + seg) << tp.nb) | slot_at(h, tp.MAXL, tp.nb, tp.W - 1));
-    if (!own.has(pid) || (removed && removed[i])) code |= 1u << field_bits;
+    if (!own.has(t, pid) || (removed && removed[i])) code |= 1u << field_bits;
     sk[(int64_t)tl * n + i] = code;
     sv[(int64_t)tl * n + i] = (uint32_t)i;
 }

@@ -460,6 +460,124 @@ k_pack_keys(const uint32_t* __restrict__ S, const int32_t* __restrict__ PQ, cons
     if (pids) pids[(int64_t)t * ld + i] = (uint8_t)partition_id_dev(fk, ap, pb, transform);
 }
 
+// The same, table-driven, for the angle family with P <= 128 sign bits per vector.  k_pack_keys spends ~750 instructions
+// per key (a 4-way select per chain bit, a select + FP64 add per partitioner coefficient) and is issue-bound; here a CTA
+// first turns its table's chain into 16 byte-indexed lookup tables (sign byte s, value v -> the key bits that byte
+// supplies) and its partitioner rows into 4 byte-indexed tables of FP32 partial sums, then packs PACK_KPT keys per
+// thread with 16 + 4 shared-memory lookups each.
+//
+// The partition bit is the SIGN of a sum the reference adds in FP64 in ascending bit order (Partitioner.scala:40-64).
+// The FP32 table sum f differs from the real sum T by at most 5 * 2^-24 * A (A = sum |coefficient|: rounding of four
+// partials to FP32 and three FP32 adds) and the reference's own sum by at most 31 * 2^-53 * A, so |f| > 8 * 2^-24 * A
+// fixes the sign of both; the few keys per million below that redo the row in the reference's order.
+constexpr int PACK_KPT = 32;
+
+template <int PBV /* float4 per table entry: 1 for pb <= 4, 2 for pb <= 8 */>
+__global__ void __launch_bounds__(256, 4)
+k_pack_keys_tab(const uint32_t* __restrict__ S, const int32_t* __restrict__ chain, const double* __restrict__ Ap, int64_t n,
+                int PW, int k, int pb, int transform, int32_t* __restrict__ keys, uint8_t* __restrict__ pids, int64_t ld) {
+    extern __shared__ __align__(16) unsigned char pack_smem[];
+    uint32_t* keytab = reinterpret_cast<uint32_t*>(pack_smem);                       // [PW*4][256]
+    float4* ptab = reinterpret_cast<float4*>(pack_smem + (size_t)PW * 4 * 256 * 4);  // [4][256][PBV]
+    __shared__ double ap[kMaxPb * 32];
+    __shared__ float bound[kMaxPb];
+    __shared__ unsigned char item_cnt[16], item[16][kMaxChain];   // per sign byte: (bit in byte) | (chain position << 3)
+    const int t = blockIdx.y, tid = threadIdx.x;
+    if (tid < 16) item_cnt[tid] = 0;
+    for (int i = tid; i < pb * 32; i += 256) ap[i] = Ap[(int64_t)t * pb * 32 + i];
+    __syncthreads();
+    if (tid == 0)
+        for (int b = 0; b < k; ++b) {
+            const int c = chain[t * k + b], sb = c >> 3;
+            item[sb][item_cnt[sb]++] = (unsigned char)((c & 7) | (b << 3));
+        }
+    if (tid >= 32 && tid < 32 + pb) {
+        const int j = tid - 32;
+        double a = 0.0;
+        for (int i = 0; i < 32; ++i) a += fabs(ap[j * 32 + i]);
+        // (not finite, or beyond what an FP32 partial can hold: no fast path for this row)
+        bound[j] = (a < 1e37) ? (float)(a * (8.0 / 16777216.0)) * 1.0001f : __int_as_float(0x7f800000);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int e = tid; e < PW * 4 * 256; e += 256) {
+        const int sb = e >> 8, v = e & 255, cnt = item_cnt[sb];
+        uint32_t r = 0;
+#pragma unroll 1
+        for (int q = 0; q < cnt; ++q) {
+            const int it = item[sb][q];
+            r |= ((uint32_t)(v >> (it & 7)) & 1u) << (31 - (it >> 3));
+        }
+        keytab[e] = r;
+    }
+    {
+        float* pf = reinterpret_cast<float*>(ptab);
+#pragma unroll 1
+        for (int e = tid; e < 4 * 256 * 4 * PBV; e += 256) {   // one (byte, value, partitioner row) per pass
+            const int j = e % (4 * PBV), bv = e / (4 * PBV), byte = bv >> 8, v = bv & 255;
+            double sum = 0.0;
+            if (j < pb) {
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i)
+                    if ((v >> i) & 1) sum = __dadd_rn(sum, ap[j * 32 + byte * 8 + i]);
+            }
+            pf[e] = (float)sum;
+        }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < PACK_KPT; ++r) {
+        const int64_t i = ((int64_t)blockIdx.x * PACK_KPT + r) * 256 + tid;
+        if (i >= n) break;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (PW == 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(S + i * 4);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            for (int q = 0; q < PW; ++q) w[q] = S[i * PW + q];
+        }
+        uint32_t key = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < PW) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) key |= keytab[(q * 4 + b) * 256 + ((w[q] >> (8 * b)) & 255u)];
+            }
+        const int32_t fk = apply_key_transform((int32_t)key, transform);
+        keys[(int64_t)t * ld + i] = fk;
+        if (pids) {
+            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int e = (b * 256 + (int)(((uint32_t)fk >> (8 * b)) & 255u)) * PBV;
+                const float4 x = ptab[e];
+                f[0] += x.x; f[1] += x.y; f[2] += x.z; f[3] += x.w;
+                if (PBV > 1) {
+                    const float4 y = ptab[e + 1];
+                    f[4] += y.x; f[5] += y.y; f[6] += y.z; f[7] += y.w;
+                }
+            }
+            uint32_t pr = 0;
+#pragma unroll
+            for (int j = 0; j < 4 * PBV; ++j)
+                if (j < pb) {
+                    bool pos = f[j] > 0.f;
+                    if (!(fabsf(f[j]) > bound[j])) {
+                        double sum = 0.0;
+#pragma unroll 1
+                        for (int q = 0; q < 32; ++q)
+                            sum = __dadd_rn(sum, (((uint32_t)fk >> q) & 1u) ? ap[j * 32 + q] : 0.0);
+                        pos = !(sum <= 0.0);
+                    }
+                    pr = (pr << 1) | (pos ? 1u : 0u);
+                }
+            int32_t pk = (int32_t)(pr << (32 - pb));
+            pk = apply_key_transform(pk, transform);
+            pids[(int64_t)t * ld + i] = (uint8_t)((uint32_t)pk >> (32 - pb));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
@@ -493,7 +611,19 @@ static int64_t hash_chunk_rows(const dpf_index* h) {
 static void pack_launch(dpf_index* h, int64_t n, int32_t* keys_out, uint8_t* pids_out, int64_t ld) {
     StageTimer tm(h, DPF_T_PACK);
     const dim3 grid((unsigned)((n + 255) / 256), h->cfg.L);
-    if (h->cfg.family_kind == DPF_FAMILY_PSTABLE)
+    // (a query batch of a few thousand keys is latency, not throughput: there the tables cost more than they save)
+    if (h->cfg.family_kind != DPF_FAMILY_PSTABLE && h->PW <= 4 && h->cfg.pb >= 1 && pids_out && n >= 65536 &&
+        h->dbg[DPF_DBG_HASH_EXACT] != 2) {
+        const dim3 g2((unsigned)((n + 256 * PACK_KPT - 1) / (256 * PACK_KPT)), h->cfg.L);
+        const int pbv = h->cfg.pb > 4 ? 2 : 1;
+        const size_t smem = (size_t)h->PW * 4 * 256 * 4 + (size_t)4 * 256 * 16 * pbv;
+        if (pbv == 1)
+            k_pack_keys_tab<1><<<g2, 256, smem, h->stream>>>(h->signs.p, h->chain.p, h->Ap.p, n, h->PW, h->cfg.k, h->cfg.pb,
+                                                            h->cfg.key_transform, keys_out, pids_out, ld);
+        else
+            k_pack_keys_tab<2><<<g2, 256, smem, h->stream>>>(h->signs.p, h->chain.p, h->Ap.p, n, h->PW, h->cfg.k, h->cfg.pb,
+                                                            h->cfg.key_transform, keys_out, pids_out, ld);
+    } else if (h->cfg.family_kind == DPF_FAMILY_PSTABLE)
         k_pack_keys<true><<<grid, 256, 0, h->stream>>>(nullptr, h->pq.p, h->chain.p, h->Ap.p, n, h->P, h->PW, h->cfg.k,
                                                        h->cfg.pb, h->cfg.key_transform, keys_out, pids_out, ld);
     else

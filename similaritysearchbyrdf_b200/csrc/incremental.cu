@@ -40,7 +40,7 @@ k_locate_slots(const int32_t* __restrict__ ids, int64_t m, int L, const int32_t*
     unsigned long long key = kSkipKey;
     if (id >= 0 && id < n) {
         const int pid = pids[(int64_t)t * ld + id];
-        if (own.has(pid)) {
+        if (own.has(t, pid)) {
             const int32_t h = keys[(int64_t)t * ld + id];
             const int seg = tp.seg_bits ? (int)((uint32_t)h >> tp.bucket_bits) : 0;
             int node = t * tp.R + pid * tp.SEG + seg;
@@ -282,7 +282,7 @@ k_occupancy(const uint8_t* __restrict__ pids, const uint8_t* __restrict__ remove
     const int t = blockIdx.y;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int pid = pids[(int64_t)t * ld + i];
-        if (own.has(pid) && !(removed && removed[i])) atomicAdd(&sh[pid], 1u);
+        if (own.has(t, pid) && !(removed && removed[i])) atomicAdd(&sh[pid], 1u);
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);

@@ -40,7 +40,7 @@ k_probe_count(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __re
     const int np = 1 << c.tp.pb;
     for (int sub = 0; sub < np; ++sub) {       // findStepWiseSubIndexIDs (RandomDrawTreeMap.java:613-621)
         if (__popc(sub ^ pid) > c.steps) continue;
-        if (!c.own.has(sub)) continue;   // this GPU's sub-forest only
+        if (!c.own.has(t, sub)) continue;   // this GPU's sub-forest only
         bool leader;
         int ptr, cnt;
         warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);
@@ -88,7 +88,7 @@ k_expand(ProbeCtx c, const int32_t* __restrict__ qkeys, const uint8_t* __restric
             const int64_t tbase = c.f.table_base[t];
             for (int sub = 0; sub < np; ++sub) {
                 if (__popc(sub ^ pid) > c.steps) continue;
-                if (!c.own.has(sub)) continue;
+                if (!c.own.has(t, sub)) continue;
                 bool leader;
                 int ptr, cnt;
                 warp_lookup(c, t, sub, seg, h, nprobes, lane, leader, ptr, cnt);

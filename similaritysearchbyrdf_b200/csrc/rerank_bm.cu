@@ -899,10 +899,10 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         const int world = h->cfg.world > 1 ? h->cfg.world : 1;
         // (FP64 / float rows cost 8 / 4 times the bytes of byte rows per sampled row: two samples there — measured on
         // configs[1] with the byte copy off: 4.1 ms of sampling with six tables against 11.4 ms of scoring)
-        // On G GPUs a rank holds 1/G of a query's entries: one sampled bucket already puts the threshold at the k / 225
-        // quantile of ~6k entries on a rank of 8 (~280 survivors per query), and the sampling floor is what does not
-        // shrink with G.
-        const int nt_default = !use_u8 ? 2 : (world <= 1 ? 6 : std::max(1, 6 / world));
+        // On G GPUs a rank holds 1/G of a query's entries and fewer samples pay: measured per rank at configs[1]
+        // (tools/nt_sweep.py --world G), 3 tables is the best or within 1% of it at G = 2, 4 and 8 (one table leaves
+        // 860 survivors per query on the fullest rank of 8 and costs 0.2 ms more than it saves).
+        const int nt_default = !use_u8 ? 2 : (world <= 1 ? 6 : 3);
         const int NT = std::min(32, std::max(1, h->dbg[DPF_DBG_TAU_TABLES] > 0 ? (int)h->dbg[DPF_DBG_TAU_TABLES] : nt_default));
         h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
         h->bm_tl_ids.reserve((size_t)nqc * NT * topk);

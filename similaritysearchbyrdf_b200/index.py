@@ -120,12 +120,12 @@ class DPFIndex:
         return cm()
 
     def set_balanced_partition(self, on=True):
-        """Multi-GPU: deal the sub-indexes to the ranks by occupancy at the first fit instead of p % world."""
+        """Multi-GPU: deal the (table, sub-index) cells to the ranks by occupancy at the first fit instead of p % world."""
         self._ck(self.lib.dpf_set_balanced_partition(self.h, 1 if on else 0))
 
     def owned_subindexes(self):
-        """Flags (uint8, 2^pb) of the sub-indexes this handle owns."""
-        out = np.zeros(1 << self.pb, np.uint8)
+        """Flags (uint8, L x 2^pb) of the (table, sub-index) cells this handle owns."""
+        out = np.zeros((self.L, 1 << self.pb), np.uint8)
         self._ck(self.lib.dpf_owned_subindexes(self.h, _p(out)))
         return out
 

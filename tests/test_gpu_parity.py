@@ -86,6 +86,30 @@ def test_hash_key_transforms(cfg1, transform):
     assert np.array_equal(ko, kg) and np.array_equal(po, pg)
 
 
+@pytest.mark.parametrize("family_size,k,pb", [(20, 32, 1), (70, 17, 3), (128, 32, 5), (100, 32, 8)])
+def test_hash_table_driven_packing_matches_bit_by_bit(family_size, k, pb):
+    """k_pack_keys_tab (byte-indexed lookup tables, FP32 partial sums with an error bound, exact redo below it) against
+    the bit-by-bit kernel and the oracle, with partitioner rows built so that many sums land inside the bound."""
+    d, L = 48, 6
+    A, chain, Ap = U.make_functions(d, family_size=family_size, table_num=3, permutation_num=2, k=k, pb=pb, seed=family_size)
+    L = chain.shape[0]
+    Ap = Ap.copy()
+    Ap[0, 0, :] = 0.0                       # all-zero row: every sum is exactly 0 -> bit 0
+    if pb > 1:
+        Ap[1, pb - 1, 1::2] = -Ap[1, pb - 1, 0::2]   # pairs that cancel: sums are 0 or tiny whenever both bits agree
+    Ap[2, 0, :] *= 1e-30                    # tiny coefficients: the bound scales with them
+    Ap[3, 0, :16] = 1e20                    # one-sided huge partials in the low half, ordinary values above
+    X = np.random.default_rng(1).standard_normal((70001, d))    # (the table-driven kernel serves n >= 65536)
+    o = U.make_oracle(d, A, chain, Ap)
+    ko, po = o.hash_dense(X)
+    ix = U.make_index(d, A, chain, Ap)
+    kg, pg = ix.hash_dense(X)
+    ix.set_debug_option(B.DBG_HASH_EXACT, 2)
+    kb, pb_ = ix.hash_dense(X)
+    assert np.array_equal(kg, kb) and np.array_equal(pg, pb_)
+    assert np.array_equal(ko, kg) and np.array_equal(po, pg)
+
+
 def test_hash_pstable_family():
     d, L, k = 24, 3, 32
     rng = np.random.default_rng(9)

@@ -87,6 +87,14 @@ def test_oracle_explicit_ownership_partitions_the_forest():
     f_off, f_cand = full.query_candidates_dense(Qs, None, 1)
     masks = [np.array([1, 0, 0, 1, 1, 0, 0, 0], np.uint8), np.array([0, 1, 0, 0, 0, 0, 1, 1], np.uint8),
              np.array([0, 0, 1, 0, 0, 1, 0, 0], np.uint8)]
+    _check_shards_unite(X, Qs, A, chain, Ap, masks, f_off, f_cand)
+    # the same per (table, sub-index) cell (dpfo_set_owned_cells): a different owner per table
+    owner = np.random.default_rng(5).integers(0, 3, (chain.shape[0], 8))
+    _check_shards_unite(X, Qs, A, chain, Ap, [(owner == g).astype(np.uint8) for g in range(3)], f_off, f_cand)
+
+
+def _check_shards_unite(X, Qs, A, chain, Ap, masks, f_off, f_cand):
+    from tests import util as U
     cands, sizes = [], []
     for m in masks:
         o = U.make_oracle(100, A, chain, Ap, bucket_overflow=40)

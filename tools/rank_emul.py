@@ -24,22 +24,24 @@ for r in ranks:
     ix = DPFIndex(d=128, L=30, k=32, pb=3, rank=r, world=a.world)
     ix.set_balanced_partition(True)
     ix.set_family(A, chain); ix.set_partitioners(Ap)
-    ix.set_stream(torch.cuda.current_stream().cuda_stream)
+    stm = torch.cuda.Stream()
+    ix.set_stream(stm.cuda_stream)
+    torch.cuda.synchronize()
     ix.fit_dense_dev(Xd.data_ptr(), 1_000_000)
     for _ in range(3):
         ix.query_topk_dense_dev(Qd.data_ptr(), a.nq, 0, 0, 10, 0, ids.data_ptr(), sc.data_ptr())
     torch.cuda.synchronize()
-    e0.record()
+    e0.record(stm)
     for _ in range(5):
         ix.query_topk_dense_dev(Qd.data_ptr(), a.nq, 0, 0, 10, 0, ids.data_ptr(), sc.data_ptr())
-    e1.record()
+    e1.record(stm)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     ix.set_profiling(True)
     ix.query_topk_dense_dev(Qd.data_ptr(), a.nq, 0, 0, 10, 0, ids.data_ptr(), sc.data_ptr())
     st = ix.stage_times_ms()
     s = ix.stats()
-    print(f"rank {r}: {ms:.3f} ms/step", {k: round(v, 3) for k, v in st.items() if v}, "owned", ix.owned_subindexes().tolist(),
+    print(f"rank {r}: {ms:.3f} ms/step", {k: round(v, 3) for k, v in st.items() if v}, "owned cells", int(ix.owned_subindexes().sum()),
           "pairs", s["bm_pairs"], "rows", s["bm_rows_staged"], "surv/q", round(s["bm_survivors"] / a.nq, 1), "direct", s["bm_direct"],
           "entries/q", round(s["last_cand_with_dups"] / a.nq), flush=True)
     ix.close()
