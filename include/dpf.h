@@ -84,6 +84,12 @@ int dpf_set_family(dpf_handle h, const double* A, int32_t P, const int32_t* chai
                    const int32_t* w);
 /* Ap: L x pb x 32 — each table's private LocalitySensitivePartitioner functions (DensevectorRDFInit.scala:63-77) */
 int dpf_set_partitioners(dpf_handle h, const double* Ap);
+/* The same for a DPF_FAMILY_PSTABLE index.  The reference builds the partitioner's LSH from the main family's
+ * configuration with vectorDim = 32 and chainLength = pb (DensevectorRDFInit.scala:63-70), so there the sub-index is
+ * PStableHashChain.compute(bits of the key).hashCode >>> (32 - pb) (Partitioner.scala:40-64, PStableHashFamily.scala:
+ * 155-177): b[L x pb], w[L x pb] are the offsets / widths of the chain functions.  dpf_set_partitioners on a pStable
+ * index with pb > 0 returns DPF_ERR_INVALID. */
+int dpf_set_partitioners_pstable(dpf_handle h, const double* Ap, const double* b, const int32_t* w);
 
 /* ---- LSH.calculateIndex + LocalitySensitivePartitioner.getPartition, batched (parity hook) --------------
  * replaces LSH.calculateIndex (LSH.scala:93-166) / LocalitySensitiveHasher.hash (Hasher.scala:44-54) /

@@ -66,6 +66,22 @@ JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_setPartitioners(JNIEnv* env, 
     if (rc != DPF_OK) throw_dpf(env, h, rc);
 }
 
+/* void setPartitionersPStable(long h, double[] Ap, double[] b, int[] w) — the same when mclab.lsh.name = pStable: the
+ * partitioner chains are PStableHashChains (DensevectorRDFInit.scala:63-70), b / w their offsets and widths (L x pb) */
+JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_setPartitionersPStable(JNIEnv* env, jclass cls, jlong jh, jdoubleArray jAp,
+                                                                          jdoubleArray jb, jintArray jw) {
+    (void)cls;
+    dpf_handle h = (dpf_handle)(intptr_t)jh;
+    double* Ap = (double*)(*env)->GetPrimitiveArrayCritical(env, jAp, 0);
+    double* b = (double*)(*env)->GetPrimitiveArrayCritical(env, jb, 0);
+    jint* w = (jint*)(*env)->GetPrimitiveArrayCritical(env, jw, 0);
+    int rc = dpf_set_partitioners_pstable(h, Ap, b, w);
+    (*env)->ReleasePrimitiveArrayCritical(env, jw, w, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jb, b, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jAp, Ap, JNI_ABORT);
+    if (rc != DPF_OK) throw_dpf(env, h, rc);
+}
+
 /* void fitDense(long h, double[] X, long n) — newMultiThreadFit / newFastFit after parsing (DensevectorRDFInit.scala:127-206) */
 JNIEXPORT void JNICALL Java_mclab_deploy_NativeDPF_setStoreMode(JNIEnv* env, jclass cls, jlong jh, jint mode) {
     (void)cls;

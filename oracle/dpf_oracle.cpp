@@ -196,18 +196,32 @@ inline int32_t apply_transform(int32_t key, int kind) {
 
 // Partitioner.scala:40-64: bits of h (bit i -> coordinate i) as a 0/1 sparse vector; chain of pb angle
 // functions of the table's private LSH; `calculateIndex(v, 0)(0) >>> (32 - partitionBits)`.
-inline int32_t partition_id(int32_t h, const double* Ap_t, int pb, int key_transform) {
-    int32_t r = 0;
+//
+// The partitioner's LSH is built from the main configuration with vectorDim = 32, tableNum = 1 and chainLength = pb
+// (DensevectorRDFInit.scala:63-70), so with mclab.lsh.name = pStable its chain is a PStableHashChain: the pb sums are
+// quantised ((sum + b) / w).toInt and packed by Arrays.hashCode like a pStable key (PStableHashFamily.scala:155-177);
+// pb_b / pb_w are that chain's b and w, NULL for the angle family.
+inline int32_t partition_id(int32_t h, const double* Ap_t, int pb, int key_transform, const double* pb_b = nullptr,
+                            const int32_t* pb_w = nullptr) {
+    if (pb == 0) return 0;
+    double sums[32];
     for (int j = 0; j < pb; ++j) {
         const double* a = Ap_t + (size_t)j * 32;
         double s = 0.0;
         for (int i = 0; i < 32; ++i)
             if ((lsr(h, i) & 1) != 0 && a[i] != 0.0) s += a[i] * 1.0;   // sparse . sparse, ascending i
-        r = lsl(r, 1) | angle_sign(s);
+        sums[j] = s;
     }
-    int32_t key = pb >= 32 ? r : lsl(r, 32 - pb);
+    int32_t key;
+    if (pb_b) {
+        key = pstable_key_from_dots(sums, pb_b, pb_w, pb);
+    } else {
+        int32_t r = 0;
+        for (int j = 0; j < pb; ++j) r = lsl(r, 1) | angle_sign(sums[j]);
+        key = pb >= 32 ? r : lsl(r, 32 - pb);
+    }
     key = apply_transform(key, key_transform);
-    return pb == 0 ? 0 : lsr(key, 32 - pb);
+    return lsr(key, 32 - pb);
 }
 
 // RandomDrawTreeMap.java:435-465
@@ -254,6 +268,10 @@ struct dpfo {
     std::vector<double> fb;           // P
     std::vector<int32_t> fw;          // P
     std::vector<double> Ap;           // L x pb x 32
+    std::vector<double> pb_b;         // L x pb: b of the partitioner chains (pStable family only)
+    std::vector<int32_t> pb_w;        // L x pb
+    const double* part_b(int t) const { return pb_b.empty() ? nullptr : &pb_b[(size_t)t * cfg.pb]; }
+    const int32_t* part_w(int t) const { return pb_w.empty() ? nullptr : &pb_w[(size_t)t * cfg.pb]; }
     std::vector<Table> tables;
     bool dense = true;
     int64_t n = 0;
@@ -472,7 +490,8 @@ void table_query(dpfo* o, const Table& T, int table, int32_t h, int32_t qid, int
                  std::vector<int32_t>& out) {
     const TreeParams& tp = o->tp;
     const int seg = seg_of(tp, h);
-    const int pid = partition_id(h, &o->Ap[(size_t)table * o->cfg.pb * 32], o->cfg.pb, o->cfg.key_transform);
+    const int pid = partition_id(h, &o->Ap[(size_t)table * o->cfg.pb * 32], o->cfg.pb, o->cfg.key_transform, o->part_b(table),
+                                 o->part_w(table));
     const int np = 1 << o->cfg.pb;
     int32_t probes[32];
     int nprobes = 0;
@@ -603,6 +622,17 @@ int dpfo_set_owned_cells(dpfo* o, const uint8_t* owned) {
 
 int dpfo_set_partitioners(dpfo* o, const double* Ap) {
     o->Ap.assign(Ap, Ap + (size_t)o->cfg.L * o->cfg.pb * 32);
+    o->pb_b.clear();
+    o->pb_w.clear();
+    return 0;
+}
+
+/* the partitioners of a pStable index (see partition_id): Ap as above, b and w of the L x pb chain functions */
+int dpfo_set_partitioners_pstable(dpfo* o, const double* Ap, const double* b, const int32_t* w) {
+    if (!o || !Ap || !b || !w) return 1;
+    o->Ap.assign(Ap, Ap + (size_t)o->cfg.L * o->cfg.pb * 32);
+    o->pb_b.assign(b, b + (size_t)o->cfg.L * o->cfg.pb);
+    o->pb_w.assign(w, w + (size_t)o->cfg.L * o->cfg.pb);
     return 0;
 }
 
@@ -618,7 +648,8 @@ int dpfo_hash_dense(dpfo* o, const double* X, int64_t n, int32_t* keys_out, int3
                 keys_out[(size_t)t * n + i] = kk[t];
                 if (pids_out)
                     pids_out[(size_t)t * n + i] =
-                        partition_id(kk[t], &o->Ap[(size_t)t * o->cfg.pb * 32], o->cfg.pb, o->cfg.key_transform);
+                        partition_id(kk[t], &o->Ap[(size_t)t * o->cfg.pb * 32], o->cfg.pb, o->cfg.key_transform, o->part_b(t),
+                                     o->part_w(t));
             }
         }
     });
@@ -638,7 +669,8 @@ int dpfo_hash_csr(dpfo* o, const int64_t* indptr, const int32_t* indices, const 
                 keys_out[(size_t)t * n + i] = kk[t];
                 if (pids_out)
                     pids_out[(size_t)t * n + i] =
-                        partition_id(kk[t], &o->Ap[(size_t)t * o->cfg.pb * 32], o->cfg.pb, o->cfg.key_transform);
+                        partition_id(kk[t], &o->Ap[(size_t)t * o->cfg.pb * 32], o->cfg.pb, o->cfg.key_transform, o->part_b(t),
+                                     o->part_w(t));
             }
         }
     });
@@ -866,6 +898,9 @@ int32_t dpfo_continue_bits_count(int32_t key) { return continue_bits_count(key);
 int32_t dpfo_angle_new_method(int32_t key) { return angle_new_method(key); }
 int32_t dpfo_partition_id(int32_t h, const double* Ap_t, int pb, int key_transform) {
     return partition_id(h, Ap_t, pb, key_transform);
+}
+int32_t dpfo_partition_id_pstable(int32_t h, const double* Ap_t, int pb, int key_transform, const double* b, const int32_t* w) {
+    return partition_id(h, Ap_t, pb, key_transform, b, w);
 }
 // Hasher.scala:18-37 (DefaultHasher on Int keys; `>>` is arithmetic in Scala)
 int32_t dpfo_default_hasher(int32_t key) {

@@ -48,6 +48,8 @@ void   dpfo_destroy(dpfo* o);
 int    dpfo_set_family(dpfo* o, const double* A, const int32_t* chain_idx, const double* b, const int32_t* w);
 /* Ap: L x pb x 32 row-major — per-table private partitioner functions (Partitioner.scala:27-64) */
 int    dpfo_set_partitioners(dpfo* o, const double* Ap);
+int    dpfo_set_partitioners_pstable(dpfo* o, const double* Ap /* L x pb x 32 */, const double* b /* L x pb */,
+                                     const int32_t* w /* L x pb */);
 int    dpfo_set_owned(dpfo* o, const uint8_t* owned /* 2^pb flags or NULL */);
 int    dpfo_set_owned_cells(dpfo* o, const uint8_t* owned /* L x 2^pb flags or NULL */);
 
@@ -100,6 +102,8 @@ void    dpfo_sampling_index(int32_t* sigma32);
 int32_t dpfo_continue_bits_count(int32_t key);                                                     /* significantBits.scala:11-67, Array(6,4,2,1) */
 int32_t dpfo_angle_new_method(int32_t key);                                                        /* significantBits.scala:100-127 */
 int32_t dpfo_partition_id(int32_t h, const double* Ap_t /*pb x 32*/, int pb, int key_transform);  /* Partitioner.scala:40-64 */
+int32_t dpfo_partition_id_pstable(int32_t h, const double* Ap_t, int pb, int key_transform, const double* b /* pb */,
+                                  const int32_t* w /* pb */);   /* the same when the partitioner's family is pStable */
 int32_t dpfo_default_hasher(int32_t key);                                                          /* Hasher.scala:18-37 */
 /* bitmap-compressed directory arithmetic (RandomDrawTreeMap.java:1186-1267) — the layout the GPU replaces */
 int32_t dpfo_dir_offset_from_slot(const int32_t* bitmap, int bitmap_words, int slot);

@@ -45,6 +45,7 @@ def lib():
         L.dpfo_set_family.argtypes = [vp, vp, vp, vp, vp]
         L.dpfo_set_partitioners.argtypes = [vp, vp]
         L.dpfo_set_owned.argtypes = [vp, vp]
+        L.dpfo_set_partitioners_pstable.argtypes = [vp, vp, vp, vp]
         L.dpfo_set_owned_cells.argtypes = [vp, vp]
         L.dpfo_hash_dense.argtypes = [vp, vp, i64, vp, vp, C.c_int]
         L.dpfo_hash_csr.argtypes = [vp, vp, vp, vp, i64, vp, vp, C.c_int]
@@ -85,6 +86,8 @@ def lib():
         L.dpfo_angle_new_method.argtypes = [i32]
         L.dpfo_partition_id.restype = i32
         L.dpfo_partition_id.argtypes = [i32, vp, C.c_int, C.c_int]
+        L.dpfo_partition_id_pstable.restype = i32
+        L.dpfo_partition_id_pstable.argtypes = [i32, vp, C.c_int, C.c_int, vp, vp]
         L.dpfo_default_hasher.restype = i32
         L.dpfo_default_hasher.argtypes = [i32]
         L.dpfo_dir_offset_from_slot.restype = i32
@@ -149,9 +152,12 @@ def angle_new_method(key):
     return lib().dpfo_angle_new_method(int(np.int32(key)))
 
 
-def partition_id(h, Ap_t, transform=0):
+def partition_id(h, Ap_t, transform=0, b=None, w=None):
     Ap_t = _f64(Ap_t)
-    return lib().dpfo_partition_id(int(np.int32(h)), _p(Ap_t), Ap_t.shape[0], transform)
+    if b is None:
+        return lib().dpfo_partition_id(int(np.int32(h)), _p(Ap_t), Ap_t.shape[0], transform)
+    b, w = _f64(b), np.ascontiguousarray(w, dtype=np.int32)
+    return lib().dpfo_partition_id_pstable(int(np.int32(h)), _p(Ap_t), Ap_t.shape[0], transform, _p(b), _p(w))
 
 
 def default_hasher(key):
@@ -200,10 +206,18 @@ class Oracle:
         rc = lib().dpfo_set_family(self.h, _p(A), _p(chain_idx), _p(b), _p(w))
         assert rc == 0, rc
 
-    def set_partitioners(self, Ap):
+    def set_partitioners(self, Ap, b=None, w=None):
+        """Ap: L x pb x 32.  With b, w (L x pb each) the partitioner chains are pStable functions (the reference builds
+        the partitioner's LSH from the main family's configuration)."""
         Ap = _f64(Ap)
         assert Ap.shape == (self.L, self.pb, 32)
-        lib().dpfo_set_partitioners(self.h, _p(Ap))
+        if b is None:
+            lib().dpfo_set_partitioners(self.h, _p(Ap))
+        else:
+            b, w = _f64(b), np.ascontiguousarray(w, dtype=np.int32)
+            assert b.shape == (self.L, self.pb) and w.shape == (self.L, self.pb)
+            rc = lib().dpfo_set_partitioners_pstable(self.h, _p(Ap), _p(b), _p(w))
+            assert rc == 0, rc
 
     def set_owned(self, owned):
         """Explicit shard: flags of the sub-indexes (shape 2^pb: the same in every table) or of the (table, sub-index)

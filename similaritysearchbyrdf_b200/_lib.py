@@ -29,7 +29,7 @@ COMM_ID_BYTES = 128
 # every symbol include/dpf.h declares
 EXPORTS = [
     "dpf_create", "dpf_destroy", "dpf_last_error", "dpf_strerror", "dpf_sync", "dpf_set_stream", "dpf_set_family",
-    "dpf_set_partitioners", "dpf_hash_dense", "dpf_hash_csr", "dpf_fit_dense", "dpf_fit_csr", "dpf_fit_dense_dev",
+    "dpf_set_partitioners", "dpf_set_partitioners_pstable", "dpf_hash_dense", "dpf_hash_csr", "dpf_fit_dense", "dpf_fit_csr", "dpf_fit_dense_dev",
     "dpf_size", "dpf_query_candidates_dense", "dpf_query_candidates_csr", "dpf_query_candidates_by_id",
     "dpf_query_topk_dense", "dpf_query_topk_dense_dev", "dpf_rerank_dense", "dpf_merge_topk_dev", "dpf_dump_buckets",
     "dpf_stats", "dpf_set_profiling", "dpf_stage_times_ms", "dpf_set_store_mode", "dpf_save", "dpf_load", "dpf_set_balanced_partition", "dpf_owned_subindexes", "dpf_parse_dense_file", "dpf_parse_sparse_file",
@@ -74,6 +74,7 @@ def load():
     L.dpf_set_stream.argtypes = [vp, vp]
     L.dpf_set_family.argtypes = [vp, vp, i32, vp, vp, vp]
     L.dpf_set_partitioners.argtypes = [vp, vp]
+    L.dpf_set_partitioners_pstable.argtypes = [vp, vp, vp, vp]
     L.dpf_hash_dense.argtypes = [vp, vp, i64, vp, vp]
     L.dpf_hash_csr.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     L.dpf_fit_dense.argtypes = [vp, vp, i64]

@@ -342,11 +342,36 @@ int dpf_set_family(dpf_handle h, const double* A, int32_t P, const int32_t* chai
 int dpf_set_partitioners(dpf_handle h, const double* Ap) {
     return guarded(h, [&] {
         DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "partitioners cannot change once vectors are indexed");
+        // the reference builds the partitioner's LSH from the main family's configuration (DensevectorRDFInit.scala:63-70):
+        // a pStable index has pStable partitioner chains, which need their b and w
+        DPF_REQUIRE(h->cfg.family_kind != DPF_FAMILY_PSTABLE || h->cfg.pb == 0, DPF_ERR_INVALID,
+                    "a pStable index takes its partitioners through dpf_set_partitioners_pstable");
         const size_t cnt = (size_t)h->cfg.L * h->cfg.pb * 32;
         DPF_REQUIRE(Ap || cnt == 0, DPF_ERR_INVALID, "null partitioner functions");
         h->Ap.reserve(std::max<size_t>(cnt, 1));
         h2d(h, h->Ap.p, Ap, cnt);
         DPF_CUDA(cudaStreamSynchronize(h->stream));
+        h->part_pstable = false;
+        h->part_set = true;
+    });
+}
+
+int dpf_set_partitioners_pstable(dpf_handle h, const double* Ap, const double* b, const int32_t* w) {
+    return guarded(h, [&] {
+        DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "partitioners cannot change once vectors are indexed");
+        DPF_REQUIRE(h->cfg.family_kind == DPF_FAMILY_PSTABLE, DPF_ERR_INVALID,
+                    "pStable partitioner chains belong to a pStable index (the angle family uses dpf_set_partitioners)");
+        const size_t cnt = (size_t)h->cfg.L * h->cfg.pb * 32, nf = (size_t)h->cfg.L * h->cfg.pb;
+        DPF_REQUIRE((Ap && b && w) || cnt == 0, DPF_ERR_INVALID, "null partitioner functions");
+        for (size_t i = 0; i < nf; ++i) DPF_REQUIRE(w[i] != 0, DPF_ERR_INVALID, "partitioner w must be non-zero");
+        h->Ap.reserve(std::max<size_t>(cnt, 1));
+        h->Apb.reserve(std::max<size_t>(nf, 1));
+        h->Apw.reserve(std::max<size_t>(nf, 1));
+        h2d(h, h->Ap.p, Ap, cnt);
+        h2d(h, h->Apb.p, b, nf);
+        h2d(h, h->Apw.p, w, nf);
+        DPF_CUDA(cudaStreamSynchronize(h->stream));
+        h->part_pstable = nf > 0;
         h->part_set = true;
     });
 }
@@ -957,6 +982,8 @@ int dpf_save(dpf_handle h, const char* path) {
         dev_to_file(h, f, h->chain.p, (size_t)L * k);
         if (has_bw) { dev_to_file(h, f, h->fb.p, (size_t)P); dev_to_file(h, f, h->fw.p, (size_t)P); }
         dev_to_file(h, f, h->Ap.p, (size_t)L * h->cfg.pb * 32);
+        put(f, (int32_t)(h->part_pstable ? 1 : 0));
+        if (h->part_pstable) { dev_to_file(h, f, h->Apb.p, (size_t)L * h->cfg.pb); dev_to_file(h, f, h->Apw.p, (size_t)L * h->cfg.pb); }
         if (dense) {
             dev_to_file(h, f, h->Xdev, (size_t)h->n * d);
         } else {
@@ -1025,6 +1052,14 @@ int dpf_load(const char* path, int32_t device, dpf_handle* out) {
         }
         h->Ap.reserve(std::max<size_t>((size_t)L * cfg.pb * 32, 1));
         file_to_dev(h, f, h->Ap.p, (size_t)L * cfg.pb * 32);
+        int32_t part_pstable = 0;
+        get(f, part_pstable);
+        h->part_pstable = part_pstable != 0;
+        if (h->part_pstable) {
+            h->Apb.reserve((size_t)L * cfg.pb); h->Apw.reserve((size_t)L * cfg.pb);
+            file_to_dev(h, f, h->Apb.p, (size_t)L * cfg.pb);
+            file_to_dev(h, f, h->Apw.p, (size_t)L * cfg.pb);
+        }
         prepare_family(h);
         h->family_set = h->part_set = true;
         h->dense = dense != 0;

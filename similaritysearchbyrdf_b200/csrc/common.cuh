@@ -180,6 +180,9 @@ struct dpf_index {
     dpf::DevBuf<double> fb;       // P (pStable b)
     dpf::DevBuf<int32_t> fw;      // P (pStable w)
     dpf::DevBuf<double> Ap;       // L x pb x 32
+    dpf::DevBuf<double> Apb;      // L x pb: b of the partitioner chains (pStable family; dpf_set_partitioners_pstable)
+    dpf::DevBuf<int32_t> Apw;     // L x pb: w
+    bool part_pstable = false;
     std::vector<double> hA;       // host copy (for At construction)
     int At_ld = 0;
 

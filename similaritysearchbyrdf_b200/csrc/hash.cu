@@ -400,18 +400,27 @@ k_project_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, 
 // key packing (AngleHashFamily.scala:187-195 / PStableHashFamily.scala:122-143), key transform
 // (LSH.scala:152-161) and K2 partition id (Partitioner.scala:40-64), one thread per (vector, table)
 // ---------------------------------------------------------------------------------------------------------
+// With the pStable family the partitioner's chain is a pStable chain too (its LSH is built from the main configuration,
+// DensevectorRDFInit.scala:63-70): the pb sums are quantised ((sum + b) / w).toInt and packed by Arrays.hashCode
+// (PStableHashFamily.scala:155-177); pbb / pbw are that chain's b and w, null for the angle family.
 __device__ __forceinline__ int32_t partition_id_dev(int32_t key, const double* ap /* pb x 32, smem */, int pb,
-                                                    int transform) {
+                                                    int transform, const double* pbb = nullptr, const int32_t* pbw = nullptr) {
     if (pb == 0) return 0;
-    uint32_t r = 0;
+    uint32_t r = pbb ? 1u : 0u;
     for (int j = 0; j < pb; ++j) {
         double s = 0.0;
 #pragma unroll 8
         for (int i = 0; i < 32; ++i)   // a * 1.0 for the set bits, ascending i; a clear bit adds +0.0, which leaves
             s = __dadd_rn(s, (((uint32_t)key >> i) & 1u) ? ap[j * 32 + i] : 0.0);   // the value (and s <= 0) unchanged
-        r = (r << 1) | (!(s <= 0.0) ? 1u : 0u);
+        if (pbb) {
+            const int32_t q = __double2int_rz(__ddiv_rn(__dadd_rn(s, pbb[j]), (double)pbw[j]));
+#pragma unroll
+            for (int sh = 24; sh >= 0; sh -= 8) r = 31u * r + (uint32_t)(int32_t)(int8_t)((uint32_t)q >> sh);
+        } else {
+            r = (r << 1) | (!(s <= 0.0) ? 1u : 0u);
+        }
     }
-    int32_t pk = (int32_t)(r << (32 - pb));
+    int32_t pk = pbb ? (int32_t)r : (int32_t)(r << (32 - pb));
     pk = apply_key_transform(pk, transform);
     return (int32_t)((uint32_t)pk >> (32 - pb));
 }
@@ -419,13 +428,19 @@ __device__ __forceinline__ int32_t partition_id_dev(int32_t key, const double* a
 template <bool PSTABLE>
 __global__ void __launch_bounds__(256)
 k_pack_keys(const uint32_t* __restrict__ S, const int32_t* __restrict__ PQ, const int32_t* __restrict__ chain,
-            const double* __restrict__ Ap, int64_t n, int P, int PW, int k, int pb, int transform,
-            int32_t* __restrict__ keys, uint8_t* __restrict__ pids, int64_t ld) {
+            const double* __restrict__ Ap, const double* __restrict__ Apb, const int32_t* __restrict__ Apw, int64_t n, int P,
+            int PW, int k, int pb, int transform, int32_t* __restrict__ keys, uint8_t* __restrict__ pids, int64_t ld) {
     __shared__ int32_t ch[kMaxChain];
     __shared__ double ap[kMaxPb * 32];
+    __shared__ double pbb[kMaxPb];
+    __shared__ int32_t pbw[kMaxPb];
     const int t = blockIdx.y;
     if (threadIdx.x < k) ch[threadIdx.x] = chain[t * k + threadIdx.x];
     for (int i = threadIdx.x; i < pb * 32; i += blockDim.x) ap[i] = Ap[(int64_t)t * pb * 32 + i];
+    if (Apb && threadIdx.x < pb) {
+        pbb[threadIdx.x] = Apb[t * pb + threadIdx.x];
+        pbw[threadIdx.x] = Apw[t * pb + threadIdx.x];
+    }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -457,7 +472,7 @@ k_pack_keys(const uint32_t* __restrict__ S, const int32_t* __restrict__ PQ, cons
     }
     const int32_t fk = apply_key_transform((int32_t)key, transform);
     keys[(int64_t)t * ld + i] = fk;
-    if (pids) pids[(int64_t)t * ld + i] = (uint8_t)partition_id_dev(fk, ap, pb, transform);
+    if (pids) pids[(int64_t)t * ld + i] = (uint8_t)partition_id_dev(fk, ap, pb, transform, Apb ? pbb : nullptr, pbw);
 }
 
 // The same, table-driven, for the angle family with P <= 128 sign bits per vector.  k_pack_keys spends ~750 instructions
@@ -624,12 +639,13 @@ static void pack_launch(dpf_index* h, int64_t n, int32_t* keys_out, uint8_t* pid
             k_pack_keys_tab<2><<<g2, 256, smem, h->stream>>>(h->signs.p, h->chain.p, h->Ap.p, n, h->PW, h->cfg.k, h->cfg.pb,
                                                             h->cfg.key_transform, keys_out, pids_out, ld);
     } else if (h->cfg.family_kind == DPF_FAMILY_PSTABLE)
-        k_pack_keys<true><<<grid, 256, 0, h->stream>>>(nullptr, h->pq.p, h->chain.p, h->Ap.p, n, h->P, h->PW, h->cfg.k,
-                                                       h->cfg.pb, h->cfg.key_transform, keys_out, pids_out, ld);
+        k_pack_keys<true><<<grid, 256, 0, h->stream>>>(nullptr, h->pq.p, h->chain.p, h->Ap.p, h->part_pstable ? h->Apb.p : nullptr,
+                                                       h->Apw.p, n, h->P, h->PW, h->cfg.k, h->cfg.pb, h->cfg.key_transform,
+                                                       keys_out, pids_out, ld);
     else
-        k_pack_keys<false><<<grid, 256, 0, h->stream>>>(h->signs.p, nullptr, h->chain.p, h->Ap.p, n, h->P, h->PW,
-                                                        h->cfg.k, h->cfg.pb, h->cfg.key_transform, keys_out, pids_out,
-                                                        ld);
+        k_pack_keys<false><<<grid, 256, 0, h->stream>>>(h->signs.p, nullptr, h->chain.p, h->Ap.p, nullptr, nullptr, n, h->P,
+                                                        h->PW, h->cfg.k, h->cfg.pb, h->cfg.key_transform, keys_out,
+                                                        pids_out, ld);
     DPF_LAUNCHED();
     DPF_CUDA(cudaGetLastError());
 }

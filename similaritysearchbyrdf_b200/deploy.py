@@ -326,7 +326,13 @@ class _RDFInit:
         L = lsh.chain.shape[0]
         from . import synth
         # one private LocalitySensitivePartitioner per table (confForPartitioner: vectorDim=32, chainLength=partitionBits)
-        Ap = synth.partitioner_family(L, pb, int(conf.get("mclab.lsh.seed", 88387)) + 1)
+        pseed = int(conf.get("mclab.lsh.seed", 88387)) + 1
+        if lsh.name == "pStable":    # confForPartitioner falls back to the main conf: the partitioner chains are pStable too
+            Ap, pb_b, pb_w = synth.pstable_partitioner_family(
+                L, pb, conf.getDouble("mclab.lsh.family.pstable.mu"), conf.getDouble("mclab.lsh.family.pstable.sigma"),
+                conf.getInt("mclab.lsh.family.pstable.w"), pseed)
+        else:
+            Ap, pb_b, pb_w = synth.partitioner_family(L, pb, pseed), None, None
         self.close()
         self.index = DPFIndex(d=conf.getInt("mclab.lsh.vectorDim"), L=L, k=lsh.chain.shape[1], pb=pb,
                               bucket_bits=conf.getInt("mclab.lshTable.bucketBits"),
@@ -336,7 +342,7 @@ class _RDFInit:
                               device=int(conf.get("mclab.gpu.device", 0)), rank=int(conf.get("mclab.gpu.rank", 0)),
                               world=int(conf.get("mclab.gpu.world", 1)))
         self.index.set_family(lsh.A, lsh.chain, lsh.b, lsh.w)
-        self.index.set_partitioners(Ap)
+        self.index.set_partitioners(Ap, pb_b, pb_w)
         self.partitioners = Ap
 
     @property

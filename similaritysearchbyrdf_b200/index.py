@@ -188,11 +188,19 @@ class DPFIndex:
         self.P = A.shape[0]
         self._ck(self.lib.dpf_set_family(self.h, _p(A), A.shape[0], _p(chain_idx), _p(b), _p(w)))
 
-    def set_partitioners(self, Ap):
+    def set_partitioners(self, Ap, b=None, w=None):
+        """Ap: L x pb x 32.  A pStable index passes the offsets b and widths w (L x pb each) of its partitioner chains
+        as well (dpf_set_partitioners_pstable)."""
         Ap = _f64(Ap)
         if Ap.shape != (self.L, self.pb, 32):
             raise ValueError("Ap must be L x pb x 32")
-        self._ck(self.lib.dpf_set_partitioners(self.h, _p(Ap)))
+        if b is None and w is None:
+            self._ck(self.lib.dpf_set_partitioners(self.h, _p(Ap)))
+            return
+        b, w = _f64(b), _i32(w)
+        if b.shape != (self.L, self.pb) or w.shape != (self.L, self.pb):
+            raise ValueError("b and w must be L x pb")
+        self._ck(self.lib.dpf_set_partitioners_pstable(self.h, _p(Ap), _p(b), _p(w)))
 
     # ---- hashing --------------------------------------------------------------------------------------------
     def hash_dense(self, X):

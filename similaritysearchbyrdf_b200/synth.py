@@ -44,6 +44,16 @@ def partitioner_family(L, pb, seed):
     return v / np.sqrt((v * v).sum(-1, keepdims=True))
 
 
+def pstable_partitioner_family(L, pb, mu, sigma, w, seed):
+    """The partitioners of a pStable index: each table's private LSH(confForPartitioner) draws a PStableHashFamily over
+    32 dimensions and picks a chain of pb functions from it (DensevectorRDFInit.scala:63-77, PStableHashFamily.scala:
+    37-78).  Returns (Ap[L x pb x 32], b[L x pb], w[L x pb])."""
+    rng = np.random.default_rng(seed)
+    Ap = mu + sigma * rng.standard_normal((L, pb, 32))
+    Ap[Ap == 0.0] = sigma if sigma else 1.0
+    return Ap, rng.random((L, pb)) * w, np.full((L, pb), w, np.int32)
+
+
 def clustered_dense(n, d, seed, centres, spread=0.35, lo=None, hi=None, integer=False, relu=False, chunk=1 << 18):
     """n x d FP64 rows: centre + spread * N(0, I).  With lo/hi the values are mapped to [lo, hi] (and rounded when
     `integer`); with `relu` negative coordinates are clamped to zero first (histogram-like, about half the

@@ -65,6 +65,32 @@ def test_deploy_dense_simple_test(tmp_path):
     D.LSHServer.lshEngine = None
 
 
+def test_deploy_dense_pstable_family(tmp_path):
+    """mclab.lsh.name = pStable through the facade: pStable keys AND pStable partitioner chains (confForPartitioner falls
+    back to the main conf, DensevectorRDFInit.scala:63-70), candidate sets equal to the oracle's with the same functions."""
+    from similaritysearchbyrdf_b200 import deploy as D
+    X, Q = synth.config1(n=3000)
+    path = os.path.join(tmp_path, "dense.txt")
+    _write_dense_file(path, X)
+    conf = D.Config.parseString("mclab.lsh.name=pStable\nmclab.lshTable.bufferOverflow=40").withFallback(D.testBaseConf)
+    D.LSHServer.lshEngine = D.LSH(conf)
+    D.LSHServer.isUseDense = True
+    all_vectors = D.DensevectorRDFInit.newMultiThreadFit(path, conf)
+    ids = list(range(100))
+    vecs = [all_vectors[i] for i in ids]
+    a = D.DensevectorRDFInit.NewMultiThreadQueryBatch(ids, vecs, 1, 5)
+    lsh = D.LSHServer.lshEngine
+    L = lsh.chain.shape[0]
+    Ap, pb_b, pb_w = synth.pstable_partitioner_family(L, conf.getInt("mclab.lsh.partitionBits"), 0.0, 1.0, 4,
+                                                      int(conf.get("mclab.lsh.seed", 88387)) + 1)
+    assert np.array_equal(Ap, D.DensevectorRDFInit.partitioners)
+    o = U.make_oracle(100, lsh.A, lsh.chain, Ap, bucket_overflow=40, family_kind=1, b=lsh.b, w=lsh.w, pb_b=pb_b, pb_w=pb_w)
+    o.fit_dense(X)
+    off, cand = o.query_candidates_dense(np.stack([v.values for v in vecs]), np.array(ids, np.int32), 1)
+    assert [set(cand[off[i]:off[i + 1]].tolist()) for i in range(100)] == a
+    D.LSHServer.lshEngine = None
+
+
 def test_deploy_sparse_facade(tmp_path):
     from similaritysearchbyrdf_b200 import deploy as D
     Dm = 300

@@ -117,13 +117,28 @@ def test_hash_pstable_family():
     chain = np.arange(L * k, dtype=np.int32).reshape(L, k)
     b = rng.random(L * k) * 4
     w = np.full(L * k, 4, np.int32)
-    Ap = synth.partitioner_family(L, 3, 2)
+    # the partitioner chains of a pStable index are pStable functions too (DensevectorRDFInit.scala:63-70)
+    Ap, pb_b, pb_w = synth.pstable_partitioner_family(L, 3, 0.0, 1.0, 4, 2)
     X = rng.standard_normal((3000, d)) * 3
-    o = U.make_oracle(d, A, chain, Ap, family_kind=1, b=b, w=w)
-    ix = U.make_index(d, A, chain, Ap, family_kind=1, b=b, w=w)
+    o = U.make_oracle(d, A, chain, Ap, family_kind=1, b=b, w=w, pb_b=pb_b, pb_w=pb_w)
+    ix = U.make_index(d, A, chain, Ap, family_kind=1, b=b, w=w, pb_b=pb_b, pb_w=pb_w)
     ko, po = o.hash_dense(X)
     kg, pg = ix.hash_dense(X)
     assert np.array_equal(ko, kg) and np.array_equal(po, pg)
+    assert len(np.unique(po)) > 2                                    # (Arrays.hashCode's top bits do not reach all 8)
+    # ... and the whole path on top of them: buckets, multi-step candidates, top-k
+    o.fit_dense(X)
+    ix.fit_dense(X)
+    U.assert_buckets_equal(o, ix, L)
+    Q = X[:200] + 0.05 * rng.standard_normal((200, d))
+    U.assert_csr_equal(o.query_candidates_dense(Q, None, 1), ix.query_candidates_dense(Q, None, 1))
+    # the angle-chain entry point is refused on a pStable index
+    from similaritysearchbyrdf_b200 import DPFIndex
+    bad = DPFIndex(d=d, L=L, k=k, pb=3, family_kind=1)
+    bad.set_family(A, chain, b, w)
+    with pytest.raises(B.DpfError):
+        bad.set_partitioners(Ap)
+    bad.close()
 
 
 def _small_csr(n, D, seed, mean=12):

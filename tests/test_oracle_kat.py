@@ -182,6 +182,45 @@ def test_partition_id_matches_definition(golden_dir):
     assert O.partition_id(0, Ap) == 0    # empty sum
 
 
+def test_partition_id_pstable_chain_matches_definition():
+    """With mclab.lsh.name = pStable the partitioner's LSH is a pStable one (confForPartitioner falls back to the main
+    conf, DensevectorRDFInit.scala:63-70): sub-index = PStableHashChain.compute(bits of the key).hashCode >>> (32 - pb)
+    (Partitioner.scala:58, PStableHashFamily.scala:155-177), restated here in plain Python."""
+    import math
+    rng = np.random.default_rng(12)
+    pb = 3
+    Ap = rng.standard_normal((pb, 32))
+    b = rng.random(pb) * 4
+    w = np.array([4, 3, 7], np.int32)
+
+    def to_int(x):                       # Scala Double.toInt
+        if math.isnan(x):
+            return 0
+        return max(-2**31, min(2**31 - 1, int(x)))
+
+    seen = set()
+    for h in list(rng.integers(-2**31, 2**31, 300)) + [0, -1, 1, -2**31]:
+        qs = []
+        for j in range(pb):
+            s = 0.0
+            for i in range(32):
+                if (int(h) >> i) & 1:
+                    s += Ap[j][i] * 1.0
+            qs.append(to_int((s + b[j]) / int(w[j])))
+        code = 1
+        for q in qs:
+            for byte in int(q).to_bytes(4, "big", signed=True):
+                code = (31 * code + (byte - 256 if byte > 127 else byte)) & 0xFFFFFFFF
+        want = code >> (32 - pb)
+        assert O.partition_id(h, Ap, 0, b, w) == want
+        seen.add(want)
+    assert len(seen) > 2                 # (the top bits of Arrays.hashCode over a dozen small bytes do not reach every value)
+    # with the "sampling" key transform the hash code is permuted before the shift (LSH.scala:113-126)
+    h = 123456789
+    code = O.pstable_key_from_dots([sum(Ap[j][i] for i in range(32) if (h >> i) & 1) for j in range(pb)], b, w)
+    assert O.partition_id(h, Ap, 1, b, w) == (O.sampling_key(code) & 0xFFFFFFFF) >> (32 - pb)
+
+
 # ---- RandomDrawTreeMap.java:435-465 -------------------------------------------------------------------------
 def test_tree_params():
     assert O.tree_params(28, 32, 32) == dict(SEG=16, nb=5, mask=31, MAXL=4)       # TestSettings defaults

@@ -15,9 +15,10 @@ def make_oracle(d, A, chain, Ap, **kw):
     L, k = chain.shape
     pb = Ap.shape[1]
     b, w = kw.pop("b", None), kw.pop("w", None)
+    pb_b, pb_w = kw.pop("pb_b", None), kw.pop("pb_w", None)
     o = O.Oracle(d=d, L=L, k=k, P=A.shape[0], pb=pb, **kw)
     o.set_family(A, chain, b, w)
-    o.set_partitioners(Ap)
+    o.set_partitioners(Ap, pb_b, pb_w)
     return o
 
 
@@ -26,12 +27,13 @@ def make_index(d, A, chain, Ap, **kw):
     L, k = chain.shape
     pb = Ap.shape[1]
     b, w = kw.pop("b", None), kw.pop("w", None)
+    pb_b, pb_w = kw.pop("pb_b", None), kw.pop("pb_w", None)
     store_mode = kw.pop("store_mode", None)
     ix = DPFIndex(d=d, L=L, k=k, pb=pb, **kw)
     if store_mode is not None:
         ix.set_store_mode(store_mode)
     ix.set_family(A, chain, b, w)
-    ix.set_partitioners(Ap)
+    ix.set_partitioners(Ap, pb_b, pb_w)
     return ix
 
 
