@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdpf_b200.so")
-SOURCES = ["hash.cu", "sort.cu", "forest.cu", "query.cu", "rerank_bm.cu", "rerank_u8.cu", "bm_group.cu", "rerank_tc.cu", "comm.cu", "incremental.cu", "store.cu", "textio.cu", "capi.cu"]
+SOURCES = ["hash.cu", "sort.cu", "forest.cu", "query.cu", "rerank_bm.cu", "rerank_u8.cu", "bm_group.cu", "rerank_tc.cu", "rerank_wide.cu", "comm.cu", "incremental.cu", "store.cu", "textio.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]
 

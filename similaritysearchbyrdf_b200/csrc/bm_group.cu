@@ -346,49 +346,54 @@ int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap
     return std::max<int64_t>(1, kMaxPairs / ((int64_t)h->cfg.L * cap));
 }
 
-void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc,
-                     uint32_t* q_entries) {
+// probe: the distinct leaves of every (query, table) pair into the probe cache + the leaf histogram.  The threshold
+// samples only need this part, so the caller forks its second stream right after it.
+void probe_leaves(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, uint32_t* q_entries) {
     const ProbeCtx c = make_ctx(h, steps, probe_mode);
     cudaStream_t st = h->stream;
-    const int L = c.L;
-    const int64_t warps = nqc * L;
+    const int64_t warps = nqc * c.L;
     const int64_t pairs_ub = warps * cap;
-    const int64_t nleaves = h->num_leaves;
     h->pair_cnt.reserve((size_t)warps + 1);
     h->probe_cache.reserve((size_t)pairs_ub);
     h->pair_q.reserve((size_t)pairs_ub);
-    const int64_t ntiles = (nleaves + LS_TILE - 1) / LS_TILE;
+    const int64_t ntiles = (h->num_leaves + LS_TILE - 1) / LS_TILE;
     h->scan_scratch.reserve((size_t)(4 * ntiles + 16));
     int32_t* ctr = h->counters.p;
-    {
-        StageTimer tm(h, DPF_T_PROBE_COUNT);
-        k_probe_leaves<<<(unsigned)((warps + 255) / 256), 256, 0, st>>>(
-            c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->leaf_cnt.p, h->pair_cnt.p, h->probe_cache.p, cap, q_entries,
-            reinterpret_cast<unsigned long long*>(ctr + CTR_STAT_NLZ), reinterpret_cast<unsigned long long*>(ctr + CTR_ENTRIES)); DPF_LAUNCHED();
-        DPF_CUDA(cudaGetLastError());
+    StageTimer tm(h, DPF_T_PROBE_COUNT);
+    k_probe_leaves<<<(unsigned)((warps + 255) / 256), 256, 0, st>>>(
+        c, qk.keys, h->qpids.p, qk.ld, q0, nqc, h->leaf_cnt.p, h->pair_cnt.p, h->probe_cache.p, cap, q_entries,
+        reinterpret_cast<unsigned long long*>(ctr + CTR_STAT_NLZ), reinterpret_cast<unsigned long long*>(ctr + CTR_ENTRIES)); DPF_LAUNCHED();
+    DPF_CUDA(cudaGetLastError());
+}
+
+// counting sort of the cached (leaf, query) pairs by leaf: scan of the histogram, then every pair takes its slot
+void group_pairs(dpf_index* h, int64_t nqc, int cap, bool use_tc) {
+    cudaStream_t st = h->stream;
+    const int L = h->cfg.L;
+    const int64_t warps = nqc * L;
+    const int64_t nleaves = h->num_leaves;
+    const int64_t ntiles = (nleaves + LS_TILE - 1) / LS_TILE;
+    int32_t* ctr = h->counters.p;
+    StageTimer tm(h, DPF_T_EXPAND);
+    DPF_CUDA(cudaMemsetAsync(h->scan_scratch.p, 0, (size_t)(4 * ntiles + 8) * sizeof(uint32_t), st));
+    DPF_CUDA(cudaMemsetAsync(ctr + CTR_NPAIRS_TC, 0, 3 * sizeof(int32_t), st));
+    if (ntiles > 0) {
+        k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
+            h->leaf_cnt.p, nleaves, (uint32_t)SS_UQ, h->leaf_len.p, 0u, h->leaf_off.p, h->leaf_unit_off.p,
+            reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE),
+            reinterpret_cast<unsigned long long*>(h->scan_scratch.p + 2), reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS),
+            reinterpret_cast<unsigned long long*>(ctr + CTR_BM_PAIRS_TOTAL)); DPF_LAUNCHED();
     }
-    {
-        StageTimer tm(h, DPF_T_EXPAND);
-        DPF_CUDA(cudaMemsetAsync(h->scan_scratch.p, 0, (size_t)(4 * ntiles + 8) * sizeof(uint32_t), st));
-        DPF_CUDA(cudaMemsetAsync(ctr + CTR_NPAIRS_TC, 0, 3 * sizeof(int32_t), st));
-        if (ntiles > 0) {
-            k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
-                h->leaf_cnt.p, nleaves, (uint32_t)SS_UQ, h->leaf_len.p, 0u, h->leaf_off.p, h->leaf_unit_off.p,
-                reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE),
-                reinterpret_cast<unsigned long long*>(h->scan_scratch.p + 2), reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS),
-                reinterpret_cast<unsigned long long*>(ctr + CTR_BM_PAIRS_TOTAL)); DPF_LAUNCHED();
-        }
-        if (ntiles > 0 && use_tc) {            // the same histogram once more, at the tcgen05 kernel's unit width
-            uint32_t* status2 = h->scan_scratch.p + 2 * ntiles + 4;
-            k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
-                h->leaf_cnt.p, nleaves, (uint32_t)TC_TQ, h->leaf_len.p, 128u, h->leaf_off.p, h->leaf_unit_off_tc.p,
-                reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE_TC), reinterpret_cast<unsigned long long*>(status2),
-                reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS_TC), nullptr); DPF_LAUNCHED();
-        }
-        k_fill_pairs<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(h->pair_cnt.p, h->probe_cache.p, cap, warps, h->leaf_cnt.p,
-                                                                  h->leaf_off.p, L, h->pair_q.p); DPF_LAUNCHED();
-        DPF_CUDA(cudaGetLastError());
+    if (ntiles > 0 && use_tc) {            // the same histogram once more, at the tcgen05 kernel's unit width
+        uint32_t* status2 = h->scan_scratch.p + 2 * ntiles + 4;
+        k_scan_leaves<<<(unsigned)ntiles, LS_THREADS, 0, st>>>(
+            h->leaf_cnt.p, nleaves, (uint32_t)TC_TQ, h->leaf_len.p, 128u, h->leaf_off.p, h->leaf_unit_off_tc.p,
+            reinterpret_cast<unsigned int*>(ctr + CTR_SCAN_TILE_TC), reinterpret_cast<unsigned long long*>(status2),
+            reinterpret_cast<uint32_t*>(ctr + CTR_NPAIRS_TC), nullptr); DPF_LAUNCHED();
     }
+    k_fill_pairs<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(h->pair_cnt.p, h->probe_cache.p, cap, warps, h->leaf_cnt.p,
+                                                              h->leaf_off.p, L, h->pair_q.p); DPF_LAUNCHED();
+    DPF_CUDA(cudaGetLastError());
 }
 
 // unit records of the grouped pairs: at most one partial unit per leaf plus one per SS_UQ pairs

@@ -34,15 +34,23 @@ namespace dpf {
 
 bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
     if (h->dbg[DPF_DBG_RERANK] == 1) return false;             // test hook: force the row-major kernel
-    if (!(h->leaf_table && h->dense && h->Xdev && h->cfg.d <= BM_KC && (h->cfg.d % 2) == 0 && (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
+    if (!(h->leaf_table && h->dense && h->Xdev && (h->cfg.d % 2) == 0 && (reinterpret_cast<uintptr_t>(h->Xdev) & 15) == 0 &&
           topk <= RR_MAXK))                                    // d even: the queries are FP64 rows moved in 16-byte pieces
         return false;
+    if (h->cfg.d > BM_KC) return wide_supported(h, metric);    // rerank_wide.cu
     if (metric == DPF_METRIC_DOT || metric == DPF_METRIC_ANGULAR) return true;
     // squared L2 = |q|^2 + |x|^2 - 2 q.x cancels in floating point; it is exact — and then identical to the reference's
     // sum of squared differences — only on the integer pipeline: byte rows and a batch of byte queries (the one case in
     // which the host has to read the batch's byte flag back before it can choose the path)
     return metric == DPF_METRIC_L2 && score_u8_usable(h) && h->Q8_valid;
 }
+
+// Survivor records the pool holds per query of a chunk.  The survivors of a query are roughly k x (entries it visits) /
+// (rows sampled for its threshold): they grow with k (the k-th best of a few hundred sampled rows is a weaker bar for
+// k = 100 than for 10) and with multi-step search (3-4 times the entries; measured on the GIST shape, k = 100: 3.4k
+// survivors per query at steps = 0, more than 9.6k at steps >= 1 — a pool that overflows sends every query to the exhaustive
+// kernel).  topk_device cuts the batch so that a chunk's share fits kMaxPool.
+int64_t bm_pool_per_query(int topk, int steps) { return (int64_t)std::max(2048, 96 * topk) * (steps > 0 ? 4 : 1); }
 
 // ---------------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk copy (sm_90+ PTX; on sm_100a: SYNCS.* and UBLKCP.S.G)
@@ -833,7 +841,8 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     if (nqc <= 0) return;
     const bool ang = metric == DPF_METRIC_ANGULAR;
     const bool l2 = metric == DPF_METRIC_L2;                    // byte pipeline only; keys are -distance, negated on output
-    const bool use_u8 = score_u8_usable(h);
+    const bool wide = d > BM_KC;                                // k_score_wide / k_threshold_wide on the FP64 rows
+    const bool use_u8 = !wide && score_u8_usable(h);
     int kind;
     const unsigned char* rows;
     unsigned row_bytes;
@@ -856,7 +865,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     if (use_tc) h->bm_descs.reserve((size_t)tc_cap * sizeof(TcRec));
     h->bm_taui.reserve((size_t)nqc + 2);
     int64_t pool_cap = h->dbg[DPF_DBG_POOL_RECORDS] > 0 ? h->dbg[DPF_DBG_POOL_RECORDS]
-                                                        : std::min<int64_t>(std::max<int64_t>(nqc * 2048, 1 << 20), 1LL << 28);
+                                                        : std::min<int64_t>(std::max<int64_t>(nqc * bm_pool_per_query(topk, steps), 1 << 20), kMaxPool);
     pool_cap = std::max<int64_t>(SURV_BLOCK, pool_cap / SURV_BLOCK * SURV_BLOCK);
     h->surv_pool.reserve((size_t)pool_cap * sizeof(SurvRec));
     h->scores.reserve((size_t)pool_cap);
@@ -873,7 +882,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     DPF_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t)nqc * 4 * sizeof(uint32_t), st));
     DPF_CUDA(cudaMemsetAsync(ctr + CTR_POOL, 0, 7 * sizeof(int32_t), st));      // pool cursor, chunk counts, overflow flag, dirty count
 
-    probe_and_group(h, qk, steps, probe_mode, q0, nqc, cap, use_tc, q_entries);
+    probe_leaves(h, qk, steps, probe_mode, q0, nqc, cap, q_entries);
 
     ChunkView cv;
     cv.Q = Qd + q0 * d;
@@ -892,7 +901,8 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     const size_t list_smem = (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
     const unsigned qgrid = (unsigned)((nqc + RR_WARPS - 1) / RR_WARPS);
 
-    // ---- thresholds: a row gather, on the handle's second stream beside the grouping chain on the main one --------------
+    // ---- thresholds: a row gather, on the handle's second stream (forked right after the probe) beside the grouping chain
+    //      (scan, pair fill, unit records) on the main one ------------------------------------------------------------
     {
         // sampled tables per query (one warp each): 6 on one GPU; a rank of G sees 1/G of every query's buckets, so its
         // lists stay short with fewer samples
@@ -902,7 +912,9 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         // On G GPUs a rank holds 1/G of a query's entries and fewer samples pay: measured per rank at configs[1]
         // (tools/nt_sweep.py --world G), 3 tables is the best or within 1% of it at G = 2, 4 and 8 (one table leaves
         // 860 survivors per query on the fullest rank of 8 and costs 0.2 ms more than it saves).
-        const int nt_default = !use_u8 ? 2 : (world <= 1 ? 6 : 3);
+        // (wide rows, k > 32: the k-th best of two buckets' rows is hardly a bar: four samples)
+        // (multi-step search visits 3-4 times the entries: twice the samples keep the survivor lists in proportion)
+        const int nt_default = (!use_u8 ? (wide && topk > 32 ? 4 : 2) : (world <= 1 ? 6 : 3)) * (wide && steps > 0 ? 2 : 1);
         const int NT = std::min(32, std::max(1, h->dbg[DPF_DBG_TAU_TABLES] > 0 ? (int)h->dbg[DPF_DBG_TAU_TABLES] : nt_default));
         h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
         h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
@@ -918,7 +930,9 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                                                          h->bm_tl_keys.p, h->bm_tl_ids.p, h->bm_tl_cnt.p);
             DPF_LAUNCHED();
         };
-        if (use_u8) {
+        if (wide) {
+            launch_threshold_wide(h, st2, metric, cv, NT, topk, list_smem);
+        } else if (use_u8) {
             // byte rows: the integer form when the whole batch is bytes, the FP64 form otherwise; which one applies is a
             // flag on the device, so both are launched and one of them returns at once
             if (try_int) {
@@ -942,6 +956,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         DPF_CUDA(cudaGetLastError());
     }
     DPF_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+    group_pairs(h, nqc, cap, use_tc);        // the main stream meanwhile: pairs grouped by leaf, unit records
     if (use_tc) emit_tc_recs(h, tc_cap, dirty);
     emit_units(h, use_tc);               // with the tcgen05 kernel the records only serve a batch that is not byte vectors
 
@@ -951,7 +966,9 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     DPF_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));            // thresholds from the second stream
     {
         StageTimer tm(h, DPF_T_RERANK);
-        if (use_u8) {
+        if (wide) {
+            launch_score_wide(h, cv, units, nunits_p, metric, flt, bm_stat);
+        } else if (use_u8) {
             if (use_tc)
                 launch_score_u8t(h, cv, reinterpret_cast<const TcRec*>(h->bm_descs.p),
                                  reinterpret_cast<const uint32_t*>(ctr + CTR_NUNITS_TC), tc_cap, h->bm_taui.p, flt, bm_stat);

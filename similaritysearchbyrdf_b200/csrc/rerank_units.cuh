@@ -7,7 +7,7 @@
 
 namespace dpf {
 
-constexpr int BM_KC = 128;             // largest supported d
+constexpr int BM_KC = 128;             // largest d of the staged kernels (k_score_stream, byte kernels); wider rows: rerank_wide.cu
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -164,10 +164,15 @@ int u8_query_pitch();                                                      // ro
 void launch_score_u8(dpf_index* h, const ChunkView& cv, const void* units, const uint32_t* nunits_p, int metric,
                      const Filter& flt, unsigned long long* bm_stat, bool int_kernel);
 // bm_group.cu: probe -> pairs grouped by leaf -> unit records, all sized on the host without reading anything back
-void probe_and_group(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, bool use_tc,
-                     uint32_t* q_entries);
+void probe_leaves(dpf_index* h, const QueryKeys& qk, int steps, int probe_mode, int64_t q0, int64_t nqc, int cap, uint32_t* q_entries);
+void group_pairs(dpf_index* h, int64_t nqc, int cap, bool use_tc);
 void emit_units(dpf_index* h, bool only_if_fp64_queries);
 void emit_tc_recs(dpf_index* h, int64_t cap, const DirtySet& dirty);                                           // the tcgen05 kernel's units
+// rerank_wide.cu: d > BM_KC (FP64 rows streamed from global memory, no staging)
+bool wide_supported(const dpf_index* h, int metric);
+void launch_threshold_wide(dpf_index* h, cudaStream_t st, int metric, const ChunkView& cv, int NT, int topk, size_t list_smem);
+void launch_score_wide(dpf_index* h, const ChunkView& cv, const void* units, const uint32_t* nunits_p, int metric, const Filter& flt,
+                       unsigned long long* bm_stat);
 // rerank_tc.cu
 bool score_u8t_usable(const dpf_index* h, int metric);
 void launch_score_u8t(dpf_index* h, const ChunkView& cv, const TcRec* recs, const uint32_t* nunits_p, int64_t cap, const int32_t* taui,

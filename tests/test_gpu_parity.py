@@ -347,6 +347,61 @@ def test_topk_bucket_major_self_exclusion_and_qids():
     assert not any(qids[i] in ig[i] for i in range(128))
 
 
+# ---- K5c: bucket-major re-rank for d > 128 (rerank_wide.cu) ---------------------------------------------------------
+@pytest.mark.parametrize("d", [130, 132, 200, 960])
+@pytest.mark.parametrize("metric", [B.METRIC_DOT, B.METRIC_ANGULAR])
+@pytest.mark.parametrize("topk", [10, 100])
+def test_topk_wide_rows_bucket_major(d, metric, topk):
+    """d > 128 (GIST shape): rows streamed once per unit of <= 16 queries.  Partial last column group (d = 130, 132),
+    long runs of pairs (both n-blocks), buckets longer than one 32-row slab, register (k <= 32) and shared-memory lists;
+    against the oracle, and the row-major kernel given the same candidates."""
+    rng = np.random.default_rng(300 + d)
+    centres = rng.standard_normal((12, d))
+    X = np.repeat(centres, 250, axis=0) + 0.05 * rng.standard_normal((3000, d))
+    A, chain, Ap = U.make_functions(d, family_size=max(40, min(d, 160)), table_num=3, permutation_num=2, seed=31 + d)
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=70); ix = U.make_index(d, A, chain, Ap, bucket_overflow=70)
+    o.fit_dense(X); ix.fit_dense(X)
+    Qs = X[::5] + 0.01 * rng.standard_normal((600, d))
+    io, so = o.query_topk_dense(Qs, None, 1, topk, metric)
+    ig, sg = ix.query_topk_dense(Qs, None, 1, topk, metric)
+    U.assert_topk_close(io, so, ig, sg)
+    st = ix.stats()
+    assert st["bm_pairs"] > 16 * 3 * 2 and st["bm_rows_staged"] > 0, "the wide bucket-major path did not run"
+    with ix.debug_options(wide=1):
+        ir, sr = ix.query_topk_dense(Qs, None, 1, topk, metric)
+    assert ix.stats()["bm_pairs"] == 0, "expected the row-major kernel"
+    U.assert_topk_close(ir, sr, ig, sg)
+    ix.close(); o.close()
+
+
+def test_topk_wide_rows_corner_cases():
+    """d > 128: integer-valued data (every dot product exact: bit-equal to the row-major kernel), self-exclusion with
+    qids, queries whose samples hold fewer than k rows, a survivor pool too small for the batch (exhaustive fallback)."""
+    d = 192
+    rng = np.random.default_rng(77)
+    X = np.rint(8 * rng.standard_normal((5000, d))) + 0.0
+    X[2500:] = X[:2500] + np.rint(rng.standard_normal((2500, d)))
+    A, chain, Ap = U.make_functions(d, family_size=96, table_num=4, permutation_num=2, seed=12)
+    o = U.make_oracle(d, A, chain, Ap, bucket_overflow=40); ix = U.make_index(d, A, chain, Ap, bucket_overflow=40)
+    o.fit_dense(X); ix.fit_dense(X)
+    qids = np.concatenate([np.arange(0, 140), np.arange(2500, 2900)]).astype(np.int32)
+    Qs = X[qids]
+    for steps, k in ((0, 5), (2, 5), (3, 64)):
+        io, so = o.query_topk_dense(Qs, qids, steps, k, B.METRIC_DOT)
+        ig, sg = ix.query_topk_dense(Qs, qids, steps, k, B.METRIC_DOT)
+        U.assert_topk_close(io, so, ig, sg)
+        assert ix.stats()["bm_pairs"] > 0
+        with ix.debug_options(wide=1):
+            ir, sr = ix.query_topk_dense(Qs, qids, steps, k, B.METRIC_DOT)
+        assert np.array_equal(ir, ig) and np.array_equal(sr, sg), (steps, k)
+    assert not any(qids[i] in ig[i] for i in range(128))
+    with ix.debug_options(pool_records=256):
+        i2, s2 = ix.query_topk_dense(Qs, qids, 3, 64, B.METRIC_DOT)
+    assert ix.stats()["bm_direct"] > 0, "expected queries to overflow the pool"
+    assert np.array_equal(i2, ig) and np.array_equal(s2, sg)
+    ix.close(); o.close()
+
+
 # ---- compact store (store.cu): lossless uint8 / float32 copy of the rows for the re-rank ----------------------------
 def _store_data(kind, n, d, seed):
     rng = np.random.default_rng(seed)

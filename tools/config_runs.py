@@ -80,18 +80,35 @@ def run_gist(a):
     ids_d = torch.empty((nq, K), dtype=torch.int32, device="cuda")
     sc_d = torch.empty((nq, K), dtype=torch.float64, device="cuda")
     for steps in (0, 1, 2, 3):
-        for rep in range(2):
-            torch.cuda.synchronize(); t0 = time.time()
-            ix.query_topk_dense_dev(Qd.data_ptr(), nq, 0, steps, K, B.METRIC_DOT, ids_d.data_ptr(), sc_d.data_ptr())
-            torch.cuda.synchronize(); ms = 1e3 * (time.time() - t0)
-        st, s2 = ix.stage_times_ms(), ix.stats()
-        uniq = s2["last_candidates"]
-        rec["steps"][str(steps)] = {
-            "ms": round(ms, 3), "queries_per_s": nq / (ms * 1e-3), "stage_ms": r3(st),
-            "unique_candidates_per_query": uniq / nq, "with_dups_per_query": s2["last_cand_with_dups"] / nq,
-            "rerank_alg_gbs": uniq * (8 * d + 4) / (st["rerank"] * 1e-3) / 1e9 if st["rerank"] else None,
-            "rerank_frac_of_hbm_peak": uniq * (8 * d + 4) / (st["rerank"] * 1e-3) / 1e9 / PEAK if st["rerank"] else None,
-            "recall_at_100": recall_at(Xd, Qd, ids_d.cpu().numpy(), K)}
+        rec["steps"][str(steps)] = {}
+        ref_ids = None
+        for mode, wide_opt in (("bucket_major_wide", 0), ("row_major", 1)):      # rerank_wide.cu against the row-major gather
+            ix.set_debug_option(B.DBG_WIDE, wide_opt)
+            for rep in range(3):
+                torch.cuda.synchronize(); t0 = time.time()
+                ix.query_topk_dense_dev(Qd.data_ptr(), nq, 0, steps, K, B.METRIC_DOT, ids_d.data_ptr(), sc_d.data_ptr())
+                torch.cuda.synchronize(); ms = 1e3 * (time.time() - t0)
+            st, s2 = ix.stage_times_ms(), ix.stats()
+            ids_h = ids_d.cpu().numpy().copy()
+            r = {"ms": round(ms, 3), "queries_per_s": nq / (ms * 1e-3), "stage_ms": r3(st),
+                 "with_dups_per_query": s2["last_cand_with_dups"] / nq}
+            if wide_opt == 0:
+                rows = s2["bm_rows_staged"]
+                r.update({"pairs": s2["bm_pairs"], "units": s2["bm_runs"], "rows_staged": rows, "survivors_per_query": s2["bm_survivors"] / nq,
+                          "answered_exhaustively": s2["bm_direct"],
+                          "rerank_alg_gbs": rows * 8 * d / (st["rerank"] * 1e-3) / 1e9 if st["rerank"] else None,
+                          "rerank_frac_of_hbm_peak": rows * 8 * d / (st["rerank"] * 1e-3) / 1e9 / PEAK if st["rerank"] else None,
+                          "rerank_tflops": 2.0 * d * 16 * rows / (st["rerank"] * 1e-3) / 1e12 if st["rerank"] else None,
+                          "recall_at_100": recall_at(Xd, Qd, ids_h, K)})
+                ref_ids = ids_h
+            else:
+                uniq = s2["last_candidates"]
+                r.update({"unique_candidates_per_query": uniq / nq,
+                          "rerank_alg_gbs": uniq * (8 * d + 4) / (st["rerank"] * 1e-3) / 1e9 if st["rerank"] else None,
+                          "rerank_frac_of_hbm_peak": uniq * (8 * d + 4) / (st["rerank"] * 1e-3) / 1e9 / PEAK if st["rerank"] else None,
+                          "ids_equal_to_bucket_major_frac": float((ids_h == ref_ids).mean())})
+            rec["steps"][str(steps)][mode] = r
+        ix.set_debug_option(B.DBG_WIDE, 0)
     emit(rec)
 
 
