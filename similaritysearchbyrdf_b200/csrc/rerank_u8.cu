@@ -429,16 +429,22 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     const bool has0 = 16u * t < pitch, has1 = 64u + 16u * t < pitch;
     const bool two_chunks = pitch > 64;
     const unsigned off0 = has0 ? 16u * t : 0u, off1 = has1 ? 64u + 16u * t : 0u;   // clamped, see k_score_u8d
-    const int64_t nunits = *nunits_p;
-    const int64_t W = (int64_t)gridDim.x * U8_WARPS;
-    const int64_t u0 = (int64_t)blockIdx.x * U8_WARPS + warp;
-    const int64_t nmine = nunits > u0 ? (nunits - u0 + W - 1) / W : 0;     // this warp's units: u0 + k W, k < nmine
+    unsigned long long xb0 = (unsigned long long)(X8 + off0), xb1 = (unsigned long long)(X8 + off1);
+    asm volatile("" : "+l"(xb0), "+l"(xb1));     // kept as two 64-bit registers (the compiler would re-add base + offset per address)
+    // (Tried: a quarter warp copying one whole 128-byte row per instruction instead of this fragment pattern — the same
+    // 1.17 ms: both halves of a row are requested back to back here and the kernel moves 6.4 TB/s from L2 to the SMs (ncu
+    // l1tex__m_xbar2l1tex_read_bytes), the rate of the measured device copy; 17 % fewer instructions did not change it either.)
+    // (unit counts are 32-bit: the record array of a chunk holds < 2^31 units; 32-bit counters keep the ring bookkeeping short)
+    const int nunits = (int)*nunits_p;
+    const int W = (int)gridDim.x * U8_WARPS;
+    const int u0 = (int)blockIdx.x * U8_WARPS + warp;
+    const int nmine = nunits > u0 ? (nunits - u0 + W - 1) / W : 0;         // this warp's units: u0 + k W, k < nmine
     if (nmine == 0) return;
     unsigned rows_staged = 0;
     SurvivorSink sink;
 
     // record k -> ring slot k % US_R (joins the cp.async group that is committed next)
-    auto rec_request = [&](int64_t k, int rslot) {
+    auto rec_request = [&](int k, int rslot) {
         if (k < nmine && lane < US_REC_CHUNKS)
             cp_async16(reinterpret_cast<unsigned char*>(&recs[rslot]) + 16 * lane,
                        reinterpret_cast<const unsigned char*>(units + (u0 + k * W)) + 16 * lane);
@@ -453,7 +459,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
         const int len = (int)r->len;
         return 32 * w < len ? __ldg(ids_sorted + r->bstart + min(32 * w + lane, len - 1)) : 0;
     };
-    int64_t pk = 0;                    // unit being produced
+    int pk = 0;                        // unit being produced
     int p_rslot = 0;                   // = pk % US_R; the record requested when pk is opened goes to (p_rslot + US_D) % US_R
     int p_tile = 0, p_len = (int)recs[0].len;
     int p_w0 = recs[0].ids0[lane], p_w1 = win_load(&recs[0], 1), p_w2 = win_load(&recs[0], 2), p_w3 = win_load(&recs[0], 3);
@@ -465,9 +471,10 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int row = min(16 * p_tile + 8 * rr + g, p_len - 1);
-                const unsigned char* xp = X8 + (unsigned long long)(unsigned)__shfl_sync(0xffffffffu, p_w0, row & 31) * pitch;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * rr) * 512), "l"(xp + off0) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * rr + 1) * 512), "l"(xp + off1) : "memory");
+                // (the chunk offsets are folded into the two base pointers: one multiply-add per address)
+                const unsigned long long ro = (unsigned long long)(unsigned)__shfl_sync(0xffffffffu, p_w0, row & 31) * pitch;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * rr) * 512), "l"(xb0 + ro) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * rr + 1) * 512), "l"(xb1 + ro) : "memory");
             }
             ++p_tile;
             if (16 * p_tile >= p_len) {                          // unit done: open the next one
@@ -520,7 +527,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
     };
     stage2(0);
     int c_slot = 0, c_rslot = 0;       // consumer's tile slot and record slot; the producer writes tile slot c_slot - 1
-    for (int64_t k = 0; k < nmine; ++k) {
+    for (int k = 0; k < nmine; ++k) {
         __syncwarp();                                            // records are copied by other lanes
         const UnitRec* r = &recs[c_rslot];
         const uint32_t bstart = r->bstart;
@@ -586,7 +593,15 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
                 }
             }
             // Nearly every tile has no score above its thresholds: one vote over all eight scores of the thread decides
-            // whether to look closer.
+            // whether to look closer.  Dot product: the largest of a query's four scores against its bar is all the vote
+            // needs (4 instructions per query instead of a compare + row / slot masks per score); rows past the bucket's
+            // end repeat its last row and unused query slots carry INT_MAX as their bar, so the only false alarms are
+            // tiles the exact test below would also open.
+            if (!ANGULAR && !L2) {
+                const int m0 = max(max(acc[0][0], acc[0][1]), max(acc[1][0], acc[1][1]));
+                const int m1 = max(max(acc[0][2], acc[0][3]), max(acc[1][2], acc[1][3]));
+                if (!__any_sync(0xffffffffu, m0 >= c_taui[0] || m1 >= c_taui[1])) continue;
+            }
             int key[2][2][2];                                    // [query g / 8 + g][row half][row 2t + e]
             bool pass[2][2][2];
             bool any = false;

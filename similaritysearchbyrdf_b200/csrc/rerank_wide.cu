@@ -10,11 +10,11 @@
 //
 //   k_score_wide       warp per unit; the bucket's rows in slabs of 32 (four DMMA m-tiles), the unit's <= 16 queries as two
 //                      n-blocks.  A slab of whole rows does not fit in shared memory next to sixteen 7.5 KB queries, so
-//                      rows and queries stream through a small per-warp ring one 64-byte column group at a time: every
-//                      thread copies (cp.async, 16 bytes) exactly the fragment pieces it multiplies, three groups ahead
-//                      (rows: HBM; queries: L2 / L1 — a slab of 32 rows re-reads the unit's queries once, +50 % / +25 %
-//                      of L2 traffic on top of the rows for two / one n-blocks).  16 DMMA.8x8x4 per six 16-byte pieces
-//                      of a thread.  Only scores that reach the query's threshold leave the kernel (SurvivorSink).
+//                      rows and queries stream through a per-warp ring 16 columns (one 128-byte line of every row and
+//                      query) at a time, copied with cp.async a quarter warp per line, two to three stages ahead (rows:
+//                      HBM; queries: L2 / L1 — a slab of 32 rows re-reads the unit's queries once, +50 % / +25 % of L2
+//                      traffic on top of the rows for two / one n-blocks).  32 DMMA.8x8x4 per stage.  Only scores that
+//                      reach the query's threshold leave the kernel (SurvivorSink).
 //   k_threshold_wide   the threshold samples of k_threshold (rerank_bm.cu) for any d: warp per (query, sampled table), the
 //                      lanes stride over the 16-byte chunks of four rows at a time, plain FP64 FMAs, lower bound = score
 //                      minus twice the rounding bound of a length-d dot product in any order.
@@ -40,13 +40,17 @@ __device__ __forceinline__ double2 ldg_d2_stream(const double* p) {
     return v;
 }
 
-// Column groups (8 columns = one 64-byte piece of every row and query) in flight per thread.  With loads straight into
-// registers one group ahead a warp kept 3 KB in flight and the kernel sat at 1.8 TB/s (measured: one group per full
-// memory round trip of ~2.7 us under load); the ring below keeps WD_ST - 1 groups = 9 KB per warp, 144 KB per SM, in flight
-// without holding registers.
-constexpr int WD_ST = 4;
-constexpr int WD_SLOTS = WD_MT + 2;        // 16-byte pieces per thread and group: four rows, two queries
-constexpr size_t WD_SMEM = (size_t)WD_WARPS * WD_ST * WD_SLOTS * 32 * 16;      // 96 KB: two CTAs per SM
+// Ring geometry.  A stage = 16 columns = ONE 128-byte line of each of the slab's 32 rows and of the unit's 16 queries
+// (48 lines, 6 KB).  Two earlier forms of this kernel had every thread fetch exactly the 16-byte fragment pieces it
+// multiplies (straight into registers one column group ahead; then through a per-thread cp.async ring three groups
+// ahead): both sat at 1.9 TB/s of rows whatever the depth, with ncu showing every unit idle and the warps throttled on the
+// memory-instruction queue — a warp instruction of that pattern asks for half of eight lines, and the SM tracks a bounded
+// number of pending lines (~512: 32 KB in flight at 64 bytes per line).  Here a quarter warp copies a whole line, four
+// lines per instruction, and the fragment owners read them back from shared memory.
+constexpr int WD_ST = 4;                   // stages per warp: two or three in flight while one is multiplied
+constexpr int WD_LINES = WD_SLAB + 16;     // lines per stage
+constexpr size_t WD_STAGE_BYTES = (size_t)WD_LINES * 128;
+constexpr size_t WD_SMEM = (size_t)WD_WARPS * WD_ST * WD_STAGE_BYTES;      // 192 KB: one CTA per SM
 
 __device__ __forceinline__ void cp16_cg(unsigned dst, const void* src) {      // rows: L2 only
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -55,27 +59,29 @@ __device__ __forceinline__ void cp16_ca(unsigned dst, const void* src) {      //
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// Every thread copies exactly the pieces it will multiply (row 8mt + g / query 8nb + g, chunk 4j + t), into its own
-// 16-byte slots of the warp's ring: no thread reads what another one copied, so the ring needs no barrier — each thread
-// waits for its own cp.async groups.
+// Shared-memory layout of a stage: line l (rows 0..31, then queries 0..15) at l * 128; its 16-byte chunk c at position
+// c ^ 4(l & 1).  Producer: a quarter warp writes the 8 chunks of one line = 128 contiguous bytes.  Consumer: thread (g, t)
+// reads chunk 4jj + t of line 8mt + g; a quarter warp covers two neighbouring lines whose halves the swizzle puts on
+// disjoint banks: LDS.128 without conflicts, no padding.
 template <bool ANGULAR>
-__global__ void __launch_bounds__(WD_WARPS * 32, 2)
+__global__ void __launch_bounds__(WD_WARPS * 32, 1)
 k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, const UnitRec* __restrict__ units,
              const uint32_t* __restrict__ nunits_p, const int32_t* __restrict__ ids_sorted, Filter flt,
              unsigned long long* __restrict__ stat /* [0] units, [1] rows staged */) {
-    extern __shared__ __align__(16) unsigned char wd_smem[];
+    extern __shared__ __align__(128) unsigned char wd_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    // slot (stage s, piece p) of this thread: ring + ((s * WD_SLOTS + p) * 32) * 16 — a warp's LDS.128 / 16-byte copies of one
-    // piece cover 512 contiguous bytes
-    double2* ring = reinterpret_cast<double2*>(wd_smem + (size_t)warp * (WD_ST * WD_SLOTS * 32 * 16)) + lane;
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const int sub = lane >> 3, cc = lane & 7;            // producer role: line 4i + sub of an instruction, chunk cc
+    unsigned char* wring = wd_smem + (size_t)warp * (WD_ST * WD_STAGE_BYTES);
+    const unsigned wring_s = (unsigned)__cvta_generic_to_shared(wring);
+    // producer: byte offset of (line 4i + sub, chunk cc) in a stage = i * 512 + p_off (4i is even: the line's parity is sub's)
+    const unsigned p_off = (unsigned)sub * 128u + (unsigned)((cc ^ (4 * (sub & 1))) * 16);
+    // consumer: byte offset of (line 8mt + g, chunk 4jj + t) = mt * 1024 + c_off[jj]
+    const unsigned c_off0 = (unsigned)g * 128u + (unsigned)((t ^ (4 * (g & 1))) * 16);
+    const unsigned c_off1 = (unsigned)g * 128u + (unsigned)(((4 + t) ^ (4 * (g & 1))) * 16);
     const int64_t nunits = *nunits_p;
     const int64_t W = (int64_t)gridDim.x * WD_WARPS;
-    const int jfull = d >> 3;                  // full groups of 8 columns
-    const bool tail = (d & 7) != 0;            // d even: the last group holds 2, 4 or 6 columns
-    const bool tail_mine = 8 * jfull + 2 * t < d;
-    const int jtot = jfull + (tail ? 1 : 0);
+    const int nst = (d + 15) >> 4;                       // stages per row
     SurvivorSink sink;
     unsigned long long rows_staged = 0, nmine = 0;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -85,9 +91,10 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
         const int len = (int)__ldg(&r->len), m = (int)__ldg(&r->m);
         ++nmine;
         rows_staged += (unsigned)len;
-        // B operand: query 8nb + g of the unit (slots >= m repeat the last query: loaded, never kept)
-        const double* qp0 = Q + (int64_t)__ldg(&r->q[g]) * d + 2 * t;
-        const double* qp1 = Q + (int64_t)__ldg(&r->q[8 + g]) * d + 2 * t;
+        // producer: queries 4i + sub of the unit (slots >= m repeat the last query: copied, never kept)
+        const double* qsrc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qsrc[i] = Q + (int64_t)__ldg(&r->q[4 * i + sub]) * d + 2 * cc;
         // results of this thread: queries 8nb + 2t + e
         int c_q[2][2];
         double c_tau[2][2];
@@ -103,10 +110,10 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
             constexpr bool TWO = decltype(two_blocks)::value;
             for (int row0 = 0; row0 < len; row0 += WD_SLAB) {
                 const int myid = __ldg(ids_sorted + bstart + min(row0 + lane, len - 1));   // rows >= len repeat the last one
-                const double* xp[WD_MT];
+                const int nrows = min(WD_SLAB, len - row0);
+                const double* xsrc[8];                   // producer: rows 4i + sub of the slab
 #pragma unroll
-                for (int mt = 0; mt < WD_MT; ++mt)
-                    xp[mt] = X + (int64_t)__shfl_sync(0xffffffffu, myid, 8 * mt + g) * d + 2 * t;
+                for (int i = 0; i < 8; ++i) xsrc[i] = X + (int64_t)__shfl_sync(0xffffffffu, myid, 4 * i + sub) * d + 2 * cc;
                 double acc[WD_MT][2][2];
                 double xn[WD_MT], qq[2] = {0.0, 0.0};
 #pragma unroll
@@ -115,54 +122,63 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
 #pragma unroll
                     for (int nb = 0; nb < 2; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = 0.0;
                 }
-                // group j -> ring stage j % WD_ST (joins the cp.async group committed next)
-                auto request = [&](int j, int s) {
-                    if (j < jtot) {
-                        const unsigned dst = ring_s + (unsigned)(s * WD_SLOTS) * 512u;
-                        if (j < jfull || tail_mine) {
+                // stage k of the slab -> ring slot; joins the cp.async group committed next.  Chunks beyond column d (last
+                // stage of a d that is not a multiple of 16) are written as zeros.
+                auto request = [&](int k, int slot) {
+                    if (k < nst) {
+                        const unsigned dst = wring_s + (unsigned)slot * (unsigned)WD_STAGE_BYTES + p_off;
+                        const int col = 16 * k;          // this lane's chunk: columns col + 2cc, col + 2cc + 1
+                        if (col + 2 * cc < d) {
 #pragma unroll
-                            for (int mt = 0; mt < WD_MT; ++mt) cp16_cg(dst + mt * 512u, xp[mt] + 8 * j);
-                            cp16_ca(dst + WD_MT * 512u, qp0 + 8 * j);
-                            if (TWO) cp16_ca(dst + (WD_MT + 1) * 512u, qp1 + 8 * j);
-                        } else {                             // the partial last group: chunks beyond column d count as 0
-                            double2* z = ring + (s * WD_SLOTS) * 32;
+                            for (int i = 0; i < 8; ++i)      // (lines of rows past the bucket's end keep what they held: masked)
+                                if (4 * i + sub < nrows) cp16_cg(dst + i * 512u, xsrc[i] + col);
 #pragma unroll
-                            for (int p = 0; p < WD_SLOTS; ++p) z[p * 32] = make_double2(0.0, 0.0);
+                            for (int i = 0; i < (TWO ? 4 : 2); ++i) cp16_ca(dst + (8 + i) * 512u, qsrc[i] + col);
+                        } else {
+                            unsigned char* z = wring + (size_t)slot * WD_STAGE_BYTES + p_off;
+#pragma unroll
+                            for (int i = 0; i < 12; ++i) *reinterpret_cast<double2*>(z + i * 512) = make_double2(0.0, 0.0);
                         }
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                 };
 #pragma unroll
-                for (int s = 0; s < WD_ST - 1; ++s) request(s, s);
-                int cs = 0;                                  // stage of group j
-                for (int j = 0; j < jtot; ++j) {
-                    request(j + WD_ST - 1, cs == 0 ? WD_ST - 1 : cs - 1);
-                    asm volatile("cp.async.wait_group %0;" ::"n"(WD_ST - 1) : "memory");
-                    const double2* src = ring + (cs * WD_SLOTS) * 32;
+                for (int k = 0; k < WD_ST - 1; ++k) request(k, k);
+                int cs = 0;                              // ring slot of stage k
+                for (int k = 0; k < nst; ++k) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(WD_ST - 2) : "memory");   // stage k has landed (this lane's part)
+                    __syncwarp();                        // ... and every lane's; all lanes are done with stage k - 1
+                    request(k + WD_ST - 1, cs == 0 ? WD_ST - 1 : cs - 1);
+                    const unsigned char* src = wring + (size_t)cs * WD_STAGE_BYTES;
                     cs = cs + 1 == WD_ST ? 0 : cs + 1;
-                    double2 a[WD_MT], b[2];
 #pragma unroll
-                    for (int mt = 0; mt < WD_MT; ++mt) a[mt] = src[mt * 32];
-                    b[0] = src[WD_MT * 32];
-                    if (TWO) b[1] = src[(WD_MT + 1) * 32];
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const unsigned co = jj ? c_off1 : c_off0;
+                        double2 a[WD_MT], b[2];
 #pragma unroll
-                    for (int mt = 0; mt < WD_MT; ++mt) {
-                        dmma884(acc[mt][0][0], acc[mt][0][1], a[mt].x, b[0].x);
-                        if (TWO) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt].x, b[1].x);
-                    }
+                        for (int mt = 0; mt < WD_MT; ++mt) a[mt] = *reinterpret_cast<const double2*>(src + mt * 1024 + co);
+                        b[0] = *reinterpret_cast<const double2*>(src + 4 * 1024 + co);
+                        if (TWO) b[1] = *reinterpret_cast<const double2*>(src + 5 * 1024 + co);
 #pragma unroll
-                    for (int mt = 0; mt < WD_MT; ++mt) {
-                        dmma884(acc[mt][0][0], acc[mt][0][1], a[mt].y, b[0].y);
-                        if (TWO) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt].y, b[1].y);
-                    }
-                    if (ANGULAR) {
+                        for (int mt = 0; mt < WD_MT; ++mt) {
+                            dmma884(acc[mt][0][0], acc[mt][0][1], a[mt].x, b[0].x);
+                            if (TWO) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt].x, b[1].x);
+                        }
 #pragma unroll
-                        for (int mt = 0; mt < WD_MT; ++mt) xn[mt] = fma(a[mt].y, a[mt].y, fma(a[mt].x, a[mt].x, xn[mt]));
-                        qq[0] = fma(b[0].y, b[0].y, fma(b[0].x, b[0].x, qq[0]));
-                        if (TWO) qq[1] = fma(b[1].y, b[1].y, fma(b[1].x, b[1].x, qq[1]));
+                        for (int mt = 0; mt < WD_MT; ++mt) {
+                            dmma884(acc[mt][0][0], acc[mt][0][1], a[mt].y, b[0].y);
+                            if (TWO) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt].y, b[1].y);
+                        }
+                        if (ANGULAR) {
+#pragma unroll
+                            for (int mt = 0; mt < WD_MT; ++mt) xn[mt] = fma(a[mt].y, a[mt].y, fma(a[mt].x, a[mt].x, xn[mt]));
+                            qq[0] = fma(b[0].y, b[0].y, fma(b[0].x, b[0].x, qq[0]));
+                            if (TWO) qq[1] = fma(b[1].y, b[1].y, fma(b[1].x, b[1].x, qq[1]));
+                        }
                     }
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");     // (only empty groups are left)
+                __syncwarp();                            // the last stage is free before the next slab's first requests
                 double xnr[WD_MT], c_qn[2][2] = {{1.0, 1.0}, {1.0, 1.0}};
                 if (ANGULAR) {
 #pragma unroll
@@ -173,7 +189,7 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
                     }
 #pragma unroll
                     for (int nb = 0; nb < 2; ++nb) {
-                        double s = qq[nb];                   // |query 8nb + g|^2: the 4 threads of the group
+                        double s = qq[nb];               // |query 8nb + g|^2: the 4 threads of the group
                         s += __shfl_xor_sync(0xffffffffu, s, 1);
                         s += __shfl_xor_sync(0xffffffffu, s, 2);
                         const double nrm = sqrt(s);
@@ -372,7 +388,7 @@ void launch_score_wide(dpf_index* h, const ChunkView& cv, const void* units, con
                        unsigned long long* bm_stat) {
     auto go = [&](auto kern) {
         DPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WD_SMEM));
-        kern<<<h->num_sms * 2, WD_WARPS * 32, WD_SMEM, h->stream>>>(h->Xdev, h->cfg.d, cv.Q, reinterpret_cast<const UnitRec*>(units), nunits_p,
+        kern<<<h->num_sms, WD_WARPS * 32, WD_SMEM, h->stream>>>(h->Xdev, h->cfg.d, cv.Q, reinterpret_cast<const UnitRec*>(units), nunits_p,
                                                               h->ids_sorted.p, flt, bm_stat);
         DPF_LAUNCHED();
     };
