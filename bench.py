@@ -485,13 +485,17 @@ def run_ours(args):
     roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algorithmic, "kernel_ms": rr_ms, "step_share": rr_ms / ms_per_step if rr_ms else None,
-                "note": "achieved = algorithmic (compulsory) bytes / CUDA-event time of the scoring kernel: the kernel is not HBM-bound — "
-                        "it is bound by the L2 row gather and by instruction issue (every bucket row is staged once per unit of "
-                        "<= 16 queries that probe its bucket; the 128 MB byte store is mostly L2-resident), which is what "
-                        "requested_gbs / dram_gbs / l2_hit / tensor_pct describe",
+                "note": "achieved = algorithmic (compulsory) bytes / CUDA-event time of the scoring kernel: the kernel is not bound by "
+                        "compulsory HBM bytes — every bucket row is staged once per unit of <= 16 queries that probe its bucket and the "
+                        "128 MB byte store is mostly L2-resident, so the binding resource is the gather path from L2 to the SMs: "
+                        "l2_to_sm_gbs (ncu l1tex__m_xbar2l1tex_read_bytes / CUDA-event time) sits at the rate of the measured device copy; "
+                        "17 % fewer instructions and whole-line copy requests left the time unchanged (DESIGN.md section 4)",
                 "requested_bytes_per_launch": requested, "requested_gbs": requested / (rr_ms * 1e-3) / 1e9 if rr_ms else None,
                 "dram_gbs": traffic / (rr_ms * 1e-3) / 1e9 if traffic and rr_ms else None,
                 "dram_frac": traffic / (rr_ms * 1e-3) / 1e9 / peak_gbs if traffic and rr_ms else None,
+                "l2_to_sm_gbs": ncu["l2_to_sm_bytes"] / (rr_ms * 1e-3) / 1e9 if ncu and ncu.get("l2_to_sm_bytes") and rr_ms else None,
+                "l2_to_sm_frac_of_copy_peak": (ncu["l2_to_sm_bytes"] / (rr_ms * 1e-3) / 1e9 / peak_gbs
+                                               if ncu and ncu.get("l2_to_sm_bytes") and rr_ms else None),
                 "ncu": ncu,
                 "store_kind": store_kind, "store_row_bytes": row_bytes, "rows_staged_per_launch": rows_staged,
                 "units_per_launch": units, "survivors_per_query": survivors / nq, "queries_answered_exhaustively": int(qstats["bm_direct"]),

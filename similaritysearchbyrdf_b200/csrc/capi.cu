@@ -491,6 +491,8 @@ static void assign_balanced_partition(dpf_index* h, int64_t n_new) {
     h->own_fixed = true;
 }
 
+constexpr int kFitCopyChunks = 8;
+
 static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_device, bool sharded_hash = false) {
     require_ready(h, false);
     DPF_REQUIRE(n > 0 && X, DPF_ERR_INVALID, "empty fit");
@@ -501,6 +503,7 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     const int d = h->cfg.d;
     h->dense = true;
     const double* Xnew;
+    int copy_chunks = 1;
     if (on_device) {
         DPF_REQUIRE(h->n == 0, DPF_ERR_STATE, "dpf_fit_dense_dev borrows the buffer and cannot append");
         h->Xdev = X;
@@ -510,10 +513,15 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
         DPF_REQUIRE(!h->X_borrowed, DPF_ERR_STATE, "cannot append to a borrowed device buffer");
         h->X.grow_keep((size_t)(h->n + n) * d, (size_t)h->n * d, h->stream);
         tr.mark("store: allocate");
-        h2d(h, h->X.p + (size_t)h->n * d, X, (size_t)n * d);
-        tr.mark("store: host -> device");
         h->Xdev = h->X.p;
         Xnew = h->X.p + (size_t)h->n * d;
+        // A large fit is copied in pieces on the second stream while the main stream hashes the pieces that have landed:
+        // the copy (1 GB at configs[1]: 18.5 of the 24 ms of a fit through the host API) hides the hashing
+        copy_chunks = (!sharded_hash && (size_t)n * d * sizeof(double) >= (64u << 20) && h->dbg[DPF_DBG_TRACE] == 0) ? kFitCopyChunks : 1;
+        if (copy_chunks == 1) {
+            h2d(h, h->X.p + (size_t)h->n * d, X, (size_t)n * d);
+            tr.mark("store: host -> device");
+        }
     }
     if (h->store_mode != DPF_STORE_F64_ONLY && h->Xc_kind != DPF_STORE_KIND_F32) {
         // room for a byte copy of the rows, taken before the build's scratch buffers carve up the pool's free blocks
@@ -528,7 +536,37 @@ static void fit_dense_common(dpf_index* h, const double* X, int64_t n, bool on_d
     grow_keys(h, n);
     tr.mark("keys: allocate");
     if (sharded_hash) hash_dense_sharded(h, Xnew, n, h->n);      // this rank's slice + one all-gather of the keys
-    else hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
+    else if (copy_chunks > 1) {
+        cudaEvent_t ev[kFitCopyChunks] = {};
+        try {
+            DPF_CUDA(cudaEventRecord(h->ev_fork, h->stream));                 // the (re)allocated store is ready
+            DPF_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+            const int64_t piece = ((n + copy_chunks - 1) / copy_chunks + 63) / 64 * 64;
+            // copies run one piece ahead of the hashing (whose fix-up step waits for the device once per piece)
+            auto copy_piece = [&](int c) {
+                const int64_t r0 = (int64_t)c * piece;
+                if (r0 >= n) return;
+                const int64_t m = std::min(piece, n - r0);
+                DPF_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+                DPF_CUDA(cudaMemcpyAsync(const_cast<double*>(Xnew) + r0 * d, X + r0 * d, (size_t)m * d * sizeof(double), cudaMemcpyHostToDevice,
+                                         h->aux_stream));
+                DPF_CUDA(cudaEventRecord(ev[c], h->aux_stream));
+            };
+            copy_piece(0);
+            copy_piece(1);
+            for (int c = 0; (int64_t)c * piece < n; ++c) {
+                const int64_t r0 = (int64_t)c * piece, m = std::min(piece, n - r0);
+                DPF_CUDA(cudaStreamWaitEvent(h->stream, ev[c], 0));
+                hash_dense_any(h, Xnew + r0 * d, m, h->keys.p + h->n + r0, h->pids.p + h->n + r0, h->key_ld);
+                copy_piece(c + 2);
+            }
+        } catch (...) {
+            cudaStreamSynchronize(h->aux_stream);
+            for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+            throw;
+        }
+        for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+    } else hash_dense_any(h, Xnew, n, h->keys.p + h->n, h->pids.p + h->n, h->key_ld);
     tr.mark("hash");
     if (h->n == 0) assign_balanced_partition(h, n);
     // the new vectors count only once the forest and the store have been rebuilt: a failure in between (out of memory,

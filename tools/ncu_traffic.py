@@ -12,7 +12,10 @@ KEYS = {"gpu__time_duration.sum": "time", "dram__bytes_read.sum": "dram_read", "
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
         "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_pct",
         "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
-        "launch__registers_per_thread": "registers", "smsp__inst_executed.sum": "warp_instructions"}
+        "launch__registers_per_thread": "registers", "smsp__inst_executed.sum": "warp_instructions",
+        "l1tex__m_xbar2l1tex_read_bytes.sum": "l2_to_sm_bytes",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio": "stall_mio_throttle",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard"}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
 
 
@@ -23,7 +26,7 @@ def main(rep, workload_key, command, out="profiles/r2_ncu_kernels.json"):
     ki = hdr.index("Kernel Name")
     kernels = {}
     for r in data:
-        name = r[ki].split("(")[0].replace("void ", "").replace("dpf::", "").split("<")[0]
+        name = r[ki].split("(")[0].replace("void ", "").replace("dpf::", "").split("<")[0].strip()
         rec = {}
         for k, short in KEYS.items():
             if k in hdr:
