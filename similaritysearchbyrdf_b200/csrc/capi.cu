@@ -813,7 +813,7 @@ static void topk_device(dpf_index* h, const double* Qd, int64_t nq, const int32_
     if (aligned && bucket_major_supported(h, metric, topk)) {
         // bucket-major: chunks of queries whose worst-case pair count fits the scratch; nothing is read back
         int cap = 1;
-        const int64_t chunk = std::min(bm_chunk_queries(h, steps, probe_mode, &cap), std::max<int64_t>(1, kMaxPool / bm_pool_per_query(topk, steps)));
+        const int64_t chunk = std::min(bm_chunk_queries(h, steps, probe_mode, &cap), std::max<int64_t>(1, kMaxPool / bm_pool_per_query(h, topk, steps)));
         for (int64_t q0 = 0; q0 < nq; q0 += chunk)
             topk_bucket_major(h, Qd, qk, steps, probe_mode, q0, std::min(nq, q0 + chunk), cap, topk, metric, ids_out_dev, score_out_dev);
         return;

@@ -371,8 +371,8 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                        int cap, int topk, int metric, int32_t* ids_out, double* score_out);
 void tc_diag_read(unsigned long long* out8);   // rerank_tc.cu
 int64_t bm_chunk_queries(const dpf_index* h, int steps, int probe_mode, int* cap_out);   // bm_group.cu
-constexpr int64_t kMaxPool = 1LL << 28;                  // survivor records of a chunk (28 bytes each with their lists)
-int64_t bm_pool_per_query(int topk, int steps);          // rerank_bm.cu
+constexpr int64_t kMaxPool = 1LL << 29;                  // survivor records of a chunk (28 bytes each with their lists)
+int64_t bm_pool_per_query(const dpf_index* h, int topk, int steps);   // rerank_bm.cu
 void gather_query_keys(dpf_index* h, const int32_t* qids_dev, int64_t nq);
 void counts_from_offsets(dpf_index* h, const int64_t* off, int64_t nq, int32_t* cnt);
 void merge_topk(dpf_index* h, const int32_t* gids, const double* gsc, int G, int64_t nq, int topk, int metric,

@@ -45,12 +45,31 @@ bool bucket_major_supported(const dpf_index* h, int metric, int topk) {
     return metric == DPF_METRIC_L2 && score_u8_usable(h) && h->Q8_valid;
 }
 
+// Threshold samples per query (one warp each = the query's own bucket in one table).  Byte rows: 6 on one GPU; a rank of G
+// sees 1/G of every query's buckets, so its lists stay short with fewer samples — measured per rank at configs[1]
+// (tools/nt_sweep.py --world G), 3 tables is the best or within 1% of it at G = 2, 4 and 8 (one table leaves 860 survivors per
+// query on the fullest rank of 8 and costs 0.2 ms more than it saves).  FP64 / float rows cost 8 / 4 times the bytes of byte
+// rows per sampled row: two samples there (measured on configs[1] with the byte copy off: 4.1 ms of sampling with six tables
+// against 11.4 ms of scoring).  Wide rows with k > 32: the k-th best of two buckets' rows is hardly a bar: four.  Multi-step
+// search on wide rows visits 3-4 times the entries: twice the samples keep the survivor lists in proportion.
+static int bm_threshold_tables(const dpf_index* h, int topk, int steps) {
+    const bool wide = h->cfg.d > BM_KC;
+    const bool use_u8 = !wide && score_u8_usable(h);
+    const int world = h->cfg.world > 1 ? h->cfg.world : 1;
+    const int nt_default = (!use_u8 ? (wide && topk > 32 ? 4 : 2) : (world <= 1 ? 6 : 3)) * (wide && steps > 0 ? 2 : 1);
+    return std::min(32, std::max(1, h->dbg[DPF_DBG_TAU_TABLES] > 0 ? (int)h->dbg[DPF_DBG_TAU_TABLES] : nt_default));
+}
+
 // Survivor records the pool holds per query of a chunk.  The survivors of a query are roughly k x (entries it visits) /
-// (rows sampled for its threshold): they grow with k (the k-th best of a few hundred sampled rows is a weaker bar for
-// k = 100 than for 10) and with multi-step search (3-4 times the entries; measured on the GIST shape, k = 100: 3.4k
-// survivors per query at steps = 0, more than 9.6k at steps >= 1 — a pool that overflows sends every query to the exhaustive
-// kernel).  topk_device cuts the batch so that a chunk's share fits kMaxPool.
-int64_t bm_pool_per_query(int topk, int steps) { return (int64_t)std::max(2048, 96 * topk) * (steps > 0 ? 4 : 1); }
+// (rows sampled for its threshold): ~60k entries at steps = 0 (3-4 times that with multi-step search), ~200 rows per sampled
+// bucket — the pool takes four times that estimate, never less than 2048 (configs[1], 6 samples: 330 survivors per query
+// measured; GIST shape, k = 100, 4 samples: 3.4k at steps = 0, 6-9k with 8 samples at steps >= 1; Deep shape, FP64 rows,
+// 2 samples: the former fixed 2048 overflowed and sent 9967 of 10000 queries to the exhaustive kernel).  topk_device cuts
+// the batch so that a chunk's share fits kMaxPool.
+int64_t bm_pool_per_query(const dpf_index* h, int topk, int steps) {
+    const int64_t est = 1200LL * topk * (steps > 0 ? 4 : 1) / bm_threshold_tables(h, topk, steps);
+    return std::min<int64_t>(std::max<int64_t>(2048, est), 1 << 20);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk copy (sm_90+ PTX; on sm_100a: SYNCS.* and UBLKCP.S.G)
@@ -865,7 +884,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     if (use_tc) h->bm_descs.reserve((size_t)tc_cap * sizeof(TcRec));
     h->bm_taui.reserve((size_t)nqc + 2);
     int64_t pool_cap = h->dbg[DPF_DBG_POOL_RECORDS] > 0 ? h->dbg[DPF_DBG_POOL_RECORDS]
-                                                        : std::min<int64_t>(std::max<int64_t>(nqc * bm_pool_per_query(topk, steps), 1 << 20), kMaxPool);
+                                                        : std::min<int64_t>(std::max<int64_t>(nqc * bm_pool_per_query(h, topk, steps), 1 << 20), kMaxPool);
     pool_cap = std::max<int64_t>(SURV_BLOCK, pool_cap / SURV_BLOCK * SURV_BLOCK);
     h->surv_pool.reserve((size_t)pool_cap * sizeof(SurvRec));
     h->scores.reserve((size_t)pool_cap);
@@ -904,18 +923,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
     // ---- thresholds: a row gather, on the handle's second stream (forked right after the probe) beside the grouping chain
     //      (scan, pair fill, unit records) on the main one ------------------------------------------------------------
     {
-        // sampled tables per query (one warp each): 6 on one GPU; a rank of G sees 1/G of every query's buckets, so its
-        // lists stay short with fewer samples
-        const int world = h->cfg.world > 1 ? h->cfg.world : 1;
-        // (FP64 / float rows cost 8 / 4 times the bytes of byte rows per sampled row: two samples there — measured on
-        // configs[1] with the byte copy off: 4.1 ms of sampling with six tables against 11.4 ms of scoring)
-        // On G GPUs a rank holds 1/G of a query's entries and fewer samples pay: measured per rank at configs[1]
-        // (tools/nt_sweep.py --world G), 3 tables is the best or within 1% of it at G = 2, 4 and 8 (one table leaves
-        // 860 survivors per query on the fullest rank of 8 and costs 0.2 ms more than it saves).
-        // (wide rows, k > 32: the k-th best of two buckets' rows is hardly a bar: four samples)
-        // (multi-step search visits 3-4 times the entries: twice the samples keep the survivor lists in proportion)
-        const int nt_default = (!use_u8 ? (wide && topk > 32 ? 4 : 2) : (world <= 1 ? 6 : 3)) * (wide && steps > 0 ? 2 : 1);
-        const int NT = std::min(32, std::max(1, h->dbg[DPF_DBG_TAU_TABLES] > 0 ? (int)h->dbg[DPF_DBG_TAU_TABLES] : nt_default));
+        const int NT = bm_threshold_tables(h, topk, steps);
         h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
         h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
         h->bm_tl_cnt.reserve((size_t)nqc * NT);

@@ -181,7 +181,8 @@ def run_deep(a):
         torch.cuda.synchronize(); ms = 1e3 * (time.time() - t0)
     st, s2 = ix.stage_times_ms(), ix.stats()
     rec["query"] = {"ms": round(ms, 2), "queries_per_s": nq / (ms * 1e-3), "stage_ms": r3(st),
-                    "with_dups_per_query": s2["last_cand_with_dups"] / nq, "bm_pairs": s2["bm_pairs"], "bm_rows_staged": s2["bm_rows_staged"]}
+                    "with_dups_per_query": s2["last_cand_with_dups"] / nq, "bm_pairs": s2["bm_pairs"], "bm_rows_staged": s2["bm_rows_staged"],
+                    "survivors_per_query": s2["bm_survivors"] / nq, "answered_exhaustively": s2["bm_direct"]}
     sub = min(nq, 200)
     rec["recall_at_10_first_200"] = recall_at(Xd, Qd[:sub], ids_d[:sub].cpu().numpy(), K, chunk=8)
     emit(rec)

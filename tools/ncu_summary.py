@@ -32,7 +32,7 @@ def main(path, out=None):
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
-    lines = ["metric,unit," + ",".join(f"{r[ki].split('(')[0]}#{r[0]}" for r in data)]
+    lines = ["metric,unit," + ",".join(f"{r[ki].split('(')[0].replace(', ', ' ').replace(',', ' ')}#{r[0]}" for r in data)]
     for k in KEYS:
         if k in hdr:
             i = hdr.index(k)
