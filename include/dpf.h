@@ -276,6 +276,7 @@ enum {
     DPF_DBG_APPEND = 11,      /* appending fit: 0 put small batches incrementally, rebuild for large ones (default);
                                  1 always rebuild; 2 always put incrementally (rebuild only when out of head-room)     */
     DPF_DBG_WIDE = 12,        /* d > 128: 0 bucket-major k_score_wide for dot / angular (default), 1 the row-major kernel */
+    DPF_DBG_TAU_FORK = 13,    /* where the threshold stream forks: 0 / 1 right after the probe (default), 2 after the pair fill            */
     DPF_DBG_COUNT = 16
 };
 int dpf_set_debug_option(dpf_handle h, int32_t option, int64_t value);

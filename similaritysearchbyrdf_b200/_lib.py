@@ -17,7 +17,7 @@ STORE_AUTO, STORE_F64_ONLY, STORE_NARROWEST = 0, 1, 2
 STAT_COUNT, T_COUNT = 16, 16
 # dpf_set_debug_option keys (include/dpf.h): test / profiling hooks, defaults are the product path
 (DBG_RERANK, DBG_BM_KERNEL, DBG_U8_IMMA, DBG_U8I_KERNEL, DBG_TAU_TABLES, DBG_TAU_KERNEL, DBG_HASH_EXACT, DBG_CAND_BUDGET,
- DBG_TRACE, DBG_STORE, DBG_POOL_RECORDS, DBG_APPEND, DBG_WIDE) = range(13)
+ DBG_TRACE, DBG_STORE, DBG_POOL_RECORDS, DBG_APPEND, DBG_WIDE, DBG_TAU_FORK) = range(14)
 DBG_DEFAULTS = {DBG_U8_IMMA: 1}
 STAT_NAMES = ["size", "near_zero_fixups", "singleton_splits", "splits", "dir_nodes", "nlz_gt28", "last_candidates",
               "last_cand_with_dups", "kernel_launches", "bm_pairs", "bm_runs",

@@ -919,15 +919,20 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
                      ctr + CTR_POOL_OVERFLOW};
     const size_t list_smem = (size_t)RR_WARPS * topk * (sizeof(double) + sizeof(int));
     const unsigned qgrid = (unsigned)((nqc + RR_WARPS - 1) / RR_WARPS);
+    // where the threshold stream forks: right after the probe (thresholds beside scan / fill / emit; default) or after the pair
+    // fill (beside the unit records only).  Measured with tools/rank_emul.py --fork: the same 2.19-2.23 ms on one GPU; on a
+    // shard of 4 / 8 GPUs the early fork gives 0.95-0.97 / 0.72-0.76 ms per local step against 0.99-1.04 / 0.77-0.78.
+    const bool fork_early = h->dbg[DPF_DBG_TAU_FORK] != 2;
 
-    // ---- thresholds: a row gather, on the handle's second stream (forked right after the probe) beside the grouping chain
-    //      (scan, pair fill, unit records) on the main one ------------------------------------------------------------
+    // ---- thresholds: a row gather, on the handle's second stream beside the grouping chain (scan, pair fill, unit records)
+    //      on the main one ------------------------------------------------------------------------------------------------
     {
         const int NT = bm_threshold_tables(h, topk, steps);
         h->bm_tl_keys.reserve((size_t)nqc * NT * topk);
         h->bm_tl_ids.reserve((size_t)nqc * NT * topk);
         h->bm_tl_cnt.reserve((size_t)nqc * NT);
         cudaStream_t st2 = h->aux_stream;
+        if (!fork_early) group_pairs(h, nqc, cap, use_tc);
         DPF_CUDA(cudaEventRecord(h->ev_fork, st));
         DPF_CUDA(cudaStreamWaitEvent(st2, h->ev_fork, 0));
         StageTimer tmt(h, DPF_T_THRESHOLD, st2);
@@ -964,7 +969,7 @@ void topk_bucket_major(dpf_index* h, const double* Qd, const QueryKeys& qk, int 
         DPF_CUDA(cudaGetLastError());
     }
     DPF_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
-    group_pairs(h, nqc, cap, use_tc);        // the main stream meanwhile: pairs grouped by leaf, unit records
+    if (fork_early) group_pairs(h, nqc, cap, use_tc);    // the main stream meanwhile: pairs grouped by leaf, unit records
     if (use_tc) emit_tc_recs(h, tc_cap, dirty);
     emit_units(h, use_tc);               // with the tcgen05 kernel the records only serve a batch that is not byte vectors
 

@@ -654,7 +654,7 @@ k_score_u8s(const unsigned char* __restrict__ X8, unsigned pitch, const unsigned
 // scoring kernel will produce; cosines are computed with the same operations.
 // ---------------------------------------------------------------------------------------------------------
 template <int METRIC, bool REG /* K <= 32: the sample list lives in registers */>
-__global__ void __launch_bounds__(RR_THREADS)
+__global__ void __launch_bounds__(RR_THREADS, 4)   // 64 registers: measured 2.15 ms per configs[1] step against 2.22 (3 CTAs, 80 registers) and 2.24 (5 CTAs, spills)
 k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView cv, int L, int NT,
                 const uint32_t* __restrict__ leaf_pos, const int32_t* __restrict__ leaf_len,
                 const int32_t* __restrict__ ids_sorted, int self_exclude, int K,
@@ -707,6 +707,8 @@ k_threshold_u8i(const unsigned char* __restrict__ X8, unsigned pitch, ChunkView 
         const int len = leaf_len[leaf];
         seen += len;
         const int32_t* bids = ids_sorted + bstart;
+        // (Tried: the rows of window w + 1 gathered while window w is multiplied — 148 registers, or 128 with spills: one or
+        // two CTAs per SM instead of three, and the kernel went from 0.57 to 0.97 ms inside a configs[1] step.)
         int idA = __ldg(bids + min(lane, len - 1));
         for (int row0 = 0; row0 < len; row0 += 32) {                 // one id window = 2 tiles of 16 rows
             int id_next = 0;

@@ -10,6 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--world", type=int, default=8)
 ap.add_argument("--nq", type=int, default=10000)
 ap.add_argument("--ranks", type=str, default="")
+ap.add_argument("--fork", type=int, default=0, help="DPF_DBG_TAU_FORK: 2 = fork the threshold stream after the pair fill")
 a = ap.parse_args()
 X, Q = synth.config2(1_000_000, a.nq, 128)
 A, chain = synth.angle_family(128, 128, 10, 3, 32, 88387 + 2)
@@ -24,6 +25,8 @@ for r in ranks:
     ix = DPFIndex(d=128, L=30, k=32, pb=3, rank=r, world=a.world)
     ix.set_balanced_partition(True)
     ix.set_family(A, chain); ix.set_partitioners(Ap)
+    if a.fork:
+        ix.set_debug_option(13, a.fork)
     stm = torch.cuda.Stream()
     ix.set_stream(stm.cuda_stream)
     torch.cuda.synchronize()
