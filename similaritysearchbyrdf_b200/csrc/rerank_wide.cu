@@ -28,7 +28,7 @@
 
 namespace dpf {
 
-constexpr int WD_WARPS = 8;
+constexpr int WD_WARPS = 6;
 constexpr int WD_MT = 4;                   // m-tiles (8 rows) per slab
 constexpr int WD_SLAB = 8 * WD_MT;
 
@@ -40,17 +40,20 @@ __device__ __forceinline__ double2 ldg_d2_stream(const double* p) {
     return v;
 }
 
-// Ring geometry.  A stage = 16 columns = ONE 128-byte line of each of the slab's 32 rows and of the unit's 16 queries
-// (48 lines, 6 KB).  Two earlier forms of this kernel had every thread fetch exactly the 16-byte fragment pieces it
-// multiplies (straight into registers one column group ahead; then through a per-thread cp.async ring three groups
-// ahead): both sat at 1.9 TB/s of rows whatever the depth, with ncu showing every unit idle and the warps throttled on the
-// memory-instruction queue — a warp instruction of that pattern asks for half of eight lines, and the SM tracks a bounded
-// number of pending lines (~512: 32 KB in flight at 64 bytes per line).  Here a quarter warp copies a whole line, four
-// lines per instruction, and the fragment owners read them back from shared memory.
-constexpr int WD_ST = 4;                   // stages per warp: two or three in flight while one is multiplied
-constexpr int WD_LINES = WD_SLAB + 16;     // lines per stage
-constexpr size_t WD_STAGE_BYTES = (size_t)WD_LINES * 128;
-constexpr size_t WD_SMEM = (size_t)WD_WARPS * WD_ST * WD_STAGE_BYTES;      // 192 KB: one CTA per SM
+// Ring geometry.  A stage = 32 columns = 256 contiguous bytes (two 128-byte lines) of each of the slab's 32 rows and of the
+// unit's 16 queries (12 KB).  Earlier forms of this kernel, all measured on 1M x 960, 10k queries: every thread fetching the
+// 16-byte fragment pieces it multiplies, straight into registers one column group ahead (184 ms) or through a per-thread
+// cp.async ring three groups ahead (176 ms) — ncu: every unit idle, the warps throttled on the memory-instruction queue: a
+// warp instruction of that pattern asks for half of eight lines and the SM tracks a bounded number of pending lines; an L2
+// bulk prefetch of 512-byte row blocks ahead of that ring (198 ms); a quarter warp copying one whole line, four lines per
+// instruction, 16 columns per stage (91 ms; 12 warps instead of 8 changed nothing).  Here half a warp copies 256 contiguous
+// bytes of a row, and the fragment owners read them back from shared memory.
+constexpr int WD_ST = 3;                   // stages per warp: one or two in flight while one is multiplied
+constexpr int WD_SCOLS = 32;               // columns per stage
+constexpr int WD_RB = WD_SCOLS * 8;        // bytes of a row per stage
+constexpr int WD_LINES = WD_SLAB + 16;     // rows + queries per stage
+constexpr size_t WD_STAGE_BYTES = (size_t)WD_LINES * WD_RB;
+constexpr size_t WD_SMEM = (size_t)WD_WARPS * WD_ST * WD_STAGE_BYTES;      // 216 KB: one CTA per SM
 
 __device__ __forceinline__ void cp16_cg(unsigned dst, const void* src) {      // rows: L2 only
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -59,10 +62,10 @@ __device__ __forceinline__ void cp16_ca(unsigned dst, const void* src) {      //
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// Shared-memory layout of a stage: line l (rows 0..31, then queries 0..15) at l * 128; its 16-byte chunk c at position
-// c ^ 4(l & 1).  Producer: a quarter warp writes the 8 chunks of one line = 128 contiguous bytes.  Consumer: thread (g, t)
-// reads chunk 4jj + t of line 8mt + g; a quarter warp covers two neighbouring lines whose halves the swizzle puts on
-// disjoint banks: LDS.128 without conflicts, no padding.
+// Shared-memory layout of a stage: entry e (rows 0..31, then queries 0..15) at e * 256; its 16-byte chunk c (0..15) at
+// position c ^ 4(e & 1).  Producer: half a warp writes the 16 chunks of one entry = 256 contiguous bytes.  Consumer: thread
+// (g, t) reads chunk 4jj + t of entry 8mt + g; a quarter warp covers two neighbouring entries whose 64-byte pieces the
+// swizzle puts on disjoint banks: LDS.128 without conflicts, no padding.
 template <bool ANGULAR>
 __global__ void __launch_bounds__(WD_WARPS * 32, 1)
 k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, const UnitRec* __restrict__ units,
@@ -71,17 +74,17 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
     extern __shared__ __align__(128) unsigned char wd_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int sub = lane >> 3, cc = lane & 7;            // producer role: line 4i + sub of an instruction, chunk cc
+    const int sub = lane >> 4, cc = lane & 15;           // producer role: entry 2i + sub of an instruction, chunk cc
     unsigned char* wring = wd_smem + (size_t)warp * (WD_ST * WD_STAGE_BYTES);
     const unsigned wring_s = (unsigned)__cvta_generic_to_shared(wring);
-    // producer: byte offset of (line 4i + sub, chunk cc) in a stage = i * 512 + p_off (4i is even: the line's parity is sub's)
-    const unsigned p_off = (unsigned)sub * 128u + (unsigned)((cc ^ (4 * (sub & 1))) * 16);
-    // consumer: byte offset of (line 8mt + g, chunk 4jj + t) = mt * 1024 + c_off[jj]
-    const unsigned c_off0 = (unsigned)g * 128u + (unsigned)((t ^ (4 * (g & 1))) * 16);
-    const unsigned c_off1 = (unsigned)g * 128u + (unsigned)(((4 + t) ^ (4 * (g & 1))) * 16);
+    // producer: byte offset of (entry 2i + sub, chunk cc) in a stage = i * 512 + p_off (2i is even: the entry's parity is sub)
+    const unsigned p_off = (unsigned)sub * WD_RB + (unsigned)((cc ^ (4 * sub)) * 16);
+    // consumer: byte offset of (entry 8mt + g, chunk 4jj + t) = mt * 2048 + c_off(jj)
+    const unsigned c_base = (unsigned)g * WD_RB;
+    const unsigned c_sw = 4u * (g & 1);
     const int64_t nunits = *nunits_p;
     const int64_t W = (int64_t)gridDim.x * WD_WARPS;
-    const int nst = (d + 15) >> 4;                       // stages per row
+    const int nst = (d + WD_SCOLS - 1) / WD_SCOLS;       // stages per row
     SurvivorSink sink;
     unsigned long long rows_staged = 0, nmine = 0;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -91,10 +94,10 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
         const int len = (int)__ldg(&r->len), m = (int)__ldg(&r->m);
         ++nmine;
         rows_staged += (unsigned)len;
-        // producer: queries 4i + sub of the unit (slots >= m repeat the last query: copied, never kept)
-        const double* qsrc[4];
+        // producer: queries 2i + sub of the unit (slots >= m repeat the last query: copied, never kept)
+        int qid[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) qsrc[i] = Q + (int64_t)__ldg(&r->q[4 * i + sub]) * d + 2 * cc;
+        for (int i = 0; i < 8; ++i) qid[i] = __ldg(&r->q[2 * i + sub]);
         // results of this thread: queries 8nb + 2t + e
         int c_q[2][2];
         double c_tau[2][2];
@@ -111,9 +114,9 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
             for (int row0 = 0; row0 < len; row0 += WD_SLAB) {
                 const int myid = __ldg(ids_sorted + bstart + min(row0 + lane, len - 1));   // rows >= len repeat the last one
                 const int nrows = min(WD_SLAB, len - row0);
-                const double* xsrc[8];                   // producer: rows 4i + sub of the slab
+                int xid[16];                             // producer: rows 2i + sub of the slab
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xsrc[i] = X + (int64_t)__shfl_sync(0xffffffffu, myid, 4 * i + sub) * d + 2 * cc;
+                for (int i = 0; i < 16; ++i) xid[i] = __shfl_sync(0xffffffffu, myid, 2 * i + sub);
                 double acc[WD_MT][2][2];
                 double xn[WD_MT], qq[2] = {0.0, 0.0};
 #pragma unroll
@@ -123,21 +126,21 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
                     for (int nb = 0; nb < 2; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = 0.0;
                 }
                 // stage k of the slab -> ring slot; joins the cp.async group committed next.  Chunks beyond column d (last
-                // stage of a d that is not a multiple of 16) are written as zeros.
+                // stage of a d that is not a multiple of 32) are written as zeros.
                 auto request = [&](int k, int slot) {
                     if (k < nst) {
                         const unsigned dst = wring_s + (unsigned)slot * (unsigned)WD_STAGE_BYTES + p_off;
-                        const int col = 16 * k;          // this lane's chunk: columns col + 2cc, col + 2cc + 1
-                        if (col + 2 * cc < d) {
+                        const int col = WD_SCOLS * k + 2 * cc;     // this lane's chunk: columns col, col + 1
+                        if (col < d) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)      // (lines of rows past the bucket's end keep what they held: masked)
-                                if (4 * i + sub < nrows) cp16_cg(dst + i * 512u, xsrc[i] + col);
+                            for (int i = 0; i < 16; ++i)     // (entries of rows past the bucket's end keep what they held: masked)
+                                if (2 * i + sub < nrows) cp16_cg(dst + i * 512u, X + (int64_t)xid[i] * d + col);
 #pragma unroll
-                            for (int i = 0; i < (TWO ? 4 : 2); ++i) cp16_ca(dst + (8 + i) * 512u, qsrc[i] + col);
+                            for (int i = 0; i < (TWO ? 8 : 4); ++i) cp16_ca(dst + (16 + i) * 512u, Q + (int64_t)qid[i] * d + col);
                         } else {
                             unsigned char* z = wring + (size_t)slot * WD_STAGE_BYTES + p_off;
 #pragma unroll
-                            for (int i = 0; i < 12; ++i) *reinterpret_cast<double2*>(z + i * 512) = make_double2(0.0, 0.0);
+                            for (int i = 0; i < 24; ++i) *reinterpret_cast<double2*>(z + i * 512) = make_double2(0.0, 0.0);
                         }
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -149,16 +152,16 @@ k_score_wide(const double* __restrict__ X, int d, const double* __restrict__ Q, 
                     asm volatile("cp.async.wait_group %0;" ::"n"(WD_ST - 2) : "memory");   // stage k has landed (this lane's part)
                     __syncwarp();                        // ... and every lane's; all lanes are done with stage k - 1
                     request(k + WD_ST - 1, cs == 0 ? WD_ST - 1 : cs - 1);
-                    const unsigned char* src = wring + (size_t)cs * WD_STAGE_BYTES;
+                    const unsigned char* src = wring + (size_t)cs * WD_STAGE_BYTES + c_base;
                     cs = cs + 1 == WD_ST ? 0 : cs + 1;
 #pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const unsigned co = jj ? c_off1 : c_off0;
+                    for (int jj = 0; jj < WD_SCOLS / 8; ++jj) {
+                        const unsigned co = (((unsigned)(4 * jj + t)) ^ c_sw) * 16u;
                         double2 a[WD_MT], b[2];
 #pragma unroll
-                        for (int mt = 0; mt < WD_MT; ++mt) a[mt] = *reinterpret_cast<const double2*>(src + mt * 1024 + co);
-                        b[0] = *reinterpret_cast<const double2*>(src + 4 * 1024 + co);
-                        if (TWO) b[1] = *reinterpret_cast<const double2*>(src + 5 * 1024 + co);
+                        for (int mt = 0; mt < WD_MT; ++mt) a[mt] = *reinterpret_cast<const double2*>(src + mt * (8 * WD_RB) + co);
+                        b[0] = *reinterpret_cast<const double2*>(src + 4 * (8 * WD_RB) + co);
+                        if (TWO) b[1] = *reinterpret_cast<const double2*>(src + 5 * (8 * WD_RB) + co);
 #pragma unroll
                         for (int mt = 0; mt < WD_MT; ++mt) {
                             dmma884(acc[mt][0][0], acc[mt][0][1], a[mt].x, b[0].x);
