@@ -10,11 +10,11 @@
 //
 //   k_score_wide       warp per unit; the bucket's rows in slabs of 32 (four DMMA m-tiles), the unit's <= 16 queries as two
 //                      n-blocks.  A slab of whole rows does not fit in shared memory next to sixteen 7.5 KB queries, so
-//                      rows and queries stream through a per-warp ring 16 columns (one 128-byte line of every row and
-//                      query) at a time, copied with cp.async a quarter warp per line, two to three stages ahead (rows:
-//                      HBM; queries: L2 / L1 — a slab of 32 rows re-reads the unit's queries once, +50 % / +25 % of L2
-//                      traffic on top of the rows for two / one n-blocks).  32 DMMA.8x8x4 per stage.  Only scores that
-//                      reach the query's threshold leave the kernel (SurvivorSink).
+//                      rows and queries stream through a per-warp ring 32 columns (256 contiguous bytes of every row and
+//                      query) at a time, copied with cp.async half a warp per row, one to two stages ahead (rows: HBM;
+//                      queries: L2 / L1 — a slab of 32 rows re-reads the unit's queries once, +50 % / +25 % of L2 traffic
+//                      on top of the rows for two / one n-blocks).  64 DMMA.8x8x4 per stage.  Only scores that reach the
+//                      query's threshold leave the kernel (SurvivorSink).
 //   k_threshold_wide   the threshold samples of k_threshold (rerank_bm.cu) for any d: warp per (query, sampled table), the
 //                      lanes stride over the 16-byte chunks of four rows at a time, plain FP64 FMAs, lower bound = score
 //                      minus twice the rounding bound of a length-d dot product in any order.
@@ -28,7 +28,7 @@
 
 namespace dpf {
 
-constexpr int WD_WARPS = 6;
+constexpr int WD_WARPS = 6;                // warps per CTA, one CTA per SM (3 ring stages of 12 KB per warp)
 constexpr int WD_MT = 4;                   // m-tiles (8 rows) per slab
 constexpr int WD_SLAB = 8 * WD_MT;
 
