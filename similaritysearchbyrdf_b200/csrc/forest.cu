@@ -123,7 +123,7 @@ k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ key
               const int64_t* __restrict__ table_base, int32_t* __restrict__ ids_sorted, int32_t* __restrict__ tmp,
               int32_t* __restrict__ child_ptr, int32_t* __restrict__ child_cnt, int32_t* __restrict__ counters,
               WorkItem* __restrict__ work_next, int node_cap, unsigned long long* __restrict__ stat_singleton,
-              int32_t* __restrict__ node_table) {
+              int32_t* __restrict__ node_table, uint8_t* __restrict__ slots /* per entry: its slot at this level */) {
     __shared__ int32_t cntW[SP_MAXW], c0W[SP_MAXW], offW[SP_MAXW], runW[SP_MAXW];
     __shared__ int32_t wcnt[SP_THREADS / 32][SP_MAXW];
     __shared__ int trigger_slot;
@@ -133,12 +133,14 @@ k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ key
     const int32_t* kt = keys + (int64_t)it.table * ld;
     int32_t* seg = ids_sorted + it.start;
     int32_t* out = tmp + it.start;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint8_t* sl8 = slots + it.start;                 // the counting pass leaves every entry's slot here: the scatter pass reads
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;   // it back in order instead of gathering the key a second time
 
     for (int i = tid; i < W; i += SP_THREADS) { cntW[i] = 0; c0W[i] = 0; }
     __syncthreads();
     for (int i = tid; i < it.cnt; i += SP_THREADS) {
         const int sl = slot_at(kt[seg[i]], level, nb, mask);
+        sl8[i] = (uint8_t)sl;
         atomicAdd(&cntW[sl], 1);
         if (i < s) atomicAdd(&c0W[sl], 1);
         if (i == s - 1) trigger_slot = sl;           // the id whose insertion overflowed the bucket
@@ -161,7 +163,7 @@ k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ key
         const bool ok = i < it.cnt;
         int32_t id = 0;
         uint32_t sl = 0xFFFFFFFFu;
-        if (ok) { id = seg[i]; sl = (uint32_t)slot_at(kt[id], level, nb, mask); }
+        if (ok) { id = seg[i]; sl = sl8[i]; }
         const uint32_t peers = __match_any_sync(0xffffffffu, sl);
         const int rank_in_warp = __popc(peers & lt);
         if (ok && rank_in_warp == 0) wcnt[w][sl] = __popc(peers);
@@ -349,6 +351,8 @@ void build_forest(dpf_index* h) {
     h->arena_used = E;
     DevBuf<int32_t> tmp;
     tmp.reserve((size_t)std::max<int64_t>(E, 1));
+    DevBuf<uint8_t> slot_buf;
+    slot_buf.reserve((size_t)std::max<int64_t>(E, 1));
 
     // ---- stable sort by (table, root, slot(MAXL)), one table group at a time -------------------------------
     {
@@ -415,7 +419,7 @@ void build_forest(dpf_index* h) {
             DPF_CUDA(cudaMemsetAsync(h->counters.p + 2, 0, sizeof(int32_t), st));
             k_split_level<<<nwork, SP_THREADS, 0, st>>>(cur, h->keys.p, ld, tp, level, h->table_base.p, h->ids_sorted.p,
                                                         tmp.p, h->child_ptr.p, h->child_cnt.p, h->counters.p, nxt,
-                                                        h->node_cap, stat_dev, h->node_table.p); DPF_LAUNCHED();
+                                                        h->node_cap, stat_dev, h->node_table.p, slot_buf.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             DPF_CUDA(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
             DPF_CUDA(cudaStreamSynchronize(st));

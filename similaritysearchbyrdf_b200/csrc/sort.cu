@@ -144,8 +144,9 @@ static size_t scan_scratch_elems(int64_t n) {
     return (size_t)(2 + 2 * ((n + SL_TILE - 1) / SL_TILE)) + 8;
 }
 
-// int32 counts -> int64 exclusive offsets (n+1 entries), single CTA chained over tiles; used for per-query
-// offsets (n = number of queries) where n is small
+// int32 counts -> int64 exclusive offsets (n+1 entries), single CTA chained over tiles of 8192 (8 consecutive entries per
+// thread: 15 rounds of barriers for the 122 880 depth-1 codes of a build instead of 120; per-query offsets where n is small)
+constexpr int SC64_ITEMS = 8;
 __global__ void __launch_bounds__(1024) k_scan_i32_to_i64(const int32_t* __restrict__ in, int64_t* __restrict__ out,
                                                           int64_t n) {
     __shared__ long long wsum[32];
@@ -153,10 +154,16 @@ __global__ void __launch_bounds__(1024) k_scan_i32_to_i64(const int32_t* __restr
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const long long v = i < n ? (long long)in[i] : 0;
-        long long inc = v;
+    for (int64_t base = 0; base < n; base += 1024 * SC64_ITEMS) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * SC64_ITEMS;
+        long long v[SC64_ITEMS];
+        long long tot = 0;
+#pragma unroll
+        for (int e = 0; e < SC64_ITEMS; ++e) {
+            v[e] = i0 + e < n ? (long long)in[i0 + e] : 0;
+            tot += v[e];
+        }
+        long long inc = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const long long y = __shfl_up_sync(0xffffffffu, inc, o);
@@ -175,9 +182,14 @@ __global__ void __launch_bounds__(1024) k_scan_i32_to_i64(const int32_t* __restr
         }
         __syncthreads();
         const long long c = carry;
-        if (i < n) out[i] = c + wsum[w] + inc - v;
+        long long run = c + wsum[w] + inc - tot;         // exclusive prefix of this thread's first entry
+#pragma unroll
+        for (int e = 0; e < SC64_ITEMS; ++e) {
+            if (i0 + e < n) out[i0 + e] = run;
+            run += v[e];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = c + wsum[w] + inc;
+        if (threadIdx.x == 1023) carry = run;
         __syncthreads();
     }
     if (threadIdx.x == 0) out[n] = carry;
