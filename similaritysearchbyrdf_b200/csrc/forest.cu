@@ -116,8 +116,12 @@ k_init_depth1(const int32_t* __restrict__ cnt1, const int64_t* __restrict__ star
 
 // One CTA per overflowing bucket: stable W-way partition of its ids by the next level's slot, creation of its
 // directory node, and the split decision for every child.  `level` is the level of the children.
-constexpr int SP_THREADS = 256;
+// Two sizes of CTA: a bucket of many thousand ids (clustered data put 100k+ ids under one depth-1 code) is a long chain of
+// rounds for ONE CTA, and the level's time is that chain; buckets above SP_BIG ids go to CTAs of 1024 threads (both kernels
+// are launched over all work items of a level and each CTA takes only the items of its class).
 constexpr int SP_MAXW = 256;
+constexpr int SP_BIG = 8192;
+template <int SP_THREADS>
 __global__ void __launch_bounds__(SP_THREADS)
 k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ keys, int64_t ld, TreeParams tp, int level,
               const int64_t* __restrict__ table_base, int32_t* __restrict__ ids_sorted, int32_t* __restrict__ tmp,
@@ -128,6 +132,7 @@ k_split_level(const WorkItem* __restrict__ work, const int32_t* __restrict__ key
     __shared__ int32_t wcnt[SP_THREADS / 32][SP_MAXW];
     __shared__ int trigger_slot;
     const WorkItem it = work[blockIdx.x];
+    if ((it.cnt > SP_BIG) != (SP_THREADS > 256)) return;
     const int W = tp.W, nb = tp.nb, mask = W - 1;
     const int s = max(it.c0, tp.T) + 1;              // population at the moment of the split
     const int32_t* kt = keys + (int64_t)it.table * ld;
@@ -417,9 +422,12 @@ void build_forest(dpf_index* h) {
         for (int level = tp.MAXL - 1; level >= 0 && nwork > 0; --level) {
             total_splits += nwork;
             DPF_CUDA(cudaMemsetAsync(h->counters.p + 2, 0, sizeof(int32_t), st));
-            k_split_level<<<nwork, SP_THREADS, 0, st>>>(cur, h->keys.p, ld, tp, level, h->table_base.p, h->ids_sorted.p,
+            k_split_level<1024><<<nwork, 1024, 0, st>>>(cur, h->keys.p, ld, tp, level, h->table_base.p, h->ids_sorted.p,
                                                         tmp.p, h->child_ptr.p, h->child_cnt.p, h->counters.p, nxt,
                                                         h->node_cap, stat_dev, h->node_table.p, slot_buf.p); DPF_LAUNCHED();
+            k_split_level<256><<<nwork, 256, 0, st>>>(cur, h->keys.p, ld, tp, level, h->table_base.p, h->ids_sorted.p,
+                                                      tmp.p, h->child_ptr.p, h->child_cnt.p, h->counters.p, nxt,
+                                                      h->node_cap, stat_dev, h->node_table.p, slot_buf.p); DPF_LAUNCHED();
             DPF_CUDA(cudaGetLastError());
             DPF_CUDA(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
             DPF_CUDA(cudaStreamSynchronize(st));
