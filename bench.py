@@ -384,7 +384,8 @@ def run_ours(args):
             ix._ck(fn(ix.h, Qh_np.ctypes.data, nq, None, args.qsteps, B.PROBE_DENSE, K, metric, ids_np.ctypes.data,
                       sc_np.ctypes.data))
 
-        for _ in range(max(1, min(args.warmup, 2))):
+        ix.set_profiling(False)                # (the stage pass above left the per-stage events on: not part of the product call)
+        for _ in range(max(3, args.warmup)):
             step_e2e()
         barrier()
         e0.record(stream)
