@@ -25,6 +25,21 @@ def test_library_exports_every_declared_symbol():
     assert sorted(B.EXPORTS) == declared
 
 
+def test_python_constants_match_the_header_enums():
+    """The ctypes side spells the header's enums by value: debug options, stage timers and store kinds must not drift
+    (a renumbered DPF_DBG_* would silently switch another kernel variant in the tests)."""
+    text = open(os.path.join(ROOT, "include", "dpf.h")).read()
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(DPF_[A-Z0-9_]+)\s*=\s*(\d+)\s*[,}/]", text)}
+    dbg = {k[len("DPF_DBG_"):]: v for k, v in enums.items() if k.startswith("DPF_DBG_") and k != "DPF_DBG_COUNT"}
+    assert len(dbg) >= 14
+    for name, value in dbg.items():
+        assert getattr(B, "DBG_" + name) == value, name
+    assert all(v < enums["DPF_DBG_COUNT"] for v in dbg.values())
+    for name in ("METRIC_DOT", "METRIC_ANGULAR", "METRIC_L2", "STORE_KIND_U8", "STORE_KIND_F32", "PROBE_DENSE"):
+        if "DPF_" + name in enums:
+            assert getattr(B, name) == enums["DPF_" + name], name
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
